@@ -1,0 +1,245 @@
+/*
+ * spt_b200.h — C ABI of libspt_b200.so: the B200 (sm_100a) hot path of the
+ * Superpoint Transformer: superpoint-graph self-attention + segment-wise
+ * scatter/pool aggregation.
+ *
+ * The reference (drprojects/superpoint_transformer @ eb959b6) has NO native code
+ * and therefore no FFI of its own: every entry point below
+ * replaces a *composition of third-party leaf calls* made from the reference's
+ * Python glue.  Each declaration cites the reference call-site it replaces
+ * (paths relative to /root/reference).  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add to bind them.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; every pointer is a DEVICE pointer
+ *     unless stated otherwise; tensors are contiguous row-major.
+ *   - the caller owns every buffer; the library never allocates device memory.
+ *     Where scratch is needed the caller passes `ws` of at least
+ *     `*_workspace_bytes(...)` bytes (256-byte aligned).
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *     no host synchronisation, no internal streams.
+ *   - return value: 0 = ok; negative = invalid argument / unsupported shape
+ *     (SPT_E_*); positive = cudaError_t of the failed launch.  Details via
+ *     spt_last_error() (thread-local, host string).
+ *   - API index tensors are int64 (the reference casts everything to int64 in
+ *     `NAGCast`, configs/datamodule/semantic/default.yaml:208-210); the internal
+ *     CSR arrays are int32 (E, N < 2^31 is checked).
+ */
+#ifndef SPT_B200_H
+#define SPT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPT_ABI_VERSION 1
+
+/* status codes (negative = caller error) */
+#define SPT_OK 0
+#define SPT_E_INVALID -1      /* null pointer / negative size / bad enum      */
+#define SPT_E_UNSUPPORTED -2  /* shape outside what the kernels implement     */
+#define SPT_E_WORKSPACE -3    /* workspace too small                          */
+#define SPT_E_TOO_LARGE -4    /* element count does not fit int32 internals   */
+
+/* reduce ops for segment pooling (src/nn/pool.py:24-82) */
+#define SPT_REDUCE_SUM 0
+#define SPT_REDUCE_MEAN 1
+#define SPT_REDUCE_MAX 2
+#define SPT_REDUCE_MIN 3
+
+/* qk-scale modes (src/utils/nn.py:75-127): D=(dim/num_heads)^-1/2, G=deg(s)^-1/2 */
+#define SPT_SCALE_D_TIMES_G 0 /* default (qk_scale=None) and 'd.g'            */
+#define SPT_SCALE_D_PLUS_G 1  /* 'd+g'                                        */
+#define SPT_SCALE_D 2         /* 'd'                                          */
+#define SPT_SCALE_G 3         /* 'g'                                          */
+#define SPT_SCALE_CONST 4     /* numeric qk_scale used as is                  */
+
+int spt_abi_version(void);
+const char* spt_last_error(void);
+/* compile-time facts, for the loader to verify it got the sm_100a build */
+const char* spt_build_info(void);
+
+/* ------------------------------------------------------------------------- *
+ *  Integer index structure (bit-exact)                                      *
+ * ------------------------------------------------------------------------- */
+
+/* Stable grouping of n items by key (key[i] in [0, num_groups)):
+ *   ptr[num_groups+1] = exclusive scan of bincount(key)
+ *   perm[n]           = stable argsort(key)   (original item id at sorted slot)
+ *   other_sorted[n]   = other[perm]  (optional; e.g. edge targets -> CSR col)
+ * Replaces the atomics-based scatter the reference relies on
+ * (torch_scatter.scatter_sum, src/nn/attention.py:315) by a deterministic CSR,
+ * and is the device version of `indices_to_pointers` (src/utils/sparse.py:23-41)
+ * with a *stable* order. With key=edge_index[0], other=edge_index[1] it is the
+ * COO->CSR build of SURVEY.md §2.2 (1); with key=super_index it reproduces
+ * `Cluster.pointers/points` (src/data/cluster.py:19-77).
+ * Out-of-range keys are skipped and counted in ws[0] (int32 error counter). */
+size_t spt_group_index_workspace_bytes(int64_t n, int64_t num_groups);
+int spt_group_index(const int64_t* key, const int64_t* other /*nullable*/,
+                    int64_t n, int64_t num_groups, int32_t* ptr, int32_t* perm,
+                    int32_t* other_sorted /*nullable*/, void* ws,
+                    size_t ws_bytes, void* stream);
+
+/* inv[perm[j]] = j */
+int spt_invert_permutation(const int32_t* perm, int64_t n, int32_t* inv,
+                           void* stream);
+/* out[j] = src[idx[j]]  (int32 payload, int32 index) */
+int spt_gather_i32(const int32_t* src, const int32_t* idx, int64_t n,
+                   int32_t* out, void* stream);
+
+/* Segment sum of int64 values (values==NULL -> ones), segments given by
+ * ptr/points (points==NULL -> identity).  `NAG.get_sub_size`
+ * (src/data/nag.py:59-110), used by `NodeSize` (src/transforms/graph.py:1475-1498). */
+int spt_segment_sum_i64(const int64_t* values /*nullable*/, const int32_t* ptr,
+                        const int32_t* points /*nullable*/, int64_t num_groups,
+                        int64_t* out, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ *  Row gathers                                                              *
+ * ------------------------------------------------------------------------- */
+
+/* out[i, :] = x[idx[i], :]   (fp32 rows of width C).
+ * `IndexUnpool.forward` (src/nn/unpool.py:12-13) and the q[s]/k[t]/v[t]
+ * expansions of src/nn/attention.py:207-211 when used stand-alone. */
+int spt_gather_rows_i64(const float* x, const int64_t* idx, int64_t n_out,
+                        int64_t C, float* out, void* stream);
+int spt_gather_rows_i32(const float* x, const int32_t* idx, int64_t n_out,
+                        int64_t C, float* out, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ *  Segment pooling  (src/nn/pool.py:44-82 -> PyG *Aggregation -> scatter)    *
+ * ------------------------------------------------------------------------- */
+
+/* out[p, c] = reduce over children i in points[ptr[p]:ptr[p+1]] of x[i, c].
+ * Empty segment -> 0 (torch_scatter / PyG semantics).  For MAX/MIN `arg`
+ * (int32 [Np, C], nullable) receives the child row of the selected element
+ * (first in child order on ties; -1 for empty segments). */
+int spt_segment_pool_fwd(const float* x, const int32_t* ptr,
+                         const int32_t* points /*nullable = identity*/,
+                         int64_t num_parents, int64_t C, int reduce, float* out,
+                         int32_t* arg /*nullable*/, void* stream);
+
+/* dx[i, c] from dout[parent(i), c]; gather-form backward (no atomics):
+ *   SUM : dx = dout[parent]          MEAN: dx = dout[parent] / max(count, 1)
+ *   MAX/MIN: dx = dout[parent] if arg[parent, c] == i else 0               */
+int spt_segment_pool_bwd(const float* dout, const int64_t* parent,
+                         const int32_t* ptr, const int32_t* arg /*nullable*/,
+                         int64_t num_children, int64_t C, int reduce, float* dx,
+                         void* stream);
+
+/* ------------------------------------------------------------------------- *
+ *  UnitSphereNorm (src/nn/norm.py:53-138, scatter_mean_weighted              *
+ *  src/utils/scatter.py:17-38)                                              *
+ * ------------------------------------------------------------------------- */
+
+/* Per parent: bbox min/max -> diameter = max span; w-weighted centroid.
+ * pos_out[i] = (pos[i] - center[parent(i)]) / (diameter[parent(i)] + 1e-2).
+ * parent==NULL (and num_parents==1, ptr={0,N}, points==NULL) is the
+ * `_forward` (no idx) case.  w==NULL -> unweighted mean.  */
+size_t spt_unitsphere_workspace_bytes(int64_t num_parents);
+int spt_unitsphere_fwd(const float* pos, const int64_t* parent /*nullable*/,
+                       const int32_t* ptr, const int32_t* points /*nullable*/,
+                       const float* w /*nullable*/, int64_t N,
+                       int64_t num_parents, float* pos_out,
+                       float* diameter /*[num_parents]*/, void* ws,
+                       size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ *  GraphNorm (torch_geometric.nn.norm.GraphNorm, selected by                *
+ *  configs/model/semantic/_attention.yaml:9-11, called through              *
+ *  src/nn/transformer.py:258-265 and src/nn/mlp.py:89-94)                   *
+ * ------------------------------------------------------------------------- */
+
+/* y = weight * (x - mean_scale*mean[b]) * rstd[b] + bias, per graph b=batch[i].
+ * batch==NULL -> single graph.  batch need not be sorted.  Outputs mean/rstd
+ * [B, C] are saved for backward.  */
+size_t spt_graphnorm_workspace_bytes(int64_t B, int64_t C);
+int spt_graphnorm_fwd(const float* x, const int64_t* batch /*nullable*/,
+                      int64_t N, int64_t C, int64_t B, const float* weight,
+                      const float* bias, const float* mean_scale, float eps,
+                      float* y, float* mean /*[B,C]*/, float* rstd /*[B,C]*/,
+                      void* ws, size_t ws_bytes, void* stream);
+int spt_graphnorm_bwd(const float* x, const float* dy,
+                      const int64_t* batch /*nullable*/, int64_t N, int64_t C,
+                      int64_t B, const float* weight, const float* mean_scale,
+                      const float* mean, const float* rstd, float* dx,
+                      float* dweight /*[C]*/, float* dbias /*[C]*/,
+                      float* dmean_scale /*[C]*/, void* ws, size_t ws_bytes,
+                      void* stream);
+
+/* ------------------------------------------------------------------------- *
+ *  Fused sparse graph attention core                                        *
+ *  (src/nn/attention.py:202-315; src/nn/pool.py:196-233 for attentive pool)  *
+ * ------------------------------------------------------------------------- */
+
+/* Rows (queries) are CSR rows; edge j (CSR slot) has target col[j] and edge
+ * features a[j, :F] (already permuted to CSR order).  For each row s, head h:
+ *   q_e = q[s]*scale(s) + Wq a_e + bq      (Wq, Wk: [H*D, F] row-major)
+ *   k_e = k[t] + Wk a_e + bk
+ *   c   = <q_e, k_e>_h ; p = softmax_row(c)  (denominator + 1e-16, PyG softmax)
+ *   agg_v[s,h,:] = sum_e p * v[t,h,:]         ([N, C])
+ *   abar [s,h,:] = sum_e p * a_e              ([N, H, F])  -> v_rpe applied by
+ *                                              the caller: Wv_h abar + bv*sump
+ *   sump [s,h]   = sum_e p                    (1 unless the row is empty)
+ * Saved for backward: m[s,h] (row max), z[s,h] (sum exp + 1e-16).
+ * q/k/v are given as base pointers + leading dimensions so that the fused
+ * qkv Linear output [N, 2HD+C] (attention.py:191-204) or separate q [Np,HD] /
+ * kv [Nc, HD+C] buffers (pool.py:187-198) can be used without copies.
+ * a, Wq, bq, Wk, bk may each be NULL (no RPE / no bias).                     */
+int spt_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk,
+                 const float* v, int64_t ldv, const float* a /*[E,F]*/,
+                 const int32_t* rowptr, const int32_t* col, int64_t num_rows,
+                 int64_t E, int H, int D, int Dv, int F, const float* Wq,
+                 const float* bq, const float* Wk, const float* bk,
+                 int scale_mode, float scale_value, float* agg_v /*[R,H*Dv]*/,
+                 float* abar /*[R,H,F] nullable*/, float* sump /*[R,H]*/,
+                 float* m /*[R,H]*/, float* z /*[R,H]*/, void* stream);
+
+/* Backward of spt_attn_fwd. Inputs: forward inputs, saved m/z, forward outputs
+ * agg_v/abar, upstream d_agg_v [R,C] and d_abar [R,H,F] (nullable).
+ * Outputs (all fully written, no pre-zeroing needed unless stated):
+ *   dq [R, ldq-strided], dk/dv [num_targets rows], da [E,F] (CSR order),
+ *   dWq,dWk [HD,F], dbq,dbk [HD]  (ACCUMULATED into; caller zero-fills),
+ * Scratch (caller provided): P [E,H], G [E,2HD].
+ * csc_ptr/csc_src/csc2csr: edges grouped by target (stable), giving for every
+ * target t its incoming CSR slots and their source rows.                     */
+int spt_attn_bwd(const float* q, int64_t ldq, const float* k, int64_t ldk,
+                 const float* v, int64_t ldv, const float* a,
+                 const int32_t* rowptr, const int32_t* col,
+                 const int32_t* csc_ptr, const int32_t* csc_src,
+                 const int32_t* csc2csr, int64_t num_rows, int64_t num_targets,
+                 int64_t E, int H, int D, int Dv, int F, const float* Wq,
+                 const float* bq, const float* Wk, const float* bk,
+                 int scale_mode, float scale_value, const float* m,
+                 const float* z, const float* agg_v, const float* abar,
+                 const float* d_agg_v, const float* d_abar /*nullable*/,
+                 float* dq, int64_t lddq, float* dk, int64_t lddk, float* dv,
+                 int64_t lddv, float* da /*nullable*/, float* dWq, float* dbq,
+                 float* dWk, float* dbk, float* P, float* G, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ *  On-the-fly horizontal edge features                                      *
+ *  (src/transforms/graph.py:1137-1277 + NAGAddSelfLoops :1419-1452)          *
+ * ------------------------------------------------------------------------- */
+
+/* From the trimmed graph se [2, Eh] (int64) and its 7-column attributes
+ * ea (fp32 [Eh,7]: mean_off 3, std_off 3, mean_dist 1) builds
+ *   edge_index_out [2, 2*Eh + (self_loops? N:0)]  = [se | flip(se) | loops]
+ *   edge_attr_out  [same, 18] fp32 in the reference column order
+ *     mean_off(3) std_off(3) mean_dist angle_source angle_target normal_angle
+ *     log_length log_surface log_volume log_size centroid_dir(3) centroid_dist
+ *   self-loop rows are zero (add_self_loops fill_value=0).                   */
+int spt_edge_features_fwd(const int64_t* se, const float* ea, const float* pos,
+                          const float* normal, const float* log_length,
+                          const float* log_surface, const float* log_volume,
+                          const float* log_size, int64_t Eh, int64_t N,
+                          int add_self_loops, int64_t* edge_index_out,
+                          float* edge_attr_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPT_B200_H */

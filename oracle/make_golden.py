@@ -1,0 +1,315 @@
+"""Generate tests/golden/*.pt by running the REFERENCE's own source
+(oracle/reference_shim.py) on seeded inputs.  Build-container only:
+
+    python -m oracle.make_golden
+
+Each fixture stores the inputs, the reference parameters (state_dict with the
+reference key names), the reference outputs and input/parameter gradients of
+sum(out * probe) in fp32 — plus the fp64 outputs of the same run as "truth".
+tests/test_oracle_golden.py replays them against oracle/path.py (CPU, anywhere);
+tests/test_gpu_parity.py replays them against the CUDA path.
+"""
+import os
+import sys
+import zlib
+
+import torch
+
+from . import reference_shim as R
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, 'tests', 'golden')
+
+
+def _graph(gen, n, e_half):
+    """symmetric graph in the reference order [i<j | j>i | self-loops]"""
+    i = torch.randint(0, n, (e_half * 2,), generator=gen)
+    j = torch.randint(0, n, (e_half * 2,), generator=gen)
+    lo, hi = torch.minimum(i, j), torch.maximum(i, j)
+    keep = lo != hi
+    uid = torch.unique(lo[keep] * n + hi[keep])[:e_half]
+    se = torch.stack((uid // n, uid % n))
+    loops = torch.arange(n)
+    return torch.cat((se, se.flip(0), torch.stack((loops, loops))), dim=1), se
+
+
+def _run(module, args, kwargs, wrt, probe_gen):
+    """forward + backward of sum(out*probe); returns outputs, grads"""
+    for t in wrt:
+        t.requires_grad_(True)
+    out = module(*args, **kwargs)
+    outs = out if isinstance(out, (tuple, list)) else (out,)
+    first = outs[0]
+    probe = torch.randn(first.shape, generator=probe_gen, dtype=torch.float32).to(first.dtype)
+    (first * probe).sum().backward()
+    grads = [t.grad.detach().clone() if t.grad is not None else None for t in wrt]
+    pgrads = {k: p.grad.detach().clone() for k, p in module.named_parameters()
+              if p.grad is not None} if hasattr(module, 'named_parameters') else {}
+    return [o.detach().clone() if torch.is_tensor(o) else o for o in outs], probe, grads, pgrads
+
+
+def attention_cases(ref):
+    cases = {}
+    specs = {
+        'kqv': dict(k_rpe=True, q_rpe=True, v_rpe=True),
+        'share_minus': dict(k_rpe=True, q_rpe=True, qk_share_rpe=True, q_on_minus_rpe=True,
+                            v_rpe=True),
+        'heads_share': dict(k_rpe=True, q_rpe=True, v_rpe=True, heads_share_rpe=True),
+        'no_rpe': dict(),
+        'k_only_dplusg': dict(k_rpe=True, qk_scale='d+g'),
+        'scale_g': dict(q_rpe=True, v_rpe=True, qk_scale='g'),
+        'scale_const': dict(k_rpe=True, q_rpe=True, qk_scale=0.37),
+    }
+    shapes = {'c32h4': (60, 32, 4, 4, 8), 'c64h16': (48, 64, 16, 4, 32), 'c16h16d2': (40, 16, 16, 2, 16),
+              'c128h4': (64, 128, 4, 4, 32)}
+    for sname, (N, C, H, D, F) in shapes.items():
+        for vname, kw in specs.items():
+            if sname != 'c32h4' and vname not in ('kqv', 'heads_share'):
+                continue
+            gen = torch.Generator().manual_seed(zlib.crc32(f'{sname}/{vname}'.encode()) % 100000)
+            ei, _ = _graph(gen, N, N * 4)
+            E = ei.shape[1]
+            x = torch.randn(N, C, generator=gen)
+            ea = torch.randn(E, F, generator=gen)
+            torch.manual_seed(1234)
+            blk = ref.SelfAttentionBlock(C, num_heads=H, qk_dim=D, in_rpe_dim=F, out_dim=C, **kw)
+            blk.apply(ref.init_weights)
+            for p in blk.parameters():  # non-zero biases so they are exercised
+                if p.dim() == 1:
+                    p.data.normal_(0, 0.1, generator=gen)
+            xin, ein = x.clone(), ea.clone()
+            outs, probe, grads, pgrads = _run(blk, (xin, ei, ein), {}, [xin, ein],
+                                              torch.Generator().manual_seed(7))
+            blk64 = ref.SelfAttentionBlock(C, num_heads=H, qk_dim=D, in_rpe_dim=F, out_dim=C,
+                                           **kw).double()
+            blk64.load_state_dict({k: v.double() for k, v in blk.state_dict().items()})
+            with torch.no_grad():
+                out64 = blk64(x.double(), ei, ea.double())
+            cases[f'{sname}_{vname}'] = dict(
+                cfg=dict(dim=C, num_heads=H, qk_dim=D, in_rpe_dim=F, **kw),
+                sd={k: v.detach().clone() for k, v in blk.state_dict().items()},
+                x=x, edge_index=ei, edge_attr=ea, out=outs[0], out64=out64, probe=probe,
+                dx=grads[0], dedge_attr=grads[1], dparams=pgrads)
+    return cases
+
+
+def segment_cases(ref):
+    cases = {}
+    gen = torch.Generator().manual_seed(11)
+    Nc, Np, C = 300, 40, 32
+    idx = torch.randint(0, Np - 3, (Nc,), generator=gen)  # 3 empty parents at the end
+    x = torch.randn(Nc, C, generator=gen)
+    for name, cls in (('max', ref.MaxPool), ('min', ref.MinPool), ('mean', ref.MeanPool),
+                      ('sum', ref.SumPool)):
+        xin = x.clone()
+        outs, probe, grads, _ = _run(cls(), (xin, None, idx), dict(num_pool=Np), [xin],
+                                     torch.Generator().manual_seed(3))
+        cases[f'pool_{name}'] = dict(x=x, index=idx, num_pool=Np, out=outs[0], probe=probe,
+                                     dx=grads[0])
+    # unpool
+    xp = torch.randn(Np, C, generator=gen)
+    xin = xp.clone()
+    outs, probe, grads, _ = _run(ref.IndexUnpool(), (xin, idx), {}, [xin],
+                                 torch.Generator().manual_seed(4))
+    cases['unpool'] = dict(x=xp, index=idx, out=outs[0], probe=probe, dx=grads[0])
+    # unit sphere norm
+    pos = torch.rand(Nc, 3, generator=gen) * 50
+    w = torch.randint(1, 60, (Nc,), generator=gen)
+    usn = ref.UnitSphereNorm()
+    p1, d1 = usn(pos, idx, w=w, num_super=Np)
+    p2, d2 = usn(pos, idx, w=None, num_super=Np)
+    p3, d3 = usn(pos, None, w=w)
+    cases['unit_sphere'] = dict(pos=pos, index=idx, w=w, num_super=Np, pos_w=p1, diam_w=d1,
+                                pos_nw=p2, diam_nw=d2, pos_none=p3, diam_none=d3)
+    # GraphNorm (leaf restatement run through the reference MLP glue)
+    B = 3
+    batch = torch.sort(torch.randint(0, B, (Nc,), generator=gen)).values
+    torch.manual_seed(5)
+    m = ref.MLP([C, 48, 24], norm=ref.GraphNorm)
+    for p in m.parameters():
+        if p.dim() == 1:
+            p.data.normal_(1.0, 0.2, generator=gen)
+    xin = x.clone()
+    outs, probe, grads, pgrads = _run(m, (xin,), dict(batch=batch), [xin],
+                                      torch.Generator().manual_seed(6))
+    cases['mlp_graphnorm'] = dict(x=x, batch=batch, dims=[C, 48, 24],
+                                  sd={k: v.detach().clone() for k, v in m.state_dict().items()},
+                                  out=outs[0], probe=probe, dx=grads[0], dparams=pgrads)
+    # same with an UNSORTED batch vector (edge-level norm index case)
+    ub = batch[torch.randperm(Nc, generator=gen)]
+    m.zero_grad()
+    xin = x.clone()
+    outs, probe, grads, pgrads = _run(m, (xin,), dict(batch=ub), [xin],
+                                      torch.Generator().manual_seed(6))
+    cases['mlp_graphnorm_unsorted'] = dict(
+        x=x, batch=ub, dims=[C, 48, 24],
+        sd={k: v.detach().clone() for k, v in m.state_dict().items()}, out=outs[0],
+        probe=probe, dx=grads[0], dparams=pgrads)
+    return cases
+
+
+SPT_CFG = dict(
+    nano=True, segment_hf=['hf'], down_dim=[32, 32, 32],
+    down_in_mlp=[[3 + 1 + 16, 32, 32], [3 + 1 + 16 + 32, 32, 32], [3 + 1 + 16 + 32, 32, 32]],
+    down_num_heads=4, down_num_blocks=2, down_ffn_ratio=1, up_dim=[32, 32],
+    up_in_mlp=[[20 + 32 + 32, 32, 32], [20 + 32 + 32, 32, 32]], up_num_heads=4,
+    up_num_blocks=1, node_mlp=[12, 16, 16], h_edge_mlp=[18, 16, 16], qk_dim=4,
+    in_rpe_dim=16, k_rpe=True, q_rpe=True, v_rpe=True, no_ffn=True,
+    use_diameter_parent=True, pool='max')
+
+
+def _prep_nag(levels, seed):
+    """synthetic NAG -> after the on-device transforms, via the REFERENCE functions"""
+    from superpoint_transformer_b200.synthetic import make_nag
+    ref = R.load()
+    nag = make_nag(levels, mean_degree=8, seed=seed)
+    raw = {l: (nag[l].edge_index.clone(), nag[l].edge_attr.clone()) for l in nag.level_range}
+    for l in nag.level_range:
+        nag._list[l - nag.start_i_level] = ref.on_the_fly_horizontal_edge_features(nag[l])
+    nag = ref.NAGAddSelfLoops()(nag)
+    # node_size by the reference's rule (NAG.get_sub_size, src/data/nag.py:94-110)
+    size = nag[1].node_size
+    for l in range(2, nag.absolute_num_levels):
+        size = torch.zeros(nag[l].num_nodes, dtype=torch.long).index_add_(
+            0, nag[l - 1].super_index, size)
+        nag[l].node_size = size
+    return nag, raw
+
+
+def spt_case(ref):
+    nag, raw = _prep_nag([240, 48, 10], seed=5)
+    torch.manual_seed(99)
+    net = ref.SPT(mlp_norm=ref.GraphNorm, norm=ref.GraphNorm, **SPT_CFG)
+    net.apply(ref.init_weights)
+    gen = torch.Generator().manual_seed(8)
+    for p in net.parameters():
+        if p.dim() == 1:
+            p.data.add_(torch.randn(p.shape, generator=gen) * 0.1)
+    run = nag.clone()
+    out = net(run)
+    probe = torch.randn(out.shape, generator=torch.Generator().manual_seed(9))
+    (out * probe).sum().backward()
+    pgrads = {k: p.grad.detach().clone() for k, p in net.named_parameters()
+              if p.grad is not None}
+    net64 = ref.SPT(mlp_norm=ref.GraphNorm, norm=ref.GraphNorm, **SPT_CFG).double()
+    net64.load_state_dict({k: v.double() for k, v in net.state_dict().items()})
+    run64 = nag.clone()
+    for d in run64:
+        for k in d.keys:
+            v = d[k]
+            if torch.is_tensor(v) and v.is_floating_point():
+                d[k] = v.double()
+    with torch.no_grad():
+        out64 = net64(run64)
+    levels = {}
+    for l in nag.level_range:
+        d = nag[l]
+        levels[l] = {k: d[k] for k in d.keys if torch.is_tensor(d[k])}
+        if d.sub is not None:
+            levels[l]['sub_pointers'] = d.sub.pointers
+            levels[l]['sub_points'] = d.sub.points
+        levels[l]['raw_edge_index'], levels[l]['raw_edge_attr'] = raw[l]
+    return dict(cfg=SPT_CFG, sd={k: v.detach().clone() for k, v in net.state_dict().items()},
+                levels=levels, start_i_level=nag.start_i_level, out=out.detach(),
+                out64=out64, probe=probe, dparams=pgrads)
+
+
+def stage_cases(ref):
+    """DownNFuseStage / UpNFuseStage with 'mean' pooling + FFN + post-norm variants"""
+    nag, _ = _prep_nag([200, 40], seed=12)
+    cases = {}
+    gen = torch.Generator().manual_seed(21)
+    C = 32
+    d1, d2 = nag[1], nag[2]
+    x_child = torch.randn(d1.num_nodes, C, generator=gen)
+    x_parent = torch.randn(d2.num_nodes, 12, generator=gen)
+    ni2 = torch.zeros(d2.num_nodes, dtype=torch.long)
+    ni1 = torch.zeros(d1.num_nodes, dtype=torch.long)
+    for name, kw in (('down_mean_ffn', dict(pool='mean', no_ffn=False, ffn_ratio=2)),
+                     ('down_max_postnorm', dict(pool='max', no_ffn=False, ffn_ratio=1,
+                                                pre_norm=False))):
+        torch.manual_seed(31)
+        st = ref.DownNFuseStage(
+            C, num_blocks=2, num_heads=4, in_mlp=[3 + 1 + 12 + C, C, C], mlp_norm=ref.GraphNorm,
+            norm=ref.GraphNorm, qk_dim=4, in_rpe_dim=18, k_rpe=True, q_rpe=True, v_rpe=True,
+            use_diameter_parent=True, version_holder=ref.VersionHolder('3.0.0'), **kw)
+        st.apply(ref.init_weights)
+        xc = x_child.clone()
+        ea = d2.edge_attr.clone()
+        outs, probe, grads, pgrads = _run(
+            st, (x_parent, xc, ni2, d1.super_index),
+            dict(pos=d2.pos, node_size=d2.node_size, super_index=None,
+                 edge_index=d2.edge_index, edge_attr=ea, num_super=d2.num_nodes),
+            [xc, ea], torch.Generator().manual_seed(41))
+        cases[name] = dict(
+            cfg=dict(dim=C, num_heads=4, qk_dim=4, pool=kw['pool'],
+                     pre_norm=kw.get('pre_norm', True)),
+            sd={k: v.detach().clone() for k, v in st.state_dict().items()},
+            x_parent=x_parent, x_child=x_child, norm_index=ni2, pool_index=d1.super_index,
+            pos=d2.pos, node_size=d2.node_size, edge_index=d2.edge_index,
+            edge_attr=d2.edge_attr, num_super=d2.num_nodes, out=outs[0], diam=outs[1],
+            probe=probe, dx_child=grads[0], dedge_attr=grads[1], dparams=pgrads)
+    # up stage
+    torch.manual_seed(32)
+    st = ref.UpNFuseStage(
+        C, num_blocks=1, num_heads=4, in_mlp=[3 + 1 + C + C, C, C], mlp_norm=ref.GraphNorm,
+        norm=ref.GraphNorm, qk_dim=4, in_rpe_dim=18, k_rpe=True, q_rpe=True, v_rpe=True,
+        use_diameter_parent=True, no_ffn=True, version_holder=ref.VersionHolder('3.0.0'))
+    st.apply(ref.init_weights)
+    xp = torch.randn(d2.num_nodes, C, generator=gen)
+    xc = x_child.clone()
+    xpp = xp.clone()
+    outs, probe, grads, pgrads = _run(
+        st, (xc, xpp, ni1, d1.super_index),
+        dict(pos=d1.pos, node_size=d1.node_size, super_index=d1.super_index,
+             edge_index=d1.edge_index, edge_attr=d1.edge_attr),
+        [xc, xpp], torch.Generator().manual_seed(42))
+    cases['up'] = dict(
+        cfg=dict(dim=C, num_heads=4, qk_dim=4),
+        sd={k: v.detach().clone() for k, v in st.state_dict().items()},
+        x_child=x_child, x_parent=xp, norm_index=ni1, unpool_index=d1.super_index, pos=d1.pos,
+        node_size=d1.node_size, super_index=d1.super_index, edge_index=d1.edge_index,
+        edge_attr=d1.edge_attr, out=outs[0], probe=probe, dx_child=grads[0],
+        dx_parent=grads[1], dparams=pgrads)
+    return cases
+
+
+def edge_feature_case(ref):
+    from superpoint_transformer_b200.synthetic import make_nag
+    nag = make_nag([300, 50], mean_degree=8, seed=77)
+    d = nag[1]
+    # degenerate rows: zero mean offset (0/0 -> NaN -> 0) and coincident centroids
+    d.edge_attr[0, :3] = 0
+    j = int(d.edge_index[1, 1])
+    d.pos[j] = d.pos[int(d.edge_index[0, 1])]
+    raw = dict(edge_index=d.edge_index.clone(), edge_attr=d.edge_attr.clone(), pos=d.pos.clone(),
+               normal=d.normal.clone(), log_length=d.log_length.clone(),
+               log_surface=d.log_surface.clone(), log_volume=d.log_volume.clone(),
+               log_size=d.log_size.clone(), num_nodes=d.num_nodes)
+    out = ref.on_the_fly_horizontal_edge_features(d.clone())
+    ei2, ea2 = out.edge_index, out.edge_attr
+    one = type(nag)([out], 1)
+    one = ref.NAGAddSelfLoops()(one)
+    raw.update(sym_edge_index=ei2, sym_edge_attr=ea2, loop_edge_index=one[1].edge_index,
+               loop_edge_attr=one[1].edge_attr)
+    return raw
+
+
+def main():
+    if not R.available():
+        print('reference sources not available; cannot regenerate golden vectors')
+        return 1
+    ref = R.load()
+    os.makedirs(OUT, exist_ok=True)
+    torch.save(attention_cases(ref), os.path.join(OUT, 'attention.pt'))
+    torch.save(segment_cases(ref), os.path.join(OUT, 'segment.pt'))
+    torch.save(stage_cases(ref), os.path.join(OUT, 'stage.pt'))
+    torch.save(spt_case(ref), os.path.join(OUT, 'spt_nano3.pt'))
+    torch.save(edge_feature_case(ref), os.path.join(OUT, 'edge_features.pt'))
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

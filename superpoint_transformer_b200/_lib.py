@@ -1,0 +1,111 @@
+"""ctypes binding of libspt_b200.so (C ABI declared in include/spt_b200.h).
+
+There is NO CPU or eager-PyTorch fallback: if the CUDA library cannot be loaded
+the import of any op fails loudly (RuntimeError), and every op refuses non-CUDA
+tensors.  The library is built in-tree by `csrc/build.py` (nvcc, sm_100a).
+"""
+import ctypes
+import os
+import threading
+
+from .csrc import build as _build
+
+c_i64 = ctypes.c_int64
+c_int = ctypes.c_int
+c_f32 = ctypes.c_float
+c_ptr = ctypes.c_void_p
+c_size = ctypes.c_size_t
+
+_LOCK = threading.Lock()
+_LIB = None
+
+# name -> (restype, argtypes); mirrors include/spt_b200.h one to one
+SIGNATURES = {
+    "spt_abi_version": (c_int, []),
+    "spt_last_error": (ctypes.c_char_p, []),
+    "spt_build_info": (ctypes.c_char_p, []),
+    "spt_group_index_workspace_bytes": (c_size, [c_i64, c_i64]),
+    "spt_group_index": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr,
+                                c_ptr, c_size, c_ptr]),
+    "spt_invert_permutation": (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
+    "spt_gather_i32": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
+    "spt_segment_sum_i64": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
+    "spt_gather_rows_i64": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
+    "spt_gather_rows_i32": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
+    "spt_segment_pool_fwd": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int, c_ptr,
+                                     c_ptr, c_ptr]),
+    "spt_segment_pool_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int,
+                                     c_ptr, c_ptr]),
+    "spt_unitsphere_workspace_bytes": (c_size, [c_i64]),
+    "spt_unitsphere_fwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64,
+                                   c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
+    "spt_graphnorm_workspace_bytes": (c_size, [c_i64, c_i64]),
+    "spt_graphnorm_fwd": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr,
+                                  c_ptr, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_size,
+                                  c_ptr]),
+    "spt_graphnorm_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr,
+                                  c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                  c_ptr, c_size, c_ptr]),
+    "spt_attn_fwd": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr,
+                             c_ptr, c_i64, c_i64, c_int, c_int, c_int, c_int, c_ptr,
+                             c_ptr, c_ptr, c_ptr, c_int, c_f32, c_ptr, c_ptr, c_ptr,
+                             c_ptr, c_ptr, c_ptr]),
+    "spt_attn_bwd": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr,  # q k v a
+                             c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,               # csr, csc
+                             c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int,  # sizes
+                             c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_f32,         # W, scale
+                             c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,         # m z agg abar dagg dabar
+                             c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64,         # dq dk dv
+                             c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,               # da dWq dbq dWk dbk
+                             c_ptr, c_ptr, c_ptr]),                            # P G stream
+    "spt_edge_features_fwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                      c_ptr, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr]),
+}
+
+
+def library_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (building first if the in-tree .so is missing or stale and nvcc is
+    available).  Raises RuntimeError — never falls back to a CPU path."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    with _LOCK:
+        if _LIB is not None:
+            return _LIB
+        path = _build.LIB_PATH
+        if not os.path.exists(path):
+            try:
+                _build.build()
+            except Exception as e:  # noqa: BLE001
+                raise RuntimeError(
+                    f"superpoint_transformer_b200: {path} is missing and could not be "
+                    f"built ({e}). The CUDA library is required; there is no fallback."
+                ) from e
+        try:
+            lib = ctypes.CDLL(path)
+        except OSError as e:
+            raise RuntimeError(
+                f"superpoint_transformer_b200: cannot load {path}: {e}") from e
+        for name, (res, args) in SIGNATURES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError as e:
+                raise RuntimeError(
+                    f"superpoint_transformer_b200: {path} does not export {name}") from e
+            fn.restype = res
+            fn.argtypes = args
+        if lib.spt_abi_version() != 1:
+            raise RuntimeError("superpoint_transformer_b200: ABI version mismatch")
+        _LIB = lib
+    return _LIB
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().spt_last_error()
+        msg = msg.decode() if msg else ""
+        raise RuntimeError(f"libspt_b200 {what} failed (status {rc}): {msg}")

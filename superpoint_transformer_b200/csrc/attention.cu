@@ -1,0 +1,553 @@
+// attention.cu — fused sparse graph attention core, shape-generic path.
+//
+// Replaces the ~20-launch composition of src/nn/attention.py:202-315
+// (3x index_select, 3 per-edge RPE Linears, einsum, 4-kernel PyG softmax,
+// atomicAdd scatter_sum) by ONE CSR pass per direction:
+//   forward : warp per query row, online softmax over its edges, K/V rows
+//             gathered straight from the qkv buffer (L2-resident), edge features
+//             streamed once; no [E, .] intermediate is materialised.
+//   backward: B1 (CSR rows)  recomputes p from the saved (m, z), produces dq
+//             row-locally, da per edge, and per-edge g=[dq_e|dk_e] + p scratch;
+//             B2 (CSC rows)  gathers dk/dv per target without atomics;
+//             B3             reduces dW = g^T a over edge slabs.
+// v-RPE is applied algebraically by the caller: since sum_e p_e (Wv a_e + bv) =
+// Wv (sum_e p_e a_e) + bv sum_e p_e, the kernel only emits abar = sum_e p_e a_e
+// ([N,H,F]) and the per-edge [E,C] v_rpe tensor of attention.py:294-301 is never
+// formed (E*C*F MACs -> N*C*F).
+//
+// This file is the runtime-generic path (any C<=256, H<=32, H*D<=256, F<=128,
+// H*F<=512).  Shapes outside raise SPT_E_UNSUPPORTED.
+#include "common.cuh"
+
+namespace spt {
+
+constexpr int kAttnWarps = 4;
+constexpr int kVPL = 8;   // channels per lane  (C   <= 256)
+constexpr int kAPL = 16;  // abar entries/lane  (H*F <= 512)
+constexpr int kOPL = 8;   // q/k dims per lane  (H*D <= 256)
+
+struct AttnShape {
+  int H, D, Dv, F, C, HD, HD2, HF;
+};
+
+__device__ __forceinline__ float qk_scale(int mode, float value, int deg) {
+  // src/utils/nn.py:75-127; `value` = (dim // num_heads)^-0.5 or the constant
+  float g = rsqrtf((float)max(deg, 1));
+  switch (mode) {
+    case SPT_SCALE_D_TIMES_G: return value * g;
+    case SPT_SCALE_D_PLUS_G: return value + g;
+    case SPT_SCALE_D: return value;
+    case SPT_SCALE_G: return g;
+    default: return value;
+  }
+}
+
+// shared-memory carve-up (floats):
+//   Wt[F][HD2+1] | bqk[HD2] | per warp: a_s[F4] r_s[HD2] qs_s[HD] p_s[32] sc_s[32]
+//   (+ backward extras)
+__host__ __device__ inline int round4(int x) { return (x + 3) & ~3; }
+
+struct FwdParams {
+  const float* q; int64_t ldq;
+  const float* k; int64_t ldk;
+  const float* v; int64_t ldv;
+  const float* a;
+  const int32_t* rowptr; const int32_t* col;
+  int64_t num_rows;
+  AttnShape s;
+  const float* Wq; const float* bq; const float* Wk; const float* bk;
+  int scale_mode; float scale_value;
+  float* agg_v; float* abar; float* sump; float* m; float* z;
+};
+
+__device__ __forceinline__ void load_weights_smem(float* Wt, float* bqk, const AttnShape& s,
+                                                  const float* Wq, const float* bq,
+                                                  const float* Wk, const float* bk) {
+  int ldw = s.HD2 + 1;
+  for (int i = threadIdx.x; i < s.F * s.HD2; i += blockDim.x) {
+    int f = i / s.HD2, o = i - f * s.HD2;
+    float w = 0.f;
+    if (o < s.HD) {
+      if (Wq) w = Wq[o * s.F + f];
+    } else {
+      if (Wk) w = Wk[(o - s.HD) * s.F + f];
+    }
+    Wt[f * ldw + o] = w;
+  }
+  for (int o = threadIdx.x; o < s.HD2; o += blockDim.x) {
+    float b = 0.f;
+    if (o < s.HD) {
+      if (bq && Wq) b = bq[o];
+    } else {
+      if (bk && Wk) b = bk[o - s.HD];
+    }
+    bqk[o] = b;
+  }
+}
+
+__global__ void __launch_bounds__(kAttnWarps * kWarp)
+k_attn_fwd_generic(FwdParams P) {
+  extern __shared__ float smem[];
+  const AttnShape s = P.s;
+  const int ldw = s.HD2 + 1;
+  const int F4 = round4(max(s.F, 1));
+  float* Wt = smem;
+  float* bqk = Wt + s.F * ldw;
+  float* warp_base = bqk + s.HD2;
+  const int per_warp = F4 + s.HD2 + s.HD + 32 + 32 + 32;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* a_s = warp_base + w * per_warp;
+  float* r_s = a_s + F4;
+  float* qs_s = r_s + s.HD2;
+  float* p_s = qs_s + s.HD;
+  float* sc_s = p_s + 32;
+  float* inv_s = sc_s + 32;
+
+  load_weights_smem(Wt, bqk, s, P.Wq, P.bq, P.Wk, P.bk);
+  __syncthreads();
+
+  const bool has_a = (P.a != nullptr) && s.F > 0;
+  int64_t row = (int64_t)blockIdx.x * kAttnWarps + w;
+  if (row >= P.num_rows) return;
+  const int b = P.rowptr[row], e = P.rowptr[row + 1];
+  const float scale = qk_scale(P.scale_mode, P.scale_value, e - b);
+
+  for (int o = lane; o < s.HD; o += 32) qs_s[o] = P.q[row * P.ldq + o] * scale;
+  float m_run = -INFINITY, l_run = 0.f;  // lanes < H
+  float acc_v[kVPL], acc_a[kAPL];
+#pragma unroll
+  for (int i = 0; i < kVPL; ++i) acc_v[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < kAPL; ++i) acc_a[i] = 0.f;
+  __syncwarp();
+
+  for (int j = b; j < e; ++j) {
+    const int64_t t = P.col[j];
+    if (has_a) {
+      for (int f = lane; f < s.F; f += 32) a_s[f] = ldg_stream(P.a + (int64_t)j * s.F + f);
+    }
+    __syncwarp();
+    for (int o = lane; o < s.HD2; o += 32) {
+      float acc = bqk[o];
+      if (has_a) {
+        for (int f = 0; f < s.F; ++f) acc = fmaf(Wt[f * ldw + o], a_s[f], acc);
+      }
+      float base = (o < s.HD) ? qs_s[o] : P.k[t * P.ldk + (o - s.HD)];
+      r_s[o] = base + acc;
+    }
+    __syncwarp();
+    if (lane < s.H) {
+      float c = 0.f;
+      for (int d = 0; d < s.D; ++d) c = fmaf(r_s[lane * s.D + d], r_s[s.HD + lane * s.D + d], c);
+      float m_new = fmaxf(m_run, c);
+      float p = expf(c - m_new);
+      float alpha = (m_run == -INFINITY) ? 0.f : expf(m_run - m_new);
+      l_run = fmaf(l_run, alpha, p);
+      m_run = m_new;
+      p_s[lane] = p;
+      sc_s[lane] = alpha;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < kVPL; ++i) {
+      int ch = lane + 32 * i;
+      if (ch < s.C) {
+        int h = ch / s.Dv;
+        acc_v[i] = fmaf(acc_v[i], sc_s[h], p_s[h] * P.v[t * P.ldv + ch]);
+      }
+    }
+    if (has_a && P.abar) {
+#pragma unroll
+      for (int i = 0; i < kAPL; ++i) {
+        int idx = lane + 32 * i;
+        if (idx < s.HF) {
+          int h = idx / s.F, f = idx - h * s.F;
+          acc_a[i] = fmaf(acc_a[i], sc_s[h], p_s[h] * a_s[f]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  if (lane < s.H) {
+    float zden = l_run + 1e-16f;  // PyG softmax: + 1e-16 after the sum
+    float inv = 1.f / zden;
+    inv_s[lane] = inv;
+    P.m[row * s.H + lane] = (e > b) ? m_run : 0.f;
+    P.z[row * s.H + lane] = zden;
+    P.sump[row * s.H + lane] = l_run * inv;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < kVPL; ++i) {
+    int ch = lane + 32 * i;
+    if (ch < s.C) P.agg_v[row * s.C + ch] = acc_v[i] * inv_s[ch / s.Dv];
+  }
+  if (P.abar) {
+#pragma unroll
+    for (int i = 0; i < kAPL; ++i) {
+      int idx = lane + 32 * i;
+      if (idx < s.HF) P.abar[row * s.HF + idx] = acc_a[i] * inv_s[idx / s.F];
+    }
+  }
+}
+
+// ---------------------------------------------------------------- backward B1
+struct BwdParams {
+  const float* q; int64_t ldq;
+  const float* k; int64_t ldk;
+  const float* v; int64_t ldv;
+  const float* a;
+  const int32_t* rowptr; const int32_t* col;
+  int64_t num_rows;
+  AttnShape s;
+  const float* Wq; const float* bq; const float* Wk; const float* bk;
+  int scale_mode; float scale_value;
+  const float* m; const float* z;
+  const float* agg_v; const float* abar;
+  const float* d_agg_v; const float* d_abar;
+  float* dq; int64_t lddq;
+  float* da;
+  float* Pbuf; float* G;
+};
+
+__global__ void __launch_bounds__(kAttnWarps * kWarp)
+k_attn_bwd_rows_generic(BwdParams P) {
+  extern __shared__ float smem[];
+  const AttnShape s = P.s;
+  const int ldw = s.HD2 + 1;
+  const int F4 = round4(max(s.F, 1));
+  float* Wt = smem;
+  float* bqk = Wt + s.F * ldw;
+  float* warp_base = bqk + s.HD2;
+  // a_s[F4] r_s[HD2] g_s[HD2] qs_s[HD] p_s dc_s delta_s m_s zinv_s (5*32) dy_s[C] dab_s[HF]
+  const int per_warp = F4 + 2 * s.HD2 + s.HD + 5 * 32 + round4(s.C) + round4(max(s.HF, 1));
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* a_s = warp_base + w * per_warp;
+  float* r_s = a_s + F4;
+  float* g_s = r_s + s.HD2;
+  float* qs_s = g_s + s.HD2;
+  float* p_s = qs_s + s.HD;
+  float* dc_s = p_s + 32;
+  float* delta_s = dc_s + 32;
+  float* m_s = delta_s + 32;
+  float* zinv_s = m_s + 32;
+  float* dy_s = zinv_s + 32;
+  float* dab_s = dy_s + round4(s.C);
+
+  load_weights_smem(Wt, bqk, s, P.Wq, P.bq, P.Wk, P.bk);
+  __syncthreads();
+
+  const bool has_a = (P.a != nullptr) && s.F > 0;
+  const bool has_dab = has_a && (P.d_abar != nullptr) && (P.abar != nullptr);
+  int64_t row = (int64_t)blockIdx.x * kAttnWarps + w;
+  if (row >= P.num_rows) return;
+  const int b = P.rowptr[row], e = P.rowptr[row + 1];
+  const float scale = qk_scale(P.scale_mode, P.scale_value, e - b);
+
+  for (int o = lane; o < s.HD; o += 32) qs_s[o] = P.q[row * P.ldq + o] * scale;
+  for (int c = lane; c < s.C; c += 32) dy_s[c] = P.d_agg_v[row * s.C + c];
+  if (has_dab)
+    for (int i = lane; i < s.HF; i += 32) dab_s[i] = P.d_abar[row * s.HF + i];
+  if (lane < s.H) {
+    m_s[lane] = P.m[row * s.H + lane];
+    zinv_s[lane] = 1.f / P.z[row * s.H + lane];
+  }
+  __syncwarp();
+  // delta[h] = <dY_h, agg_v_h> + <dAbar_h, abar_h>   (= sum_e p_e dp_e)
+  for (int h = 0; h < s.H; ++h) {
+    float part = 0.f;
+    for (int d = lane; d < s.Dv; d += 32)
+      part = fmaf(dy_s[h * s.Dv + d], P.agg_v[row * s.C + h * s.Dv + d], part);
+    if (has_dab)
+      for (int f = lane; f < s.F; f += 32)
+        part = fmaf(dab_s[h * s.F + f], P.abar[row * s.HF + h * s.F + f], part);
+    part = warp_sum(part);
+    if (lane == 0) delta_s[h] = part;
+  }
+  float dq_acc[kOPL];
+#pragma unroll
+  for (int i = 0; i < kOPL; ++i) dq_acc[i] = 0.f;
+  __syncwarp();
+
+  for (int j = b; j < e; ++j) {
+    const int64_t t = P.col[j];
+    if (has_a)
+      for (int f = lane; f < s.F; f += 32) a_s[f] = ldg_stream(P.a + (int64_t)j * s.F + f);
+    __syncwarp();
+    for (int o = lane; o < s.HD2; o += 32) {
+      float acc = bqk[o];
+      if (has_a)
+        for (int f = 0; f < s.F; ++f) acc = fmaf(Wt[f * ldw + o], a_s[f], acc);
+      float base = (o < s.HD) ? qs_s[o] : P.k[t * P.ldk + (o - s.HD)];
+      r_s[o] = base + acc;
+    }
+    __syncwarp();
+    if (lane < s.H) {
+      float c = 0.f;
+      for (int d = 0; d < s.D; ++d) c = fmaf(r_s[lane * s.D + d], r_s[s.HD + lane * s.D + d], c);
+      float p = expf(c - m_s[lane]) * zinv_s[lane];
+      p_s[lane] = p;
+      P.Pbuf[(int64_t)j * s.H + lane] = p;
+    }
+    __syncwarp();
+    for (int h = 0; h < s.H; ++h) {
+      float part = 0.f;
+      for (int d = lane; d < s.Dv; d += 32)
+        part = fmaf(dy_s[h * s.Dv + d], P.v[t * P.ldv + h * s.Dv + d], part);
+      if (has_dab)
+        for (int f = lane; f < s.F; f += 32) part = fmaf(dab_s[h * s.F + f], a_s[f], part);
+      part = warp_sum(part);
+      if (lane == 0) dc_s[h] = p_s[h] * (part - delta_s[h]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 2 * kOPL; ++i) {
+      int o = lane + 32 * i;
+      if (o < s.HD2) {
+        int oo = (o < s.HD) ? o : o - s.HD;
+        int h = oo / s.D;
+        // dq_e = dc * k_e ; dk_e = dc * q_e
+        float g = dc_s[h] * ((o < s.HD) ? r_s[s.HD + oo] : r_s[oo]);
+        g_s[o] = g;
+        P.G[(int64_t)j * s.HD2 + o] = g;
+        if (o < s.HD) dq_acc[i % kOPL] += g;
+      }
+    }
+    __syncwarp();
+    if (has_a && P.da) {
+      for (int f = lane; f < s.F; f += 32) {
+        float acc = 0.f;
+        if (has_dab)
+          for (int h = 0; h < s.H; ++h) acc = fmaf(p_s[h], dab_s[h * s.F + f], acc);
+        for (int o = 0; o < s.HD2; ++o) acc = fmaf(Wt[f * ldw + o], g_s[o], acc);
+        P.da[(int64_t)j * s.F + f] = acc;
+      }
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int i = 0; i < kOPL; ++i) {
+    int o = lane + 32 * i;
+    if (o < s.HD) P.dq[row * P.lddq + o] = dq_acc[i] * scale;
+  }
+}
+
+// ---------------------------------------------------------------- backward B2
+// warp per target: dv[t] = sum_in p * dY[src] ; dk[t] = sum_in dk_e
+__global__ void __launch_bounds__(kAttnWarps * kWarp)
+k_attn_bwd_targets_generic(const int32_t* __restrict__ csc_ptr,
+                           const int32_t* __restrict__ csc_src,
+                           const int32_t* __restrict__ csc2csr, int64_t num_targets,
+                           AttnShape s, const float* __restrict__ Pbuf,
+                           const float* __restrict__ G, const float* __restrict__ d_agg_v,
+                           float* __restrict__ dk, int64_t lddk, float* __restrict__ dv,
+                           int64_t lddv) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int64_t t = (int64_t)blockIdx.x * kAttnWarps + w;
+  if (t >= num_targets) return;
+  float dv_acc[kVPL], dk_acc[kOPL];
+#pragma unroll
+  for (int i = 0; i < kVPL; ++i) dv_acc[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < kOPL; ++i) dk_acc[i] = 0.f;
+  const int b = csc_ptr[t], e = csc_ptr[t + 1];
+  for (int jt = b; jt < e; ++jt) {
+    const int64_t j = csc2csr[jt];
+    const int64_t src = csc_src[jt];
+#pragma unroll
+    for (int i = 0; i < kVPL; ++i) {
+      int ch = lane + 32 * i;
+      if (ch < s.C)
+        dv_acc[i] = fmaf(Pbuf[j * s.H + ch / s.Dv], d_agg_v[src * s.C + ch], dv_acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < kOPL; ++i) {
+      int o = lane + 32 * i;
+      if (o < s.HD) dk_acc[i] += G[j * s.HD2 + s.HD + o];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kVPL; ++i) {
+    int ch = lane + 32 * i;
+    if (ch < s.C) dv[t * lddv + ch] = dv_acc[i];
+  }
+#pragma unroll
+  for (int i = 0; i < kOPL; ++i) {
+    int o = lane + 32 * i;
+    if (o < s.HD) dk[t * lddk + o] = dk_acc[i];
+  }
+}
+
+// ---------------------------------------------------------------- backward B3
+// dWqk[o, f] += sum_j G[j, o] * a[j, f] ; dbqk[o] += sum_j G[j, o]
+constexpr int kDwThreads = 256;
+constexpr int kDwTile = 32;   // edges per smem tile
+constexpr int kDwPerThread = 16;
+
+__global__ void __launch_bounds__(kDwThreads)
+k_attn_bwd_dw_generic(const float* __restrict__ G, const float* __restrict__ a, int64_t E,
+                      AttnShape s, int64_t edges_per_cta, float* __restrict__ dWq,
+                      float* __restrict__ dbq, float* __restrict__ dWk,
+                      float* __restrict__ dbk) {
+  extern __shared__ float smem[];
+  float* Gs = smem;                       // [kDwTile][HD2]
+  float* As = Gs + kDwTile * s.HD2;       // [kDwTile][F]
+  const int64_t e0 = (int64_t)blockIdx.x * edges_per_cta;
+  const int64_t e1 = min(e0 + edges_per_cta, E);
+  if (e0 >= e1) return;
+  const int nout = s.HD2 * s.F;
+  for (int obase = 0; obase < nout; obase += kDwThreads * kDwPerThread) {
+    float acc[kDwPerThread], accb[kDwPerThread];
+#pragma unroll
+    for (int i = 0; i < kDwPerThread; ++i) acc[i] = accb[i] = 0.f;
+    for (int64_t t0 = e0; t0 < e1; t0 += kDwTile) {
+      int nt = (int)min((int64_t)kDwTile, e1 - t0);
+      __syncthreads();
+      for (int i = threadIdx.x; i < nt * s.HD2; i += kDwThreads) Gs[i] = G[t0 * s.HD2 + i];
+      for (int i = threadIdx.x; i < nt * s.F; i += kDwThreads) As[i] = a[t0 * s.F + i];
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < kDwPerThread; ++i) {
+        int idx = obase + threadIdx.x + kDwThreads * i;
+        if (idx < nout) {
+          int o = idx / s.F, f = idx - o * s.F;
+          float sacc = 0.f, sb = 0.f;
+          for (int ee = 0; ee < nt; ++ee) {
+            float g = Gs[ee * s.HD2 + o];
+            sacc = fmaf(g, As[ee * s.F + f], sacc);
+            sb += g;
+          }
+          acc[i] += sacc;
+          accb[i] += sb;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kDwPerThread; ++i) {
+      int idx = obase + threadIdx.x + kDwThreads * i;
+      if (idx < nout) {
+        int o = idx / s.F, f = idx - o * s.F;
+        if (o < s.HD) {
+          if (dWq) atomicAdd(&dWq[o * s.F + f], acc[i]);
+          if (dbq && f == 0) atomicAdd(&dbq[o], accb[i]);
+        } else {
+          if (dWk) atomicAdd(&dWk[(o - s.HD) * s.F + f], acc[i]);
+          if (dbk && f == 0) atomicAdd(&dbk[o - s.HD], accb[i]);
+        }
+      }
+    }
+  }
+}
+
+static int check_shape(const char* who, int H, int D, int Dv, int F, AttnShape* out) {
+  SPT_REQUIRE(H >= 1 && D >= 1 && Dv >= 1 && F >= 0, SPT_E_INVALID, "%s: bad dims", who);
+  AttnShape s;
+  s.H = H; s.D = D; s.Dv = Dv; s.F = F;
+  s.C = H * Dv; s.HD = H * D; s.HD2 = 2 * H * D; s.HF = H * F;
+  SPT_REQUIRE(H <= 32 && s.C <= 32 * kVPL && s.HD <= 32 * kOPL && s.HF <= 32 * kAPL && F <= 128,
+              SPT_E_UNSUPPORTED,
+              "%s: shape H=%d D=%d Dv=%d F=%d outside generic kernel limits "
+              "(H<=32, C<=256, H*D<=256, H*F<=512, F<=128)", who, H, D, Dv, F);
+  *out = s;
+  return SPT_OK;
+}
+
+}  // namespace spt
+
+using namespace spt;
+
+extern "C" {
+
+int spt_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v,
+                 int64_t ldv, const float* a, const int32_t* rowptr, const int32_t* col,
+                 int64_t num_rows, int64_t E, int H, int D, int Dv, int F, const float* Wq,
+                 const float* bq, const float* Wk, const float* bk, int scale_mode,
+                 float scale_value, float* agg_v, float* abar, float* sump, float* m,
+                 float* z, void* stream_) {
+  SPT_REQUIRE(num_rows >= 0 && E >= 0, SPT_E_INVALID, "attn_fwd: negative size");
+  if (num_rows == 0) return SPT_OK;
+  AttnShape s;
+  int rc = check_shape("attn_fwd", H, D, Dv, a ? F : 0, &s);
+  if (rc != SPT_OK) return rc;
+  SPT_REQUIRE(q && k && v && rowptr && (E == 0 || col) && agg_v && sump && m && z,
+              SPT_E_INVALID, "attn_fwd: null pointer");
+  SPT_REQUIRE(scale_mode >= SPT_SCALE_D_TIMES_G && scale_mode <= SPT_SCALE_CONST,
+              SPT_E_INVALID, "attn_fwd: bad scale mode %d", scale_mode);
+  FwdParams P;
+  P.q = q; P.ldq = ldq; P.k = k; P.ldk = ldk; P.v = v; P.ldv = ldv; P.a = a;
+  P.rowptr = rowptr; P.col = col; P.num_rows = num_rows; P.s = s;
+  P.Wq = a ? Wq : nullptr; P.bq = bq; P.Wk = a ? Wk : nullptr; P.bk = bk;
+  P.scale_mode = scale_mode; P.scale_value = scale_value;
+  P.agg_v = agg_v; P.abar = a ? abar : nullptr; P.sump = sump; P.m = m; P.z = z;
+  int F4 = round4(s.F > 1 ? s.F : 1);
+  int per_warp = F4 + s.HD2 + s.HD + 96;
+  size_t smem = (size_t)(s.F * (s.HD2 + 1) + s.HD2 + kAttnWarps * per_warp) * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(k_attn_fwd_generic, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem);
+  k_attn_fwd_generic<<<(unsigned)ceil_div(num_rows, kAttnWarps), kAttnWarps * kWarp, smem, st>>>(P);
+  return check_launch("attn_fwd");
+}
+
+int spt_attn_bwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v,
+                 int64_t ldv, const float* a, const int32_t* rowptr, const int32_t* col,
+                 const int32_t* csc_ptr, const int32_t* csc_src, const int32_t* csc2csr,
+                 int64_t num_rows, int64_t num_targets, int64_t E, int H, int D, int Dv,
+                 int F, const float* Wq, const float* bq, const float* Wk, const float* bk,
+                 int scale_mode, float scale_value, const float* m, const float* z,
+                 const float* agg_v, const float* abar, const float* d_agg_v,
+                 const float* d_abar, float* dq, int64_t lddq, float* dk, int64_t lddk,
+                 float* dv, int64_t lddv, float* da, float* dWq, float* dbq, float* dWk,
+                 float* dbk, float* Pbuf, float* G, void* stream_) {
+  SPT_REQUIRE(num_rows >= 0 && num_targets >= 0 && E >= 0, SPT_E_INVALID,
+              "attn_bwd: negative size");
+  AttnShape s;
+  int rc = check_shape("attn_bwd", H, D, Dv, a ? F : 0, &s);
+  if (rc != SPT_OK) return rc;
+  SPT_REQUIRE(q && k && v && rowptr && csc_ptr && m && z && agg_v && d_agg_v && dq && dk &&
+                  dv && (E == 0 || (col && csc_src && csc2csr && Pbuf && G)),
+              SPT_E_INVALID, "attn_bwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (num_rows > 0) {
+    BwdParams P;
+    P.q = q; P.ldq = ldq; P.k = k; P.ldk = ldk; P.v = v; P.ldv = ldv; P.a = a;
+    P.rowptr = rowptr; P.col = col; P.num_rows = num_rows; P.s = s;
+    P.Wq = a ? Wq : nullptr; P.bq = bq; P.Wk = a ? Wk : nullptr; P.bk = bk;
+    P.scale_mode = scale_mode; P.scale_value = scale_value;
+    P.m = m; P.z = z; P.agg_v = agg_v; P.abar = abar; P.d_agg_v = d_agg_v; P.d_abar = d_abar;
+    P.dq = dq; P.lddq = lddq; P.da = da; P.Pbuf = Pbuf; P.G = G;
+    int F4 = round4(s.F > 1 ? s.F : 1);
+    int per_warp = F4 + 2 * s.HD2 + s.HD + 160 + round4(s.C) + round4(s.HF > 1 ? s.HF : 1);
+    size_t smem = (size_t)(s.F * (s.HD2 + 1) + s.HD2 + kAttnWarps * per_warp) * sizeof(float);
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(k_attn_bwd_rows_generic,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_attn_bwd_rows_generic<<<(unsigned)ceil_div(num_rows, kAttnWarps), kAttnWarps * kWarp, smem,
+                              st>>>(P);
+  }
+  if (num_targets > 0) {
+    k_attn_bwd_targets_generic<<<(unsigned)ceil_div(num_targets, kAttnWarps),
+                                 kAttnWarps * kWarp, 0, st>>>(
+        csc_ptr, csc_src, csc2csr, num_targets, s, Pbuf, G, d_agg_v, dk, lddk, dv, lddv);
+  }
+  if (a && s.F > 0 && E > 0 && (dWq || dWk || dbq || dbk)) {
+    int64_t ctas = ceil_div(E, 2048);
+    if (ctas > 148 * 4) ctas = 148 * 4;
+    int64_t per = ceil_div(E, ctas);
+    per = ceil_div(per, kDwTile) * kDwTile;
+    ctas = ceil_div(E, per);
+    size_t smem = (size_t)kDwTile * (s.HD2 + s.F) * sizeof(float);
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(k_attn_bwd_dw_generic, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)smem);
+    k_attn_bwd_dw_generic<<<(unsigned)ctas, kDwThreads, smem, st>>>(G, a, E, s, per, dWq, dbq,
+                                                                  dWk, dbk);
+  } else if (!a && E > 0 && (dbq || dbk)) {
+    // no edge features: biases unused by the forward (Wq/Wk ignored) -> zero grads
+  }
+  return check_launch("attn_bwd");
+}
+
+}  // extern "C"

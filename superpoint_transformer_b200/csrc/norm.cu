@@ -1,0 +1,475 @@
+// norm.cu — GraphNorm forward/backward (torch_geometric.nn.norm.GraphNorm semantics,
+// SURVEY.md Appendix A) for few, huge segments (one per cloud in the batch).
+//
+//   mean[b]  = sum_{i in b} x_i / max(n_b, 1)
+//   out_i    = x_i - mean_scale * mean[b]
+//   var[b]   = sum out_i^2 / max(n_b, 1)
+//   y_i      = weight * out_i / sqrt(var[b] + eps) + bias
+//
+// Two-pass statistics (mean, then centred second moment) like the reference, so
+// there is no E[x^2]-E[x]^2 cancellation.  Each CTA reduces a slab of rows in
+// registers/shared memory and flushes per-column partials with fp64 atomics into
+// a [B, C] accumulator (B is tiny; the atomics are ~C per CTA).  `batch` may be
+// unsorted (edge-level norms use norm_index[edge_index[0]], src/models/components/
+// spt.py:829-835): threads flush whenever the segment id of their row changes.
+#include "common.cuh"
+
+namespace spt {
+
+constexpr int kNormThreads = 256;
+constexpr int kNormRows = 128;  // rows per CTA slab
+
+struct ColMap {
+  int tx;  // threads along columns (each VEC wide)
+  int ty;  // row lanes
+};
+
+// Column-sliced slab reduction shared by the three statistics passes.
+//   MODE 0: acc0 += x                         (+ row count)
+//   MODE 1: acc0 += (x - mean_scale*mean)^2
+//   MODE 2: acc0 += dy*xhat ; acc1 += dy      (backward)
+// Thread (cx, ry) owns VEC columns and every ty-th row of the slab.  When the
+// whole slab belongs to one segment (the common case: `batch` sorted, slabs much
+// smaller than graphs) the ty row-lanes are reduced through shared memory and only
+// tx*VEC fp64 atomics leave the CTA; otherwise each thread flushes on every
+// segment change.
+template <int MODE, int VEC>
+__global__ void __launch_bounds__(kNormThreads)
+k_graphnorm_stats(const float* __restrict__ x, const float* __restrict__ dy,
+                  const int64_t* __restrict__ batch, int64_t N, int64_t C, int64_t B,
+                  const float* __restrict__ mean_scale,
+                  const double* __restrict__ sum_x, const double* __restrict__ count,
+                  const float* __restrict__ mean, const float* __restrict__ rstd,
+                  double* __restrict__ acc0 /*[B,C]*/, double* __restrict__ acc1 /*[B,C]*/,
+                  double* __restrict__ cnt_out /*[B]*/, int tx, int ty) {
+  constexpr int NACC = (MODE == 2) ? 2 : 1;
+  __shared__ float red[NACC][kNormThreads * VEC];
+  int cx = threadIdx.x % tx;
+  int ry = threadIdx.x / tx;
+  int64_t r0 = (int64_t)blockIdx.x * kNormRows;
+  int64_t r1 = min(r0 + (int64_t)kNormRows, N);
+  int64_t first_b = batch ? batch[r0] : 0;
+  for (int64_t ct = 0; ct < C; ct += (int64_t)tx * VEC) {
+    int64_t c0 = ct + (int64_t)cx * VEC;
+    bool active = c0 < C;
+    float a[NACC][VEC], mu[VEC], rs[VEC], ms[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      a[0][v] = 0.f;
+      if (NACC == 2) a[NACC - 1][v] = 0.f;
+      mu[v] = 0.f;
+      rs[v] = 1.f;
+      ms[v] = (MODE != 0 && active) ? mean_scale[c0 + v] : 0.f;
+    }
+    int64_t cur = -1;
+    int nrows = 0;
+    bool uniform = true;
+    if (active) {
+      for (int64_t r = r0 + ry; r < r1; r += ty) {
+        int64_t b = batch ? batch[r] : 0;
+        if (b < 0 || b >= B) continue;
+        if (b != first_b) uniform = false;
+        if (b != cur) {
+          if (cur >= 0) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+              atomicAdd(&acc0[cur * C + c0 + v], (double)a[0][v]);
+              if (NACC == 2) atomicAdd(&acc1[cur * C + c0 + v], (double)a[NACC - 1][v]);
+            }
+            if (MODE == 0 && c0 == 0) atomicAdd(&cnt_out[cur], (double)nrows);
+          }
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            a[0][v] = 0.f;
+            if (NACC == 2) a[NACC - 1][v] = 0.f;
+          }
+          nrows = 0;
+          cur = b;
+          if (MODE == 1) {
+            double n = fmax(count[b], 1.0);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+              mu[v] = ms[v] * (float)(sum_x[b * C + c0 + v] / n);
+          } else if (MODE == 2) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+              mu[v] = ms[v] * mean[b * C + c0 + v];
+              rs[v] = rstd[b * C + c0 + v];
+            }
+          }
+        }
+        float xv[VEC], gv[VEC];
+        if (VEC == 4) {
+          float4 t = *reinterpret_cast<const float4*>(x + r * C + c0);
+          xv[0] = t.x; xv[1 % VEC] = t.y; xv[2 % VEC] = t.z; xv[3 % VEC] = t.w;
+          if (MODE == 2) {
+            float4 g = *reinterpret_cast<const float4*>(dy + r * C + c0);
+            gv[0] = g.x; gv[1 % VEC] = g.y; gv[2 % VEC] = g.z; gv[3 % VEC] = g.w;
+          }
+        } else {
+          xv[0] = x[r * C + c0];
+          if (MODE == 2) gv[0] = dy[r * C + c0];
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          if (MODE == 0) {
+            a[0][v] += xv[v];
+          } else if (MODE == 1) {
+            float d = xv[v] - mu[v];
+            a[0][v] = fmaf(d, d, a[0][v]);
+          } else {
+            float xhat = (xv[v] - mu[v]) * rs[v];
+            a[0][v] = fmaf(gv[v], xhat, a[0][v]);
+            a[NACC - 1][v] += gv[v];
+          }
+        }
+        ++nrows;
+      }
+    }
+    // CTA-uniform decision: every row of the slab in segment first_b?
+    int all_uniform = __syncthreads_and(uniform ? 1 : 0);
+    if (all_uniform && ty > 1) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        red[0][threadIdx.x * VEC + v] = a[0][v];
+        if (NACC == 2) red[NACC - 1][threadIdx.x * VEC + v] = a[NACC - 1][v];
+      }
+      __syncthreads();
+      if (ry == 0 && active && first_b >= 0 && first_b < B) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          float s0 = 0.f, s1 = 0.f;
+          for (int y = 0; y < ty; ++y) {
+            s0 += red[0][(y * tx + cx) * VEC + v];
+            if (NACC == 2) s1 += red[NACC - 1][(y * tx + cx) * VEC + v];
+          }
+          atomicAdd(&acc0[first_b * C + c0 + v], (double)s0);
+          if (NACC == 2) atomicAdd(&acc1[first_b * C + c0 + v], (double)s1);
+        }
+        if (MODE == 0 && c0 == 0) atomicAdd(&cnt_out[first_b], (double)(r1 - r0));
+      }
+      __syncthreads();
+    } else if (active && cur >= 0) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        atomicAdd(&acc0[cur * C + c0 + v], (double)a[0][v]);
+        if (NACC == 2) atomicAdd(&acc1[cur * C + c0 + v], (double)a[NACC - 1][v]);
+      }
+      if (MODE == 0 && c0 == 0) atomicAdd(&cnt_out[cur], (double)nrows);
+    }
+  }
+}
+
+// [B,C] finalisation: mean, rstd
+__global__ void k_graphnorm_finalize(const double* __restrict__ sum_x,
+                                     const double* __restrict__ sum_sq,
+                                     const double* __restrict__ count, int64_t B,
+                                     int64_t C, float eps, float* __restrict__ mean,
+                                     float* __restrict__ rstd) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  int64_t b = i / C;
+  double n = fmax(count[b], 1.0);
+  float m = (float)(sum_x[i] / n);
+  float var = (float)(sum_sq[i] / n);
+  mean[i] = m;
+  rstd[i] = 1.f / sqrtf(var + eps);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kNormThreads)
+k_graphnorm_apply(const float* __restrict__ x, const int64_t* __restrict__ batch,
+                  int64_t N, int64_t C, int64_t B, const float* __restrict__ weight,
+                  const float* __restrict__ bias, const float* __restrict__ mean_scale,
+                  const float* __restrict__ mean, const float* __restrict__ rstd,
+                  float* __restrict__ y) {
+  int64_t cv = C / VEC;
+  int64_t total = N * cv;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    int64_t r = i / cv;
+    int64_t c0 = (i - r * cv) * VEC;
+    int64_t b = batch ? batch[r] : 0;
+    if (b < 0 || b >= B) continue;
+    float xv[VEC], o[VEC];
+    if (VEC == 4) {
+      float4 t = *reinterpret_cast<const float4*>(x + r * C + c0);
+      xv[0] = t.x; xv[1 % VEC] = t.y; xv[2 % VEC] = t.z; xv[3 % VEC] = t.w;
+    } else {
+      xv[0] = x[r * C + c0];
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      int64_t c = c0 + v;
+      float out = xv[v] - mean_scale[c] * mean[b * C + c];
+      float w = weight ? weight[c] : 1.f;
+      float bb = bias ? bias[c] : 0.f;
+      o[v] = fmaf(w * out, rstd[b * C + c], bb);
+    }
+    if (VEC == 4)
+      *reinterpret_cast<float4*>(y + r * C + c0) =
+          make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
+    else
+      y[r * C + c0] = o[0];
+  }
+}
+
+// [B,C] coefficients so that dx_i = k1 * dy_i - k2 * xhat_i - k3
+//   k1 = w*rstd ; k2 = w*rstd*s1/n ; k3 = mean_scale * T / n,
+//   T  = rstd*w*(s2 - s1*rstd*(1-mean_scale)*mean)   (= sum_j dout_j)
+// and parameter grads: dweight = sum_b s1, dbias = sum_b s2,
+//   dmean_scale = -sum_b mean*T.  One thread per column, loops over b.
+__global__ void k_graphnorm_bwd_coef(const double* __restrict__ s1,
+                                     const double* __restrict__ s2,
+                                     const double* __restrict__ count, int64_t B,
+                                     int64_t C, const float* __restrict__ weight,
+                                     const float* __restrict__ mean_scale,
+                                     const float* __restrict__ mean,
+                                     const float* __restrict__ rstd,
+                                     float* __restrict__ k2, float* __restrict__ k3,
+                                     float* __restrict__ dweight,
+                                     float* __restrict__ dbias,
+                                     float* __restrict__ dmean_scale) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double w = weight ? (double)weight[c] : 1.0;
+  double ms = mean_scale[c];
+  double dw = 0, db = 0, dms = 0;
+  for (int64_t b = 0; b < B; ++b) {
+    double n = fmax(count[b], 1.0);
+    double S1 = s1[b * C + c], S2 = s2[b * C + c];
+    double rs = rstd[b * C + c], mu = mean[b * C + c];
+    double T = rs * w * (S2 - S1 * rs * (1.0 - ms) * mu);
+    k2[b * C + c] = (float)(w * rs * S1 / n);
+    k3[b * C + c] = (float)(ms * T / n);
+    dw += S1;
+    db += S2;
+    dms -= mu * T;
+  }
+  if (dweight) dweight[c] = (float)dw;
+  if (dbias) dbias[c] = (float)db;
+  if (dmean_scale) dmean_scale[c] = (float)dms;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kNormThreads)
+k_graphnorm_bwd_apply(const float* __restrict__ x, const float* __restrict__ dy,
+                      const int64_t* __restrict__ batch, int64_t N, int64_t C, int64_t B,
+                      const float* __restrict__ weight, const float* __restrict__ mean_scale,
+                      const float* __restrict__ mean, const float* __restrict__ rstd,
+                      const float* __restrict__ k2, const float* __restrict__ k3,
+                      float* __restrict__ dx) {
+  int64_t cv = C / VEC;
+  int64_t total = N * cv;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    int64_t r = i / cv;
+    int64_t c0 = (i - r * cv) * VEC;
+    int64_t b = batch ? batch[r] : 0;
+    float o[VEC];
+    if (b < 0 || b >= B) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) o[v] = 0.f;
+    } else {
+      float xv[VEC], gv[VEC];
+      if (VEC == 4) {
+        float4 t = *reinterpret_cast<const float4*>(x + r * C + c0);
+        float4 g = *reinterpret_cast<const float4*>(dy + r * C + c0);
+        xv[0] = t.x; xv[1 % VEC] = t.y; xv[2 % VEC] = t.z; xv[3 % VEC] = t.w;
+        gv[0] = g.x; gv[1 % VEC] = g.y; gv[2 % VEC] = g.z; gv[3 % VEC] = g.w;
+      } else {
+        xv[0] = x[r * C + c0];
+        gv[0] = dy[r * C + c0];
+      }
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        int64_t c = c0 + v;
+        float rs = rstd[b * C + c];
+        float xhat = (xv[v] - mean_scale[c] * mean[b * C + c]) * rs;
+        float w = weight ? weight[c] : 1.f;
+        o[v] = w * rs * gv[v] - k2[b * C + c] * xhat - k3[b * C + c];
+      }
+    }
+    if (VEC == 4)
+      *reinterpret_cast<float4*>(dx + r * C + c0) =
+          make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
+    else
+      dx[r * C + c0] = o[0];
+  }
+}
+
+// rows per segment (fp64 counter so it shares the workspace layout)
+__global__ void k_count_rows(const int64_t* __restrict__ batch, int64_t N, int64_t B,
+                             double* __restrict__ count) {
+  // per-thread run-length compression: consecutive rows usually share a segment
+  int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  int64_t per = (N + nthreads - 1) / nthreads;
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t r0 = t * per, r1 = min(r0 + per, N);
+  int64_t cur = -1;
+  int64_t run = 0;
+  for (int64_t r = r0; r < r1; ++r) {
+    int64_t b = batch ? batch[r] : 0;
+    if (b < 0 || b >= B) continue;
+    if (b != cur) {
+      if (cur >= 0) atomicAdd(&count[cur], (double)run);
+      cur = b;
+      run = 0;
+    }
+    ++run;
+  }
+  if (cur >= 0) atomicAdd(&count[cur], (double)run);
+}
+
+static inline ColMap col_map(int64_t C, int vec) {
+  int64_t cols = C / vec;
+  int tx = 1;
+  while (tx < cols && tx < kNormThreads) tx <<= 1;  // pow2 >= cols (cap 256)
+  if (tx > kNormThreads) tx = kNormThreads;
+  ColMap m;
+  m.tx = tx;
+  m.ty = kNormThreads / tx;
+  return m;
+}
+
+}  // namespace spt
+
+using namespace spt;
+
+namespace {
+inline int64_t imin(int64_t a, int64_t b) { return a < b ? a : b; }
+
+struct NormWs {
+  double* acc0;
+  double* acc1;
+  double* count;
+  float* k2;
+  float* k3;
+  size_t zero_bytes;
+};
+inline NormWs carve(void* ws, int64_t B, int64_t C) {
+  size_t bc = (size_t)B * (size_t)C;
+  char* p = (char*)ws;
+  NormWs w;
+  w.acc0 = (double*)p;
+  w.acc1 = (double*)(p + align_up(bc * 8, 256));
+  w.count = (double*)(p + 2 * align_up(bc * 8, 256));
+  w.k2 = (float*)(p + 2 * align_up(bc * 8, 256) + align_up((size_t)B * 8, 256));
+  w.k3 = (float*)((char*)w.k2 + align_up(bc * 4, 256));
+  w.zero_bytes = 2 * align_up(bc * 8, 256) + align_up((size_t)B * 8, 256);
+  return w;
+}
+}  // namespace
+
+extern "C" {
+
+// ws: acc0[B*C] f64 | acc1[B*C] f64 | count[B] f64 | k2[B*C] f32 | k3[B*C] f32
+size_t spt_graphnorm_workspace_bytes(int64_t B, int64_t C) {
+  if (B < 0 || C < 0) return 0;
+  size_t bc = (size_t)B * (size_t)C;
+  return align_up(bc * 8, 256) * 2 + align_up((size_t)B * 8, 256) +
+         align_up(bc * 4, 256) * 2;
+}
+
+int spt_graphnorm_fwd(const float* x, const int64_t* batch, int64_t N, int64_t C,
+                      int64_t B, const float* weight, const float* bias,
+                      const float* mean_scale, float eps, float* y, float* mean,
+                      float* rstd, void* ws, size_t ws_bytes, void* stream_) {
+  SPT_REQUIRE(N >= 0 && C > 0 && B > 0, SPT_E_INVALID, "graphnorm_fwd: bad sizes");
+  SPT_REQUIRE(mean_scale && mean && rstd && ws && (N == 0 || (x && y)), SPT_E_INVALID,
+              "graphnorm_fwd: null pointer");
+  SPT_REQUIRE(ws_bytes >= spt_graphnorm_workspace_bytes(B, C), SPT_E_WORKSPACE,
+              "graphnorm_fwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream_;
+  NormWs w = carve(ws, B, C);
+  cudaError_t ce = cudaMemsetAsync(ws, 0, w.zero_bytes, st);
+  if (ce != cudaSuccess) {
+    set_error("graphnorm_fwd memset: %s", cudaGetErrorString(ce));
+    return (int)ce;
+  }
+  int vec = (C % 4 == 0) ? 4 : 1;
+  ColMap cm = col_map(C, vec);
+  unsigned slabs = (unsigned)ceil_div(N > 0 ? N : 1, kNormRows);
+  int64_t total = N * (C / vec);
+  int agrid = (int)imin(ceil_div(total > 0 ? total : 1, kNormThreads), 148 * 16);
+  if (N > 0) {
+    if (vec == 4) {
+      k_graphnorm_stats<0, 4><<<slabs, kNormThreads, 0, st>>>(
+          x, nullptr, batch, N, C, B, mean_scale, nullptr, nullptr, nullptr, nullptr,
+          w.acc0, nullptr, w.count, cm.tx, cm.ty);
+      k_graphnorm_stats<1, 4><<<slabs, kNormThreads, 0, st>>>(
+          x, nullptr, batch, N, C, B, mean_scale, w.acc0, w.count, nullptr, nullptr,
+          w.acc1, nullptr, nullptr, cm.tx, cm.ty);
+    } else {
+      k_graphnorm_stats<0, 1><<<slabs, kNormThreads, 0, st>>>(
+          x, nullptr, batch, N, C, B, mean_scale, nullptr, nullptr, nullptr, nullptr,
+          w.acc0, nullptr, w.count, cm.tx, cm.ty);
+      k_graphnorm_stats<1, 1><<<slabs, kNormThreads, 0, st>>>(
+          x, nullptr, batch, N, C, B, mean_scale, w.acc0, w.count, nullptr, nullptr,
+          w.acc1, nullptr, nullptr, cm.tx, cm.ty);
+    }
+  }
+  k_graphnorm_finalize<<<(unsigned)ceil_div(B * C, 256), 256, 0, st>>>(
+      w.acc0, w.acc1, w.count, B, C, eps, mean, rstd);
+  if (N > 0) {
+    if (vec == 4)
+      k_graphnorm_apply<4><<<agrid, kNormThreads, 0, st>>>(x, batch, N, C, B, weight, bias,
+                                                          mean_scale, mean, rstd, y);
+    else
+      k_graphnorm_apply<1><<<agrid, kNormThreads, 0, st>>>(x, batch, N, C, B, weight, bias,
+                                                          mean_scale, mean, rstd, y);
+  }
+  return check_launch("graphnorm_fwd");
+}
+
+int spt_graphnorm_bwd(const float* x, const float* dy, const int64_t* batch, int64_t N,
+                      int64_t C, int64_t B, const float* weight, const float* mean_scale,
+                      const float* mean, const float* rstd, float* dx, float* dweight,
+                      float* dbias, float* dmean_scale, void* ws, size_t ws_bytes,
+                      void* stream_) {
+  SPT_REQUIRE(N >= 0 && C > 0 && B > 0, SPT_E_INVALID, "graphnorm_bwd: bad sizes");
+  SPT_REQUIRE(mean_scale && mean && rstd && ws && (N == 0 || (x && dy && dx)),
+              SPT_E_INVALID, "graphnorm_bwd: null pointer");
+  SPT_REQUIRE(ws_bytes >= spt_graphnorm_workspace_bytes(B, C), SPT_E_WORKSPACE,
+              "graphnorm_bwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream_;
+  NormWs w = carve(ws, B, C);
+  cudaError_t ce = cudaMemsetAsync(ws, 0, w.zero_bytes, st);
+  if (ce != cudaSuccess) {
+    set_error("graphnorm_bwd memset: %s", cudaGetErrorString(ce));
+    return (int)ce;
+  }
+  int vec = (C % 4 == 0) ? 4 : 1;
+  ColMap cm = col_map(C, vec);
+  unsigned slabs = (unsigned)ceil_div(N > 0 ? N : 1, kNormRows);
+  int64_t total = N * (C / vec);
+  int agrid = (int)imin(ceil_div(total > 0 ? total : 1, kNormThreads), 148 * 16);
+  if (N > 0) {
+    if (vec == 4)
+      k_graphnorm_stats<2, 4><<<slabs, kNormThreads, 0, st>>>(
+          x, dy, batch, N, C, B, mean_scale, nullptr, nullptr, mean, rstd, w.acc0,
+          w.acc1, nullptr, cm.tx, cm.ty);
+    else
+      k_graphnorm_stats<2, 1><<<slabs, kNormThreads, 0, st>>>(
+          x, dy, batch, N, C, B, mean_scale, nullptr, nullptr, mean, rstd, w.acc0,
+          w.acc1, nullptr, cm.tx, cm.ty);
+    k_count_rows<<<(unsigned)imin(ceil_div(N, 256 * 64), 148 * 8), 256, 0, st>>>(
+        batch, N, B, w.count);
+  }
+  k_graphnorm_bwd_coef<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(
+      w.acc0, w.acc1, w.count, B, C, weight, mean_scale, mean, rstd, w.k2, w.k3, dweight,
+      dbias, dmean_scale);
+  if (N > 0) {
+    if (vec == 4)
+      k_graphnorm_bwd_apply<4><<<agrid, kNormThreads, 0, st>>>(
+          x, dy, batch, N, C, B, weight, mean_scale, mean, rstd, w.k2, w.k3, dx);
+    else
+      k_graphnorm_bwd_apply<1><<<agrid, kNormThreads, 0, st>>>(
+          x, dy, batch, N, C, B, weight, mean_scale, mean, rstd, w.k2, w.k3, dx);
+  }
+  return check_launch("graphnorm_bwd");
+}
+
+}  // extern "C"

@@ -1,0 +1,353 @@
+// segment.cu — HBM-bound segment kernels: row gathers, CSR segment pooling
+// (sum/mean/max/min, fwd + gather-form bwd), UnitSphereNorm.
+//
+// Layout: features are fp32 row-major [rows, C].  A warp owns one output row and
+// moves it as 16-byte vectors (C % 4 == 0 fast path; scalar path otherwise), so
+// every gathered child row is one or a few full 128-byte lines.
+#include "common.cuh"
+
+namespace spt {
+
+// ------------------------------------------------------------------ row gather
+template <typename IdxT, int VEC>
+__global__ void k_gather_rows(const float* __restrict__ x, const IdxT* __restrict__ idx,
+                              int64_t n_out, int64_t C, float* __restrict__ out) {
+  // one warp per output row, rows grid-strided
+  int lane = threadIdx.x & 31;
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n_out; r += nwarps) {
+    int64_t s = (int64_t)idx[r];
+    const float* src = x + s * C;
+    float* dst = out + r * C;
+    if (VEC == 4) {
+      for (int64_t c = lane * 4; c < C; c += 128)
+        *reinterpret_cast<float4*>(dst + c) = *reinterpret_cast<const float4*>(src + c);
+    } else {
+      for (int64_t c = lane; c < C; c += 32) dst[c] = src[c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ pool fwd
+template <int REDUCE, int VEC>
+__global__ void k_segment_pool_fwd(const float* __restrict__ x,
+                                   const int32_t* __restrict__ ptr,
+                                   const int32_t* __restrict__ points,
+                                   int64_t num_parents, int64_t C,
+                                   float* __restrict__ out, int32_t* __restrict__ arg) {
+  int lane = threadIdx.x & 31;
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t p = warp; p < num_parents; p += nwarps) {
+    int b = ptr[p], e = ptr[p + 1];
+    float inv = 1.f;
+    if (REDUCE == SPT_REDUCE_MEAN) inv = 1.f / (float)max(e - b, 1);
+    for (int64_t c0 = (int64_t)lane * VEC; c0 < C; c0 += 32 * VEC) {
+      float acc[VEC];
+      int32_t am[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        acc[v] = (REDUCE == SPT_REDUCE_MAX) ? -FLT_MAX
+                 : (REDUCE == SPT_REDUCE_MIN) ? FLT_MAX : 0.f;
+        am[v] = -1;
+      }
+      // two children in flight to overlap the dependent index->row loads
+      int i = b;
+      for (; i + 1 < e; i += 2) {
+        int ch0 = points ? points[i] : i;
+        int ch1 = points ? points[i + 1] : i + 1;
+        float r0[VEC], r1[VEC];
+        if (VEC == 4) {
+          float4 t0 = *reinterpret_cast<const float4*>(x + (int64_t)ch0 * C + c0);
+          float4 t1 = *reinterpret_cast<const float4*>(x + (int64_t)ch1 * C + c0);
+          r0[0] = t0.x; r0[1 % VEC] = t0.y; r0[2 % VEC] = t0.z; r0[3 % VEC] = t0.w;
+          r1[0] = t1.x; r1[1 % VEC] = t1.y; r1[2 % VEC] = t1.z; r1[3 % VEC] = t1.w;
+        } else {
+          r0[0] = x[(int64_t)ch0 * C + c0];
+          r1[0] = x[(int64_t)ch1 * C + c0];
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          if (REDUCE == SPT_REDUCE_MAX) {
+            if (r0[v] > acc[v] || am[v] < 0) { acc[v] = r0[v]; am[v] = ch0; }
+            if (r1[v] > acc[v]) { acc[v] = r1[v]; am[v] = ch1; }
+          } else if (REDUCE == SPT_REDUCE_MIN) {
+            if (r0[v] < acc[v] || am[v] < 0) { acc[v] = r0[v]; am[v] = ch0; }
+            if (r1[v] < acc[v]) { acc[v] = r1[v]; am[v] = ch1; }
+          } else {
+            acc[v] += r0[v];
+            acc[v] += r1[v];
+          }
+        }
+      }
+      if (i < e) {
+        int ch0 = points ? points[i] : i;
+        float r0[VEC];
+        if (VEC == 4) {
+          float4 t0 = *reinterpret_cast<const float4*>(x + (int64_t)ch0 * C + c0);
+          r0[0] = t0.x; r0[1 % VEC] = t0.y; r0[2 % VEC] = t0.z; r0[3 % VEC] = t0.w;
+        } else {
+          r0[0] = x[(int64_t)ch0 * C + c0];
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          if (REDUCE == SPT_REDUCE_MAX) {
+            if (r0[v] > acc[v] || am[v] < 0) { acc[v] = r0[v]; am[v] = ch0; }
+          } else if (REDUCE == SPT_REDUCE_MIN) {
+            if (r0[v] < acc[v] || am[v] < 0) { acc[v] = r0[v]; am[v] = ch0; }
+          } else {
+            acc[v] += r0[v];
+          }
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        if (REDUCE == SPT_REDUCE_MAX || REDUCE == SPT_REDUCE_MIN) {
+          if (am[v] < 0) acc[v] = 0.f;  // empty segment -> 0
+        } else if (REDUCE == SPT_REDUCE_MEAN) {
+          acc[v] *= inv;
+        }
+      }
+      if (VEC == 4) {
+        *reinterpret_cast<float4*>(out + p * C + c0) =
+            make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
+        if (arg && (REDUCE == SPT_REDUCE_MAX || REDUCE == SPT_REDUCE_MIN))
+          *reinterpret_cast<int4*>(arg + p * C + c0) =
+              make_int4(am[0], am[1 % VEC], am[2 % VEC], am[3 % VEC]);
+      } else {
+        out[p * C + c0] = acc[0];
+        if (arg && (REDUCE == SPT_REDUCE_MAX || REDUCE == SPT_REDUCE_MIN))
+          arg[p * C + c0] = am[0];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ pool bwd
+template <int REDUCE, int VEC>
+__global__ void k_segment_pool_bwd(const float* __restrict__ dout,
+                                   const int64_t* __restrict__ parent,
+                                   const int32_t* __restrict__ ptr,
+                                   const int32_t* __restrict__ arg,
+                                   int64_t num_children, int64_t C,
+                                   float* __restrict__ dx) {
+  int lane = threadIdx.x & 31;
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < num_children; i += nwarps) {
+    int64_t p = parent[i];
+    float scale = 1.f;
+    if (REDUCE == SPT_REDUCE_MEAN) scale = 1.f / (float)max(ptr[p + 1] - ptr[p], 1);
+    for (int64_t c0 = (int64_t)lane * VEC; c0 < C; c0 += 32 * VEC) {
+      if (VEC == 4) {
+        float4 g = *reinterpret_cast<const float4*>(dout + p * C + c0);
+        if (REDUCE == SPT_REDUCE_MAX || REDUCE == SPT_REDUCE_MIN) {
+          int4 a = *reinterpret_cast<const int4*>(arg + p * C + c0);
+          g.x = (a.x == (int)i) ? g.x : 0.f;
+          g.y = (a.y == (int)i) ? g.y : 0.f;
+          g.z = (a.z == (int)i) ? g.z : 0.f;
+          g.w = (a.w == (int)i) ? g.w : 0.f;
+        } else if (REDUCE == SPT_REDUCE_MEAN) {
+          g.x *= scale; g.y *= scale; g.z *= scale; g.w *= scale;
+        }
+        *reinterpret_cast<float4*>(dx + i * C + c0) = g;
+      } else {
+        float g = dout[p * C + c0];
+        if (REDUCE == SPT_REDUCE_MAX || REDUCE == SPT_REDUCE_MIN)
+          g = (arg[p * C + c0] == (int)i) ? g : 0.f;
+        else if (REDUCE == SPT_REDUCE_MEAN)
+          g *= scale;
+        dx[i * C + c0] = g;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ unit sphere
+// one warp per parent: bbox, weighted centroid -> center[3], diameter
+__global__ void k_unitsphere_stats(const float* __restrict__ pos,
+                                   const int32_t* __restrict__ ptr,
+                                   const int32_t* __restrict__ points,
+                                   const float* __restrict__ w, int64_t num_parents,
+                                   float* __restrict__ center /*[Np,3]*/,
+                                   float* __restrict__ diameter /*[Np]*/) {
+  int lane = threadIdx.x & 31;
+  int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (p >= num_parents) return;
+  int b = ptr[p], e = ptr[p + 1];
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
+  float mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  float sw = 0.f, sx[3] = {0.f, 0.f, 0.f};
+  for (int i = b + lane; i < e; i += 32) {
+    int ch = points ? points[i] : i;
+    float wi = w ? w[ch] : 1.f;
+    sw += wi;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      float v = pos[(int64_t)ch * 3 + d];
+      mn[d] = fminf(mn[d], v);
+      mx[d] = fmaxf(mx[d], v);
+      sx[d] += v * wi;
+    }
+  }
+  sw = warp_sum(sw);
+  float diam = 0.f;
+  float cen[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    mn[d] = warp_min(mn[d]);
+    mx[d] = warp_max(mx[d]);
+    sx[d] = warp_sum(sx[d]);
+    // empty segment: scatter min/max leave 0 (torch_scatter) -> span 0
+    float span = (e > b) ? (mx[d] - mn[d]) : 0.f;
+    diam = fmaxf(diam, span);
+    // scatter_mean_weighted: w_segment == 0 -> 1 ; unweighted: clamp(count,1)
+    float den = (sw == 0.f) ? 1.f : sw;
+    cen[d] = sx[d] / den;
+  }
+  if (lane == 0) {
+    center[p * 3 + 0] = cen[0];
+    center[p * 3 + 1] = cen[1];
+    center[p * 3 + 2] = cen[2];
+    diameter[p] = diam;
+  }
+}
+
+__global__ void k_unitsphere_apply(const float* __restrict__ pos,
+                                   const int64_t* __restrict__ parent,
+                                   const float* __restrict__ center,
+                                   const float* __restrict__ diameter, int64_t N,
+                                   float* __restrict__ pos_out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  int64_t p = parent ? parent[i] : 0;
+  float inv = 1.f / (diameter[p] + 1e-2f);
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+    pos_out[i * 3 + d] = (pos[i * 3 + d] - center[p * 3 + d]) * inv;
+}
+
+static inline int warps_grid(int64_t rows, int threads, int64_t cap_blocks) {
+  int64_t wpb = threads / 32;
+  int64_t b = ceil_div(rows, wpb);
+  if (b < 1) b = 1;
+  if (b > cap_blocks) b = cap_blocks;
+  return (int)b;
+}
+
+}  // namespace spt
+
+using namespace spt;
+
+extern "C" {
+
+int spt_gather_rows_i64(const float* x, const int64_t* idx, int64_t n_out,
+                        int64_t C, float* out, void* stream_) {
+  SPT_REQUIRE(n_out >= 0 && C >= 0, SPT_E_INVALID, "gather_rows: negative size");
+  if (n_out == 0 || C == 0) return SPT_OK;
+  SPT_REQUIRE(x && idx && out, SPT_E_INVALID, "gather_rows: null pointer");
+  cudaStream_t st = (cudaStream_t)stream_;
+  int grid = warps_grid(n_out, 256, 148 * 32);
+  if (C % 4 == 0)
+    k_gather_rows<int64_t, 4><<<grid, 256, 0, st>>>(x, idx, n_out, C, out);
+  else
+    k_gather_rows<int64_t, 1><<<grid, 256, 0, st>>>(x, idx, n_out, C, out);
+  return check_launch("gather_rows_i64");
+}
+
+int spt_gather_rows_i32(const float* x, const int32_t* idx, int64_t n_out,
+                        int64_t C, float* out, void* stream_) {
+  SPT_REQUIRE(n_out >= 0 && C >= 0, SPT_E_INVALID, "gather_rows: negative size");
+  if (n_out == 0 || C == 0) return SPT_OK;
+  SPT_REQUIRE(x && idx && out, SPT_E_INVALID, "gather_rows: null pointer");
+  cudaStream_t st = (cudaStream_t)stream_;
+  int grid = warps_grid(n_out, 256, 148 * 32);
+  if (C % 4 == 0)
+    k_gather_rows<int32_t, 4><<<grid, 256, 0, st>>>(x, idx, n_out, C, out);
+  else
+    k_gather_rows<int32_t, 1><<<grid, 256, 0, st>>>(x, idx, n_out, C, out);
+  return check_launch("gather_rows_i32");
+}
+
+#define SPT_DISPATCH_REDUCE(KERNEL, ...)                                        \
+  do {                                                                          \
+    if (C % 4 == 0) {                                                           \
+      switch (reduce) {                                                         \
+        case SPT_REDUCE_SUM: KERNEL<SPT_REDUCE_SUM, 4> __VA_ARGS__; break;      \
+        case SPT_REDUCE_MEAN: KERNEL<SPT_REDUCE_MEAN, 4> __VA_ARGS__; break;    \
+        case SPT_REDUCE_MAX: KERNEL<SPT_REDUCE_MAX, 4> __VA_ARGS__; break;      \
+        default: KERNEL<SPT_REDUCE_MIN, 4> __VA_ARGS__; break;                  \
+      }                                                                         \
+    } else {                                                                    \
+      switch (reduce) {                                                         \
+        case SPT_REDUCE_SUM: KERNEL<SPT_REDUCE_SUM, 1> __VA_ARGS__; break;      \
+        case SPT_REDUCE_MEAN: KERNEL<SPT_REDUCE_MEAN, 1> __VA_ARGS__; break;    \
+        case SPT_REDUCE_MAX: KERNEL<SPT_REDUCE_MAX, 1> __VA_ARGS__; break;      \
+        default: KERNEL<SPT_REDUCE_MIN, 1> __VA_ARGS__; break;                  \
+      }                                                                         \
+    }                                                                           \
+  } while (0)
+
+int spt_segment_pool_fwd(const float* x, const int32_t* ptr, const int32_t* points,
+                         int64_t num_parents, int64_t C, int reduce, float* out,
+                         int32_t* arg, void* stream_) {
+  SPT_REQUIRE(num_parents >= 0 && C >= 0, SPT_E_INVALID, "segment_pool_fwd: negative size");
+  SPT_REQUIRE(reduce >= SPT_REDUCE_SUM && reduce <= SPT_REDUCE_MIN, SPT_E_INVALID,
+              "segment_pool_fwd: bad reduce %d", reduce);
+  if (num_parents == 0 || C == 0) return SPT_OK;
+  SPT_REQUIRE(ptr && out, SPT_E_INVALID, "segment_pool_fwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream_;
+  int grid = warps_grid(num_parents, 128, 148 * 64);
+  SPT_DISPATCH_REDUCE(k_segment_pool_fwd,
+                      <<<grid, 128, 0, st>>>(x, ptr, points, num_parents, C, out, arg));
+  return check_launch("segment_pool_fwd");
+}
+
+int spt_segment_pool_bwd(const float* dout, const int64_t* parent, const int32_t* ptr,
+                         const int32_t* arg, int64_t num_children, int64_t C,
+                         int reduce, float* dx, void* stream_) {
+  SPT_REQUIRE(num_children >= 0 && C >= 0, SPT_E_INVALID, "segment_pool_bwd: negative size");
+  SPT_REQUIRE(reduce >= SPT_REDUCE_SUM && reduce <= SPT_REDUCE_MIN, SPT_E_INVALID,
+              "segment_pool_bwd: bad reduce %d", reduce);
+  if (num_children == 0 || C == 0) return SPT_OK;
+  SPT_REQUIRE(dout && parent && dx, SPT_E_INVALID, "segment_pool_bwd: null pointer");
+  SPT_REQUIRE(reduce != SPT_REDUCE_MEAN || ptr, SPT_E_INVALID,
+              "segment_pool_bwd: mean needs ptr");
+  SPT_REQUIRE((reduce != SPT_REDUCE_MAX && reduce != SPT_REDUCE_MIN) || arg,
+              SPT_E_INVALID, "segment_pool_bwd: max/min need arg");
+  cudaStream_t st = (cudaStream_t)stream_;
+  int grid = warps_grid(num_children, 256, 148 * 32);
+  SPT_DISPATCH_REDUCE(k_segment_pool_bwd,
+                      <<<grid, 256, 0, st>>>(dout, parent, ptr, arg, num_children, C, dx));
+  return check_launch("segment_pool_bwd");
+}
+
+size_t spt_unitsphere_workspace_bytes(int64_t num_parents) {
+  if (num_parents < 0) return 0;
+  return align_up((size_t)num_parents * 3 * sizeof(float), 256);
+}
+
+int spt_unitsphere_fwd(const float* pos, const int64_t* parent, const int32_t* ptr,
+                       const int32_t* points, const float* w, int64_t N,
+                       int64_t num_parents, float* pos_out, float* diameter,
+                       void* ws, size_t ws_bytes, void* stream_) {
+  SPT_REQUIRE(N >= 0 && num_parents >= 0, SPT_E_INVALID, "unitsphere: negative size");
+  if (num_parents == 0) return SPT_OK;
+  SPT_REQUIRE(ptr && diameter && ws && (N == 0 || (pos && pos_out)), SPT_E_INVALID,
+              "unitsphere: null pointer");
+  SPT_REQUIRE(parent || num_parents == 1, SPT_E_INVALID,
+              "unitsphere: parent index required when num_parents > 1");
+  SPT_REQUIRE(ws_bytes >= spt_unitsphere_workspace_bytes(num_parents), SPT_E_WORKSPACE,
+              "unitsphere: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream_;
+  float* center = (float*)ws;
+  k_unitsphere_stats<<<(unsigned)ceil_div(num_parents * 32, 256), 256, 0, st>>>(
+      pos, ptr, points, w, num_parents, center, diameter);
+  if (N > 0)
+    k_unitsphere_apply<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(pos, parent, center,
+                                                                  diameter, N, pos_out);
+  return check_launch("unitsphere_fwd");
+}
+
+}  // extern "C"

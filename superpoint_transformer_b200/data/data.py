@@ -1,0 +1,247 @@
+"""Data: one NAG level (PyG-free holder with the attribute names and helpers of
+reference src/data/data.py that the hot path touches: x, pos, edge_index,
+edge_attr, super_index, sub, node_size, v_edge_attr, batch, norm_index(),
+num_nodes, add_keys_to())."""
+import torch
+
+from .cluster import Cluster
+
+__all__ = ['Data', 'Batch']
+
+
+class Data:
+    def __init__(self, **kwargs):
+        object.__setattr__(self, '_store', {})
+        for k, v in kwargs.items():
+            self[k] = v
+
+    # attribute / item access ------------------------------------------------
+    def __getattr__(self, key):
+        if key.startswith('__'):
+            raise AttributeError(key)
+        store = object.__getattribute__(self, '_store')
+        if key in store:
+            return store[key]
+        raise AttributeError(f"'Data' object has no attribute '{key}'")
+
+    def __setattr__(self, key, value):
+        if value is None:
+            self._store.pop(key, None)
+        else:
+            self._store[key] = value
+
+    def __delattr__(self, key):
+        self._store.pop(key, None)
+
+    def __getitem__(self, key):
+        return self._store.get(key)
+
+    def __setitem__(self, key, value):
+        setattr(self, key, value)
+
+    def __contains__(self, key):
+        return key in self._store
+
+    @property
+    def keys(self):
+        return list(self._store.keys())
+
+    # well-known fields default to None ----------------------------------------
+    def _get(self, key):
+        return self._store.get(key)
+
+    pos = property(lambda self: self._get('pos'))
+    x = property(lambda self: self._get('x'))
+    edge_index = property(lambda self: self._get('edge_index'))
+    edge_attr = property(lambda self: self._get('edge_attr'))
+    super_index = property(lambda self: self._get('super_index'))
+    sub = property(lambda self: self._get('sub'))
+    node_size = property(lambda self: self._get('node_size'))
+    v_edge_attr = property(lambda self: self._get('v_edge_attr'))
+    batch = property(lambda self: self._get('batch'))
+    diameter = property(lambda self: self._get('diameter'))
+    normal = property(lambda self: self._get('normal'))
+
+    for _k in ('pos', 'x', 'edge_index', 'edge_attr', 'super_index', 'sub', 'node_size',
+               'v_edge_attr', 'batch', 'diameter', 'normal'):
+        locals()[_k] = locals()[_k].setter(
+            (lambda k: lambda self, v: Data.__setattr__(self, k, v))(_k))
+    del _k
+
+    @property
+    def edge_keys(self):
+        """Keys starting with `edge_` other than edge_index / edge_attr
+        (reference src/data/data.py:158-164)."""
+        return [k for k in self.keys
+                if k.startswith('edge_') and k not in ('edge_index', 'edge_attr')]
+
+    def raise_if_edge_keys(self):
+        if len(self.edge_keys) > 0:
+            raise NotImplementedError(
+                f"Edge keys are not supported, stack them in `edge_attr`: {self.edge_keys}")
+
+    # derived ------------------------------------------------------------------
+    @property
+    def num_nodes(self):
+        for key in ('pos', 'x', 'super_index', 'node_size', 'batch'):
+            t = self._get(key)
+            if t is not None:
+                return int(t.shape[0])
+        if self.sub is not None:
+            return self.sub.num_clusters
+        if self.edge_index is not None and self.edge_index.numel() > 0:
+            return int(self.edge_index.max()) + 1
+        return 0
+
+    @property
+    def num_points(self):
+        return self.num_nodes
+
+    @property
+    def num_edges(self):
+        return 0 if self.edge_index is None else int(self.edge_index.shape[1])
+
+    @property
+    def has_edges(self):
+        return self.edge_index is not None and self.edge_index.shape[1] > 0
+
+    @property
+    def is_super(self):
+        return self.sub is not None
+
+    @property
+    def is_sub(self):
+        return self.super_index is not None
+
+    @property
+    def num_super(self):
+        return int(self.super_index.max()) + 1 if self.is_sub else 0
+
+    @property
+    def device(self):
+        for v in self._store.values():
+            if isinstance(v, (torch.Tensor, Cluster)):
+                return v.device
+        return torch.device('cpu')
+
+    def norm_index(self, mode='graph'):
+        """Index used by the index-based norms (reference src/data/data.py:103-130)."""
+        n, dev = self.num_nodes, self.device
+        batch = self.batch if self.batch is not None else \
+            self._cached_zeros(n, dev)
+        if mode == 'graph':
+            return batch
+        if mode == 'node':
+            return torch.arange(n, device=dev)
+        if mode == 'segment':
+            sup = self.super_index if self.super_index is not None else \
+                torch.zeros(n, dtype=torch.long, device=dev)
+            return sup * (batch.max() + 1) + batch
+        raise NotImplementedError(f"Unknown mode='{mode}'")
+
+    def _cached_zeros(self, n, dev):
+        z = self._store.get('_zero_batch')
+        if z is None or z.shape[0] != n or z.device != dev:
+            z = torch.zeros(n, dtype=torch.long, device=dev)
+            self._store['_zero_batch'] = z
+        return z
+
+    def add_keys_to(self, keys, to='x', strict=True, delete_after=False):
+        """Concatenate attributes `keys` into `to` (reference src/data/data.py:1097-1141)."""
+        if keys is None or len(keys) == 0:
+            return
+        prev = self._get(to)
+        feats = [prev] if prev is not None else []
+        for key in keys:
+            feat = self._get(key)
+            if feat is None:
+                if strict:
+                    raise Exception(f"Data should contain the attribute '{key}'")
+                continue
+            if delete_after:
+                delattr(self, key)
+            if prev is not None and prev.shape[0] != feat.shape[0]:
+                raise Exception(f"The tensors '{to}' and '{key}' can't be concatenated")
+            feats.append(feat.unsqueeze(-1) if feat.dim() == 1 else feat)
+        setattr(self, to, torch.cat(feats, dim=1))
+
+    def to(self, device, non_blocking=False):
+        out = Data()
+        for k, v in self._store.items():
+            if isinstance(v, torch.Tensor):
+                out._store[k] = v.to(device, non_blocking=non_blocking)
+            elif isinstance(v, Cluster):
+                out._store[k] = v.to(device, non_blocking=non_blocking)
+            else:
+                out._store[k] = v
+        return out
+
+    def cuda(self, non_blocking=False):
+        return self.to('cuda', non_blocking=non_blocking)
+
+    def cpu(self):
+        return self.to('cpu')
+
+    def clone(self):
+        out = Data()
+        out._store.update(self._store)
+        return out
+
+    def __repr__(self):
+        parts = []
+        for k, v in self._store.items():
+            if k.startswith('_'):
+                continue
+            parts.append(f"{k}={list(v.shape)}" if isinstance(v, torch.Tensor) else f"{k}={v}")
+        return f"Data({', '.join(parts)})"
+
+
+class Batch(Data):
+    """Disjoint union of Data objects of one level.  Node-indexed integer
+    attributes are offset like reference Data.__inc__ (src/data/data.py:267-274):
+    edge_index by the node count, super_index by the parent count, Cluster.points
+    by the child count; `batch` records the item of every node."""
+
+    @classmethod
+    def from_data_list(cls, data_list, num_super_list=None):
+        out = cls()
+        keys = [k for k in data_list[0].keys if not k.startswith('_')]
+        n_nodes = [d.num_nodes for d in data_list]
+        node_off = [0]
+        for n in n_nodes:
+            node_off.append(node_off[-1] + n)
+        if num_super_list is None and data_list[0].super_index is not None:
+            num_super_list = [int(d.super_index.max()) + 1 for d in data_list]
+        sup_off = [0]
+        for n in (num_super_list or []):
+            sup_off.append(sup_off[-1] + n)
+        for k in keys:
+            vals = [d[k] for d in data_list]
+            if k == 'edge_index':
+                out[k] = torch.cat([v + node_off[i] for i, v in enumerate(vals)], dim=1)
+            elif k == 'super_index':
+                out[k] = torch.cat([v + sup_off[i] for i, v in enumerate(vals)])
+            elif k == 'sub':
+                child_off, ptrs, pts = 0, [], []
+                ptr_off = 0
+                for i, c in enumerate(vals):
+                    p = c.pointers + ptr_off
+                    ptrs.append(p if i == 0 else p[1:])
+                    pts.append(c.points + child_off)
+                    ptr_off += c.num_points
+                    child_off += c.num_points
+                out[k] = Cluster(torch.cat(ptrs), torch.cat(pts))
+            elif isinstance(vals[0], torch.Tensor):
+                out[k] = torch.cat(vals, dim=0)
+            else:
+                out[k] = vals[0]
+        dev = out.device
+        out['batch'] = torch.repeat_interleave(
+            torch.arange(len(data_list), device=dev),
+            torch.tensor(n_nodes, device=dev))
+        out['_num_graphs'] = len(data_list)
+        return out
+
+    @property
+    def num_graphs(self):
+        return self._store.get('_num_graphs', 1)

@@ -1,0 +1,106 @@
+"""Normalisation layers of the hot path (API of reference src/nn/norm.py).
+
+`UnitSphereNorm` and `GraphNorm` run hand-written CUDA segment kernels
+(csrc/segment.cu, csrc/norm.cu).  `GraphNorm` reproduces
+torch_geometric.nn.norm.GraphNorm (the norm selected by
+configs/model/semantic/_attention.yaml:9-11 and spt.yaml:19-21) including its
+parameter names (`weight`, `bias`, `mean_scale`) so reference checkpoints load.
+"""
+import torch
+from torch import nn
+
+from .. import ops
+
+__all__ = ['BatchNorm', 'UnitSphereNorm', 'GraphNorm', 'LayerNorm',
+           'INDEX_BASED_NORMS']
+
+
+class BatchNorm(nn.Module):
+    """BatchNorm1d usable on [N, C] (and [B, N, C]) tensors; dense library op,
+    kept as torch (reference src/nn/norm.py:20-50; not used by the default SPT
+    configs, which select GraphNorm)."""
+
+    def __init__(self, num_features, **kwargs):
+        super().__init__()
+        self.batch_norm = nn.BatchNorm1d(num_features, **kwargs)
+
+    def forward(self, x):
+        if x.dim() == 2:
+            return self.batch_norm(x)
+        if x.dim() == 3:
+            return self.batch_norm(x.transpose(1, 2)).transpose(1, 2)
+        raise ValueError(f"Non supported number of dimensions {x.dim()}")
+
+
+class UnitSphereNorm(nn.Module):
+    """Normalise node positions inside their parent segment to a unit-diameter
+    sphere: per-segment bbox -> diameter, `w`-weighted centroid -> centre
+    (reference src/nn/norm.py:53-138).
+
+    forward(pos, idx, w=None, num_super=None) -> (pos_normalised, diameter[Np,1])
+    """
+
+    def __init__(self, log_diameter=False):
+        super().__init__()
+        self.log_diameter = log_diameter
+
+    def forward(self, pos, idx, w=None, num_super=None):
+        pos, diameter = ops.unit_sphere_norm(pos, idx, w=w, num_super=num_super)
+        if self.log_diameter:
+            diameter = torch.log(diameter + 1)
+        return pos, diameter
+
+
+class GraphNorm(nn.Module):
+    """x -> weight * (x - mean_scale * mean_g) / sqrt(var_g + eps) + bias, with
+    mean/var over the nodes of each graph g = batch[i] (PyG GraphNorm, called as
+    `norm(x, batch=index)` from src/nn/transformer.py:258-265, src/nn/mlp.py:89-94)."""
+
+    def __init__(self, in_channels, eps=1e-5):
+        super().__init__()
+        self.in_channels = in_channels
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(in_channels))
+        self.bias = nn.Parameter(torch.zeros(in_channels))
+        self.mean_scale = nn.Parameter(torch.ones(in_channels))
+
+    def reset_parameters(self):
+        nn.init.ones_(self.weight)
+        nn.init.zeros_(self.bias)
+        nn.init.ones_(self.mean_scale)
+
+    def forward(self, x, batch=None, batch_size=None):
+        return ops.graph_norm(x, self.weight, self.bias, self.mean_scale, batch=batch,
+                              batch_size=batch_size, eps=self.eps)
+
+    def __repr__(self):
+        return f'{self.__class__.__name__}({self.in_channels})'
+
+
+class LayerNorm(nn.Module):
+    """Per-node LayerNorm (mode='node'; dense torch op).  The graph-wise mode of
+    PyG's LayerNorm (code default of reference src/nn/transformer.py:137, never
+    selected by the shipped configs) is not built yet and raises."""
+
+    def __init__(self, in_channels, eps=1e-5, affine=True, mode='node'):
+        super().__init__()
+        if mode != 'node':
+            raise NotImplementedError(
+                "LayerNorm(mode='graph') is not implemented in the B200 path yet; "
+                "the shipped configs use GraphNorm")
+        self.in_channels = in_channels
+        self.eps = eps
+        self.mode = mode
+        if affine:
+            self.weight = nn.Parameter(torch.ones(in_channels))
+            self.bias = nn.Parameter(torch.zeros(in_channels))
+        else:
+            self.register_parameter('weight', None)
+            self.register_parameter('bias', None)
+
+    def forward(self, x, batch=None, batch_size=None):
+        return torch.nn.functional.layer_norm(
+            x, (self.in_channels,), self.weight, self.bias, self.eps)
+
+
+INDEX_BASED_NORMS = (LayerNorm, GraphNorm)

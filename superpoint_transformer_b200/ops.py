@@ -1,0 +1,596 @@
+"""torch-facing wrappers of the C ABI: index structures + autograd Functions.
+
+PyTorch is plumbing here (device memory, streams, autograd bookkeeping); all
+the arithmetic of the hot path happens in libspt_b200.so.  Every function
+refuses non-CUDA tensors: there is no CPU fallback.
+"""
+import weakref
+
+import torch
+
+from . import _lib
+
+REDUCE = {"sum": 0, "add": 0, "mean": 1, "max": 2, "min": 3}
+SCALE_D_TIMES_G, SCALE_D_PLUS_G, SCALE_D, SCALE_G, SCALE_CONST = range(5)
+
+_LAUNCHES = 0  # kernels-launching ABI calls issued (bench.py reads it)
+
+
+def launch_count():
+    return _LAUNCHES
+
+
+def _count(n=1):
+    global _LAUNCHES
+    _LAUNCHES += n
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "superpoint_transformer_b200 ops run on CUDA tensors only "
+                "(no CPU fallback); got a tensor on " + str(t.device))
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t):
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        raise TypeError(f"expected float32 tensor, got {t.dtype}")
+    return t.contiguous()
+
+
+def _i64c(t):
+    if t is None:
+        return None
+    if t.dtype != torch.int64:
+        t = t.long()
+    return t.contiguous()
+
+
+# ---------------------------------------------------------------------------
+# index structures
+# ---------------------------------------------------------------------------
+class SegmentIndex:
+    """Stable CSR of `n` items grouped by `key` in [0, num_groups).
+
+    ptr  int32 [num_groups+1], perm int32 [n] (= stable argsort(key)),
+    other_sorted int32 [n] (optional payload gathered through perm).
+    With key=super_index this equals the reference `Cluster.pointers/points`
+    (src/data/cluster.py:19-77).
+    """
+
+    __slots__ = ("ptr", "perm", "other_sorted", "n", "num_groups", "_err", "__weakref__")
+
+    def __init__(self, ptr, perm, other_sorted, n, num_groups, err):
+        self.ptr, self.perm, self.other_sorted = ptr, perm, other_sorted
+        self.n, self.num_groups, self._err = n, num_groups, err
+
+    def num_invalid_keys(self):
+        """Host sync: number of keys that were outside [0, num_groups)."""
+        return int(self._err[0].item())
+
+
+def group_index(key, num_groups, other=None):
+    lib = _lib.load()
+    _require_cuda(key, other)
+    key = _i64c(key)
+    other = _i64c(other)
+    n = key.numel()
+    dev = key.device
+    ptr = torch.empty(num_groups + 1, dtype=torch.int32, device=dev)
+    perm = torch.empty(n, dtype=torch.int32, device=dev)
+    osort = torch.empty(n, dtype=torch.int32, device=dev) if other is not None else None
+    nbytes = lib.spt_group_index_workspace_bytes(n, num_groups)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.spt_group_index(_p(key), _p(other), n, num_groups, _p(ptr), _p(perm),
+                                 _p(osort), _p(ws), nbytes, _stream())
+    _lib.check(rc, "spt_group_index")
+    _count(8)
+    err = ws[:4].view(torch.int32)
+    return SegmentIndex(ptr, perm, osort, n, num_groups, err)
+
+
+class GraphIndex:
+    """CSR (by source) + CSC (by target) of an attention graph.
+
+    rowptr/col/perm: edges grouped by source row (stable), col = target of each
+    CSR slot, perm = original edge id of each CSR slot.
+    csc_ptr/csc_src/csc2csr: edges grouped by target; for each CSC slot the
+    source row and the CSR slot of the same edge.
+    """
+
+    __slots__ = ("rowptr", "col", "perm", "csc_ptr", "csc_src", "csc2csr",
+                 "num_rows", "num_targets", "E", "__weakref__")
+
+
+def build_graph_index(edge_index, num_rows, num_targets=None):
+    lib = _lib.load()
+    _require_cuda(edge_index)
+    num_targets = num_rows if num_targets is None else num_targets
+    edge_index = _i64c(edge_index)
+    src, dst = edge_index[0], edge_index[1]
+    E = src.numel()
+    csr = group_index(src, num_rows, other=dst)
+    csc = group_index(dst, num_targets, other=src)
+    g = GraphIndex()
+    g.rowptr, g.col, g.perm = csr.ptr, csr.other_sorted, csr.perm
+    g.csc_ptr, g.csc_src = csc.ptr, csc.other_sorted
+    inv = torch.empty(E, dtype=torch.int32, device=src.device)
+    c2c = torch.empty(E, dtype=torch.int32, device=src.device)
+    with torch.cuda.device(src.device):
+        _lib.check(lib.spt_invert_permutation(_p(csr.perm), E, _p(inv), _stream()),
+                   "spt_invert_permutation")
+        _lib.check(lib.spt_gather_i32(_p(inv), _p(csc.perm), E, _p(c2c), _stream()),
+                   "spt_gather_i32")
+    _count(2)
+    g.csc2csr = c2c
+    g.num_rows, g.num_targets, g.E = num_rows, num_targets, E
+    return g
+
+
+class _IdentityCache:
+    """Cache keyed by tensor identity (id + version + weakref check).  The
+    reference rebuilds nothing because it has no index structure; here the CSR
+    of a level is shared by every block of a stage, forward and backward."""
+
+    def __init__(self, maxsize=64):
+        self._d = {}
+        self._maxsize = maxsize
+
+    def get(self, tensor, extra, builder):
+        key = (id(tensor), tensor._version, tuple(tensor.shape), extra)
+        hit = self._d.get(key)
+        if hit is not None:
+            ref, val = hit
+            if ref() is tensor:
+                return val
+        val = builder()
+        # drop entries whose key tensor died (frees cached device buffers), then
+        # the oldest if still full
+        for k in [k for k, (r, _) in self._d.items() if r() is None]:
+            del self._d[k]
+        while len(self._d) >= self._maxsize:
+            del self._d[next(iter(self._d))]
+        self._d[key] = (weakref.ref(tensor), val)
+        return val
+
+    def put(self, tensor, extra, val):
+        key = (id(tensor), tensor._version, tuple(tensor.shape), extra)
+        self._d[key] = (weakref.ref(tensor), val)
+
+    def clear(self):
+        self._d.clear()
+
+
+_graph_cache = _IdentityCache()
+_segment_cache = _IdentityCache()
+_numseg_cache = _IdentityCache(256)
+_permuted_cache = _IdentityCache()
+
+
+def clear_caches():
+    for c in (_graph_cache, _segment_cache, _numseg_cache, _permuted_cache):
+        c.clear()
+
+
+def graph_index(edge_index, num_rows, num_targets=None):
+    return _graph_cache.get(edge_index, ("g", num_rows, num_targets),
+                            lambda: build_graph_index(edge_index, num_rows, num_targets))
+
+
+def segment_index(index, num_groups):
+    return _segment_cache.get(index, ("s", num_groups),
+                              lambda: group_index(index, num_groups))
+
+
+def register_segment_index(index, num_groups, seg):
+    _segment_cache.put(index, ("s", num_groups), seg)
+
+
+def num_segments(batch):
+    """int(batch.max()) + 1 with one host sync per distinct tensor (the PyG
+    GraphNorm the reference uses syncs on every call)."""
+    if batch is None:
+        return 1
+    return _numseg_cache.get(batch, "n",
+                             lambda: (int(batch.max().item()) + 1) if batch.numel() else 1)
+
+
+def register_num_segments(batch, n):
+    if batch is not None:
+        _numseg_cache.put(batch, "n", int(n))
+
+
+# ---------------------------------------------------------------------------
+# row gathers
+# ---------------------------------------------------------------------------
+def _gather_rows(x, idx):
+    lib = _lib.load()
+    n_out, C = idx.numel(), x.shape[1]
+    out = torch.empty((n_out, C), dtype=x.dtype, device=x.device)
+    fn = lib.spt_gather_rows_i32 if idx.dtype == torch.int32 else lib.spt_gather_rows_i64
+    with torch.cuda.device(x.device):
+        _lib.check(fn(_p(x), _p(idx), n_out, C, _p(out), _stream()), "spt_gather_rows")
+    _count()
+    return out
+
+
+class _PermuteRows(torch.autograd.Function):
+    """out[j] = x[perm[j]] with perm a permutation; backward scatters back through
+    the inverse permutation (a gather, deterministic)."""
+
+    @staticmethod
+    def forward(ctx, x, perm):
+        ctx.save_for_backward(perm)
+        return _gather_rows(x, perm)
+
+    @staticmethod
+    def backward(ctx, g):
+        (perm,) = ctx.saved_tensors
+        lib = _lib.load()
+        g = _f32c(g)
+        inv = torch.empty_like(perm)
+        with torch.cuda.device(g.device):
+            _lib.check(lib.spt_invert_permutation(_p(perm), perm.numel(), _p(inv), _stream()),
+                       "spt_invert_permutation")
+        _count()
+        return _gather_rows(g, inv), None
+
+
+def permute_rows(x, perm):
+    _require_cuda(x, perm)
+    return _PermuteRows.apply(_f32c(x), perm)
+
+
+def permute_rows_cached(x, perm):
+    """edge_attr is shared by all blocks of a stage (src/nn/stage.py:277-280): the
+    CSR-ordered copy is made once and its gradient accumulates in CSR order."""
+    return _permuted_cache.get(x, ("p", id(perm)), lambda: permute_rows(x, perm))
+
+
+class _IndexUnpool(torch.autograd.Function):
+    """x_parent.index_select(0, idx) (src/nn/unpool.py:12-13); backward is a CSR
+    segment-sum instead of an atomic index_add."""
+
+    @staticmethod
+    def forward(ctx, x, idx):
+        ctx.num_parents = x.shape[0]
+        ctx.save_for_backward(idx)
+        return _gather_rows(x, idx)
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        seg = segment_index(idx, ctx.num_parents)
+        out, _ = _segment_pool_fwd(_f32c(g), seg, "sum")
+        return out, None
+
+
+def index_unpool(x, idx):
+    _require_cuda(x, idx)
+    return _IndexUnpool.apply(_f32c(x), _i64c(idx))
+
+
+# ---------------------------------------------------------------------------
+# segment pooling
+# ---------------------------------------------------------------------------
+def _segment_pool_fwd(x, seg, reduce):
+    lib = _lib.load()
+    r = REDUCE[reduce]
+    Np, C = seg.num_groups, x.shape[1]
+    out = torch.empty((Np, C), dtype=torch.float32, device=x.device)
+    arg = torch.empty((Np, C), dtype=torch.int32, device=x.device) if r >= 2 else None
+    with torch.cuda.device(x.device):
+        _lib.check(lib.spt_segment_pool_fwd(_p(x), _p(seg.ptr), _p(seg.perm), Np, C, r,
+                                            _p(out), _p(arg), _stream()),
+                   "spt_segment_pool_fwd")
+    _count()
+    return out, arg
+
+
+class _SegmentPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, index, seg, reduce):
+        out, arg = _segment_pool_fwd(x, seg, reduce)
+        ctx.reduce = reduce
+        ctx.seg = seg
+        ctx.shape = x.shape
+        ctx.save_for_backward(index, arg if arg is not None else index)
+        ctx.has_arg = arg is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        index, arg = ctx.saved_tensors
+        lib = _lib.load()
+        g = _f32c(g)
+        Nc, C = ctx.shape
+        dx = torch.empty((Nc, C), dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            _lib.check(lib.spt_segment_pool_bwd(_p(g), _p(index), _p(ctx.seg.ptr),
+                                                _p(arg) if ctx.has_arg else None, Nc, C,
+                                                REDUCE[ctx.reduce], _p(dx), _stream()),
+                       "spt_segment_pool_bwd")
+        _count()
+        return dx, None, None, None
+
+
+def segment_pool(x, index, num_pool, reduce="max", seg=None):
+    """reduce over children of each parent; PyG *Aggregation semantics
+    (src/nn/pool.py:44-82): empty parents -> 0, max/min gradient to one arg."""
+    _require_cuda(x, index)
+    index = _i64c(index)
+    if seg is None:
+        seg = segment_index(index, num_pool)
+    return _SegmentPool.apply(_f32c(x), index, seg, reduce)
+
+
+def node_size(super_index, num_parents, child_size=None):
+    """NAG.get_sub_size step (src/data/nag.py:59-110): exact int64 sums."""
+    lib = _lib.load()
+    _require_cuda(super_index, child_size)
+    super_index = _i64c(super_index)
+    seg = segment_index(super_index, num_parents)
+    out = torch.empty(num_parents, dtype=torch.int64, device=super_index.device)
+    vals = _i64c(child_size)
+    with torch.cuda.device(super_index.device):
+        _lib.check(lib.spt_segment_sum_i64(_p(vals), _p(seg.ptr), _p(seg.perm), num_parents,
+                                           _p(out), _stream()), "spt_segment_sum_i64")
+    _count()
+    return out
+
+
+# ---------------------------------------------------------------------------
+# UnitSphereNorm
+# ---------------------------------------------------------------------------
+def unit_sphere_norm(pos, idx=None, w=None, num_super=None):
+    """(pos_normalised [N,3], diameter [Np,1]); src/nn/norm.py:67-138. No grad
+    (pos never requires grad on the reference path)."""
+    lib = _lib.load()
+    _require_cuda(pos, idx, w)
+    pos = _f32c(pos.detach())
+    N = pos.shape[0]
+    dev = pos.device
+    wf = None if w is None else w.detach().float().contiguous()
+    if idx is None:
+        Np = 1
+        ptr = torch.tensor([0, N], dtype=torch.int32, device=dev)
+        points, parent = None, None
+    else:
+        idx = _i64c(idx)
+        Np = int(num_super) if num_super is not None else num_segments(idx)
+        seg = segment_index(idx, Np)
+        ptr, points, parent = seg.ptr, seg.perm, idx
+    out = torch.empty_like(pos)
+    diam = torch.empty((Np, 1), dtype=torch.float32, device=dev)
+    nbytes = lib.spt_unitsphere_workspace_bytes(Np)
+    ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.spt_unitsphere_fwd(_p(pos), _p(parent), _p(ptr), _p(points), _p(wf),
+                                          N, Np, _p(out), _p(diam), _p(ws), nbytes,
+                                          _stream()), "spt_unitsphere_fwd")
+    _count(2)
+    return out, diam
+
+
+# ---------------------------------------------------------------------------
+# GraphNorm
+# ---------------------------------------------------------------------------
+class _GraphNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, mean_scale, batch, B, eps):
+        lib = _lib.load()
+        N, C = x.shape
+        dev = x.device
+        y = torch.empty_like(x)
+        mean = torch.empty((B, C), dtype=torch.float32, device=dev)
+        rstd = torch.empty((B, C), dtype=torch.float32, device=dev)
+        nbytes = lib.spt_graphnorm_workspace_bytes(B, C)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.spt_graphnorm_fwd(_p(x), _p(batch), N, C, B, _p(weight), _p(bias),
+                                             _p(mean_scale), eps, _p(y), _p(mean), _p(rstd),
+                                             _p(ws), nbytes, _stream()), "spt_graphnorm_fwd")
+        _count(5)
+        ctx.B = B
+        ctx.has_batch = batch is not None
+        ctx.save_for_backward(x, weight, mean_scale, mean, rstd,
+                              batch if batch is not None else mean)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, mean_scale, mean, rstd, batch = ctx.saved_tensors
+        if not ctx.has_batch:
+            batch = None
+        lib = _lib.load()
+        dy = _f32c(dy)
+        N, C = x.shape
+        dev = x.device
+        dx = torch.empty_like(x)
+        dw = torch.empty(C, dtype=torch.float32, device=dev)
+        db = torch.empty(C, dtype=torch.float32, device=dev)
+        dms = torch.empty(C, dtype=torch.float32, device=dev)
+        nbytes = lib.spt_graphnorm_workspace_bytes(ctx.B, C)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.spt_graphnorm_bwd(_p(x), _p(dy), _p(batch), N, C, ctx.B, _p(weight),
+                                             _p(mean_scale), _p(mean), _p(rstd), _p(dx),
+                                             _p(dw), _p(db), _p(dms), _p(ws), nbytes,
+                                             _stream()), "spt_graphnorm_bwd")
+        _count(5)
+        return dx, dw, db, dms, None, None, None
+
+
+def graph_norm(x, weight, bias, mean_scale, batch=None, batch_size=None, eps=1e-5):
+    """PyG GraphNorm semantics."""
+    _require_cuda(x, weight, bias, mean_scale, batch)
+    batch = _i64c(batch)
+    B = int(batch_size) if batch_size is not None else num_segments(batch)
+    return _GraphNorm.apply(_f32c(x), _f32c(weight), _f32c(bias), _f32c(mean_scale), batch,
+                            B, float(eps))
+
+
+# ---------------------------------------------------------------------------
+# fused attention core
+# ---------------------------------------------------------------------------
+class _AttnCore(torch.autograd.Function):
+    """q/k/v come either fused as qkv [N, 2HD+C] (kv=None) or as q [R,HD] and
+    kv [T, HD+C].  Returns (agg_v [R,C], abar [R,H,F] or None, sump [R,H])."""
+
+    @staticmethod
+    def forward(ctx, qsrc, kv, a, Wq, bq, Wk, bk, g, H, D, scale_mode, scale_value,
+                want_abar):
+        lib = _lib.load()
+        dev = qsrc.device
+        HD = H * D
+        fused = kv is None
+        if fused:
+            ld = qsrc.shape[1]
+            C = ld - 2 * HD
+            qp, kp, vp = qsrc.data_ptr(), qsrc.data_ptr() + 4 * HD, qsrc.data_ptr() + 8 * HD
+            ldq = ldk = ldv = ld
+        else:
+            C = kv.shape[1] - HD
+            qp, kp, vp = qsrc.data_ptr(), kv.data_ptr(), kv.data_ptr() + 4 * HD
+            ldq, ldk, ldv = qsrc.shape[1], kv.shape[1], kv.shape[1]
+        Dv = C // H
+        F = a.shape[1] if a is not None else 0
+        R = g.num_rows
+        agg = torch.empty((R, C), dtype=torch.float32, device=dev)
+        abar = (torch.empty((R, H, F), dtype=torch.float32, device=dev)
+                if (want_abar and a is not None) else None)
+        sump = torch.empty((R, H), dtype=torch.float32, device=dev)
+        m = torch.empty((R, H), dtype=torch.float32, device=dev)
+        z = torch.empty((R, H), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.spt_attn_fwd(qp, ldq, kp, ldk, vp, ldv, _p(a), _p(g.rowptr),
+                                        _p(g.col), R, g.E, H, D, Dv, F, _p(Wq), _p(bq),
+                                        _p(Wk), _p(bk), scale_mode, scale_value, _p(agg),
+                                        _p(abar), _p(sump), _p(m), _p(z), _stream()),
+                       "spt_attn_fwd")
+        _count()
+        ctx.g, ctx.H, ctx.D, ctx.Dv, ctx.F = g, H, D, Dv, F
+        ctx.scale_mode, ctx.scale_value = scale_mode, scale_value
+        ctx.fused = fused
+        ctx.opt = (kv is not None, a is not None, Wq is not None, bq is not None,
+                   Wk is not None, bk is not None, abar is not None)
+        dummy = m
+        ctx.save_for_backward(qsrc, kv if kv is not None else dummy,
+                              a if a is not None else dummy,
+                              Wq if Wq is not None else dummy,
+                              bq if bq is not None else dummy,
+                              Wk if Wk is not None else dummy,
+                              bk if bk is not None else dummy, m, z, agg,
+                              abar if abar is not None else dummy)
+        ctx.mark_non_differentiable(sump)
+        if abar is None:
+            return agg, None, sump
+        return agg, abar, sump
+
+    @staticmethod
+    def backward(ctx, d_agg, d_abar, _d_sump):
+        lib = _lib.load()
+        qsrc, kv, a, Wq, bq, Wk, bk, m, z, agg, abar = ctx.saved_tensors
+        has_kv, has_a, has_Wq, has_bq, has_Wk, has_bk, has_abar = ctx.opt
+        kv = kv if has_kv else None
+        a = a if has_a else None
+        Wq = Wq if has_Wq else None
+        bq = bq if has_bq else None
+        Wk = Wk if has_Wk else None
+        bk = bk if has_bk else None
+        abar = abar if has_abar else None
+        g, H, D, Dv, F = ctx.g, ctx.H, ctx.D, ctx.Dv, ctx.F
+        HD, C = H * D, H * Dv
+        dev = qsrc.device
+        d_agg = _f32c(d_agg) if d_agg is not None else torch.zeros_like(agg)
+        d_abar = _f32c(d_abar) if (d_abar is not None and abar is not None) else None
+        if ctx.fused:
+            dqkv = torch.empty_like(qsrc)
+            ld = qsrc.shape[1]
+            qp, kp, vp = qsrc.data_ptr(), qsrc.data_ptr() + 4 * HD, qsrc.data_ptr() + 8 * HD
+            dqp, dkp, dvp = dqkv.data_ptr(), dqkv.data_ptr() + 4 * HD, dqkv.data_ptr() + 8 * HD
+            ldq = ldk = ldv = lddq = lddk = lddv = ld
+            dkv = None
+        else:
+            dqkv = torch.empty_like(qsrc)
+            dkv = torch.empty_like(kv)
+            qp, kp, vp = qsrc.data_ptr(), kv.data_ptr(), kv.data_ptr() + 4 * HD
+            dqp, dkp, dvp = dqkv.data_ptr(), dkv.data_ptr(), dkv.data_ptr() + 4 * HD
+            ldq, ldk, ldv = qsrc.shape[1], kv.shape[1], kv.shape[1]
+            lddq, lddk, lddv = ldq, ldk, ldv
+        need = ctx.needs_input_grad
+        da = torch.empty_like(a) if (a is not None and need[2]) else None
+        dWq = torch.zeros_like(Wq) if (Wq is not None and a is not None) else None
+        dbq = torch.zeros_like(bq) if (bq is not None and dWq is not None) else None
+        dWk = torch.zeros_like(Wk) if (Wk is not None and a is not None) else None
+        dbk = torch.zeros_like(bk) if (bk is not None and dWk is not None) else None
+        E = g.E
+        Pb = torch.empty((max(E, 1), H), dtype=torch.float32, device=dev)
+        G = torch.empty((max(E, 1), 2 * HD), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.spt_attn_bwd(
+                qp, ldq, kp, ldk, vp, ldv, _p(a), _p(g.rowptr), _p(g.col), _p(g.csc_ptr),
+                _p(g.csc_src), _p(g.csc2csr), g.num_rows, g.num_targets, E, H, D, Dv, F,
+                _p(Wq), _p(bq), _p(Wk), _p(bk), ctx.scale_mode, ctx.scale_value, _p(m), _p(z),
+                _p(agg), _p(abar), _p(d_agg), _p(d_abar), dqp, lddq, dkp, lddk, dvp, lddv,
+                _p(da), _p(dWq), _p(dbq), _p(dWk), _p(dbk), _p(Pb), _p(G), _stream()),
+                "spt_attn_bwd")
+        _count(3)
+        if bq is not None and dbq is None:
+            dbq = torch.zeros_like(bq)
+        if bk is not None and dbk is None:
+            dbk = torch.zeros_like(bk)
+        if Wq is not None and dWq is None:
+            dWq = torch.zeros_like(Wq)
+        if Wk is not None and dWk is None:
+            dWk = torch.zeros_like(Wk)
+        return (dqkv, dkv, da, dWq, dbq, dWk, dbk, None, None, None, None, None, None)
+
+
+def attention_core(qsrc, kv, a_csr, Wq, bq, Wk, bk, graph, num_heads, qk_dim,
+                   scale_mode=SCALE_D_TIMES_G, scale_value=1.0, want_abar=True):
+    """See include/spt_b200.h:spt_attn_fwd.  `a_csr` must already be in CSR order
+    (permute_rows(edge_attr, graph.perm))."""
+    _require_cuda(qsrc, kv, a_csr, Wq, bq, Wk, bk)
+    return _AttnCore.apply(_f32c(qsrc), _f32c(kv), _f32c(a_csr), _f32c(Wq), _f32c(bq),
+                           _f32c(Wk), _f32c(bk), graph, int(num_heads), int(qk_dim),
+                           int(scale_mode), float(scale_value), bool(want_abar))
+
+
+# ---------------------------------------------------------------------------
+# on-the-fly edge features
+# ---------------------------------------------------------------------------
+def horizontal_edge_features(se, edge_attr7, pos, normal, log_length, log_surface,
+                             log_volume, log_size, num_nodes, add_self_loops=False):
+    """(edge_index [2, 2Eh(+N)], edge_attr [.., 18]); see spt_edge_features_fwd."""
+    lib = _lib.load()
+    _require_cuda(se, edge_attr7, pos, normal, log_length, log_surface, log_volume, log_size)
+    se = _i64c(se)
+    Eh = se.shape[1]
+    dev = se.device
+    f = lambda t: t.detach().float().contiguous()  # noqa: E731  (fp16 inputs allowed)
+    ea, pos, normal = f(edge_attr7), f(pos), f(normal)
+    ll, ls, lv, lz = f(log_length).view(-1), f(log_surface).view(-1), f(log_volume).view(-1), \
+        f(log_size).view(-1)
+    E_out = 2 * Eh + (num_nodes if add_self_loops else 0)
+    ei = torch.empty((2, E_out), dtype=torch.int64, device=dev)
+    out = torch.empty((E_out, 18), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.spt_edge_features_fwd(_p(se), _p(ea), _p(pos), _p(normal), _p(ll), _p(ls),
+                                             _p(lv), _p(lz), Eh, num_nodes,
+                                             1 if add_self_loops else 0, _p(ei), _p(out),
+                                             _stream()), "spt_edge_features_fwd")
+    _count()
+    return ei, out
