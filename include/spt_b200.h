@@ -198,27 +198,34 @@ int spt_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk,
                  float* abar /*[R,H,F] nullable*/, float* sump /*[R,H]*/,
                  float* m /*[R,H]*/, float* z /*[R,H]*/, void* stream);
 
-/* Backward of spt_attn_fwd. Inputs: forward inputs, saved m/z, forward outputs
- * agg_v/abar, upstream d_agg_v [R,C] and d_abar [R,H,F] (nullable).
- * Outputs (all fully written, no pre-zeroing needed unless stated):
- *   dq [R, ldq-strided], dk/dv [num_targets rows], da [E,F] (CSR order),
- *   dWq,dWk [HD,F], dbq,dbk [HD]  (ACCUMULATED into; caller zero-fills),
- * Scratch (caller provided): P [E,H], G [E,2HD].
- * csc_ptr/csc_src/csc2csr: edges grouped by target (stable), giving for every
- * target t its incoming CSR slots and their source rows.                     */
-int spt_attn_bwd(const float* q, int64_t ldq, const float* k, int64_t ldk,
-                 const float* v, int64_t ldv, const float* a,
-                 const int32_t* rowptr, const int32_t* col,
-                 const int32_t* csc_ptr, const int32_t* csc_src,
-                 const int32_t* csc2csr, int64_t num_rows, int64_t num_targets,
-                 int64_t E, int H, int D, int Dv, int F, const float* Wq,
-                 const float* bq, const float* Wk, const float* bk,
-                 int scale_mode, float scale_value, const float* m,
-                 const float* z, const float* agg_v, const float* abar,
-                 const float* d_agg_v, const float* d_abar /*nullable*/,
-                 float* dq, int64_t lddq, float* dk, int64_t lddk, float* dv,
-                 int64_t lddv, float* da /*nullable*/, float* dWq, float* dbq,
-                 float* dWk, float* dbk, float* P, float* G, void* stream);
+/* Backward of spt_attn_fwd, three launches so each can be timed on its own:
+ *  (1) rows    : per CSR row, recompute p from (m, z); writes dq [R rows, lddq],
+ *                da [E,F] (CSR order, nullable) and the per-edge scratch
+ *                P [E,H] (= p) and G [E,2HD] (= [dq_e | dk_e]).
+ *  (2) targets : per target t (edges grouped by target: csc_ptr/csc_src/csc2csr,
+ *                csc2csr = CSR slot of each CSC slot), gathers
+ *                dv[t] = sum p * d_agg_v[src], dk[t] = sum dk_e — no atomics;
+ *                every target row is written (zeros when it has no incoming edge).
+ *  (3) weights : dWq,dWk [HD,F] += G^T a ; dbq,dbk [HD] += colsum(G)
+ *                (ACCUMULATED with fp32 atomics; the caller zero-fills).        */
+int spt_attn_bwd_rows(const float* q, int64_t ldq, const float* k, int64_t ldk,
+                      const float* v, int64_t ldv, const float* a,
+                      const int32_t* rowptr, const int32_t* col, int64_t num_rows,
+                      int64_t E, int H, int D, int Dv, int F, const float* Wq,
+                      const float* bq, const float* Wk, const float* bk,
+                      int scale_mode, float scale_value, const float* m,
+                      const float* z, const float* agg_v, const float* abar,
+                      const float* d_agg_v, const float* d_abar /*nullable*/,
+                      float* dq, int64_t lddq, float* da /*nullable*/, float* P,
+                      float* G, void* stream);
+int spt_attn_bwd_targets(const int32_t* csc_ptr, const int32_t* csc_src,
+                         const int32_t* csc2csr, int64_t num_targets, int64_t E,
+                         int H, int D, int Dv, const float* P, const float* G,
+                         const float* d_agg_v, float* dk, int64_t lddk, float* dv,
+                         int64_t lddv, void* stream);
+int spt_attn_bwd_weights(const float* G, const float* a, int64_t E, int H, int D,
+                         int F, float* dWq, float* dbq, float* dWk, float* dbk,
+                         void* stream);
 
 /* ------------------------------------------------------------------------- *
  *  On-the-fly horizontal edge features                                      *

@@ -50,14 +50,16 @@ SIGNATURES = {
                              c_ptr, c_i64, c_i64, c_int, c_int, c_int, c_int, c_ptr,
                              c_ptr, c_ptr, c_ptr, c_int, c_f32, c_ptr, c_ptr, c_ptr,
                              c_ptr, c_ptr, c_ptr]),
-    "spt_attn_bwd": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr,  # q k v a
-                             c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,               # csr, csc
-                             c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int,  # sizes
-                             c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_f32,         # W, scale
-                             c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,         # m z agg abar dagg dabar
-                             c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64,         # dq dk dv
-                             c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,               # da dWq dbq dWk dbk
-                             c_ptr, c_ptr, c_ptr]),                            # P G stream
+    "spt_attn_bwd_rows": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr,  # q k v a
+                                  c_ptr, c_ptr, c_i64, c_i64,                        # csr, sizes
+                                  c_int, c_int, c_int, c_int,                        # H D Dv F
+                                  c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_f32,          # W, scale
+                                  c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,          # m z agg abar dagg dabar
+                                  c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),        # dq da P G stream
+    "spt_attn_bwd_targets": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int, c_int, c_int,
+                                     c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_ptr]),
+    "spt_attn_bwd_weights": (c_int, [c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_ptr,
+                                     c_ptr, c_ptr, c_ptr]),
     "spt_edge_features_fwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                       c_ptr, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr]),
 }

@@ -491,63 +491,78 @@ int spt_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const
   return check_launch("attn_fwd");
 }
 
-int spt_attn_bwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v,
-                 int64_t ldv, const float* a, const int32_t* rowptr, const int32_t* col,
-                 const int32_t* csc_ptr, const int32_t* csc_src, const int32_t* csc2csr,
-                 int64_t num_rows, int64_t num_targets, int64_t E, int H, int D, int Dv,
-                 int F, const float* Wq, const float* bq, const float* Wk, const float* bk,
-                 int scale_mode, float scale_value, const float* m, const float* z,
-                 const float* agg_v, const float* abar, const float* d_agg_v,
-                 const float* d_abar, float* dq, int64_t lddq, float* dk, int64_t lddk,
-                 float* dv, int64_t lddv, float* da, float* dWq, float* dbq, float* dWk,
-                 float* dbk, float* Pbuf, float* G, void* stream_) {
-  SPT_REQUIRE(num_rows >= 0 && num_targets >= 0 && E >= 0, SPT_E_INVALID,
-              "attn_bwd: negative size");
+int spt_attn_bwd_rows(const float* q, int64_t ldq, const float* k, int64_t ldk,
+                      const float* v, int64_t ldv, const float* a, const int32_t* rowptr,
+                      const int32_t* col, int64_t num_rows, int64_t E, int H, int D, int Dv,
+                      int F, const float* Wq, const float* bq, const float* Wk,
+                      const float* bk, int scale_mode, float scale_value, const float* m,
+                      const float* z, const float* agg_v, const float* abar,
+                      const float* d_agg_v, const float* d_abar, float* dq, int64_t lddq,
+                      float* da, float* Pbuf, float* G, void* stream_) {
+  SPT_REQUIRE(num_rows >= 0 && E >= 0, SPT_E_INVALID, "attn_bwd_rows: negative size");
+  if (num_rows == 0) return SPT_OK;
   AttnShape s;
-  int rc = check_shape("attn_bwd", H, D, Dv, a ? F : 0, &s);
+  int rc = check_shape("attn_bwd_rows", H, D, Dv, a ? F : 0, &s);
   if (rc != SPT_OK) return rc;
-  SPT_REQUIRE(q && k && v && rowptr && csc_ptr && m && z && agg_v && d_agg_v && dq && dk &&
-                  dv && (E == 0 || (col && csc_src && csc2csr && Pbuf && G)),
-              SPT_E_INVALID, "attn_bwd: null pointer");
+  SPT_REQUIRE(q && k && v && rowptr && m && z && agg_v && d_agg_v && dq &&
+                  (E == 0 || (col && Pbuf && G)),
+              SPT_E_INVALID, "attn_bwd_rows: null pointer");
   cudaStream_t st = (cudaStream_t)stream_;
-  if (num_rows > 0) {
-    BwdParams P;
-    P.q = q; P.ldq = ldq; P.k = k; P.ldk = ldk; P.v = v; P.ldv = ldv; P.a = a;
-    P.rowptr = rowptr; P.col = col; P.num_rows = num_rows; P.s = s;
-    P.Wq = a ? Wq : nullptr; P.bq = bq; P.Wk = a ? Wk : nullptr; P.bk = bk;
-    P.scale_mode = scale_mode; P.scale_value = scale_value;
-    P.m = m; P.z = z; P.agg_v = agg_v; P.abar = abar; P.d_agg_v = d_agg_v; P.d_abar = d_abar;
-    P.dq = dq; P.lddq = lddq; P.da = da; P.Pbuf = Pbuf; P.G = G;
-    int F4 = round4(s.F > 1 ? s.F : 1);
-    int per_warp = F4 + 2 * s.HD2 + s.HD + 160 + round4(s.C) + round4(s.HF > 1 ? s.HF : 1);
-    size_t smem = (size_t)(s.F * (s.HD2 + 1) + s.HD2 + kAttnWarps * per_warp) * sizeof(float);
-    if (smem > 48 * 1024)
-      cudaFuncSetAttribute(k_attn_bwd_rows_generic,
-                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_attn_bwd_rows_generic<<<(unsigned)ceil_div(num_rows, kAttnWarps), kAttnWarps * kWarp, smem,
-                              st>>>(P);
-  }
-  if (num_targets > 0) {
-    k_attn_bwd_targets_generic<<<(unsigned)ceil_div(num_targets, kAttnWarps),
-                                 kAttnWarps * kWarp, 0, st>>>(
-        csc_ptr, csc_src, csc2csr, num_targets, s, Pbuf, G, d_agg_v, dk, lddk, dv, lddv);
-  }
-  if (a && s.F > 0 && E > 0 && (dWq || dWk || dbq || dbk)) {
-    int64_t ctas = ceil_div(E, 2048);
-    if (ctas > 148 * 4) ctas = 148 * 4;
-    int64_t per = ceil_div(E, ctas);
-    per = ceil_div(per, kDwTile) * kDwTile;
-    ctas = ceil_div(E, per);
-    size_t smem = (size_t)kDwTile * (s.HD2 + s.F) * sizeof(float);
-    if (smem > 48 * 1024)
-      cudaFuncSetAttribute(k_attn_bwd_dw_generic, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)smem);
-    k_attn_bwd_dw_generic<<<(unsigned)ctas, kDwThreads, smem, st>>>(G, a, E, s, per, dWq, dbq,
-                                                                  dWk, dbk);
-  } else if (!a && E > 0 && (dbq || dbk)) {
-    // no edge features: biases unused by the forward (Wq/Wk ignored) -> zero grads
-  }
-  return check_launch("attn_bwd");
+  BwdParams P;
+  P.q = q; P.ldq = ldq; P.k = k; P.ldk = ldk; P.v = v; P.ldv = ldv; P.a = a;
+  P.rowptr = rowptr; P.col = col; P.num_rows = num_rows; P.s = s;
+  P.Wq = a ? Wq : nullptr; P.bq = bq; P.Wk = a ? Wk : nullptr; P.bk = bk;
+  P.scale_mode = scale_mode; P.scale_value = scale_value;
+  P.m = m; P.z = z; P.agg_v = agg_v; P.abar = abar; P.d_agg_v = d_agg_v; P.d_abar = d_abar;
+  P.dq = dq; P.lddq = lddq; P.da = da; P.Pbuf = Pbuf; P.G = G;
+  int F4 = round4(s.F > 1 ? s.F : 1);
+  int per_warp = F4 + 2 * s.HD2 + s.HD + 160 + round4(s.C) + round4(s.HF > 1 ? s.HF : 1);
+  size_t smem = (size_t)(s.F * (s.HD2 + 1) + s.HD2 + kAttnWarps * per_warp) * sizeof(float);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(k_attn_bwd_rows_generic, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem);
+  k_attn_bwd_rows_generic<<<(unsigned)ceil_div(num_rows, kAttnWarps), kAttnWarps * kWarp, smem,
+                            st>>>(P);
+  return check_launch("attn_bwd_rows");
+}
+
+int spt_attn_bwd_targets(const int32_t* csc_ptr, const int32_t* csc_src,
+                         const int32_t* csc2csr, int64_t num_targets, int64_t E, int H, int D,
+                         int Dv, const float* Pbuf, const float* G, const float* d_agg_v,
+                         float* dk, int64_t lddk, float* dv, int64_t lddv, void* stream_) {
+  SPT_REQUIRE(num_targets >= 0 && E >= 0, SPT_E_INVALID, "attn_bwd_targets: negative size");
+  if (num_targets == 0) return SPT_OK;
+  AttnShape s;
+  int rc = check_shape("attn_bwd_targets", H, D, Dv, 0, &s);
+  if (rc != SPT_OK) return rc;
+  SPT_REQUIRE(csc_ptr && dk && dv && (E == 0 || (csc_src && csc2csr && Pbuf && G && d_agg_v)),
+              SPT_E_INVALID, "attn_bwd_targets: null pointer");
+  k_attn_bwd_targets_generic<<<(unsigned)ceil_div(num_targets, kAttnWarps), kAttnWarps * kWarp,
+                               0, (cudaStream_t)stream_>>>(
+      csc_ptr, csc_src, csc2csr, num_targets, s, Pbuf, G, d_agg_v, dk, lddk, dv, lddv);
+  return check_launch("attn_bwd_targets");
+}
+
+int spt_attn_bwd_weights(const float* G, const float* a, int64_t E, int H, int D, int F,
+                         float* dWq, float* dbq, float* dWk, float* dbk, void* stream_) {
+  SPT_REQUIRE(E >= 0, SPT_E_INVALID, "attn_bwd_weights: negative size");
+  if (E == 0 || F == 0 || !(dWq || dWk || dbq || dbk)) return SPT_OK;
+  AttnShape s;
+  int rc = check_shape("attn_bwd_weights", H, D, 1, F, &s);
+  if (rc != SPT_OK) return rc;
+  SPT_REQUIRE(G && a, SPT_E_INVALID, "attn_bwd_weights: null pointer");
+  int64_t ctas = ceil_div(E, 2048);
+  if (ctas > 148 * 4) ctas = 148 * 4;
+  int64_t per = ceil_div(E, ctas);
+  per = ceil_div(per, kDwTile) * kDwTile;
+  ctas = ceil_div(E, per);
+  size_t smem = (size_t)kDwTile * (s.HD2 + s.F) * sizeof(float);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(k_attn_bwd_dw_generic, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem);
+  k_attn_bwd_dw_generic<<<(unsigned)ctas, kDwThreads, smem, (cudaStream_t)stream_>>>(
+      G, a, E, s, per, dWq, dbq, dWk, dbk);
+  return check_launch("attn_bwd_weights");
 }
 
 }  // extern "C"

@@ -121,16 +121,25 @@ class NAG:
             src = values if values is not None else torch.ones_like(index)
             return out.index_add_(0, index, src)
 
-        if low >= self.start_i_level and self[low].node_size is not None:
+        start = self.start_i_level
+        if low >= start and self[low].node_size is not None:
             sizes = seg_sum(self[low].node_size, self[low].super_index,
                             self[low + 1].num_nodes)
+            cur = low + 1
         elif self[low + 1].sub is not None:
             sizes = self[low + 1].sub.sizes.long()
-        elif low >= self.start_i_level:
+            cur = low + 1
+        elif low >= start:
             sizes = seg_sum(None, self[low].super_index, self[low + 1].num_nodes)
+            cur = low + 1
+        elif self[start].node_size is not None:
+            # nano NAGs (level `low` not loaded) whose first-level sizes were
+            # computed at preprocessing time
+            sizes = self[start].node_size
+            cur = start
         else:
             raise ValueError(f"Cannot infer the size of level {low=} element sizes")
-        for i in range(low + 1, high):
+        for i in range(cur, high):
             sizes = seg_sum(sizes, self[i].super_index, self[i + 1].num_nodes)
         return sizes
 

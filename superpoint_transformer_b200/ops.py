@@ -25,6 +25,38 @@ def _count(n=1):
     _LAUNCHES += n
 
 
+# optional per-kernel CUDA-event timing (bench.py roofline): list of
+# (tag, meta, start_event, end_event); events are recorded on the launch stream.
+_TIMING = None
+
+
+def enable_event_timing(on=True):
+    global _TIMING
+    _TIMING = [] if on else None
+
+
+def timing_records():
+    return _TIMING
+
+
+class _timed:
+    def __init__(self, tag, **meta):
+        self.tag, self.meta = tag, meta
+
+    def __enter__(self):
+        if _TIMING is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record(torch.cuda.current_stream())
+        return self
+
+    def __exit__(self, *exc):
+        if _TIMING is not None:
+            self.e.record(torch.cuda.current_stream())
+            _TIMING.append((self.tag, self.meta, self.s, self.e))
+        return False
+
+
 def _require_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
@@ -96,7 +128,7 @@ def group_index(key, num_groups, other=None):
         rc = lib.spt_group_index(_p(key), _p(other), n, num_groups, _p(ptr), _p(perm),
                                  _p(osort), _p(ws), nbytes, _stream())
     _lib.check(rc, "spt_group_index")
-    _count(8)
+    _count(8 if other is not None else 7)
     err = ws[:4].view(torch.int32)
     return SegmentIndex(ptr, perm, osort, n, num_groups, err)
 
@@ -402,7 +434,7 @@ class _GraphNorm(torch.autograd.Function):
             _lib.check(lib.spt_graphnorm_fwd(_p(x), _p(batch), N, C, B, _p(weight), _p(bias),
                                              _p(mean_scale), eps, _p(y), _p(mean), _p(rstd),
                                              _p(ws), nbytes, _stream()), "spt_graphnorm_fwd")
-        _count(5)
+        _count(4)
         ctx.B = B
         ctx.has_batch = batch is not None
         ctx.save_for_backward(x, weight, mean_scale, mean, rstd,
@@ -429,7 +461,7 @@ class _GraphNorm(torch.autograd.Function):
                                              _p(mean_scale), _p(mean), _p(rstd), _p(dx),
                                              _p(dw), _p(db), _p(dms), _p(ws), nbytes,
                                              _stream()), "spt_graphnorm_bwd")
-        _count(5)
+        _count(4)
         return dx, dw, db, dms, None, None, None
 
 
@@ -474,7 +506,8 @@ class _AttnCore(torch.autograd.Function):
         sump = torch.empty((R, H), dtype=torch.float32, device=dev)
         m = torch.empty((R, H), dtype=torch.float32, device=dev)
         z = torch.empty((R, H), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), _timed('attn_fwd', R=R, E=g.E, H=H, D=D, Dv=Dv, F=F,
+                                            abar=abar is not None):
             _lib.check(lib.spt_attn_fwd(qp, ldq, kp, ldk, vp, ldv, _p(a), _p(g.rowptr),
                                         _p(g.col), R, g.E, H, D, Dv, F, _p(Wq), _p(bq),
                                         _p(Wk), _p(bk), scale_mode, scale_value, _p(agg),
@@ -539,15 +572,27 @@ class _AttnCore(torch.autograd.Function):
         E = g.E
         Pb = torch.empty((max(E, 1), H), dtype=torch.float32, device=dev)
         G = torch.empty((max(E, 1), 2 * HD), dtype=torch.float32, device=dev)
+        meta = dict(R=g.num_rows, T=g.num_targets, E=E, H=H, D=D, Dv=Dv, F=F,
+                    abar=abar is not None, da=da is not None)
         with torch.cuda.device(dev):
-            _lib.check(lib.spt_attn_bwd(
-                qp, ldq, kp, ldk, vp, ldv, _p(a), _p(g.rowptr), _p(g.col), _p(g.csc_ptr),
-                _p(g.csc_src), _p(g.csc2csr), g.num_rows, g.num_targets, E, H, D, Dv, F,
-                _p(Wq), _p(bq), _p(Wk), _p(bk), ctx.scale_mode, ctx.scale_value, _p(m), _p(z),
-                _p(agg), _p(abar), _p(d_agg), _p(d_abar), dqp, lddq, dkp, lddk, dvp, lddv,
-                _p(da), _p(dWq), _p(dbq), _p(dWk), _p(dbk), _p(Pb), _p(G), _stream()),
-                "spt_attn_bwd")
-        _count(3)
+            with _timed('attn_bwd_rows', **meta):
+                _lib.check(lib.spt_attn_bwd_rows(
+                    qp, ldq, kp, ldk, vp, ldv, _p(a), _p(g.rowptr), _p(g.col), g.num_rows, E,
+                    H, D, Dv, F, _p(Wq), _p(bq), _p(Wk), _p(bk), ctx.scale_mode,
+                    ctx.scale_value, _p(m), _p(z), _p(agg), _p(abar), _p(d_agg), _p(d_abar),
+                    dqp, lddq, _p(da), _p(Pb), _p(G), _stream()), "spt_attn_bwd_rows")
+            with _timed('attn_bwd_targets', **meta):
+                _lib.check(lib.spt_attn_bwd_targets(
+                    _p(g.csc_ptr), _p(g.csc_src), _p(g.csc2csr), g.num_targets, E, H, D, Dv,
+                    _p(Pb), _p(G), _p(d_agg), dkp, lddk, dvp, lddv, _stream()),
+                    "spt_attn_bwd_targets")
+            _count(2)
+            if a is not None and (dWq is not None or dWk is not None):
+                with _timed('attn_bwd_weights', **meta):
+                    _lib.check(lib.spt_attn_bwd_weights(
+                        _p(G), _p(a), E, H, D, F, _p(dWq), _p(dbq), _p(dWk), _p(dbk),
+                        _stream()), "spt_attn_bwd_weights")
+                _count(1)
         if bq is not None and dbq is None:
             dbq = torch.zeros_like(bq)
         if bk is not None and dbk is None:

@@ -27,12 +27,13 @@ class NodeSize:
         self.low = low
 
     def __call__(self, nag):
-        first = max(self.low + 1, nag.start_i_level)
-        for i_level in range(first, nag.absolute_num_levels):
-            low = self.low
-            if low < nag.start_i_level - 1:
-                low = nag.start_i_level - 1
-            nag[i_level].node_size = nag.get_sub_size(i_level, low=low)
+        start = nag.start_i_level
+        low = max(self.low, start - 1)
+        for i_level in range(max(self.low + 1, start), nag.absolute_num_levels):
+            d = nag[i_level]
+            if i_level == start and low < start and d.sub is None and d.node_size is not None:
+                continue  # first loaded level of a nano NAG: sizes come with the data
+            d.node_size = nag.get_sub_size(i_level, low=low)
         return nag
 
 
