@@ -382,17 +382,48 @@ def _scaled_levels(n1):
     return [n1, max(n1 // 5, 2), max(n1 // 25, 1)]
 
 
-def cpu_reference_sample(target_seconds=20.0):
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    sd, hw, hb = _cpu_state_dict()
-    # probe at 1k superpoints, then size the sample for ~target_seconds of CPU work
+def _available_cores():
+    """host cores this process may use: affinity mask capped by the cgroup CPU quota"""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open('/sys/fs/cgroup/cpu.max').read().split()[:2]
+        if quota != 'max':
+            n = min(n, max(1, int(float(quota) / float(period) + 0.999)))
+    except Exception:  # noqa: BLE001
+        pass
+    return max(1, n)
+
+
+def _pick_threads(sd, hw, hb):
+    """The reference's torch CPU path does not scale to every core of a many-core
+    host on graphs this small; give it its best case: probe 8,16,32,... threads on
+    a 1k-superpoint NAG and keep the fastest.  Returns (threads, seconds per
+    superpoint at that setting)."""
+    avail = _available_cores()
     nag = _cpu_scene(_scaled_levels(1000), seed=1)
     labels = torch.randint(0, NUM_CLASSES, (1000,))
-    cpu_step(sd, hw, hb, nag, labels)
-    t = time.time()
-    cpu_step(sd, hw, hb, nag, labels)
-    per_sp = (time.time() - t) / 1000
+    cands = sorted({c for c in (8, 16, 32, 64, avail) if c <= avail} or {avail})
+    best = None
+    for c in cands:
+        torch.set_num_threads(c)
+        cpu_step(sd, hw, hb, nag, labels)
+        t = time.time()
+        cpu_step(sd, hw, hb, nag, labels)
+        dt = time.time() - t
+        if best is None or dt < best[1]:
+            best = (c, dt)
+        elif dt > 1.5 * best[1]:
+            break
+    torch.set_num_threads(best[0])
+    return best[0], best[1] / 1000, avail
+
+
+def cpu_reference_sample(target_seconds=20.0):
+    sd, hw, hb = _cpu_state_dict()
+    threads, per_sp, avail = _pick_threads(sd, hw, hb)
     n1 = int(min(max(target_seconds / max(per_sp, 1e-9), 1000), LEVELS[0]))
     n1 = max(1000, (n1 // 1000) * 1000)
     nag = _cpu_scene(_scaled_levels(n1), seed=1)
@@ -400,10 +431,12 @@ def cpu_reference_sample(target_seconds=20.0):
     t = time.time()
     cpu_step(sd, hw, hb, nag, labels)
     dt = time.time() - t
-    return {"value": round(n1 / dt, 1), "unit": UNIT, "cores": cores, "kind": "port",
+    return {"value": round(n1 / dt, 1), "unit": UNIT, "cores": threads, "kind": "port",
+            "host_cores_available": avail,
             "sample": f"one fwd+bwd of the same model on a {n1}/{n1 // 5}/{n1 // 25}-superpoint "
                       f"NAG of the same law ({dt:.1f} s); oracle/path.py (reference glue "
-                      f"restated, torch CPU leaves), fp32, {cores} threads"}
+                      f"restated, torch CPU leaves), fp32, {threads} threads (fastest of the "
+                      f"probed thread counts on this {avail}-core host)"}
 
 
 def run_reference(args):
@@ -411,17 +444,10 @@ def run_reference(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     sd, hw, hb = _cpu_state_dict()
-    budget = 200.0
+    threads, per_sp, avail = _pick_threads(sd, hw, hb)
+    budget = 180.0
     total_steps = args.steps + args.warmup
-    nag = _cpu_scene(_scaled_levels(1000), seed=1)
-    labels = torch.randint(0, NUM_CLASSES, (1000,))
-    cpu_step(sd, hw, hb, nag, labels)
-    t = time.time()
-    cpu_step(sd, hw, hb, nag, labels)
-    per_sp = (time.time() - t) / 1000
     n1 = int(budget / total_steps / max(per_sp, 1e-9))
     n1 = max(1000, min((n1 // 1000) * 1000, LEVELS[0]))
     nag = _cpu_scene(_scaled_levels(n1), seed=1)
@@ -435,15 +461,16 @@ def run_reference(args):
     ms = dt / args.steps * 1e3
     value = n1 / (ms * 1e-3)
     sample = (f"each step = fwd+bwd on a {n1}/{n1 // 5}/{n1 // 25}-superpoint NAG of the cfg-2 "
-              f"law (bounded sample of the 100k workload), oracle/path.py on {cores} threads")
+              f"law (bounded sample of the 100k workload), oracle/path.py on {threads} threads "
+              f"(fastest probed; host has {avail} cores)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": sample},
+        "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": threads,
+                         "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
