@@ -201,7 +201,11 @@ int spt_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk,
 /* Backward of spt_attn_fwd, three launches so each can be timed on its own:
  *  (1) rows    : per CSR row, recompute p from (m, z); writes dq [R rows, lddq],
  *                da [E,F] (CSR order, nullable) and the per-edge scratch
- *                P [E,H] (= p) and G [E,2HD] (= [dq_e | dk_e]).
+ *                P [E,H] (= p) and G [E,2HD] (= [dq_e | dk_e]; the specialised
+ *                kernel only fills the dk_e half).  dWq,dWk [HD,F] / dbq,dbk [HD]
+ *                (nullable) are ACCUMULATED into (caller zero-fills): fused in the
+ *                specialised kernel, a follow-up slab reduction (= entry (3)) in
+ *                the generic one.
  *  (2) targets : per target t (edges grouped by target: csc_ptr/csc_src/csc2csr,
  *                csc2csr = CSR slot of each CSC slot), gathers
  *                dv[t] = sum p * d_agg_v[src], dk[t] = sum dk_e — no atomics;
@@ -216,8 +220,9 @@ int spt_attn_bwd_rows(const float* q, int64_t ldq, const float* k, int64_t ldk,
                       int scale_mode, float scale_value, const float* m,
                       const float* z, const float* agg_v, const float* abar,
                       const float* d_agg_v, const float* d_abar /*nullable*/,
-                      float* dq, int64_t lddq, float* da /*nullable*/, float* P,
-                      float* G, void* stream);
+                      float* dq, int64_t lddq, float* da /*nullable*/,
+                      float* dWq, float* dbq, float* dWk, float* dbk /*nullable*/,
+                      float* P, float* G, void* stream);
 int spt_attn_bwd_targets(const int32_t* csc_ptr, const int32_t* csc_src,
                          const int32_t* csc2csr, int64_t num_targets, int64_t E,
                          int H, int D, int Dv, const float* P, const float* G,

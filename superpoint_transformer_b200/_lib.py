@@ -55,7 +55,9 @@ SIGNATURES = {
                                   c_int, c_int, c_int, c_int,                        # H D Dv F
                                   c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_f32,          # W, scale
                                   c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,          # m z agg abar dagg dabar
-                                  c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),        # dq da P G stream
+                                  c_ptr, c_i64, c_ptr,                               # dq da
+                                  c_ptr, c_ptr, c_ptr, c_ptr,                        # dWq dbq dWk dbk
+                                  c_ptr, c_ptr, c_ptr]),                             # P G stream
     "spt_attn_bwd_targets": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int, c_int, c_int,
                                      c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_ptr]),
     "spt_attn_bwd_weights": (c_int, [c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_ptr,

@@ -18,6 +18,7 @@
 // This file is the runtime-generic path (any C<=256, H<=32, H*D<=256, F<=128,
 // H*F<=512).  Shapes outside raise SPT_E_UNSUPPORTED.
 #include "common.cuh"
+#include "attention_fast.cuh"
 
 namespace spt {
 
@@ -474,6 +475,27 @@ int spt_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const
               SPT_E_INVALID, "attn_fwd: null pointer");
   SPT_REQUIRE(scale_mode >= SPT_SCALE_D_TIMES_G && scale_mode <= SPT_SCALE_CONST,
               SPT_E_INVALID, "attn_fwd: bad scale mode %d", scale_mode);
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (a && fast::shape_ok(H, D, Dv, F) && ldv % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(v) & 15) == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0) {
+    fast::FwdArgs A;
+    A.q = q; A.ldq = ldq; A.k = k; A.ldk = ldk; A.v = v; A.ldv = ldv; A.a = a;
+    A.rowptr = rowptr; A.col = col; A.num_rows = num_rows;
+    A.Wq = Wq; A.bq = bq; A.Wk = Wk; A.bk = bk;
+    A.scale_mode = scale_mode; A.scale_value = scale_value;
+    A.agg_v = agg_v; A.abar = abar; A.sump = sump; A.m = m; A.z = z;
+    A.rows_per_warp = 8;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(fast::k_attn_fwd_fast, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)fast::fwd_smem_bytes());
+      attr_set = true;
+    }
+    int64_t warps = ceil_div(num_rows, A.rows_per_warp);
+    fast::k_attn_fwd_fast<<<(unsigned)ceil_div(warps, fast::kWarps), fast::kWarps * kWarp,
+                            fast::fwd_smem_bytes(), st>>>(A);
+    return check_launch("attn_fwd(fast)");
+  }
   FwdParams P;
   P.q = q; P.ldq = ldq; P.k = k; P.ldk = ldk; P.v = v; P.ldv = ldv; P.a = a;
   P.rowptr = rowptr; P.col = col; P.num_rows = num_rows; P.s = s;
@@ -483,7 +505,6 @@ int spt_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const
   int F4 = round4(s.F > 1 ? s.F : 1);
   int per_warp = F4 + s.HD2 + s.HD + 96;
   size_t smem = (size_t)(s.F * (s.HD2 + 1) + s.HD2 + kAttnWarps * per_warp) * sizeof(float);
-  cudaStream_t st = (cudaStream_t)stream_;
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(k_attn_fwd_generic, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)smem);
@@ -498,7 +519,8 @@ int spt_attn_bwd_rows(const float* q, int64_t ldq, const float* k, int64_t ldk,
                       const float* bk, int scale_mode, float scale_value, const float* m,
                       const float* z, const float* agg_v, const float* abar,
                       const float* d_agg_v, const float* d_abar, float* dq, int64_t lddq,
-                      float* da, float* Pbuf, float* G, void* stream_) {
+                      float* da, float* dWq, float* dbq, float* dWk, float* dbk, float* Pbuf,
+                      float* G, void* stream_) {
   SPT_REQUIRE(num_rows >= 0 && E >= 0, SPT_E_INVALID, "attn_bwd_rows: negative size");
   if (num_rows == 0) return SPT_OK;
   AttnShape s;
@@ -508,6 +530,32 @@ int spt_attn_bwd_rows(const float* q, int64_t ldq, const float* k, int64_t ldk,
                   (E == 0 || (col && Pbuf && G)),
               SPT_E_INVALID, "attn_bwd_rows: null pointer");
   cudaStream_t st = (cudaStream_t)stream_;
+  if (a && fast::shape_ok(H, D, Dv, F) && ldv % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(v) & 15) == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0) {
+    fast::BwdArgs A;
+    A.q = q; A.ldq = ldq; A.k = k; A.ldk = ldk; A.v = v; A.ldv = ldv; A.a = a;
+    A.rowptr = rowptr; A.col = col; A.num_rows = num_rows;
+    A.Wq = Wq; A.bq = bq; A.Wk = Wk; A.bk = bk;
+    A.scale_mode = scale_mode; A.scale_value = scale_value;
+    A.m = m; A.z = z; A.agg_v = agg_v; A.abar = abar; A.d_agg_v = d_agg_v; A.d_abar = d_abar;
+    A.dq = dq; A.lddq = lddq; A.da = da; A.Pbuf = Pbuf; A.G = G;
+    A.dWq = Wq ? dWq : nullptr; A.dbq = (Wq && bq) ? dbq : nullptr;
+    A.dWk = Wk ? dWk : nullptr; A.dbk = (Wk && bk) ? dbk : nullptr;
+    A.rows_per_warp = 8;
+    A.num_row_blocks = (int)ceil_div(num_rows, A.rows_per_warp);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(fast::k_attn_bwd_rows_fast,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)fast::bwd_smem_bytes());
+      attr_set = true;
+    }
+    int64_t ctas = ceil_div(A.num_row_blocks, fast::kWarps);
+    if (ctas > 148 * 2) ctas = 148 * 2;   // persistent: dW flushed once per CTA
+    fast::k_attn_bwd_rows_fast<<<(unsigned)ctas, fast::kWarps * kWarp, fast::bwd_smem_bytes(),
+                                 st>>>(A);
+    return check_launch("attn_bwd_rows(fast)");
+  }
   BwdParams P;
   P.q = q; P.ldq = ldq; P.k = k; P.ldk = ldk; P.v = v; P.ldv = ldv; P.a = a;
   P.rowptr = rowptr; P.col = col; P.num_rows = num_rows; P.s = s;
@@ -523,7 +571,13 @@ int spt_attn_bwd_rows(const float* q, int64_t ldq, const float* k, int64_t ldk,
                          (int)smem);
   k_attn_bwd_rows_generic<<<(unsigned)ceil_div(num_rows, kAttnWarps), kAttnWarps * kWarp, smem,
                             st>>>(P);
-  return check_launch("attn_bwd_rows");
+  rc = check_launch("attn_bwd_rows");
+  if (rc != SPT_OK) return rc;
+  // generic path: dW = G^T a as a separate slab reduction
+  if (a && s.F > 0 && E > 0 && (dWq || dWk || dbq || dbk))
+    return spt_attn_bwd_weights(G, a, E, H, D, F, Wq ? dWq : nullptr, (Wq && bq) ? dbq : nullptr,
+                                Wk ? dWk : nullptr, (Wk && bk) ? dbk : nullptr, stream_);
+  return SPT_OK;
 }
 
 int spt_attn_bwd_targets(const int32_t* csc_ptr, const int32_t* csc_src,

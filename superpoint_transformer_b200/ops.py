@@ -580,19 +580,14 @@ class _AttnCore(torch.autograd.Function):
                     qp, ldq, kp, ldk, vp, ldv, _p(a), _p(g.rowptr), _p(g.col), g.num_rows, E,
                     H, D, Dv, F, _p(Wq), _p(bq), _p(Wk), _p(bk), ctx.scale_mode,
                     ctx.scale_value, _p(m), _p(z), _p(agg), _p(abar), _p(d_agg), _p(d_abar),
-                    dqp, lddq, _p(da), _p(Pb), _p(G), _stream()), "spt_attn_bwd_rows")
+                    dqp, lddq, _p(da), _p(dWq), _p(dbq), _p(dWk), _p(dbk), _p(Pb), _p(G),
+                    _stream()), "spt_attn_bwd_rows")
             with _timed('attn_bwd_targets', **meta):
                 _lib.check(lib.spt_attn_bwd_targets(
                     _p(g.csc_ptr), _p(g.csc_src), _p(g.csc2csr), g.num_targets, E, H, D, Dv,
                     _p(Pb), _p(G), _p(d_agg), dkp, lddk, dvp, lddv, _stream()),
                     "spt_attn_bwd_targets")
             _count(2)
-            if a is not None and (dWq is not None or dWk is not None):
-                with _timed('attn_bwd_weights', **meta):
-                    _lib.check(lib.spt_attn_bwd_weights(
-                        _p(G), _p(a), E, H, D, F, _p(dWq), _p(dbq), _p(dWk), _p(dbk),
-                        _stream()), "spt_attn_bwd_weights")
-                _count(1)
         if bq is not None and dbq is None:
             dbq = torch.zeros_like(bq)
         if bk is not None and dbk is None:
