@@ -19,6 +19,7 @@
 // H*F<=512).  Shapes outside raise SPT_E_UNSUPPORTED.
 #include "common.cuh"
 #include "attention_fast.cuh"
+#include <stdlib.h>
 
 namespace spt {
 
@@ -551,7 +552,9 @@ int spt_attn_bwd_rows(const float* q, int64_t ldq, const float* k, int64_t ldk,
       attr_set = true;
     }
     int64_t ctas = ceil_div(A.num_row_blocks, fast::kWarps);
-    if (ctas > 148 * 2) ctas = 148 * 2;   // persistent: dW flushed once per CTA
+    int64_t cap = 148 * 2;                 // persistent: dW flushed once per CTA
+    if (const char* e = getenv("SPT_BWD_CTA_CAP")) cap = atoll(e);
+    if (ctas > cap) ctas = cap;
     fast::k_attn_bwd_rows_fast<<<(unsigned)ctas, fast::kWarps * kWarp, fast::bwd_smem_bytes(),
                                  st>>>(A);
     return check_launch("attn_bwd_rows(fast)");

@@ -51,9 +51,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
                "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int dbg0 = 0,
+                                          int dbg1 = 0) {
   uint32_t done;
+#ifdef SPT_WATCHDOG
+  long long t0 = clock64();
+#endif
   do {
+#ifdef SPT_WATCHDOG
+    if (clock64() - t0 > 2000000000LL) {
+      if ((threadIdx.x & 31) == 0)
+        printf("mbar_wait stuck: block %d warp %d parity %u gtile %d gbase %d\n", blockIdx.x,
+               threadIdx.x >> 5, parity, dbg0, dbg1);
+      __trap();
+    }
+#endif
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -73,50 +85,69 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
       : "memory");
 }
 
-// Per-warp streaming reader of the CSR-ordered edge-feature slab [e0, e1).
+// Per-warp streaming reader of CSR-ordered edge-feature slabs [e0, e1).  The two
+// mbarriers are initialised ONCE per warp (`init`); tiles are numbered globally
+// across successive slabs (`open`) so the stage / phase-parity sequence simply
+// continues — barriers are never re-initialised.
 struct EdgeStream {
   const float* a;       // [E, kF] global
   float* buf;           // warp-private smem: kStages * kTile * kF floats
   uint64_t* bar;        // kStages mbarriers
-  int64_t e0, e1;       // slab
+  int64_t e0, e1;       // current slab
   int64_t tile_base;    // first edge of the tile currently readable
-  int tile;             // index of that tile
+  int gtile;            // global index of that tile
+  int gbase;            // global index of the slab's first tile
+  int gnext;            // global index the next slab will start at
   int lane;
 
-  __device__ __forceinline__ void issue(int k) {
-    int64_t b = e0 + (int64_t)k * kTile;
-    if (b >= e1) return;
-    int n = (int)min((int64_t)kTile, e1 - b);
-    int s = k % kStages;
-    if (lane == 0) {
-      mbar_expect_tx(&bar[s], (uint32_t)n * kF * 4);
-      tma_load_1d(buf + s * kTile * kF, a + b * kF, (uint32_t)n * kF * 4, &bar[s]);
-    }
-  }
-  __device__ __forceinline__ void begin() {
+  __device__ __forceinline__ void init(const float* a_, float* buf_, uint64_t* bar_, int lane_) {
+    a = a_; buf = buf_; bar = bar_; lane = lane_;
+    gnext = 0;
     if (lane == 0) {
 #pragma unroll
       for (int s = 0; s < kStages; ++s) mbar_init(&bar[s], 1);
       mbar_fence_init();
     }
     __syncwarp();
-    tile = 0;
+  }
+  // issue slab-local tile k
+  __device__ __forceinline__ void issue(int k) {
+    int64_t b = e0 + (int64_t)k * kTile;
+    if (b >= e1) return;
+    int n = (int)min((int64_t)kTile, e1 - b);
+    int s = (gbase + k) % kStages;
+    if (lane == 0) {
+      mbar_expect_tx(&bar[s], (uint32_t)n * kF * 4);
+      tma_load_1d(buf + s * kTile * kF, a + b * kF, (uint32_t)n * kF * 4, &bar[s]);
+    }
+  }
+  __device__ __forceinline__ void wait_current() {
+    mbar_wait(&bar[gtile % kStages], (uint32_t)((gtile / kStages) & 1), gtile, gbase);
+  }
+  // start streaming a new slab; the previous one must have been read to its end
+  __device__ __forceinline__ void open(int64_t e0_, int64_t e1_) {
+    e0 = e0_; e1 = e1_;
+    if (e1 <= e0) return;
+    __syncwarp();                   // all lanes finished the previous slab's tiles
+    gbase = gnext;
+    gnext = gbase + (int)((e1 - e0 + kTile - 1) / kTile);
+    gtile = gbase;
     tile_base = e0;
     issue(0);
     issue(1);
-    mbar_wait(&bar[0], 0);
+    wait_current();
   }
   // pointer to the features of CSR slot j (advances the ring when j leaves the tile);
-  // j must be visited in increasing order
+  // j must be visited in increasing order and every slot of the slab must be visited
   __device__ __forceinline__ const float* row(int64_t j) {
     if (j >= tile_base + kTile) {
-      __syncwarp();                 // every lane is done reading the old tile
-      issue(tile + kStages);        // refill the stage we just released
-      ++tile;
+      __syncwarp();                           // every lane is done reading the old tile
+      issue(gtile - gbase + kStages);         // refill the stage we just released
+      ++gtile;
       tile_base += kTile;
-      mbar_wait(&bar[tile % kStages], (uint32_t)((tile / kStages) & 1));
+      wait_current();
     }
-    return buf + (tile % kStages) * kTile * kF + (int)(j - tile_base) * kF;
+    return buf + (gtile % kStages) * kTile * kF + (int)(j - tile_base) * kF;
   }
 };
 
@@ -186,9 +217,8 @@ k_attn_fwd_fast(FwdArgs P) {
   }
 
   EdgeStream es;
-  es.a = P.a; es.buf = buf; es.bar = bars; es.lane = lane;
-  es.e0 = P.rowptr[row0]; es.e1 = P.rowptr[row1];
-  if (es.e1 > es.e0) es.begin();
+  es.init(P.a, buf, bars, lane);
+  es.open(P.rowptr[row0], P.rowptr[row1]);
 
   const int hsel = (lane >> 3) << 2;   // lane holding compat of my head (0,4,8,12)
   for (int64_t row = row0; row < row1; ++row) {
@@ -316,21 +346,14 @@ k_attn_bwd_rows_fast(BwdArgs P) {
 
   const int hsel = (lane >> 3) << 2;
   const int myhead = lane >> 3;
-  bool bars_ready = false;
+  EdgeStream es;
+  es.init(P.a, buf, bars, lane);
 
   for (int64_t blk = (int64_t)blockIdx.x * kWarps + w; blk < P.num_row_blocks;
        blk += (int64_t)gridDim.x * kWarps) {
     const int64_t row0 = blk * P.rows_per_warp;
     const int64_t row1 = min(row0 + (int64_t)P.rows_per_warp, P.num_rows);
-    EdgeStream es;
-    es.a = P.a; es.buf = buf; es.bar = bars; es.lane = lane;
-    es.e0 = P.rowptr[row0]; es.e1 = P.rowptr[row1];
-    if (es.e1 > es.e0) {
-      // (re)initialise the barriers for every slab: phases restart from 0
-      __syncwarp();
-      es.begin();
-      bars_ready = true;
-    }
+    es.open(P.rowptr[row0], P.rowptr[row1]);
     for (int64_t row = row0; row < row1; ++row) {
       const int b = P.rowptr[row], e = P.rowptr[row + 1];
       const float scale = qk_scale_fast(P.scale_mode, P.scale_value, e - b);
@@ -434,7 +457,6 @@ k_attn_bwd_rows_fast(BwdArgs P) {
       if (lane < kHD) P.dq[row * P.lddq + lane] = dq_acc * scale;
     }
   }
-  (void)bars_ready;
 
   // ---- reduce dW over the CTA's warps in shared memory, then one atomic per entry
   if (want_dw) {

@@ -26,7 +26,8 @@ SOURCES = [
     "attention.cu",
     "edge_features.cu",
 ]
-HEADERS = ["common.cuh", os.path.join(ROOT, "include", "spt_b200.h")]
+HEADERS = sorted(f for f in os.listdir(HERE) if f.endswith((".cuh", ".h"))) + \
+    [os.path.join(ROOT, "include", "spt_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -34,7 +35,7 @@ NVCC_FLAGS = [
     "-Xptxas=-v",
     "-Xcompiler", "-fPIC",
     "-shared",
-]
+] + (["-DSPT_WATCHDOG"] if os.environ.get("SPT_WATCHDOG") else [])
 
 
 def _nvcc():
