@@ -199,8 +199,11 @@ def spt_case(ref):
             v = d[k]
             if torch.is_tensor(v) and v.is_floating_point():
                 d[k] = v.double()
-    with torch.no_grad():
-        out64 = net64(run64)
+    out64 = net64(run64)
+    (out64 * probe.double()).sum().backward()
+    pgrads64 = {k: p.grad.detach().clone() for k, p in net64.named_parameters()
+                if p.grad is not None}
+    out64 = out64.detach()
     levels = {}
     for l in nag.level_range:
         d = nag[l]
@@ -211,7 +214,7 @@ def spt_case(ref):
         levels[l]['raw_edge_index'], levels[l]['raw_edge_attr'] = raw[l]
     return dict(cfg=SPT_CFG, sd={k: v.detach().clone() for k, v in net.state_dict().items()},
                 levels=levels, start_i_level=nag.start_i_level, out=out.detach(),
-                out64=out64, probe=probe, dparams=pgrads)
+                out64=out64, probe=probe, dparams=pgrads, dparams64=pgrads64)
 
 
 def stage_cases(ref):
