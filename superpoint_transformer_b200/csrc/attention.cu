@@ -442,6 +442,14 @@ k_attn_bwd_dw_generic(const float* __restrict__ G, const float* __restrict__ a, 
   }
 }
 
+// preconditions of the specialised kernels: 16-byte aligned rows, 32-bit offsets
+static bool fast_layout_ok(const float* v, const float* a, int64_t ldq, int64_t ldk,
+                           int64_t ldv, int64_t rows) {
+  return ldv % 4 == 0 && (reinterpret_cast<uintptr_t>(v) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(a) & 15) == 0 && ldq < (1 << 20) && ldk < (1 << 20) &&
+         ldv < (1 << 20) && rows * (ldk > ldv ? ldk : ldv) < (int64_t)4000000000LL;
+}
+
 static int check_shape(const char* who, int H, int D, int Dv, int F, AttnShape* out) {
   SPT_REQUIRE(H >= 1 && D >= 1 && Dv >= 1 && F >= 0, SPT_E_INVALID, "%s: bad dims", who);
   AttnShape s;
@@ -477,10 +485,9 @@ int spt_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const
   SPT_REQUIRE(scale_mode >= SPT_SCALE_D_TIMES_G && scale_mode <= SPT_SCALE_CONST,
               SPT_E_INVALID, "attn_fwd: bad scale mode %d", scale_mode);
   cudaStream_t st = (cudaStream_t)stream_;
-  if (a && fast::shape_ok(H, D, Dv, F) && ldv % 4 == 0 &&
-      (reinterpret_cast<uintptr_t>(v) & 15) == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0) {
+  if (a && fast::shape_ok(H, D, Dv, F) && fast_layout_ok(v, a, ldq, ldk, ldv, num_rows)) {
     fast::FwdArgs A;
-    A.q = q; A.ldq = ldq; A.k = k; A.ldk = ldk; A.v = v; A.ldv = ldv; A.a = a;
+    A.q = q; A.ldq = (int)ldq; A.k = k; A.ldk = (int)ldk; A.v = v; A.ldv = (int)ldv; A.a = a;
     A.rowptr = rowptr; A.col = col; A.num_rows = num_rows;
     A.Wq = Wq; A.bq = bq; A.Wk = Wk; A.bk = bk;
     A.scale_mode = scale_mode; A.scale_value = scale_value;
@@ -531,19 +538,16 @@ int spt_attn_bwd_rows(const float* q, int64_t ldq, const float* k, int64_t ldk,
                   (E == 0 || (col && Pbuf && G)),
               SPT_E_INVALID, "attn_bwd_rows: null pointer");
   cudaStream_t st = (cudaStream_t)stream_;
-  if (a && fast::shape_ok(H, D, Dv, F) && ldv % 4 == 0 &&
-      (reinterpret_cast<uintptr_t>(v) & 15) == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0) {
+  if (a && fast::shape_ok(H, D, Dv, F) && fast_layout_ok(v, a, ldq, ldk, ldv, num_rows) &&
+      lddq < (1 << 20)) {
     fast::BwdArgs A;
-    A.q = q; A.ldq = ldq; A.k = k; A.ldk = ldk; A.v = v; A.ldv = ldv; A.a = a;
+    A.q = q; A.ldq = (int)ldq; A.k = k; A.ldk = (int)ldk; A.v = v; A.ldv = (int)ldv; A.a = a;
     A.rowptr = rowptr; A.col = col; A.num_rows = num_rows;
     A.Wq = Wq; A.bq = bq; A.Wk = Wk; A.bk = bk;
     A.scale_mode = scale_mode; A.scale_value = scale_value;
     A.m = m; A.z = z; A.agg_v = agg_v; A.abar = abar; A.d_agg_v = d_agg_v; A.d_abar = d_abar;
-    A.dq = dq; A.lddq = lddq; A.da = da; A.Pbuf = Pbuf; A.G = G;
-    A.dWq = Wq ? dWq : nullptr; A.dbq = (Wq && bq) ? dbq : nullptr;
-    A.dWk = Wk ? dWk : nullptr; A.dbk = (Wk && bk) ? dbk : nullptr;
+    A.dq = dq; A.lddq = (int)lddq; A.da = da; A.Pbuf = Pbuf; A.G = G;
     A.rows_per_warp = 8;
-    A.num_row_blocks = (int)ceil_div(num_rows, A.rows_per_warp);
     static bool attr_set = false;
     if (!attr_set) {
       cudaFuncSetAttribute(fast::k_attn_bwd_rows_fast,
@@ -551,13 +555,24 @@ int spt_attn_bwd_rows(const float* q, int64_t ldq, const float* k, int64_t ldk,
                            (int)fast::bwd_smem_bytes());
       attr_set = true;
     }
-    int64_t ctas = ceil_div(A.num_row_blocks, fast::kWarps);
-    int64_t cap = 148 * 2;                 // persistent: dW flushed once per CTA
-    if (const char* e = getenv("SPT_BWD_CTA_CAP")) cap = atoll(e);
-    if (ctas > cap) ctas = cap;
-    fast::k_attn_bwd_rows_fast<<<(unsigned)ctas, fast::kWarps * kWarp, fast::bwd_smem_bytes(),
-                                 st>>>(A);
-    return check_launch("attn_bwd_rows(fast)");
+    int64_t warps = ceil_div(num_rows, A.rows_per_warp);
+    fast::k_attn_bwd_rows_fast<<<(unsigned)ceil_div(warps, fast::kWarps), fast::kWarps * kWarp,
+                                 fast::bwd_smem_bytes(), st>>>(A);
+    int rc2 = check_launch("attn_bwd_rows(fast)");
+    if (rc2 != SPT_OK) return rc2;
+    if (E > 0 && ((Wq && (dWq || dbq)) || (Wk && (dWk || dbk)))) {
+      fast::DwArgs W;
+      W.G = G; W.a = a; W.E = E;
+      W.dWq = Wq ? dWq : nullptr; W.dbq = (Wq && bq) ? dbq : nullptr;
+      W.dWk = Wk ? dWk : nullptr; W.dbk = (Wk && bk) ? dbk : nullptr;
+      int64_t ctas = ceil_div(E, 1024);
+      if (ctas > 148 * 4) ctas = 148 * 4;
+      W.edges_per_cta = ceil_div(E, ctas);
+      ctas = ceil_div(E, W.edges_per_cta);
+      fast::k_attn_bwd_dw_fast<<<(unsigned)ctas, 256, 0, st>>>(W);
+      return check_launch("attn_bwd_weights(fast)");
+    }
+    return SPT_OK;
   }
   BwdParams P;
   P.q = q; P.ldq = ldq; P.k = k; P.ldk = ldk; P.v = v; P.ldv = ldv; P.a = a;
@@ -594,6 +609,17 @@ int spt_attn_bwd_targets(const int32_t* csc_ptr, const int32_t* csc_src,
   if (rc != SPT_OK) return rc;
   SPT_REQUIRE(csc_ptr && dk && dv && (E == 0 || (csc_src && csc2csr && Pbuf && G && d_agg_v)),
               SPT_E_INVALID, "attn_bwd_targets: null pointer");
+  if (fast::shape_ok(H, D, Dv, fast::kF) && lddv % 4 == 0 && lddk < (1 << 20) &&
+      lddv < (1 << 20) && (reinterpret_cast<uintptr_t>(dv) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(d_agg_v) & 15) == 0) {
+    fast::TgtArgs T;
+    T.csc_ptr = csc_ptr; T.csc_src = csc_src; T.csc2csr = csc2csr; T.num_targets = num_targets;
+    T.Pbuf = Pbuf; T.G = G; T.d_agg_v = d_agg_v;
+    T.dk = dk; T.lddk = (int)lddk; T.dv = dv; T.lddv = (int)lddv;
+    fast::k_attn_bwd_targets_fast<<<(unsigned)ceil_div(num_targets * 32, 256), 256, 0,
+                                    (cudaStream_t)stream_>>>(T);
+    return check_launch("attn_bwd_targets(fast)");
+  }
   k_attn_bwd_targets_generic<<<(unsigned)ceil_div(num_targets, kAttnWarps), kAttnWarps * kWarp,
                                0, (cudaStream_t)stream_>>>(
       csc_ptr, csc_src, csc2csr, num_targets, s, Pbuf, G, d_agg_v, dk, lddk, dv, lddv);

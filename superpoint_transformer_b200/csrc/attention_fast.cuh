@@ -136,25 +136,38 @@ struct EdgeStream {
     issue(0);
     issue(1);
     wait_current();
+    start_tile();
   }
-  // pointer to the features of CSR slot j (advances the ring when j leaves the tile);
-  // j must be visited in increasing order and every slot of the slab must be visited
-  __device__ __forceinline__ const float* row(int64_t j) {
-    if (j >= tile_base + kTile) {
+  // Features of the NEXT CSR slot (slots are consumed strictly in order, one call
+  // per slot, every slot of the slab exactly once).  `left` = slots remaining in the
+  // readable tile, `cur` = running shared-memory pointer.
+  int left;
+  const float* cur;
+  __device__ __forceinline__ void start_tile() {
+    left = (int)min((int64_t)kTile, e1 - tile_base);
+    cur = buf + (gtile % kStages) * kTile * kF;
+  }
+  __device__ __forceinline__ const float* next() {
+    if (left == 0) {
       __syncwarp();                           // every lane is done reading the old tile
       issue(gtile - gbase + kStages);         // refill the stage we just released
       ++gtile;
       tile_base += kTile;
       wait_current();
+      start_tile();
     }
-    return buf + (gtile % kStages) * kTile * kF + (int)(j - tile_base) * kF;
+    const float* r = cur;
+    cur += kF;
+    --left;
+    return r;
   }
 };
 
+
 struct FwdArgs {
-  const float* q; int64_t ldq;
-  const float* k; int64_t ldk;
-  const float* v; int64_t ldv;
+  const float* q; int ldq;
+  const float* k; int ldk;
+  const float* v; int ldv;
   const float* a;
   const int32_t* rowptr; const int32_t* col;
   int64_t num_rows;
@@ -175,14 +188,22 @@ __device__ __forceinline__ float qk_scale_fast(int mode, float value, int deg) {
   }
 }
 
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+// 2^x on the SFU (MUFU.EX2, 2 ulp): the softmax is evaluated in base 2 with the
+// logits pre-multiplied by log2(e); ex2(-inf) = 0 covers the first edge of a row.
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // r_o = b_o + sum_f w[f] * a[f], a read as 8 broadcast LDS.128; 4 partial sums
-__device__ __forceinline__ float gemv32(const float (&w)[kF], float bias, const float* arow,
-                                        float (&av)[kF]) {
+__device__ __forceinline__ float gemv32(const float (&w)[kF], float bias, const float* arow) {
   float s0 = bias, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
   for (int c = 0; c < kF / 4; ++c) {
     float4 t = *reinterpret_cast<const float4*>(arow + 4 * c);
-    av[4 * c + 0] = t.x; av[4 * c + 1] = t.y; av[4 * c + 2] = t.z; av[4 * c + 3] = t.w;
     s0 = fmaf(w[4 * c + 0], t.x, s0);
     s1 = fmaf(w[4 * c + 1], t.y, s1);
     s2 = fmaf(w[4 * c + 2], t.z, s2);
@@ -191,7 +212,7 @@ __device__ __forceinline__ float gemv32(const float (&w)[kF], float bias, const 
   return (s0 + s1) + (s2 + s3);
 }
 
-__global__ void __launch_bounds__(kWarps * kWarp)
+__global__ void __launch_bounds__(kWarps * kWarp, 3)
 k_attn_fwd_fast(FwdArgs P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -220,51 +241,56 @@ k_attn_fwd_fast(FwdArgs P) {
   es.init(P.a, buf, bars, lane);
   es.open(P.rowptr[row0], P.rowptr[row1]);
 
-  const int hsel = (lane >> 3) << 2;   // lane holding compat of my head (0,4,8,12)
+  const bool is_k = lane >= kHD;
+  const int hsel = (lane >> 3) << 2;           // lane holding the logit of my head
+  const int aoff = 4 * (lane & 7);             // my 4 features of a_e (abar)
+  const float* kbase = P.k + (lane & (kHD - 1));   // only dereferenced by k lanes
+  const float* vbase = P.v + 4 * lane;
+  const bool want_abar = P.abar != nullptr;
+  const int* colp = P.col;
+
+  int b = P.rowptr[row0];
   for (int64_t row = row0; row < row1; ++row) {
-    const int b = P.rowptr[row], e = P.rowptr[row + 1];
+    const int e = P.rowptr[row + 1];
     const float scale = qk_scale_fast(P.scale_mode, P.scale_value, e - b);
-    const float qs = (lane < kHD) ? P.q[row * P.ldq + lane] * scale : 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
+    const float qs = is_k ? 0.f : P.q[row * P.ldq + lane] * scale;
+    float m_run = -INFINITY, l_run = 0.f;      // base-2 running max / sum of my head
     float4 accv = make_float4(0.f, 0.f, 0.f, 0.f), acca = make_float4(0.f, 0.f, 0.f, 0.f);
 
     // software prefetch of the gathered key / value rows, one edge ahead
-    int64_t t_cur = (b < e) ? P.col[b] : 0;
     float k_cur = 0.f;
     float4 v_cur = make_float4(0.f, 0.f, 0.f, 0.f);
     if (b < e) {
-      if (lane >= kHD) k_cur = P.k[t_cur * P.ldk + (lane - kHD)];
-      v_cur = *reinterpret_cast<const float4*>(P.v + t_cur * P.ldv + 4 * lane);
+      const unsigned t = (unsigned)colp[b];
+      if (is_k) k_cur = kbase[(size_t)(t * (unsigned)P.ldk)];
+      v_cur = *reinterpret_cast<const float4*>(vbase + (size_t)(t * (unsigned)P.ldv));
     }
     for (int j = b; j < e; ++j) {
       float k_nxt = 0.f;
       float4 v_nxt = make_float4(0.f, 0.f, 0.f, 0.f);
       if (j + 1 < e) {
-        int64_t t_n = P.col[j + 1];
-        if (lane >= kHD) k_nxt = P.k[t_n * P.ldk + (lane - kHD)];
-        v_nxt = *reinterpret_cast<const float4*>(P.v + t_n * P.ldv + 4 * lane);
+        const unsigned t = (unsigned)colp[j + 1];
+        if (is_k) k_nxt = kbase[(size_t)(t * (unsigned)P.ldk)];
+        v_nxt = *reinterpret_cast<const float4*>(vbase + (size_t)(t * (unsigned)P.ldv));
       }
-      const float* arow = es.row(j);
-      float av[kF];
-      float r = gemv32(wreg, bias, arow, av);
-      float val = ((lane < kHD) ? qs : k_cur) + r;          // q_e (lanes<16) | k_e
+      const float* arow = es.next();
+      const float r = gemv32(wreg, bias, arow);
+      const float val = (is_k ? k_cur : qs) + r;            // q_e (lanes<16) | k_e
       float prod = val * __shfl_xor_sync(kFull, val, 16);
       prod += __shfl_xor_sync(kFull, prod, 1);
       prod += __shfl_xor_sync(kFull, prod, 2);              // <q_e,k_e>_h in lanes 4h..4h+3
-      float c = __shfl_sync(kFull, prod, hsel);             // compat of my head
-      float m_new = fmaxf(m_run, c);
-      float alpha = (m_run == -INFINITY) ? 0.f : expf(m_run - m_new);
-      float p = expf(c - m_new);
+      const float c2 = __shfl_sync(kFull, prod, hsel) * kLog2e;   // logit of my head, base 2
+      const float m_new = fmaxf(m_run, c2);
+      const float alpha = ex2(m_run - m_new);
+      const float p = ex2(c2 - m_new);
       l_run = fmaf(l_run, alpha, p);
       m_run = m_new;
       accv.x = fmaf(accv.x, alpha, p * v_cur.x);
       accv.y = fmaf(accv.y, alpha, p * v_cur.y);
       accv.z = fmaf(accv.z, alpha, p * v_cur.z);
       accv.w = fmaf(accv.w, alpha, p * v_cur.w);
-      if (P.abar) {
-        const int f0 = 4 * (lane & 7);
-        // av[] is lane-uniform: select my 4 features without dynamic register indexing
-        float4 a4 = *reinterpret_cast<const float4*>(arow + f0);
+      if (want_abar) {
+        const float4 a4 = *reinterpret_cast<const float4*>(arow + aoff);
         acca.x = fmaf(acca.x, alpha, p * a4.x);
         acca.y = fmaf(acca.y, alpha, p * a4.y);
         acca.z = fmaf(acca.z, alpha, p * a4.z);
@@ -277,23 +303,24 @@ k_attn_fwd_fast(FwdArgs P) {
     const float inv = 1.f / zden;
     *reinterpret_cast<float4*>(P.agg_v + row * kC + 4 * lane) =
         make_float4(accv.x * inv, accv.y * inv, accv.z * inv, accv.w * inv);
-    if (P.abar)
+    if (want_abar)
       *reinterpret_cast<float4*>(P.abar + row * (kH * kF) + 4 * lane) =
           make_float4(acca.x * inv, acca.y * inv, acca.z * inv, acca.w * inv);
     if ((lane & 7) == 0) {
-      int h = lane >> 3;
-      P.m[row * kH + h] = (e > b) ? m_run : 0.f;
+      const int h = lane >> 3;
+      P.m[row * kH + h] = (e > b) ? m_run * kLn2 : 0.f;    // natural-log units
       P.z[row * kH + h] = zden;
       P.sump[row * kH + h] = l_run * inv;
     }
+    b = e;
   }
 }
 
 // ------------------------------------------------------------------ backward rows
 struct BwdArgs {
-  const float* q; int64_t ldq;
-  const float* k; int64_t ldk;
-  const float* v; int64_t ldv;
+  const float* q; int ldq;
+  const float* k; int ldk;
+  const float* v; int ldv;
   const float* a;
   const int32_t* rowptr; const int32_t* col;
   int64_t num_rows;
@@ -302,17 +329,15 @@ struct BwdArgs {
   const float* m; const float* z;
   const float* agg_v; const float* abar;
   const float* d_agg_v; const float* d_abar;
-  float* dq; int64_t lddq;
+  float* dq; int lddq;
   float* da;
   float* Pbuf;   // [E, H]
-  float* G;      // [E, 2HD]  (only the dk_e half [.., HD:2HD] is written)
-  float* dWq; float* dbq; float* dWk; float* dbk;   // accumulated (atomics), nullable
+  float* G;      // [E, 2HD] = [dq_e | dk_e]
   int rows_per_warp;
-  int num_row_blocks;   // persistent: warps loop over row blocks
 };
 
-// smem per warp: stream (kStages tiles) + g[32]; per CTA: dW reduction [32][33]
-__global__ void __launch_bounds__(kWarps * kWarp)
+// smem per warp: stream (kStages tiles) + g[32]
+__global__ void __launch_bounds__(kWarps * kWarp, 2)
 k_attn_bwd_rows_fast(BwdArgs P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -320,7 +345,11 @@ k_attn_bwd_rows_fast(BwdArgs P) {
   unsigned char* after = smem_raw + (size_t)kWarps * kStages * kTileBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(after) + w * kStages;
   float* g_s = reinterpret_cast<float*>(after + kWarps * kStages * 8) + w * 32;
-  float* red = reinterpret_cast<float*>(after + kWarps * kStages * 8) + kWarps * 32;  // [32][33]
+
+  const int64_t gw = (int64_t)blockIdx.x * kWarps + w;
+  const int64_t row0 = gw * P.rows_per_warp;
+  if (row0 >= P.num_rows) return;
+  const int64_t row1 = min(row0 + (int64_t)P.rows_per_warp, P.num_rows);
 
   // lane o: row o of [Wq;Wk] (forward GEMV) ; lane f: column f (da GEMV)
   float wrow[kF], wcol[2 * kHD];
@@ -338,153 +367,247 @@ k_attn_bwd_rows_fast(BwdArgs P) {
       wcol[kHD + oo] = P.Wk ? P.Wk[oo * kF + lane] : 0.f;
     }
   }
-  float dwacc[kF];   // lane o: d[Wq;Wk][o][f]
-  float dbacc = 0.f;
-#pragma unroll
-  for (int f = 0; f < kF; ++f) dwacc[f] = 0.f;
-  const bool want_dw = (P.dWq != nullptr) || (P.dWk != nullptr);
 
+  const bool is_k = lane >= kHD;
   const int hsel = (lane >> 3) << 2;
   const int myhead = lane >> 3;
+  const int aoff = 4 * (lane & 7);
+  const int dcsel = ((lane & 15) >> 2) << 3;     // lane group holding dc of head(o)
+  const float* kbase = P.k + (lane & (kHD - 1));
+  const float* vbase = P.v + 4 * lane;
+  const bool has_dab = P.d_abar != nullptr && P.abar != nullptr;
+  const bool want_da = P.da != nullptr;
+  const int* colp = P.col;
+
   EdgeStream es;
   es.init(P.a, buf, bars, lane);
+  es.open(P.rowptr[row0], P.rowptr[row1]);
 
-  for (int64_t blk = (int64_t)blockIdx.x * kWarps + w; blk < P.num_row_blocks;
-       blk += (int64_t)gridDim.x * kWarps) {
-    const int64_t row0 = blk * P.rows_per_warp;
-    const int64_t row1 = min(row0 + (int64_t)P.rows_per_warp, P.num_rows);
-    es.open(P.rowptr[row0], P.rowptr[row1]);
-    for (int64_t row = row0; row < row1; ++row) {
-      const int b = P.rowptr[row], e = P.rowptr[row + 1];
-      const float scale = qk_scale_fast(P.scale_mode, P.scale_value, e - b);
-      const float qs = (lane < kHD) ? P.q[row * P.ldq + lane] * scale : 0.f;
-      const float m_h = P.m[row * kH + myhead];
-      const float zinv = 1.f / P.z[row * kH + myhead];
-      const float4 dy = *reinterpret_cast<const float4*>(P.d_agg_v + row * kC + 4 * lane);
-      float4 dab = make_float4(0.f, 0.f, 0.f, 0.f);   // d_abar[row][myhead][4(l%8)..]
-      float dabf[kH] = {0.f, 0.f, 0.f, 0.f};          // d_abar[row][h][lane]   (lane = f)
-      const bool has_dab = P.d_abar != nullptr && P.abar != nullptr;
-      // delta_h = <dY_h, agg_v_h> + <dAbar_h, abar_h>
-      float delta;
-      {
-        float4 ag = *reinterpret_cast<const float4*>(P.agg_v + row * kC + 4 * lane);
-        float part = dy.x * ag.x + dy.y * ag.y + dy.z * ag.z + dy.w * ag.w;
-        if (has_dab) {
-          dab = *reinterpret_cast<const float4*>(P.d_abar + row * (kH * kF) + 4 * lane);
-          float4 ab = *reinterpret_cast<const float4*>(P.abar + row * (kH * kF) + 4 * lane);
-          part += dab.x * ab.x + dab.y * ab.y + dab.z * ab.z + dab.w * ab.w;
+  int b = P.rowptr[row0];
+  for (int64_t row = row0; row < row1; ++row) {
+    const int e = P.rowptr[row + 1];
+    const float scale = qk_scale_fast(P.scale_mode, P.scale_value, e - b);
+    const float qs = is_k ? 0.f : P.q[row * P.ldq + lane] * scale;
+    const float m2 = P.m[row * kH + myhead] * kLog2e;
+    const float zinv = 1.f / P.z[row * kH + myhead];
+    const float4 dy = *reinterpret_cast<const float4*>(P.d_agg_v + row * kC + 4 * lane);
+    float4 dab = make_float4(0.f, 0.f, 0.f, 0.f);   // d_abar[row][myhead][4(l%8)..]
+    float dabf[kH] = {0.f, 0.f, 0.f, 0.f};          // d_abar[row][h][lane]   (lane = f)
+    // delta_h = <dY_h, agg_v_h> + <dAbar_h, abar_h>   (= sum_e p_e dp_e)
+    float delta;
+    {
+      const float4 ag = *reinterpret_cast<const float4*>(P.agg_v + row * kC + 4 * lane);
+      float part = dy.x * ag.x + dy.y * ag.y + dy.z * ag.z + dy.w * ag.w;
+      if (has_dab) {
+        dab = *reinterpret_cast<const float4*>(P.d_abar + row * (kH * kF) + 4 * lane);
+        const float4 ab = *reinterpret_cast<const float4*>(P.abar + row * (kH * kF) + 4 * lane);
+        part += dab.x * ab.x + dab.y * ab.y + dab.z * ab.z + dab.w * ab.w;
 #pragma unroll
-          for (int h = 0; h < kH; ++h) dabf[h] = P.d_abar[row * (kH * kF) + h * kF + lane];
-        }
-        part += __shfl_xor_sync(kFull, part, 1);
-        part += __shfl_xor_sync(kFull, part, 2);
-        part += __shfl_xor_sync(kFull, part, 4);
-        delta = part;   // same value in the 8 lanes of my head
+        for (int h = 0; h < kH; ++h) dabf[h] = P.d_abar[row * (kH * kF) + h * kF + lane];
       }
-      float dq_acc = 0.f;
+      part += __shfl_xor_sync(kFull, part, 1);
+      part += __shfl_xor_sync(kFull, part, 2);
+      part += __shfl_xor_sync(kFull, part, 4);
+      delta = part;   // same value in the 8 lanes of my head
+    }
+    float dq_acc = 0.f;
 
-      int64_t t_cur = (b < e) ? P.col[b] : 0;
-      float k_cur = 0.f;
-      float4 v_cur = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (b < e) {
-        if (lane >= kHD) k_cur = P.k[t_cur * P.ldk + (lane - kHD)];
-        v_cur = *reinterpret_cast<const float4*>(P.v + t_cur * P.ldv + 4 * lane);
+    float k_cur = 0.f;
+    float4 v_cur = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (b < e) {
+      const unsigned t = (unsigned)colp[b];
+      if (is_k) k_cur = kbase[(size_t)(t * (unsigned)P.ldk)];
+      v_cur = *reinterpret_cast<const float4*>(vbase + (size_t)(t * (unsigned)P.ldv));
+    }
+    for (int j = b; j < e; ++j) {
+      float k_nxt = 0.f;
+      float4 v_nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j + 1 < e) {
+        const unsigned t = (unsigned)colp[j + 1];
+        if (is_k) k_nxt = kbase[(size_t)(t * (unsigned)P.ldk)];
+        v_nxt = *reinterpret_cast<const float4*>(vbase + (size_t)(t * (unsigned)P.ldv));
       }
-      for (int j = b; j < e; ++j) {
-        float k_nxt = 0.f;
-        float4 v_nxt = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j + 1 < e) {
-          int64_t t_n = P.col[j + 1];
-          if (lane >= kHD) k_nxt = P.k[t_n * P.ldk + (lane - kHD)];
-          v_nxt = *reinterpret_cast<const float4*>(P.v + t_n * P.ldv + 4 * lane);
-        }
-        const float* arow = es.row(j);
-        float av[kF];
-        float r = gemv32(wrow, bias, arow, av);
-        float val = ((lane < kHD) ? qs : k_cur) + r;
-        float other = __shfl_xor_sync(kFull, val, 16);        // k_e for q lanes, q_e for k lanes
-        float prod = val * other;
-        prod += __shfl_xor_sync(kFull, prod, 1);
-        prod += __shfl_xor_sync(kFull, prod, 2);
-        float c = __shfl_sync(kFull, prod, hsel);
-        float p = expf(c - m_h) * zinv;                        // softmax weight of my head
-        // dp_h = <dY_h, v_h> + <dAbar_h, a>
-        float part = dy.x * v_cur.x + dy.y * v_cur.y + dy.z * v_cur.z + dy.w * v_cur.w;
+      const float* arow = es.next();
+      const float r = gemv32(wrow, bias, arow);
+      const float val = (is_k ? k_cur : qs) + r;
+      const float other = __shfl_xor_sync(kFull, val, 16);    // k_e for q lanes, q_e for k lanes
+      float prod = val * other;
+      prod += __shfl_xor_sync(kFull, prod, 1);
+      prod += __shfl_xor_sync(kFull, prod, 2);
+      const float c2 = __shfl_sync(kFull, prod, hsel) * kLog2e;
+      const float p = ex2(c2 - m2) * zinv;                     // softmax weight of my head
+      // dp_h = <dY_h, v_h> + <dAbar_h, a>
+      float part = dy.x * v_cur.x + dy.y * v_cur.y + dy.z * v_cur.z + dy.w * v_cur.w;
+      if (has_dab) {
+        const float4 a4 = *reinterpret_cast<const float4*>(arow + aoff);
+        part += dab.x * a4.x + dab.y * a4.y + dab.z * a4.z + dab.w * a4.w;
+      }
+      part += __shfl_xor_sync(kFull, part, 1);
+      part += __shfl_xor_sync(kFull, part, 2);
+      part += __shfl_xor_sync(kFull, part, 4);
+      const float dc = p * (part - delta);                     // d logit of my head
+      // g_o = dc_{h(o)} * other ; h(o) = (o % 16) / 4 lives in lanes 8*h(o)..
+      const float g = __shfl_sync(kFull, dc, dcsel) * other;   // dq_e (lanes<16) | dk_e
+      if (!is_k) dq_acc += g;
+      P.G[(size_t)j * (2 * kHD) + lane] = g;
+      if ((lane & 7) == 0) P.Pbuf[(size_t)j * kH + myhead] = p;
+      if (want_da) {
+        g_s[lane] = g;
+        __syncwarp();
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
         if (has_dab) {
-          float4 a4 = *reinterpret_cast<const float4*>(arow + 4 * (lane & 7));
-          part += dab.x * a4.x + dab.y * a4.y + dab.z * a4.z + dab.w * a4.w;
+          // sum_h p_h * dAbar[row][h][f=lane]
+          s0 = __shfl_sync(kFull, p, 0) * dabf[0];
+          s1 = __shfl_sync(kFull, p, 8) * dabf[1];
+          s2 = __shfl_sync(kFull, p, 16) * dabf[2];
+          s3 = __shfl_sync(kFull, p, 24) * dabf[3];
         }
-        part += __shfl_xor_sync(kFull, part, 1);
-        part += __shfl_xor_sync(kFull, part, 2);
-        part += __shfl_xor_sync(kFull, part, 4);
-        float dc = p * (part - delta);                         // d compat of my head
-        // g_o = dc_{h(o)} * other ; h(o) = (o % 16) / 4 lives in lanes 8*h(o)..
-        float dco = __shfl_sync(kFull, dc, ((lane & 15) >> 2) << 3);
-        float g = dco * other;                                 // dq_e (lanes<16) | dk_e
-        if (lane < kHD) dq_acc += g;
-        else P.G[(int64_t)j * (2 * kHD) + lane] = g;
-        if ((lane & 7) == 0) P.Pbuf[(int64_t)j * kH + myhead] = p;
-        if (want_dw) {
 #pragma unroll
-          for (int f = 0; f < kF; ++f) dwacc[f] = fmaf(g, av[f], dwacc[f]);
-          dbacc += g;
+        for (int c4 = 0; c4 < (2 * kHD) / 4; ++c4) {
+          const float4 gg = *reinterpret_cast<const float4*>(g_s + 4 * c4);
+          s0 = fmaf(wcol[4 * c4 + 0], gg.x, s0);
+          s1 = fmaf(wcol[4 * c4 + 1], gg.y, s1);
+          s2 = fmaf(wcol[4 * c4 + 2], gg.z, s2);
+          s3 = fmaf(wcol[4 * c4 + 3], gg.w, s3);
         }
-        if (P.da) {
-          g_s[lane] = g;
-          __syncwarp();
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-          if (has_dab) {
-            // sum_h p_h * dAbar[row][h][f=lane]
-            s0 = __shfl_sync(kFull, p, 0) * dabf[0];
-            s1 = __shfl_sync(kFull, p, 8) * dabf[1];
-            s2 = __shfl_sync(kFull, p, 16) * dabf[2];
-            s3 = __shfl_sync(kFull, p, 24) * dabf[3];
-          }
-#pragma unroll
-          for (int c4 = 0; c4 < (2 * kHD) / 4; ++c4) {
-            float4 gg = *reinterpret_cast<const float4*>(g_s + 4 * c4);
-            s0 = fmaf(wcol[4 * c4 + 0], gg.x, s0);
-            s1 = fmaf(wcol[4 * c4 + 1], gg.y, s1);
-            s2 = fmaf(wcol[4 * c4 + 2], gg.z, s2);
-            s3 = fmaf(wcol[4 * c4 + 3], gg.w, s3);
-          }
-          P.da[(int64_t)j * kF + lane] = (s0 + s1) + (s2 + s3);
-          __syncwarp();
-        }
-        k_cur = k_nxt;
-        v_cur = v_nxt;
+        P.da[(size_t)j * kF + lane] = (s0 + s1) + (s2 + s3);
+        __syncwarp();
       }
-      if (lane < kHD) P.dq[row * P.lddq + lane] = dq_acc * scale;
+      k_cur = k_nxt;
+      v_cur = v_nxt;
+    }
+    if (!is_k) P.dq[row * P.lddq + lane] = dq_acc * scale;
+    b = e;
+  }
+}
+
+// ------------------------------------------------------------------ backward targets
+// warp per target t: dv[t] = sum_in p * dY[src] (4 channels per lane),
+// dk[t] = sum_in dk_e (lanes 16-31 read the dk_e half of G, coalesced 64 B).
+struct TgtArgs {
+  const int32_t* csc_ptr; const int32_t* csc_src; const int32_t* csc2csr;
+  int64_t num_targets;
+  const float* Pbuf; const float* G; const float* d_agg_v;
+  float* dk; int lddk; float* dv; int lddv;
+};
+
+__global__ void __launch_bounds__(256)
+k_attn_bwd_targets_fast(TgtArgs P) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (t >= P.num_targets) return;
+  const int b = P.csc_ptr[t], e = P.csc_ptr[t + 1];
+  const int myhead = lane >> 3;
+  const bool is_k = lane >= kHD;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float dk = 0.f;
+  for (int base = b; base < e; base += 32) {
+    // coalesced fetch of up to 32 (slot, source) pairs, then broadcast by shuffle
+    const int n = min(32, e - base);
+    int jj = 0, ss = 0;
+    if (lane < n) {
+      jj = P.csc2csr[base + lane];
+      ss = P.csc_src[base + lane];
+    }
+    int i = 0;
+    for (; i + 1 < n; i += 2) {   // two edges in flight
+      const unsigned j0 = (unsigned)__shfl_sync(kFull, jj, i);
+      const unsigned j1 = (unsigned)__shfl_sync(kFull, jj, i + 1);
+      const unsigned s0 = (unsigned)__shfl_sync(kFull, ss, i);
+      const unsigned s1 = (unsigned)__shfl_sync(kFull, ss, i + 1);
+      const float p0 = P.Pbuf[(size_t)j0 * kH + myhead];
+      const float p1 = P.Pbuf[(size_t)j1 * kH + myhead];
+      const float4 y0 = *reinterpret_cast<const float4*>(P.d_agg_v + (size_t)s0 * kC + 4 * lane);
+      const float4 y1 = *reinterpret_cast<const float4*>(P.d_agg_v + (size_t)s1 * kC + 4 * lane);
+      float g0 = 0.f, g1 = 0.f;
+      if (is_k) {
+        g0 = P.G[(size_t)j0 * (2 * kHD) + lane];
+        g1 = P.G[(size_t)j1 * (2 * kHD) + lane];
+      }
+      acc.x = fmaf(p0, y0.x, acc.x); acc.y = fmaf(p0, y0.y, acc.y);
+      acc.z = fmaf(p0, y0.z, acc.z); acc.w = fmaf(p0, y0.w, acc.w);
+      acc.x = fmaf(p1, y1.x, acc.x); acc.y = fmaf(p1, y1.y, acc.y);
+      acc.z = fmaf(p1, y1.z, acc.z); acc.w = fmaf(p1, y1.w, acc.w);
+      dk += g0;
+      dk += g1;
+    }
+    if (i < n) {
+      const unsigned j0 = (unsigned)__shfl_sync(kFull, jj, i);
+      const unsigned s0 = (unsigned)__shfl_sync(kFull, ss, i);
+      const float p0 = P.Pbuf[(size_t)j0 * kH + myhead];
+      const float4 y0 = *reinterpret_cast<const float4*>(P.d_agg_v + (size_t)s0 * kC + 4 * lane);
+      if (is_k) dk += P.G[(size_t)j0 * (2 * kHD) + lane];
+      acc.x = fmaf(p0, y0.x, acc.x); acc.y = fmaf(p0, y0.y, acc.y);
+      acc.z = fmaf(p0, y0.z, acc.z); acc.w = fmaf(p0, y0.w, acc.w);
     }
   }
+  *reinterpret_cast<float4*>(P.dv + t * P.lddv + 4 * lane) = acc;
+  if (is_k) P.dk[t * P.lddk + (lane - kHD)] = dk;
+}
 
-  // ---- reduce dW over the CTA's warps in shared memory, then one atomic per entry
-  if (want_dw) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < 32 * 33; i += blockDim.x) red[i] = 0.f;
-    __syncthreads();
+// ------------------------------------------------------------------ backward weights
+// d[Wq;Wk] (32x32) += G^T a over an edge slab per CTA, db += colsum(G).  Each warp
+// takes every 8th edge of the slab; lane (oi = lane/4, fi = lane%4) owns the
+// register tile o in {4oi..4oi+3} x f in {8fi..8fi+7} (3 LDG.128 : 32 FFMA).
+struct DwArgs {
+  const float* G; const float* a; int64_t E;
+  float* dWq; float* dbq; float* dWk; float* dbk;
+  int64_t edges_per_cta;
+};
+
+__global__ void __launch_bounds__(256)
+k_attn_bwd_dw_fast(DwArgs P) {
+  __shared__ float red[32 * 33];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int oi = lane >> 2, fi = lane & 3;
+  float acc[4][8];
+  float accb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int f = 0; f < kF; ++f) atomicAdd(&red[lane * 33 + f], dwacc[f]);
-    atomicAdd(&red[lane * 33 + 32], dbacc);
-    __syncthreads();
-    for (int i = threadIdx.x; i < 32 * 33; i += blockDim.x) {
-      int o = i / 33, f = i - o * 33;
-      float val = red[i];
-      if (val == 0.f) continue;
-      if (o < kHD) {
-        if (f < kF) { if (P.dWq) atomicAdd(&P.dWq[o * kF + f], val); }
-        else if (P.dbq) atomicAdd(&P.dbq[o], val);
-      } else {
-        if (f < kF) { if (P.dWk) atomicAdd(&P.dWk[(o - kHD) * kF + f], val); }
-        else if (P.dbk) atomicAdd(&P.dbk[o - kHD], val);
-      }
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  const int64_t e0 = (int64_t)blockIdx.x * P.edges_per_cta;
+  const int64_t e1 = min(e0 + P.edges_per_cta, P.E);
+#pragma unroll 2
+  for (int64_t j = e0 + w; j < e1; j += 8) {
+    const float4 g = ldg_stream4(P.G + j * 32 + 4 * oi);
+    const float4 a0 = ldg_stream4(P.a + j * 32 + 8 * fi);
+    const float4 a1 = ldg_stream4(P.a + j * 32 + 8 * fi + 4);
+    const float gv[4] = {g.x, g.y, g.z, g.w};
+    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) acc[i][jj] = fmaf(gv[i], av[jj], acc[i][jj]);
+      accb[i] += gv[i];
+    }
+  }
+  for (int i = threadIdx.x; i < 32 * 33; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) atomicAdd(&red[(4 * oi + i) * 33 + 8 * fi + jj], acc[i][jj]);
+    if (fi == 0) atomicAdd(&red[(4 * oi + i) * 33 + 32], accb[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * 33; i += blockDim.x) {
+    const int o = i / 33, f = i - o * 33;
+    const float val = red[i];
+    if (val == 0.f) continue;
+    if (o < kHD) {
+      if (f < kF) { if (P.dWq) atomicAdd(&P.dWq[o * kF + f], val); }
+      else if (P.dbq) atomicAdd(&P.dbq[o], val);
+    } else {
+      if (f < kF) { if (P.dWk) atomicAdd(&P.dWk[(o - kHD) * kF + f], val); }
+      else if (P.dbk) atomicAdd(&P.dbk[o - kHD], val);
     }
   }
 }
 
 inline size_t fwd_smem_bytes() { return (size_t)kWarps * kStages * kTileBytes + kWarps * kStages * 8; }
 inline size_t bwd_smem_bytes() {
-  return (size_t)kWarps * kStages * kTileBytes + kWarps * kStages * 8 + kWarps * 32 * 4 + 32 * 33 * 4;
+  return (size_t)kWarps * kStages * kTileBytes + kWarps * kStages * 8 + kWarps * 32 * 4;
 }
 
 }  // namespace fast
