@@ -25,10 +25,13 @@ namespace fast {
 constexpr int kH = 4, kD = 4, kDv = 32, kF = 32;
 constexpr int kHD = kH * kD;        // 16
 constexpr int kC = kH * kDv;        // 128
-constexpr int kTile = 32;           // edges per TMA tile
+constexpr int kTile = 16;           // edges per TMA tile
 constexpr int kTileBytes = kTile * kF * 4;
 constexpr int kWarps = 8;           // warps per CTA
 constexpr int kStages = 2;
+constexpr int kDepth = 6;           // gathered K/V rows in flight per warp (cp.async ring)
+constexpr int kSlotBytes = kC * 4 + kHD * 4;   // one V row (512 B) + one K row (64 B)
+constexpr int kWarpSmem = kStages * kTileBytes + kDepth * kSlotBytes;   // per-warp bytes
 
 __host__ __device__ inline bool shape_ok(int H, int D, int Dv, int F) {
   return H == kH && D == kD && Dv == kDv && F == kF;
@@ -164,6 +167,61 @@ struct EdgeStream {
 };
 
 
+// Per-warp deep prefetch of the gathered key / value rows: for CSR slot j the rows
+// k[col[j]] (64 B) and v[col[j]] (512 B) are copied with cp.async (LDGSTS) into a
+// kDepth-slot shared-memory ring, kDepth slots ahead of their use.  Every lane
+// later reads back exactly the bytes it copied itself, so no warp barrier is
+// needed; one commit group per slot keeps the per-thread group counts aligned.
+struct GatherStream {
+  unsigned char* ring;      // warp-private: kDepth * kSlotBytes
+  const int32_t* col;
+  const float* kbase;       // P.k + (lane - kHD)   (k lanes only)
+  const float* vbase;       // P.v + 4 * lane
+  unsigned ldk, ldv;
+  int64_t e1;               // end of the slab
+  int slot;                 // ring slot of the CSR slot being consumed
+  int lane;
+  bool is_k;
+
+  __device__ __forceinline__ void issue(int64_t j, int s) {
+    if (j < e1) {
+      const unsigned t = (unsigned)col[j];
+      unsigned char* dst = ring + s * kSlotBytes;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(
+                       smem_u32(dst + 16 * lane)),
+                   "l"(vbase + (size_t)(t * ldv))
+                   : "memory");
+      if (is_k)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(
+                         smem_u32(dst + kC * 4 + 4 * (lane - kHD))),
+                     "l"(kbase + (size_t)(t * ldk))
+                     : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  __device__ __forceinline__ void open(int64_t e0, int64_t e1_) {
+    e1 = e1_;
+    slot = 0;
+#pragma unroll
+    for (int d = 0; d < kDepth; ++d) issue(e0 + d, d);
+  }
+  // make slot j readable (all but the kDepth most recent groups have landed)
+  __device__ __forceinline__ void wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kDepth - 1) : "memory");
+  }
+  __device__ __forceinline__ float4 v() const {
+    return *reinterpret_cast<const float4*>(ring + slot * kSlotBytes + 16 * lane);
+  }
+  __device__ __forceinline__ float k() const {
+    return *reinterpret_cast<const float*>(ring + slot * kSlotBytes + kC * 4 + 4 * (lane - kHD));
+  }
+  // done with CSR slot j: refill its ring slot with CSR slot j + kDepth
+  __device__ __forceinline__ void release(int64_t j) {
+    issue(j + kDepth, slot);
+    slot = (slot + 1 == kDepth) ? 0 : slot + 1;
+  }
+};
+
 struct FwdArgs {
   const float* q; int ldq;
   const float* k; int ldk;
@@ -216,9 +274,9 @@ __global__ void __launch_bounds__(kWarps * kWarp, 3)
 k_attn_fwd_fast(FwdArgs P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* buf = reinterpret_cast<float*>(smem_raw) + (size_t)w * kStages * kTile * kF;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(
-      smem_raw + (size_t)kWarps * kStages * kTileBytes) + w * kStages;
+  unsigned char* mine = smem_raw + (size_t)w * kWarpSmem;
+  float* buf = reinterpret_cast<float*>(mine);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kWarps * kWarpSmem) + w * kStages;
 
   const int64_t gw = (int64_t)blockIdx.x * kWarps + w;
   const int64_t row0 = gw * P.rows_per_warp;
@@ -237,17 +295,23 @@ k_attn_fwd_fast(FwdArgs P) {
     if (W && B) bias = B[o];
   }
 
-  EdgeStream es;
-  es.init(P.a, buf, bars, lane);
-  es.open(P.rowptr[row0], P.rowptr[row1]);
-
   const bool is_k = lane >= kHD;
   const int hsel = (lane >> 3) << 2;           // lane holding the logit of my head
   const int aoff = 4 * (lane & 7);             // my 4 features of a_e (abar)
-  const float* kbase = P.k + (lane & (kHD - 1));   // only dereferenced by k lanes
-  const float* vbase = P.v + 4 * lane;
   const bool want_abar = P.abar != nullptr;
-  const int* colp = P.col;
+  const int64_t e_begin = P.rowptr[row0], e_end = P.rowptr[row1];
+
+  EdgeStream es;
+  es.init(P.a, buf, bars, lane);
+  es.open(e_begin, e_end);
+  GatherStream gs;
+  gs.ring = mine + kStages * kTileBytes;
+  gs.col = P.col;
+  gs.kbase = P.k + (lane & (kHD - 1));
+  gs.vbase = P.v + 4 * lane;
+  gs.ldk = (unsigned)P.ldk; gs.ldv = (unsigned)P.ldv;
+  gs.lane = lane; gs.is_k = is_k;
+  gs.open(e_begin, e_end);
 
   int b = P.rowptr[row0];
   for (int64_t row = row0; row < row1; ++row) {
@@ -257,24 +321,13 @@ k_attn_fwd_fast(FwdArgs P) {
     float m_run = -INFINITY, l_run = 0.f;      // base-2 running max / sum of my head
     float4 accv = make_float4(0.f, 0.f, 0.f, 0.f), acca = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    // software prefetch of the gathered key / value rows, one edge ahead
-    float k_cur = 0.f;
-    float4 v_cur = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (b < e) {
-      const unsigned t = (unsigned)colp[b];
-      if (is_k) k_cur = kbase[(size_t)(t * (unsigned)P.ldk)];
-      v_cur = *reinterpret_cast<const float4*>(vbase + (size_t)(t * (unsigned)P.ldv));
-    }
     for (int j = b; j < e; ++j) {
-      float k_nxt = 0.f;
-      float4 v_nxt = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (j + 1 < e) {
-        const unsigned t = (unsigned)colp[j + 1];
-        if (is_k) k_nxt = kbase[(size_t)(t * (unsigned)P.ldk)];
-        v_nxt = *reinterpret_cast<const float4*>(vbase + (size_t)(t * (unsigned)P.ldv));
-      }
       const float* arow = es.next();
       const float r = gemv32(wreg, bias, arow);
+      gs.wait();                                            // k/v rows of slot j landed
+      const float k_cur = is_k ? gs.k() : 0.f;
+      const float4 v_cur = gs.v();
+      gs.release(j);                                        // prefetch slot j + kDepth
       const float val = (is_k ? k_cur : qs) + r;            // q_e (lanes<16) | k_e
       float prod = val * __shfl_xor_sync(kFull, val, 16);
       prod += __shfl_xor_sync(kFull, prod, 1);
@@ -296,8 +349,6 @@ k_attn_fwd_fast(FwdArgs P) {
         acca.z = fmaf(acca.z, alpha, p * a4.z);
         acca.w = fmaf(acca.w, alpha, p * a4.w);
       }
-      k_cur = k_nxt;
-      v_cur = v_nxt;
     }
     const float zden = l_run + 1e-16f;
     const float inv = 1.f / zden;
@@ -341,8 +392,9 @@ __global__ void __launch_bounds__(kWarps * kWarp, 2)
 k_attn_bwd_rows_fast(BwdArgs P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* buf = reinterpret_cast<float*>(smem_raw) + (size_t)w * kStages * kTile * kF;
-  unsigned char* after = smem_raw + (size_t)kWarps * kStages * kTileBytes;
+  unsigned char* mine = smem_raw + (size_t)w * kWarpSmem;
+  float* buf = reinterpret_cast<float*>(mine);
+  unsigned char* after = smem_raw + (size_t)kWarps * kWarpSmem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(after) + w * kStages;
   float* g_s = reinterpret_cast<float*>(after + kWarps * kStages * 8) + w * 32;
 
@@ -373,15 +425,21 @@ k_attn_bwd_rows_fast(BwdArgs P) {
   const int myhead = lane >> 3;
   const int aoff = 4 * (lane & 7);
   const int dcsel = ((lane & 15) >> 2) << 3;     // lane group holding dc of head(o)
-  const float* kbase = P.k + (lane & (kHD - 1));
-  const float* vbase = P.v + 4 * lane;
   const bool has_dab = P.d_abar != nullptr && P.abar != nullptr;
   const bool want_da = P.da != nullptr;
-  const int* colp = P.col;
+  const int64_t e_begin = P.rowptr[row0], e_end = P.rowptr[row1];
 
   EdgeStream es;
   es.init(P.a, buf, bars, lane);
-  es.open(P.rowptr[row0], P.rowptr[row1]);
+  es.open(e_begin, e_end);
+  GatherStream gs;
+  gs.ring = mine + kStages * kTileBytes;
+  gs.col = P.col;
+  gs.kbase = P.k + (lane & (kHD - 1));
+  gs.vbase = P.v + 4 * lane;
+  gs.ldk = (unsigned)P.ldk; gs.ldv = (unsigned)P.ldv;
+  gs.lane = lane; gs.is_k = is_k;
+  gs.open(e_begin, e_end);
 
   int b = P.rowptr[row0];
   for (int64_t row = row0; row < row1; ++row) {
@@ -412,23 +470,13 @@ k_attn_bwd_rows_fast(BwdArgs P) {
     }
     float dq_acc = 0.f;
 
-    float k_cur = 0.f;
-    float4 v_cur = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (b < e) {
-      const unsigned t = (unsigned)colp[b];
-      if (is_k) k_cur = kbase[(size_t)(t * (unsigned)P.ldk)];
-      v_cur = *reinterpret_cast<const float4*>(vbase + (size_t)(t * (unsigned)P.ldv));
-    }
     for (int j = b; j < e; ++j) {
-      float k_nxt = 0.f;
-      float4 v_nxt = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (j + 1 < e) {
-        const unsigned t = (unsigned)colp[j + 1];
-        if (is_k) k_nxt = kbase[(size_t)(t * (unsigned)P.ldk)];
-        v_nxt = *reinterpret_cast<const float4*>(vbase + (size_t)(t * (unsigned)P.ldv));
-      }
       const float* arow = es.next();
       const float r = gemv32(wrow, bias, arow);
+      gs.wait();
+      const float k_cur = is_k ? gs.k() : 0.f;
+      const float4 v_cur = gs.v();
+      gs.release(j);
       const float val = (is_k ? k_cur : qs) + r;
       const float other = __shfl_xor_sync(kFull, val, 16);    // k_e for q lanes, q_e for k lanes
       float prod = val * other;
@@ -473,8 +521,6 @@ k_attn_bwd_rows_fast(BwdArgs P) {
         P.da[(size_t)j * kF + lane] = (s0 + s1) + (s2 + s3);
         __syncwarp();
       }
-      k_cur = k_nxt;
-      v_cur = v_nxt;
     }
     if (!is_k) P.dq[row * P.lddq + lane] = dq_acc * scale;
     b = e;
@@ -605,9 +651,9 @@ k_attn_bwd_dw_fast(DwArgs P) {
   }
 }
 
-inline size_t fwd_smem_bytes() { return (size_t)kWarps * kStages * kTileBytes + kWarps * kStages * 8; }
+inline size_t fwd_smem_bytes() { return (size_t)kWarps * kWarpSmem + kWarps * kStages * 8; }
 inline size_t bwd_smem_bytes() {
-  return (size_t)kWarps * kStages * kTileBytes + kWarps * kStages * 8 + kWarps * 32 * 4;
+  return (size_t)kWarps * kWarpSmem + kWarps * kStages * 8 + kWarps * 32 * 4;
 }
 
 }  // namespace fast
