@@ -109,6 +109,13 @@ int spt_gather_rows_i64(const float* x, const int64_t* idx, int64_t n_out,
 int spt_gather_rows_i32(const float* x, const int32_t* idx, int64_t n_out,
                         int64_t C, float* out, void* stream);
 
+/* x = hi + lo exactly, hi = x truncated to tf32 (13 low mantissa bits cleared).
+ * Operand split of the "3xTF32" dense projections: the reference runs its Linear
+ * layers as cuBLAS GEMMs (src/nn/attention.py:191,318; src/nn/mlp.py:45); here they
+ * are three tensor-core TF32 GEMMs on (hi,lo) pairs with fp32 accumulation, which
+ * keeps fp32-level accuracy (~2^-21 relative). */
+int spt_split_tf32(const float* x, int64_t n, float* hi, float* lo, void* stream);
+
 /* ------------------------------------------------------------------------- *
  *  Segment pooling  (src/nn/pool.py:44-82 -> PyG *Aggregation -> scatter)    *
  * ------------------------------------------------------------------------- */

@@ -32,6 +32,7 @@ SIGNATURES = {
     "spt_segment_sum_i64": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
     "spt_gather_rows_i64": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
     "spt_gather_rows_i32": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
+    "spt_split_tf32": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
     "spt_segment_pool_fwd": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int, c_ptr,
                                      c_ptr, c_ptr]),
     "spt_segment_pool_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int,
@@ -81,7 +82,7 @@ def load():
         if _LIB is not None:
             return _LIB
         path = _build.LIB_PATH
-        if not os.path.exists(path):
+        if not os.path.exists(path) or _build.needs_build():
             try:
                 _build.build()
             except Exception as e:  # noqa: BLE001

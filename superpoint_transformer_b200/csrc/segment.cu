@@ -351,3 +351,48 @@ int spt_unitsphere_fwd(const float* pos, const int64_t* parent, const int32_t* p
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ tf32 split
+// x = hi + lo exactly, hi = x with the 13 low mantissa bits cleared (a tf32 number),
+// lo = x - hi.  Feeding (hi,lo) pairs to three tensor-core TF32 GEMMs
+// (hi*hi + lo*hi + hi*lo, fp32 accumulate) reproduces an fp32 GEMM to ~2^-21
+// relative error ("3xTF32"); used by the dense projections (qkv, out_proj, MLPs).
+namespace spt {
+__global__ void k_split_tf32(const float* __restrict__ x, int64_t n4, int64_t n,
+                             float* __restrict__ hi, float* __restrict__ lo) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    float4 v = reinterpret_cast<const float4*>(x)[i];
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+    reinterpret_cast<float4*>(hi)[i] = h;
+    reinterpret_cast<float4*>(lo)[i] = l;
+  }
+  // scalar tail
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    int64_t j = (n4 << 2) + threadIdx.x;
+    float v = x[j];
+    float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    hi[j] = h;
+    lo[j] = v - h;
+  }
+}
+}  // namespace spt
+
+extern "C" int spt_split_tf32(const float* x, int64_t n, float* hi, float* lo, void* stream_) {
+  SPT_REQUIRE(n >= 0, SPT_E_INVALID, "split_tf32: negative size");
+  if (n == 0) return SPT_OK;
+  SPT_REQUIRE(x && hi && lo, SPT_E_INVALID, "split_tf32: null pointer");
+  SPT_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(hi) |
+                reinterpret_cast<uintptr_t>(lo)) & 15) == 0,
+              SPT_E_INVALID, "split_tf32: pointers must be 16-byte aligned");
+  int64_t n4 = n >> 2;
+  int64_t blocks = spt::ceil_div(n4 > 0 ? n4 : 1, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  spt::k_split_tf32<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(x, n4, n, hi, lo);
+  return spt::check_launch("split_tf32");
+}

@@ -10,6 +10,8 @@ Linears is one fused CUDA pass per direction (csrc/attention.cu) instead of the
 import torch
 from torch import nn
 
+from .linear import Linear
+
 from .. import ops
 from ..utils.nn import build_qk_scale
 
@@ -21,7 +23,7 @@ def _encoder(spec, in_dim, out_dim, build):
     shared, module (reference src/nn/attention.py:127-157)."""
     if not isinstance(spec, bool):
         return spec
-    return nn.Linear(in_dim, out_dim) if (spec and build) else None
+    return Linear(in_dim, out_dim) if (spec and build) else None
 
 
 class SelfAttentionBlock(nn.Module):
@@ -40,7 +42,7 @@ class SelfAttentionBlock(nn.Module):
         self.qk_share_rpe = qk_share_rpe
         self.q_on_minus_rpe = q_on_minus_rpe
 
-        self.qkv = nn.Linear(dim, qk_dim * 2 * num_heads + dim, bias=qkv_bias)
+        self.qkv = Linear(dim, qk_dim * 2 * num_heads + dim, bias=qkv_bias)
 
         qk_out = qk_dim if heads_share_rpe else qk_dim * num_heads
         v_out = dim // num_heads if heads_share_rpe else dim
@@ -53,8 +55,8 @@ class SelfAttentionBlock(nn.Module):
                                     not (kd_on and qk_share_rpe))
         self.v_rpe = _encoder(v_rpe, in_rpe_dim, v_out, True)
 
-        self.in_proj = nn.Linear(in_dim, dim) if in_dim is not None else None
-        self.out_proj = nn.Linear(dim, out_dim) if out_dim is not None else None
+        self.in_proj = Linear(in_dim, dim) if in_dim is not None else None
+        self.out_proj = Linear(dim, out_dim) if out_dim is not None else None
 
         if attn_drop is not None and attn_drop > 0:
             raise NotImplementedError(
@@ -126,7 +128,7 @@ class SelfAttentionBlock(nn.Module):
             # of H tiny batched GEMMs (4x the MACs, but a well-shaped library GEMM)
             blocks = [Wv] * H if self.heads_share_rpe else list(Wv.view(H, Dv, F))
             Wbd = torch.block_diag(*blocks)              # [C, H*F]
-            rv = abar.reshape(N, H * F) @ Wbd.t()        # [N, C]
+            rv = ops.linear(abar.reshape(N, H * F), Wbd)   # [N, C]
             if bv is not None:
                 b_full = bv.repeat(H) if self.heads_share_rpe else bv
                 rv = rv + sump.repeat_interleave(Dv, dim=1) * b_full.view(1, -1)

@@ -7,6 +7,8 @@ when no norm follows; src/nn/mlp.py:37-57) so checkpoints are interchangeable.
 """
 from torch import nn
 
+from .linear import Linear
+
 from .norm import BatchNorm, INDEX_BASED_NORMS
 
 __all__ = ['MLP', 'FFN', 'Classifier']
@@ -18,7 +20,7 @@ def _layers(dims, activation, last_activation, norm, last_norm, drop, device):
     n = len(dims) - 1
     for i in range(n):
         is_last = i == n - 1
-        mods.append(nn.Linear(dims[i], dims[i + 1], bias=norm is None, device=device))
+        mods.append(Linear(dims[i], dims[i + 1], bias=norm is None, device=device))
         if norm is not None and (last_norm or not is_last):
             mods.append(norm(dims[i + 1]).to(device))
         if activation is not None and (last_activation or not is_last):
@@ -57,7 +59,7 @@ class Classifier(nn.Module):
 
     def __init__(self, in_dim, num_classes, bias=True, device='cpu'):
         super().__init__()
-        self.classifier = nn.Linear(in_dim, num_classes, bias=bias, device=device)
+        self.classifier = Linear(in_dim, num_classes, bias=bias, device=device)
 
     def forward(self, x):
         return self.classifier(x)

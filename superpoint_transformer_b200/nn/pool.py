@@ -8,6 +8,8 @@ pools reuse the fused attention core with rows = parents, edges = children.
 import torch
 from torch import nn
 
+from .linear import Linear
+
 from .. import ops
 from ..utils.nn import build_qk_scale, LearnableParameter
 
@@ -61,14 +63,14 @@ class BaseAttentivePool(nn.Module):
         self.dim, self.num_heads, self.qk_dim = dim, num_heads, qk_dim
         self.qk_scale = build_qk_scale(dim, num_heads, qk_scale)
         self.heads_share_rpe = heads_share_rpe
-        self.kv = nn.Linear(dim, qk_dim * num_heads + dim, bias=qkv_bias)
+        self.kv = Linear(dim, qk_dim * num_heads + dim, bias=qkv_bias)
         rpe_dim = qk_dim if heads_share_rpe else qk_dim * num_heads
         self.k_rpe = k_rpe if not isinstance(k_rpe, bool) else \
-            (nn.Linear(in_rpe_dim, rpe_dim) if k_rpe else None)
+            (Linear(in_rpe_dim, rpe_dim) if k_rpe else None)
         self.q_rpe = q_rpe if not isinstance(q_rpe, bool) else \
-            (nn.Linear(in_rpe_dim, rpe_dim) if q_rpe else None)
-        self.in_proj = nn.Linear(in_dim, dim) if in_dim is not None else None
-        self.out_proj = nn.Linear(dim, out_dim) if out_dim is not None else None
+            (Linear(in_rpe_dim, rpe_dim) if q_rpe else None)
+        self.in_proj = Linear(in_dim, dim) if in_dim is not None else None
+        self.out_proj = Linear(dim, out_dim) if out_dim is not None else None
         self.out_drop = nn.Dropout(drop) if drop is not None and drop > 0 else None
 
     def _rpe_weights(self, lin):
@@ -128,7 +130,7 @@ class AttentivePool(BaseAttentivePool):
                          qkv_bias=qkv_bias, qk_dim=qk_dim, qk_scale=qk_scale,
                          attn_drop=attn_drop, drop=drop, in_rpe_dim=in_rpe_dim, k_rpe=k_rpe,
                          q_rpe=q_rpe, v_rpe=v_rpe, heads_share_rpe=heads_share_rpe)
-        self.q = nn.Linear(q_in_dim, qk_dim * num_heads, bias=qkv_bias)
+        self.q = Linear(q_in_dim, qk_dim * num_heads, bias=qkv_bias)
 
     def _get_query(self, x_parent):
         return self.q(x_parent)

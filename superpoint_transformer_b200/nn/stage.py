@@ -5,6 +5,8 @@ of :574-806 without the sparse-CNN branch)."""
 import torch
 from torch import nn
 
+from .linear import Linear
+
 from .fusion import CatFusion, fusion_factory
 from .mlp import MLP
 from .norm import BatchNorm, UnitSphereNorm
@@ -25,7 +27,7 @@ def _shared_rpe(rpe, num_blocks, num_heads, in_dim, out_dim, blocks_share, heads
     if not heads_share:
         out_dim = out_dim * num_heads
     if blocks_share and rpe:
-        return [nn.Linear(in_dim, out_dim)] * num_blocks
+        return [Linear(in_dim, out_dim)] * num_blocks
     return [rpe] * num_blocks
 
 

@@ -315,6 +315,85 @@ def index_unpool(x, idx):
 
 
 # ---------------------------------------------------------------------------
+# dense projections: fp32-accurate "3xTF32" GEMMs on the tensor cores
+# ---------------------------------------------------------------------------
+LINEAR_3XTF32_MIN_ROWS = 4096   # below this a plain fp32 GEMM is as fast
+
+
+def _split_tf32(x):
+    lib = _lib.load()
+    x = x.contiguous()
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.spt_split_tf32(_p(x), x.numel(), _p(hi), _p(lo), _stream()),
+                   "spt_split_tf32")
+    _count()
+    return hi, lo
+
+
+class _tf32_matmul:
+    """scoped enable of TF32 tensor-core GEMMs: only the three split GEMMs run in
+    TF32; every other matmul of the process stays IEEE fp32."""
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+        return False
+
+
+def _mm3(ah, al, bh, bl, out=None):
+    """ah@bh + al@bh + ah@bl with fp32 accumulation inside the tensor cores."""
+    with _tf32_matmul():
+        out = torch.mm(ah, bh) if out is None else out.addmm_(ah, bh)
+        out.addmm_(al, bh)
+        out.addmm_(ah, bl)
+    return out
+
+
+class _Linear3x(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W, b):
+        xh, xl = _split_tf32(x)
+        Wh, Wl = _split_tf32(W)
+        with _tf32_matmul():
+            out = torch.addmm(b, xh, Wh.t()) if b is not None else torch.mm(xh, Wh.t())
+            out.addmm_(xl, Wh.t())
+            out.addmm_(xh, Wl.t())
+        ctx.save_for_backward(x, W)
+        ctx.has_bias = b is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, W = ctx.saved_tensors
+        g = g.contiguous()
+        gh, gl = _split_tf32(g)
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            Wh, Wl = _split_tf32(W)
+            dx = _mm3(gh, gl, Wh, Wl)
+        if ctx.needs_input_grad[1]:
+            xh, xl = _split_tf32(x)
+            dW = _mm3(gh.t(), gl.t(), xh, xl)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = g.sum(0)
+        return dx, dW, db
+
+
+def linear(x, weight, bias=None):
+    """y = x W^T + b.  Large row counts go through the 3xTF32 tensor-core path
+    (fp32-accurate); small ones and non-CUDA / non-fp32 inputs use the plain GEMM."""
+    if (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
+            and x.shape[0] >= LINEAR_3XTF32_MIN_ROWS and x.numel() % 4 == 0
+            and weight.numel() % 4 == 0):
+        return _Linear3x.apply(x, weight, bias)
+    return torch.nn.functional.linear(x, weight, bias)
+
+
+# ---------------------------------------------------------------------------
 # segment pooling
 # ---------------------------------------------------------------------------
 def _segment_pool_fwd(x, seg, reduce):

@@ -15,6 +15,7 @@ from . import ops
 from .nn import (Stage, PointStage, DownNFuseStage, UpNFuseStage, BatchNorm, CatFusion,
                  MLP, LayerNorm)
 from .nn.pool import BaseAttentivePool, pool_factory
+from .nn.linear import Linear
 from .utils.nn import VersionHolder, listify_with_reference
 
 __all__ = ['SPT']
@@ -29,7 +30,7 @@ def _stage_rpe_specs(rpe, num_stages, in_dim, out_dim, stages_share):
             "A prebuilt RPE encoder is passed to all stages: set stages_share_rpe=True"
         return [rpe] * num_stages
     if stages_share and rpe:
-        return [nn.Linear(in_dim, out_dim)] * num_stages
+        return [Linear(in_dim, out_dim)] * num_stages
     return [rpe] * num_stages
 
 
