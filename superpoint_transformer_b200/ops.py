@@ -318,6 +318,11 @@ def index_unpool(x, idx):
 # dense projections: fp32-accurate "3xTF32" GEMMs on the tensor cores
 # ---------------------------------------------------------------------------
 LINEAR_3XTF32_MIN_ROWS = 4096   # below this a plain fp32 GEMM is as fast
+# Measured on B200 (profiles/r1_notes.md): three library TF32 GEMMs + operand splits are
+# SLOWER than one cuBLAS SGEMM for these skinny (K,N <= 300) shapes because every pass
+# re-streams the [rows, K] operand; the split path therefore stays off until the fused
+# single-pass kernel replaces it.
+LINEAR_3XTF32 = False
 
 
 def _split_tf32(x):
@@ -386,7 +391,7 @@ class _Linear3x(torch.autograd.Function):
 def linear(x, weight, bias=None):
     """y = x W^T + b.  Large row counts go through the 3xTF32 tensor-core path
     (fp32-accurate); small ones and non-CUDA / non-fp32 inputs use the plain GEMM."""
-    if (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
+    if (LINEAR_3XTF32 and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
             and x.shape[0] >= LINEAR_3XTF32_MIN_ROWS and x.numel() % 4 == 0
             and weight.numel() % 4 == 0):
         return _Linear3x.apply(x, weight, bias)
