@@ -116,6 +116,21 @@ int spt_gather_rows_i32(const float* x, const int32_t* idx, int64_t n_out,
  * keeps fp32-level accuracy (~2^-21 relative). */
 int spt_split_tf32(const float* x, int64_t n, float* hi, float* lo, void* stream);
 
+/* Dense projections on the tensor cores, fp32-accurate (in-register 3xTF32 split,
+ * fp32 accumulate), operand streamed once:
+ *   gemm_nt     : C[M,N]  = A[M,K] . B[N,K]^T + bias[N]   (nn.Linear forward; dX with
+ *                 B = W^T).  K, lda, ldb multiples of 4; A, B 16-byte aligned.
+ *   gemm_tn_acc : C[N,K] += A[M,N]^T . B[M,K] ; colsumA[N] += column sums of A
+ *                 (dW and dbias of nn.Linear; fp32 atomics, caller zero-fills).
+ * Replaces the cuBLAS calls behind src/nn/attention.py:191,226,239,295,318 and
+ * src/nn/mlp.py:45 (which the reference runs in TF32, src/train.py:93-94). */
+int spt_gemm_nt(const float* A, int64_t M, int64_t K, int64_t lda, const float* B,
+                int64_t N, int64_t ldb, const float* bias /*nullable*/, float* C,
+                int64_t ldc, void* stream);
+int spt_gemm_tn_acc(const float* A, int64_t M, int64_t N, int64_t lda, const float* B,
+                    int64_t K, int64_t ldb, float* C, int64_t ldc,
+                    float* colsumA /*nullable*/, void* stream);
+
 /* ------------------------------------------------------------------------- *
  *  Segment pooling  (src/nn/pool.py:44-82 -> PyG *Aggregation -> scatter)    *
  * ------------------------------------------------------------------------- */

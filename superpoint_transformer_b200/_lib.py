@@ -33,6 +33,10 @@ SIGNATURES = {
     "spt_gather_rows_i64": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
     "spt_gather_rows_i32": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
     "spt_split_tf32": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
+    "spt_gemm_nt": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_ptr,
+                            c_i64, c_ptr]),
+    "spt_gemm_tn_acc": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_i64, c_ptr,
+                                c_i64, c_ptr, c_ptr]),
     "spt_segment_pool_fwd": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int, c_ptr,
                                      c_ptr, c_ptr]),
     "spt_segment_pool_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int,

@@ -24,6 +24,7 @@ SOURCES = [
     "segment.cu",
     "norm.cu",
     "attention.cu",
+    "gemm.cu",
     "edge_features.cu",
 ]
 HEADERS = sorted(f for f in os.listdir(HERE) if f.endswith((".cuh", ".h"))) + \

@@ -46,9 +46,11 @@ k_graphnorm_stats(const float* __restrict__ x, const float* __restrict__ dy,
   __shared__ float red[NACC][kNormThreads * VEC];
   int cx = threadIdx.x % tx;
   int ry = threadIdx.x / tx;
-  int64_t r0 = (int64_t)blockIdx.x * kNormRows;
-  int64_t r1 = min(r0 + (int64_t)kNormRows, N);
-  int64_t first_b = batch ? batch[r0] : 0;
+  // persistent CTA: slabs blockIdx.x, blockIdx.x + gridDim.x, ... ; partial sums
+  // stay in registers across slabs and leave the CTA once (few fp64 atomics)
+  const int64_t nslabs = (N + kNormRows - 1) / kNormRows;
+  const int64_t first_row = (int64_t)blockIdx.x * kNormRows;
+  int64_t first_b = batch ? batch[first_row < N ? first_row : 0] : 0;
   for (int64_t ct = 0; ct < C; ct += (int64_t)tx * VEC) {
     int64_t c0 = ct + (int64_t)cx * VEC;
     bool active = c0 < C;
@@ -64,7 +66,12 @@ k_graphnorm_stats(const float* __restrict__ x, const float* __restrict__ dy,
     int64_t cur = -1;
     int nrows = 0;
     bool uniform = true;
+    int64_t rows_seen = 0;
     if (active) {
+     for (int64_t slab = blockIdx.x; slab < nslabs; slab += gridDim.x) {
+      const int64_t r0 = slab * kNormRows;
+      const int64_t r1 = min(r0 + (int64_t)kNormRows, N);
+      rows_seen += r1 - r0;
       for (int64_t r = r0 + ry; r < r1; r += ty) {
         int64_t b = batch ? batch[r] : 0;
         if (b < 0 || b >= B) continue;
@@ -125,8 +132,9 @@ k_graphnorm_stats(const float* __restrict__ x, const float* __restrict__ dy,
         }
         ++nrows;
       }
+     }
     }
-    // CTA-uniform decision: every row of the slab in segment first_b?
+    // CTA-uniform decision: every row of this CTA's slabs in segment first_b?
     int all_uniform = __syncthreads_and(uniform ? 1 : 0);
     if (all_uniform && ty > 1) {
 #pragma unroll
@@ -146,7 +154,7 @@ k_graphnorm_stats(const float* __restrict__ x, const float* __restrict__ dy,
           atomicAdd(&acc0[first_b * C + c0 + v], (double)s0);
           if (NACC == 2) atomicAdd(&acc1[first_b * C + c0 + v], (double)s1);
         }
-        if (MODE == 0 && c0 == 0) atomicAdd(&cnt_out[first_b], (double)(r1 - r0));
+        if (MODE == 0 && c0 == 0) atomicAdd(&cnt_out[first_b], (double)rows_seen);
       }
       __syncthreads();
     } else if (active && cur >= 0) {
@@ -391,7 +399,7 @@ int spt_graphnorm_fwd(const float* x, const int64_t* batch, int64_t N, int64_t C
   }
   int vec = (C % 4 == 0) ? 4 : 1;
   ColMap cm = col_map(C, vec);
-  unsigned slabs = (unsigned)ceil_div(N > 0 ? N : 1, kNormRows);
+  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, kNormRows), 148 * 2);
   int64_t total = N * (C / vec);
   int agrid = (int)imin(ceil_div(total > 0 ? total : 1, kNormThreads), 148 * 16);
   if (N > 0) {
@@ -443,7 +451,7 @@ int spt_graphnorm_bwd(const float* x, const float* dy, const int64_t* batch, int
   }
   int vec = (C % 4 == 0) ? 4 : 1;
   ColMap cm = col_map(C, vec);
-  unsigned slabs = (unsigned)ceil_div(N > 0 ? N : 1, kNormRows);
+  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, kNormRows), 148 * 2);
   int64_t total = N * (C / vec);
   int agrid = (int)imin(ceil_div(total > 0 ? total : 1, kNormThreads), 148 * 16);
   if (N > 0) {

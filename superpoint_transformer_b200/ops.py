@@ -317,15 +317,12 @@ def index_unpool(x, idx):
 # ---------------------------------------------------------------------------
 # dense projections: fp32-accurate "3xTF32" GEMMs on the tensor cores
 # ---------------------------------------------------------------------------
-LINEAR_3XTF32_MIN_ROWS = 4096   # below this a plain fp32 GEMM is as fast
-# Measured on B200 (profiles/r1_notes.md): three library TF32 GEMMs + operand splits are
-# SLOWER than one cuBLAS SGEMM for these skinny (K,N <= 300) shapes because every pass
-# re-streams the [rows, K] operand; the split path therefore stays off until the fused
-# single-pass kernel replaces it.
-LINEAR_3XTF32 = False
+LINEAR_TC_MIN_ROWS = 2048   # below this the plain library GEMM is as fast
+LINEAR_TC = True            # fused single-pass 3xTF32 tensor-core GEMMs (csrc/gemm.cu)
 
 
 def _split_tf32(x):
+    """(hi, lo) with x == hi + lo exactly, hi a tf32 number (spt_split_tf32)."""
     lib = _lib.load()
     x = x.contiguous()
     hi, lo = torch.empty_like(x), torch.empty_like(x)
@@ -336,65 +333,56 @@ def _split_tf32(x):
     return hi, lo
 
 
-class _tf32_matmul:
-    """scoped enable of TF32 tensor-core GEMMs: only the three split GEMMs run in
-    TF32; every other matmul of the process stays IEEE fp32."""
-
-    def __enter__(self):
-        self.prev = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = True
-
-    def __exit__(self, *exc):
-        torch.backends.cuda.matmul.allow_tf32 = self.prev
-        return False
-
-
-def _mm3(ah, al, bh, bl, out=None):
-    """ah@bh + al@bh + ah@bl with fp32 accumulation inside the tensor cores."""
-    with _tf32_matmul():
-        out = torch.mm(ah, bh) if out is None else out.addmm_(ah, bh)
-        out.addmm_(al, bh)
-        out.addmm_(ah, bl)
+def _gemm_nt(a, b, bias=None):
+    """a [M,K] @ b[N,K]^T (+ bias) on the tensor cores, fp32-accurate."""
+    lib = _lib.load()
+    M, K = a.shape
+    N = b.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device), _timed('gemm_nt', M=M, N=N, K=K):
+        _lib.check(lib.spt_gemm_nt(_p(a), M, K, a.stride(0), _p(b), N, b.stride(0), _p(bias),
+                                   _p(out), N, _stream()), "spt_gemm_nt")
+    _count()
     return out
 
 
-class _Linear3x(torch.autograd.Function):
+class _LinearTC(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, W, b):
-        xh, xl = _split_tf32(x)
-        Wh, Wl = _split_tf32(W)
-        with _tf32_matmul():
-            out = torch.addmm(b, xh, Wh.t()) if b is not None else torch.mm(xh, Wh.t())
-            out.addmm_(xl, Wh.t())
-            out.addmm_(xh, Wl.t())
         ctx.save_for_backward(x, W)
         ctx.has_bias = b is not None
-        return out
+        return _gemm_nt(x, W, b)
 
     @staticmethod
     def backward(ctx, g):
         x, W = ctx.saved_tensors
+        lib = _lib.load()
         g = g.contiguous()
-        gh, gl = _split_tf32(g)
+        M, N = g.shape
+        K = x.shape[1]
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
-            Wh, Wl = _split_tf32(W)
-            dx = _mm3(gh, gl, Wh, Wl)
-        if ctx.needs_input_grad[1]:
-            xh, xl = _split_tf32(x)
-            dW = _mm3(gh.t(), gl.t(), xh, xl)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = g.sum(0)
+            dx = _gemm_nt(g, W.t().contiguous())
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dW = torch.zeros((N, K), dtype=torch.float32, device=g.device)
+            db = torch.zeros(N, dtype=torch.float32, device=g.device) if ctx.has_bias else None
+            with torch.cuda.device(g.device), _timed('gemm_tn', M=M, N=N, K=K):
+                _lib.check(lib.spt_gemm_tn_acc(_p(g), M, N, g.stride(0), _p(x), K, x.stride(0),
+                                               _p(dW), K, _p(db), _stream()),
+                           "spt_gemm_tn_acc")
+            _count()
         return dx, dW, db
 
 
 def linear(x, weight, bias=None):
-    """y = x W^T + b.  Large row counts go through the 3xTF32 tensor-core path
-    (fp32-accurate); small ones and non-CUDA / non-fp32 inputs use the plain GEMM."""
-    if (LINEAR_3XTF32 and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
-            and x.shape[0] >= LINEAR_3XTF32_MIN_ROWS and x.numel() % 4 == 0
-            and weight.numel() % 4 == 0):
-        return _Linear3x.apply(x, weight, bias)
+    """y = x W^T + b.  Large row counts run the fused 3xTF32 tensor-core kernels
+    (fp32-accurate, operand streamed once); tiny or oddly-shaped ones (K or N not a
+    multiple of 4) use the plain fp32 library GEMM."""
+    if (LINEAR_TC and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
+            and x.shape[0] >= LINEAR_TC_MIN_ROWS and x.shape[1] % 4 == 0
+            and weight.shape[0] % 4 == 0 and x.is_contiguous() and weight.is_contiguous()
+            and x.data_ptr() % 16 == 0 and weight.data_ptr() % 16 == 0):
+        return _LinearTC.apply(x, weight, bias)
     return torch.nn.functional.linear(x, weight, bias)
 
 
