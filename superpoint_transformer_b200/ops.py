@@ -379,10 +379,17 @@ def linear(x, weight, bias=None):
     (fp32-accurate, operand streamed once); tiny or oddly-shaped ones (K or N not a
     multiple of 4) use the plain fp32 library GEMM."""
     if (LINEAR_TC and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
-            and x.shape[0] >= LINEAR_TC_MIN_ROWS and x.shape[1] % 4 == 0
-            and weight.shape[0] % 4 == 0 and x.is_contiguous() and weight.is_contiguous()
-            and x.data_ptr() % 16 == 0 and weight.data_ptr() % 16 == 0):
-        return _LinearTC.apply(x, weight, bias)
+            and x.shape[0] >= LINEAR_TC_MIN_ROWS and weight.shape[0] % 4 == 0):
+        K = x.shape[1]
+        if K % 4 != 0:
+            # e.g. the 18 raw edge features: zero-pad K to a multiple of 4 (one extra
+            # pass over x, still far cheaper than the SIMT library GEMM it replaces)
+            pad = 4 - K % 4
+            x = torch.nn.functional.pad(x, (0, pad))
+            weight = torch.nn.functional.pad(weight, (0, pad))
+        x, weight = x.contiguous(), weight.contiguous()
+        if x.data_ptr() % 16 == 0 and weight.data_ptr() % 16 == 0:
+            return _LinearTC.apply(x, weight, bias)
     return torch.nn.functional.linear(x, weight, bias)
 
 
