@@ -269,19 +269,8 @@ def run_own(args):
             d.diameter = None
         return step(res_nag, res_labels)
 
-    for _ in range(args.warmup):
-        resident_step()
-    # count my launches per step and time my kernels with CUDA events (eager steps: the
-    # same kernels on the same inputs; events cannot be read back from a graph replay)
-    ops.enable_event_timing(True)
-    l0 = ops.launch_count()
-    n_evt_steps = 3
-    ms_eager, _, _ = timed(resident_step, n_evt_steps)
-    launches_per_step = (ops.launch_count() - l0) // n_evt_steps
-    records = ops.timing_records()
-    ops.enable_event_timing(False)
-    ms_eager_step = ms_eager / n_evt_steps
-
+    # CUDA graphs are captured first (their own warm-up runs on the capture stream, before
+    # any eager step creates autograd nodes on the default stream)
     graph_mode, run_resident = False, resident_step
     if not args.no_graph:
         try:
@@ -304,8 +293,20 @@ def run_own(args):
         sampler.start()
         time.sleep(0.3)
     ms, t0, t1 = timed(run_resident, args.steps)
-    launches = launches_per_step * args.steps
     clocks = sampler.stop(t0, t1) if sampler else None
+    # count my launches per step and time my kernels with CUDA events (eager steps: the
+    # same kernels on the same inputs; events cannot be read back from a graph replay)
+    for _ in range(2):
+        resident_step()
+    ops.enable_event_timing(True)
+    l0 = ops.launch_count()
+    n_evt_steps = 3
+    ms_eager, _, _ = timed(resident_step, n_evt_steps)
+    launches_per_step = (ops.launch_count() - l0) // n_evt_steps
+    records = ops.timing_records()
+    ops.enable_event_timing(False)
+    ms_eager_step = ms_eager / n_evt_steps
+    launches = launches_per_step * args.steps
     ms_per_step = ms / args.steps
     value = world * n1 / (ms_per_step * 1e-3)
 

@@ -476,7 +476,8 @@ def unit_sphere_norm(pos, idx=None, w=None, num_super=None):
     wf = None if w is None else w.detach().float().contiguous()
     if idx is None:
         Np = 1
-        ptr = torch.tensor([0, N], dtype=torch.int32, device=dev)
+        # built on the device (no H2D copy: keeps the call CUDA-graph capturable)
+        ptr = torch.arange(2, dtype=torch.int32, device=dev) * N
         points, parent = None, None
     else:
         idx = _i64c(idx)
