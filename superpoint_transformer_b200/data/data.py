@@ -144,6 +144,11 @@ class Data:
         if z is None or z.shape[0] != n or z.device != dev:
             z = torch.zeros(n, dtype=torch.long, device=dev)
             self._store['_zero_batch'] = z
+            if z.is_cuda:
+                # single graph: tell the norm kernels the segment count up front (no
+                # batch.max() host sync -> the forward stays CUDA-graph capturable)
+                from .. import ops
+                ops.register_num_segments(z, 1)
         return z
 
     def add_keys_to(self, keys, to='x', strict=True, delete_after=False):
@@ -166,7 +171,7 @@ class Data:
         setattr(self, to, torch.cat(feats, dim=1))
 
     def to(self, device, non_blocking=False):
-        out = Data()
+        out = self.__class__()
         for k, v in self._store.items():
             if isinstance(v, torch.Tensor):
                 out._store[k] = v.to(device, non_blocking=non_blocking)
@@ -174,6 +179,11 @@ class Data:
                 out._store[k] = v.to(device, non_blocking=non_blocking)
             else:
                 out._store[k] = v
+        out._store.pop('_zero_batch', None)
+        b, ng = out._store.get('batch'), out._store.get('_num_graphs')
+        if b is not None and ng is not None and b.is_cuda:
+            from .. import ops
+            ops.register_num_segments(b, ng)
         return out
 
     def cuda(self, non_blocking=False):
@@ -183,7 +193,7 @@ class Data:
         return self.to('cpu')
 
     def clone(self):
-        out = Data()
+        out = self.__class__()
         out._store.update(self._store)
         return out
 
@@ -240,6 +250,9 @@ class Batch(Data):
             torch.arange(len(data_list), device=dev),
             torch.tensor(n_nodes, device=dev))
         out['_num_graphs'] = len(data_list)
+        if out['batch'].is_cuda:
+            from .. import ops
+            ops.register_num_segments(out['batch'], len(data_list))
         return out
 
     @property
