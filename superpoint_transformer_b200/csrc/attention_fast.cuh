@@ -25,13 +25,12 @@ namespace fast {
 constexpr int kH = 4, kD = 4, kDv = 32, kF = 32;
 constexpr int kHD = kH * kD;        // 16
 constexpr int kC = kH * kDv;        // 128
-constexpr int kTile = 16;           // edges per TMA tile
-constexpr int kTileBytes = kTile * kF * 4;
+constexpr int kTile = 8;            // CSR slots per tile
 constexpr int kWarps = 8;           // warps per CTA
-constexpr int kStages = 2;
-constexpr int kDepth = 6;           // gathered K/V rows in flight per warp (cp.async ring)
-constexpr int kSlotBytes = kC * 4 + kHD * 4;   // one V row (512 B) + one K row (64 B)
-constexpr int kWarpSmem = kStages * kTileBytes + kDepth * kSlotBytes;   // per-warp bytes
+constexpr int kStages = 2;          // tiles in flight per warp
+constexpr int kSlotBytes = kC * 4 + kHD * 4;   // one gathered V row (512 B) + K row (64 B)
+constexpr int kStageBytes = kTile * kF * 4 + kTile * kSlotBytes;   // a tile + gathered rows
+constexpr int kWarpSmem = kStages * kStageBytes;                   // per-warp bytes
 
 __host__ __device__ inline bool shape_ok(int H, int D, int Dv, int F) {
   return H == kH && D == kD && Dv == kDv && F == kF;
@@ -88,23 +87,32 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
       : "memory");
 }
 
-// Per-warp streaming reader of CSR-ordered edge-feature slabs [e0, e1).  The two
-// mbarriers are initialised ONCE per warp (`init`); tiles are numbered globally
-// across successive slabs (`open`) so the stage / phase-parity sequence simply
-// continues — barriers are never re-initialised.
-struct EdgeStream {
-  const float* a;       // [E, kF] global
-  float* buf;           // warp-private smem: kStages * kTile * kF floats
-  uint64_t* bar;        // kStages mbarriers
-  int64_t e0, e1;       // current slab
-  int64_t tile_base;    // first edge of the tile currently readable
-  int gtile;            // global index of that tile
-  int gbase;            // global index of the slab's first tile
-  int gnext;            // global index the next slab will start at
+// Per-warp tile stream over a contiguous slab [e0, e1) of CSR slots.  One tile =
+// kTile slots; for every tile the warp stages, kStages tiles ahead of use:
+//   * the edge features a[slot, :F]  — ONE 1-D TMA bulk copy (slots are contiguous),
+//     completion on a warp-private mbarrier (initialised once; tiles are numbered
+//     globally so the stage / phase-parity sequence continues across slabs);
+//   * the gathered rows k[col[slot]] (64 B) and v[col[slot]] (512 B) — cp.async (LDGSTS),
+//     issued for the whole tile at once: the tile's col[] is fetched with one coalesced
+//     load and broadcast by shuffle, every lane copies (and later reads back) its own
+//     16-byte / 4-byte piece of each row, one commit group per tile.
+struct TileStream {
+  const float* a;           // [E, kF]
+  const int32_t* col;
+  const float* kbase;       // P.k + (lane - kHD)   (dereferenced by k lanes only)
+  const float* vbase;       // P.v + 4 * lane
+  unsigned ldk, ldv;
+  unsigned char* smem;      // warp-private: kStages * kStageBytes
+  uint64_t* bar;            // kStages mbarriers
   int lane;
+  bool is_k;
+  int64_t e0, e1, tile_base;
+  int gtile, gbase, gnext;
+  int left;                 // slots not yet consumed in the readable tile
+  const unsigned char* cur; // stage-relative cursor: a row at cur, gathered rows at cur_g
+  const unsigned char* cur_g;
 
-  __device__ __forceinline__ void init(const float* a_, float* buf_, uint64_t* bar_, int lane_) {
-    a = a_; buf = buf_; bar = bar_; lane = lane_;
+  __device__ __forceinline__ void init() {
     gnext = 0;
     if (lane == 0) {
 #pragma unroll
@@ -113,112 +121,80 @@ struct EdgeStream {
     }
     __syncwarp();
   }
-  // issue slab-local tile k
-  __device__ __forceinline__ void issue(int k) {
-    int64_t b = e0 + (int64_t)k * kTile;
-    if (b >= e1) return;
-    int n = (int)min((int64_t)kTile, e1 - b);
-    int s = (gbase + k) % kStages;
-    if (lane == 0) {
-      mbar_expect_tx(&bar[s], (uint32_t)n * kF * 4);
-      tma_load_1d(buf + s * kTile * kF, a + b * kF, (uint32_t)n * kF * 4, &bar[s]);
+  __device__ __forceinline__ void issue(int k) {   // slab-local tile k
+    const int64_t b = e0 + (int64_t)k * kTile;
+    if (b < e1) {
+      const int n = (int)min((int64_t)kTile, e1 - b);
+      unsigned char* st = smem + ((gbase + k) % kStages) * kStageBytes;
+      if (lane == 0) {
+        uint64_t* br = &bar[(gbase + k) % kStages];
+        mbar_expect_tx(br, (uint32_t)n * kF * 4);
+        tma_load_1d(st, a + b * kF, (uint32_t)n * kF * 4, br);
+      }
+      const int c = (lane < n) ? col[b + lane] : 0;
+      unsigned char* g = st + kTile * kF * 4;
+#pragma unroll
+      for (int e = 0; e < kTile; ++e) {
+        if (e < n) {
+          const unsigned t = (unsigned)__shfl_sync(kFull, c, e);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(
+                           smem_u32(g + e * kSlotBytes + 16 * lane)),
+                       "l"(vbase + (size_t)(t * ldv))
+                       : "memory");
+          if (is_k)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(
+                             smem_u32(g + e * kSlotBytes + kC * 4 + 4 * (lane - kHD))),
+                         "l"(kbase + (size_t)(t * ldk))
+                         : "memory");
+        }
+      }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");   // (possibly empty) group per tile
   }
   __device__ __forceinline__ void wait_current() {
     mbar_wait(&bar[gtile % kStages], (uint32_t)((gtile / kStages) & 1), gtile, gbase);
+    asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 1) : "memory");
+    left = (int)min((int64_t)kTile, e1 - tile_base);
+    cur = smem + (gtile % kStages) * kStageBytes;
+    cur_g = cur + kTile * kF * 4;
   }
-  // start streaming a new slab; the previous one must have been read to its end
   __device__ __forceinline__ void open(int64_t e0_, int64_t e1_) {
     e0 = e0_; e1 = e1_;
+    left = 0;
     if (e1 <= e0) return;
-    __syncwarp();                   // all lanes finished the previous slab's tiles
+    __syncwarp();
     gbase = gnext;
     gnext = gbase + (int)((e1 - e0 + kTile - 1) / kTile);
     gtile = gbase;
     tile_base = e0;
-    issue(0);
-    issue(1);
+#pragma unroll
+    for (int k = 0; k < kStages; ++k) issue(k);
     wait_current();
-    start_tile();
+    cur -= kF * 4;            // next() pre-increments
+    cur_g -= kSlotBytes;
   }
-  // Features of the NEXT CSR slot (slots are consumed strictly in order, one call
-  // per slot, every slot of the slab exactly once).  `left` = slots remaining in the
-  // readable tile, `cur` = running shared-memory pointer.
-  int left;
-  const float* cur;
-  __device__ __forceinline__ void start_tile() {
-    left = (int)min((int64_t)kTile, e1 - tile_base);
-    cur = buf + (gtile % kStages) * kTile * kF;
-  }
-  __device__ __forceinline__ const float* next() {
+  // advance to the next CSR slot (strictly in order, every slot exactly once)
+  __device__ __forceinline__ void next() {
     if (left == 0) {
-      __syncwarp();                           // every lane is done reading the old tile
-      issue(gtile - gbase + kStages);         // refill the stage we just released
+      __syncwarp();                           // every lane is done with the old tile
+      issue(gtile - gbase + kStages);         // refill the stage just released
       ++gtile;
       tile_base += kTile;
       wait_current();
-      start_tile();
+    } else {
+      cur += kF * 4;
+      cur_g += kSlotBytes;
     }
-    const float* r = cur;
-    cur += kF;
     --left;
-    return r;
   }
-};
-
-
-// Per-warp deep prefetch of the gathered key / value rows: for CSR slot j the rows
-// k[col[j]] (64 B) and v[col[j]] (512 B) are copied with cp.async (LDGSTS) into a
-// kDepth-slot shared-memory ring, kDepth slots ahead of their use.  Every lane
-// later reads back exactly the bytes it copied itself, so no warp barrier is
-// needed; one commit group per slot keeps the per-thread group counts aligned.
-struct GatherStream {
-  unsigned char* ring;      // warp-private: kDepth * kSlotBytes
-  const int32_t* col;
-  const float* kbase;       // P.k + (lane - kHD)   (k lanes only)
-  const float* vbase;       // P.v + 4 * lane
-  unsigned ldk, ldv;
-  int64_t e1;               // end of the slab
-  int slot;                 // ring slot of the CSR slot being consumed
-  int lane;
-  bool is_k;
-
-  __device__ __forceinline__ void issue(int64_t j, int s) {
-    if (j < e1) {
-      const unsigned t = (unsigned)col[j];
-      unsigned char* dst = ring + s * kSlotBytes;
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(
-                       smem_u32(dst + 16 * lane)),
-                   "l"(vbase + (size_t)(t * ldv))
-                   : "memory");
-      if (is_k)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(
-                         smem_u32(dst + kC * 4 + 4 * (lane - kHD))),
-                     "l"(kbase + (size_t)(t * ldk))
-                     : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-  __device__ __forceinline__ void open(int64_t e0, int64_t e1_) {
-    e1 = e1_;
-    slot = 0;
-#pragma unroll
-    for (int d = 0; d < kDepth; ++d) issue(e0 + d, d);
-  }
-  // make slot j readable (all but the kDepth most recent groups have landed)
-  __device__ __forceinline__ void wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(kDepth - 1) : "memory");
+  __device__ __forceinline__ const float* a_row() const {
+    return reinterpret_cast<const float*>(cur);
   }
   __device__ __forceinline__ float4 v() const {
-    return *reinterpret_cast<const float4*>(ring + slot * kSlotBytes + 16 * lane);
+    return *reinterpret_cast<const float4*>(cur_g + 16 * lane);
   }
   __device__ __forceinline__ float k() const {
-    return *reinterpret_cast<const float*>(ring + slot * kSlotBytes + kC * 4 + 4 * (lane - kHD));
-  }
-  // done with CSR slot j: refill its ring slot with CSR slot j + kDepth
-  __device__ __forceinline__ void release(int64_t j) {
-    issue(j + kDepth, slot);
-    slot = (slot + 1 == kDepth) ? 0 : slot + 1;
+    return *reinterpret_cast<const float*>(cur_g + kC * 4 + 4 * (lane - kHD));
   }
 };
 
@@ -275,7 +251,6 @@ k_attn_fwd_fast(FwdArgs P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* mine = smem_raw + (size_t)w * kWarpSmem;
-  float* buf = reinterpret_cast<float*>(mine);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kWarps * kWarpSmem) + w * kStages;
 
   const int64_t gw = (int64_t)blockIdx.x * kWarps + w;
@@ -301,17 +276,14 @@ k_attn_fwd_fast(FwdArgs P) {
   const bool want_abar = P.abar != nullptr;
   const int64_t e_begin = P.rowptr[row0], e_end = P.rowptr[row1];
 
-  EdgeStream es;
-  es.init(P.a, buf, bars, lane);
-  es.open(e_begin, e_end);
-  GatherStream gs;
-  gs.ring = mine + kStages * kTileBytes;
-  gs.col = P.col;
-  gs.kbase = P.k + (lane & (kHD - 1));
-  gs.vbase = P.v + 4 * lane;
-  gs.ldk = (unsigned)P.ldk; gs.ldv = (unsigned)P.ldv;
-  gs.lane = lane; gs.is_k = is_k;
-  gs.open(e_begin, e_end);
+  TileStream ts;
+  ts.a = P.a; ts.col = P.col;
+  ts.kbase = P.k + (lane & (kHD - 1));
+  ts.vbase = P.v + 4 * lane;
+  ts.ldk = (unsigned)P.ldk; ts.ldv = (unsigned)P.ldv;
+  ts.smem = mine; ts.bar = bars; ts.lane = lane; ts.is_k = is_k;
+  ts.init();
+  ts.open(e_begin, e_end);
 
   int b = P.rowptr[row0];
   for (int64_t row = row0; row < row1; ++row) {
@@ -322,12 +294,11 @@ k_attn_fwd_fast(FwdArgs P) {
     float4 accv = make_float4(0.f, 0.f, 0.f, 0.f), acca = make_float4(0.f, 0.f, 0.f, 0.f);
 
     for (int j = b; j < e; ++j) {
-      const float* arow = es.next();
+      ts.next();
+      const float* arow = ts.a_row();
       const float r = gemv32(wreg, bias, arow);
-      gs.wait();                                            // k/v rows of slot j landed
-      const float k_cur = is_k ? gs.k() : 0.f;
-      const float4 v_cur = gs.v();
-      gs.release(j);                                        // prefetch slot j + kDepth
+      const float k_cur = is_k ? ts.k() : 0.f;
+      const float4 v_cur = ts.v();
       const float val = (is_k ? k_cur : qs) + r;            // q_e (lanes<16) | k_e
       float prod = val * __shfl_xor_sync(kFull, val, 16);
       prod += __shfl_xor_sync(kFull, prod, 1);
@@ -393,7 +364,6 @@ k_attn_bwd_rows_fast(BwdArgs P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* mine = smem_raw + (size_t)w * kWarpSmem;
-  float* buf = reinterpret_cast<float*>(mine);
   unsigned char* after = smem_raw + (size_t)kWarps * kWarpSmem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(after) + w * kStages;
   float* g_s = reinterpret_cast<float*>(after + kWarps * kStages * 8) + w * 32;
@@ -429,17 +399,14 @@ k_attn_bwd_rows_fast(BwdArgs P) {
   const bool want_da = P.da != nullptr;
   const int64_t e_begin = P.rowptr[row0], e_end = P.rowptr[row1];
 
-  EdgeStream es;
-  es.init(P.a, buf, bars, lane);
-  es.open(e_begin, e_end);
-  GatherStream gs;
-  gs.ring = mine + kStages * kTileBytes;
-  gs.col = P.col;
-  gs.kbase = P.k + (lane & (kHD - 1));
-  gs.vbase = P.v + 4 * lane;
-  gs.ldk = (unsigned)P.ldk; gs.ldv = (unsigned)P.ldv;
-  gs.lane = lane; gs.is_k = is_k;
-  gs.open(e_begin, e_end);
+  TileStream ts;
+  ts.a = P.a; ts.col = P.col;
+  ts.kbase = P.k + (lane & (kHD - 1));
+  ts.vbase = P.v + 4 * lane;
+  ts.ldk = (unsigned)P.ldk; ts.ldv = (unsigned)P.ldv;
+  ts.smem = mine; ts.bar = bars; ts.lane = lane; ts.is_k = is_k;
+  ts.init();
+  ts.open(e_begin, e_end);
 
   int b = P.rowptr[row0];
   for (int64_t row = row0; row < row1; ++row) {
@@ -471,12 +438,11 @@ k_attn_bwd_rows_fast(BwdArgs P) {
     float dq_acc = 0.f;
 
     for (int j = b; j < e; ++j) {
-      const float* arow = es.next();
+      ts.next();
+      const float* arow = ts.a_row();
       const float r = gemv32(wrow, bias, arow);
-      gs.wait();
-      const float k_cur = is_k ? gs.k() : 0.f;
-      const float4 v_cur = gs.v();
-      gs.release(j);
+      const float k_cur = is_k ? ts.k() : 0.f;
+      const float4 v_cur = ts.v();
       const float val = (is_k ? k_cur : qs) + r;
       const float other = __shfl_xor_sync(kFull, val, 16);    // k_e for q lanes, q_e for k lanes
       float prod = val * other;
