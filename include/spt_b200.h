@@ -273,6 +273,18 @@ int spt_edge_features_fwd(const int64_t* se, const float* ea, const float* pos,
                           int add_self_loops, int64_t* edge_index_out,
                           float* edge_attr_out, void* stream);
 
+/* On-the-fly VERTICAL (child -> parent) edge features, default key set of
+ * _on_the_fly_vertical_edge_features (src/transforms/graph.py:1336-1416):
+ *   v_edge_attr[i] = [centroid_dir(3), sqrt(centroid_dist), |n_child . n_parent|,
+ *                     d log_length, d log_surface, d log_volume, d log_size]  ([Nc, 9])
+ * child_logs [4, Nc] / parent_logs [4, Np] = stacked (log_length, log_surface,
+ * log_volume, log_size); parent = super_index of the child level (int64). */
+int spt_vertical_edge_features_fwd(const float* child_pos, const float* parent_pos,
+                                   const float* child_normal, const float* parent_normal,
+                                   const float* child_logs, const float* parent_logs,
+                                   const int64_t* parent, int64_t Nc, int64_t Np,
+                                   float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -295,6 +295,19 @@ def edge_feature_case(ref):
     one = ref.NAGAddSelfLoops()(one)
     raw.update(sym_edge_index=ei2, sym_edge_attr=ea2, loop_edge_index=one[1].edge_index,
                loop_edge_attr=one[1].edge_attr)
+    # vertical (child -> parent) features through the reference function
+    nag2 = make_nag([300, 50], mean_degree=8, seed=78)
+    child, parent = nag2[1], nag2[2]
+    k = int(child.super_index[0])
+    parent.pos[k] = child.pos[0]          # coincident centroids: 0/0 -> NaN -> 0
+    vkeys = ('log_length', 'log_surface', 'log_volume', 'log_size')
+    raw['v'] = dict(child_pos=child.pos.clone(), parent_pos=parent.pos.clone(),
+                    child_normal=child.normal.clone(), parent_normal=parent.normal.clone(),
+                    child_logs=[child[kk].clone() for kk in vkeys],
+                    parent_logs=[parent[kk].clone() for kk in vkeys],
+                    super_index=child.super_index.clone())
+    out_child = ref.on_the_fly_vertical_edge_features(child.clone(), parent.clone())
+    raw['v']['v_edge_attr'] = out_child.v_edge_attr
     return raw
 
 

@@ -454,3 +454,24 @@ def horizontal_edge_features(se, ea, pos, normal, log_length, log_surface, log_v
 def add_self_loops(edge_index, edge_attr, num_nodes):
     """NAGAddSelfLoops (src/transforms/graph.py:1419-1452)."""
     return L.add_self_loops(edge_index, edge_attr, fill_value=0., num_nodes=num_nodes)
+
+
+def vertical_edge_features(child_pos, parent_pos, child_normal, parent_normal, child_logs,
+                           parent_logs, idx):
+    """_on_the_fly_vertical_edge_features with the default 7 keys
+    (src/transforms/graph.py:1336-1416).  *_logs = (log_length, log_surface, log_volume,
+    log_size) tensors.  Returns v_edge_attr [Nc, 9]."""
+    f_list = []
+    d = parent_pos[idx] - child_pos                                   # :1373-1376
+    dist = d.norm(dim=1)
+    d = d / dist.view(-1, 1)
+    dist = dist.sqrt()
+    d[d.isnan()] = 0                                                  # :1379-1380
+    d = d.clip(-1, 1)
+    f_list.append(d)
+    f_list.append(dist.view(-1, 1))
+    f = (child_normal * parent_normal[idx]).sum(dim=1).abs()          # :1388-1392
+    f_list.append(f.view(-1, 1))
+    for c, p_ in zip(child_logs, parent_logs):                        # :1394-1408
+        f_list.append((p_[idx] - c).view(-1, 1))
+    return torch.cat(f_list, dim=1)                                   # :1413

@@ -230,5 +230,6 @@ def load():
     graph = _load('src.transforms.graph', 'src/transforms/graph.py')
     ns.on_the_fly_horizontal_edge_features = graph._on_the_fly_horizontal_edge_features
     ns.NAGAddSelfLoops = graph.NAGAddSelfLoops
+    ns.on_the_fly_vertical_edge_features = graph._on_the_fly_vertical_edge_features
     _LOADED = ns
     return ns

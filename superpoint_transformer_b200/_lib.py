@@ -69,6 +69,8 @@ SIGNATURES = {
                                      c_ptr, c_ptr, c_ptr]),
     "spt_edge_features_fwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                       c_ptr, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr]),
+    "spt_vertical_edge_features_fwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                               c_i64, c_i64, c_ptr, c_ptr]),
 }
 
 

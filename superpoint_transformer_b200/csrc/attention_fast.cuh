@@ -26,7 +26,7 @@ constexpr int kH = 4, kD = 4, kDv = 32, kF = 32;
 constexpr int kHD = kH * kD;        // 16
 constexpr int kC = kH * kDv;        // 128
 constexpr int kTile = 8;            // CSR slots per tile
-constexpr int kWarps = 8;           // warps per CTA
+constexpr int kWarps = 4;           // warps per CTA (45 KB smem/CTA -> 5 CTAs/SM)
 constexpr int kStages = 2;          // tiles in flight per warp
 constexpr int kSlotBytes = kC * 4 + kHD * 4;   // one gathered V row (512 B) + K row (64 B)
 constexpr int kStageBytes = kTile * kF * 4 + kTile * kSlotBytes;   // a tile + gathered rows
@@ -246,7 +246,7 @@ __device__ __forceinline__ float gemv32(const float (&w)[kF], float bias, const 
   return (s0 + s1) + (s2 + s3);
 }
 
-__global__ void __launch_bounds__(kWarps * kWarp, 3)
+__global__ void __launch_bounds__(kWarps * kWarp, 5)
 k_attn_fwd_fast(FwdArgs P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -359,7 +359,7 @@ struct BwdArgs {
 };
 
 // smem per warp: stream (kStages tiles) + g[32]
-__global__ void __launch_bounds__(kWarps * kWarp, 2)
+__global__ void __launch_bounds__(kWarps * kWarp, 4)
 k_attn_bwd_rows_fast(BwdArgs P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -580,18 +580,30 @@ k_attn_bwd_dw_fast(DwArgs P) {
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
   const int64_t e0 = (int64_t)blockIdx.x * P.edges_per_cta;
   const int64_t e1 = min(e0 + P.edges_per_cta, P.E);
-#pragma unroll 2
-  for (int64_t j = e0 + w; j < e1; j += 8) {
-    const float4 g = ldg_stream4(P.G + j * 32 + 4 * oi);
-    const float4 a0 = ldg_stream4(P.a + j * 32 + 8 * fi);
-    const float4 a1 = ldg_stream4(P.a + j * 32 + 8 * fi + 4);
-    const float gv[4] = {g.x, g.y, g.z, g.w};
-    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  // 4 edges in flight per warp iteration (12 independent 16-byte streaming loads)
+  for (int64_t j0 = e0 + 4 * w; j0 < e1; j0 += 32) {
+    float4 g[4], a0[4], a1[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int u = 0; u < 4; ++u) {
+      const int64_t j = j0 + u;
+      if (j < e1) {
+        g[u] = ldg_stream4(P.G + j * 32 + 4 * oi);
+        a0[u] = ldg_stream4(P.a + j * 32 + 8 * fi);
+        a1[u] = ldg_stream4(P.a + j * 32 + 8 * fi + 4);
+      } else {
+        g[u] = a0[u] = a1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj) acc[i][jj] = fmaf(gv[i], av[jj], acc[i][jj]);
-      accb[i] += gv[i];
+    for (int u = 0; u < 4; ++u) {
+      const float gv[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
+      const float av[8] = {a0[u].x, a0[u].y, a0[u].z, a0[u].w, a1[u].x, a1[u].y, a1[u].z, a1[u].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) acc[i][jj] = fmaf(gv[i], av[jj], acc[i][jj]);
+        accb[i] += gv[i];
+      }
     }
   }
   for (int i = threadIdx.x; i < 32 * 33; i += blockDim.x) red[i] = 0.f;

@@ -125,3 +125,59 @@ extern "C" int spt_edge_features_fwd(const int64_t* se, const float* ea, const f
       add_self_loops, edge_index_out, edge_attr_out);
   return check_launch("edge_features_fwd");
 }
+
+// ---------------------------------------------------------------------------
+// On-the-fly VERTICAL (child -> parent) edge features, default key set
+// (src/transforms/graph.py:1336-1416): centroid_dir(3) centroid_dist normal_angle
+// log_length log_surface log_volume log_size  -> v_edge_attr [Nc, 9]
+// ---------------------------------------------------------------------------
+namespace spt {
+constexpr int kVF = 9;
+__global__ void k_vertical_edge_features(
+    const float* __restrict__ cpos, const float* __restrict__ ppos,
+    const float* __restrict__ cnrm, const float* __restrict__ pnrm,
+    const float* __restrict__ cl0, const float* __restrict__ cl1, const float* __restrict__ cl2,
+    const float* __restrict__ cl3, const float* __restrict__ pl0, const float* __restrict__ pl1,
+    const float* __restrict__ pl2, const float* __restrict__ pl3,
+    const int64_t* __restrict__ parent, int64_t Nc, float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Nc) return;
+  const int64_t p = parent[i];
+  float d[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) d[k] = ppos[p * 3 + k] - cpos[i * 3 + k];
+  const float dist = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  float f[kVF];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) f[k] = nan_to_zero_clip(d[k] / dist);
+  f[3] = sqrtf(dist);
+  f[4] = fabsf(cnrm[i * 3] * pnrm[p * 3] + cnrm[i * 3 + 1] * pnrm[p * 3 + 1] +
+               cnrm[i * 3 + 2] * pnrm[p * 3 + 2]);
+  f[5] = pl0[p] - cl0[i];
+  f[6] = pl1[p] - cl1[i];
+  f[7] = pl2[p] - cl2[i];
+  f[8] = pl3[p] - cl3[i];
+#pragma unroll
+  for (int k = 0; k < kVF; ++k) out[i * kVF + k] = f[k];
+}
+}  // namespace spt
+
+extern "C" int spt_vertical_edge_features_fwd(
+    const float* child_pos, const float* parent_pos, const float* child_normal,
+    const float* parent_normal, const float* child_logs /*4 arrays, see below*/,
+    const float* parent_logs, const int64_t* parent, int64_t Nc, int64_t Np, float* out,
+    void* stream_) {
+  // child_logs / parent_logs: [4, Nc] / [4, Np] row-major = (log_length, log_surface,
+  // log_volume, log_size)
+  SPT_REQUIRE(Nc >= 0 && Np >= 0, SPT_E_INVALID, "vertical_edge_features: negative size");
+  if (Nc == 0) return SPT_OK;
+  SPT_REQUIRE(child_pos && parent_pos && child_normal && parent_normal && child_logs &&
+                  parent_logs && parent && out,
+              SPT_E_INVALID, "vertical_edge_features: null pointer");
+  spt::k_vertical_edge_features<<<(unsigned)spt::ceil_div(Nc, 256), 256, 0,
+                                  (cudaStream_t)stream_>>>(
+      child_pos, parent_pos, child_normal, parent_normal, child_logs, child_logs + Nc,
+      child_logs + 2 * Nc, child_logs + 3 * Nc, parent_logs, parent_logs + Np,
+      parent_logs + 2 * Np, parent_logs + 3 * Np, parent, Nc, out);
+  return spt::check_launch("vertical_edge_features_fwd");
+}

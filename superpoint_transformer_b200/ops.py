@@ -714,3 +714,27 @@ def horizontal_edge_features(se, edge_attr7, pos, normal, log_length, log_surfac
                                              _stream()), "spt_edge_features_fwd")
     _count()
     return ei, out
+
+
+def vertical_edge_features(child, parent, normal_key='normal'):
+    """v_edge_attr [Nc, 9] of the child level (see spt_vertical_edge_features_fwd);
+    `child` / `parent` are Data-like objects with pos, normal, log_* and
+    child.super_index."""
+    lib = _lib.load()
+    idx = _i64c(child.super_index)
+    f = lambda t: t.detach().float().contiguous()  # noqa: E731
+    cpos, ppos = f(child.pos), f(parent.pos)
+    cn, pn = f(child[normal_key]), f(parent[normal_key])
+    _require_cuda(idx, cpos, ppos, cn, pn)
+    keys = ('log_length', 'log_surface', 'log_volume', 'log_size')
+    clog = torch.stack([f(child[k]).view(-1) for k in keys]).contiguous()
+    plog = torch.stack([f(parent[k]).view(-1) for k in keys]).contiguous()
+    Nc, Np = cpos.shape[0], ppos.shape[0]
+    out = torch.empty((Nc, 9), dtype=torch.float32, device=cpos.device)
+    with torch.cuda.device(cpos.device):
+        _lib.check(lib.spt_vertical_edge_features_fwd(_p(cpos), _p(ppos), _p(cn), _p(pn),
+                                                      _p(clog), _p(plog), _p(idx), Nc, Np,
+                                                      _p(out), _stream()),
+                   "spt_vertical_edge_features_fwd")
+    _count()
+    return out

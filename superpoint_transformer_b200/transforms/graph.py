@@ -10,8 +10,8 @@ import torch
 
 from .. import ops
 
-__all__ = ['NodeSize', 'OnTheFlyHorizontalEdgeFeatures', 'NAGAddSelfLoops',
-           'ON_THE_FLY_HORIZONTAL_FEATURES']
+__all__ = ['NodeSize', 'OnTheFlyHorizontalEdgeFeatures', 'OnTheFlyVerticalEdgeFeatures',
+           'NAGAddSelfLoops', 'ON_THE_FLY_HORIZONTAL_FEATURES', 'ON_THE_FLY_VERTICAL_FEATURES']
 
 # column order of the reference's f_list assembly
 ON_THE_FLY_HORIZONTAL_FEATURES = [
@@ -67,6 +67,33 @@ class OnTheFlyHorizontalEdgeFeatures:
                 d['log_surface'], d['log_volume'], d['log_size'], d.num_nodes,
                 add_self_loops=self.add_self_loops)
             d.edge_index, d.edge_attr = ei, ea
+        return nag
+
+
+ON_THE_FLY_VERTICAL_FEATURES = [
+    'centroid_dir', 'centroid_dist', 'normal_angle', 'log_length', 'log_surface', 'log_volume',
+    'log_size']
+
+
+class OnTheFlyVerticalEdgeFeatures:
+    """child -> parent edge features `v_edge_attr` [Nc, 9] for every loaded level that has
+    a parent (reference src/transforms/graph.py:1280-1416; consumed by the attentive pools).
+    Only the full default key set is built by the kernel."""
+
+    def __init__(self, keys=None, use_mean_normal=False):
+        keys = ON_THE_FLY_VERTICAL_FEATURES if keys is None else list(keys)
+        self.enabled = len(keys) > 0
+        if self.enabled and sorted(keys) != sorted(ON_THE_FLY_VERTICAL_FEATURES):
+            raise NotImplementedError(
+                "the CUDA vertical edge-feature kernel builds the full 9-column default set")
+        self.normal_key = 'mean_normal' if use_mean_normal else 'normal'
+
+    def __call__(self, nag):
+        if not self.enabled:
+            return nag
+        for i_level in range(nag.start_i_level + 1, nag.absolute_num_levels):
+            child, parent = nag[i_level - 1], nag[i_level]
+            child.v_edge_attr = ops.vertical_edge_features(child, parent, self.normal_key)
         return nag
 
 

@@ -159,3 +159,12 @@ def test_edge_features(golden):
     assert torch.equal(ei2, c['loop_edge_index'])
     torch.testing.assert_close(ea2, c['loop_edge_attr'], atol=0, rtol=0)
     assert not torch.isnan(ea).any()
+
+
+def test_vertical_edge_features(golden):
+    v = golden('edge_features.pt')['v']
+    out = P.vertical_edge_features(v['child_pos'], v['parent_pos'], v['child_normal'],
+                                   v['parent_normal'], v['child_logs'], v['parent_logs'],
+                                   v['super_index'])
+    torch.testing.assert_close(out, v['v_edge_attr'], atol=0, rtol=0)
+    assert out.shape[1] == 9 and not torch.isnan(out).any()
