@@ -191,10 +191,11 @@ def run_own(args):
     n1 = LEVELS[0]
 
     def fwd_bwd(nag, labels):
-        flat.zero_()
+        flat.release()
         out = net(nag)
         loss = torch.nn.functional.cross_entropy(head(out), labels)
         loss.backward()
+        flat.collect()
         return loss
 
     def step(nag, labels):

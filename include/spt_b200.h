@@ -182,12 +182,16 @@ size_t spt_graphnorm_workspace_bytes(int64_t B, int64_t C);
 int spt_graphnorm_fwd(const float* x, const int64_t* batch /*nullable*/,
                       int64_t N, int64_t C, int64_t B, const float* weight,
                       const float* bias, const float* mean_scale, float eps,
+                      float act_slope /* 1 = none; else fused LeakyReLU(slope),
+                        the activation that follows the norm in src/nn/mlp.py:41-55 */,
                       float* y, float* mean /*[B,C]*/, float* rstd /*[B,C]*/,
                       void* ws, size_t ws_bytes, void* stream);
 int spt_graphnorm_bwd(const float* x, const float* dy,
                       const int64_t* batch /*nullable*/, int64_t N, int64_t C,
                       int64_t B, const float* weight, const float* mean_scale,
-                      const float* mean, const float* rstd, float* dx,
+                      const float* mean, const float* rstd,
+                      const float* y_act /*forward output, needed iff act_slope != 1*/,
+                      float act_slope, float* dx,
                       float* dweight /*[C]*/, float* dbias /*[C]*/,
                       float* dmean_scale /*[C]*/, void* ws, size_t ws_bytes,
                       void* stream);

@@ -46,11 +46,11 @@ SIGNATURES = {
                                    c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
     "spt_graphnorm_workspace_bytes": (c_size, [c_i64, c_i64]),
     "spt_graphnorm_fwd": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr,
-                                  c_ptr, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_size,
+                                  c_ptr, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_size,
                                   c_ptr]),
     "spt_graphnorm_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr,
-                                  c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
-                                  c_ptr, c_size, c_ptr]),
+                                  c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_ptr, c_ptr, c_ptr,
+                                  c_ptr, c_ptr, c_size, c_ptr]),
     "spt_attn_fwd": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr,
                              c_ptr, c_i64, c_i64, c_int, c_int, c_int, c_int, c_ptr,
                              c_ptr, c_ptr, c_ptr, c_int, c_f32, c_ptr, c_ptr, c_ptr,

@@ -36,6 +36,7 @@ struct ColMap {
 template <int MODE, int VEC>
 __global__ void __launch_bounds__(kNormThreads)
 k_graphnorm_stats(const float* __restrict__ x, const float* __restrict__ dy,
+                  const float* __restrict__ yact, float slope,
                   const int64_t* __restrict__ batch, int64_t N, int64_t C, int64_t B,
                   const float* __restrict__ mean_scale,
                   const double* __restrict__ sum_x, const double* __restrict__ count,
@@ -72,8 +73,41 @@ k_graphnorm_stats(const float* __restrict__ x, const float* __restrict__ dy,
       const int64_t r0 = slab * kNormRows;
       const int64_t r1 = min(r0 + (int64_t)kNormRows, N);
       rows_seen += r1 - r0;
-      for (int64_t r = r0 + ry; r < r1; r += ty) {
-        int64_t b = batch ? batch[r] : 0;
+      constexpr int U = 4;   // rows in flight per thread (independent 16-byte loads)
+      for (int64_t rb = r0 + ry; rb < r1; rb += (int64_t)ty * U) {
+        int64_t bq[U];
+        float xq[U][VEC], gq[U][VEC];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t r = rb + (int64_t)u * ty;
+          bq[u] = -1;
+          if (r < r1) {
+            bq[u] = batch ? batch[r] : 0;
+            if (VEC == 4) {
+              float4 t = *reinterpret_cast<const float4*>(x + r * C + c0);
+              xq[u][0] = t.x; xq[u][1 % VEC] = t.y; xq[u][2 % VEC] = t.z; xq[u][3 % VEC] = t.w;
+              if (MODE == 2) {
+                float4 g = *reinterpret_cast<const float4*>(dy + r * C + c0);
+                if (yact) {   // fused LeakyReLU: d(pre-activation) = dy * (y > 0 ? 1 : slope)
+                  float4 yy = *reinterpret_cast<const float4*>(yact + r * C + c0);
+                  g.x *= (yy.x > 0.f) ? 1.f : slope; g.y *= (yy.y > 0.f) ? 1.f : slope;
+                  g.z *= (yy.z > 0.f) ? 1.f : slope; g.w *= (yy.w > 0.f) ? 1.f : slope;
+                }
+                gq[u][0] = g.x; gq[u][1 % VEC] = g.y; gq[u][2 % VEC] = g.z; gq[u][3 % VEC] = g.w;
+              }
+            } else {
+              xq[u][0] = x[r * C + c0];
+              if (MODE == 2) {
+                float g = dy[r * C + c0];
+                if (yact) g *= (yact[r * C + c0] > 0.f) ? 1.f : slope;
+                gq[u][0] = g;
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+        const int64_t b = bq[u];
         if (b < 0 || b >= B) continue;
         if (b != first_b) uniform = false;
         if (b != cur) {
@@ -105,32 +139,21 @@ k_graphnorm_stats(const float* __restrict__ x, const float* __restrict__ dy,
             }
           }
         }
-        float xv[VEC], gv[VEC];
-        if (VEC == 4) {
-          float4 t = *reinterpret_cast<const float4*>(x + r * C + c0);
-          xv[0] = t.x; xv[1 % VEC] = t.y; xv[2 % VEC] = t.z; xv[3 % VEC] = t.w;
-          if (MODE == 2) {
-            float4 g = *reinterpret_cast<const float4*>(dy + r * C + c0);
-            gv[0] = g.x; gv[1 % VEC] = g.y; gv[2 % VEC] = g.z; gv[3 % VEC] = g.w;
-          }
-        } else {
-          xv[0] = x[r * C + c0];
-          if (MODE == 2) gv[0] = dy[r * C + c0];
-        }
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
           if (MODE == 0) {
-            a[0][v] += xv[v];
+            a[0][v] += xq[u][v];
           } else if (MODE == 1) {
-            float d = xv[v] - mu[v];
+            float d = xq[u][v] - mu[v];
             a[0][v] = fmaf(d, d, a[0][v]);
           } else {
-            float xhat = (xv[v] - mu[v]) * rs[v];
-            a[0][v] = fmaf(gv[v], xhat, a[0][v]);
-            a[NACC - 1][v] += gv[v];
+            float xhat = (xq[u][v] - mu[v]) * rs[v];
+            a[0][v] = fmaf(gq[u][v], xhat, a[0][v]);
+            a[NACC - 1][v] += gq[u][v];
           }
         }
         ++nrows;
+        }
       }
      }
     }
@@ -190,7 +213,7 @@ k_graphnorm_apply(const float* __restrict__ x, const int64_t* __restrict__ batch
                   int64_t N, int64_t C, int64_t B, const float* __restrict__ weight,
                   const float* __restrict__ bias, const float* __restrict__ mean_scale,
                   const float* __restrict__ mean, const float* __restrict__ rstd,
-                  float* __restrict__ y) {
+                  float slope, float* __restrict__ y) {
   int64_t cv = C / VEC;
   int64_t total = N * cv;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -213,7 +236,8 @@ k_graphnorm_apply(const float* __restrict__ x, const int64_t* __restrict__ batch
       float out = xv[v] - mean_scale[c] * mean[b * C + c];
       float w = weight ? weight[c] : 1.f;
       float bb = bias ? bias[c] : 0.f;
-      o[v] = fmaf(w * out, rstd[b * C + c], bb);
+      float val = fmaf(w * out, rstd[b * C + c], bb);
+      o[v] = (val > 0.f) ? val : val * slope;   // slope == 1: identity
     }
     if (VEC == 4)
       *reinterpret_cast<float4*>(y + r * C + c0) =
@@ -267,7 +291,7 @@ k_graphnorm_bwd_apply(const float* __restrict__ x, const float* __restrict__ dy,
                       const float* __restrict__ weight, const float* __restrict__ mean_scale,
                       const float* __restrict__ mean, const float* __restrict__ rstd,
                       const float* __restrict__ k2, const float* __restrict__ k3,
-                      float* __restrict__ dx) {
+                      const float* __restrict__ yact, float slope, float* __restrict__ dx) {
   int64_t cv = C / VEC;
   int64_t total = N * cv;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -287,9 +311,15 @@ k_graphnorm_bwd_apply(const float* __restrict__ x, const float* __restrict__ dy,
         float4 g = *reinterpret_cast<const float4*>(dy + r * C + c0);
         xv[0] = t.x; xv[1 % VEC] = t.y; xv[2 % VEC] = t.z; xv[3 % VEC] = t.w;
         gv[0] = g.x; gv[1 % VEC] = g.y; gv[2 % VEC] = g.z; gv[3 % VEC] = g.w;
+        if (yact) {
+          float4 yy = *reinterpret_cast<const float4*>(yact + r * C + c0);
+          gv[0] *= (yy.x > 0.f) ? 1.f : slope; gv[1 % VEC] *= (yy.y > 0.f) ? 1.f : slope;
+          gv[2 % VEC] *= (yy.z > 0.f) ? 1.f : slope; gv[3 % VEC] *= (yy.w > 0.f) ? 1.f : slope;
+        }
       } else {
         xv[0] = x[r * C + c0];
         gv[0] = dy[r * C + c0];
+        if (yact) gv[0] *= (yact[r * C + c0] > 0.f) ? 1.f : slope;
       }
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
@@ -383,8 +413,8 @@ size_t spt_graphnorm_workspace_bytes(int64_t B, int64_t C) {
 
 int spt_graphnorm_fwd(const float* x, const int64_t* batch, int64_t N, int64_t C,
                       int64_t B, const float* weight, const float* bias,
-                      const float* mean_scale, float eps, float* y, float* mean,
-                      float* rstd, void* ws, size_t ws_bytes, void* stream_) {
+                      const float* mean_scale, float eps, float act_slope, float* y,
+                      float* mean, float* rstd, void* ws, size_t ws_bytes, void* stream_) {
   SPT_REQUIRE(N >= 0 && C > 0 && B > 0, SPT_E_INVALID, "graphnorm_fwd: bad sizes");
   SPT_REQUIRE(mean_scale && mean && rstd && ws && (N == 0 || (x && y)), SPT_E_INVALID,
               "graphnorm_fwd: null pointer");
@@ -399,23 +429,23 @@ int spt_graphnorm_fwd(const float* x, const int64_t* batch, int64_t N, int64_t C
   }
   int vec = (C % 4 == 0) ? 4 : 1;
   ColMap cm = col_map(C, vec);
-  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, kNormRows), 148 * 2);
+  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, kNormRows), 148 * 4);
   int64_t total = N * (C / vec);
   int agrid = (int)imin(ceil_div(total > 0 ? total : 1, kNormThreads), 148 * 16);
   if (N > 0) {
     if (vec == 4) {
       k_graphnorm_stats<0, 4><<<slabs, kNormThreads, 0, st>>>(
-          x, nullptr, batch, N, C, B, mean_scale, nullptr, nullptr, nullptr, nullptr,
+          x, nullptr, nullptr, 1.f, batch, N, C, B, mean_scale, nullptr, nullptr, nullptr, nullptr,
           w.acc0, nullptr, w.count, cm.tx, cm.ty);
       k_graphnorm_stats<1, 4><<<slabs, kNormThreads, 0, st>>>(
-          x, nullptr, batch, N, C, B, mean_scale, w.acc0, w.count, nullptr, nullptr,
+          x, nullptr, nullptr, 1.f, batch, N, C, B, mean_scale, w.acc0, w.count, nullptr, nullptr,
           w.acc1, nullptr, nullptr, cm.tx, cm.ty);
     } else {
       k_graphnorm_stats<0, 1><<<slabs, kNormThreads, 0, st>>>(
-          x, nullptr, batch, N, C, B, mean_scale, nullptr, nullptr, nullptr, nullptr,
+          x, nullptr, nullptr, 1.f, batch, N, C, B, mean_scale, nullptr, nullptr, nullptr, nullptr,
           w.acc0, nullptr, w.count, cm.tx, cm.ty);
       k_graphnorm_stats<1, 1><<<slabs, kNormThreads, 0, st>>>(
-          x, nullptr, batch, N, C, B, mean_scale, w.acc0, w.count, nullptr, nullptr,
+          x, nullptr, nullptr, 1.f, batch, N, C, B, mean_scale, w.acc0, w.count, nullptr, nullptr,
           w.acc1, nullptr, nullptr, cm.tx, cm.ty);
     }
   }
@@ -424,19 +454,22 @@ int spt_graphnorm_fwd(const float* x, const int64_t* batch, int64_t N, int64_t C
   if (N > 0) {
     if (vec == 4)
       k_graphnorm_apply<4><<<agrid, kNormThreads, 0, st>>>(x, batch, N, C, B, weight, bias,
-                                                          mean_scale, mean, rstd, y);
+                                                          mean_scale, mean, rstd, act_slope, y);
     else
       k_graphnorm_apply<1><<<agrid, kNormThreads, 0, st>>>(x, batch, N, C, B, weight, bias,
-                                                          mean_scale, mean, rstd, y);
+                                                          mean_scale, mean, rstd, act_slope, y);
   }
   return check_launch("graphnorm_fwd");
 }
 
 int spt_graphnorm_bwd(const float* x, const float* dy, const int64_t* batch, int64_t N,
                       int64_t C, int64_t B, const float* weight, const float* mean_scale,
-                      const float* mean, const float* rstd, float* dx, float* dweight,
-                      float* dbias, float* dmean_scale, void* ws, size_t ws_bytes,
-                      void* stream_) {
+                      const float* mean, const float* rstd, const float* y_act,
+                      float act_slope, float* dx, float* dweight, float* dbias,
+                      float* dmean_scale, void* ws, size_t ws_bytes, void* stream_) {
+  const float* yact = (act_slope != 1.f) ? y_act : nullptr;
+  SPT_REQUIRE(act_slope == 1.f || y_act, SPT_E_INVALID,
+              "graphnorm_bwd: fused activation needs the forward output");
   SPT_REQUIRE(N >= 0 && C > 0 && B > 0, SPT_E_INVALID, "graphnorm_bwd: bad sizes");
   SPT_REQUIRE(mean_scale && mean && rstd && ws && (N == 0 || (x && dy && dx)),
               SPT_E_INVALID, "graphnorm_bwd: null pointer");
@@ -451,17 +484,17 @@ int spt_graphnorm_bwd(const float* x, const float* dy, const int64_t* batch, int
   }
   int vec = (C % 4 == 0) ? 4 : 1;
   ColMap cm = col_map(C, vec);
-  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, kNormRows), 148 * 2);
+  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, kNormRows), 148 * 4);
   int64_t total = N * (C / vec);
   int agrid = (int)imin(ceil_div(total > 0 ? total : 1, kNormThreads), 148 * 16);
   if (N > 0) {
     if (vec == 4)
       k_graphnorm_stats<2, 4><<<slabs, kNormThreads, 0, st>>>(
-          x, dy, batch, N, C, B, mean_scale, nullptr, nullptr, mean, rstd, w.acc0,
+          x, dy, yact, act_slope, batch, N, C, B, mean_scale, nullptr, nullptr, mean, rstd, w.acc0,
           w.acc1, nullptr, cm.tx, cm.ty);
     else
       k_graphnorm_stats<2, 1><<<slabs, kNormThreads, 0, st>>>(
-          x, dy, batch, N, C, B, mean_scale, nullptr, nullptr, mean, rstd, w.acc0,
+          x, dy, yact, act_slope, batch, N, C, B, mean_scale, nullptr, nullptr, mean, rstd, w.acc0,
           w.acc1, nullptr, cm.tx, cm.ty);
     k_count_rows<<<(unsigned)imin(ceil_div(N, 256 * 64), 148 * 8), 256, 0, st>>>(
         batch, N, B, w.count);
@@ -472,10 +505,12 @@ int spt_graphnorm_bwd(const float* x, const float* dy, const int64_t* batch, int
   if (N > 0) {
     if (vec == 4)
       k_graphnorm_bwd_apply<4><<<agrid, kNormThreads, 0, st>>>(
-          x, dy, batch, N, C, B, weight, mean_scale, mean, rstd, w.k2, w.k3, dx);
+          x, dy, batch, N, C, B, weight, mean_scale, mean, rstd, w.k2, w.k3, yact, act_slope,
+          dx);
     else
       k_graphnorm_bwd_apply<1><<<agrid, kNormThreads, 0, st>>>(
-          x, dy, batch, N, C, B, weight, mean_scale, mean, rstd, w.k2, w.k3, dx);
+          x, dy, batch, N, C, B, weight, mean_scale, mean, rstd, w.k2, w.k3, yact, act_slope,
+          dx);
   }
   return check_launch("graphnorm_bwd");
 }

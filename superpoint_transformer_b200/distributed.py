@@ -50,6 +50,30 @@ class FlatGradients:
     def zero_(self):
         self.flat.zero_()
 
+    def release(self):
+        """Detach the parameters from the flat buffer before a backward pass: autograd
+        then *assigns* fresh gradients instead of launching one accumulate-add kernel per
+        parameter (233 for the cfg-2 model); `collect()` packs them afterwards."""
+        for p in self.params:
+            p.grad = None
+
+    def collect(self):
+        """Pack the freshly produced gradients into the flat buffer with one multi-tensor
+        copy and re-point `.grad` at the flat views (missing gradients count as zero)."""
+        if not hasattr(self, '_views'):
+            self._views, off = [], 0
+            for p in self.params:
+                n = p.numel()
+                self._views.append(self.flat[off:off + n].view_as(p))
+                off += n
+        have = [(v, p.grad) for v, p in zip(self._views, self.params) if p.grad is not None]
+        if len(have) != len(self.params):
+            self.flat.zero_()
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        for v, p in zip(self._views, self.params):
+            p.grad = v
+
     def rebind(self):
         """re-point .grad at the flat buffer (after optimizer.zero_grad(set_to_none=True))"""
         off = 0

@@ -9,7 +9,7 @@ from torch import nn
 
 from .linear import Linear
 
-from .norm import BatchNorm, INDEX_BASED_NORMS
+from .norm import BatchNorm, GraphNorm, INDEX_BASED_NORMS
 
 __all__ = ['MLP', 'FFN', 'Classifier']
 
@@ -38,8 +38,18 @@ class MLP(nn.Module):
         self.out_dim = dims[-1]
 
     def forward(self, x, batch=None):
-        for m in self.mlp:
+        mods = list(self.mlp)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            nxt = mods[i + 1] if i + 1 < len(mods) else None
+            if isinstance(m, GraphNorm) and isinstance(nxt, nn.LeakyReLU) and x.is_cuda:
+                # norm + LeakyReLU in one CUDA pass (forward and backward)
+                x = m(x, batch=batch, act_slope=nxt.negative_slope)
+                i += 2
+                continue
             x = m(x, batch=batch) if isinstance(m, INDEX_BASED_NORMS) else m(x)
+            i += 1
         return x
 
 

@@ -69,9 +69,9 @@ class GraphNorm(nn.Module):
         nn.init.zeros_(self.bias)
         nn.init.ones_(self.mean_scale)
 
-    def forward(self, x, batch=None, batch_size=None):
+    def forward(self, x, batch=None, batch_size=None, act_slope=1.0):
         return ops.graph_norm(x, self.weight, self.bias, self.mean_scale, batch=batch,
-                              batch_size=batch_size, eps=self.eps)
+                              batch_size=batch_size, eps=self.eps, act_slope=act_slope)
 
     def __repr__(self):
         return f'{self.__class__.__name__}({self.in_channels})'

@@ -379,8 +379,14 @@ def linear(x, weight, bias=None):
     (fp32-accurate, operand streamed once); tiny or oddly-shaped ones (K or N not a
     multiple of 4) use the plain fp32 library GEMM."""
     if (LINEAR_TC and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
-            and x.shape[0] >= LINEAR_TC_MIN_ROWS and weight.shape[0] % 4 == 0):
-        K = x.shape[1]
+            and x.shape[0] >= LINEAR_TC_MIN_ROWS):
+        K, N = x.shape[1], weight.shape[0]
+        if N % 4 != 0:
+            # e.g. a 13-class head: zero-pad the output features, slice the result
+            padn = 4 - N % 4
+            wp = torch.nn.functional.pad(weight, (0, 0, 0, padn))
+            bp = torch.nn.functional.pad(bias, (0, padn)) if bias is not None else None
+            return linear(x, wp, bp)[:, :N]
         if K % 4 != 0:
             # e.g. the 18 raw edge features: zero-pad K to a multiple of 4 (one extra
             # pass over x, still far cheaper than the SIMT library GEMM it replaces)
@@ -501,7 +507,7 @@ def unit_sphere_norm(pos, idx=None, w=None, num_super=None):
 # ---------------------------------------------------------------------------
 class _GraphNorm(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, mean_scale, batch, B, eps):
+    def forward(ctx, x, weight, bias, mean_scale, batch, B, eps, act_slope):
         lib = _lib.load()
         N, C = x.shape
         dev = x.device
@@ -512,20 +518,25 @@ class _GraphNorm(torch.autograd.Function):
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             _lib.check(lib.spt_graphnorm_fwd(_p(x), _p(batch), N, C, B, _p(weight), _p(bias),
-                                             _p(mean_scale), eps, _p(y), _p(mean), _p(rstd),
-                                             _p(ws), nbytes, _stream()), "spt_graphnorm_fwd")
+                                             _p(mean_scale), eps, act_slope, _p(y), _p(mean),
+                                             _p(rstd), _p(ws), nbytes, _stream()),
+                       "spt_graphnorm_fwd")
         _count(4)
         ctx.B = B
         ctx.has_batch = batch is not None
+        ctx.act_slope = act_slope
         ctx.save_for_backward(x, weight, mean_scale, mean, rstd,
-                              batch if batch is not None else mean)
+                              batch if batch is not None else mean,
+                              y if act_slope != 1.0 else mean)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight, mean_scale, mean, rstd, batch = ctx.saved_tensors
+        x, weight, mean_scale, mean, rstd, batch, yact = ctx.saved_tensors
         if not ctx.has_batch:
             batch = None
+        if ctx.act_slope == 1.0:
+            yact = None
         lib = _lib.load()
         dy = _f32c(dy)
         N, C = x.shape
@@ -538,20 +549,22 @@ class _GraphNorm(torch.autograd.Function):
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             _lib.check(lib.spt_graphnorm_bwd(_p(x), _p(dy), _p(batch), N, C, ctx.B, _p(weight),
-                                             _p(mean_scale), _p(mean), _p(rstd), _p(dx),
-                                             _p(dw), _p(db), _p(dms), _p(ws), nbytes,
-                                             _stream()), "spt_graphnorm_bwd")
+                                             _p(mean_scale), _p(mean), _p(rstd), _p(yact),
+                                             ctx.act_slope, _p(dx), _p(dw), _p(db), _p(dms),
+                                             _p(ws), nbytes, _stream()), "spt_graphnorm_bwd")
         _count(4)
-        return dx, dw, db, dms, None, None, None
+        return dx, dw, db, dms, None, None, None, None
 
 
-def graph_norm(x, weight, bias, mean_scale, batch=None, batch_size=None, eps=1e-5):
-    """PyG GraphNorm semantics."""
+def graph_norm(x, weight, bias, mean_scale, batch=None, batch_size=None, eps=1e-5,
+               act_slope=1.0):
+    """PyG GraphNorm semantics; `act_slope != 1` fuses the
+    LeakyReLU that follows the norm in the reference MLP (src/nn/mlp.py:41-55)."""
     _require_cuda(x, weight, bias, mean_scale, batch)
     batch = _i64c(batch)
     B = int(batch_size) if batch_size is not None else num_segments(batch)
     return _GraphNorm.apply(_f32c(x), _f32c(weight), _f32c(bias), _f32c(mean_scale), batch,
-                            B, float(eps))
+                            B, float(eps), float(act_slope))
 
 
 # ---------------------------------------------------------------------------

@@ -29,9 +29,10 @@ def _worker(rank, world, port, out):
     flat = FlatGradients(model.parameters())
     scenes = [torch.randn(10 + i, 6, generator=torch.Generator().manual_seed(i)) for i in range(6)]
     mine = shard_indices(len(scenes), rank, world)
-    flat.zero_()
+    flat.release()
     for i in mine:  # local mean over this rank's scenes
         (model(scenes[i]).pow(2).mean() / len(mine)).backward()
+    flat.collect()
     flat.all_reduce()
     out[rank] = flat.flat.clone()
     dist.barrier()

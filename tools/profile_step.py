@@ -33,10 +33,11 @@ def main():
         for l, (ea, hf) in base.items():
             d = nag[l]
             d.x, d.edge_attr, d['hf'], d.diameter = None, ea, hf, None
-        flat.zero_()
+        flat.release()
         out = net(nag)
         loss = torch.nn.functional.cross_entropy(head(out), labels)
         loss.backward()
+        flat.collect()
         opt.step()
 
     for _ in range(3):
