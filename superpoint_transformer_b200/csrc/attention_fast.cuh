@@ -193,6 +193,9 @@ struct TileStream {
   __device__ __forceinline__ float4 v() const {
     return *reinterpret_cast<const float4*>(cur_g + 16 * lane);
   }
+  __device__ __forceinline__ ulonglong2 v2() const {   // same 16 bytes as two fp32x2 pairs
+    return *reinterpret_cast<const ulonglong2*>(cur_g + 16 * lane);
+  }
   __device__ __forceinline__ float k() const {
     return *reinterpret_cast<const float*>(cur_g + kC * 4 + 4 * (lane - kHD));
   }
@@ -232,18 +235,46 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-// r_o = b_o + sum_f w[f] * a[f], a read as 8 broadcast LDS.128; 4 partial sums
-__device__ __forceinline__ float gemv32(const float (&w)[kF], float bias, const float* arow) {
-  float s0 = bias, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+// ---- packed fp32x2 math (Blackwell FFMA2 / FMUL2: two fp32 lanes per instruction) ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ float hsum2(f32x2 v) {
+  float lo, hi;
+  unpack2(v, lo, hi);
+  return lo + hi;
+}
+// acc += a * b
+__device__ __forceinline__ void fma2(f32x2& acc, f32x2 a, f32x2 b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+// acc = acc * s + t
+__device__ __forceinline__ void scale_add2(f32x2& acc, f32x2 s, f32x2 t) {
+  asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc) : "l"(s), "l"(t));
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// r_o = b_o + sum_f w[f] * a[f]: the weight row is held as 16 packed pairs, a_e is read
+// as 8 broadcast LDS.128 (= 2 packed pairs each) -> 16 FFMA2 on two independent chains
+__device__ __forceinline__ float gemv32(const f32x2 (&w2)[kF / 2], float bias, const float* arow) {
+  f32x2 s01 = pack2(bias, 0.f), s23 = 0ull;
 #pragma unroll
   for (int c = 0; c < kF / 4; ++c) {
-    float4 t = *reinterpret_cast<const float4*>(arow + 4 * c);
-    s0 = fmaf(w[4 * c + 0], t.x, s0);
-    s1 = fmaf(w[4 * c + 1], t.y, s1);
-    s2 = fmaf(w[4 * c + 2], t.z, s2);
-    s3 = fmaf(w[4 * c + 3], t.w, s3);
+    const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(arow + 4 * c);
+    fma2(s01, w2[2 * c], t.x);
+    fma2(s23, w2[2 * c + 1], t.y);
   }
-  return (s0 + s1) + (s2 + s3);
+  return hsum2(s01) + hsum2(s23);
 }
 
 __global__ void __launch_bounds__(kWarps * kWarp, 5)
@@ -258,15 +289,16 @@ k_attn_fwd_fast(FwdArgs P) {
   if (row0 >= P.num_rows) return;
   const int64_t row1 = min(row0 + (int64_t)P.rows_per_warp, P.num_rows);
 
-  // lane o: row o of [Wq; Wk] and its bias
-  float wreg[kF];
+  // lane o: row o of [Wq; Wk] (16 packed pairs) and its bias
+  f32x2 wreg[kF / 2];
   float bias = 0.f;
   {
     const float* W = (lane < kHD) ? P.Wq : P.Wk;
     const float* B = (lane < kHD) ? P.bq : P.bk;
     int o = lane & (kHD - 1);
 #pragma unroll
-    for (int f = 0; f < kF; ++f) wreg[f] = W ? W[o * kF + f] : 0.f;
+    for (int f = 0; f < kF / 2; ++f)
+      wreg[f] = W ? pack2(W[o * kF + 2 * f], W[o * kF + 2 * f + 1]) : 0ull;
     if (W && B) bias = B[o];
   }
 
@@ -291,14 +323,14 @@ k_attn_fwd_fast(FwdArgs P) {
     const float scale = qk_scale_fast(P.scale_mode, P.scale_value, e - b);
     const float qs = is_k ? 0.f : P.q[row * P.ldq + lane] * scale;
     float m_run = -INFINITY, l_run = 0.f;      // base-2 running max / sum of my head
-    float4 accv = make_float4(0.f, 0.f, 0.f, 0.f), acca = make_float4(0.f, 0.f, 0.f, 0.f);
+    f32x2 accv01 = 0ull, accv23 = 0ull, acca01 = 0ull, acca23 = 0ull;
 
     for (int j = b; j < e; ++j) {
       ts.next();
       const float* arow = ts.a_row();
       const float r = gemv32(wreg, bias, arow);
       const float k_cur = is_k ? ts.k() : 0.f;
-      const float4 v_cur = ts.v();
+      const ulonglong2 v_cur = ts.v2();
       const float val = (is_k ? k_cur : qs) + r;            // q_e (lanes<16) | k_e
       float prod = val * __shfl_xor_sync(kFull, val, 16);
       prod += __shfl_xor_sync(kFull, prod, 1);
@@ -309,25 +341,27 @@ k_attn_fwd_fast(FwdArgs P) {
       const float p = ex2(c2 - m_new);
       l_run = fmaf(l_run, alpha, p);
       m_run = m_new;
-      accv.x = fmaf(accv.x, alpha, p * v_cur.x);
-      accv.y = fmaf(accv.y, alpha, p * v_cur.y);
-      accv.z = fmaf(accv.z, alpha, p * v_cur.z);
-      accv.w = fmaf(accv.w, alpha, p * v_cur.w);
+      const f32x2 pp = pack2(p, p), aa = pack2(alpha, alpha);
+      scale_add2(accv01, aa, mul2(pp, v_cur.x));            // acc = acc*alpha + p*v
+      scale_add2(accv23, aa, mul2(pp, v_cur.y));
       if (want_abar) {
-        const float4 a4 = *reinterpret_cast<const float4*>(arow + aoff);
-        acca.x = fmaf(acca.x, alpha, p * a4.x);
-        acca.y = fmaf(acca.y, alpha, p * a4.y);
-        acca.z = fmaf(acca.z, alpha, p * a4.z);
-        acca.w = fmaf(acca.w, alpha, p * a4.w);
+        const ulonglong2 a4 = *reinterpret_cast<const ulonglong2*>(arow + aoff);
+        scale_add2(acca01, aa, mul2(pp, a4.x));
+        scale_add2(acca23, aa, mul2(pp, a4.y));
       }
     }
     const float zden = l_run + 1e-16f;
     const float inv = 1.f / zden;
-    *reinterpret_cast<float4*>(P.agg_v + row * kC + 4 * lane) =
-        make_float4(accv.x * inv, accv.y * inv, accv.z * inv, accv.w * inv);
-    if (want_abar)
-      *reinterpret_cast<float4*>(P.abar + row * (kH * kF) + 4 * lane) =
-          make_float4(acca.x * inv, acca.y * inv, acca.z * inv, acca.w * inv);
+    {
+      const f32x2 ii = pack2(inv, inv);
+      ulonglong2 o;
+      o.x = mul2(accv01, ii); o.y = mul2(accv23, ii);
+      *reinterpret_cast<ulonglong2*>(P.agg_v + row * kC + 4 * lane) = o;
+      if (want_abar) {
+        o.x = mul2(acca01, ii); o.y = mul2(acca23, ii);
+        *reinterpret_cast<ulonglong2*>(P.abar + row * (kH * kF) + 4 * lane) = o;
+      }
+    }
     if ((lane & 7) == 0) {
       const int h = lane >> 3;
       P.m[row * kH + h] = (e > b) ? m_run * kLn2 : 0.f;    // natural-log units
@@ -373,20 +407,22 @@ k_attn_bwd_rows_fast(BwdArgs P) {
   if (row0 >= P.num_rows) return;
   const int64_t row1 = min(row0 + (int64_t)P.rows_per_warp, P.num_rows);
 
-  // lane o: row o of [Wq;Wk] (forward GEMV) ; lane f: column f (da GEMV)
-  float wrow[kF], wcol[2 * kHD];
+  // lane o: row o of [Wq;Wk] (forward GEMV) ; lane f: column f (da GEMV); packed pairs
+  f32x2 wrow[kF / 2], wcol[kHD];
   float bias = 0.f;
   {
     const float* W = (lane < kHD) ? P.Wq : P.Wk;
     const float* B = (lane < kHD) ? P.bq : P.bk;
     int o = lane & (kHD - 1);
 #pragma unroll
-    for (int f = 0; f < kF; ++f) wrow[f] = W ? W[o * kF + f] : 0.f;
+    for (int f = 0; f < kF / 2; ++f)
+      wrow[f] = W ? pack2(W[o * kF + 2 * f], W[o * kF + 2 * f + 1]) : 0ull;
     if (W && B) bias = B[o];
 #pragma unroll
-    for (int oo = 0; oo < kHD; ++oo) {
-      wcol[oo] = P.Wq ? P.Wq[oo * kF + lane] : 0.f;
-      wcol[kHD + oo] = P.Wk ? P.Wk[oo * kF + lane] : 0.f;
+    for (int oo = 0; oo < kHD / 2; ++oo) {
+      wcol[oo] = P.Wq ? pack2(P.Wq[(2 * oo) * kF + lane], P.Wq[(2 * oo + 1) * kF + lane]) : 0ull;
+      wcol[kHD / 2 + oo] =
+          P.Wk ? pack2(P.Wk[(2 * oo) * kF + lane], P.Wk[(2 * oo + 1) * kF + lane]) : 0ull;
     }
   }
 
@@ -468,23 +504,20 @@ k_attn_bwd_rows_fast(BwdArgs P) {
       if (want_da) {
         g_s[lane] = g;
         __syncwarp();
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        f32x2 s01 = 0ull, s23 = 0ull;
         if (has_dab) {
           // sum_h p_h * dAbar[row][h][f=lane]
-          s0 = __shfl_sync(kFull, p, 0) * dabf[0];
-          s1 = __shfl_sync(kFull, p, 8) * dabf[1];
-          s2 = __shfl_sync(kFull, p, 16) * dabf[2];
-          s3 = __shfl_sync(kFull, p, 24) * dabf[3];
+          s01 = pack2(__shfl_sync(kFull, p, 0) * dabf[0], __shfl_sync(kFull, p, 8) * dabf[1]);
+          s23 = pack2(__shfl_sync(kFull, p, 16) * dabf[2], __shfl_sync(kFull, p, 24) * dabf[3]);
         }
+        // sum_o W[o][f] g_o : g broadcast from shared memory as packed pairs (o, o+1)
 #pragma unroll
         for (int c4 = 0; c4 < (2 * kHD) / 4; ++c4) {
-          const float4 gg = *reinterpret_cast<const float4*>(g_s + 4 * c4);
-          s0 = fmaf(wcol[4 * c4 + 0], gg.x, s0);
-          s1 = fmaf(wcol[4 * c4 + 1], gg.y, s1);
-          s2 = fmaf(wcol[4 * c4 + 2], gg.z, s2);
-          s3 = fmaf(wcol[4 * c4 + 3], gg.w, s3);
+          const ulonglong2 gg = *reinterpret_cast<const ulonglong2*>(g_s + 4 * c4);
+          fma2(s01, wcol[2 * c4], gg.x);
+          fma2(s23, wcol[2 * c4 + 1], gg.y);
         }
-        P.da[(size_t)j * kF + lane] = (s0 + s1) + (s2 + s3);
+        P.da[(size_t)j * kF + lane] = hsum2(s01) + hsum2(s23);
         __syncwarp();
       }
     }
@@ -572,36 +605,42 @@ k_attn_bwd_dw_fast(DwArgs P) {
   __shared__ float red[32 * 33];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int oi = lane >> 2, fi = lane & 3;
-  float acc[4][8];
+  f32x2 acc[4][4];            // [o][f pair]: o = 4oi + i, f = 8fi + 2jp, +1
   float accb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0ull;
   const int64_t e0 = (int64_t)blockIdx.x * P.edges_per_cta;
   const int64_t e1 = min(e0 + P.edges_per_cta, P.E);
   // 4 edges in flight per warp iteration (12 independent 16-byte streaming loads)
   for (int64_t j0 = e0 + 4 * w; j0 < e1; j0 += 32) {
-    float4 g[4], a0[4], a1[4];
+    float4 g[4];
+    ulonglong2 a0[4], a1[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int64_t j = j0 + u;
       if (j < e1) {
         g[u] = ldg_stream4(P.G + j * 32 + 4 * oi);
-        a0[u] = ldg_stream4(P.a + j * 32 + 8 * fi);
-        a1[u] = ldg_stream4(P.a + j * 32 + 8 * fi + 4);
+        const float4 t0 = ldg_stream4(P.a + j * 32 + 8 * fi);
+        const float4 t1 = ldg_stream4(P.a + j * 32 + 8 * fi + 4);
+        a0[u].x = pack2(t0.x, t0.y); a0[u].y = pack2(t0.z, t0.w);
+        a1[u].x = pack2(t1.x, t1.y); a1[u].y = pack2(t1.z, t1.w);
       } else {
-        g[u] = a0[u] = a1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        a0[u].x = a0[u].y = a1[u].x = a1[u].y = 0ull;
       }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const float gv[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
-      const float av[8] = {a0[u].x, a0[u].y, a0[u].z, a0[u].w, a1[u].x, a1[u].y, a1[u].z, a1[u].w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) acc[i][jj] = fmaf(gv[i], av[jj], acc[i][jj]);
+        const f32x2 gg = pack2(gv[i], gv[i]);
+        fma2(acc[i][0], gg, a0[u].x);
+        fma2(acc[i][1], gg, a0[u].y);
+        fma2(acc[i][2], gg, a1[u].x);
+        fma2(acc[i][3], gg, a1[u].y);
         accb[i] += gv[i];
       }
     }
@@ -611,7 +650,12 @@ k_attn_bwd_dw_fast(DwArgs P) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) atomicAdd(&red[(4 * oi + i) * 33 + 8 * fi + jj], acc[i][jj]);
+    for (int jp = 0; jp < 4; ++jp) {
+      float lo, hi;
+      unpack2(acc[i][jp], lo, hi);
+      atomicAdd(&red[(4 * oi + i) * 33 + 8 * fi + 2 * jp], lo);
+      atomicAdd(&red[(4 * oi + i) * 33 + 8 * fi + 2 * jp + 1], hi);
+    }
     if (fi == 0) atomicAdd(&red[(4 * oi + i) * 33 + 32], accb[i]);
   }
   __syncthreads();
