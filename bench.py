@@ -338,6 +338,10 @@ def run_own(args):
                             algorithmic_MB=round(a['bytes'] / 1e6, 2),
                             achieved_GBs=round(gbs, 1), frac=round(gbs / peak_gbs, 4)))
     kernels.sort(key=lambda k: -k['share_of_step'])
+    if args.kernels_out and rank == 0:
+        with open(args.kernels_out, 'w') as fh:
+            json.dump(dict(eager_ms_per_step=ms_eager_step, steps=n_evt_steps, kernels=kernels),
+                      fh, indent=1)
     roofline = None
     if kernels:
         top = kernels[0]
@@ -587,6 +591,7 @@ def main():
     ap.add_argument('--impl', default='own', choices=['own', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='eager launches, no CUDA graphs')
+    ap.add_argument('--kernels-out', default=None, help='write the full per-kernel timing table (JSON)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'own' else args.warmup
     if args.impl == 'reference':

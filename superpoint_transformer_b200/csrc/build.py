@@ -25,6 +25,7 @@ SOURCES = [
     "norm.cu",
     "attention.cu",
     "gemm.cu",
+    "gemm_umma.cu",
     "edge_features.cu",
 ]
 HEADERS = sorted(f for f in os.listdir(HERE) if f.endswith((".cuh", ".h"))) + \

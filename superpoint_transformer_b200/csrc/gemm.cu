@@ -294,6 +294,25 @@ k_gemm_tn_acc(const float* __restrict__ A, int64_t M, int N, int64_t lda,
 
 using namespace spt;
 
+namespace spt {
+namespace umma {  // gemm_umma.cu: tcgen05 / TMEM / TMA path
+bool shape_ok(const float* A, int64_t M, int64_t K, int64_t lda, const float* B, int64_t N,
+              int64_t ldb, const float* C, int64_t ldc);
+int launch(const float* A, int64_t M, int64_t K, int64_t lda, const float* B, int64_t N,
+           int64_t ldb, const float* bias, float* C, int64_t ldc, cudaStream_t stream);
+}  // namespace umma
+}  // namespace spt
+
+// SPT_GEMM_MMA_SYNC=1 keeps the mma.sync kernel for A/B measurements (debug only)
+static bool use_umma() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SPT_GEMM_MMA_SYNC");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 extern "C" {
 
 int spt_gemm_nt(const float* A, int64_t M, int64_t K, int64_t lda, const float* B, int64_t N,
@@ -305,6 +324,8 @@ int spt_gemm_nt(const float* A, int64_t M, int64_t K, int64_t lda, const float* 
                   ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0,
               SPT_E_UNSUPPORTED, "gemm_nt: K, lda, ldb must be multiples of 4 and A, B 16-byte aligned");
   SPT_REQUIRE(K < (1 << 24) && N < (1 << 24), SPT_E_TOO_LARGE, "gemm_nt: K/N too large");
+  if (M >= 512 && use_umma() && umma::shape_ok(A, M, K, lda, B, N, ldb, C, ldc))
+    return umma::launch(A, M, K, lda, B, N, ldb, bias, C, ldc, (cudaStream_t)stream_);
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(gemm::k_gemm_nt, cudaFuncAttributeMaxDynamicSharedMemorySize,
