@@ -7,18 +7,22 @@
 //   x = hi + lo,  hi = tf32(x),  lo = tf32(x - hi),   A.B ~= Alo.Bhi + Ahi.Blo + Ahi.Bhi
 // (~2^-21 relative), accumulated in fp32 in TMEM.
 //
-// One persistent CTA per SM, warp-specialised, tile = 128 rows x BN (<=256) columns:
-//   warp 0      TMA producer : per 32-wide K chunk, one 2-D tiled copy of the A rows and one
-//                              of the B rows (SWIZZLE_128B, OOB rows/cols zero-filled)
-//   warps 8-11  splitter     : rewrite the raw fp32 chunk in place as `hi`, write `lo` to the
-//                              twin buffer (element-wise, so the TMA swizzle is preserved),
-//                              fence.proxy.async, arrive
+// One persistent CTA per SM, warp-specialised, tile = 128 rows x BN (<=192) columns:
+//   warp 0      TMA producer A: 128 x 32 fp32 chunks (SWIZZLE_128B, OOB zero-filled) into a deep
+//                              ring of raw landing slots (up to 8 x 16 KB in flight per SM)
+//   warp 3      TMA producer B: BN x 32 chunks of the (L2-resident) weights
+//   warps 8-11  splitter A   : A row -> registers -> hi / lo -> tcgen05.st into TMEM (row = lane,
+//                              K along columns), freeing the landing slot at once
+//   warps 12-15 splitter B   : B chunk rewritten in place as `hi` + twin `lo` buffer
+//                              (element-wise, so the TMA swizzle is preserved), fence.proxy.async
 //   warp 1      MMA issuer   : 3 x tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) per 8-wide
-//                              k-step out of K-major SWIZZLE_128B smem descriptors;
-//                              tcgen05.commit releases the stage / publishes the accumulator
-//   warps 4-7   epilogue     : tcgen05.ld 32 lanes x 32 columns, + bias, swizzled st.shared,
-//                              TMA store (clipped at M, N); two TMEM accumulators so the
-//                              epilogue of tile i overlaps the MMAs of tile i+1
+//                              k-step, A operand from TMEM, B from K-major SWIZZLE_128B smem
+//                              descriptors; tcgen05.commit releases the operand stage /
+//                              publishes the accumulator
+//   warps 4-7   epilogue     : tcgen05.ld 32 lanes x 32 columns (next slab in flight while
+//                              this one is stored), + bias from smem, 16-byte stores straight
+//                              to C; two TMEM accumulators so the epilogue of tile i overlaps
+//                              the MMAs of tile i+1
 //   warp 2      TMEM allocate / free
 // HBM traffic per tile: A once, C once; B chunks are re-read from L2.
 #include <cuda.h>  // CUtensorMap types; the encoder is fetched through the runtime API
@@ -31,17 +35,27 @@ namespace umma {
 constexpr int BM = 128;         // UMMA_M
 constexpr int BK = 32;          // fp32 per K chunk: one 128-byte swizzle row
 constexpr int UK = 8;           // UMMA_K of kind::tf32 (32 bytes)
-constexpr int kThreads = 384;   // 12 warps
+constexpr int kThreads = 512;   // 16 warps
 constexpr int kEpiWarp0 = 4;    // epilogue warps 4..7  (TMEM lane quadrant = warp % 4)
-constexpr int kSplitWarp0 = 8;  // splitter warps 8..11
+constexpr int kSplitWarp0 = 8;   // A splitter warps 8..11 (TMEM lane quadrant = warp % 4)
+constexpr int kBSplitWarp0 = 12; // B splitter warps 12..15
 constexpr int kSlab = 32;       // epilogue column slab (32 fp32 = 128 B = one swizzle row)
 constexpr int kMaxStages = 4;
 constexpr uint32_t kABytes = BM * BK * 4;      // 16 KB
-constexpr uint32_t kSlabBytes = BM * kSlab * 4;  // 16 KB
-constexpr size_t kSmemBudget = 227 * 1024;
+constexpr size_t kSmemBudget = 226 * 1024;  // 227 KB opt-in limit minus 1 KB the kernel uses statically
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
+}
+// one lane of a converged warp (the compiler keeps the guarded region on the uniform datapath)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)
@@ -144,35 +158,204 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// round-to-nearest (ties away) to the 10-bit TF32 mantissa with full-rate integer ops;
+// cvt.rna.tf32.f32 runs on the quarter-rate conversion pipe and paced the splitter warps
 __device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
-// in place: raw -> hi; twin buffer: lo
-__device__ __forceinline__ void split_chunk(float4* hi, float4* lo, int n4, int t) {
-  for (int i = t; i < n4; i += 128) {
-    const float4 x = hi[i];
-    float4 h, l;
-    h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
-    l.x = tf32_rna(x.x - h.x); l.y = tf32_rna(x.y - h.y);
-    l.z = tf32_rna(x.z - h.z); l.w = tf32_rna(x.w - h.w);
-    hi[i] = h;
-    lo[i] = l;
+// in place: raw -> hi; twin buffer: lo.  4 independent 16-byte chains per thread iteration.
+__device__ __forceinline__ void split_chunk(float4* hi, float4* lo, int n4, int t, int nt) {
+  for (int i0 = t; i0 < n4; i0 += 4 * nt) {
+    float4 x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u * nt < n4) x[u] = hi[i0 + u * nt];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (i0 + u * nt < n4) {
+        float4 h, l;
+        h.x = tf32_rna(x[u].x); h.y = tf32_rna(x[u].y);
+        h.z = tf32_rna(x[u].z); h.w = tf32_rna(x[u].w);
+        l.x = tf32_rna(x[u].x - h.x); l.y = tf32_rna(x[u].y - h.y);
+        l.z = tf32_rna(x[u].z - h.z); l.w = tf32_rna(x[u].w - h.w);
+        hi[i0 + u * nt] = h;
+        lo[i0 + u * nt] = l;
+      }
+    }
   }
 }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+        "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
+        "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(
+          taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+      "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),
+      "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]),
+      "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]),
+      "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T : A rows on the 128 lanes, K along the columns
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// one 32-column slab of one accumulator row: + bias (smem broadcast) -> swizzled staging row
+__device__ __forceinline__ void stage_slab(const uint32_t (&v)[32], unsigned char* buf, int row,
+                                           const float* bias_slab) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float4 o;
+    o.x = __uint_as_float(v[4 * j + 0]);
+    o.y = __uint_as_float(v[4 * j + 1]);
+    o.z = __uint_as_float(v[4 * j + 2]);
+    o.w = __uint_as_float(v[4 * j + 3]);
+    if (bias_slab) {
+      const float4 bb = *(const float4*)(bias_slab + 4 * j);
+      o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+    }
+    *(float4*)(buf + row * 128 + ((j ^ (row & 7)) << 4)) = o;
+  }
+}
+
+#define TRC(role, idx, slot)                                                     \
+  do {                                                                          \
+    if (P.trace && blockIdx.x == 0 && (idx) < 32)                               \
+      P.trace[((role) * 32 + (idx)) * 4 + (slot)] = clock64();                  \
+  } while (0)
+
+constexpr uint32_t kTmemCols = 512;
+constexpr int kMaxRing = 8;     // raw A landing slots
+constexpr int kMaxAStages = 4;  // A operand stages in TMEM (64 columns each)
+constexpr int kMaxBSlots = 8;   // B operand slots in smem
+constexpr uint32_t kSlabBytes = BM * kSlab * 4;  // 16 KB epilogue staging buffer
+constexpr int kBarWords = 2 * kMaxRing + 2 * kMaxAStages + 3 * kMaxBSlots + 4 + 2;  // + tmem slot
 
 struct Params {
   const float* bias;  // nullable
   int64_t M;
   int N, K;
-  int BN;             // columns per tile, multiple of 16, <= 256
+  int BN;             // columns per tile, multiple of 16, <= 192
   int n_blocks;       // ceil(N / BN)
   int64_t tiles;      // ceil(M / 128) * n_blocks
-  int stages;
-  uint32_t tmem_cols; // power of two >= 2 * acc_stride
+  int ring;           // raw A landing slots (16 KB each)
+  int a_stages;       // A hi/lo operand stages in TMEM
+  int b_slots;        // B hi/lo operand slots in smem
+  int b_resident;     // 1: slot kc holds chunk kc for the whole kernel (split once per CTA)
+  int epi_bufs;       // 16 KB staging buffers for the TMA store (1 or 2)
+  int epi_groups;     // 1, or 2 when the B splitter warps are free to help (resident B)
   uint32_t acc_stride;
+  long long* trace;   // debug: per-role clock64 stamps of CTA 0 (SPT_UMMA_TRACE)
+  int dbg;            // debug: timing experiments (SPT_UMMA_DBG), wrong results
 };
+
+// Epilogue role of one group of 4 warps (TMEM lane quadrant q = warp % 4).  Group g of
+// P.epi_groups takes the 32-column slabs g, g + groups, ...: tcgen05.ld (next slab in
+// flight) -> + bias -> swizzled staging tile -> TMA store (clipped at M, N).
+__device__ __forceinline__ void epilogue_role(const Params& P, const CUtensorMap* tmC,
+                                              unsigned char* epi, int g, int q, int lane,
+                                              uint32_t tmem_base, uint64_t* tmem_full,
+                                              uint64_t* tmem_empty, const float* bias_s) {
+  const int row = q * 32 + lane;  // tile-local row == TMEM lane
+  const int G = P.epi_groups;
+  const int nb = P.epi_bufs / G;  // staging buffers of this group
+  unsigned char* mybuf = epi + (size_t)g * nb * kSlabBytes;
+  const bool tr = (g == 0 && row == 0);
+  uint32_t tl = 0, sc = 0;
+  for (int64_t t = blockIdx.x; t < P.tiles; t += gridDim.x, ++tl) {
+    const int m_blk = (int)(t / P.n_blocks), n_blk = (int)(t % P.n_blocks);
+    const uint32_t acc = tl & 1, accph = (tl >> 1) & 1;
+    if (tr) TRC(5, tl, 0);
+    mbar_wait(&tmem_full[acc], accph, 7);
+    tc_fence_after();
+    if (tr) TRC(5, tl, 1);
+    const int ncols = min(P.BN, P.N - n_blk * P.BN);
+    const int nslab = (ncols + kSlab - 1) / kSlab;
+    const float* bs = P.bias ? bias_s + n_blk * (int)P.acc_stride : nullptr;
+    const uint32_t tsrc = tmem_base + acc * P.acc_stride + ((uint32_t)(q * 32) << 16);
+    uint32_t va[32], vb[32];
+    if (g < nslab) tmem_ld32_nowait(tsrc + g * kSlab, va);
+    for (int sl = g; sl < nslab; sl += 2 * G) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int cur = sl + h * G;
+        if (cur >= nslab) break;
+        tmem_wait_ld();  // slab `cur` is in registers
+        if (tr && cur == 0) TRC(6, tl, 0);
+        if (cur + G < nslab) {
+          if (h == 0) tmem_ld32_nowait(tsrc + (cur + G) * kSlab, vb);
+          else tmem_ld32_nowait(tsrc + (cur + G) * kSlab, va);
+        }
+        unsigned char* buf = mybuf + (sc % nb) * kSlabBytes;
+        if (q == 0) {  // the store that last used `buf` has read it
+          if (elect_one()) {
+            if (nb == 2) bulk_wait_read<1>();
+            else bulk_wait_read<0>();
+          }
+          __syncwarp();
+        }
+        if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (tr && cur == 0) TRC(6, tl, 1);
+        if (h == 0) stage_slab(va, buf, row, bs ? bs + cur * kSlab : nullptr);
+        else stage_slab(vb, buf, row, bs ? bs + cur * kSlab : nullptr);
+        fence_proxy_async();
+        if (tr && cur == 0) TRC(6, tl, 2);
+        if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (q == 0) {
+          if (elect_one()) {
+            tma_store_2d(tmC, buf, n_blk * P.BN + cur * kSlab, m_blk * BM);
+            bulk_commit();
+          }
+          __syncwarp();
+        }
+        if (tr && cur == 0) TRC(6, tl, 3);
+        ++sc;
+      }
+    }
+    // every tcgen05.ld of this group on this accumulator has completed (last wait::ld)
+    tc_fence_before();
+    mbar_arrive(&tmem_empty[acc]);
+    if (tr) TRC(5, tl, 2);
+  }
+  if (q == 0) {
+    if (elect_one()) bulk_wait_read<0>();
+    __syncwarp();
+  }
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 k_gemm_nt_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -181,15 +364,21 @@ k_gemm_nt_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   unsigned char* smem =
       (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // swizzle atoms
   const uint32_t b_bytes = (uint32_t)P.BN * BK * 4;
-  const uint32_t stage_bytes = 2 * kABytes + 2 * b_bytes;
-  unsigned char* epi = smem + (size_t)P.stages * stage_bytes;  // 2 x 16 KB, 1024-aligned
-  uint64_t* bars = (uint64_t*)(epi + 2 * kSlabBytes);
-  uint64_t* full_raw = bars;
-  uint64_t* full_split = bars + kMaxStages;
-  uint64_t* empty = bars + 2 * kMaxStages;
-  uint64_t* tmem_full = bars + 3 * kMaxStages;
-  uint64_t* tmem_empty = tmem_full + 2;
+  unsigned char* ringbuf = smem;                                   // ring x 16 KB raw A
+  unsigned char* bbuf = ringbuf + (size_t)P.ring * kABytes;        // b_slots x (Bhi | Blo)
+  unsigned char* epi = bbuf + (size_t)P.b_slots * 2 * b_bytes;     // epi_bufs x 16 KB
+  uint64_t* bars = (uint64_t*)(epi + (size_t)P.epi_bufs * kSlabBytes);
+  uint64_t* a_full = bars;                      // [ring]     TMA landed a raw A chunk
+  uint64_t* a_free = a_full + kMaxRing;         // [ring]     splitter holds it in registers
+  uint64_t* a_ready = a_free + kMaxRing;        // [a_stages] hi/lo written to TMEM
+  uint64_t* a_empty = a_ready + kMaxAStages;    // [a_stages] MMAs that read the stage retired
+  uint64_t* b_full = a_empty + kMaxAStages;     // [b_slots]  TMA landed a raw B chunk
+  uint64_t* b_ready = b_full + kMaxBSlots;      // [b_slots]  hi/lo in place
+  uint64_t* b_empty = b_ready + kMaxBSlots;     // [b_slots]  (streaming B only)
+  uint64_t* tmem_full = b_empty + kMaxBSlots;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+  float* bias_s = (float*)(bars + kBarWords);   // [n_blocks * acc_stride], zero-padded
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KC = (P.K + BK - 1) / BK;
@@ -200,142 +389,229 @@ k_gemm_nt_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < P.stages; ++s) {
-      mbar_init(&full_raw[s], 1);
-      mbar_init(&full_split[s], 128);
-      mbar_init(&empty[s], 1);
+    for (int r = 0; r < P.ring; ++r) {
+      mbar_init(&a_full[r], 1);
+      mbar_init(&a_free[r], 128);
+    }
+    for (int s = 0; s < P.a_stages; ++s) {
+      mbar_init(&a_ready[s], 128);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < P.b_slots; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_ready[s], P.b_resident ? 256 : 128);
+      mbar_init(&b_empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 128);
+      mbar_init(&tmem_empty[a], 128 * P.epi_groups);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(tmem_slot)),
-                 "r"(P.tmem_cols)
+                 "r"(kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (P.bias) {
+    // tile n_blk, slab column c reads bias_s[n_blk * acc_stride + c]
+    for (int i = threadIdx.x; i < P.n_blocks * (int)P.acc_stride; i += kThreads) {
+      const int nb = i / (int)P.acc_stride, c = i - nb * (int)P.acc_stride;
+      const int col = nb * P.BN + c;
+      bias_s[i] = (c < P.BN && col < P.N) ? __ldg(P.bias + col) : 0.f;
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_a = tmem_base + 2 * P.acc_stride;  // stage s: hi at +64 s, lo at +64 s + 32
 
   if (warp == 0) {
-    // ---------------- TMA producer ----------------
-    if (lane == 0) {
-      uint32_t it = 0;
+    // ---------------- TMA producer, A: deep ring of raw 128 x 32 chunks ----------------
+    uint32_t it = 0, ph = 0;
+    int r = 0;
+    for (int64_t t = blockIdx.x; t < P.tiles; t += gridDim.x) {
+      const int m_blk = (int)(t / P.n_blocks);
+      for (int kc = 0; kc < KC; ++kc, ++it) {
+        mbar_wait(&a_free[r], ph ^ 1, 0);
+        if (elect_one()) {
+          TRC(0, it, 0);
+          mbar_expect_tx(&a_full[r], kABytes);
+          tma_load_2d(ringbuf + (size_t)r * kABytes, &tmA, kc * BK, m_blk * BM, &a_full[r]);
+        }
+        __syncwarp();
+        if (++r == P.ring) { r = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 3) {
+    // ---------------- TMA producer, B (L2-resident weights) ----------------
+    if (P.b_resident) {
+      if (elect_one()) {
+        for (int kc = 0; kc < KC; ++kc) {
+          mbar_expect_tx(&b_full[kc], b_bytes);
+          tma_load_2d(bbuf + (size_t)kc * 2 * b_bytes, &tmB, kc * BK, 0, &b_full[kc]);
+        }
+      }
+      __syncwarp();
+    } else {
+      uint32_t it = 0, ph = 0;
+      int s = 0;
       for (int64_t t = blockIdx.x; t < P.tiles; t += gridDim.x) {
-        const int m_blk = (int)(t / P.n_blocks), n_blk = (int)(t % P.n_blocks);
+        const int n_blk = (int)(t % P.n_blocks);
         for (int kc = 0; kc < KC; ++kc, ++it) {
-          const int s = it % P.stages;
-          const uint32_t ph = (it / P.stages) & 1;
-          mbar_wait(&empty[s], ph ^ 1, 0);
-          unsigned char* st = smem + (size_t)s * stage_bytes;
-          mbar_expect_tx(&full_raw[s], kABytes + b_bytes);
-          tma_load_2d(st, &tmA, kc * BK, m_blk * BM, &full_raw[s]);
-          tma_load_2d(st + 2 * kABytes, &tmB, kc * BK, n_blk * P.BN, &full_raw[s]);
+          mbar_wait(&b_empty[s], ph ^ 1, 1);
+          if (elect_one()) {
+            TRC(1, it, 0);
+            mbar_expect_tx(&b_full[s], b_bytes);
+            tma_load_2d(bbuf + (size_t)s * 2 * b_bytes, &tmB, kc * BK, n_blk * P.BN,
+                        &b_full[s]);
+          }
+          __syncwarp();
+          if (++s == P.b_slots) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.BN >> 3) << 17) |
-                             ((uint32_t)(BM >> 4) << 24);
-      uint32_t it = 0, tl = 0;
-      for (int64_t t = blockIdx.x; t < P.tiles; t += gridDim.x, ++tl) {
-        const uint32_t acc = tl & 1, accph = (tl >> 1) & 1;
-        mbar_wait(&tmem_empty[acc], accph ^ 1, 1);
+    // ---------------- MMA issuer (converged warp, one elected lane issues) ----------------
+    uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.BN >> 3) << 17) |
+                     ((uint32_t)(BM >> 4) << 24);
+    if (P.dbg == 2)
+      idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.BN >> 3) << 17) |
+              ((uint32_t)(BM >> 4) << 24);
+    uint32_t it = 0, tl = 0;
+    int sa = 0, sb = 0;
+    uint32_t pha = 0, phb = 0;
+    const uint32_t bbase = smem_u32(bbuf);
+    for (int64_t t = blockIdx.x; t < P.tiles; t += gridDim.x, ++tl) {
+      const uint32_t acc = tl & 1, accph = (tl >> 1) & 1;
+      mbar_wait(&tmem_empty[acc], accph ^ 1, 2);
+      tc_fence_after();
+      const uint32_t d = tmem_base + acc * P.acc_stride;
+      for (int kc = 0; kc < KC; ++kc, ++it) {
+        if (P.b_resident) sb = kc;
+        if (lane == 0) TRC(4, it, 0);
+        if (!P.b_resident)
+          mbar_wait(&b_ready[sb], phb, 3);
+        else if (tl == 0)
+          mbar_wait(&b_ready[sb], 0, 3);
+        mbar_wait(&a_ready[sa], pha, 3);
         tc_fence_after();
-        const uint32_t d = tmem_base + acc * P.acc_stride;
-        for (int kc = 0; kc < KC; ++kc, ++it) {
-          const int s = it % P.stages;
-          const uint32_t ph = (it / P.stages) & 1;
-          mbar_wait(&full_split[s], ph, 2);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint64_t a_hi = smem_desc_sw128(sa), a_lo = smem_desc_sw128(sa + kABytes);
-          const uint64_t b_hi = smem_desc_sw128(sa + 2 * kABytes);
-          const uint64_t b_lo = smem_desc_sw128(sa + 2 * kABytes + b_bytes);
+        if (lane == 0) TRC(4, it, 1);
+        const uint32_t a_hi = tmem_a + 64 * sa, a_lo = a_hi + 32;
+        const uint32_t sbase = bbase + (uint32_t)sb * 2 * b_bytes;
+        const uint64_t b_hi = smem_desc_sw128(sbase), b_lo = smem_desc_sw128(sbase + b_bytes);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
             const uint64_t o = (uint64_t)(k * UK * 4 >> 4);  // advance inside the swizzle row
-            umma_tf32(d, a_lo + o, b_hi + o, idesc, (kc | k) != 0);
-            umma_tf32(d, a_hi + o, b_lo + o, idesc, 1);
-            umma_tf32(d, a_hi + o, b_hi + o, idesc, 1);
+            if (P.dbg == 2) {
+              umma_f16_ts(d, a_lo + k * UK, b_hi + o, idesc, (kc | k) != 0);
+              umma_f16_ts(d, a_hi + k * UK, b_lo + o, idesc, 1);
+              umma_f16_ts(d, a_hi + k * UK, b_hi + o, idesc, 1);
+              continue;
+            }
+            umma_tf32_ts(d, a_lo + k * UK, b_hi + o, idesc, (kc | k) != 0);
+            if (P.dbg == 1) continue;
+            umma_tf32_ts(d, a_hi + k * UK, b_lo + o, idesc, 1);
+            umma_tf32_ts(d, a_hi + k * UK, b_hi + o, idesc, 1);
           }
-          umma_commit(&empty[s]);  // stage free once these MMAs have read it
+          umma_commit(&a_empty[sa]);  // TMEM stage free once these MMAs have read it
+          if (!P.b_resident) umma_commit(&b_empty[sb]);
+          if (kc == KC - 1) umma_commit(&tmem_full[acc]);
         }
-        umma_commit(&tmem_full[acc]);
+        __syncwarp();
+        if (lane == 0) TRC(4, it, 2);
+        if (++sa == P.a_stages) { sa = 0; pha ^= 1; }
+        if (!P.b_resident && ++sb == P.b_slots) { sb = 0; phb ^= 1; }
+      }
+    }
+  } else if (warp >= kBSplitWarp0) {
+    // ---------------- splitter, B: in place -> hi, twin buffer -> lo ----------------
+    const int ts = threadIdx.x - kBSplitWarp0 * 32;
+    if (P.b_resident) {
+      // resident weights: split once, together with the (still idle) epilogue warps
+      for (int kc = 0; kc < KC; ++kc) {
+        mbar_wait(&b_full[kc], 0, 6);
+        unsigned char* bs = bbuf + (size_t)kc * 2 * b_bytes;
+        split_chunk((float4*)bs, (float4*)(bs + b_bytes), b_bytes / 16, ts + 128, 256);
+        fence_proxy_async();
+        mbar_arrive(&b_ready[kc]);
+        if (ts == 0) TRC(3, kc, 2);
+      }
+      if (P.epi_groups == 2)  // the weights are split once: become the second epilogue group
+        epilogue_role(P, &tmC, epi, 1, warp - kBSplitWarp0, lane, tmem_base, tmem_full,
+                      tmem_empty, bias_s);
+    } else {
+      uint32_t it = 0;
+      for (int64_t t = blockIdx.x; t < P.tiles; t += gridDim.x) {
+        for (int kc = 0; kc < KC; ++kc, ++it) {
+          const int s = it % P.b_slots;
+          if (ts == 0) TRC(3, it, 0);
+          mbar_wait(&b_full[s], (it / P.b_slots) & 1, 6);
+          if (ts == 0) TRC(3, it, 1);
+          unsigned char* bs = bbuf + (size_t)s * 2 * b_bytes;
+          split_chunk((float4*)bs, (float4*)(bs + b_bytes), b_bytes / 16, ts, 128);
+          fence_proxy_async();
+          mbar_arrive(&b_ready[s]);
+          if (ts == 0) TRC(3, it, 2);
+        }
       }
     }
   } else if (warp >= kSplitWarp0) {
-    // ---------------- splitter ----------------
-    const int ts = threadIdx.x - kSplitWarp0 * 32;
+    // ---------------- splitter, A: raw row -> registers -> hi / lo -> TMEM ----------------
+    const int q = warp - kSplitWarp0;   // TMEM lane quadrant (warp % 4)
+    const int row = q * 32 + lane;      // chunk row == TMEM lane
     uint32_t it = 0;
     for (int64_t t = blockIdx.x; t < P.tiles; t += gridDim.x) {
       for (int kc = 0; kc < KC; ++kc, ++it) {
-        const int s = it % P.stages;
-        const uint32_t ph = (it / P.stages) & 1;
-        mbar_wait(&full_raw[s], ph, 3);
-        unsigned char* st = smem + (size_t)s * stage_bytes;
-        split_chunk((float4*)st, (float4*)(st + kABytes), kABytes / 16, ts);
-        split_chunk((float4*)(st + 2 * kABytes), (float4*)(st + 2 * kABytes + b_bytes),
-                    b_bytes / 16, ts);
-        fence_proxy_async();
-        mbar_arrive(&full_split[s]);
+        const int r = it % P.ring, s = it % P.a_stages;
+        if (row == 0) TRC(2, it, 0);
+        mbar_wait(&a_full[r], (it / P.ring) & 1, 4);
+        if (row == 0) TRC(2, it, 1);
+        const unsigned char* arow = ringbuf + (size_t)r * kABytes + row * 128;
+        float4 x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = *(const float4*)(arow + ((j ^ (row & 7)) << 4));
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xs[4] = {x[j].x, x[j].y, x[j].z, x[j].w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float h = tf32_rna(xs[c]);
+            hi[4 * j + c] = __float_as_uint(h);
+            lo[4 * j + c] = __float_as_uint(tf32_rna(xs[c] - h));
+          }
+        }
+        mbar_arrive(&a_free[r]);  // values are in registers: the slot can be refilled
+        mbar_wait(&a_empty[s], ((it / P.a_stages) & 1) ^ 1, 5);  // previous MMAs retired
+        tc_fence_after();
+        if (row == 0) TRC(2, it, 2);
+        const uint32_t ta = tmem_a + 64 * s + ((uint32_t)(q * 32) << 16);
+        tmem_st32(ta, hi);
+        tmem_st32(ta + 32, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(&a_ready[s]);
+        if (row == 0) TRC(2, it, 3);
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ---------------- epilogue ----------------
-    const int q = warp - kEpiWarp0;        // TMEM lane quadrant
-    const int et = threadIdx.x - kEpiWarp0 * 32;
-    const int row = q * 32 + lane;         // tile-local row == TMEM lane
-    uint32_t tl = 0, sc = 0;
-    for (int64_t t = blockIdx.x; t < P.tiles; t += gridDim.x, ++tl) {
-      const int m_blk = (int)(t / P.n_blocks), n_blk = (int)(t % P.n_blocks);
-      const uint32_t acc = tl & 1, accph = (tl >> 1) & 1;
-      mbar_wait(&tmem_full[acc], accph, 4);
-      tc_fence_after();
-      const int ncols = min(P.BN, P.N - n_blk * P.BN);
-      const int nslab = (ncols + kSlab - 1) / kSlab;
-      for (int sl = 0; sl < nslab; ++sl, ++sc) {
-        unsigned char* buf = epi + (sc & 1) * kSlabBytes;
-        if (et == 0) bulk_wait_read<1>();  // the store that last used `buf` has read it
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        uint32_t v[32];
-        tmem_ld32(tmem_base + acc * P.acc_stride + ((uint32_t)(q * 32) << 16) + sl * kSlab, v);
-        const int c0 = n_blk * P.BN + sl * kSlab;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 o;
-          o.x = __uint_as_float(v[4 * j + 0]);
-          o.y = __uint_as_float(v[4 * j + 1]);
-          o.z = __uint_as_float(v[4 * j + 2]);
-          o.w = __uint_as_float(v[4 * j + 3]);
-          if (P.bias) {
-            const int c = c0 + 4 * j;
-            if (c + 0 < P.N) o.x += __ldg(P.bias + c + 0);
-            if (c + 1 < P.N) o.y += __ldg(P.bias + c + 1);
-            if (c + 2 < P.N) o.z += __ldg(P.bias + c + 2);
-            if (c + 3 < P.N) o.w += __ldg(P.bias + c + 3);
-          }
-          *(float4*)(buf + row * 128 + ((j ^ (row & 7)) << 4)) = o;
-        }
+    if (P.b_resident) {
+      const int ts = threadIdx.x - kEpiWarp0 * 32;
+      for (int kc = 0; kc < KC; ++kc) {
+        mbar_wait(&b_full[kc], 0, 6);
+        unsigned char* bs = bbuf + (size_t)kc * 2 * b_bytes;
+        split_chunk((float4*)bs, (float4*)(bs + b_bytes), b_bytes / 16, ts, 256);
         fence_proxy_async();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (et == 0) {
-          tma_store_2d(&tmC, buf, c0, m_blk * BM);
-          bulk_commit();
-        }
+        mbar_arrive(&b_ready[kc]);
       }
-      tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
     }
-    if (et == 0) bulk_wait_read<0>();
+    epilogue_role(P, &tmC, epi, 0, warp - kEpiWarp0, lane, tmem_base, tmem_full, tmem_empty,
+                  bias_s);
   }
 
   tc_fence_before();
@@ -343,7 +619,7 @@ k_gemm_nt_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"(P.tmem_cols)
+                 "r"(kTmemCols)
                  : "memory");
   }
 }
@@ -391,7 +667,7 @@ bool shape_ok(const float* A, int64_t M, int64_t K, int64_t lda, const float* B,
               int64_t ldb, const float* C, int64_t ldc) {
   const uintptr_t al = (uintptr_t)A | (uintptr_t)B | (uintptr_t)C;
   return (al & 15) == 0 && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0 && M >= 1 &&
-         M < (1ll << 31) - 256 && N >= 1 && N < (1 << 30) && K >= 1 && K < (1 << 30) &&
+         M < (1ll << 31) - 256 && N >= 1 && N <= 4096 && K >= 1 && K < (1 << 30) &&
          encoder() != nullptr;
 }
 
@@ -403,20 +679,48 @@ int launch(const float* A, int64_t M, int64_t K, int64_t lda, const float* B, in
   P.N = (int)N;
   P.K = (int)K;
   const int n16 = (int)((N + 15) / 16 * 16);
-  P.BN = n16 <= 256 ? n16 : 128;
+  P.BN = n16 <= 192 ? n16 : 128;  // 2 accumulators + >= 2 A-operand stages in 512 TMEM columns
   P.n_blocks = (int)((N + P.BN - 1) / P.BN);
   P.tiles = ((M + BM - 1) / BM) * P.n_blocks;
   P.acc_stride = (uint32_t)((P.BN + 31) / 32 * 32);
-  uint32_t cols = 32;
-  while (cols < 2 * P.acc_stride) cols <<= 1;
-  P.tmem_cols = cols;
-  const size_t stage_bytes = 2 * (size_t)kABytes + 2 * (size_t)P.BN * BK * 4;
-  const size_t fixed = 1024 + 2 * (size_t)kSlabBytes + 256;
-  int stages = (int)((kSmemBudget - fixed) / stage_bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
-  SPT_REQUIRE(stages >= 2, SPT_E_UNSUPPORTED, "gemm_nt(umma): shared memory budget");
-  P.stages = stages;
-  const size_t smem = fixed + (size_t)stages * stage_bytes;
+  int a_stages = (int)((kTmemCols - 2 * P.acc_stride) / 64);
+  P.a_stages = a_stages > kMaxAStages ? kMaxAStages : a_stages;
+  const int KC = (int)((K + BK - 1) / BK);
+  const size_t b_slot = 2 * (size_t)P.BN * BK * 4;
+  const size_t misc = 1024 /*alignment*/ + (size_t)kBarWords * 8 + 16 +
+                      (size_t)P.n_blocks * P.acc_stride * 4;
+  // B resident (split once per CTA) when the whole [BN, K] hi/lo pair fits beside >= 2
+  // landing slots; otherwise B chunks stream through 2-3 slots like A.
+  P.b_resident = 0;
+  P.ring = 0;
+  if (P.n_blocks == 1 && KC <= kMaxBSlots) {
+    for (int eb = 2; eb >= 1 && !P.b_resident; --eb) {
+      const size_t fixed = misc + (size_t)KC * b_slot + (size_t)eb * kSlabBytes;
+      if (fixed + (eb == 2 ? 4 : 2) * (size_t)kABytes <= kSmemBudget) {
+        P.b_resident = 1;
+        P.b_slots = KC;
+        P.epi_bufs = eb;
+        P.ring = (int)((kSmemBudget - fixed) / kABytes);
+      }
+    }
+  }
+  if (!P.b_resident) {
+    P.epi_bufs = 2;
+    P.b_slots = 3;
+    size_t fixed = misc + (size_t)P.b_slots * b_slot + (size_t)P.epi_bufs * kSlabBytes;
+    if (fixed + 3 * (size_t)kABytes > kSmemBudget) {
+      P.b_slots = 2;
+      fixed = misc + (size_t)P.b_slots * b_slot + (size_t)P.epi_bufs * kSlabBytes;
+    }
+    SPT_REQUIRE(fixed + 2 * (size_t)kABytes <= kSmemBudget, SPT_E_UNSUPPORTED,
+                "gemm_nt(umma): shared memory budget");
+    P.ring = (int)((kSmemBudget - fixed) / kABytes);
+  }
+  P.epi_groups = (P.b_resident && P.epi_bufs == 2) ? 2 : 1;
+  if (P.ring > kMaxRing) P.ring = kMaxRing;
+  SPT_REQUIRE(P.a_stages >= 2 && P.ring >= 2, SPT_E_UNSUPPORTED, "gemm_nt(umma): on-chip budget");
+  const size_t smem = misc + (size_t)P.b_slots * b_slot + (size_t)P.epi_bufs * kSlabBytes +
+                      (size_t)P.ring * kABytes;
 
   CUtensorMap tmA, tmB, tmC;
   SPT_REQUIRE(make_map(&tmA, A, M, K, lda, BM) && make_map(&tmB, B, N, K, ldb, P.BN) &&
@@ -434,7 +738,36 @@ int launch(const float* A, int64_t M, int64_t K, int64_t lda, const float* B, in
     attr = true;
   }
   const unsigned grid = (unsigned)(P.tiles < sm_count ? P.tiles : sm_count);
+  static long long* trace_dev = nullptr;
+  const bool tracing = getenv("SPT_UMMA_TRACE") != nullptr;
+  if (tracing && !trace_dev) cudaMalloc(&trace_dev, 7 * 32 * 4 * sizeof(long long));
+  if (tracing) cudaMemsetAsync(trace_dev, 0, 7 * 32 * 4 * sizeof(long long), stream);
+  P.trace = tracing ? trace_dev : nullptr;
+  {
+    const char* e = getenv("SPT_UMMA_DBG");
+    P.dbg = e ? atoi(e) : 0;
+  }
   k_gemm_nt_umma<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmC, P);
+  if (tracing) {
+    static int dumped = 0;
+    cudaStreamSynchronize(stream);
+    if (dumped++ == 2) {
+      static long long h[7 * 32 * 4];
+      cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
+      long long t0 = h[0];
+      const char* names[7] = {"prodA", "prodB", "splitA", "splitB", "mma", "epi", "slab"};
+      printf("TRACE cfg ring %d a_stages %d b_slots %d resident %d epi_bufs %d smem %zu\n", P.ring,
+             P.a_stages, P.b_slots, P.b_resident, P.epi_bufs, smem);
+      for (int r = 0; r < 7; ++r)
+        for (int i = 0; i < 32; ++i) {
+          long long* e = &h[(r * 32 + i) * 4];
+          if (!e[0] && !e[1] && !e[2]) continue;
+          printf("TRACE %s %d %lld %lld %lld %lld\n", names[r], i, e[0] ? e[0] - t0 : -1,
+                 e[1] ? e[1] - t0 : -1, e[2] ? e[2] - t0 : -1, e[3] ? e[3] - t0 : -1);
+        }
+      fflush(stdout);
+    }
+  }
   return check_launch("gemm_nt(umma)");
 }
 

@@ -6,7 +6,7 @@ import torch
 from superpoint_transformer_b200 import ops
 faulthandler.dump_traceback_later(120, exit=True)
 dev = 'cuda'
-shapes = [(128, 128, 32), (128, 128, 128), (1000, 128, 128), (4096, 16, 12), (5000, 160, 128),
+shapes = [(50000, 256, 128), (128, 128, 32), (128, 128, 128), (1000, 128, 128), (4096, 16, 12), (5000, 160, 128),
           (20000, 256, 128), (7777, 300, 64), (3001, 128, 256), (100000, 128, 128),
           (100000, 160, 128), (100000, 128, 256), (100000, 256, 128)]
 if os.environ.get("SHAPES"):
