@@ -300,6 +300,10 @@ bool shape_ok(const float* A, int64_t M, int64_t K, int64_t lda, const float* B,
               int64_t ldb, const float* C, int64_t ldc);
 int launch(const float* A, int64_t M, int64_t K, int64_t lda, const float* B, int64_t N,
            int64_t ldb, const float* bias, float* C, int64_t ldc, cudaStream_t stream);
+bool tn_shape_ok(const float* A, int64_t M, int64_t N, int64_t lda, const float* B, int64_t K,
+                 int64_t ldb);
+int tn_launch(const float* A, int64_t M, int64_t N, int64_t lda, const float* B, int64_t K,
+              int64_t ldb, float* C, int64_t ldc, float* colsum, cudaStream_t stream);
 }  // namespace umma
 }  // namespace spt
 
@@ -360,6 +364,8 @@ int spt_gemm_tn_acc(const float* A, int64_t M, int64_t N, int64_t lda, const flo
                   ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0,
               SPT_E_UNSUPPORTED,
               "gemm_tn_acc: N, K, lda, ldb must be multiples of 4 and A, B 16-byte aligned");
+  if (M >= 2048 && use_umma() && umma::tn_shape_ok(A, M, N, lda, B, K, ldb))
+    return umma::tn_launch(A, M, N, lda, B, K, ldb, C, ldc, colsumA, (cudaStream_t)stream_);
   int ntiles = (int)ceil_div(N, gemm::TM), ktiles = (int)ceil_div(K, gemm::TK);
   int64_t tiles = (int64_t)ntiles * ktiles;
   // enough row slabs to fill the machine (~4 CTAs per SM), slabs multiple of TR rows

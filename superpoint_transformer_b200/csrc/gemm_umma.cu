@@ -649,7 +649,7 @@ static EncodeTiledFn encoder() {
 
 // row-major fp32 matrix [rows, cols], leading dimension ld; box = [box_rows, 32 cols]
 static bool make_map(CUtensorMap* tm, const float* ptr, int64_t rows, int64_t cols, int64_t ld,
-                     int box_rows) {
+                     int box_rows, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = encoder();
   if (!enc) return false;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -657,7 +657,7 @@ static bool make_map(CUtensorMap* tm, const float* ptr, int64_t rows, int64_t co
   cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides,
-             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
          CUDA_SUCCESS;
 }
@@ -769,6 +769,343 @@ int launch(const float* A, int64_t M, int64_t K, int64_t lda, const float* B, in
     }
   }
   return check_launch("gemm_nt(umma)");
+}
+
+
+// ==========================================================================================
+//  C[N,K] += A[M,N]^T . B[M,K] ;  colsumA[N] += column sums of A        (dW / dbias of Linear)
+// ==========================================================================================
+// The reduction runs over the ROWS of both operands, so both are "MN-major" for the tensor
+// core: a [rows x 32 columns] TMA box with SWIZZLE_128B_ATOM_32B is exactly one column block
+// of the canonical MN-major tf32 layout (128-byte rows, column blocks LBO apart).  Per chunk of
+// `bkm` rows: TMA lands the column blocks of A and B, 8 splitter warps rewrite them in place
+// as `hi` and write the `lo` twins (and keep per-thread column sums of A for dbias), the MMA
+// warp issues 3 x tcgen05.mma.kind::tf32 per 8-row k-step into TMEM accumulators that live
+// for the whole kernel; at the end 4 warps add the [N, K] partial of this CTA to C with
+// 16-byte atomics.  Each CTA owns a contiguous range of row chunks.
+struct TnParams {
+  float* C;
+  int64_t ldc;
+  float* colsum;      // nullable
+  int64_t M;
+  int N, K;
+  int bkm;            // rows per chunk: 8, 16 or 32
+  int ncbA, ncbB;     // 32-column blocks TMA fills for A (= ceil(N/32)) and B (= ceil(Kp/32))
+  int n_blocks;       // 128-row blocks of the output (= ceil(N/128))
+  int Kp;             // K rounded up to 16 (UMMA N); pieces of <= 256 columns
+  int stages;
+  int64_t chunks;     // ceil(M / bkm)
+  uint32_t blk_bytes; // bkm * 128: one column block of one operand half
+  uint32_t a_bytes;   // a_blocks * blk_bytes      (A region, hi or lo)
+  int a_blocks;       // 4 per 128-row output block; 1 for a last block of <= 32 real columns
+  int grouped;        // N, K <= 32: the four MN blocks hold four consecutive row groups
+                      // (block-diagonal batching, 4x fewer MMAs); bkm = rows per group
+  uint32_t b_bytes;   // ncbB * blk_bytes          (B region, hi or lo)
+};
+
+// MN-major 32-bit operand: the only layout the tensor core takes is SWIZZLE_128B_BASE32B
+// (32-byte units XOR-ed with the row index mod 4 inside 128-byte rows; 4-row K atoms), which
+// is what TMA writes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+// LBO = byte stride between 32-column blocks, SBO = 512 (between 4-row groups).
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | (32ull << 32) |
+         (1ull << 46) | (1ull << 61);
+}
+
+constexpr int kTnSplitWarp0 = 8;    // splitter warps 8..15 (256 threads)
+constexpr int kTnMaxStages = 4;
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_gemm_tn_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const TnParams P) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem =
+      (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // stage: [A hi | A lo | B hi | B lo]
+  const uint32_t stage_bytes = 2 * (P.a_bytes + P.b_bytes);
+  uint64_t* bars = (uint64_t*)(smem + (size_t)P.stages * stage_bytes);
+  uint64_t* full = bars;                       // [stages] TMA landed the raw chunk
+  uint64_t* split = full + kTnMaxStages;       // [stages] hi/lo written (256 arrivals)
+  uint64_t* empty = split + kTnMaxStages;      // [stages] MMAs that read the stage retired
+  uint64_t* acc_full = empty + kTnMaxStages;   // [1]
+  uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
+  float* colsum_s = (float*)(bars + 16);       // [n_blocks * 128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // contiguous chunk range of this CTA
+  const int64_t per = (P.chunks + gridDim.x - 1) / gridDim.x;
+  const int64_t c0 = (int64_t)blockIdx.x * per;
+  const int64_t c1 = min(P.chunks, c0 + per);
+  const int nchunks = (int)max((int64_t)0, c1 - c0);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < P.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&split[s], 256);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < P.n_blocks * 128; i += kThreads) colsum_s[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int ksteps = P.bkm / UK;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    int s = 0;
+    uint32_t ph = 0;
+    for (int c = 0; c < nchunks; ++c) {
+      mbar_wait(&empty[s], ph ^ 1, 0);
+      if (elect_one()) {
+        unsigned char* st = smem + (size_t)s * stage_bytes;
+        const int rows_per_chunk = P.grouped ? 4 * P.bkm : P.bkm;
+        const int row0 = (int)((c0 + c) * rows_per_chunk);
+        mbar_expect_tx(&full[s], (uint32_t)(P.ncbA + P.ncbB) * P.blk_bytes);
+        unsigned char* sb = st + 2 * P.a_bytes;
+        if (P.grouped) {  // block g <- rows of group g, columns 0..31
+          for (int g = 0; g < 4; ++g) {
+            tma_load_2d(st + (size_t)g * P.blk_bytes, &tmA, 0, row0 + g * P.bkm, &full[s]);
+            tma_load_2d(sb + (size_t)g * P.blk_bytes, &tmB, 0, row0 + g * P.bkm, &full[s]);
+          }
+        } else {
+          for (int cb = 0; cb < P.ncbA; ++cb)
+            tma_load_2d(st + (size_t)cb * P.blk_bytes, &tmA, cb * 32, row0, &full[s]);
+          for (int cb = 0; cb < P.ncbB; ++cb)
+            tma_load_2d(sb + (size_t)cb * P.blk_bytes, &tmB, cb * 32, row0, &full[s]);
+        }
+      }
+      __syncwarp();
+      if (++s == P.stages) { s = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    int s = 0;
+    uint32_t ph = 0;
+    const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                ((uint32_t)(BM >> 4) << 24);
+    const uint32_t sbase0 = smem_u32(smem);
+    for (int c = 0; c < nchunks; ++c) {
+      mbar_wait(&split[s], ph, 1);
+      tc_fence_after();
+      const uint32_t sa = sbase0 + (uint32_t)s * stage_bytes;
+      const uint32_t sb = sa + 2 * P.a_bytes;
+      if (elect_one()) {
+        for (int ks = 0; ks < ksteps; ++ks) {
+          for (int nb = 0; nb < P.n_blocks; ++nb) {
+            // a block of <= 32 real columns is stored once; LBO = 0 makes the other three
+            // 32-row groups of the M=128 operand alias it (their output rows are never read)
+            const uint32_t lbo_a = (P.ncbA - 4 * nb == 1) ? 0u : P.blk_bytes;
+            const uint32_t a_hi_addr = sa + (uint32_t)nb * 4 * P.blk_bytes + ks * 1024;
+            const uint64_t a_hi = smem_desc_mn_sw128(a_hi_addr, lbo_a);
+            const uint64_t a_lo = smem_desc_mn_sw128(a_hi_addr + P.a_bytes, lbo_a);
+            for (int k0 = 0; k0 < P.Kp; k0 += 256) {
+              const int nw = min(256, P.Kp - k0);
+              const uint32_t idesc = idesc_base | ((uint32_t)(nw >> 3) << 17);
+              const uint32_t b_hi_addr = sb + (uint32_t)(k0 >> 5) * P.blk_bytes + ks * 1024;
+              const uint64_t b_hi = smem_desc_mn_sw128(b_hi_addr, P.blk_bytes);
+              const uint64_t b_lo = smem_desc_mn_sw128(b_hi_addr + P.b_bytes, P.blk_bytes);
+              const uint32_t d = tmem_base + (uint32_t)(nb * P.Kp + k0);
+              const uint32_t accum = (c | ks) != 0;
+              umma_tf32(d, a_lo, b_hi, idesc, accum);
+              umma_tf32(d, a_hi, b_lo, idesc, 1);
+              umma_tf32(d, a_hi, b_hi, idesc, 1);
+            }
+          }
+        }
+        umma_commit(&empty[s]);
+        if (c == nchunks - 1) umma_commit(acc_full);
+      }
+      __syncwarp();
+      if (++s == P.stages) { s = 0; ph ^= 1; }
+    }
+  } else if (warp >= kTnSplitWarp0) {
+    // ---------------- splitter (+ column sums of A) ----------------
+    const int ts = threadIdx.x - kTnSplitWarp0 * 32;  // 0..255
+    const int blk4 = P.bkm * 8;                       // float4 per column block
+    const int nA4 = P.ncbA * blk4, nB4 = P.ncbB * blk4;
+    // thread-fixed position inside a block: row (ts / 8) % bkm, physical 16-byte chunk ts % 8
+    const int prow = (ts >> 3) % P.bkm;
+    // logical 4-column group of this thread (32-byte units swizzled with row % 4)
+    const int lchunk = ((((ts & 7) >> 1) ^ (prow & 3)) << 1) | (ts & 1);
+    float4 cs[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) cs[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int c = 0; c < nchunks; ++c) {
+      mbar_wait(&full[s], ph, 2);
+      unsigned char* st = smem + (size_t)s * stage_bytes;
+      float4* ahi = (float4*)st;
+      float4* alo = (float4*)(st + P.a_bytes);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = ts + 256 * u;
+        if (i < nA4) {
+          const float4 x = ahi[i];
+          float4 h, l;
+          h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
+          l.x = tf32_rna(x.x - h.x); l.y = tf32_rna(x.y - h.y);
+          l.z = tf32_rna(x.z - h.z); l.w = tf32_rna(x.w - h.w);
+          ahi[i] = h;
+          alo[i] = l;
+          cs[u].x += x.x; cs[u].y += x.y; cs[u].z += x.z; cs[u].w += x.w;
+        }
+      }
+      float4* bhi = (float4*)(st + 2 * P.a_bytes);
+      float4* blo = (float4*)(st + 2 * P.a_bytes + P.b_bytes);
+      split_chunk(bhi, blo, nB4, ts, 256);
+      fence_proxy_async();
+      mbar_arrive(&split[s]);
+      if (++s == P.stages) { s = 0; ph ^= 1; }
+    }
+    if (P.colsum) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = ts + 256 * u;
+        if (i < nA4) {
+          const int col = (P.grouped ? 0 : (i / blk4) * 32) + lchunk * 4;
+          atomicAdd(&colsum_s[col + 0], cs[u].x);
+          atomicAdd(&colsum_s[col + 1], cs[u].y);
+          atomicAdd(&colsum_s[col + 2], cs[u].z);
+          atomicAdd(&colsum_s[col + 3], cs[u].w);
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0 && nchunks > 0) {
+    // ---------------- epilogue: TMEM partial -> atomics on C ----------------
+    const int q = warp - kEpiWarp0;
+    const int row = q * 32 + lane;
+    mbar_wait(acc_full, 0, 3);
+    tc_fence_after();
+    for (int nb = 0; nb < P.n_blocks; ++nb) {
+      // grouped: output row `lane` of row group q sits on the diagonal block (q, q)
+      const int n = P.grouped ? lane : nb * 128 + row;
+      for (int kk = 0; kk < (P.grouped ? 32 : P.Kp); kk += 32) {
+        const int k0 = kk;  // column of C
+        const int tcol = P.grouped ? 32 * q : nb * P.Kp + kk;
+        uint32_t v[32];
+        tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)tcol, v);
+        tmem_wait_ld();
+        if (n < P.N) {
+          float* crow = P.C + (int64_t)n * P.ldc + k0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (k0 + j + 3 < P.K && (P.ldc & 3) == 0) {  // 16-byte vector reduction
+              atomicAdd((float4*)(crow + j),
+                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                    __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (k0 + j + e < P.K) atomicAdd(crow + j + e, __uint_as_float(v[j + e]));
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (P.colsum && nchunks > 0)
+    for (int i = threadIdx.x; i < P.N; i += kThreads) {
+      const float v = colsum_s[i];
+      if (v != 0.f) atomicAdd(P.colsum + i, v);
+    }
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(kTmemCols)
+                 : "memory");
+  }
+}
+
+bool tn_shape_ok(const float* A, int64_t M, int64_t N, int64_t lda, const float* B, int64_t K,
+                 int64_t ldb) {
+  const uintptr_t al = (uintptr_t)A | (uintptr_t)B;
+  if ((al & 15) != 0 || lda % 4 != 0 || ldb % 4 != 0 || M < 1 || M >= (1ll << 31) - 64 ||
+      N < 1 || K < 1 || encoder() == nullptr)
+    return false;
+  const int64_t n_blocks = (N + 127) / 128, Kp = (K + 15) / 16 * 16;
+  return n_blocks * Kp <= (int64_t)kTmemCols && N <= 256;  // accumulators + 8 colsum registers
+}
+
+int tn_launch(const float* A, int64_t M, int64_t N, int64_t lda, const float* B, int64_t K,
+              int64_t ldb, float* C, int64_t ldc, float* colsum, cudaStream_t stream) {
+  TnParams P;
+  P.C = C;
+  P.ldc = ldc;
+  P.colsum = colsum;
+  P.M = M;
+  P.N = (int)N;
+  P.K = (int)K;
+  P.n_blocks = (int)((N + 127) / 128);
+  P.Kp = (int)((K + 15) / 16 * 16);
+  P.ncbA = (int)((N + 31) / 32);
+  P.ncbB = (P.Kp + 31) / 32;
+  P.grouped = (N <= 32 && K <= 32) ? 1 : 0;
+  if (P.grouped) {
+    P.Kp = 128;
+    P.ncbA = P.ncbB = 4;
+  }
+  const size_t misc = 1024 + 16 * 8 + (size_t)P.n_blocks * 128 * 4;
+  P.a_blocks = (P.ncbA - 4 * (P.n_blocks - 1) == 1) ? 4 * (P.n_blocks - 1) + 1 : 4 * P.n_blocks;
+  P.bkm = 0;
+  // rows per chunk: as many as fit 3 stages (narrow operands take up to 256-row chunks so that
+  // the per-chunk barrier round trips amortise); bkm * ncbA <= 256 keeps the per-thread
+  // column sums in 8 registers
+  for (int bkm = 256; bkm >= 8 && !P.bkm; bkm >>= 1) {
+    if (bkm * P.ncbA > 256 && bkm > 8) continue;
+    const size_t blk = (size_t)bkm * 128;
+    const size_t stage = 2 * ((size_t)P.a_blocks + P.ncbB) * blk;
+    const int st = (int)((kSmemBudget - misc) / stage);
+    if (st >= 3 || (bkm == 8 && st >= 2)) {
+      P.bkm = bkm;
+      P.stages = st > kTnMaxStages ? kTnMaxStages : st;
+    }
+  }
+  SPT_REQUIRE(P.bkm != 0, SPT_E_UNSUPPORTED, "gemm_tn_acc(umma): shared memory budget");
+  P.blk_bytes = (uint32_t)P.bkm * 128;
+  P.a_bytes = (uint32_t)P.a_blocks * P.blk_bytes;
+  P.b_bytes = (uint32_t)P.ncbB * P.blk_bytes;
+  P.chunks = P.grouped ? (M + 4 * P.bkm - 1) / (4 * P.bkm) : (M + P.bkm - 1) / P.bkm;
+  const size_t smem = misc + (size_t)P.stages * 2 * (P.a_bytes + P.b_bytes);
+
+  CUtensorMap tmA, tmB;
+  SPT_REQUIRE(make_map(&tmA, A, M, N, lda, P.bkm, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
+                  make_map(&tmB, B, M, K, ldb, P.bkm, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B),
+              SPT_E_UNSUPPORTED, "gemm_tn_acc(umma): cuTensorMapEncodeTiled failed");
+  static int sm_count = 0;
+  static bool attr = false;
+  if (!attr) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(k_gemm_tn_umma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)kSmemBudget);
+    attr = true;
+  }
+  // >= 8 chunks per CTA so that the atomics of the [N, K] partials stay a small fraction
+  int64_t grid = P.chunks / 8;
+  if (grid < 1) grid = 1;
+  if (grid > sm_count) grid = sm_count;
+  k_gemm_tn_umma<<<(unsigned)grid, kThreads, smem, stream>>>(tmA, tmB, P);
+  return check_launch("gemm_tn_acc(umma)");
 }
 
 }  // namespace umma
