@@ -196,6 +196,26 @@ int spt_graphnorm_bwd(const float* x, const float* dy,
                       float* dmean_scale /*[C]*/, void* ws, size_t ws_bytes,
                       void* stream);
 
+/* Graph-wise GroupNorm (src/nn/norm.py:141-237, mode='graph') and PyG
+ * LayerNorm(mode='graph') (= num_groups 1; the code default of
+ * src/nn/transformer.py:137): statistics per (graph, channel group) over
+ * nodes x group channels, y = weight * (x - mean) * rstd + bias.
+ * eps_outside != 0 reproduces PyG LayerNorm called without `batch`
+ * (x / (std + eps)); otherwise rstd = 1/sqrt(var + eps).
+ * Workspace: spt_graphnorm_workspace_bytes(B, C). */
+int spt_groupnorm_fwd(const float* x, const int64_t* batch /*nullable*/, int64_t N,
+                      int64_t C, int64_t B, int64_t num_groups,
+                      const float* weight /*nullable*/, const float* bias /*nullable*/,
+                      float eps, int eps_outside, float* y, float* mean /*[B,C]*/,
+                      float* rstd /*[B,C]*/, void* ws, size_t ws_bytes, void* stream);
+int spt_groupnorm_bwd(const float* x, const float* dy,
+                      const int64_t* batch /*nullable*/, int64_t N, int64_t C,
+                      int64_t B, int64_t num_groups, const float* weight /*nullable*/,
+                      const float* mean, const float* rstd, float eps, int eps_outside,
+                      float* dx, float* dweight /*[C], nullable*/,
+                      float* dbias /*[C], nullable*/, void* ws, size_t ws_bytes,
+                      void* stream);
+
 /* ------------------------------------------------------------------------- *
  *  Fused sparse graph attention core                                        *
  *  (src/nn/attention.py:202-315; src/nn/pool.py:196-233 for attentive pool)  *

@@ -148,6 +148,39 @@ def segment_cases(ref):
     return cases
 
 
+def norm_pool_cases(ref):
+    """GroupNorm (reference source), LayerNorm(mode='graph') (PyG leaf), StdPool"""
+    cases = {}
+    gen = torch.Generator().manual_seed(21)
+    N, C, B = 500, 32, 3
+    x = torch.randn(N, C, generator=gen) * 2 + 1.5
+    batch = torch.sort(torch.randint(0, B, (N,), generator=gen)).values
+    for name, mk, kw in (
+            ('groupnorm_g4', lambda: ref.GroupNorm(C, num_groups=4), dict(batch=batch)),
+            ('groupnorm_g1', lambda: ref.GroupNorm(C, num_groups=1), dict(batch=batch)),
+            ('groupnorm_g8_nobatch', lambda: ref.GroupNorm(C, num_groups=8), dict()),
+            ('layernorm_graph', lambda: ref.LayerNorm(C, mode='graph'), dict(batch=batch)),
+            ('layernorm_graph_nobatch', lambda: ref.LayerNorm(C, mode='graph'), dict())):
+        m = mk()
+        m.weight.data.normal_(1.0, 0.3, generator=gen)
+        m.bias.data.normal_(0.0, 0.3, generator=gen)
+        xin = x.clone()
+        outs, probe, grads, pgrads = _run(m, (xin,), kw, [xin], torch.Generator().manual_seed(8))
+        cases[name] = dict(x=x, batch=kw.get('batch'), weight=m.weight.detach().clone(),
+                           bias=m.bias.detach().clone(), out=outs[0], probe=probe, dx=grads[0],
+                           dparams=pgrads)
+    Nc, Np = 400, 50
+    idx = torch.randint(0, Np - 4, (Nc,), generator=gen)  # 4 empty parents
+    idx[:3] = Np - 5                                      # ... and a parent with 3 equal rows
+    xs = torch.randn(Nc, C, generator=gen)
+    xs[:3] = xs[0]
+    xin = xs.clone()
+    outs, probe, grads, _ = _run(ref.StdPool(), (xin, None, idx), dict(num_pool=Np), [xin],
+                                 torch.Generator().manual_seed(9))
+    cases['pool_std'] = dict(x=xs, index=idx, num_pool=Np, out=outs[0], probe=probe, dx=grads[0])
+    return cases
+
+
 SPT_CFG = dict(
     nano=True, segment_hf=['hf'], down_dim=[32, 32, 32],
     down_in_mlp=[[3 + 1 + 16, 32, 32], [3 + 1 + 16 + 32, 32, 32], [3 + 1 + 16 + 32, 32, 32]],
@@ -322,6 +355,7 @@ def main():
     torch.save(stage_cases(ref), os.path.join(OUT, 'stage.pt'))
     torch.save(spt_case(ref), os.path.join(OUT, 'spt_nano3.pt'))
     torch.save(edge_feature_case(ref), os.path.join(OUT, 'edge_features.pt'))
+    torch.save(norm_pool_cases(ref), os.path.join(OUT, 'norms.pt'))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
     return 0

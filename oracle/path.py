@@ -70,6 +70,33 @@ def norm_apply(sd, prefix, x, index):
     return F.layer_norm(x, (x.shape[1],), w, b, 1e-5)
 
 
+def group_norm(x, index, weight, bias, num_groups, eps=1e-5):
+    """GroupNorm.forward, mode='graph' (src/nn/norm.py:181-218): mean / variance over the
+    nodes of each graph x the channels of each group; eps inside the sqrt."""
+    if index is None:
+        index = torch.zeros(x.shape[0], dtype=torch.long)
+    B = int(index.max()) + 1
+    G = num_groups
+    xg = x.view(-1, G, x.shape[1] // G)
+    norm = (L.degree(index, B, dtype=x.dtype).clamp(min=1) * (x.shape[1] // G)).view(-1, 1, 1)
+    mean = L.scatter_sum(xg, index, 0, B).sum(dim=-1, keepdim=True) / norm
+    xc = xg - mean.index_select(0, index)
+    var = L.scatter_sum(xc * xc, index, 0, B).sum(dim=-1, keepdim=True) / norm
+    out = (xc / (var + eps).sqrt().index_select(0, index)).view(-1, x.shape[1])
+    if weight is not None:
+        out = out * weight + bias
+    return out
+
+
+def std_pool(x, index, num_pool):
+    """StdPool (src/nn/pool.py:81-82) -> PyG StdAggregation: biased std from two segment
+    means, clamp(min=1e-5).sqrt(), floor values zeroed."""
+    mean = L.scatter_mean(x, index, 0, num_pool)
+    mean2 = L.scatter_mean(x * x, index, 0, num_pool)
+    out = (mean2 - mean * mean).clamp(min=1e-5).sqrt()
+    return out.masked_fill(out <= (1e-5) ** 0.5, 0.0)
+
+
 def mlp(sd, prefix, x, batch=None, last_activation=True):
     """MLP.forward (src/nn/mlp.py:84-94) over the ModuleList built by mlp()
     (:8-57): [Linear(bias iff no norm), norm?, act?]*.  The layout is read back

@@ -51,6 +51,11 @@ SIGNATURES = {
     "spt_graphnorm_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr,
                                   c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_ptr, c_ptr, c_ptr,
                                   c_ptr, c_ptr, c_size, c_ptr]),
+    "spt_groupnorm_fwd": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_f32,
+                                  c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
+    "spt_groupnorm_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr,
+                                  c_ptr, c_ptr, c_f32, c_int, c_ptr, c_ptr, c_ptr, c_ptr,
+                                  c_size, c_ptr]),
     "spt_attn_fwd": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr,
                              c_ptr, c_i64, c_i64, c_int, c_int, c_int, c_int, c_ptr,
                              c_ptr, c_ptr, c_ptr, c_int, c_f32, c_ptr, c_ptr, c_ptr,

@@ -57,6 +57,23 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+// Explicit shared-space accesses.  Not only faster than generic LD/ST: LDS/STS travel through
+// the same in-order shared-memory pipe as the mbarrier arrive, which is what makes
+// "read the slot, then arrive on its `free` barrier" safe.  (A generic LD.E to a shared
+// address is NOT ordered with the arrive: the TMA refill raced the reads.)
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(saddr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)
                : "memory");
@@ -92,6 +109,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
   } while (!done);
+  // Every caller is a whole warp.  Lanes can leave the polling loop in different iterations;
+  // the .sync.aligned tcgen05 instructions and elect.sync that follow need the warp converged.
+  __syncwarp();
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1,
                                             uint64_t* bar) {
@@ -164,12 +184,13 @@ __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 // in place: raw -> hi; twin buffer: lo.  4 independent 16-byte chains per thread iteration.
-__device__ __forceinline__ void split_chunk(float4* hi, float4* lo, int n4, int t, int nt) {
+__device__ __forceinline__ void split_chunk(void* hi_, void* lo_, int n4, int t, int nt) {
+  const uint32_t hi = smem_u32(hi_), lo = smem_u32(lo_);
   for (int i0 = t; i0 < n4; i0 += 4 * nt) {
     float4 x[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      if (i0 + u * nt < n4) x[u] = hi[i0 + u * nt];
+      if (i0 + u * nt < n4) x[u] = lds128(hi + 16u * (uint32_t)(i0 + u * nt));
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (i0 + u * nt < n4) {
@@ -178,8 +199,8 @@ __device__ __forceinline__ void split_chunk(float4* hi, float4* lo, int n4, int 
         h.z = tf32_rna(x[u].z); h.w = tf32_rna(x[u].w);
         l.x = tf32_rna(x[u].x - h.x); l.y = tf32_rna(x[u].y - h.y);
         l.z = tf32_rna(x[u].z - h.z); l.w = tf32_rna(x[u].w - h.w);
-        hi[i0 + u * nt] = h;
-        lo[i0 + u * nt] = l;
+        sts128(hi + 16u * (uint32_t)(i0 + u * nt), h);
+        sts128(lo + 16u * (uint32_t)(i0 + u * nt), l);
       }
     }
   }
@@ -243,10 +264,10 @@ __device__ __forceinline__ void stage_slab(const uint32_t (&v)[32], unsigned cha
     o.z = __uint_as_float(v[4 * j + 2]);
     o.w = __uint_as_float(v[4 * j + 3]);
     if (bias_slab) {
-      const float4 bb = *(const float4*)(bias_slab + 4 * j);
+      const float4 bb = lds128(smem_u32(bias_slab + 4 * j));
       o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
     }
-    *(float4*)(buf + row * 128 + ((j ^ (row & 7)) << 4)) = o;
+    sts128(smem_u32(buf) + (uint32_t)(row * 128 + ((j ^ (row & 7)) << 4)), o);
   }
 }
 
@@ -319,12 +340,11 @@ __device__ __forceinline__ void epilogue_role(const Params& P, const CUtensorMap
           else tmem_ld32_nowait(tsrc + (cur + G) * kSlab, va);
         }
         unsigned char* buf = mybuf + (sc % nb) * kSlabBytes;
-        if (q == 0) {  // the store that last used `buf` has read it
-          if (elect_one()) {
-            if (nb == 2) bulk_wait_read<1>();
-            else bulk_wait_read<0>();
-          }
-          __syncwarp();
+        // bulk async-groups are per thread: the same lane must commit and wait, so a fixed
+        // lane (not elect.sync, whose choice is not specified to be stable) drives the store
+        if (q == 0 && lane == 0) {  // the store that last used `buf` has read it
+          if (nb == 2) bulk_wait_read<1>();
+          else bulk_wait_read<0>();
         }
         if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
         else asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -335,12 +355,9 @@ __device__ __forceinline__ void epilogue_role(const Params& P, const CUtensorMap
         if (tr && cur == 0) TRC(6, tl, 2);
         if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
         else asm volatile("bar.sync 2, 128;" ::: "memory");
-        if (q == 0) {
-          if (elect_one()) {
-            tma_store_2d(tmC, buf, n_blk * P.BN + cur * kSlab, m_blk * BM);
-            bulk_commit();
-          }
-          __syncwarp();
+        if (q == 0 && lane == 0) {
+          tma_store_2d(tmC, buf, n_blk * P.BN + cur * kSlab, m_blk * BM);
+          bulk_commit();
         }
         if (tr && cur == 0) TRC(6, tl, 3);
         ++sc;
@@ -351,10 +368,7 @@ __device__ __forceinline__ void epilogue_role(const Params& P, const CUtensorMap
     mbar_arrive(&tmem_empty[acc]);
     if (tr) TRC(5, tl, 2);
   }
-  if (q == 0) {
-    if (elect_one()) bulk_wait_read<0>();
-    __syncwarp();
-  }
+  if (q == 0 && lane == 0) bulk_wait_read<0>();
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -536,7 +550,7 @@ k_gemm_nt_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kc = 0; kc < KC; ++kc) {
         mbar_wait(&b_full[kc], 0, 6);
         unsigned char* bs = bbuf + (size_t)kc * 2 * b_bytes;
-        split_chunk((float4*)bs, (float4*)(bs + b_bytes), b_bytes / 16, ts + 128, 256);
+        split_chunk(bs, bs + b_bytes, b_bytes / 16, ts + 128, 256);
         fence_proxy_async();
         mbar_arrive(&b_ready[kc]);
         if (ts == 0) TRC(3, kc, 2);
@@ -553,7 +567,7 @@ k_gemm_nt_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&b_full[s], (it / P.b_slots) & 1, 6);
           if (ts == 0) TRC(3, it, 1);
           unsigned char* bs = bbuf + (size_t)s * 2 * b_bytes;
-          split_chunk((float4*)bs, (float4*)(bs + b_bytes), b_bytes / 16, ts, 128);
+          split_chunk(bs, bs + b_bytes, b_bytes / 16, ts, 128);
           fence_proxy_async();
           mbar_arrive(&b_ready[s]);
           if (ts == 0) TRC(3, it, 2);
@@ -571,10 +585,10 @@ k_gemm_nt_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (row == 0) TRC(2, it, 0);
         mbar_wait(&a_full[r], (it / P.ring) & 1, 4);
         if (row == 0) TRC(2, it, 1);
-        const unsigned char* arow = ringbuf + (size_t)r * kABytes + row * 128;
+        const uint32_t arow = smem_u32(ringbuf) + (uint32_t)r * kABytes + (uint32_t)row * 128u;
         float4 x[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = *(const float4*)(arow + ((j ^ (row & 7)) << 4));
+        for (int j = 0; j < 8; ++j) x[j] = lds128(arow + (uint32_t)((j ^ (row & 7)) << 4));
         uint32_t hi[32], lo[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -586,7 +600,6 @@ k_gemm_nt_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             lo[4 * j + c] = __float_as_uint(tf32_rna(xs[c] - h));
           }
         }
-        mbar_arrive(&a_free[r]);  // values are in registers: the slot can be refilled
         mbar_wait(&a_empty[s], ((it / P.a_stages) & 1) ^ 1, 5);  // previous MMAs retired
         tc_fence_after();
         if (row == 0) TRC(2, it, 2);
@@ -594,6 +607,10 @@ k_gemm_nt_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_st32(ta, hi);
         tmem_st32(ta + 32, lo);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        // Free the landing slot only now: the tcgen05.st above consumed the loaded values, so
+        // the slot reads have really completed (an arrive issued right behind the loads is
+        // not ordered with them in hardware and let the TMA refill race the reads).
+        mbar_arrive(&a_free[r]);
         tc_fence_before();
         mbar_arrive(&a_ready[s]);
         if (row == 0) TRC(2, it, 3);
@@ -605,7 +622,7 @@ k_gemm_nt_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kc = 0; kc < KC; ++kc) {
         mbar_wait(&b_full[kc], 0, 6);
         unsigned char* bs = bbuf + (size_t)kc * 2 * b_bytes;
-        split_chunk((float4*)bs, (float4*)(bs + b_bytes), b_bytes / 16, ts, 256);
+        split_chunk(bs, bs + b_bytes, b_bytes / 16, ts, 256);
         fence_proxy_async();
         mbar_arrive(&b_ready[kc]);
       }
@@ -950,25 +967,22 @@ k_gemm_tn_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int c = 0; c < nchunks; ++c) {
       mbar_wait(&full[s], ph, 2);
       unsigned char* st = smem + (size_t)s * stage_bytes;
-      float4* ahi = (float4*)st;
-      float4* alo = (float4*)(st + P.a_bytes);
+      const uint32_t ahi = smem_u32(st), alo = ahi + P.a_bytes;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int i = ts + 256 * u;
         if (i < nA4) {
-          const float4 x = ahi[i];
+          const float4 x = lds128(ahi + 16u * (uint32_t)i);
           float4 h, l;
           h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
           l.x = tf32_rna(x.x - h.x); l.y = tf32_rna(x.y - h.y);
           l.z = tf32_rna(x.z - h.z); l.w = tf32_rna(x.w - h.w);
-          ahi[i] = h;
-          alo[i] = l;
+          sts128(ahi + 16u * (uint32_t)i, h);
+          sts128(alo + 16u * (uint32_t)i, l);
           cs[u].x += x.x; cs[u].y += x.y; cs[u].z += x.z; cs[u].w += x.w;
         }
       }
-      float4* bhi = (float4*)(st + 2 * P.a_bytes);
-      float4* blo = (float4*)(st + 2 * P.a_bytes + P.b_bytes);
-      split_chunk(bhi, blo, nB4, ts, 256);
+      split_chunk(st + 2 * P.a_bytes, st + 2 * P.a_bytes + P.b_bytes, nB4, ts, 256);
       fence_proxy_async();
       mbar_arrive(&split[s]);
       if (++s == P.stages) { s = 0; ph ^= 1; }

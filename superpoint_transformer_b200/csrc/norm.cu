@@ -62,7 +62,7 @@ k_graphnorm_stats(const float* __restrict__ x, const float* __restrict__ dy,
       if (NACC == 2) a[NACC - 1][v] = 0.f;
       mu[v] = 0.f;
       rs[v] = 1.f;
-      ms[v] = (MODE != 0 && active) ? mean_scale[c0 + v] : 0.f;
+      ms[v] = (MODE != 0 && active) ? (mean_scale ? mean_scale[c0 + v] : 1.f) : 0.f;
     }
     int64_t cur = -1;
     int nrows = 0;
@@ -233,7 +233,7 @@ k_graphnorm_apply(const float* __restrict__ x, const int64_t* __restrict__ batch
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
       int64_t c = c0 + v;
-      float out = xv[v] - mean_scale[c] * mean[b * C + c];
+      float out = xv[v] - (mean_scale ? mean_scale[c] : 1.f) * mean[b * C + c];
       float w = weight ? weight[c] : 1.f;
       float bb = bias ? bias[c] : 0.f;
       float val = fmaf(w * out, rstd[b * C + c], bb);
@@ -325,7 +325,7 @@ k_graphnorm_bwd_apply(const float* __restrict__ x, const float* __restrict__ dy,
       for (int v = 0; v < VEC; ++v) {
         int64_t c = c0 + v;
         float rs = rstd[b * C + c];
-        float xhat = (xv[v] - mean_scale[c] * mean[b * C + c]) * rs;
+        float xhat = (xv[v] - (mean_scale ? mean_scale[c] : 1.f) * mean[b * C + c]) * rs;
         float w = weight ? weight[c] : 1.f;
         o[v] = w * rs * gv[v] - k2[b * C + c] * xhat - k3[b * C + c];
       }
@@ -359,6 +359,82 @@ __global__ void k_count_rows(const int64_t* __restrict__ batch, int64_t N, int64
     ++run;
   }
   if (cur >= 0) atomicAdd(&count[cur], (double)run);
+}
+
+// ---------------------------------------------------------------------------------------
+// Graph-wise GroupNorm / LayerNorm(mode='graph'): statistics per (graph b, channel group g)
+// over nodes x group channels (reference src/nn/norm.py:181-218; PyG LayerNorm 'graph' is
+// the num_groups = 1 case).  The N x C passes are the GraphNorm kernels above run with
+// mean_scale == 1; these [B, G]-sized kernels turn their per-channel sums into group values.
+// ---------------------------------------------------------------------------------------
+// sum_x[b, c] <- n_b * mean_{b, g(c)}  (so that the MODE 1 pass centres on the group mean)
+__global__ void k_groupnorm_mean(double* __restrict__ sum_x, const double* __restrict__ count,
+                                 int64_t B, int64_t C, int64_t G) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * G) return;
+  const int64_t b = t / G, g = t - b * G, gc = C / G;
+  const double n = fmax(count[b], 1.0);
+  double s = 0;
+  for (int64_t j = 0; j < gc; ++j) s += sum_x[b * C + g * gc + j];
+  const double m = s / (n * (double)gc);
+  for (int64_t j = 0; j < gc; ++j) sum_x[b * C + g * gc + j] = m * n;
+}
+
+__global__ void k_groupnorm_finalize(const double* __restrict__ sum_x /* n * mean */,
+                                     const double* __restrict__ sum_sq,
+                                     const double* __restrict__ count, int64_t B, int64_t C,
+                                     int64_t G, float eps, int eps_outside,
+                                     float* __restrict__ mean, float* __restrict__ rstd) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * G) return;
+  const int64_t b = t / G, g = t - b * G, gc = C / G;
+  const double n = fmax(count[b], 1.0);
+  double s = 0;
+  for (int64_t j = 0; j < gc; ++j) s += sum_sq[b * C + g * gc + j];
+  const float var = (float)(s / (n * (double)gc));
+  // PyG LayerNorm without `batch`: x / (std + eps); everything else: x / sqrt(var + eps)
+  const float rs = eps_outside ? 1.f / (sqrtf(var) + eps) : 1.f / sqrtf(var + eps);
+  for (int64_t j = 0; j < gc; ++j) {
+    mean[b * C + g * gc + j] = (float)(sum_x[b * C + g * gc + j] / n);
+    rstd[b * C + g * gc + j] = rs;
+  }
+}
+
+// dx_i = w rs dy_i - k2 xhat_i - k3 with group-wide k2 = f * mean_g(w dy xhat),
+// k3 = rs * mean_g(w dy); f = rs (eps inside the sqrt) or 1/std (eps outside)
+__global__ void k_groupnorm_bwd_coef(const double* __restrict__ s1, const double* __restrict__ s2,
+                                     const double* __restrict__ count, int64_t B, int64_t C,
+                                     int64_t G, const float* __restrict__ weight,
+                                     const float* __restrict__ rstd, float eps, int eps_outside,
+                                     float* __restrict__ k2, float* __restrict__ k3,
+                                     float* __restrict__ dweight, float* __restrict__ dbias) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < B * G) {
+    const int64_t b = t / G, g = t - b * G, gc = C / G;
+    const double n = fmax(count[b], 1.0) * (double)gc;
+    double a1 = 0, a2 = 0;
+    for (int64_t j = 0; j < gc; ++j) {
+      const int64_t c = g * gc + j;
+      const double w = weight ? (double)weight[c] : 1.0;
+      a1 += w * s1[b * C + c];
+      a2 += w * s2[b * C + c];
+    }
+    const double rs = rstd[b * C + g * gc];
+    const double f = eps_outside ? 1.0 / fmax(1.0 / rs - (double)eps, 1e-30) : rs;
+    for (int64_t j = 0; j < gc; ++j) {
+      k2[b * C + g * gc + j] = (float)(f * a1 / n);
+      k3[b * C + g * gc + j] = (float)(rs * a2 / n);
+    }
+  }
+  if (t < C) {
+    double dw = 0, db = 0;
+    for (int64_t b = 0; b < B; ++b) {
+      dw += s1[b * C + t];
+      db += s2[b * C + t];
+    }
+    if (dweight) dweight[t] = (float)dw;
+    if (dbias) dbias[t] = (float)db;
+  }
 }
 
 static inline ColMap col_map(int64_t C, int vec) {
@@ -513,6 +589,115 @@ int spt_graphnorm_bwd(const float* x, const float* dy, const int64_t* batch, int
           dx);
   }
   return check_launch("graphnorm_bwd");
+}
+
+int spt_groupnorm_fwd(const float* x, const int64_t* batch, int64_t N, int64_t C, int64_t B,
+                      int64_t num_groups, const float* weight, const float* bias, float eps,
+                      int eps_outside, float* y, float* mean, float* rstd, void* ws,
+                      size_t ws_bytes, void* stream_) {
+  SPT_REQUIRE(N >= 0 && C > 0 && B > 0 && num_groups > 0 && C % num_groups == 0, SPT_E_INVALID,
+              "groupnorm_fwd: bad sizes");
+  SPT_REQUIRE(mean && rstd && ws && (N == 0 || (x && y)), SPT_E_INVALID,
+              "groupnorm_fwd: null pointer");
+  SPT_REQUIRE(ws_bytes >= spt_graphnorm_workspace_bytes(B, C), SPT_E_WORKSPACE,
+              "groupnorm_fwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream_;
+  NormWs w = carve(ws, B, C);
+  cudaError_t ce = cudaMemsetAsync(ws, 0, w.zero_bytes, st);
+  if (ce != cudaSuccess) {
+    set_error("groupnorm_fwd memset: %s", cudaGetErrorString(ce));
+    return (int)ce;
+  }
+  const int64_t G = num_groups;
+  int vec = (C % 4 == 0) ? 4 : 1;
+  ColMap cm = col_map(C, vec);
+  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, kNormRows), 148 * 4);
+  int64_t total = N * (C / vec);
+  int agrid = (int)imin(ceil_div(total > 0 ? total : 1, kNormThreads), 148 * 16);
+  const unsigned ggrid = (unsigned)ceil_div(B * G, 128);
+  if (N > 0) {
+    if (vec == 4)
+      k_graphnorm_stats<0, 4><<<slabs, kNormThreads, 0, st>>>(
+          x, nullptr, nullptr, 1.f, batch, N, C, B, nullptr, nullptr, nullptr, nullptr, nullptr,
+          w.acc0, nullptr, w.count, cm.tx, cm.ty);
+    else
+      k_graphnorm_stats<0, 1><<<slabs, kNormThreads, 0, st>>>(
+          x, nullptr, nullptr, 1.f, batch, N, C, B, nullptr, nullptr, nullptr, nullptr, nullptr,
+          w.acc0, nullptr, w.count, cm.tx, cm.ty);
+  }
+  k_groupnorm_mean<<<ggrid, 128, 0, st>>>(w.acc0, w.count, B, C, G);
+  if (N > 0) {
+    if (vec == 4)
+      k_graphnorm_stats<1, 4><<<slabs, kNormThreads, 0, st>>>(
+          x, nullptr, nullptr, 1.f, batch, N, C, B, nullptr, w.acc0, w.count, nullptr, nullptr,
+          w.acc1, nullptr, nullptr, cm.tx, cm.ty);
+    else
+      k_graphnorm_stats<1, 1><<<slabs, kNormThreads, 0, st>>>(
+          x, nullptr, nullptr, 1.f, batch, N, C, B, nullptr, w.acc0, w.count, nullptr, nullptr,
+          w.acc1, nullptr, nullptr, cm.tx, cm.ty);
+  }
+  k_groupnorm_finalize<<<ggrid, 128, 0, st>>>(w.acc0, w.acc1, w.count, B, C, G, eps, eps_outside,
+                                              mean, rstd);
+  if (N > 0) {
+    if (vec == 4)
+      k_graphnorm_apply<4><<<agrid, kNormThreads, 0, st>>>(x, batch, N, C, B, weight, bias,
+                                                          nullptr, mean, rstd, 1.f, y);
+    else
+      k_graphnorm_apply<1><<<agrid, kNormThreads, 0, st>>>(x, batch, N, C, B, weight, bias,
+                                                          nullptr, mean, rstd, 1.f, y);
+  }
+  return check_launch("groupnorm_fwd");
+}
+
+int spt_groupnorm_bwd(const float* x, const float* dy, const int64_t* batch, int64_t N,
+                      int64_t C, int64_t B, int64_t num_groups, const float* weight,
+                      const float* mean, const float* rstd, float eps, int eps_outside,
+                      float* dx, float* dweight, float* dbias, void* ws, size_t ws_bytes,
+                      void* stream_) {
+  SPT_REQUIRE(N >= 0 && C > 0 && B > 0 && num_groups > 0 && C % num_groups == 0, SPT_E_INVALID,
+              "groupnorm_bwd: bad sizes");
+  SPT_REQUIRE(mean && rstd && ws && (N == 0 || (x && dy && dx)), SPT_E_INVALID,
+              "groupnorm_bwd: null pointer");
+  SPT_REQUIRE(ws_bytes >= spt_graphnorm_workspace_bytes(B, C), SPT_E_WORKSPACE,
+              "groupnorm_bwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream_;
+  NormWs w = carve(ws, B, C);
+  cudaError_t ce = cudaMemsetAsync(ws, 0, w.zero_bytes, st);
+  if (ce != cudaSuccess) {
+    set_error("groupnorm_bwd memset: %s", cudaGetErrorString(ce));
+    return (int)ce;
+  }
+  const int64_t G = num_groups;
+  int vec = (C % 4 == 0) ? 4 : 1;
+  ColMap cm = col_map(C, vec);
+  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, kNormRows), 148 * 4);
+  int64_t total = N * (C / vec);
+  int agrid = (int)imin(ceil_div(total > 0 ? total : 1, kNormThreads), 148 * 16);
+  if (N > 0) {
+    if (vec == 4)
+      k_graphnorm_stats<2, 4><<<slabs, kNormThreads, 0, st>>>(
+          x, dy, nullptr, 1.f, batch, N, C, B, nullptr, nullptr, nullptr, mean, rstd, w.acc0,
+          w.acc1, nullptr, cm.tx, cm.ty);
+    else
+      k_graphnorm_stats<2, 1><<<slabs, kNormThreads, 0, st>>>(
+          x, dy, nullptr, 1.f, batch, N, C, B, nullptr, nullptr, nullptr, mean, rstd, w.acc0,
+          w.acc1, nullptr, cm.tx, cm.ty);
+    k_count_rows<<<(unsigned)imin(ceil_div(N, 256 * 64), 148 * 8), 256, 0, st>>>(
+        batch, N, B, w.count);
+  }
+  const int64_t work = B * G > C ? B * G : C;
+  k_groupnorm_bwd_coef<<<(unsigned)ceil_div(work, 128), 128, 0, st>>>(
+      w.acc0, w.acc1, w.count, B, C, G, weight, rstd, eps, eps_outside, w.k2, w.k3, dweight,
+      dbias);
+  if (N > 0) {
+    if (vec == 4)
+      k_graphnorm_bwd_apply<4><<<agrid, kNormThreads, 0, st>>>(
+          x, dy, batch, N, C, B, weight, nullptr, mean, rstd, w.k2, w.k3, nullptr, 1.f, dx);
+    else
+      k_graphnorm_bwd_apply<1><<<agrid, kNormThreads, 0, st>>>(
+          x, dy, batch, N, C, B, weight, nullptr, mean, rstd, w.k2, w.k3, nullptr, 1.f, dx);
+  }
+  return check_launch("groupnorm_bwd");
 }
 
 }  // extern "C"

@@ -11,7 +11,7 @@ from torch import nn
 
 from .. import ops
 
-__all__ = ['BatchNorm', 'UnitSphereNorm', 'GraphNorm', 'LayerNorm',
+__all__ = ['BatchNorm', 'UnitSphereNorm', 'GraphNorm', 'LayerNorm', 'GroupNorm',
            'INDEX_BASED_NORMS']
 
 
@@ -78,16 +78,15 @@ class GraphNorm(nn.Module):
 
 
 class LayerNorm(nn.Module):
-    """Per-node LayerNorm (mode='node'; dense torch op).  The graph-wise mode of
-    PyG's LayerNorm (code default of reference src/nn/transformer.py:137, never
-    selected by the shipped configs) is not built yet and raises."""
+    """torch_geometric.nn.norm.LayerNorm: `mode='graph'` (its default, and the code
+    default of reference src/nn/transformer.py:137) normalises over all nodes and
+    channels of each graph with the segment kernels of csrc/norm.cu; `mode='node'` is
+    the dense per-node torch op."""
 
-    def __init__(self, in_channels, eps=1e-5, affine=True, mode='node'):
+    def __init__(self, in_channels, eps=1e-5, affine=True, mode='graph'):
         super().__init__()
-        if mode != 'node':
-            raise NotImplementedError(
-                "LayerNorm(mode='graph') is not implemented in the B200 path yet; "
-                "the shipped configs use GraphNorm")
+        if mode not in ('graph', 'node'):
+            raise ValueError(f"Unknown normalization mode: {mode}")
         self.in_channels = in_channels
         self.eps = eps
         self.mode = mode
@@ -99,8 +98,49 @@ class LayerNorm(nn.Module):
             self.register_parameter('bias', None)
 
     def forward(self, x, batch=None, batch_size=None):
+        if self.mode == 'graph':
+            # PyG puts eps outside the sqrt when no `batch` is given (x / (std + eps))
+            return ops.group_norm(x, self.weight, self.bias, batch=batch, batch_size=batch_size,
+                                  num_groups=1, eps=self.eps, eps_outside=batch is None)
         return torch.nn.functional.layer_norm(
             x, (self.in_channels,), self.weight, self.bias, self.eps)
 
+    def __repr__(self):
+        return f'{self.__class__.__name__}({self.in_channels}, mode={self.mode})'
 
-INDEX_BASED_NORMS = (LayerNorm, GraphNorm)
+
+class GroupNorm(nn.Module):
+    """Group normalisation on graphs (reference src/nn/norm.py:141-237): `mode='graph'`
+    takes mean/variance over the nodes of each graph x the channels of each group."""
+
+    def __init__(self, in_channels, num_groups=4, eps=1e-5, affine=True, mode='graph'):
+        super().__init__()
+        assert in_channels % num_groups == 0, \
+            "`in_channels` must be a multiple of `num_groups`"
+        self.in_channels = in_channels
+        self.num_groups = num_groups
+        self.group_channels = in_channels // num_groups
+        self.eps = eps
+        self.mode = mode
+        if affine:
+            self.weight = nn.Parameter(torch.ones(in_channels))
+            self.bias = nn.Parameter(torch.zeros(in_channels))
+        else:
+            self.register_parameter('weight', None)
+            self.register_parameter('bias', None)
+
+    def forward(self, x, batch=None, batch_size=None):
+        if self.mode == 'graph':
+            return ops.group_norm(x, self.weight, self.bias, batch=batch, batch_size=batch_size,
+                                  num_groups=self.num_groups, eps=self.eps)
+        if self.mode == 'node' and batch is None:
+            return nn.functional.group_norm(x, self.num_groups, weight=self.weight,
+                                            bias=self.bias, eps=self.eps)
+        raise ValueError(f"Unknown normalization mode: {self.mode}")
+
+    def __repr__(self):
+        return (f'{self.__class__.__name__}(in_channels={self.in_channels}, '
+                f'num_groups={self.num_groups}, mode={self.mode})')
+
+
+INDEX_BASED_NORMS = (LayerNorm, GraphNorm, GroupNorm)

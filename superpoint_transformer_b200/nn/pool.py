@@ -13,7 +13,7 @@ from .linear import Linear
 from .. import ops
 from ..utils.nn import build_qk_scale, LearnableParameter
 
-__all__ = ['pool_factory', 'SumPool', 'MeanPool', 'MaxPool', 'MinPool',
+__all__ = ['pool_factory', 'SumPool', 'MeanPool', 'MaxPool', 'MinPool', 'StdPool',
            'AttentivePool', 'AttentivePoolWithLearntQueries', 'BaseAttentivePool',
            'AggregationPoolMixIn']
 
@@ -45,6 +45,21 @@ class MaxPool(_SegmentPool):
 
 class MinPool(_SegmentPool):
     _reduce = 'min'
+
+
+class StdPool(AggregationPoolMixIn, nn.Module):
+    """PyG StdAggregation as used by reference src/nn/pool.py:81-82: biased std from two
+    segment means, `sqrt(clamp(E[x^2] - E[x]^2, 1e-5))`, values at the clamp floor set
+    to 0.  Both segment reductions run on the CSR pool kernel (csrc/segment.cu)."""
+    _reduce = 'std'
+
+    def forward(self, x_child, x_parent, index, edge_attr=None, num_pool=None):
+        if num_pool is None:
+            num_pool = ops.num_segments(index)
+        mean = ops.segment_pool(x_child, index, num_pool, reduce='mean')
+        mean2 = ops.segment_pool(x_child * x_child, index, num_pool, reduce='mean')
+        out = (mean2 - mean * mean).clamp(min=1e-5).sqrt()
+        return out.masked_fill(out <= (1e-5) ** 0.5, 0.0)
 
 
 class BaseAttentivePool(nn.Module):
@@ -158,10 +173,8 @@ def pool_factory(pool, *args, **kwargs):
     """String / module -> pool module (reference src/nn/pool.py:24-41)."""
     if isinstance(pool, (AggregationPoolMixIn, BaseAttentivePool)):
         return pool
-    table = {'max': MaxPool, 'min': MinPool, 'mean': MeanPool, 'sum': SumPool}
+    table = {'max': MaxPool, 'min': MinPool, 'mean': MeanPool, 'sum': SumPool, 'std': StdPool}
     if isinstance(pool, str):
-        if pool == 'std':
-            raise NotImplementedError("'std' pooling is not built in the B200 path yet")
         if pool in table:
             return table[pool]()
     return pool(*args, **kwargs)

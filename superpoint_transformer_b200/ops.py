@@ -556,6 +556,66 @@ class _GraphNorm(torch.autograd.Function):
         return dx, dw, db, dms, None, None, None, None
 
 
+class _GroupNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, batch, B, G, eps, eps_outside):
+        lib = _lib.load()
+        N, C = x.shape
+        dev = x.device
+        y = torch.empty_like(x)
+        mean = torch.empty((B, C), dtype=torch.float32, device=dev)
+        rstd = torch.empty((B, C), dtype=torch.float32, device=dev)
+        nbytes = lib.spt_graphnorm_workspace_bytes(B, C)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.spt_groupnorm_fwd(_p(x), _p(batch), N, C, B, G, _p(weight), _p(bias),
+                                             eps, eps_outside, _p(y), _p(mean), _p(rstd),
+                                             _p(ws), nbytes, _stream()), "spt_groupnorm_fwd")
+        _count(6)
+        ctx.cfg = (B, G, eps, eps_outside, batch is not None, weight is not None)
+        ctx.save_for_backward(x, weight if weight is not None else mean, mean, rstd,
+                              batch if batch is not None else mean)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, mean, rstd, batch = ctx.saved_tensors
+        B, G, eps, eps_outside, has_batch, affine = ctx.cfg
+        if not has_batch:
+            batch = None
+        if not affine:
+            weight = None
+        lib = _lib.load()
+        dy = _f32c(dy)
+        N, C = x.shape
+        dev = x.device
+        dx = torch.empty_like(x)
+        dw = torch.empty(C, dtype=torch.float32, device=dev) if affine else None
+        db = torch.empty(C, dtype=torch.float32, device=dev) if affine else None
+        nbytes = lib.spt_graphnorm_workspace_bytes(B, C)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.spt_groupnorm_bwd(_p(x), _p(dy), _p(batch), N, C, B, G, _p(weight),
+                                             _p(mean), _p(rstd), eps, eps_outside, _p(dx),
+                                             _p(dw), _p(db), _p(ws), nbytes, _stream()),
+                       "spt_groupnorm_bwd")
+        _count(4)
+        return dx, dw, db, None, None, None, None, None
+
+
+def group_norm(x, weight=None, bias=None, batch=None, batch_size=None, num_groups=1, eps=1e-5,
+               eps_outside=False):
+    """Graph-wise GroupNorm (reference src/nn/norm.py:181-218); `num_groups=1` is PyG
+    LayerNorm(mode='graph').  `eps_outside` = PyG LayerNorm called without `batch`."""
+    _require_cuda(x, weight, bias, batch)
+    batch = _i64c(batch)
+    B = int(batch_size) if batch_size is not None else num_segments(batch)
+    assert (weight is None) == (bias is None), "affine needs both weight and bias"
+    return _GroupNorm.apply(_f32c(x), None if weight is None else _f32c(weight),
+                            None if bias is None else _f32c(bias), batch, B, int(num_groups),
+                            float(eps), int(bool(eps_outside)))
+
+
 def graph_norm(x, weight, bias, mean_scale, batch=None, batch_size=None, eps=1e-5,
                act_slope=1.0):
     """PyG GraphNorm semantics; `act_slope != 1` fuses the

@@ -168,3 +168,33 @@ def test_vertical_edge_features(golden):
                                    v['super_index'])
     torch.testing.assert_close(out, v['v_edge_attr'], atol=0, rtol=0)
     assert out.shape[1] == 9 and not torch.isnan(out).any()
+
+
+@pytest.mark.parametrize('name,groups', [('groupnorm_g4', 4), ('groupnorm_g1', 1),
+                                         ('groupnorm_g8_nobatch', 8)])
+def test_group_norm(golden, name, groups):
+    """oracle restatement of GroupNorm(mode='graph') vs the reference source run here"""
+    c = golden('norms.pt')[name]
+    x, w, b = _req(c['x'], c['weight'], c['bias'])
+    out = P.group_norm(x, c['batch'], w, b, groups)
+    torch.testing.assert_close(out, c['out'], atol=1e-5, rtol=1e-5)
+    (out * c['probe']).sum().backward()
+    torch.testing.assert_close(x.grad, c['dx'], atol=1e-5, rtol=1e-4)
+    torch.testing.assert_close(w.grad, c['dparams']['weight'], atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(b.grad, c['dparams']['bias'], atol=1e-4, rtol=1e-4)
+
+
+def test_layer_norm_graph_is_group_norm_1(golden):
+    """PyG LayerNorm(mode='graph') with a batch vector == GroupNorm(num_groups=1)"""
+    c = golden('norms.pt')['layernorm_graph']
+    out = P.group_norm(c['x'], c['batch'], c['weight'], c['bias'], 1)
+    torch.testing.assert_close(out, c['out'], atol=1e-5, rtol=1e-5)
+
+
+def test_std_pool(golden):
+    c = golden('norms.pt')['pool_std']
+    (x,) = _req(c['x'])
+    out = P.std_pool(x, c['index'], c['num_pool'])
+    torch.testing.assert_close(out, c['out'], atol=1e-6, rtol=1e-5)
+    (out * c['probe']).sum().backward()
+    torch.testing.assert_close(x.grad, c['dx'], atol=1e-6, rtol=1e-4)
