@@ -418,7 +418,7 @@ def run_own(args):
                        "l2": "inputs_exceed_l2 (per-step working set > 126 MB; no flush needed)",
                        "cuda_graph": {"value": graph_mode, "e2e": e2e_graph,
                                       "eager_ms_per_step": round(ms_eager_step, 4)},
-                       "matmul": "fp32-accurate 3xTF32 on tensor cores (csrc/gemm.cu)",
+                       "matmul": "fp32-accurate 3xTF32 on tcgen05 tensor cores, TMEM accumulators, TMA (csrc/gemm_umma.cu)",
                        "csr": "graph CSR cached across steps in `value` (amortised, SURVEY §8d); "
                               "rebuilt every step in `e2e`"},
             "clocks": clocks,
