@@ -465,6 +465,15 @@ static int check_shape(const char* who, int H, int D, int Dv, int F, AttnShape* 
 
 }  // namespace spt
 
+namespace spt {
+namespace umma {  // csrc/gemm_umma.cu
+bool tn_shape_ok(const float* A, int64_t M, int64_t N, int64_t lda, const float* B, int64_t K,
+                 int64_t ldb);
+int tn_launch(const float* A, int64_t M, int64_t N, int64_t lda, const float* B, int64_t K,
+              int64_t ldb, float* C, int64_t ldc, float* colsum, cudaStream_t stream);
+}  // namespace umma
+}  // namespace spt
+
 using namespace spt;
 
 extern "C" {
@@ -561,6 +570,15 @@ int spt_attn_bwd_rows(const float* q, int64_t ldq, const float* k, int64_t ldk,
     int rc2 = check_launch("attn_bwd_rows(fast)");
     if (rc2 != SPT_OK) return rc2;
     if (E > 0 && ((Wq && (dWq || dbq)) || (Wk && (dWk || dbk)))) {
+      // d[Wq;Wk] = G^T a, d[bq;bk] = colsum(G): a [E,32]^T [E,32] product.  When the caller
+      // hands the four gradients as one contiguous [2HD, F] / [2HD] pair it runs on the
+      // tcgen05 gemm_tn kernel (block-diagonal row-group batching, csrc/gemm_umma.cu).
+      const bool packed = Wq && Wk && dWq && dWk && dWk == dWq + fast::kHD * fast::kF &&
+                          ((!dbq && !dbk) || (bq && bk && dbq && dbk && dbk == dbq + fast::kHD));
+      if (packed && E >= 2048 &&
+          umma::tn_shape_ok(G, E, 2 * fast::kHD, 2 * fast::kHD, a, fast::kF, fast::kF))
+        return umma::tn_launch(G, E, 2 * fast::kHD, 2 * fast::kHD, a, fast::kF, fast::kF, dWq,
+                               fast::kF, dbq, st);
       fast::DwArgs W;
       W.G = G; W.a = a; W.E = E;
       W.dWq = Wq ? dWq : nullptr; W.dbq = (Wq && bq) ? dbq : nullptr;

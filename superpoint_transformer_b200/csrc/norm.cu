@@ -117,7 +117,7 @@ k_graphnorm_stats(const float* __restrict__ x, const float* __restrict__ dy,
               atomicAdd(&acc0[cur * C + c0 + v], (double)a[0][v]);
               if (NACC == 2) atomicAdd(&acc1[cur * C + c0 + v], (double)a[NACC - 1][v]);
             }
-            if (MODE == 0 && c0 == 0) atomicAdd(&cnt_out[cur], (double)nrows);
+            if (MODE != 1 && cnt_out && c0 == 0) atomicAdd(&cnt_out[cur], (double)nrows);
           }
 #pragma unroll
           for (int v = 0; v < VEC; ++v) {
@@ -177,7 +177,7 @@ k_graphnorm_stats(const float* __restrict__ x, const float* __restrict__ dy,
           atomicAdd(&acc0[first_b * C + c0 + v], (double)s0);
           if (NACC == 2) atomicAdd(&acc1[first_b * C + c0 + v], (double)s1);
         }
-        if (MODE == 0 && c0 == 0) atomicAdd(&cnt_out[first_b], (double)rows_seen);
+        if (MODE != 1 && cnt_out && c0 == 0) atomicAdd(&cnt_out[first_b], (double)rows_seen);
       }
       __syncthreads();
     } else if (active && cur >= 0) {
@@ -186,7 +186,7 @@ k_graphnorm_stats(const float* __restrict__ x, const float* __restrict__ dy,
         atomicAdd(&acc0[cur * C + c0 + v], (double)a[0][v]);
         if (NACC == 2) atomicAdd(&acc1[cur * C + c0 + v], (double)a[NACC - 1][v]);
       }
-      if (MODE == 0 && c0 == 0) atomicAdd(&cnt_out[cur], (double)nrows);
+      if (MODE != 1 && cnt_out && c0 == 0) atomicAdd(&cnt_out[cur], (double)nrows);
     }
   }
 }
@@ -338,28 +338,6 @@ k_graphnorm_bwd_apply(const float* __restrict__ x, const float* __restrict__ dy,
   }
 }
 
-// rows per segment (fp64 counter so it shares the workspace layout)
-__global__ void k_count_rows(const int64_t* __restrict__ batch, int64_t N, int64_t B,
-                             double* __restrict__ count) {
-  // per-thread run-length compression: consecutive rows usually share a segment
-  int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-  int64_t per = (N + nthreads - 1) / nthreads;
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t r0 = t * per, r1 = min(r0 + per, N);
-  int64_t cur = -1;
-  int64_t run = 0;
-  for (int64_t r = r0; r < r1; ++r) {
-    int64_t b = batch ? batch[r] : 0;
-    if (b < 0 || b >= B) continue;
-    if (b != cur) {
-      if (cur >= 0) atomicAdd(&count[cur], (double)run);
-      cur = b;
-      run = 0;
-    }
-    ++run;
-  }
-  if (cur >= 0) atomicAdd(&count[cur], (double)run);
-}
 
 // ---------------------------------------------------------------------------------------
 // Graph-wise GroupNorm / LayerNorm(mode='graph'): statistics per (graph b, channel group g)
@@ -567,13 +545,11 @@ int spt_graphnorm_bwd(const float* x, const float* dy, const int64_t* batch, int
     if (vec == 4)
       k_graphnorm_stats<2, 4><<<slabs, kNormThreads, 0, st>>>(
           x, dy, yact, act_slope, batch, N, C, B, mean_scale, nullptr, nullptr, mean, rstd, w.acc0,
-          w.acc1, nullptr, cm.tx, cm.ty);
+          w.acc1, w.count, cm.tx, cm.ty);   // also counts the rows per graph
     else
       k_graphnorm_stats<2, 1><<<slabs, kNormThreads, 0, st>>>(
           x, dy, yact, act_slope, batch, N, C, B, mean_scale, nullptr, nullptr, mean, rstd, w.acc0,
-          w.acc1, nullptr, cm.tx, cm.ty);
-    k_count_rows<<<(unsigned)imin(ceil_div(N, 256 * 64), 148 * 8), 256, 0, st>>>(
-        batch, N, B, w.count);
+          w.acc1, w.count, cm.tx, cm.ty);
   }
   k_graphnorm_bwd_coef<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(
       w.acc0, w.acc1, w.count, B, C, weight, mean_scale, mean, rstd, w.k2, w.k3, dweight,
@@ -677,13 +653,11 @@ int spt_groupnorm_bwd(const float* x, const float* dy, const int64_t* batch, int
     if (vec == 4)
       k_graphnorm_stats<2, 4><<<slabs, kNormThreads, 0, st>>>(
           x, dy, nullptr, 1.f, batch, N, C, B, nullptr, nullptr, nullptr, mean, rstd, w.acc0,
-          w.acc1, nullptr, cm.tx, cm.ty);
+          w.acc1, w.count, cm.tx, cm.ty);
     else
       k_graphnorm_stats<2, 1><<<slabs, kNormThreads, 0, st>>>(
           x, dy, nullptr, 1.f, batch, N, C, B, nullptr, nullptr, nullptr, mean, rstd, w.acc0,
-          w.acc1, nullptr, cm.tx, cm.ty);
-    k_count_rows<<<(unsigned)imin(ceil_div(N, 256 * 64), 148 * 8), 256, 0, st>>>(
-        batch, N, B, w.count);
+          w.acc1, w.count, cm.tx, cm.ty);
   }
   const int64_t work = B * G > C ? B * G : C;
   k_groupnorm_bwd_coef<<<(unsigned)ceil_div(work, 128), 128, 0, st>>>(

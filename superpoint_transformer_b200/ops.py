@@ -552,7 +552,7 @@ class _GraphNorm(torch.autograd.Function):
                                              _p(mean_scale), _p(mean), _p(rstd), _p(yact),
                                              ctx.act_slope, _p(dx), _p(dw), _p(db), _p(dms),
                                              _p(ws), nbytes, _stream()), "spt_graphnorm_bwd")
-        _count(4)
+        _count(3)
         return dx, dw, db, dms, None, None, None, None
 
 
@@ -599,7 +599,7 @@ class _GroupNorm(torch.autograd.Function):
                                              _p(mean), _p(rstd), eps, eps_outside, _p(dx),
                                              _p(dw), _p(db), _p(ws), nbytes, _stream()),
                        "spt_groupnorm_bwd")
-        _count(4)
+        _count(3)
         return dx, dw, db, None, None, None, None, None
 
 
@@ -718,10 +718,22 @@ class _AttnCore(torch.autograd.Function):
             lddq, lddk, lddv = ldq, ldk, ldv
         need = ctx.needs_input_grad
         da = torch.empty_like(a) if (a is not None and need[2]) else None
-        dWq = torch.zeros_like(Wq) if (Wq is not None and a is not None) else None
-        dbq = torch.zeros_like(bq) if (bq is not None and dWq is not None) else None
-        dWk = torch.zeros_like(Wk) if (Wk is not None and a is not None) else None
-        dbk = torch.zeros_like(bk) if (bk is not None and dWk is not None) else None
+        if (a is not None and Wq is not None and Wk is not None and Wq.shape == Wk.shape
+                and (bq is None) == (bk is None)):
+            # one contiguous [2HD, F] / [2HD] pair: lets the library run d[Wq;Wk] = G^T a as a
+            # single tensor-core gemm_tn
+            dW2 = torch.zeros((2 * Wq.shape[0], Wq.shape[1]), dtype=torch.float32, device=dev)
+            dWq, dWk = dW2[:Wq.shape[0]], dW2[Wq.shape[0]:]
+            if bq is not None:
+                db2 = torch.zeros(2 * Wq.shape[0], dtype=torch.float32, device=dev)
+                dbq, dbk = db2[:Wq.shape[0]], db2[Wq.shape[0]:]
+            else:
+                dbq = dbk = None
+        else:
+            dWq = torch.zeros_like(Wq) if (Wq is not None and a is not None) else None
+            dbq = torch.zeros_like(bq) if (bq is not None and dWq is not None) else None
+            dWk = torch.zeros_like(Wk) if (Wk is not None and a is not None) else None
+            dbk = torch.zeros_like(bk) if (bk is not None and dWk is not None) else None
         E = g.E
         Pb = torch.empty((max(E, 1), H), dtype=torch.float32, device=dev)
         G = torch.empty((max(E, 1), 2 * HD), dtype=torch.float32, device=dev)
