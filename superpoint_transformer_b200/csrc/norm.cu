@@ -28,6 +28,10 @@ struct ColMap {
 //   MODE 0: acc0 += x                         (+ row count)
 //   MODE 1: acc0 += (x - mean_scale*mean)^2
 //   MODE 2: acc0 += dy*xhat ; acc1 += dy      (backward)
+//   MODE 3: acc0 += d ; acc1 += d*d, d = x - pivot[c]   (single-pass forward statistics:
+//           `mean_scale` carries the per-channel pivot, a sample mean of the first rows, so
+//           the fp32 partial sums hold O(sigma) quantities and the shifted-moment algebra of
+//           the finalise kernel has nothing to cancel)
 // Thread (cx, ry) owns VEC columns and every ty-th row of the slab.  When the
 // whole slab belongs to one segment (the common case: `batch` sorted, slabs much
 // smaller than graphs) the ty row-lanes are reduced through shared memory and only
@@ -43,7 +47,7 @@ k_graphnorm_stats(const float* __restrict__ x, const float* __restrict__ dy,
                   const float* __restrict__ mean, const float* __restrict__ rstd,
                   double* __restrict__ acc0 /*[B,C]*/, double* __restrict__ acc1 /*[B,C]*/,
                   double* __restrict__ cnt_out /*[B]*/, int tx, int ty) {
-  constexpr int NACC = (MODE == 2) ? 2 : 1;
+  constexpr int NACC = (MODE >= 2) ? 2 : 1;
   __shared__ float red[NACC][kNormThreads * VEC];
   int cx = threadIdx.x % tx;
   int ry = threadIdx.x / tx;
@@ -143,6 +147,10 @@ k_graphnorm_stats(const float* __restrict__ x, const float* __restrict__ dy,
         for (int v = 0; v < VEC; ++v) {
           if (MODE == 0) {
             a[0][v] += xq[u][v];
+          } else if (MODE == 3) {
+            float d = xq[u][v] - ms[v];
+            a[0][v] += d;
+            a[NACC - 1][v] = fmaf(d, d, a[NACC - 1][v]);
           } else if (MODE == 1) {
             float d = xq[u][v] - mu[v];
             a[0][v] = fmaf(d, d, a[0][v]);
@@ -191,20 +199,35 @@ k_graphnorm_stats(const float* __restrict__ x, const float* __restrict__ dy,
   }
 }
 
-// [B,C] finalisation: mean, rstd
-__global__ void k_graphnorm_finalize(const double* __restrict__ sum_x,
-                                     const double* __restrict__ sum_sq,
-                                     const double* __restrict__ count, int64_t B,
-                                     int64_t C, float eps, float* __restrict__ mean,
-                                     float* __restrict__ rstd) {
+// per-channel pivot = mean of the first `rows` rows (any graph): one thread per channel
+__global__ void k_graphnorm_pivot(const float* __restrict__ x, int64_t rows, int64_t C,
+                                  float* __restrict__ pivot) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int64_t r = 0; r < rows; ++r) s += x[r * C + c];
+  pivot[c] = rows > 0 ? s / (float)rows : 0.f;
+}
+
+// [B,C] finalisation from shifted moments S1 = sum(x - p), S2 = sum((x - p)^2):
+//   mean = p + S1/n ;  sum((x - ms*mean)^2)/n = S2/n + 2 q S1/n + q^2,  q = p - ms*mean
+__global__ void k_graphnorm_finalize_shifted(const double* __restrict__ s1,
+                                             const double* __restrict__ s2,
+                                             const double* __restrict__ count,
+                                             const float* __restrict__ pivot,
+                                             const float* __restrict__ mean_scale, int64_t B,
+                                             int64_t C, float eps, float* __restrict__ mean,
+                                             float* __restrict__ rstd) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
-  int64_t b = i / C;
-  double n = fmax(count[b], 1.0);
-  float m = (float)(sum_x[i] / n);
-  float var = (float)(sum_sq[i] / n);
-  mean[i] = m;
-  rstd[i] = 1.f / sqrtf(var + eps);
+  const int64_t b = i / C, c = i - b * C;
+  const double n = fmax(count[b], 1.0);
+  const double p = pivot[c], m1 = s1[i] / n, m2 = s2[i] / n;
+  const double mu = p + m1;
+  const double q = p - (double)mean_scale[c] * mu;
+  const double var = fmax(m2 + 2.0 * q * m1 + q * q, 0.0);
+  mean[i] = (float)mu;
+  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
 template <int VEC>
@@ -486,25 +509,23 @@ int spt_graphnorm_fwd(const float* x, const int64_t* batch, int64_t N, int64_t C
   unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, kNormRows), 148 * 4);
   int64_t total = N * (C / vec);
   int agrid = (int)imin(ceil_div(total > 0 ? total : 1, kNormThreads), 148 * 16);
+  // single pass over x: shifted first and second moments around a per-channel pivot
+  float* pivot = w.k2;  // [C] floats of the (forward-unused) k2 area
   if (N > 0) {
-    if (vec == 4) {
-      k_graphnorm_stats<0, 4><<<slabs, kNormThreads, 0, st>>>(
-          x, nullptr, nullptr, 1.f, batch, N, C, B, mean_scale, nullptr, nullptr, nullptr, nullptr,
-          w.acc0, nullptr, w.count, cm.tx, cm.ty);
-      k_graphnorm_stats<1, 4><<<slabs, kNormThreads, 0, st>>>(
-          x, nullptr, nullptr, 1.f, batch, N, C, B, mean_scale, w.acc0, w.count, nullptr, nullptr,
-          w.acc1, nullptr, nullptr, cm.tx, cm.ty);
-    } else {
-      k_graphnorm_stats<0, 1><<<slabs, kNormThreads, 0, st>>>(
-          x, nullptr, nullptr, 1.f, batch, N, C, B, mean_scale, nullptr, nullptr, nullptr, nullptr,
-          w.acc0, nullptr, w.count, cm.tx, cm.ty);
-      k_graphnorm_stats<1, 1><<<slabs, kNormThreads, 0, st>>>(
-          x, nullptr, nullptr, 1.f, batch, N, C, B, mean_scale, w.acc0, w.count, nullptr, nullptr,
-          w.acc1, nullptr, nullptr, cm.tx, cm.ty);
-    }
+    k_graphnorm_pivot<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(x, imin(N, 64), C, pivot);
+    if (vec == 4)
+      k_graphnorm_stats<3, 4><<<slabs, kNormThreads, 0, st>>>(
+          x, nullptr, nullptr, 1.f, batch, N, C, B, pivot, nullptr, nullptr, nullptr, nullptr,
+          w.acc0, w.acc1, w.count, cm.tx, cm.ty);
+    else
+      k_graphnorm_stats<3, 1><<<slabs, kNormThreads, 0, st>>>(
+          x, nullptr, nullptr, 1.f, batch, N, C, B, pivot, nullptr, nullptr, nullptr, nullptr,
+          w.acc0, w.acc1, w.count, cm.tx, cm.ty);
+  } else {
+    cudaMemsetAsync(pivot, 0, (size_t)C * 4, st);
   }
-  k_graphnorm_finalize<<<(unsigned)ceil_div(B * C, 256), 256, 0, st>>>(
-      w.acc0, w.acc1, w.count, B, C, eps, mean, rstd);
+  k_graphnorm_finalize_shifted<<<(unsigned)ceil_div(B * C, 256), 256, 0, st>>>(
+      w.acc0, w.acc1, w.count, pivot, mean_scale, B, C, eps, mean, rstd);
   if (N > 0) {
     if (vec == 4)
       k_graphnorm_apply<4><<<agrid, kNormThreads, 0, st>>>(x, batch, N, C, B, weight, bias,
