@@ -133,7 +133,9 @@ def host_scene(levels, seed):
 
 def device_transforms(S, nag):
     nag = S.transforms.NodeSize()(nag)
-    return S.transforms.OnTheFlyHorizontalEdgeFeatures(add_self_loops=True)(nag)
+    # csr_order: edges emitted grouped by source (the model is invariant to edge order), so the
+    # attention blocks read edge_attr in place
+    return S.transforms.OnTheFlyHorizontalEdgeFeatures(add_self_loops=True, csr_order=True)(nag)
 
 
 def attn_bytes(tag, m, elt=4, idx=4):
@@ -420,7 +422,8 @@ def run_own(args):
                                       "eager_ms_per_step": round(ms_eager_step, 4)},
                        "matmul": "fp32-accurate 3xTF32 on tcgen05 tensor cores, TMEM accumulators, TMA (csrc/gemm_umma.cu)",
                        "csr": "graph CSR cached across steps in `value` (amortised, SURVEY §8d); "
-                              "rebuilt every step in `e2e`"},
+                              "rebuilt every step in `e2e`; on-the-fly edges emitted in CSR order "
+                              "(OnTheFlyHorizontalEdgeFeatures(csr_order=True))"},
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT,
                     "ms_per_step": round(ms_e2e / e2e_steps, 4),

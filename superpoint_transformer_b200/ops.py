@@ -146,9 +146,28 @@ class GraphIndex:
                  "num_rows", "num_targets", "E", "__weakref__")
 
 
+# edge_index tensors whose columns are already grouped by source row in CSR order (stable):
+# the attention blocks then read `edge_attr` as it is (no per-stage permutation, no inverse
+# permutation of its gradient).  Registered by OnTheFlyHorizontalEdgeFeatures(csr_order=True).
+_csr_ordered = {}
+
+
+def mark_csr_ordered(edge_index):
+    import weakref
+    key = id(edge_index)
+    _csr_ordered[key] = (weakref.ref(edge_index, lambda _r, k=key: _csr_ordered.pop(k, None)),
+                         edge_index._version)
+
+
+def is_csr_ordered(edge_index):
+    hit = _csr_ordered.get(id(edge_index))
+    return hit is not None and hit[0]() is edge_index and hit[1] == edge_index._version
+
+
 def build_graph_index(edge_index, num_rows, num_targets=None):
     lib = _lib.load()
     _require_cuda(edge_index)
+    presorted = is_csr_ordered(edge_index)
     num_targets = num_rows if num_targets is None else num_targets
     edge_index = _i64c(edge_index)
     src, dst = edge_index[0], edge_index[1]
@@ -158,6 +177,11 @@ def build_graph_index(edge_index, num_rows, num_targets=None):
     g = GraphIndex()
     g.rowptr, g.col, g.perm = csr.ptr, csr.other_sorted, csr.perm
     g.csc_ptr, g.csc_src = csc.ptr, csc.other_sorted
+    if presorted:  # CSR slot == edge id
+        g.perm = None
+        g.csc2csr = csc.perm
+        g.num_rows, g.num_targets, g.E = num_rows, num_targets, E
+        return g
     inv = torch.empty(E, dtype=torch.int32, device=src.device)
     c2c = torch.empty(E, dtype=torch.int32, device=src.device)
     with torch.cuda.device(src.device):
@@ -288,6 +312,8 @@ def permute_rows(x, perm):
 def permute_rows_cached(x, perm):
     """edge_attr is shared by all blocks of a stage (src/nn/stage.py:277-280): the
     CSR-ordered copy is made once and its gradient accumulates in CSR order."""
+    if perm is None:   # edges already in CSR order (mark_csr_ordered)
+        return _f32c(x)
     return _permuted_cache.get(x, ("p", id(perm)), lambda: permute_rows(x, perm))
 
 

@@ -45,15 +45,22 @@ class OnTheFlyHorizontalEdgeFeatures:
     `log_length/log_surface/log_volume/log_size` [N, 1].  Output: `edge_index`
     [2, 2Eh (+N)] ordered [i->j | j->i (| self-loops)], `edge_attr` fp32 18 columns.
     Only the full default key set is built by the kernel.
+
+    `csr_order=True` (an extension; the model is invariant to the order of the edges)
+    additionally groups the output edges by source node, stably, so that the attention
+    blocks consume `edge_attr` in place instead of permuting it (and un-permuting its
+    gradient) once per stage and step.
     """
 
-    def __init__(self, keys=None, use_mean_normal=False, add_self_loops=False):
+    def __init__(self, keys=None, use_mean_normal=False, add_self_loops=False,
+                 csr_order=False):
         keys = ON_THE_FLY_HORIZONTAL_FEATURES if keys is None else list(keys)
         if sorted(keys) != sorted(ON_THE_FLY_HORIZONTAL_FEATURES):
             raise NotImplementedError(
                 "the CUDA edge-feature kernel builds the full 18-column default set")
         self.normal_key = 'mean_normal' if use_mean_normal else 'normal'
         self.add_self_loops = add_self_loops
+        self.csr_order = csr_order
 
     def __call__(self, nag):
         for i_level in nag.level_range:
@@ -66,6 +73,11 @@ class OnTheFlyHorizontalEdgeFeatures:
                 d.edge_index, d.edge_attr, d.pos, d[self.normal_key], d['log_length'],
                 d['log_surface'], d['log_volume'], d['log_size'], d.num_nodes,
                 add_self_loops=self.add_self_loops)
+            if self.csr_order:
+                seg = ops.group_index(ei[0], d.num_nodes)
+                ei = ei.index_select(1, seg.perm.long())
+                ea = ops._gather_rows(ea, seg.perm)
+                ops.mark_csr_ordered(ei)
             d.edge_index, d.edge_attr = ei, ea
         return nag
 
