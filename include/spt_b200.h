@@ -116,8 +116,12 @@ int spt_gather_rows_i32(const float* x, const int32_t* idx, int64_t n_out,
  * keeps fp32-level accuracy (~2^-21 relative). */
 int spt_split_tf32(const float* x, int64_t n, float* hi, float* lo, void* stream);
 
-/* Dense projections on the tensor cores, fp32-accurate (in-register 3xTF32 split,
- * fp32 accumulate), operand streamed once:
+/* Dense projections on the 5th-generation tensor cores, fp32-accurate (3xTF32:
+ * hi/lo operand split, three tcgen05.mma.kind::tf32 per k-step, fp32 accumulation in
+ * TMEM), every operand streamed from HBM once by TMA (csrc/gemm_umma.cu).  Shapes the
+ * TMA descriptors cannot take (fewer than 512 / 2048 rows, leading dimensions or C not
+ * 16-byte aligned, N > 4096, dW accumulators beyond 512 TMEM columns) run the
+ * mma.sync kernels of csrc/gemm.cu with the same numerics.
  *   gemm_nt     : C[M,N]  = A[M,K] . B[N,K]^T + bias[N]   (nn.Linear forward; dX with
  *                 B = W^T).  K, lda, ldb multiples of 4; A, B 16-byte aligned.
  *   gemm_tn_acc : C[N,K] += A[M,N]^T . B[M,K] ; colsumA[N] += column sums of A

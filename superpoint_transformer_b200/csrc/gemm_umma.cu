@@ -244,15 +244,6 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
       "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc,
-                                            uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // one 32-column slab of one accumulator row: + bias (smem broadcast) -> swizzled staging row
 __device__ __forceinline__ void stage_slab(const uint32_t (&v)[32], unsigned char* buf, int row,
                                            const float* bias_slab) {
@@ -299,7 +290,6 @@ struct Params {
   int epi_groups;     // 1, or 2 when the B splitter warps are free to help (resident B)
   uint32_t acc_stride;
   long long* trace;   // debug: per-role clock64 stamps of CTA 0 (SPT_UMMA_TRACE)
-  int dbg;            // debug: timing experiments (SPT_UMMA_DBG), wrong results
 };
 
 // Epilogue role of one group of 4 warps (TMEM lane quadrant q = warp % 4).  Group g of
@@ -490,11 +480,8 @@ k_gemm_nt_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer (converged warp, one elected lane issues) ----------------
-    uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.BN >> 3) << 17) |
-                     ((uint32_t)(BM >> 4) << 24);
-    if (P.dbg == 2)
-      idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.BN >> 3) << 17) |
-              ((uint32_t)(BM >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.BN >> 3) << 17) |
+                           ((uint32_t)(BM >> 4) << 24);
     uint32_t it = 0, tl = 0;
     int sa = 0, sb = 0;
     uint32_t pha = 0, phb = 0;
@@ -521,14 +508,7 @@ k_gemm_nt_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
             const uint64_t o = (uint64_t)(k * UK * 4 >> 4);  // advance inside the swizzle row
-            if (P.dbg == 2) {
-              umma_f16_ts(d, a_lo + k * UK, b_hi + o, idesc, (kc | k) != 0);
-              umma_f16_ts(d, a_hi + k * UK, b_lo + o, idesc, 1);
-              umma_f16_ts(d, a_hi + k * UK, b_hi + o, idesc, 1);
-              continue;
-            }
             umma_tf32_ts(d, a_lo + k * UK, b_hi + o, idesc, (kc | k) != 0);
-            if (P.dbg == 1) continue;
             umma_tf32_ts(d, a_hi + k * UK, b_lo + o, idesc, 1);
             umma_tf32_ts(d, a_hi + k * UK, b_hi + o, idesc, 1);
           }
@@ -756,14 +736,10 @@ int launch(const float* A, int64_t M, int64_t K, int64_t lda, const float* B, in
   }
   const unsigned grid = (unsigned)(P.tiles < sm_count ? P.tiles : sm_count);
   static long long* trace_dev = nullptr;
-  const bool tracing = getenv("SPT_UMMA_TRACE") != nullptr;
+  static const bool tracing = getenv("SPT_UMMA_TRACE") != nullptr;  // diagnostic only
   if (tracing && !trace_dev) cudaMalloc(&trace_dev, 7 * 32 * 4 * sizeof(long long));
   if (tracing) cudaMemsetAsync(trace_dev, 0, 7 * 32 * 4 * sizeof(long long), stream);
   P.trace = tracing ? trace_dev : nullptr;
-  {
-    const char* e = getenv("SPT_UMMA_DBG");
-    P.dbg = e ? atoi(e) : 0;
-  }
   k_gemm_nt_umma<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmC, P);
   if (tracing) {
     static int dumped = 0;
