@@ -178,6 +178,34 @@ def norm_pool_cases(ref):
     outs, probe, grads, _ = _run(ref.StdPool(), (xin, None, idx), dict(num_pool=Np), [xin],
                                  torch.Generator().manual_seed(9))
     cases['pool_std'] = dict(x=xs, index=idx, num_pool=Np, out=outs[0], probe=probe, dx=grads[0])
+    # TransformerBlock with the reference's code-default norm = PyG LayerNorm(mode='graph')
+    # (src/nn/transformer.py:137) and with GroupNorm, on a 3-graph batch
+    Nn, Cb, Fb = 260, 32, 8
+    ei, _ = _graph(gen, Nn, Nn * 3)
+    bidx = torch.sort(torch.randint(0, 3, (Nn,), generator=gen)).values
+    xb = torch.randn(Nn, Cb, generator=gen)
+    eab = torch.randn(ei.shape[1], Fb, generator=gen)
+    import functools
+    for name, norm in (('block_layernorm_graph', None),
+                       ('block_groupnorm4', functools.partial(ref.GroupNorm, num_groups=4))):
+        torch.manual_seed(77)
+        kw = dict(num_heads=4, qk_dim=4, in_rpe_dim=Fb, k_rpe=True, q_rpe=True, v_rpe=True,
+                  ffn_ratio=1)
+        vh = ref.VersionHolder('3.0.0')
+        blk = ref.TransformerBlock(Cb, version_holder=vh, **kw) if norm is None else \
+            ref.TransformerBlock(Cb, norm=norm, version_holder=vh, **kw)
+        blk.apply(ref.init_weights)
+        for p_ in blk.parameters():
+            if p_.dim() == 1:
+                p_.data.normal_(0.5, 0.3, generator=gen)
+        blk.eval()
+        xin, ein = xb.clone(), eab.clone()
+        outs, probe, grads, pgrads = _run(blk, (xin, bidx, ei, ein), {}, [xin, ein],
+                                          torch.Generator().manual_seed(10))
+        cases[name] = dict(x=xb, batch=bidx, edge_index=ei, edge_attr=eab, cfg=kw,
+                           sd={k: v.detach().clone() for k, v in blk.state_dict().items()},
+                           out=outs[0], probe=probe, dx=grads[0], dedge_attr=grads[1],
+                           dparams=pgrads)
     return cases
 
 

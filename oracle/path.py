@@ -60,13 +60,24 @@ def linear(sd, prefix, x):
     return F.linear(x, w, None if b is None else b.to(x.dtype))
 
 
+NORM_KIND = {'kind': None}   # None: GraphNorm if `mean_scale` exists, else per-node LayerNorm;
+                             # 'layer_graph': PyG LayerNorm(mode='graph') (the code default of
+                             # src/nn/transformer.py:137); ('group', G): GroupNorm(mode='graph')
+
+
 def norm_apply(sd, prefix, x, index):
     """Index-based norm dispatch (src/nn/transformer.py:258-265, src/nn/mlp.py:89-94).
-    GraphNorm is recognised by its `mean_scale` parameter."""
+    GraphNorm is recognised by its `mean_scale` parameter; LayerNorm(graph) / GroupNorm share
+    their parameter names with the per-node LayerNorm and are selected through NORM_KIND."""
     w = sd[prefix + '.weight'].to(x.dtype)
     b = sd[prefix + '.bias'].to(x.dtype)
     if _has(sd, prefix + '.mean_scale'):
         return L.graph_norm(x, index, w, b, sd[prefix + '.mean_scale'].to(x.dtype))
+    kind = NORM_KIND['kind']
+    if kind == 'layer_graph':
+        return L.layer_norm_graph(x, index, w, b, 1e-5)
+    if isinstance(kind, tuple) and kind[0] == 'group':
+        return group_norm(x, index, w, b, kind[1])
     return F.layer_norm(x, (x.shape[1],), w, b, 1e-5)
 
 

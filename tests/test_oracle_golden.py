@@ -198,3 +198,22 @@ def test_std_pool(golden):
     torch.testing.assert_close(out, c['out'], atol=1e-6, rtol=1e-5)
     (out * c['probe']).sum().backward()
     torch.testing.assert_close(x.grad, c['dx'], atol=1e-6, rtol=1e-4)
+
+
+@pytest.mark.parametrize('name,kind', [('block_layernorm_graph', 'layer_graph'),
+                                       ('block_groupnorm4', ('group', 4))])
+def test_transformer_block_graphwise_norms(golden, name, kind):
+    """TransformerBlock with the reference's code-default norm (PyG LayerNorm, mode='graph')
+    and with GroupNorm, 3-graph batch: oracle vs the reference source run here."""
+    c = golden('norms.pt')[name]
+    sd = _sd_grad({'b.' + k: v for k, v in c['sd'].items()})
+    x, ea = _req(c['x'], c['edge_attr'])
+    P.NORM_KIND['kind'] = kind
+    try:
+        out = P.transformer_block(sd, 'b', x, c['batch'], c['edge_index'], ea, num_heads=4, qk_dim=4)
+    finally:
+        P.NORM_KIND['kind'] = None
+    torch.testing.assert_close(out, c['out'], atol=2e-5, rtol=1e-5)
+    (out * c['probe']).sum().backward()
+    torch.testing.assert_close(x.grad, c['dx'], atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(ea.grad, c['dedge_attr'], atol=1e-4, rtol=1e-4)
