@@ -476,6 +476,19 @@ int tn_launch(const float* A, int64_t M, int64_t N, int64_t lda, const float* B,
 
 using namespace spt;
 
+// CSR rows per warp of the specialised attention kernels: 8 on large levels (long slabs
+// amortise the tile-stream prologue), fewer on the coarse levels so that the grid still fills
+// the machine `waves` times over (a 20 k-row level with 8 rows/warp is < 1 wave).  Measured
+// (cfg 2): backward rows 20 k: 0.30 -> 0.26 ms, 4 k: 0.155 -> 0.087 ms with 3 waves; the forward
+// only gains below one wave (4 k: 0.089 -> 0.052 ms; 20 k was slower with 2 rows/warp).
+static int rows_per_warp_for(int64_t num_rows, int ctas_per_sm, int waves) {
+  const int64_t target_warps = (int64_t)148 * ctas_per_sm * fast::kWarps * waves;
+  int64_t r = num_rows / target_warps;
+  if (r < 1) r = 1;
+  if (r > 8 || (waves == 1 && r >= 4)) r = 8;
+  return (int)r;
+}
+
 extern "C" {
 
 int spt_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v,
@@ -501,7 +514,7 @@ int spt_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const
     A.Wq = Wq; A.bq = bq; A.Wk = Wk; A.bk = bk;
     A.scale_mode = scale_mode; A.scale_value = scale_value;
     A.agg_v = agg_v; A.abar = abar; A.sump = sump; A.m = m; A.z = z;
-    A.rows_per_warp = 8;
+    A.rows_per_warp = rows_per_warp_for(num_rows, 5, 1);
     static bool attr_set = false;
     if (!attr_set) {
       cudaFuncSetAttribute(fast::k_attn_fwd_fast, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -556,7 +569,7 @@ int spt_attn_bwd_rows(const float* q, int64_t ldq, const float* k, int64_t ldk,
     A.scale_mode = scale_mode; A.scale_value = scale_value;
     A.m = m; A.z = z; A.agg_v = agg_v; A.abar = abar; A.d_agg_v = d_agg_v; A.d_abar = d_abar;
     A.dq = dq; A.lddq = (int)lddq; A.da = da; A.Pbuf = Pbuf; A.G = G;
-    A.rows_per_warp = 8;
+    A.rows_per_warp = rows_per_warp_for(num_rows, 4, 3);
     static bool attr_set = false;
     if (!attr_set) {
       cudaFuncSetAttribute(fast::k_attn_bwd_rows_fast,
