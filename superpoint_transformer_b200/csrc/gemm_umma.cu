@@ -7,24 +7,32 @@
 //   x = hi + lo,  hi = tf32(x),  lo = tf32(x - hi),   A.B ~= Alo.Bhi + Ahi.Blo + Ahi.Bhi
 // (~2^-21 relative), accumulated in fp32 in TMEM.
 //
-// One persistent CTA per SM, warp-specialised, tile = 128 rows x BN (<=192) columns:
-//   warp 0      TMA producer A: 128 x 32 fp32 chunks (SWIZZLE_128B, OOB zero-filled) into a deep
-//                              ring of raw landing slots (up to 8 x 16 KB in flight per SM)
-//   warp 3      TMA producer B: BN x 32 chunks of the (L2-resident) weights
-//   warps 8-11  splitter A   : A row -> registers -> hi / lo -> tcgen05.st into TMEM (row = lane,
-//                              K along columns), freeing the landing slot at once
+// k_gemm_nt_umma: one persistent CTA per SM, warp-specialised, tile = 128 rows x BN (<=192):
+//   warp 0      TMA producer A: 128 x 32 fp32 chunks (SWIZZLE_128B, OOB zero-filled) into a
+//                              ring of raw landing slots (2-8 x 16 KB in flight per SM)
+//   warp 3      TMA producer B: the [BN, K] weights; RESIDENT in shared memory for the whole
+//                              kernel when they fit (split once per CTA), else streamed per
+//                              32-wide K chunk through 2-3 slots
+//   warps 8-11  splitter A   : A row -> registers (ld.shared) -> hi / lo -> tcgen05.st into TMEM
+//                              (row = lane, K along columns); the landing slot is released
+//                              only after that tcgen05.st has consumed the values
 //   warps 12-15 splitter B   : B chunk rewritten in place as `hi` + twin `lo` buffer
-//                              (element-wise, so the TMA swizzle is preserved), fence.proxy.async
-//   warp 1      MMA issuer   : 3 x tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) per 8-wide
-//                              k-step, A operand from TMEM, B from K-major SWIZZLE_128B smem
-//                              descriptors; tcgen05.commit releases the operand stage /
-//                              publishes the accumulator
-//   warps 4-7   epilogue     : tcgen05.ld 32 lanes x 32 columns (next slab in flight while
-//                              this one is stored), + bias from smem, 16-byte stores straight
-//                              to C; two TMEM accumulators so the epilogue of tile i overlaps
+//                              (element-wise, so the TMA swizzle is preserved), fence.proxy.async;
+//                              resident mode: done once, helped by warps 4-7, after which warps
+//                              12-15 become the second epilogue group
+//   warp 1      MMA issuer   : converged warp, elect.sync around the issue (uniform datapath):
+//                              3 x tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) per 8-wide k-step,
+//                              A operand from TMEM, B from K-major SWIZZLE_128B smem descriptors;
+//                              tcgen05.commit releases the operand stage / publishes the
+//                              accumulator
+//   warps 4-7   epilogue     : tcgen05.ld 32 lanes x 32 columns (next slab in flight), + bias
+//                              from smem, swizzled st.shared, fence.proxy.async, TMA store
+//                              (clipped at M, N) issued by a FIXED lane (bulk groups are per
+//                              thread); two TMEM accumulators so the epilogue of tile i overlaps
 //                              the MMAs of tile i+1
-//   warp 2      TMEM allocate / free
-// HBM traffic per tile: A once, C once; B chunks are re-read from L2.
+//   warp 2      TMEM allocate / free (512 columns)
+// HBM traffic per tile: A once, C once; B from L2 (once per CTA when resident).
+// k_gemm_tn_umma (dW / dbias) is described where it is defined, further down.
 #include <cuda.h>  // CUtensorMap types; the encoder is fetched through the runtime API
 
 #include "common.cuh"
