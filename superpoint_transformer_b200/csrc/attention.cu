@@ -19,6 +19,7 @@
 // H*F<=512).  Shapes outside raise SPT_E_UNSUPPORTED.
 #include "common.cuh"
 #include "attention_fast.cuh"
+#include "attention_tile.cuh"
 #include <stdlib.h>
 
 namespace spt {
@@ -471,6 +472,7 @@ bool tn_shape_ok(const float* A, int64_t M, int64_t N, int64_t lda, const float*
                  int64_t ldb);
 int tn_launch(const float* A, int64_t M, int64_t N, int64_t lda, const float* B, int64_t K,
               int64_t ldb, float* C, int64_t ldc, float* colsum, cudaStream_t stream);
+bool make_map_rows32(CUtensorMap* tm, const float* ptr, int64_t rows, int64_t ld, int box_rows);
 }  // namespace umma
 }  // namespace spt
 
@@ -482,11 +484,55 @@ using namespace spt;
 // (cfg 2): backward rows 20 k: 0.30 -> 0.26 ms, 4 k: 0.155 -> 0.087 ms with 3 waves; the forward
 // only gains below one wave (4 k: 0.089 -> 0.052 ms; 20 k was slower with 2 rows/warp).
 static int rows_per_warp_for(int64_t num_rows, int ctas_per_sm, int waves) {
+  // test override: force a launch geometry that the heuristics only pick at scale
+  if (const char* ov = getenv("SPT_ATTN_ROWS_PER_WARP")) {
+    int r = atoi(ov);
+    if (r >= 1 && r <= 64) return r;
+  }
   const int64_t target_warps = (int64_t)148 * ctas_per_sm * fast::kWarps * waves;
   int64_t r = num_rows / target_warps;
   if (r < 1) r = 1;
   if (r > 8 || (waves == 1 && r >= 4)) r = 8;
   return (int)r;
+}
+
+// Row-tile kernels (csrc/attention_tile.cuh): rows per warp.  A warp's edge slab streams
+// through its private TMA ring, so longer blocks amortise the ring prologue; the grid should
+// still cover every SM a few times over.
+static int tile_rows_per_warp(int64_t num_rows, int warps_per_cta) {
+  if (const char* ov = getenv("SPT_ATTN_ROWS_PER_WARP")) {
+    int r = atoi(ov);
+    if (r >= 1 && r <= 64) return r;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t target_warps = (int64_t)sms * 2 * warps_per_cta * 4;   // 4 waves of 2 CTAs/SM
+  int64_t r = num_rows / target_warps;
+  if (r < 1) r = 1;
+  if (r > 8) r = 8;
+  return (int)r;
+}
+
+// cudaFuncSetAttribute is per device: remember which devices were set up
+template <typename K>
+static void ensure_smem(K kernel, int bytes, unsigned long long* done_mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(*done_mask & bit)) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    *done_mask |= bit;
+  }
+}
+
+static bool tile_layout_ok(const float* q, const float* k, const float* v, const float* a,
+                           int64_t ldq, int64_t ldk, int64_t ldv, int64_t rows, int64_t E) {
+  const uintptr_t al8 = (uintptr_t)q | (uintptr_t)k;
+  return E > 0 && E < (1ll << 31) - 64 && ldv % 4 == 0 && ldq % 2 == 0 && ldk % 2 == 0 &&
+         (al8 & 7) == 0 && ((uintptr_t)v & 15) == 0 && ((uintptr_t)a & 15) == 0 &&
+         ldq < (1 << 20) && ldk < (1 << 20) && ldv < (1 << 20) &&
+         rows * (ldk > ldv ? ldk : ldv) < (int64_t)4000000000LL && !getenv("SPT_ATTN_NO_TILE");
 }
 
 extern "C" {
@@ -507,6 +553,25 @@ int spt_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const
   SPT_REQUIRE(scale_mode >= SPT_SCALE_D_TIMES_G && scale_mode <= SPT_SCALE_CONST,
               SPT_E_INVALID, "attn_fwd: bad scale mode %d", scale_mode);
   cudaStream_t st = (cudaStream_t)stream_;
+  if (a && tile::shape_ok(H, D, Dv, F) && tile_layout_ok(q, k, v, a, ldq, ldk, ldv, num_rows, E)) {
+    CUtensorMap tmA;
+    if (umma::make_map_rows32(&tmA, a, E, F, 8)) {
+      tile::FwdArgs A;
+      A.q = q; A.ldq = (int)ldq; A.k = k; A.ldk = (int)ldk; A.v = v; A.ldv = (int)ldv;
+      A.rowptr = rowptr; A.col = col; A.num_rows = num_rows;
+      A.Wq = Wq; A.bq = bq; A.Wk = Wk; A.bk = bk;
+      A.scale_mode = scale_mode; A.scale_value = scale_value;
+      A.agg_v = agg_v; A.abar = abar; A.sump = sump; A.m = m; A.z = z;
+      A.rows_per_warp = tile_rows_per_warp(num_rows, tile::kFwdWarps);
+      const int smem = tile::FwdSmem<tile::kFwdWarps>::total + 1024;
+      static unsigned long long done = 0;
+      ensure_smem(tile::k_attn_fwd_tile, smem, &done);
+      const int64_t warps = ceil_div(num_rows, A.rows_per_warp);
+      tile::k_attn_fwd_tile<<<(unsigned)ceil_div(warps, tile::kFwdWarps), tile::kFwdWarps * kWarp,
+                              smem, st>>>(tmA, A);
+      return check_launch("attn_fwd(tile)");
+    }
+  }
   if (a && fast::shape_ok(H, D, Dv, F) && fast_layout_ok(v, a, ldq, ldk, ldv, num_rows)) {
     fast::FwdArgs A;
     A.q = q; A.ldq = (int)ldq; A.k = k; A.ldk = (int)ldk; A.v = v; A.ldv = (int)ldv; A.a = a;
@@ -560,8 +625,36 @@ int spt_attn_bwd_rows(const float* q, int64_t ldq, const float* k, int64_t ldk,
                   (E == 0 || (col && Pbuf && G)),
               SPT_E_INVALID, "attn_bwd_rows: null pointer");
   cudaStream_t st = (cudaStream_t)stream_;
-  if (a && fast::shape_ok(H, D, Dv, F) && fast_layout_ok(v, a, ldq, ldk, ldv, num_rows) &&
-      lddq < (1 << 20)) {
+  bool tile_done = false;
+  if (a && tile::shape_ok(H, D, Dv, F) && tile_layout_ok(q, k, v, a, ldq, ldk, ldv, num_rows, E) &&
+      lddq < (1 << 20) && lddq % 2 == 0 && ((uintptr_t)dq & 7) == 0 &&
+      ((uintptr_t)G & 7) == 0 && (!da || ((uintptr_t)da & 7) == 0) &&
+      ((uintptr_t)d_agg_v & 15) == 0 && ((uintptr_t)agg_v & 15) == 0 &&
+      (!abar || ((uintptr_t)abar & 15) == 0) && (!d_abar || ((uintptr_t)d_abar & 15) == 0)) {
+    CUtensorMap tmA;
+    if (umma::make_map_rows32(&tmA, a, E, F, 8)) {
+      tile::BwdArgs A;
+      A.q = q; A.ldq = (int)ldq; A.k = k; A.ldk = (int)ldk; A.v = v; A.ldv = (int)ldv;
+      A.rowptr = rowptr; A.col = col; A.num_rows = num_rows;
+      A.Wq = Wq; A.bq = bq; A.Wk = Wk; A.bk = bk;
+      A.scale_mode = scale_mode; A.scale_value = scale_value;
+      A.m = m; A.z = z; A.agg_v = agg_v; A.abar = abar; A.d_agg_v = d_agg_v; A.d_abar = d_abar;
+      A.dq = dq; A.lddq = (int)lddq; A.da = da; A.Pbuf = Pbuf; A.G = G;
+      A.rows_per_warp = tile_rows_per_warp(num_rows, tile::kBwdWarps);
+      const int smem = tile::BwdSmem<tile::kBwdWarps>::total + 1024;
+      static unsigned long long done = 0;
+      ensure_smem(tile::k_attn_bwd_tile, smem, &done);
+      const int64_t warps = ceil_div(num_rows, A.rows_per_warp);
+      tile::k_attn_bwd_tile<<<(unsigned)ceil_div(warps, tile::kBwdWarps), tile::kBwdWarps * kWarp,
+                              smem, st>>>(tmA, A);
+      int rc2 = check_launch("attn_bwd_rows(tile)");
+      if (rc2 != SPT_OK) return rc2;
+      tile_done = true;
+    }
+  }
+  if (tile_done || (a && fast::shape_ok(H, D, Dv, F) &&
+                    fast_layout_ok(v, a, ldq, ldk, ldv, num_rows) && lddq < (1 << 20))) {
+    if (!tile_done) {
     fast::BwdArgs A;
     A.q = q; A.ldq = (int)ldq; A.k = k; A.ldk = (int)ldk; A.v = v; A.ldv = (int)ldv; A.a = a;
     A.rowptr = rowptr; A.col = col; A.num_rows = num_rows;
@@ -582,6 +675,7 @@ int spt_attn_bwd_rows(const float* q, int64_t ldq, const float* k, int64_t ldk,
                                  fast::bwd_smem_bytes(), st>>>(A);
     int rc2 = check_launch("attn_bwd_rows(fast)");
     if (rc2 != SPT_OK) return rc2;
+    }
     if (E > 0 && ((Wq && (dWq || dbq)) || (Wk && (dWk || dbk)))) {
       // d[Wq;Wk] = G^T a, d[bq;bk] = colsum(G): a [E,32]^T [E,32] product.  When the caller
       // hands the four gradients as one contiguous [2HD, F] / [2HD] pair it runs on the

@@ -1,0 +1,773 @@
+// attention_tile.cuh — row-tile attention kernels for the SPT "4 heads" family
+// (H*D = 16 -> 2*H*D = 32 RPE outputs, F = 32 edge features, C = H*Dv = 128):
+// BASELINE.json cfg 2/3/5 (C=128, H=4, qk_dim=4, in_rpe_dim=32).
+//
+// Replaces the per-edge dependent chain of attention_fast.cuh (144 / 242 warp
+// instructions per edge) by a per-ROW-TILE schedule.  One warp owns a block of
+// consecutive CSR rows; one row = one tile of <= 32 CSR slots (longer rows take
+// several tiles, merged with an online softmax):
+//
+//   A  edge features a[slots, 0:32] of the warp's slab stream HBM -> shared memory
+//      through a warp-private ring of 2-D TMA boxes (8 rows x 128 B, SWIZZLE_128B,
+//      completion on mbarriers) — read exactly once, independent of the row structure;
+//   B  the RPE product of the whole tile, R[32 x 32] = A_tile [32 x 32] . [Wq;Wk]^T, runs on
+//      the tensor cores: mma.sync m16n8k8 TF32 with the 3xTF32 split (fp32-accurate),
+//      A fragments by ldmatrix from the swizzled tile (conflict-free), weight fragments
+//      pre-split (hi/lo) once per CTA in fragment order;
+//   C  in the accumulator fragment a thread holds r_q[h,d] and r_k[h,d] of the same
+//      (edge, head, d in {2t,2t+1}): head logit = 2 FMAs + one shfl.xor(1);
+//      two-pass softmax over the tile in registers (3 shfl.xor over the row lanes);
+//   D  p goes through a [32 x 4] shared-memory tile to the accumulation layout
+//      (lane = 4 value channels + 4 abar entries): per edge one LDG.128 of the gathered
+//      v row, one LDS.128 of the staged a row and 4 packed FMAs, 8 edges in flight.
+//
+// The backward rows kernel has the same front end, recomputes p from the saved (m, z),
+// evaluates dp = <dY, v> + <dAbar, a> with a butterfly transpose-reduce (7 shuffles per 8
+// edges), forms G = [dq_e | dk_e] directly in the accumulator fragment, and feeds that
+// fragment — with a permuted k order, no shuffles — as the A operand of the second
+// tensor-core product da = G . [Wq;Wk] + P . dAbar.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+#include "attention_fast.cuh"
+
+namespace spt {
+namespace tile {
+
+using fast::smem_u32;
+using fast::mbar_init;
+using fast::mbar_fence_init;
+using fast::mbar_expect_tx;
+using fast::mbar_wait;
+using fast::f32x2;
+using fast::pack2;
+using fast::unpack2;
+using fast::fma2;
+using fast::mul2;
+using fast::ex2;
+using fast::kLog2e;
+using fast::kLn2;
+
+constexpr int kH = 4, kD = 4, kDv = 32, kF = 32;
+constexpr int kHD = kH * kD;          // 16
+constexpr int kHD2 = 2 * kHD;         // 32
+constexpr int kC = kH * kDv;          // 128
+constexpr int kChunk = 32;            // CSR slots per ring chunk = 4 TMA boxes of 8 rows
+constexpr int kRing = 3;              // chunks per warp: <= 2 under the current tile + 1 in flight
+constexpr int kChunkBytes = kChunk * kF * 4;     // 4096
+constexpr int kRingSlots = kRing * kChunk;       // 96
+constexpr int kFragBytes = 16 * 32 * 16;         // one pre-split weight fragment set (8 KB)
+
+constexpr int kFwdWarps = 8;
+constexpr int kBwdWarps = 6;
+
+__host__ __device__ inline bool shape_ok(int H, int D, int Dv, int F) {
+  return H == kH && D == kD && Dv == kDv && F == kF;
+}
+
+__device__ __forceinline__ void tma_box(void* dst, const CUtensorMap* tm, int row, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(0), "r"(row)
+      : "memory");
+}
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                        uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+
+// x = hi + lo, hi = x rounded to tf32 (integer round-to-nearest: full-rate ALU ops, the
+// cvt.rna.tf32 instruction is quarter rate).  lo is passed as is: the tensor core reads the
+// upper 19 bits of a tf32 operand, i.e. truncates lo at 2^-11 of an already 2^-11-small term.
+__device__ __forceinline__ void split_tf32(uint32_t x, uint32_t& hi, uint32_t& lo) {
+  hi = (x + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(__uint_as_float(x) - __uint_as_float(hi));
+}
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+      "{%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// c += (ahi + alo) . (bhi + blo) without the lo.lo term (small terms first)
+__device__ __forceinline__ void mma_3x(float (&c)[4], const uint32_t (&ahi)[4],
+                                       const uint32_t (&alo)[4], const uint4& b) {
+  mma_tf32(c, alo, b.x, b.y);
+  mma_tf32(c, ahi, b.z, b.w);
+  mma_tf32(c, ahi, b.x, b.y);
+}
+
+__device__ __forceinline__ float2 ldg_stream2(const float* p) {
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];"
+               : "=f"(r.x), "=f"(r.y)
+               : "l"(p));
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------
+// Warp-private ring of edge-feature chunks.  Chunk j covers the CSR slots
+// [base + 32 j, base + 32 j + 32) of the warp's slab and lives in stage j % 3; its 8-row boxes
+// arrive by 2-D TMA on the stage's mbarrier (phase parity (j / 3) & 1).  Slot s of the slab
+// sits at physical row (s - base) % 96 of the ring; inside a row the 16-byte chunk c is at
+// c ^ (row & 7) (SWIZZLE_128B; the ring and every stage start on 1024-byte boundaries).
+// ---------------------------------------------------------------------------------------
+struct Ring {
+  unsigned char* buf;
+  uint64_t* bar;
+  const CUtensorMap* tm;
+  int64_t base;
+  int slab;      // slots in the slab
+  int nchunks, issued, ready;
+  int lane;
+
+  __device__ __forceinline__ void init(int64_t e0, int64_t e1) {
+    base = e0;
+    slab = (int)(e1 - e0);
+    nchunks = (slab + kChunk - 1) / kChunk;
+    issued = ready = 0;
+    if (lane == 0) {
+#pragma unroll
+      for (int s = 0; s < kRing; ++s) mbar_init(&bar[s], 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    while (issued < nchunks && issued < kRing) issue_one();
+  }
+  __device__ __forceinline__ void issue_one() {
+    const int j = issued;
+    if (lane == 0) {
+      const int s0 = j * kChunk;
+      const int rows = min(kChunk, slab - s0);
+      const int nb = (rows + 7) >> 3;
+      const int stage = j % kRing;
+      unsigned char* dst = buf + stage * kChunkBytes;
+      mbar_expect_tx(&bar[stage], (uint32_t)nb * 1024u);
+      for (int b = 0; b < nb; ++b)
+        tma_box(dst + b * 1024, tm, (int)(base + s0 + 8 * b), &bar[stage]);
+    }
+    ++issued;
+  }
+  // make the slab-relative slots [o, o + n) readable; returns their first physical row
+  __device__ __forceinline__ int prepare(int o, int n) {
+    const int c_lo = o / kChunk, c_hi = (o + n - 1) / kChunk;
+    __syncwarp();   // every lane is done with the chunks below c_lo
+    while (issued < nchunks && issued < c_lo + kRing) issue_one();
+    while (ready <= c_hi) {
+      mbar_wait(&bar[ready % kRing], (uint32_t)((ready / kRing) & 1), ready, o);
+      ++ready;
+    }
+    __syncwarp();
+    return o % kRingSlots;
+  }
+};
+
+// weight fragments in shared memory.
+//   frag1[(kk*4 + nn)*32 + lane] = {b0.hi, b1.hi, b0.lo, b1.lo} of  B1[k=f][n=o] = W[o][f]:
+//       b0 = W[8nn + g][8kk + t], b1 = W[8nn + g][8kk + t + 4]           (GEMV 1: r = a W^T)
+//   frag2[(ks*4 + nf)*32 + lane] of  B2[k=o][n=f] = W[o][f] with the k order of the
+//       accumulator fragment (slot s < 4 <-> o = 8ks + 2s, slot 4 + s <-> o = 8ks + 2s + 1):
+//       b0 = W[8ks + 2t][8nf + g], b1 = W[8ks + 2t + 1][8nf + g]          (GEMV 2: da = G W)
+// W = [Wq; Wk] (rows 0-15 / 16-31); an absent encoder is a zero block.
+__device__ __forceinline__ float w_at(const float* Wq, const float* Wk, int o, int f) {
+  const float* W = (o < kHD) ? Wq : Wk;
+  return W ? W[(o & (kHD - 1)) * kF + f] : 0.f;
+}
+__device__ __forceinline__ uint4 split_pair(float w0, float w1) {
+  uint32_t h0, l0, h1, l1;
+  split_tf32(__float_as_uint(w0), h0, l0);
+  split_tf32(__float_as_uint(w1), h1, l1);
+  // lo rounded as well (done once per CTA)
+  l0 = (l0 + 0x1000u) & 0xffffe000u;
+  l1 = (l1 + 0x1000u) & 0xffffe000u;
+  return make_uint4(h0, h1, l0, l1);
+}
+__device__ __forceinline__ void build_frag1(uint4* frag, const float* Wq, const float* Wk) {
+  for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) {
+    const int ln = i & 31, fr = i >> 5, kk = fr >> 2, nn = fr & 3, g = ln >> 2, t = ln & 3;
+    frag[i] = split_pair(w_at(Wq, Wk, 8 * nn + g, 8 * kk + t),
+                         w_at(Wq, Wk, 8 * nn + g, 8 * kk + t + 4));
+  }
+}
+__device__ __forceinline__ void build_frag2(uint4* frag, const float* Wq, const float* Wk) {
+  for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) {
+    const int ln = i & 31, fr = i >> 5, ks = fr >> 2, nf = fr & 3, g = ln >> 2, t = ln & 3;
+    frag[i] = split_pair(w_at(Wq, Wk, 8 * ks + 2 * t, 8 * nf + g),
+                         w_at(Wq, Wk, 8 * ks + 2 * t + 1, 8 * nf + g));
+  }
+}
+__device__ __forceinline__ void build_bias(float* bias_s, const float* Wq, const float* bq,
+                                           const float* Wk, const float* bk) {
+  for (int o = threadIdx.x; o < kHD2; o += blockDim.x) {
+    float b = 0.f;
+    if (o < kHD) { if (Wq && bq) b = bq[o]; }
+    else { if (Wk && bk) b = bk[o - kHD]; }
+    bias_s[o] = b;
+  }
+}
+
+// R = A_tile . W^T + bias for the tile whose first physical ring row is `prow`:
+// acc[m][nn][.] = accumulator fragments (m-tile m = edges 16m..16m+15, n-tile nn = outputs
+// 8nn..8nn+7): c0,c1 = (edge 16m+g, outputs 8nn+2t, +1), c2,c3 = (edge 16m+8+g, same outputs).
+__device__ __forceinline__ void rpe_tile(float (&acc)[2][4][4], const unsigned char* ring,
+                                         int prow, bool two, const uint4* frag1,
+                                         const float* bias_s, int lane) {
+  const int t = lane & 3;
+#pragma unroll
+  for (int nn = 0; nn < 4; ++nn) {
+    const float2 b = *reinterpret_cast<const float2*>(bias_s + 8 * nn + 2 * t);
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      acc[m][nn][0] = b.x; acc[m][nn][1] = b.y; acc[m][nn][2] = b.x; acc[m][nn][3] = b.y;
+    }
+  }
+  // ldmatrix row addresses: lane L feeds row 16m + (L&7) + 8*((L>>3)&1) of matrix L>>3
+  uint32_t rowaddr[2], rsw[2];
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    int r = prow + 16 * m + (lane & 7) + ((lane >> 3) & 1) * 8;
+    if (r >= kRingSlots) r -= kRingSlots;
+    rowaddr[m] = smem_u32(ring + r * 128);
+    rsw[m] = (uint32_t)(r & 7);
+  }
+  const uint32_t csel = (uint32_t)(lane >> 4);
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      if (m == 0 || two) {
+        uint32_t a[4];
+        ldsm_x4(rowaddr[m] + (((2 * kk + csel) ^ rsw[m]) << 4), a[0], a[1], a[2], a[3]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_tf32(a[i], ahi[m][i], alo[m][i]);
+      }
+    }
+#pragma unroll
+    for (int nn = 0; nn < 4; ++nn) {
+      const uint4 b = frag1[(kk * 4 + nn) * 32 + lane];
+      mma_3x(acc[0][nn], ahi[0], alo[0], b);
+      if (two) mma_3x(acc[1][nn], ahi[1], alo[1], b);
+    }
+  }
+}
+
+struct FwdArgs {
+  const float* q; int ldq;
+  const float* k; int ldk;
+  const float* v; int ldv;
+  const int32_t* rowptr; const int32_t* col;
+  int64_t num_rows;
+  const float* Wq; const float* bq; const float* Wk; const float* bk;
+  int scale_mode; float scale_value;
+  float* agg_v; float* abar; float* sump; float* m; float* z;
+  int rows_per_warp;
+};
+
+// shared memory: [kWarps rings, 1024-aligned][frag1 8 KB][bias 128 B][bars][p tiles]
+template <int kWarps>
+struct FwdSmem {
+  static constexpr int ring_off = 0;
+  static constexpr int frag_off = kWarps * kRing * kChunkBytes;
+  static constexpr int bias_off = frag_off + kFragBytes;
+  static constexpr int bar_off = bias_off + 128;
+  static constexpr int p_off = bar_off + kWarps * kRing * 8 + ((kWarps * kRing) & 1) * 8;
+  static constexpr int total = p_off + kWarps * 32 * kH * 4;
+};
+
+__global__ void __launch_bounds__(kFwdWarps * 32, 2)
+k_attn_fwd_tile(const __grid_constant__ CUtensorMap tmA, const FwdArgs P) {
+  using L = FwdSmem<kFwdWarps>;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem =
+      smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);   // SWIZZLE_128B atoms
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  uint4* frag1 = reinterpret_cast<uint4*>(smem + L::frag_off);
+  float* bias_s = reinterpret_cast<float*>(smem + L::bias_off);
+  float* p_s = reinterpret_cast<float*>(smem + L::p_off) + w * 32 * kH;
+
+  build_frag1(frag1, P.Wq, P.Wk);
+  build_bias(bias_s, P.Wq, P.bq, P.Wk, P.bk);
+  __syncthreads();
+
+  const int64_t gw = (int64_t)blockIdx.x * kFwdWarps + w;
+  const int64_t row0 = gw * P.rows_per_warp;
+  if (row0 >= P.num_rows) return;
+  const int64_t row1 = min(row0 + (int64_t)P.rows_per_warp, P.num_rows);
+
+  Ring ring;
+  ring.buf = smem + L::ring_off + w * (kRing * kChunkBytes);
+  ring.bar = reinterpret_cast<uint64_t*>(smem + L::bar_off) + w * kRing;
+  ring.tm = &tmA;
+  ring.lane = lane;
+  const int e_begin = P.rowptr[row0];
+  ring.init(e_begin, P.rowptr[row1]);
+
+  const bool want_abar = P.abar != nullptr;
+  const int hb = lane >> 3;                     // head of my 4 value channels
+  const int hsrc = 2 * (hb & 1);                // a lane holding head hb in the fragment layout
+  const float* vbase = P.v + 4 * lane;
+  const float* kbase = P.k + 2 * t;
+
+  int b = e_begin;
+  for (int64_t row = row0; row < row1; ++row) {
+    const int e = P.rowptr[row + 1];
+    const float scale = fast::qk_scale_fast(P.scale_mode, P.scale_value, e - b);
+    float2 qA = *reinterpret_cast<const float2*>(P.q + row * P.ldq + 2 * t);
+    float2 qB = *reinterpret_cast<const float2*>(P.q + row * P.ldq + 8 + 2 * t);
+    qA.x *= scale; qA.y *= scale; qB.x *= scale; qB.y *= scale;
+    float mA = -INFINITY, mB = -INFINITY, lA = 0.f, lB = 0.f;   // heads t>>1 and 2 + (t>>1)
+    f32x2 accv01 = 0ull, accv23 = 0ull, acca01 = 0ull, acca23 = 0ull;
+
+    for (int tb = b; tb < e; tb += 32) {
+      const int n = min(32, e - tb);
+      const bool two = n > 16;
+      const int mycol = (lane < n) ? P.col[tb + lane] : 0;
+      // gathered k rows of my 4 edges (issued before the tensor-core phase)
+      float2 kA[4], kB[4];
+#pragma unroll
+      for (int idx = 0; idx < 4; ++idx) {
+        if (idx < 2 || two) {
+          const unsigned tc = (unsigned)__shfl_sync(kFull, mycol, 8 * idx + g);
+          const float* kp = kbase + (size_t)tc * (unsigned)P.ldk;
+          kA[idx] = ldg_stream2(kp);
+          kB[idx] = ldg_stream2(kp + 8);
+        }
+      }
+      const int prow = ring.prepare(tb - e_begin, n);
+      float acc[2][4][4];
+      rpe_tile(acc, ring.buf, prow, two, frag1, bias_s, lane);
+
+      // logits (base 2) of my 4 edges x 2 heads
+      float cA[4], cB[4];
+#pragma unroll
+      for (int idx = 0; idx < 4; ++idx) {
+        cA[idx] = -INFINITY; cB[idx] = -INFINITY;
+        if (idx < 2 || two) {
+          const int m = idx >> 1, hf = (idx & 1) * 2;
+          float pa = (qA.x + acc[m][0][hf]) * (kA[idx].x + acc[m][2][hf]);
+          pa = fmaf(qA.y + acc[m][0][hf + 1], kA[idx].y + acc[m][2][hf + 1], pa);
+          float pb = (qB.x + acc[m][1][hf]) * (kB[idx].x + acc[m][3][hf]);
+          pb = fmaf(qB.y + acc[m][1][hf + 1], kB[idx].y + acc[m][3][hf + 1], pb);
+          pa += __shfl_xor_sync(kFull, pa, 1);
+          pb += __shfl_xor_sync(kFull, pb, 1);
+          if (8 * idx + g < n) { cA[idx] = pa * kLog2e; cB[idx] = pb * kLog2e; }
+        }
+      }
+      float tA = fmaxf(fmaxf(cA[0], cA[1]), fmaxf(cA[2], cA[3]));
+      float tB = fmaxf(fmaxf(cB[0], cB[1]), fmaxf(cB[2], cB[3]));
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        tA = fmaxf(tA, __shfl_xor_sync(kFull, tA, o));
+        tB = fmaxf(tB, __shfl_xor_sync(kFull, tB, o));
+      }
+      const float mA_new = fmaxf(mA, tA), mB_new = fmaxf(mB, tB);
+      const float alA = ex2(mA - mA_new), alB = ex2(mB - mB_new);   // 0 on the first tile
+      float sA = 0.f, sB = 0.f;
+#pragma unroll
+      for (int idx = 0; idx < 4; ++idx) {
+        if (idx < 2 || two) {
+          const float pA = ex2(cA[idx] - mA_new), pB = ex2(cB[idx] - mB_new);
+          sA += pA; sB += pB;
+          if ((t & 1) == 0) {
+            p_s[(8 * idx + g) * kH + (t >> 1)] = pA;
+            p_s[(8 * idx + g) * kH + 2 + (t >> 1)] = pB;
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        sA += __shfl_xor_sync(kFull, sA, o);
+        sB += __shfl_xor_sync(kFull, sB, o);
+      }
+      lA = fmaf(lA, alA, sA); lB = fmaf(lB, alB, sB);
+      mA = mA_new; mB = mB_new;
+      __syncwarp();
+
+      // accumulation layout: lane = value channels 4*lane.. (head hb) + abar[hb][4*(lane&7)..]
+      if (tb != b) {   // later tiles of a long row: rescale the running sums
+        const float a0 = __shfl_sync(kFull, alA, hsrc), a1 = __shfl_sync(kFull, alB, hsrc);
+        const float al = hb < 2 ? a0 : a1;
+        const f32x2 aa = pack2(al, al);
+        accv01 = mul2(accv01, aa); accv23 = mul2(accv23, aa);
+        acca01 = mul2(acca01, aa); acca23 = mul2(acca23, aa);
+      }
+      for (int e0 = 0; e0 < n; e0 += 8) {
+        ulonglong2 vv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (e0 + u < n) {
+            const unsigned tc = (unsigned)__shfl_sync(kFull, mycol, e0 + u);
+            const float4 x = ldg_stream4(vbase + (size_t)tc * (unsigned)P.ldv);
+            vv[u].x = pack2(x.x, x.y); vv[u].y = pack2(x.z, x.w);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (e0 + u < n) {
+            const float p = p_s[(e0 + u) * kH + hb];
+            const f32x2 pp = pack2(p, p);
+            fma2(accv01, pp, vv[u].x);
+            fma2(accv23, pp, vv[u].y);
+            if (want_abar) {
+              int r = prow + e0 + u;
+              if (r >= kRingSlots) r -= kRingSlots;
+              const ulonglong2 a4 = *reinterpret_cast<const ulonglong2*>(
+                  ring.buf + r * 128 + ((((lane & 7) ^ r) & 7) << 4));
+              fma2(acca01, pp, a4.x);
+              fma2(acca23, pp, a4.y);
+            }
+          }
+        }
+      }
+    }
+
+    // epilogue of the row
+    const float zA = lA + 1e-16f, zB = lB + 1e-16f;     // PyG softmax: + 1e-16 after the sum
+    {
+      const float z0 = __shfl_sync(kFull, zA, hsrc), z1 = __shfl_sync(kFull, zB, hsrc);
+      const float inv = 1.f / (hb < 2 ? z0 : z1);
+      const f32x2 ii = pack2(inv, inv);
+      ulonglong2 o;
+      o.x = mul2(accv01, ii); o.y = mul2(accv23, ii);
+      *reinterpret_cast<ulonglong2*>(P.agg_v + row * kC + 4 * lane) = o;
+      if (want_abar) {
+        o.x = mul2(acca01, ii); o.y = mul2(acca23, ii);
+        *reinterpret_cast<ulonglong2*>(P.abar + row * (kH * kF) + 4 * lane) = o;
+      }
+    }
+    if (g == 0 && (t & 1) == 0) {
+      const int h0 = t >> 1, h1 = 2 + (t >> 1);
+      P.m[row * kH + h0] = (e > b) ? mA * kLn2 : 0.f;    // natural-log units
+      P.m[row * kH + h1] = (e > b) ? mB * kLn2 : 0.f;
+      P.z[row * kH + h0] = zA;
+      P.z[row * kH + h1] = zB;
+      P.sump[row * kH + h0] = lA / zA;
+      P.sump[row * kH + h1] = lB / zB;
+    }
+    b = e;
+  }
+}
+
+// ------------------------------------------------------------------ backward rows
+struct BwdArgs {
+  const float* q; int ldq;
+  const float* k; int ldk;
+  const float* v; int ldv;
+  const int32_t* rowptr; const int32_t* col;
+  int64_t num_rows;
+  const float* Wq; const float* bq; const float* Wk; const float* bk;
+  int scale_mode; float scale_value;
+  const float* m; const float* z;
+  const float* agg_v; const float* abar;
+  const float* d_agg_v; const float* d_abar;
+  float* dq; int lddq;
+  float* da;
+  float* Pbuf;   // [E, H]
+  float* G;      // [E, 2HD] = [dq_e | dk_e]
+  int rows_per_warp;
+};
+
+template <int kWarps>
+struct BwdSmem {
+  static constexpr int ring_off = 0;
+  static constexpr int frag1_off = kWarps * kRing * kChunkBytes;
+  static constexpr int frag2_off = frag1_off + kFragBytes;
+  static constexpr int bias_off = frag2_off + kFragBytes;
+  static constexpr int bar_off = bias_off + 128;
+  static constexpr int p_off = bar_off + kWarps * kRing * 8 + ((kWarps * kRing) & 1) * 8;
+  static constexpr int dp_off = p_off + kWarps * 32 * kH * 4;
+  static constexpr int total = dp_off + kWarps * 32 * kH * 4;
+};
+
+__global__ void __launch_bounds__(kBwdWarps * 32, 2)
+k_attn_bwd_tile(const __grid_constant__ CUtensorMap tmA, const BwdArgs P) {
+  using L = BwdSmem<kBwdWarps>;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  uint4* frag1 = reinterpret_cast<uint4*>(smem + L::frag1_off);
+  uint4* frag2 = reinterpret_cast<uint4*>(smem + L::frag2_off);
+  float* bias_s = reinterpret_cast<float*>(smem + L::bias_off);
+  float* p_s = reinterpret_cast<float*>(smem + L::p_off) + w * 32 * kH;
+  float* dp_s = reinterpret_cast<float*>(smem + L::dp_off) + w * 32 * kH;
+
+  build_frag1(frag1, P.Wq, P.Wk);
+  build_frag2(frag2, P.Wq, P.Wk);
+  build_bias(bias_s, P.Wq, P.bq, P.Wk, P.bk);
+  __syncthreads();
+
+  const int64_t gw = (int64_t)blockIdx.x * kBwdWarps + w;
+  const int64_t row0 = gw * P.rows_per_warp;
+  if (row0 >= P.num_rows) return;
+  const int64_t row1 = min(row0 + (int64_t)P.rows_per_warp, P.num_rows);
+
+  Ring ring;
+  ring.buf = smem + L::ring_off + w * (kRing * kChunkBytes);
+  ring.bar = reinterpret_cast<uint64_t*>(smem + L::bar_off) + w * kRing;
+  ring.tm = &tmA;
+  ring.lane = lane;
+  const int e_begin = P.rowptr[row0];
+  ring.init(e_begin, P.rowptr[row1]);
+
+  const bool has_dab = P.d_abar != nullptr && P.abar != nullptr;
+  const bool want_da = P.da != nullptr;
+  const int hb = lane >> 3;
+  const int j8 = lane & 7;
+  const float* vbase = P.v + 4 * lane;
+  const float* kbase = P.k + 2 * t;
+  const int hsl = (t & 1) * 2 + (t >> 1);   // head fed through k-slot t of the P . dAbar step
+
+  int b = e_begin;
+  for (int64_t row = row0; row < row1; ++row) {
+    const int e = P.rowptr[row + 1];
+    const float scale = fast::qk_scale_fast(P.scale_mode, P.scale_value, e - b);
+    float2 qA = *reinterpret_cast<const float2*>(P.q + row * P.ldq + 2 * t);
+    float2 qB = *reinterpret_cast<const float2*>(P.q + row * P.ldq + 8 + 2 * t);
+    qA.x *= scale; qA.y *= scale; qB.x *= scale; qB.y *= scale;
+    const int hA = t >> 1, hB = 2 + (t >> 1);
+    const float m2A = P.m[row * kH + hA] * kLog2e, m2B = P.m[row * kH + hB] * kLog2e;
+    const float ziA = 1.f / P.z[row * kH + hA], ziB = 1.f / P.z[row * kH + hB];
+    // accumulation layout operands of the row
+    const float4 dy = *reinterpret_cast<const float4*>(P.d_agg_v + row * kC + 4 * lane);
+    float4 dab = make_float4(0.f, 0.f, 0.f, 0.f);
+    float delta;   // <dY_h, agg_h> + <dAbar_h, abar_h> of head hb (= sum_e p_e dp_e)
+    {
+      const float4 ag = *reinterpret_cast<const float4*>(P.agg_v + row * kC + 4 * lane);
+      float part = dy.x * ag.x + dy.y * ag.y + dy.z * ag.z + dy.w * ag.w;
+      if (has_dab) {
+        dab = *reinterpret_cast<const float4*>(P.d_abar + row * (kH * kF) + 4 * lane);
+        const float4 ab = *reinterpret_cast<const float4*>(P.abar + row * (kH * kF) + 4 * lane);
+        part += dab.x * ab.x + dab.y * ab.y + dab.z * ab.z + dab.w * ab.w;
+      }
+      part += __shfl_xor_sync(kFull, part, 1);
+      part += __shfl_xor_sync(kFull, part, 2);
+      part += __shfl_xor_sync(kFull, part, 4);
+      delta = part;
+    }
+    const f32x2 dy01 = pack2(dy.x, dy.y), dy23 = pack2(dy.z, dy.w);
+    const f32x2 dab01 = pack2(dab.x, dab.y), dab23 = pack2(dab.z, dab.w);
+    // B fragment of the P . dAbar k-step: b0 = dAbar[row][head(k-slot t)][8nf + g], b1 = 0
+    uint32_t dbhi[4], dblo[4];
+#pragma unroll
+    for (int nf = 0; nf < 4; ++nf) {
+      const float x = has_dab ? P.d_abar[row * (kH * kF) + hsl * kF + 8 * nf + g] : 0.f;
+      split_tf32(__float_as_uint(x), dbhi[nf], dblo[nf]);
+    }
+    float dqacc[4] = {0.f, 0.f, 0.f, 0.f};   // dq[8nn + 2t + j], nn = 0,1
+
+    for (int tb = b; tb < e; tb += 32) {
+      const int n = min(32, e - tb);
+      const bool two = n > 16;
+      const int mycol = (lane < n) ? P.col[tb + lane] : 0;
+      float2 kA[4], kB[4];
+#pragma unroll
+      for (int idx = 0; idx < 4; ++idx) {
+        if (idx < 2 || two) {
+          const unsigned tc = (unsigned)__shfl_sync(kFull, mycol, 8 * idx + g);
+          const float* kp = kbase + (size_t)tc * (unsigned)P.ldk;
+          kA[idx] = ldg_stream2(kp);
+          kB[idx] = ldg_stream2(kp + 8);
+        }
+      }
+      const int prow = ring.prepare(tb - e_begin, n);
+      float acc[2][4][4];
+      rpe_tile(acc, ring.buf, prow, two, frag1, bias_s, lane);
+
+      // q_e, k_e in place (acc[m][0/1] = q_e heads A/B, acc[m][2/3] = k_e), p of my edges
+      float pA[4], pB[4];
+#pragma unroll
+      for (int idx = 0; idx < 4; ++idx) {
+        pA[idx] = 0.f; pB[idx] = 0.f;
+        if (idx < 2 || two) {
+          const int m = idx >> 1, hf = (idx & 1) * 2;
+          acc[m][0][hf] += qA.x; acc[m][0][hf + 1] += qA.y;
+          acc[m][1][hf] += qB.x; acc[m][1][hf + 1] += qB.y;
+          acc[m][2][hf] += kA[idx].x; acc[m][2][hf + 1] += kA[idx].y;
+          acc[m][3][hf] += kB[idx].x; acc[m][3][hf + 1] += kB[idx].y;
+          float pa = acc[m][0][hf] * acc[m][2][hf];
+          pa = fmaf(acc[m][0][hf + 1], acc[m][2][hf + 1], pa);
+          float pb = acc[m][1][hf] * acc[m][3][hf];
+          pb = fmaf(acc[m][1][hf + 1], acc[m][3][hf + 1], pb);
+          pa += __shfl_xor_sync(kFull, pa, 1);
+          pb += __shfl_xor_sync(kFull, pb, 1);
+          if (8 * idx + g < n) {
+            pA[idx] = ex2(fmaf(pa, kLog2e, -m2A)) * ziA;
+            pB[idx] = ex2(fmaf(pb, kLog2e, -m2B)) * ziB;
+          }
+          if ((t & 1) == 0) {
+            p_s[(8 * idx + g) * kH + hA] = pA[idx];
+            p_s[(8 * idx + g) * kH + hB] = pB[idx];
+            if (8 * idx + g < n) {
+              P.Pbuf[(size_t)(tb + 8 * idx + g) * kH + hA] = pA[idx];
+              P.Pbuf[(size_t)(tb + 8 * idx + g) * kH + hB] = pB[idx];
+            }
+          }
+        }
+      }
+      __syncwarp();
+
+      // dp - delta of every (edge, head): accumulation layout, 8 edges per butterfly
+      for (int e0 = 0; e0 < n; e0 += 8) {
+        float s[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          s[u] = 0.f;
+          if (e0 + u < n) {
+            const unsigned tc = (unsigned)__shfl_sync(kFull, mycol, e0 + u);
+            const float4 x = ldg_stream4(vbase + (size_t)tc * (unsigned)P.ldv);
+            f32x2 d2 = mul2(dy01, pack2(x.x, x.y));
+            fma2(d2, dy23, pack2(x.z, x.w));
+            if (has_dab) {
+              int r = prow + e0 + u;
+              if (r >= kRingSlots) r -= kRingSlots;
+              const ulonglong2 a4 = *reinterpret_cast<const ulonglong2*>(
+                  ring.buf + r * 128 + (((j8 ^ r) & 7) << 4));
+              fma2(d2, dab01, a4.x);
+              fma2(d2, dab23, a4.y);
+            }
+            s[u] = fast::hsum2(d2);
+          }
+        }
+        // transpose-reduce over the 8 lanes of a head: lane j8 ends with edge e0 + j8
+        float r4[4], r2[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float send = (j8 & 4) ? s[i] : s[i + 4];
+          const float keep = (j8 & 4) ? s[i + 4] : s[i];
+          r4[i] = keep + __shfl_xor_sync(kFull, send, 4);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float send = (j8 & 2) ? r4[i] : r4[i + 2];
+          const float keep = (j8 & 2) ? r4[i + 2] : r4[i];
+          r2[i] = keep + __shfl_xor_sync(kFull, send, 2);
+        }
+        const float send = (j8 & 1) ? r2[0] : r2[1];
+        const float keep = (j8 & 1) ? r2[1] : r2[0];
+        const float dp = keep + __shfl_xor_sync(kFull, send, 1);
+        dp_s[(e0 + j8) * kH + hb] = dp - delta;
+      }
+      __syncwarp();
+
+      // G = [dq_e | dk_e] in place: acc[m][0/1] <- dc * k_e, acc[m][2/3] <- dc * q_e
+      float pk[4];   // p of k-slot t of the P . dAbar step, per edge
+#pragma unroll
+      for (int idx = 0; idx < 4; ++idx) {
+        pk[idx] = 0.f;
+        if (idx < 2 || two) {
+          const int m = idx >> 1, hf = (idx & 1) * 2;
+          const bool valid = 8 * idx + g < n;
+          const float dA = valid ? pA[idx] * dp_s[(8 * idx + g) * kH + hA] : 0.f;
+          const float dB = valid ? pB[idx] * dp_s[(8 * idx + g) * kH + hB] : 0.f;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const float qa = acc[m][0][hf + j], ka = acc[m][2][hf + j];
+            const float qb = acc[m][1][hf + j], kb = acc[m][3][hf + j];
+            acc[m][0][hf + j] = valid ? dA * ka : 0.f;
+            acc[m][2][hf + j] = valid ? dA * qa : 0.f;
+            acc[m][1][hf + j] = valid ? dB * kb : 0.f;
+            acc[m][3][hf + j] = valid ? dB * qb : 0.f;
+          }
+          pk[idx] = (t & 1) ? pB[idx] : pA[idx];
+          if (valid) {
+            float* gp = P.G + (size_t)(tb + 8 * idx + g) * kHD2 + 2 * t;
+#pragma unroll
+            for (int nn = 0; nn < 4; ++nn)
+              *reinterpret_cast<float2*>(gp + 8 * nn) =
+                  make_float2(acc[m][nn][hf], acc[m][nn][hf + 1]);
+          }
+          dqacc[0] += acc[m][0][hf]; dqacc[1] += acc[m][0][hf + 1];
+          dqacc[2] += acc[m][1][hf]; dqacc[3] += acc[m][1][hf + 1];
+        }
+      }
+
+      if (want_da) {
+        // da = G . W + P . dAbar  (second tensor-core product; A = accumulator fragment)
+        float dacc[2][4][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+          for (int nf = 0; nf < 4; ++nf)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dacc[m][nf][i] = 0.f;
+        if (has_dab) {
+#pragma unroll
+          for (int m = 0; m < 2; ++m) {
+            if (m == 0 || two) {
+              uint32_t ahi[4], alo[4];
+              split_tf32(__float_as_uint(pk[2 * m]), ahi[0], alo[0]);
+              split_tf32(__float_as_uint(pk[2 * m + 1]), ahi[1], alo[1]);
+              ahi[2] = ahi[3] = alo[2] = alo[3] = 0u;
+#pragma unroll
+              for (int nf = 0; nf < 4; ++nf) {
+                mma_tf32(dacc[m][nf], alo, dbhi[nf], 0u);
+                mma_tf32(dacc[m][nf], ahi, dblo[nf], 0u);
+                mma_tf32(dacc[m][nf], ahi, dbhi[nf], 0u);
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+          for (int m = 0; m < 2; ++m) {
+            if (m == 0 || two) {
+              // k-slot s <-> output 8ks + 2s, slot 4 + s <-> 8ks + 2s + 1
+              split_tf32(__float_as_uint(acc[m][ks][0]), ahi[m][0], alo[m][0]);
+              split_tf32(__float_as_uint(acc[m][ks][2]), ahi[m][1], alo[m][1]);
+              split_tf32(__float_as_uint(acc[m][ks][1]), ahi[m][2], alo[m][2]);
+              split_tf32(__float_as_uint(acc[m][ks][3]), ahi[m][3], alo[m][3]);
+            }
+          }
+#pragma unroll
+          for (int nf = 0; nf < 4; ++nf) {
+            const uint4 bfr = frag2[(ks * 4 + nf) * 32 + lane];
+            mma_3x(dacc[0][nf], ahi[0], alo[0], bfr);
+            if (two) mma_3x(dacc[1][nf], ahi[1], alo[1], bfr);
+          }
+        }
+#pragma unroll
+        for (int idx = 0; idx < 4; ++idx) {
+          if ((idx < 2 || two) && 8 * idx + g < n) {
+            const int m = idx >> 1, hf = (idx & 1) * 2;
+            float* dp_ = P.da + (size_t)(tb + 8 * idx + g) * kF + 2 * t;
+#pragma unroll
+            for (int nf = 0; nf < 4; ++nf)
+              *reinterpret_cast<float2*>(dp_ + 8 * nf) =
+                  make_float2(dacc[m][nf][hf], dacc[m][nf][hf + 1]);
+          }
+        }
+      }
+    }
+
+    // dq of the row: reduce my 4 partial sums over the 8 row lanes (g)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float x = dqacc[i];
+      x += __shfl_xor_sync(kFull, x, 4);
+      x += __shfl_xor_sync(kFull, x, 8);
+      x += __shfl_xor_sync(kFull, x, 16);
+      dqacc[i] = x * scale;
+    }
+    if (g == 0) {
+      *reinterpret_cast<float2*>(P.dq + row * P.lddq + 2 * t) = make_float2(dqacc[0], dqacc[1]);
+      *reinterpret_cast<float2*>(P.dq + row * P.lddq + 8 + 2 * t) =
+          make_float2(dqacc[2], dqacc[3]);
+    }
+    b = e;
+  }
+}
+
+}  // namespace tile
+}  // namespace spt

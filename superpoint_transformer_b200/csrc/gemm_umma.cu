@@ -667,6 +667,11 @@ static bool make_map(CUtensorMap* tm, const float* ptr, int64_t rows, int64_t co
          CUDA_SUCCESS;
 }
 
+// exported for csrc/attention.cu: [rows, 32] fp32 matrix, boxes of `box_rows` x 32 columns
+bool make_map_rows32(CUtensorMap* tm, const float* ptr, int64_t rows, int64_t ld, int box_rows) {
+  return make_map(tm, ptr, rows, 32, ld, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 // layout the tensor-core path needs; otherwise the caller uses the mma.sync kernel
 bool shape_ok(const float* A, int64_t M, int64_t K, int64_t lda, const float* B, int64_t N,
               int64_t ldb, const float* C, int64_t ldc) {
