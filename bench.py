@@ -34,17 +34,51 @@ if ROOT not in sys.path:
 
 METRIC = "superpoints/sec (fwd+bwd) on 100k-SP 3-level NAG"
 UNIT = "superpoints/s"
-LEVELS = [100_000, 20_000, 4_000]
 MEAN_DEGREE = 16
 DIM, HEADS, QK_DIM, RPE_DIM, HF_DIM, NUM_CLASSES = 128, 4, 4, 32, 12, 13
-WORKLOAD = ("cfg2: S3DIS-shaped 3-level NAG 100k/20k/4k superpoints, sym. degree "
-            "~clamp(Poisson16,1,30)+self-loop, random node ids; nano-3 SPT C=128 H=4 "
-            "qk_dim=4 F=32 (h_edge_mlp 18->32->32, node_mlp 12->32->32), 3 blocks/down "
-            "level + 1 block/up level, k/q/v RPE, max-pool, GraphNorm, 13-class CE head, "
-            "AdamW step; fp32 (ieee matmul)")
+_MODEL = ("nano-3 SPT C=128 H=4 qk_dim=4 F=32 (h_edge_mlp 18->32->32, node_mlp 12->32->32), "
+          "3 blocks/down level + 1 block/up level, k/q/v RPE, max-pool, GraphNorm, 13-class CE "
+          "head, AdamW step; fp32 (ieee matmul)")
+_LAW = "sym. degree ~clamp(Poisson16,1,30)+self-loop, random node ids"
+
+# BASELINE.json configs.  cfg2 is the configuration the metric is quoted on
+# (the default, one scene per GPU: weak scaling).  cfg4 / cfg5 are the 8-GPU workloads: a fixed
+# set of scenes / tiles per step sharded over the ranks (strong scaling).
+BENCH_CONFIGS = {
+    'cfg2': dict(levels=[100_000, 20_000, 4_000], no_ffn=True, scaling='weak', seed=1,
+                 metric=METRIC,
+                 workload=f"cfg2: S3DIS-shaped 3-level NAG 100k/20k/4k superpoints, {_LAW}; "
+                          f"{_MODEL}"),
+    'cfg3': dict(levels=[500_000, 100_000, 20_000], no_ffn=True, scaling='weak', seed=2,
+                 metric="superpoints/sec (fwd+bwd) on 500k-SP 3-level NAG (DALES tile)",
+                 workload=f"cfg3: DALES-tile 3-level NAG 500k/100k/20k superpoints, {_LAW}; "
+                          f"{_MODEL}"),
+    'cfg4': dict(levels=[50_000, 10_000, 2_000], no_ffn=False, scaling='strong', seed=100,
+                 scenes=64, scenes_per_batch=8,
+                 metric="superpoints/sec (fwd+bwd), 64 scenes x 50k-SP 3-level NAGs per step",
+                 workload=f"cfg4: KITTI-360-scan stream, 64 independent scenes x 50k/10k/2k "
+                          f"superpoints per optimizer step (seeds 100..163), NAGBatch of 8 scenes "
+                          f"per micro-batch, scenes LPT-sharded over the ranks by edge count, "
+                          f"gradient accumulation + one NCCL all-reduce per step; {_LAW}; "
+                          f"{_MODEL} with FFN branch (no_ffn=False, ffn_ratio=1: "
+                          f"configs/experiment/semantic/kitti360.yaml:22-27)"),
+    'cfg5': dict(levels=[1_000_000, 200_000, 40_000], no_ffn=True, scaling='strong', seed=3,
+                 tiles=8,
+                 metric="superpoints/sec (fwd+bwd) on a 1M-SP 3-level graph in 8 tiles",
+                 workload=f"cfg5: SuperCluster-size graph 1M/200k/40k superpoints cut into 8 "
+                          f"tiles by level-3 ancestor (spatial stripes balanced by edge count), "
+                          f"spatially coherent synthetic graph (neighbours close along x), cross-tile edges dropped (reference SampleXYTiling, "
+                          f"src/transforms/sampling.py:471), tiles LPT-sharded over the ranks, "
+                          f"one NCCL all-reduce per step; {_LAW}; {_MODEL}"),
+}
+# not a BASELINE configuration: a 2k-superpoint scene for the CPU tests of this script
+BENCH_CONFIGS['tiny'] = dict(levels=[2_000, 400, 80], no_ffn=True, scaling='weak', seed=1,
+                             metric=METRIC, workload=f"tiny: 2k/400/80 superpoints (test only); {_MODEL}")
+LEVELS = BENCH_CONFIGS['cfg2']['levels']
+WORKLOAD = BENCH_CONFIGS['cfg2']['workload']
 
 
-def model_kwargs(S):
+def model_kwargs(S=None, no_ffn=True):
     inj = 3 + 1 + 32
     return dict(
         nano=True, segment_hf=['hf'], down_dim=[DIM] * 3,
@@ -52,8 +86,20 @@ def model_kwargs(S):
         down_num_heads=HEADS, down_num_blocks=3, down_ffn_ratio=1, up_dim=[DIM] * 2,
         up_in_mlp=[[inj + 2 * DIM, DIM, DIM], [inj + 2 * DIM, DIM, DIM]], up_num_heads=HEADS,
         up_num_blocks=1, node_mlp=[HF_DIM, 32, 32], h_edge_mlp=[18, RPE_DIM, RPE_DIM],
-        qk_dim=QK_DIM, in_rpe_dim=RPE_DIM, k_rpe=True, q_rpe=True, v_rpe=True, no_ffn=True,
+        qk_dim=QK_DIM, in_rpe_dim=RPE_DIM, k_rpe=True, q_rpe=True, v_rpe=True, no_ffn=no_ffn,
         use_diameter_parent=True, pool='max')
+
+
+def bench_config(cfg_name, world):
+    """the `config` object of the JSON line: identical for the own and the reference arm"""
+    c = BENCH_CONFIGS[cfg_name]
+    par = (f"scene-shard dp{world} (one scene per GPU, flat NCCL grad all-reduce)"
+           if c['scaling'] == 'weak' else
+           f"scene/tile-shard dp{world} (fixed work per step split over the ranks by edge "
+           f"count, flat NCCL grad all-reduce)")
+    return {"workload": c['workload'], "name": cfg_name, "levels": c['levels'],
+            "parallelism": par,
+            "l2": "inputs_exceed_l2 (per-step working set > 126 MB; no flush needed)"}
 
 
 # --------------------------------------------------------------------------- #
@@ -111,24 +157,142 @@ class ClockSampler:
 # --------------------------------------------------------------------------- #
 #  workload
 # --------------------------------------------------------------------------- #
-def host_scene(levels, seed):
-    """compact host-side NAG as the reference ships it to the device (trimmed graph,
-    fp16 raw edge attributes: configs/datamodule/semantic/default.yaml:40-42), pinned."""
-    from superpoint_transformer_b200.synthetic import make_nag
-    nag = make_nag(levels, mean_degree=MEAN_DEGREE, seed=seed)
+def _pin(nag, labels):
+    """fp16 raw edge attributes (configs/datamodule/semantic/default.yaml:40-42), pinned"""
     nbytes = 0
     for d in nag:
-        d.edge_attr = d.edge_attr.half()
+        if d.edge_attr is not None and d.edge_attr.dtype != torch.float16:
+            d.edge_attr = d.edge_attr.half()
         d.sub = None  # rebuilt on device from super_index (bit-exact, tests)
         for k in d.keys:
             v = d[k]
             if torch.is_tensor(v):
                 d[k] = v.pin_memory()
                 nbytes += v.numel() * v.element_size()
-    labels = torch.randint(0, NUM_CLASSES, (levels[0],),
-                           generator=torch.Generator().manual_seed(seed + 7)).pin_memory()
+    labels = labels.pin_memory()
     nbytes += labels.numel() * 8
     return nag, labels, nbytes
+
+
+def scene_labels(n1, seed):
+    return torch.randint(0, NUM_CLASSES, (n1,), generator=torch.Generator().manual_seed(seed + 7))
+
+
+def host_scene(levels, seed):
+    """compact host-side NAG as the reference ships it to the device (trimmed graph,
+    fp16 raw edge attributes), pinned."""
+    from superpoint_transformer_b200.synthetic import make_nag
+    nag = make_nag(levels, mean_degree=MEAN_DEGREE, seed=seed)
+    return _pin(nag, scene_labels(levels[0], seed))
+
+
+def cut_tiles(nag, num_tiles):
+    """Cut a NAG into `num_tiles` independent NAGs by top-level ancestor (cfg 5): the top-level
+    nodes are sorted along x and split into stripes of equal level-1 EDGE count; every lower
+    node follows its ancestor, edges whose ends fall into different tiles are dropped (the
+    reference tiles at preprocessing and treats tiles as independent samples,
+    src/transforms/sampling.py:471).  Host-side, once (outside every timed region).  Returns
+    (tiles, kept_edge_fraction)."""
+    import numpy as np
+    from superpoint_transformer_b200.data import Data, NAG, Cluster
+    levels = list(nag.level_range)
+    top = levels[-1]
+    # ancestor of every node at the top level
+    anc = {top: torch.arange(nag[top].num_nodes)}
+    for l in reversed(levels[:-1]):
+        anc[l] = anc[l + 1][nag[l].super_index]
+    # level-1 edges per top-level ancestor (of the source node) -> balanced x-stripes
+    l1 = levels[0]
+    e_per_top = torch.bincount(anc[l1][nag[l1].edge_index[0]], minlength=nag[top].num_nodes)
+    order = torch.argsort(nag[top].pos[:, 0])
+    csum = torch.cumsum(e_per_top[order].double(), 0)
+    tile_of_sorted = torch.clamp((csum / csum[-1] * num_tiles).long(), max=num_tiles - 1)
+    tile_top = torch.empty_like(tile_of_sorted)
+    tile_top[order] = tile_of_sorted
+    tiles, kept, total = [], 0, 0
+    for tl in range(num_tiles):
+        datas, new_id = [], {}
+        for l in levels:
+            keep = tile_top[anc[l]] == tl
+            idx = torch.nonzero(keep).view(-1)
+            nid = torch.full((nag[l].num_nodes,), -1, dtype=torch.long)
+            nid[idx] = torch.arange(idx.numel())
+            new_id[l] = nid
+        for l in levels:
+            d, nid = nag[l], new_id[l]
+            idx = torch.nonzero(nid >= 0).view(-1)
+            out = {}
+            for k in d.keys:
+                v = d[k]
+                if k in ('edge_index', 'edge_attr', 'super_index', 'sub') or not torch.is_tensor(v):
+                    continue
+                out[k] = v[idx]
+            ei = d.edge_index
+            ek = (nid[ei[0]] >= 0) & (nid[ei[1]] >= 0)
+            out['edge_index'] = nid[ei[:, ek]]
+            out['edge_attr'] = d.edge_attr[ek]
+            if l == l1:
+                kept += int(ek.sum()); total += int((nid[ei[0]] >= 0).sum())
+            if d.super_index is not None:
+                out['super_index'] = new_id[l + 1][d.super_index[idx]]
+            datas.append(Data(**out))
+        for i in range(1, len(datas)):
+            datas[i].sub = Cluster.from_super_index(datas[i - 1].super_index, datas[i].num_nodes)
+        tiles.append(NAG(datas, start_i_level=nag.start_i_level))
+    return tiles, kept / max(total, 1)
+
+
+def rank_micro_batches(cfg_name, rank, world):
+    """Host-side inputs of this rank for one step: list of (pinned NAG, labels, bytes, n1, E1)
+    micro-batches + a description of the sharding (per-rank edge totals)."""
+    from superpoint_transformer_b200.synthetic import make_nag
+    from superpoint_transformer_b200.distributed import shard_indices
+    from superpoint_transformer_b200.data import NAGBatch
+    c = BENCH_CONFIGS[cfg_name]
+    if c['scaling'] == 'weak':
+        nag, labels, nb = host_scene(c['levels'], seed=c['seed'] + rank)
+        return [(nag, labels, nb, c['levels'][0])], None
+    if cfg_name == 'cfg4':
+        seeds = [c['seed'] + i for i in range(c['scenes'])]
+        # every rank generates all scenes (deterministic in the seed, ~0.2 s each, setup only),
+        # so all ranks derive the same LPT assignment by level-1 edge count without talking
+        allsc = [make_nag(c['levels'], mean_degree=MEAN_DEGREE, seed=sd) for sd in seeds]
+        weights = [float(sc[1].edge_index.shape[1]) for sc in allsc]
+        mine = shard_indices(len(seeds), rank, world, weights=weights)
+        per_rank = [sum(weights[i] for i in shard_indices(len(seeds), r, world, weights=weights))
+                    for r in range(world)]
+        scenes = [allsc[i] for i in mine]
+        del allsc
+        e_mine = sum(int(sc[1].edge_index.shape[1]) for sc in scenes)
+        out = []
+        spb = c['scenes_per_batch']
+        for j in range(0, len(scenes), spb):
+            group = scenes[j:j + spb]
+            labels = torch.cat([scene_labels(c['levels'][0], seeds[mine[j + i]])
+                                for i in range(len(group))])
+            batch = NAGBatch.from_nag_list(group) if len(group) > 1 else group[0]
+            nag, labels, nb = _pin(batch, labels)
+            out.append((nag, labels, nb, c['levels'][0] * len(group)))
+        return out, dict(items=len(seeds), mine=len(mine), trimmed_edges_level1_mine=e_mine,
+                         edges_per_rank=[int(x) for x in per_rank],
+                         imbalance_max_over_mean=round(max(per_rank) * world / sum(per_rank), 4))
+    if cfg_name == 'cfg5':
+        full = make_nag(c['levels'], mean_degree=MEAN_DEGREE, seed=c['seed'], spatial=True)
+        tiles, kept = cut_tiles(full, c['tiles'])
+        w = [float(t[1].edge_index.shape[1]) for t in tiles]
+        mine = shard_indices(len(tiles), rank, world, weights=w)
+        per_rank = [sum(w[i] for i in shard_indices(len(tiles), r, world, weights=w))
+                    for r in range(world)]
+        out = []
+        for i in mine:
+            n1 = tiles[i][1].num_nodes
+            nag, labels, nb = _pin(tiles[i], scene_labels(n1, c['seed'] + 31 * i))
+            out.append((nag, labels, nb, n1))
+        return out, dict(items=len(tiles), mine=len(mine), kept_edge_fraction=round(kept, 4),
+                         trimmed_edges_level1_per_tile=[int(x) for x in w],
+                         edges_per_rank=[int(x) for x in per_rank],
+                         imbalance_max_over_mean=round(max(per_rank) * world / sum(per_rank), 4))
+    raise ValueError(cfg_name)
 
 
 def device_transforms(S, nag):
@@ -159,8 +323,25 @@ def attn_bytes(tag, m, elt=4, idx=4):
 
 
 def kernel_bytes(tag, m):
+    """algorithmic bytes per launch: every input / output tensor once"""
     if tag.startswith('gemm'):   # A [M,K] + W [N,K] + C [M,N] once each (dW: A, B in, C out)
         return (m['M'] * m['K'] + m['N'] * m['K'] + m['M'] * m['N']) * 4
+    if tag == 'graphnorm_fwd':   # x read for the statistics, x read + y written by the apply
+        return 3 * m['N'] * m['C'] * 4
+    if tag == 'graphnorm_bwd':   # x, dy (+ saved activation) read twice, dx written
+        return (5 + (2 if m.get('act') else 0)) * m['N'] * m['C'] * 4
+    if tag == 'segment_pool_fwd':
+        return (m['Nc'] + m['Np'] * (2 if m['r'] >= 2 else 1)) * m['C'] * 4 + (m['Np'] + m['Nc']) * 4
+    if tag == 'segment_pool_bwd':
+        return (m['Nc'] + m['Np'] * (2 if m['r'] >= 2 else 1)) * m['C'] * 4 + m['Nc'] * 8
+    if tag == 'gather_rows':
+        return 2 * m['n'] * m['C'] * 4 + m['n'] * 4
+    if tag == 'group_index':
+        return m['n'] * (8 + 4 + (12 if m.get('other') else 0)) + (m['G'] + 1) * 4
+    if tag == 'edge_features':
+        return m['Eh'] * (16 + 28) + (2 * m['Eh'] + (m['N'] if m.get('loops') else 0)) * (16 + 72)
+    if tag == 'unitsphere':
+        return m['N'] * (12 + 12 + 4 + 8) + m['Np'] * 16
     return attn_bytes(tag, m)
 
 
@@ -173,6 +354,8 @@ def run_own(args):
 
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py (own arm) needs a CUDA device; there is no CPU fallback")
+    cfg_name = args.config
+    cfg = BENCH_CONFIGS[cfg_name]
     rank, world, local = init_process_group_from_env()
     dev = torch.device('cuda', local)
     torch.cuda.set_device(dev)
@@ -180,7 +363,8 @@ def run_own(args):
     torch.backends.cudnn.allow_tf32 = False
     torch.manual_seed(0)
 
-    net = S.SPT(mlp_norm=S.nn.GraphNorm, norm=S.nn.GraphNorm, **model_kwargs(S))
+    net = S.SPT(mlp_norm=S.nn.GraphNorm, norm=S.nn.GraphNorm,
+                **model_kwargs(S, no_ffn=cfg['no_ffn']))
     net.apply(S.init_weights)
     head = S.nn.Classifier(DIM, NUM_CLASSES)
     model = torch.nn.ModuleDict(dict(net=net, head=head)).to(dev)
@@ -189,55 +373,45 @@ def run_own(args):
     opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=1e-4, fused=True,
                             capturable=not args.no_graph)
 
-    host_nag, host_labels, h2d_bytes = host_scene(LEVELS, seed=1 + rank)
-    n1 = LEVELS[0]
+    # this rank's share of one step: a list of micro-batches (host side, pinned)
+    micro, shard_info = rank_micro_batches(cfg_name, rank, world)
+    n_mb = len(micro)
+    sp_rank = sum(m[3] for m in micro)                  # level-1 superpoints per step, this rank
+    h2d_bytes = sum(m[2] for m in micro)
+    sp_total = torch.tensor([float(sp_rank)], device=dev)
+    if world > 1:
+        dist.all_reduce(sp_total)
+    sp_total = float(sp_total.item())
+    # every micro-batch is averaged over the GLOBAL number of superpoints of the step, so the
+    # accumulated gradient is the gradient of the mean loss of the whole step
+    loss_scale = [m[3] / sp_total * world for m in micro]   # all_reduce divides by world
 
-    def fwd_bwd(nag, labels):
+    def fwd_bwd(nag, labels, i_mb):
         flat.release()
         out = net(nag)
         loss = torch.nn.functional.cross_entropy(head(out), labels)
-        loss.backward()
-        flat.collect()
+        (loss * loss_scale[i_mb] if (n_mb > 1 or world > 1) else loss).backward()
+        flat.collect(accumulate=i_mb > 0)
         return loss
 
-    def step(nag, labels):
-        loss = fwd_bwd(nag, labels)
-        flat.all_reduce()
-        opt.step()
-        return loss
+    class Graphed:
+        """A callable captured as a CUDA graph after two eager warm-up runs on a side stream."""
 
-    class GraphedStep:
-        """fwd+bwd and the optimizer step captured as two CUDA graphs (the NCCL
-        gradient all-reduce stays between them, eager).  The launch-bound inner loop
-        (~800 kernels / step) replays without Python or driver launch overhead."""
-
-        def __init__(self, body):
-            self.loss = None
+        def __init__(self, body, pool=None):
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(2):
                     body()
-                    flat.all_reduce()
-                    opt.step()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            self.g1 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g1):
-                self.loss = body()
-            self.g2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g2):
-                opt.step()
+            self.g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g, pool=pool):
+                self.out = body()
 
         def __call__(self):
-            self.g1.replay()
-            flat.all_reduce()
-            self.g2.replay()
-            return self.loss
-
-    def fresh_device_nag():
-        nag = host_nag.to(dev, non_blocking=True)
-        return device_transforms(S, nag), host_labels.to(dev, non_blocking=True)
+            self.g.replay()
+            return self.out
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -261,34 +435,61 @@ def run_own(args):
         return ms.item(), t0, t1
 
     # ---- resident-input phase ------------------------------------------------
-    res_nag, res_labels = fresh_device_nag()
-    base = {l: (res_nag[l].x, res_nag[l].edge_attr, res_nag[l]['hf']) for l in res_nag.level_range}
+    resident = []
+    for nag_h, lab_h, _, _ in micro:
+        nag = device_transforms(S, nag_h.to(dev, non_blocking=True))
+        lab = lab_h.to(dev, non_blocking=True)
+        base = {l: (nag[l].x, nag[l].edge_attr, nag[l]['hf']) for l in nag.level_range}
+        resident.append((nag, lab, base))
+    edges_l1 = int(sum(r[0][1].edge_index.shape[1] for r in resident))
 
-    def resident_step():
+    def restore(i):
         # SPT.forward rewrites x / edge_attr / hf on the NAG: restore the inputs (no copy)
+        nag, _, base = resident[i]
         for l, (x, ea, hf) in base.items():
-            d = res_nag[l]
+            d = nag[l]
             d.x, d.edge_attr, d['hf'] = x, ea, hf
             d.diameter = None
-        return step(res_nag, res_labels)
 
-    # CUDA graphs are captured first (their own warm-up runs on the capture stream, before
-    # any eager step creates autograd nodes on the default stream)
-    graph_mode, run_resident = False, resident_step
+    def eager_step():
+        loss = None
+        for i in range(n_mb):
+            restore(i)
+            loss = fwd_bwd(resident[i][0], resident[i][1], i)
+        flat.all_reduce()
+        opt.step()
+        return loss
+
+    # parity of the timed path: loss of the untouched model on micro-batch 0 (compared with
+    # the CPU oracle's loss on the same scene, same parameters, below)
+    with torch.no_grad():
+        restore(0)
+        loss0_gpu = float(torch.nn.functional.cross_entropy(
+            head(net(resident[0][0])), resident[0][1]).item())
+
+    graph_mode, run_resident = False, eager_step
     if not args.no_graph:
         try:
-            def body():
-                for l, (x, ea, hf) in base.items():
-                    d = res_nag[l]
-                    d.x, d.edge_attr, d['hf'] = x, ea, hf
-                    d.diameter = None
-                return fwd_bwd(res_nag, res_labels)
-            run_resident = GraphedStep(body)
+            pool = torch.cuda.graph_pool_handle()
+            graphs = []
+            for i in range(n_mb):
+                def body(i=i):
+                    restore(i)
+                    return fwd_bwd(resident[i][0], resident[i][1], i)
+                graphs.append(Graphed(body, pool=pool))
+            g_opt = Graphed(lambda: opt.step(), pool=pool)
+
+            def run_resident():   # noqa: F811
+                for gph in graphs:
+                    loss = gph()
+                flat.all_reduce()
+                g_opt()
+                return loss
             graph_mode = True
         except Exception as ex:  # noqa: BLE001
             sys.stderr.write(f"[bench] CUDA graph capture failed, running eager: {ex!r}\n")
             torch.cuda.synchronize()
-            run_resident = resident_step
+            run_resident = eager_step
     for _ in range(args.warmup):
         run_resident()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -300,18 +501,18 @@ def run_own(args):
     # count my launches per step and time my kernels with CUDA events (eager steps: the
     # same kernels on the same inputs; events cannot be read back from a graph replay)
     for _ in range(2):
-        resident_step()
+        eager_step()
     ops.enable_event_timing(True)
     l0 = ops.launch_count()
     n_evt_steps = 3
-    ms_eager, _, _ = timed(resident_step, n_evt_steps)
+    ms_eager, _, _ = timed(eager_step, n_evt_steps)
     launches_per_step = (ops.launch_count() - l0) // n_evt_steps
     records = ops.timing_records()
     ops.enable_event_timing(False)
     ms_eager_step = ms_eager / n_evt_steps
     launches = launches_per_step * args.steps
     ms_per_step = ms / args.steps
-    value = world * n1 / (ms_per_step * 1e-3)
+    value = sp_total / (ms_per_step * 1e-3)
 
     # ---- per-kernel roofline from the live events ------------------------------
     peaks = {}
@@ -323,11 +524,11 @@ def run_own(args):
         if 'hbm_gbs' in peaks else (6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)')
     agg = {}
     for tag, meta, s, e in records:
-        size = meta.get('E', meta.get('M'))
+        size = meta.get('E', meta.get('M', meta.get('N', meta.get('Nc', meta.get('n')))))
         shape = f"E={meta['E']},rows={meta['R']}" if 'E' in meta else \
-            f"M={meta['M']},N={meta['N']},K={meta['K']}"
+            ','.join(f"{k}={v}" for k, v in meta.items())
         key = (tag, shape)
-        a = agg.setdefault(key, dict(tag=tag, E=size, R=shape, ms=0.0, n=0,
+        a = agg.setdefault(key, dict(tag=tag, E=size, R=shape, ms=0.0, n=0, meta=meta,
                                      bytes=kernel_bytes(tag, meta)))
         a['ms'] += s.elapsed_time(e)
         a['n'] += 1
@@ -340,10 +541,29 @@ def run_own(args):
                             algorithmic_MB=round(a['bytes'] / 1e6, 2),
                             achieved_GBs=round(gbs, 1), frac=round(gbs / peak_gbs, 4)))
     kernels.sort(key=lambda k: -k['share_of_step'])
+    own_share = round(sum(k['share_of_step'] for k in kernels), 4)
+    # SURVEY §8(d) block formula for the attention core (fwd + bwd rows + bwd targets of the
+    # largest level): (5NC + 3EF) elt + 2((N+1)+2E) idx + 2NH 4, over the summed launch times
+    survey = None
+    big = [a for a in agg.values() if a['tag'] in ('attn_fwd', 'attn_bwd_rows', 'attn_bwd_targets')]
+    if big:
+        emax = max(a['E'] for a in big)
+        grp = [a for a in big if a['E'] == emax]
+        if len(grp) == 3:
+            m0 = grp[0]['meta']
+            N_, E_, C_, F_, H_ = m0['R'], m0['E'], m0['H'] * m0['Dv'], m0['F'], m0['H']
+            bytes_d = (5 * N_ * C_ + 3 * E_ * F_) * 4 + 2 * ((N_ + 1) + 2 * E_) * 4 + 2 * N_ * H_ * 4
+            t_ms = sum(a['ms'] / a['n'] for a in grp)
+            survey = dict(formula="SURVEY §8(d): 5NC*4 + 3EF*4 + 2((N+1)+2E)*4 + 2NH*4 over "
+                                  "attn_fwd + attn_bwd_rows (incl. the dW product) + attn_bwd_targets",
+                          rows=N_, edges=E_, algorithmic_bytes=int(bytes_d),
+                          ms=round(t_ms, 4), achieved_GBs=round(bytes_d / t_ms / 1e6, 1),
+                          frac=round(bytes_d / t_ms / 1e6 / peak_gbs, 4))
     if args.kernels_out and rank == 0:
         with open(args.kernels_out, 'w') as fh:
-            json.dump(dict(eager_ms_per_step=ms_eager_step, steps=n_evt_steps, kernels=kernels),
-                      fh, indent=1)
+            json.dump(dict(eager_ms_per_step=ms_eager_step, steps=n_evt_steps,
+                           own_kernel_share_of_eager_step=own_share, attention_block=survey,
+                           kernels=kernels), fh, indent=1)
     roofline = None
     if kernels:
         top = kernels[0]
@@ -357,110 +577,121 @@ def run_own(args):
                         achieved=top['achieved_GBs'], peak=peak_gbs, unit='GB/s',
                         frac=top['frac'], traffic=traffic, peak_source=peak_src,
                         algorithmic_bytes=int(top['algorithmic_MB'] * 1e6),
-                        avg_launch_ms=top['avg_ms'], share_of_step=top['share_of_step'])
+                        avg_launch_ms=top['avg_ms'], share_of_step=top['share_of_step'],
+                        attention_block_survey_8d=survey)
 
     # ---- end-to-end phase: host buffers every step -------------------------------
+    def fresh(i):
+        nag = micro[i][0].to(dev, non_blocking=True)
+        return device_transforms(S, nag), micro[i][1].to(dev, non_blocking=True)
+
     def e2e_step():
-        nag, labels = fresh_device_nag()
-        loss = step(nag, labels)
+        loss = None
+        for i in range(n_mb):
+            nag, labels = fresh(i)
+            loss = fwd_bwd(nag, labels, i)
+        flat.all_reduce()
+        opt.step()
         return float(loss.item())  # D2H read of the step's result
 
     e2e_graph = False
     e2e_h2d = "eager: one pinned->device copy per tensor on the compute stream"
     if graph_mode:
-        def make_static_set():
-            # static device input buffers + the graphs (transforms + CSR build + fwd + bwd | step)
-            snag = host_nag.to(dev)
-            slab = host_labels.to(dev)
+        def make_static_set(i, pool):
+            # static device input buffers + the graph (transforms + CSR build + fwd + bwd)
+            snag = micro[i][0].to(dev)
+            slab = micro[i][1].to(dev)
             pairs = []
-            for l in host_nag.level_range:
-                hd, sd_ = host_nag[l], snag[l]
+            for l in micro[i][0].level_range:
+                hd, sd_ = micro[i][0][l], snag[l]
                 for k in hd.keys:
                     if torch.is_tensor(hd[k]):
                         pairs.append((sd_[k], hd[k]))
-            pairs.append((slab, host_labels))
+            pairs.append((slab, micro[i][1]))
 
             def body():
-                nag = snag.clone()
-                nag = device_transforms(S, nag)
-                return fwd_bwd(nag, slab)
-            return pairs, GraphedStep(body)
+                nag = device_transforms(S, snag.clone())
+                return fwd_bwd(nag, slab, i)
+            return pairs, Graphed(body, pool=pool)
 
         try:
-            # double-buffered inputs: while step i replays on the compute stream, the pinned-memory
-            # H2D copy of step i+1's inputs runs on a copy stream into the other buffer set.
-            # Every step still uploads its 43 MB and reads its loss back.
-            sets = [make_static_set(), make_static_set()]
+            # inputs are double-buffered: while micro-batch j replays on the compute stream the
+            # pinned-memory H2D copy of the NEXT one runs on a copy stream into its own buffer
+            # set.  Every step still uploads all its inputs and reads its loss back.
+            pool2 = torch.cuda.graph_pool_handle()
+            slots = [make_static_set(i, pool2) for i in range(n_mb)]
+            if n_mb == 1:
+                slots.append(make_static_set(0, pool2))   # second buffer set of the same scene
             copy_stream = torch.cuda.Stream()
-            h2d_done = [torch.cuda.Event(), torch.cuda.Event()]
-            state = {'i': 0}
+            h2d_done = [torch.cuda.Event() for _ in slots]
+            state = {'j': 0}
 
-            def enqueue_h2d(b):
-                # the graph that last read buffer set b is already enqueued on the compute stream
+            def enqueue_h2d(sl):
+                # the graph that last read slot sl is already enqueued on the compute stream
                 copy_stream.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(copy_stream):
-                    for dst, src in sets[b][0]:
+                    for dst, src in slots[sl][0]:
                         dst.copy_(src, non_blocking=True)
-                    h2d_done[b].record(copy_stream)
+                    h2d_done[sl].record(copy_stream)
 
             enqueue_h2d(0)
 
             def e2e_step():  # noqa: F811
-                b = state['i'] & 1
-                enqueue_h2d(1 - b)
-                torch.cuda.current_stream().wait_event(h2d_done[b])
-                loss = sets[b][1]()
-                state['i'] += 1
+                loss = None
+                for _ in range(n_mb):
+                    sl = state['j'] % len(slots)
+                    enqueue_h2d((sl + 1) % len(slots))
+                    torch.cuda.current_stream().wait_event(h2d_done[sl])
+                    loss = slots[sl][1]()
+                    state['j'] += 1
+                flat.all_reduce()
+                g_opt()
                 return float(loss.item())
             e2e_step()
             e2e_graph = True
-            e2e_h2d = ("double-buffered: the pinned->device copy of step i+1 overlaps the compute "
-                       "of step i (copy stream), every step uploads all inputs")
+            e2e_h2d = ("double-buffered: the pinned->device copy of the next micro-batch overlaps "
+                       "the compute of the current one (copy stream), every step uploads all inputs")
         except Exception as ex:  # noqa: BLE001
-            sys.stderr.write(f"[bench] pipelined e2e failed ({ex!r}); single-buffer graphs\n")
+            sys.stderr.write(f"[bench] pipelined e2e failed ({ex!r}); eager e2e\n")
             torch.cuda.synchronize()
-            try:
-                pairs, e2e_graphed = make_static_set()
-
-                def e2e_step():  # noqa: F811
-                    for dst, src in pairs:
-                        dst.copy_(src, non_blocking=True)
-                    loss = e2e_graphed()
-                    return float(loss.item())
-                e2e_graph = True
-                e2e_h2d = "single buffer: H2D copies on the compute stream before each replay"
-            except Exception as ex2:  # noqa: BLE001
-                sys.stderr.write(f"[bench] e2e CUDA graph capture failed, running eager: {ex2!r}\n")
-                torch.cuda.synchronize()
 
     for _ in range(max(1, min(args.warmup, 3))):
         e2e_step()
     e2e_steps = args.steps
     ms_e2e, _, _ = timed(e2e_step, e2e_steps)
-    e2e_value = world * n1 / (ms_e2e / e2e_steps * 1e-3)
+    e2e_value = sp_total / (ms_e2e / e2e_steps * 1e-3)
 
     # ---- CPU baseline (oracle port, rank 0, N=1 only) ----------------------------
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference_sample(target_seconds=20.0)
+        cpu = cpu_reference_sample(cfg_name, target_seconds=20.0)
+        if cpu.get('loss') is not None and cpu.get('same_scene'):
+            parity = {"loss_gpu": loss0_gpu, "loss_cpu_oracle": cpu['loss'],
+                      "abs_diff": abs(loss0_gpu - cpu['loss']),
+                      "what": "cross-entropy of the untouched model on the step's first "
+                              "micro-batch: CUDA path vs oracle/path.py on the host (same seed, "
+                              "same parameters, same fp16-rounded raw edge attributes)"}
 
     if rank == 0:
+        config = bench_config(cfg_name, world)
         line = {
-            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world,
+            "metric": cfg['metric'], "value": round(value, 1), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD, "superpoints_per_rank": n1,
-                       "edges_level1": int(res_nag[1].edge_index.shape[1]),
-                       "parallelism": f"scene-shard dp{world} (one scene per GPU, flat NCCL "
-                                      f"grad all-reduce)",
-                       "l2": "inputs_exceed_l2 (per-step working set > 126 MB; no flush needed)",
-                       "cuda_graph": {"value": graph_mode, "e2e": e2e_graph,
-                                      "eager_ms_per_step": round(ms_eager_step, 4)},
-                       "matmul": "fp32-accurate 3xTF32 on tcgen05 tensor cores, TMEM accumulators, TMA (csrc/gemm_umma.cu)",
-                       "csr": "graph CSR cached across steps in `value` (amortised, SURVEY §8d); "
-                              "rebuilt every step in `e2e`; on-the-fly edges emitted in CSR order "
-                              "(OnTheFlyHorizontalEdgeFeatures(csr_order=True))"},
+            "higher_is_better": True, "scaling": cfg['scaling'], "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": config,
+            "exec": {"superpoints_per_step": int(sp_total), "superpoints_this_rank": int(sp_rank),
+                     "micro_batches_this_rank": n_mb, "edges_level1_this_rank": edges_l1,
+                     "sharding": shard_info,
+                     "cuda_graph": {"value": graph_mode, "e2e": e2e_graph,
+                                    "eager_ms_per_step": round(ms_eager_step, 4)},
+                     "own_kernel_share_of_eager_step": own_share,
+                     "matmul": "fp32-accurate 3xTF32 on tcgen05 tensor cores, TMEM accumulators, "
+                               "TMA (csrc/gemm_umma.cu)",
+                     "csr": "graph CSR cached across steps in `value` (amortised, SURVEY §8d); "
+                            "rebuilt every step in `e2e`; on-the-fly edges emitted in CSR order "
+                            "(OnTheFlyHorizontalEdgeFeatures(csr_order=True))"},
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT,
                     "ms_per_step": round(ms_e2e / e2e_steps, 4),
@@ -468,8 +699,9 @@ def run_own(args):
                     "h2d": e2e_h2d},
             "gpu_launches": int(launches),
             "roofline": roofline,
-            "kernels": kernels[:8],
+            "kernels": kernels[:10],
             "cpu_baseline": cpu,
+            "parity": parity,
         }
         print(json.dumps(line))
     if world > 1:
@@ -481,15 +713,16 @@ def run_own(args):
 #  CPU reference (oracle port)
 # --------------------------------------------------------------------------- #
 def _cpu_scene(levels, seed):
-    """same generator + the oracle's CPU transforms -> NAG ready for spt_forward"""
+    """same generator + the oracle's CPU transforms -> NAG ready for spt_forward (raw edge
+    attributes rounded through fp16 exactly like the device path's host buffers)"""
     from oracle import path as P
     from superpoint_transformer_b200.synthetic import make_nag
     nag = make_nag(levels, mean_degree=MEAN_DEGREE, seed=seed)
     size = nag[1].node_size
     for l in nag.level_range:
         d = nag[l]
-        ei, ea = P.horizontal_edge_features(d.edge_index, d.edge_attr, d.pos, d.normal,
-                                            d['log_length'], d['log_surface'],
+        ei, ea = P.horizontal_edge_features(d.edge_index, d.edge_attr.half().float(), d.pos,
+                                            d.normal, d['log_length'], d['log_surface'],
                                             d['log_volume'], d['log_size'])
         d.edge_index, d.edge_attr = P.add_self_loops(ei, ea, d.num_nodes)
         if l > 1:
@@ -499,12 +732,12 @@ def _cpu_scene(levels, seed):
     return nag
 
 
-def _cpu_state_dict():
+def _cpu_state_dict(no_ffn=True):
     """random-init parameters with the reference key names (built from the product's
     module tree on CPU — construction only, no product compute)"""
     import superpoint_transformer_b200 as S
     torch.manual_seed(0)
-    net = S.SPT(mlp_norm=S.nn.GraphNorm, norm=S.nn.GraphNorm, **model_kwargs(S))
+    net = S.SPT(mlp_norm=S.nn.GraphNorm, norm=S.nn.GraphNorm, **model_kwargs(S, no_ffn=no_ffn))
     net.apply(S.init_weights)
     head = S.nn.Classifier(DIM, NUM_CLASSES)
     sd = {k: v.detach().clone().requires_grad_(v.is_floating_point())
@@ -514,7 +747,7 @@ def _cpu_state_dict():
     return sd, hw, hb
 
 
-def cpu_step(sd, hw, hb, nag, labels):
+def cpu_step(sd, hw, hb, nag, labels, opt=None):
     from oracle import path as P
     for v in list(sd.values()) + [hw, hb]:
         if v.grad is not None:
@@ -523,7 +756,14 @@ def cpu_step(sd, hw, hb, nag, labels):
                         use_diameter_parent=True, pool_reduce='max')
     loss = torch.nn.functional.cross_entropy(torch.nn.functional.linear(out, hw, hb), labels)
     loss.backward()
+    if opt is not None:
+        opt.step()
     return float(loss.detach())
+
+
+def _cpu_optimizer(sd, hw, hb):
+    ps = [v for v in sd.values() if v.requires_grad] + [hw, hb]
+    return torch.optim.AdamW(ps, lr=1e-3, weight_decay=1e-4)
 
 
 def _scaled_levels(n1):
@@ -569,22 +809,43 @@ def _pick_threads(sd, hw, hb):
     return best[0], best[1] / 1000, avail
 
 
-def cpu_reference_sample(target_seconds=20.0):
-    sd, hw, hb = _cpu_state_dict()
+def _reference_scene_levels(cfg_name):
+    """what ONE reference step processes: cfg2/cfg3 the full scene of the own arm's rank 0;
+    cfg4 one of the 64 scenes; cfg5 a scene of one tile's size (bounded samples, stated)."""
+    c = BENCH_CONFIGS[cfg_name]
+    if cfg_name == 'cfg5':
+        return [l // c['tiles'] for l in c['levels']], c['seed'], "one tile-sized scene (1/8 of the graph)"
+    if cfg_name == 'cfg4':
+        return c['levels'], c['seed'], "one of the 64 scenes"
+    return c['levels'], c['seed'], "the full scene of rank 0"
+
+
+def cpu_reference_sample(cfg_name='cfg2', target_seconds=20.0):
+    c = BENCH_CONFIGS[cfg_name]
+    sd, hw, hb = _cpu_state_dict(no_ffn=c['no_ffn'])
     threads, per_sp, avail = _pick_threads(sd, hw, hb)
-    n1 = int(min(max(target_seconds / max(per_sp, 1e-9), 1000), LEVELS[0]))
-    n1 = max(1000, (n1 // 1000) * 1000)
-    nag = _cpu_scene(_scaled_levels(n1), seed=1)
-    labels = torch.randint(0, NUM_CLASSES, (n1,))
+    levels, seed, _ = _reference_scene_levels(cfg_name)
+    # the full scene when one step of it stays within ~2x the target, else a scaled-down one
+    same = per_sp * levels[0] <= 2.5 * target_seconds and c['scaling'] == 'weak'
+    if same:
+        n1 = levels[0]
+        nag = _cpu_scene(levels, seed=seed)
+    else:
+        n1 = int(min(max(target_seconds / max(per_sp, 1e-9), 1000), levels[0]))
+        n1 = max(1000, (n1 // 1000) * 1000)
+        nag = _cpu_scene(_scaled_levels(n1), seed=seed)
+    labels = scene_labels(n1, seed)
     t = time.time()
-    cpu_step(sd, hw, hb, nag, labels)
+    loss = cpu_step(sd, hw, hb, nag, labels)
     dt = time.time() - t
     return {"value": round(n1 / dt, 1), "unit": UNIT, "cores": threads, "kind": "port",
-            "host_cores_available": avail,
-            "sample": f"one fwd+bwd of the same model on a {n1}/{n1 // 5}/{n1 // 25}-superpoint "
-                      f"NAG of the same law ({dt:.1f} s); oracle/path.py (reference glue "
-                      f"restated, torch CPU leaves), fp32, {threads} threads (fastest of the "
-                      f"probed thread counts on this {avail}-core host)"}
+            "host_cores_available": avail, "loss": loss, "same_scene": bool(same),
+            "sample": f"one fwd+bwd of the same model on a {n1}/{nag[2].num_nodes}/"
+                      f"{nag[3].num_nodes}-superpoint NAG of the same law "
+                      f"({'the scene of rank 0' if same else 'bounded sample'}, {dt:.1f} s); "
+                      f"oracle/path.py (reference glue restated, torch CPU leaves), fp32, "
+                      f"{threads} threads (fastest of the probed thread counts on this "
+                      f"{avail}-core host)"}
 
 
 def run_reference(args):
@@ -592,31 +853,32 @@ def run_reference(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
-    sd, hw, hb = _cpu_state_dict()
+    cfg_name = args.config
+    c = BENCH_CONFIGS[cfg_name]
+    sd, hw, hb = _cpu_state_dict(no_ffn=c['no_ffn'])
     threads, per_sp, avail = _pick_threads(sd, hw, hb)
-    budget = 180.0
-    total_steps = args.steps + args.warmup
-    n1 = int(budget / total_steps / max(per_sp, 1e-9))
-    n1 = max(1000, min((n1 // 1000) * 1000, LEVELS[0]))
-    nag = _cpu_scene(_scaled_levels(n1), seed=1)
-    labels = torch.randint(0, NUM_CLASSES, (n1,))
+    levels, seed, what = _reference_scene_levels(cfg_name)
+    n1 = levels[0]
+    nag = _cpu_scene(levels, seed=seed)          # the stated configuration, not a scaled sample
+    labels = scene_labels(n1, seed)
+    opt = _cpu_optimizer(sd, hw, hb)
     for _ in range(args.warmup):
-        cpu_step(sd, hw, hb, nag, labels)
+        cpu_step(sd, hw, hb, nag, labels, opt)
     t = time.time()
     for _ in range(args.steps):
-        cpu_step(sd, hw, hb, nag, labels)
+        cpu_step(sd, hw, hb, nag, labels, opt)
     dt = time.time() - t
     ms = dt / args.steps * 1e3
     value = n1 / (ms * 1e-3)
-    sample = (f"each step = fwd+bwd on a {n1}/{n1 // 5}/{n1 // 25}-superpoint NAG of the cfg-2 "
-              f"law (bounded sample of the 100k workload), oracle/path.py on {threads} threads "
-              f"(fastest probed; host has {avail} cores)")
+    sample = (f"each step = fwd + bwd + AdamW on {what}: a {n1}/{levels[1]}/{levels[2]}-superpoint "
+              f"NAG (seed {seed}), oracle/path.py on {threads} threads (fastest probed; host has "
+              f"{avail} cores)")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT,
+        "impl": "reference", "metric": c['metric'], "value": round(value, 1), "unit": UNIT,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": c['scaling'],
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
+        "config": bench_config(cfg_name, world),
         "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": threads,
                          "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0,
@@ -630,6 +892,8 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='own', choices=['own', 'reference'])
+    ap.add_argument('--config', default=os.environ.get('BENCH_CONFIG', 'cfg2'),
+                    choices=sorted(BENCH_CONFIGS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='eager launches, no CUDA graphs')
     ap.add_argument('--kernels-out', default=None, help='write the full per-kernel timing table (JSON)')

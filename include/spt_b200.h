@@ -148,6 +148,27 @@ int spt_segment_pool_fwd(const float* x, const int32_t* ptr,
                          int64_t num_parents, int64_t C, int reduce, float* out,
                          int32_t* arg /*nullable*/, void* stream);
 
+/* torch_scatter scatter_mean / scatter_std over CSR segments (reference call sites
+ * src/transforms/graph.py:266-285 — per-segment mean / std of point attributes — and
+ * :1025-1044; semantics SURVEY.md Appendix A): mean = sum / max(count, 1),
+ * std = sqrt(sum (x - mean)^2 / (max(count - 1, 1) + 1e-6)).  Either output may be NULL. */
+int spt_segment_mean_std_fwd(const float* x, const int32_t* ptr,
+                             const int32_t* points /*nullable = identity*/,
+                             int64_t num_parents, int64_t C, float* mean_out /*nullable*/,
+                             float* std_out /*nullable*/, void* stream);
+
+/* Superedge descriptors from their level-0 sub-edges: replaces
+ * _minimalistic_horizontal_edge_features (src/transforms/graph.py:950-1060): for superedge s
+ * with sub-edges j in perm[ptr[s]:ptr[s+1]] (CSR of `se_id`), offsets o_j =
+ * points[sp_dst[j]] - points[sp_src[j]]:
+ *   out[s, 0:3] = mean o_j ; out[s, 3:6] = clip(unbiased std of o_j in the orthonormal base
+ *   built around the mean offset (src/utils/geometry.py:42-77), -2, 2) ;
+ *   out[s, 6] = sqrt(mean |o_j|). */
+int spt_superedge_features_fwd(const float* points /*[N0,3]*/, const int64_t* sp_src,
+                               const int64_t* sp_dst, const int32_t* ptr, const int32_t* perm,
+                               int64_t num_superedges, float* out /*[num_superedges,7]*/,
+                               void* stream);
+
 /* dx[i, c] from dout[parent(i), c]; gather-form backward (no atomics):
  *   SUM : dx = dout[parent]          MEAN: dx = dout[parent] / max(count, 1)
  *   MAX/MIN: dx = dout[parent] if arg[parent, c] == i else 0               */

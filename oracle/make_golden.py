@@ -372,18 +372,123 @@ def edge_feature_case(ref):
     return raw
 
 
+def round2_cases(ref):
+    """fixtures added in round 2: attentive pools (src/nn/pool.py:156-360), superedge features
+    from sub-edges (src/transforms/graph.py:950-1060), key subsets of the on-the-fly
+    horizontal features (:1063-1277)."""
+    from superpoint_transformer_b200.data import Data
+    from superpoint_transformer_b200.synthetic import make_nag
+    cases = {}
+    # ---- attentive pools -------------------------------------------------------------
+    gen = torch.Generator().manual_seed(29)
+    Nc, Np, C, Cp, H, D, F = 700, 90, 32, 20, 4, 8, 9
+    idx = torch.randint(0, Np - 2, (Nc,), generator=gen)       # 2 parents without children
+    xc, xp = torch.randn(Nc, C, generator=gen), torch.randn(Np, Cp, generator=gen)
+    ea = torch.randn(Nc, F, generator=gen)
+    specs = {
+        'attpool_kq': (ref.AttentivePool, dict(dim=C, q_in_dim=Cp, num_heads=H, qk_dim=D,
+                                               in_rpe_dim=F, k_rpe=True, q_rpe=True, out_dim=C)),
+        'attpool_k_shared': (ref.AttentivePool, dict(dim=C, q_in_dim=Cp, num_heads=H, qk_dim=D,
+                                                     in_rpe_dim=F, k_rpe=True,
+                                                     heads_share_rpe=True, qk_scale='d+g')),
+        'attpool_plain_inproj': (ref.AttentivePool, dict(dim=C, q_in_dim=Cp, num_heads=H,
+                                                         qk_dim=D, in_dim=C, out_dim=24)),
+        'attpool_learnt_kq': (ref.AttentivePoolWithLearntQueries,
+                              dict(dim=C, num_heads=H, qk_dim=D, in_rpe_dim=F, k_rpe=True,
+                                   q_rpe=True, out_dim=C)),
+        'attpool_learnt_plain': (ref.AttentivePoolWithLearntQueries,
+                                 dict(dim=C, num_heads=H, qk_dim=D)),
+    }
+    for name, (cls, kw) in specs.items():
+        torch.manual_seed(77)
+        m = cls(**kw)
+        m.apply(ref.init_weights)
+        for p in m.parameters():
+            if p.dim() == 1:
+                p.data.normal_(0, 0.2, generator=gen)
+        a, b, e = xc.clone(), xp.clone(), ea.clone()
+        use_ea = kw.get('k_rpe') or kw.get('q_rpe')
+        wrt = [a, b, e] if use_ea else [a, b]
+        outs, probe, grads, pgrads = _run(m, (a, b, idx), dict(edge_attr=e if use_ea else None,
+                                                                num_pool=Np), wrt,
+                                          torch.Generator().manual_seed(31))
+        m64 = cls(**kw).double()
+        m64.load_state_dict({k: v.double() for k, v in m.state_dict().items()})
+        out64 = m64(xc.double(), xp.double(), idx, edge_attr=ea.double() if use_ea else None,
+                    num_pool=Np).detach()
+        cases[name] = dict(cls=cls.__name__, kw=kw, x_child=xc, x_parent=xp, index=idx,
+                           edge_attr=ea if use_ea else None, num_pool=Np,
+                           sd={k: v.detach().clone() for k, v in m.state_dict().items()},
+                           out=outs[0], out64=out64, probe=probe, dx_child=grads[0],
+                           dx_parent=grads[1], dedge_attr=grads[2] if use_ea else None,
+                           dparams=pgrads)
+    # ---- superedge features from sub-edges -------------------------------------------------
+    gen = torch.Generator().manual_seed(41)
+    N0, N1, E = 4000, 120, 260
+    points = torch.rand(N0, 3, generator=gen) * 20
+    i = torch.randint(0, N1, (4 * E,), generator=gen)
+    j = torch.randint(0, N1, (4 * E,), generator=gen)
+    lo, hi = torch.minimum(i, j), torch.maximum(i, j)
+    uid = torch.unique(lo[lo != hi] * N1 + hi[lo != hi])[:E]
+    se = torch.stack((uid // N1, uid % N1))
+    E = se.shape[1]
+    counts = torch.randint(1, 40, (E,), generator=gen)
+    counts[0] = 1                          # single sub-edge: std = 0 / (1 + 1e-6)
+    counts[1] = 2                          # two opposite sub-edges: zero mean offset
+    counts[2] = 3                          # mean offset along (v, v, v): second fallback
+    se_id = torch.repeat_interleave(torch.arange(E), counts)
+    Es = se_id.numel()
+    spi = torch.randint(0, N0, (2, Es), generator=gen)
+    first = torch.cumsum(counts, 0) - counts
+    a0, b0 = int(first[1]), int(first[1]) + 1
+    spi[:, b0] = spi[:, a0].flip(0)        # reversed copy -> offsets cancel exactly
+    c0 = int(first[2])
+    points[spi[0, c0:c0 + 3]] = torch.tensor([[1., 1., 1.]])
+    points[spi[1, c0:c0 + 3]] = torch.tensor([[3., 3., 3.]])
+    perm = torch.randperm(Es, generator=gen)   # se_id unsorted, as subedges() may emit
+    se_id, spi = se_id[perm], spi[:, perm]
+    d = Data(edge_index=se.clone(), pos=torch.zeros(N1, 3))
+    out = ref.minimalistic_horizontal_edge_features(d, points.clone(), spi, se_id)
+    cases['superedge'] = dict(points=points, se_point_index=spi, se_id=se_id, edge_index=se,
+                              edge_attr=out.edge_attr.clone())
+    # ---- key subsets of the on-the-fly horizontal features -----------------------------------
+    nag = make_nag([200, 30], mean_degree=8, seed=91)
+    dd = nag[1]
+    raw = dict(edge_index=dd.edge_index.clone(), edge_attr=dd.edge_attr.clone(), pos=dd.pos.clone(),
+               normal=dd.normal.clone(), log_length=dd.log_length.clone(),
+               log_surface=dd.log_surface.clone(), log_volume=dd.log_volume.clone(),
+               log_size=dd.log_size.clone(), num_nodes=dd.num_nodes, subsets={})
+    for keys in (['mean_off', 'std_off', 'log_size', 'centroid_dir'],
+                 ['normal_angle', 'centroid_dist'],
+                 ['angle_source', 'mean_dist', 'log_length', 'log_volume'],
+                 []):
+        out = ref.on_the_fly_horizontal_edge_features(dd.clone(), keys=keys or None) \
+            if keys else None
+        raw['subsets']['+'.join(keys) if keys else 'none'] = dict(
+            keys=keys, edge_index=None if out is None else out.edge_index,
+            edge_attr=None if out is None else out.edge_attr)
+    del raw['subsets']['none']   # sanitize_keys(None) = default set; the empty set is a host-side branch
+    cases['h_subsets'] = raw
+    return cases
+
+
 def main():
     if not R.available():
         print('reference sources not available; cannot regenerate golden vectors')
         return 1
     ref = R.load()
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == 'round2':   # leave the round-1 fixtures untouched
+        torch.save(round2_cases(ref), os.path.join(OUT, 'round2.pt'))
+        print('round2.pt', os.path.getsize(os.path.join(OUT, 'round2.pt')))
+        return 0
     torch.save(attention_cases(ref), os.path.join(OUT, 'attention.pt'))
     torch.save(segment_cases(ref), os.path.join(OUT, 'segment.pt'))
     torch.save(stage_cases(ref), os.path.join(OUT, 'stage.pt'))
     torch.save(spt_case(ref), os.path.join(OUT, 'spt_nano3.pt'))
     torch.save(edge_feature_case(ref), os.path.join(OUT, 'edge_features.pt'))
     torch.save(norm_pool_cases(ref), os.path.join(OUT, 'norms.pt'))
+    torch.save(round2_cases(ref), os.path.join(OUT, 'round2.pt'))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
     return 0

@@ -454,10 +454,27 @@ def spt_forward(sd, nag, *, num_heads, qk_dim, nano=True, num_down, num_up,
 # --------------------------------------------------------------------------- #
 #  on-the-fly transforms (src/transforms/graph.py)
 # --------------------------------------------------------------------------- #
+H_KEYS = ('mean_off', 'std_off', 'mean_dist', 'angle_source', 'angle_target', 'normal_angle',
+          'log_length', 'log_surface', 'log_volume', 'log_size', 'centroid_dir', 'centroid_dist')
+_H_WIDTH = {'mean_off': 3, 'std_off': 3, 'centroid_dir': 3}
+
+
 def horizontal_edge_features(se, ea, pos, normal, log_length, log_surface, log_volume,
-                             log_size):
-    """_on_the_fly_horizontal_edge_features with the default 12 keys
-    (src/transforms/graph.py:1137-1277).  Returns (edge_index [2,2Eh], edge_attr [2Eh,18])."""
+                             log_size, keys=None):
+    """_on_the_fly_horizontal_edge_features (src/transforms/graph.py:1137-1277).  Returns
+    (edge_index [2,2Eh], edge_attr [2Eh,18]); with a `keys` subset only the columns of those
+    keys, in the reference's assembly order (mean_off first: it is PREPENDED at :1214-1218,
+    every other key appended in the order of the `if` chain)."""
+    if keys is not None:
+        ei, full = horizontal_edge_features(se, ea, pos, normal, log_length, log_surface,
+                                            log_volume, log_size)
+        cols, c = [], 0
+        for k in H_KEYS:
+            w = _H_WIDTH.get(k, 1)
+            if k in keys:
+                cols += list(range(c, c + w))
+            c += w
+        return ei, (full[:, cols] if cols else None)
     f_list = []
     f = ea[:, 3:6].float()                                            # std_off :1187-1191
     f_list.append(torch.cat((f, f), dim=0))
@@ -513,3 +530,41 @@ def vertical_edge_features(child_pos, parent_pos, child_normal, parent_normal, c
     for c, p_ in zip(child_logs, parent_logs):                        # :1394-1408
         f_list.append((p_[idx] - c).view(-1, 1))
     return torch.cat(f_list, dim=1)                                   # :1413
+
+
+# --------------------------------------------------------------------------- #
+#  superedge features from level-0 sub-edges (preprocessing)
+# --------------------------------------------------------------------------- #
+def base_vectors_3d(x):
+    """src/utils/geometry.py:42-77.  NB: like the reference, zero rows of `x` are overwritten
+    IN PLACE with (1, 0, 0) (`a = x` aliases the argument)."""
+    a = x
+    a[torch.where(a.norm(dim=1) == 0)[0]] = torch.tensor([[1, 0, 0]], dtype=x.dtype)
+    a = a / a.norm(dim=1).view(-1, 1)
+    b = torch.vstack((a[:, 1] - a[:, 2], a[:, 2] - a[:, 0], a[:, 0] - a[:, 1])).T
+    b[torch.where(b.norm(dim=1) == 0)[0]] = torch.tensor([[2, 1, -1]], dtype=x.dtype)
+    b = b / b.norm(dim=1).view(-1, 1)
+    c = torch.linalg.cross(a, b)
+    return torch.cat((a.unsqueeze(1), b.unsqueeze(1), c.unsqueeze(1)), dim=1)
+
+
+def minimalistic_horizontal_edge_features(points, se_point_index, se_id, num_superedges):
+    """_minimalistic_horizontal_edge_features (src/transforms/graph.py:1007-1058):
+    [mean_off | std_off (clipped to [-2, 2]) | sqrt(mean_dist)] per superedge."""
+    offset = points[se_point_index[1]] - points[se_point_index[0]]    # :1007
+    dist = offset.norm(dim=1)                                         # :1017
+    mean_off = L.scatter_mean(offset, se_id, 0, num_superedges)       # :1024
+    base = base_vectors_3d(mean_off)[se_id]                           # :1031
+    u = (offset * base[:, 0]).sum(dim=1).view(-1, 1)
+    v = (offset * base[:, 1]).sum(dim=1).view(-1, 1)
+    w = (offset * base[:, 2]).sum(dim=1).view(-1, 1)
+    std_off = L.scatter_std(torch.cat((u, v, w), dim=1), se_id, 0, num_superedges)   # :1035
+    std_off = std_off.clip(-2, 2)
+    mean_dist = L.scatter_mean(dist, se_id, 0, num_superedges).sqrt()  # :1043
+    return torch.cat((mean_off, std_off, mean_dist.view(-1, 1)), dim=1)
+
+
+def cluster_mean_std(f, super_index, num_clusters):
+    """scatter parts of _compute_cluster_features (src/transforms/graph.py:266-285)."""
+    return (L.scatter_mean(f, super_index, 0, num_clusters),
+            L.scatter_std(f, super_index, 0, num_clusters))

@@ -209,10 +209,19 @@ def load():
     for k in keys.__all__:
         setattr(utils, k, getattr(keys, k))
     for k in ('print_tensor_info', 'isolated_nodes', 'edge_to_superedge', 'subedges',
-              'to_trimmed', 'cluster_radius_nn_graph', 'base_vectors_3d',
+              'to_trimmed', 'cluster_radius_nn_graph',
               'scatter_mean_orientation', 'geometric_features', 'arange_interleave',
               'csr_to_dense'):
         setattr(utils, k, None)
+    # src/utils/geometry.py (base_vectors_3d, used by _minimalistic_horizontal_edge_features):
+    # its own third-party imports (pgeof) and the neighbour helpers are stubs, the function
+    # itself is the reference's
+    _module('pgeof')
+    _module('src.utils.neighbors', neighbors_dense_to_csr=None)
+    if not hasattr(usc, 'scatter_pca'):
+        usc.scatter_pca = None
+    geom = _load('src.utils.geometry', 'src/utils/geometry.py')
+    utils.base_vectors_3d = geom.base_vectors_3d
 
     def is_trimmed(edge_index, return_trimmed=False):
         # stand-in for src/utils/graph.py:505-521 (needs PyG coalesce): i<j, no dups
@@ -231,5 +240,7 @@ def load():
     ns.on_the_fly_horizontal_edge_features = graph._on_the_fly_horizontal_edge_features
     ns.NAGAddSelfLoops = graph.NAGAddSelfLoops
     ns.on_the_fly_vertical_edge_features = graph._on_the_fly_vertical_edge_features
+    ns.minimalistic_horizontal_edge_features = graph._minimalistic_horizontal_edge_features
+    ns.base_vectors_3d = geom.base_vectors_3d
     _LOADED = ns
     return ns

@@ -72,6 +72,9 @@ SIGNATURES = {
                                      c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_ptr]),
     "spt_attn_bwd_weights": (c_int, [c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_ptr,
                                      c_ptr, c_ptr, c_ptr]),
+    "spt_segment_mean_std_fwd": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr]),
+    "spt_superedge_features_fwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr,
+                                           c_ptr]),
     "spt_edge_features_fwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                       c_ptr, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr]),
     "spt_vertical_edge_features_fwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,

@@ -489,7 +489,7 @@ static int rows_per_warp_for(int64_t num_rows, int ctas_per_sm, int waves) {
     int r = atoi(ov);
     if (r >= 1 && r <= 64) return r;
   }
-  const int64_t target_warps = (int64_t)148 * ctas_per_sm * fast::kWarps * waves;
+  const int64_t target_warps = (int64_t)device_sm_count() * ctas_per_sm * fast::kWarps * waves;
   int64_t r = num_rows / target_warps;
   if (r < 1) r = 1;
   if (r > 8 || (waves == 1 && r >= 4)) r = 8;
@@ -504,26 +504,12 @@ static int tile_rows_per_warp(int64_t num_rows, int warps_per_cta) {
     int r = atoi(ov);
     if (r >= 1 && r <= 64) return r;
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t target_warps = (int64_t)sms * 2 * warps_per_cta * 4;   // 4 waves of 2 CTAs/SM
+  const int sms = device_sm_count();
+  const int64_t target_warps = (int64_t)sms * warps_per_cta * 4;   // >= 4 waves of 1 CTA/SM
   int64_t r = num_rows / target_warps;
   if (r < 1) r = 1;
-  if (r > 8) r = 8;
+  if (r > 16) r = 16;
   return (int)r;
-}
-
-// cudaFuncSetAttribute is per device: remember which devices were set up
-template <typename K>
-static void ensure_smem(K kernel, int bytes, unsigned long long* done_mask) {
-  int dev = 0;
-  cudaGetDevice(&dev);
-  const unsigned long long bit = 1ull << (dev & 63);
-  if (!(*done_mask & bit)) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    *done_mask |= bit;
-  }
 }
 
 static bool tile_layout_ok(const float* q, const float* k, const float* v, const float* a,
@@ -563,9 +549,9 @@ int spt_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const
       A.scale_mode = scale_mode; A.scale_value = scale_value;
       A.agg_v = agg_v; A.abar = abar; A.sump = sump; A.m = m; A.z = z;
       A.rows_per_warp = tile_rows_per_warp(num_rows, tile::kFwdWarps);
-      const int smem = tile::FwdSmem<tile::kFwdWarps>::total + 1024;
+      const int smem = tile::FwdSmem::total + 1024;
       static unsigned long long done = 0;
-      ensure_smem(tile::k_attn_fwd_tile, smem, &done);
+      ensure_dynamic_smem(tile::k_attn_fwd_tile, smem, &done);
       const int64_t warps = ceil_div(num_rows, A.rows_per_warp);
       tile::k_attn_fwd_tile<<<(unsigned)ceil_div(warps, tile::kFwdWarps), tile::kFwdWarps * kWarp,
                               smem, st>>>(tmA, A);
@@ -580,12 +566,8 @@ int spt_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const
     A.scale_mode = scale_mode; A.scale_value = scale_value;
     A.agg_v = agg_v; A.abar = abar; A.sump = sump; A.m = m; A.z = z;
     A.rows_per_warp = rows_per_warp_for(num_rows, 5, 1);
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(fast::k_attn_fwd_fast, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)fast::fwd_smem_bytes());
-      attr_set = true;
-    }
+    static unsigned long long attr_done = 0;
+    ensure_dynamic_smem(fast::k_attn_fwd_fast, (int)fast::fwd_smem_bytes(), &attr_done);
     int64_t warps = ceil_div(num_rows, A.rows_per_warp);
     fast::k_attn_fwd_fast<<<(unsigned)ceil_div(warps, fast::kWarps), fast::kWarps * kWarp,
                             fast::fwd_smem_bytes(), st>>>(A);
@@ -641,9 +623,9 @@ int spt_attn_bwd_rows(const float* q, int64_t ldq, const float* k, int64_t ldk,
       A.m = m; A.z = z; A.agg_v = agg_v; A.abar = abar; A.d_agg_v = d_agg_v; A.d_abar = d_abar;
       A.dq = dq; A.lddq = (int)lddq; A.da = da; A.Pbuf = Pbuf; A.G = G;
       A.rows_per_warp = tile_rows_per_warp(num_rows, tile::kBwdWarps);
-      const int smem = tile::BwdSmem<tile::kBwdWarps>::total + 1024;
+      const int smem = tile::BwdSmem::total + 1024;
       static unsigned long long done = 0;
-      ensure_smem(tile::k_attn_bwd_tile, smem, &done);
+      ensure_dynamic_smem(tile::k_attn_bwd_tile, smem, &done);
       const int64_t warps = ceil_div(num_rows, A.rows_per_warp);
       tile::k_attn_bwd_tile<<<(unsigned)ceil_div(warps, tile::kBwdWarps), tile::kBwdWarps * kWarp,
                               smem, st>>>(tmA, A);
@@ -663,13 +645,8 @@ int spt_attn_bwd_rows(const float* q, int64_t ldq, const float* k, int64_t ldk,
     A.m = m; A.z = z; A.agg_v = agg_v; A.abar = abar; A.d_agg_v = d_agg_v; A.d_abar = d_abar;
     A.dq = dq; A.lddq = (int)lddq; A.da = da; A.Pbuf = Pbuf; A.G = G;
     A.rows_per_warp = rows_per_warp_for(num_rows, 4, 3);
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(fast::k_attn_bwd_rows_fast,
-                           cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)fast::bwd_smem_bytes());
-      attr_set = true;
-    }
+    static unsigned long long attr_done = 0;
+    ensure_dynamic_smem(fast::k_attn_bwd_rows_fast, (int)fast::bwd_smem_bytes(), &attr_done);
     int64_t warps = ceil_div(num_rows, A.rows_per_warp);
     fast::k_attn_bwd_rows_fast<<<(unsigned)ceil_div(warps, fast::kWarps), fast::kWarps * kWarp,
                                  fast::bwd_smem_bytes(), st>>>(A);
@@ -691,7 +668,7 @@ int spt_attn_bwd_rows(const float* q, int64_t ldq, const float* k, int64_t ldk,
       W.dWq = Wq ? dWq : nullptr; W.dbq = (Wq && bq) ? dbq : nullptr;
       W.dWk = Wk ? dWk : nullptr; W.dbk = (Wk && bk) ? dbk : nullptr;
       int64_t ctas = ceil_div(E, 1024);
-      if (ctas > 148 * 4) ctas = 148 * 4;
+      if (ctas > device_sm_count() * 4) ctas = device_sm_count() * 4;
       W.edges_per_cta = ceil_div(E, ctas);
       ctas = ceil_div(E, W.edges_per_cta);
       fast::k_attn_bwd_dw_fast<<<(unsigned)ctas, 256, 0, st>>>(W);
@@ -760,7 +737,7 @@ int spt_attn_bwd_weights(const float* G, const float* a, int64_t E, int H, int D
   if (rc != SPT_OK) return rc;
   SPT_REQUIRE(G && a, SPT_E_INVALID, "attn_bwd_weights: null pointer");
   int64_t ctas = ceil_div(E, 2048);
-  if (ctas > 148 * 4) ctas = 148 * 4;
+  if (ctas > device_sm_count() * 4) ctas = device_sm_count() * 4;
   int64_t per = ceil_div(E, ctas);
   per = ceil_div(per, kDwTile) * kDwTile;
   ctas = ceil_div(E, per);

@@ -58,8 +58,12 @@ constexpr int kChunkBytes = kChunk * kF * 4;     // 4096
 constexpr int kRingSlots = kRing * kChunk;       // 96
 constexpr int kFragBytes = 16 * 32 * 16;         // one pre-split weight fragment set (8 KB)
 
-constexpr int kFwdWarps = 8;
-constexpr int kBwdWarps = 6;
+constexpr int kVStageBytes = 32 * kC * 4;        // gathered v rows of one tile (16 KB)
+
+// one CTA per SM (the per-warp staging buffers take the shared memory), 7 warps: the register
+// file then allows up to 255 registers per thread, i.e. no spills in either kernel
+constexpr int kFwdWarps = 7;
+constexpr int kBwdWarps = 7;
 
 __host__ __device__ inline bool shape_ok(int H, int D, int Dv, int F) {
   return H == kH && D == kD && Dv == kDv && F == kF;
@@ -240,23 +244,37 @@ __device__ __forceinline__ void rpe_tile(float (&acc)[2][4][4], const unsigned c
   const uint32_t csel = (uint32_t)(lane >> 4);
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
-    uint32_t ahi[2][4], alo[2][4];
+    uint4 b[4];
 #pragma unroll
-    for (int m = 0; m < 2; ++m) {
-      if (m == 0 || two) {
-        uint32_t a[4];
-        ldsm_x4(rowaddr[m] + (((2 * kk + csel) ^ rsw[m]) << 4), a[0], a[1], a[2], a[3]);
+    for (int nn = 0; nn < 4; ++nn) b[nn] = frag1[(kk * 4 + nn) * 32 + lane];
+    {
+      uint32_t a[4], ahi[4], alo[4];
+      ldsm_x4(rowaddr[0] + (((2 * kk + csel) ^ rsw[0]) << 4), a[0], a[1], a[2], a[3]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) split_tf32(a[i], ahi[m][i], alo[m][i]);
-      }
+      for (int i = 0; i < 4; ++i) split_tf32(a[i], ahi[i], alo[i]);
+#pragma unroll
+      for (int nn = 0; nn < 4; ++nn) mma_3x(acc[0][nn], ahi, alo, b[nn]);
     }
+    if (two) {   // warp-uniform: rows 16..31 of the tile hold edges
+      uint32_t a[4], ahi[4], alo[4];
+      ldsm_x4(rowaddr[1] + (((2 * kk + csel) ^ rsw[1]) << 4), a[0], a[1], a[2], a[3]);
 #pragma unroll
-    for (int nn = 0; nn < 4; ++nn) {
-      const uint4 b = frag1[(kk * 4 + nn) * 32 + lane];
-      mma_3x(acc[0][nn], ahi[0], alo[0], b);
-      if (two) mma_3x(acc[1][nn], ahi[1], alo[1], b);
+      for (int i = 0; i < 4; ++i) split_tf32(a[i], ahi[i], alo[i]);
+#pragma unroll
+      for (int nn = 0; nn < 4; ++nn) mma_3x(acc[1][nn], ahi, alo, b[nn]);
     }
   }
+}
+
+// gathered value rows of a tile: lane e copies v[col_e, 0:128] (512 B) into slot e of the
+// warp's staging buffer with ONE bulk async copy (cp.async.bulk, completion on `bar`); issued
+// at the start of the tile, consumed after the tensor-core phase and the softmax.
+__device__ __forceinline__ void stage_v(unsigned char* v_s, uint64_t* bar, const float* v,
+                                        unsigned ldv, int mycol, int n, int lane) {
+  if (lane == 0) mbar_expect_tx(bar, (uint32_t)n * (kC * 4));
+  __syncwarp();
+  if (lane < n)
+    fast::tma_load_1d(v_s + lane * (kC * 4), v + (size_t)((unsigned)mycol * ldv), kC * 4, bar);
 }
 
 struct FwdArgs {
@@ -271,20 +289,33 @@ struct FwdArgs {
   int rows_per_warp;
 };
 
-// shared memory: [kWarps rings, 1024-aligned][frag1 8 KB][bias 128 B][bars][p tiles]
-template <int kWarps>
-struct FwdSmem {
+// shared memory (after 1024-byte alignment):
+//   [kWarps x edge-feature ring 12 KB][kWarps x gathered-v stage 16 KB]
+//   [weight fragments NFRAG x 8 KB][bias 128 B][mbarriers 4 per warp][kWarps x NP x p tile 512 B]
+template <int kWarps, int NFRAG, int NP>
+struct Smem {
   static constexpr int ring_off = 0;
-  static constexpr int frag_off = kWarps * kRing * kChunkBytes;
-  static constexpr int bias_off = frag_off + kFragBytes;
+  static constexpr int v_off = kWarps * kRing * kChunkBytes;
+  static constexpr int frag_off = v_off + kWarps * kVStageBytes;
+  static constexpr int bias_off = frag_off + NFRAG * kFragBytes;
   static constexpr int bar_off = bias_off + 128;
-  static constexpr int p_off = bar_off + kWarps * kRing * 8 + ((kWarps * kRing) & 1) * 8;
-  static constexpr int total = p_off + kWarps * 32 * kH * 4;
+  static constexpr int p_off = bar_off + kWarps * 4 * 8;
+  static constexpr int total = p_off + kWarps * NP * 32 * kH * 4;
+};
+using FwdSmem = Smem<kFwdWarps, 1, 1>;
+using BwdSmem = Smem<kBwdWarps, 2, 1>;
+
+// per-row operands fetched one row ahead (rowptr -> col -> gathered rows is otherwise a chain
+// of dependent memory latencies at the start of every row)
+struct RowAhead {
+  int e_next;       // rowptr[row + 2]
+  int col_next;     // col[first tile of row + 1][lane]
+  float2 qA, qB;    // q[row + 1][2t..], q[row + 1][8 + 2t..]
 };
 
-__global__ void __launch_bounds__(kFwdWarps * 32, 2)
+__global__ void __launch_bounds__(kFwdWarps * 32, 1)
 k_attn_fwd_tile(const __grid_constant__ CUtensorMap tmA, const FwdArgs P) {
-  using L = FwdSmem<kFwdWarps>;
+  using L = FwdSmem;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem =
       smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);   // SWIZZLE_128B atoms
@@ -293,6 +324,8 @@ k_attn_fwd_tile(const __grid_constant__ CUtensorMap tmA, const FwdArgs P) {
   uint4* frag1 = reinterpret_cast<uint4*>(smem + L::frag_off);
   float* bias_s = reinterpret_cast<float*>(smem + L::bias_off);
   float* p_s = reinterpret_cast<float*>(smem + L::p_off) + w * 32 * kH;
+  unsigned char* v_s = smem + L::v_off + w * kVStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bar_off) + w * 4;
 
   build_frag1(frag1, P.Wq, P.Wk);
   build_bias(bias_s, P.Wq, P.bq, P.Wk, P.bk);
@@ -305,24 +338,40 @@ k_attn_fwd_tile(const __grid_constant__ CUtensorMap tmA, const FwdArgs P) {
 
   Ring ring;
   ring.buf = smem + L::ring_off + w * (kRing * kChunkBytes);
-  ring.bar = reinterpret_cast<uint64_t*>(smem + L::bar_off) + w * kRing;
+  ring.bar = bars;
   ring.tm = &tmA;
   ring.lane = lane;
+  uint64_t* vbar = bars + 3;
+  if (lane == 0) mbar_init(vbar, 1);
   const int e_begin = P.rowptr[row0];
-  ring.init(e_begin, P.rowptr[row1]);
+  const int e_end = P.rowptr[row1];
+  ring.init(e_begin, e_end);   // (fences the mbarrier inits, syncs the warp)
 
   const bool want_abar = P.abar != nullptr;
   const int hb = lane >> 3;                     // head of my 4 value channels
   const int hsrc = 2 * (hb & 1);                // a lane holding head hb in the fragment layout
-  const float* vbase = P.v + 4 * lane;
   const float* kbase = P.k + 2 * t;
+  const unsigned ldk = (unsigned)P.ldk, ldv = (unsigned)P.ldv;
+  uint32_t vtile = 0;                           // tiles staged so far (phase parity of vbar)
 
   int b = e_begin;
+  RowAhead nx;
+  nx.e_next = P.rowptr[row0 + 1];
+  nx.col_next = (b + lane < e_end) ? P.col[b + lane] : 0;
+  nx.qA = *reinterpret_cast<const float2*>(P.q + row0 * P.ldq + 2 * t);
+  nx.qB = *reinterpret_cast<const float2*>(P.q + row0 * P.ldq + 8 + 2 * t);
+
   for (int64_t row = row0; row < row1; ++row) {
-    const int e = P.rowptr[row + 1];
+    const int e = nx.e_next;
+    int mycol = nx.col_next;
+    float2 qA = nx.qA, qB = nx.qB;
+    if (row + 1 < row1) {   // operands of the next row
+      nx.e_next = P.rowptr[row + 2];
+      nx.col_next = (e + lane < e_end) ? P.col[e + lane] : 0;
+      nx.qA = *reinterpret_cast<const float2*>(P.q + (row + 1) * P.ldq + 2 * t);
+      nx.qB = *reinterpret_cast<const float2*>(P.q + (row + 1) * P.ldq + 8 + 2 * t);
+    }
     const float scale = fast::qk_scale_fast(P.scale_mode, P.scale_value, e - b);
-    float2 qA = *reinterpret_cast<const float2*>(P.q + row * P.ldq + 2 * t);
-    float2 qB = *reinterpret_cast<const float2*>(P.q + row * P.ldq + 8 + 2 * t);
     qA.x *= scale; qA.y *= scale; qB.x *= scale; qB.y *= scale;
     float mA = -INFINITY, mB = -INFINITY, lA = 0.f, lB = 0.f;   // heads t>>1 and 2 + (t>>1)
     f32x2 accv01 = 0ull, accv23 = 0ull, acca01 = 0ull, acca23 = 0ull;
@@ -330,14 +379,17 @@ k_attn_fwd_tile(const __grid_constant__ CUtensorMap tmA, const FwdArgs P) {
     for (int tb = b; tb < e; tb += 32) {
       const int n = min(32, e - tb);
       const bool two = n > 16;
-      const int mycol = (lane < n) ? P.col[tb + lane] : 0;
-      // gathered k rows of my 4 edges (issued before the tensor-core phase)
+      if (tb != b) mycol = (lane < n) ? P.col[tb + lane] : 0;
+      __syncwarp();                              // previous tile's v / p stages are free
+      stage_v(v_s, vbar, P.v, ldv, mycol, n, lane);
+      // gathered k rows of my 4 edges (in flight during the tensor-core phase)
       float2 kA[4], kB[4];
 #pragma unroll
       for (int idx = 0; idx < 4; ++idx) {
-        if (idx < 2 || two) {
-          const unsigned tc = (unsigned)__shfl_sync(kFull, mycol, 8 * idx + g);
-          const float* kp = kbase + (size_t)tc * (unsigned)P.ldk;
+        const unsigned tc = (unsigned)__shfl_sync(kFull, mycol, 8 * idx + g);
+        kA[idx] = make_float2(0.f, 0.f); kB[idx] = kA[idx];
+        if (8 * idx + g < n) {
+          const float* kp = kbase + (size_t)(tc * ldk);
           kA[idx] = ldg_stream2(kp);
           kB[idx] = ldg_stream2(kp + 8);
         }
@@ -350,17 +402,16 @@ k_attn_fwd_tile(const __grid_constant__ CUtensorMap tmA, const FwdArgs P) {
       float cA[4], cB[4];
 #pragma unroll
       for (int idx = 0; idx < 4; ++idx) {
-        cA[idx] = -INFINITY; cB[idx] = -INFINITY;
-        if (idx < 2 || two) {
-          const int m = idx >> 1, hf = (idx & 1) * 2;
-          float pa = (qA.x + acc[m][0][hf]) * (kA[idx].x + acc[m][2][hf]);
-          pa = fmaf(qA.y + acc[m][0][hf + 1], kA[idx].y + acc[m][2][hf + 1], pa);
-          float pb = (qB.x + acc[m][1][hf]) * (kB[idx].x + acc[m][3][hf]);
-          pb = fmaf(qB.y + acc[m][1][hf + 1], kB[idx].y + acc[m][3][hf + 1], pb);
-          pa += __shfl_xor_sync(kFull, pa, 1);
-          pb += __shfl_xor_sync(kFull, pb, 1);
-          if (8 * idx + g < n) { cA[idx] = pa * kLog2e; cB[idx] = pb * kLog2e; }
-        }
+        const int m = idx >> 1, hf = (idx & 1) * 2;
+        float pa = (qA.x + acc[m][0][hf]) * (kA[idx].x + acc[m][2][hf]);
+        pa = fmaf(qA.y + acc[m][0][hf + 1], kA[idx].y + acc[m][2][hf + 1], pa);
+        float pb = (qB.x + acc[m][1][hf]) * (kB[idx].x + acc[m][3][hf]);
+        pb = fmaf(qB.y + acc[m][1][hf + 1], kB[idx].y + acc[m][3][hf + 1], pb);
+        pa += __shfl_xor_sync(kFull, pa, 1);
+        pb += __shfl_xor_sync(kFull, pb, 1);
+        const bool valid = 8 * idx + g < n;
+        cA[idx] = valid ? pa * kLog2e : -INFINITY;
+        cB[idx] = valid ? pb * kLog2e : -INFINITY;
       }
       float tA = fmaxf(fmaxf(cA[0], cA[1]), fmaxf(cA[2], cA[3]));
       float tB = fmaxf(fmaxf(cB[0], cB[1]), fmaxf(cB[2], cB[3]));
@@ -374,14 +425,11 @@ k_attn_fwd_tile(const __grid_constant__ CUtensorMap tmA, const FwdArgs P) {
       float sA = 0.f, sB = 0.f;
 #pragma unroll
       for (int idx = 0; idx < 4; ++idx) {
-        if (idx < 2 || two) {
-          const float pA = ex2(cA[idx] - mA_new), pB = ex2(cB[idx] - mB_new);
-          sA += pA; sB += pB;
-          if ((t & 1) == 0) {
-            p_s[(8 * idx + g) * kH + (t >> 1)] = pA;
-            p_s[(8 * idx + g) * kH + 2 + (t >> 1)] = pB;
-          }
-        }
+        const float pA = ex2(cA[idx] - mA_new), pB = ex2(cB[idx] - mB_new);
+        sA += pA; sB += pB;
+        if ((t & 1) == 0)
+          *reinterpret_cast<float2*>(p_s + (8 * idx + g) * kH + t) =
+              make_float2(pA, pB);   // heads (t>>1, 2+(t>>1)) stored at words t, t+1: see below
       }
 #pragma unroll
       for (int o = 4; o < 32; o <<= 1) {
@@ -393,6 +441,8 @@ k_attn_fwd_tile(const __grid_constant__ CUtensorMap tmA, const FwdArgs P) {
       __syncwarp();
 
       // accumulation layout: lane = value channels 4*lane.. (head hb) + abar[hb][4*(lane&7)..]
+      // p tile word order per edge: [h0, h2, h1, h3] (the float2 stores above): head hb is word
+      const int pw = ((hb & 1) << 1) | (hb >> 1);
       if (tb != b) {   // later tiles of a long row: rescale the running sums
         const float a0 = __shfl_sync(kFull, alA, hsrc), a1 = __shfl_sync(kFull, alB, hsrc);
         const float al = hb < 2 ? a0 : a1;
@@ -400,28 +450,27 @@ k_attn_fwd_tile(const __grid_constant__ CUtensorMap tmA, const FwdArgs P) {
         accv01 = mul2(accv01, aa); accv23 = mul2(accv23, aa);
         acca01 = mul2(acca01, aa); acca23 = mul2(acca23, aa);
       }
+      mbar_wait(vbar, vtile & 1u);               // the gathered v rows have landed
+      ++vtile;
+      const unsigned char* vrow = v_s + 16 * lane;
+      const float* prow_s = p_s + pw;
+      // physical ring row of edge u: prow + u (wraps at 96); my 16-byte chunk is (lane&7)^(row&7)
+      const uint32_t abase = smem_u32(ring.buf);
       for (int e0 = 0; e0 < n; e0 += 8) {
-        ulonglong2 vv[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           if (e0 + u < n) {
-            const unsigned tc = (unsigned)__shfl_sync(kFull, mycol, e0 + u);
-            const float4 x = ldg_stream4(vbase + (size_t)tc * (unsigned)P.ldv);
-            vv[u].x = pack2(x.x, x.y); vv[u].y = pack2(x.z, x.w);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          if (e0 + u < n) {
-            const float p = p_s[(e0 + u) * kH + hb];
+            const ulonglong2 vv = *reinterpret_cast<const ulonglong2*>(vrow + (e0 + u) * (kC * 4));
+            const float p = prow_s[(e0 + u) * kH];
             const f32x2 pp = pack2(p, p);
-            fma2(accv01, pp, vv[u].x);
-            fma2(accv23, pp, vv[u].y);
+            fma2(accv01, pp, vv.x);
+            fma2(accv23, pp, vv.y);
             if (want_abar) {
               int r = prow + e0 + u;
               if (r >= kRingSlots) r -= kRingSlots;
-              const ulonglong2 a4 = *reinterpret_cast<const ulonglong2*>(
-                  ring.buf + r * 128 + ((((lane & 7) ^ r) & 7) << 4));
+              ulonglong2 a4;
+              const uint32_t ad = abase + r * 128 + (((lane ^ r) & 7) << 4);
+              asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(a4.x), "=l"(a4.y) : "r"(ad));
               fma2(acca01, pp, a4.x);
               fma2(acca23, pp, a4.y);
             }
@@ -446,8 +495,9 @@ k_attn_fwd_tile(const __grid_constant__ CUtensorMap tmA, const FwdArgs P) {
     }
     if (g == 0 && (t & 1) == 0) {
       const int h0 = t >> 1, h1 = 2 + (t >> 1);
-      P.m[row * kH + h0] = (e > b) ? mA * kLn2 : 0.f;    // natural-log units
-      P.m[row * kH + h1] = (e > b) ? mB * kLn2 : 0.f;
+      const bool any = e > b;
+      P.m[row * kH + h0] = any ? mA * kLn2 : 0.f;    // natural-log units
+      P.m[row * kH + h1] = any ? mB * kLn2 : 0.f;
       P.z[row * kH + h0] = zA;
       P.z[row * kH + h1] = zB;
       P.sump[row * kH + h0] = lA / zA;
@@ -476,30 +526,19 @@ struct BwdArgs {
   int rows_per_warp;
 };
 
-template <int kWarps>
-struct BwdSmem {
-  static constexpr int ring_off = 0;
-  static constexpr int frag1_off = kWarps * kRing * kChunkBytes;
-  static constexpr int frag2_off = frag1_off + kFragBytes;
-  static constexpr int bias_off = frag2_off + kFragBytes;
-  static constexpr int bar_off = bias_off + 128;
-  static constexpr int p_off = bar_off + kWarps * kRing * 8 + ((kWarps * kRing) & 1) * 8;
-  static constexpr int dp_off = p_off + kWarps * 32 * kH * 4;
-  static constexpr int total = dp_off + kWarps * 32 * kH * 4;
-};
-
-__global__ void __launch_bounds__(kBwdWarps * 32, 2)
+__global__ void __launch_bounds__(kBwdWarps * 32, 1)
 k_attn_bwd_tile(const __grid_constant__ CUtensorMap tmA, const BwdArgs P) {
-  using L = BwdSmem<kBwdWarps>;
+  using L = BwdSmem;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  uint4* frag1 = reinterpret_cast<uint4*>(smem + L::frag1_off);
-  uint4* frag2 = reinterpret_cast<uint4*>(smem + L::frag2_off);
+  uint4* frag1 = reinterpret_cast<uint4*>(smem + L::frag_off);
+  uint4* frag2 = reinterpret_cast<uint4*>(smem + L::frag_off + kFragBytes);
   float* bias_s = reinterpret_cast<float*>(smem + L::bias_off);
-  float* p_s = reinterpret_cast<float*>(smem + L::p_off) + w * 32 * kH;
-  float* dp_s = reinterpret_cast<float*>(smem + L::dp_off) + w * 32 * kH;
+  float* dp_s = reinterpret_cast<float*>(smem + L::p_off) + w * 32 * kH;
+  unsigned char* v_s = smem + L::v_off + w * kVStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bar_off) + w * 4;
 
   build_frag1(frag1, P.Wq, P.Wk);
   build_frag2(frag2, P.Wq, P.Wk);
@@ -513,28 +552,44 @@ k_attn_bwd_tile(const __grid_constant__ CUtensorMap tmA, const BwdArgs P) {
 
   Ring ring;
   ring.buf = smem + L::ring_off + w * (kRing * kChunkBytes);
-  ring.bar = reinterpret_cast<uint64_t*>(smem + L::bar_off) + w * kRing;
+  ring.bar = bars;
   ring.tm = &tmA;
   ring.lane = lane;
+  uint64_t* vbar = bars + 3;
+  if (lane == 0) mbar_init(vbar, 1);
   const int e_begin = P.rowptr[row0];
-  ring.init(e_begin, P.rowptr[row1]);
+  const int e_end = P.rowptr[row1];
+  ring.init(e_begin, e_end);
 
   const bool has_dab = P.d_abar != nullptr && P.abar != nullptr;
   const bool want_da = P.da != nullptr;
   const int hb = lane >> 3;
   const int j8 = lane & 7;
-  const float* vbase = P.v + 4 * lane;
   const float* kbase = P.k + 2 * t;
+  const unsigned ldk = (unsigned)P.ldk, ldv = (unsigned)P.ldv;
+  const int hA = t >> 1, hB = 2 + (t >> 1);
   const int hsl = (t & 1) * 2 + (t >> 1);   // head fed through k-slot t of the P . dAbar step
+  uint32_t vtile = 0;
 
   int b = e_begin;
+  RowAhead nx;
+  nx.e_next = P.rowptr[row0 + 1];
+  nx.col_next = (b + lane < e_end) ? P.col[b + lane] : 0;
+  nx.qA = *reinterpret_cast<const float2*>(P.q + row0 * P.ldq + 2 * t);
+  nx.qB = *reinterpret_cast<const float2*>(P.q + row0 * P.ldq + 8 + 2 * t);
+
   for (int64_t row = row0; row < row1; ++row) {
-    const int e = P.rowptr[row + 1];
+    const int e = nx.e_next;
+    int mycol = nx.col_next;
+    float2 qA = nx.qA, qB = nx.qB;
+    if (row + 1 < row1) {
+      nx.e_next = P.rowptr[row + 2];
+      nx.col_next = (e + lane < e_end) ? P.col[e + lane] : 0;
+      nx.qA = *reinterpret_cast<const float2*>(P.q + (row + 1) * P.ldq + 2 * t);
+      nx.qB = *reinterpret_cast<const float2*>(P.q + (row + 1) * P.ldq + 8 + 2 * t);
+    }
     const float scale = fast::qk_scale_fast(P.scale_mode, P.scale_value, e - b);
-    float2 qA = *reinterpret_cast<const float2*>(P.q + row * P.ldq + 2 * t);
-    float2 qB = *reinterpret_cast<const float2*>(P.q + row * P.ldq + 8 + 2 * t);
     qA.x *= scale; qA.y *= scale; qB.x *= scale; qB.y *= scale;
-    const int hA = t >> 1, hB = 2 + (t >> 1);
     const float m2A = P.m[row * kH + hA] * kLog2e, m2B = P.m[row * kH + hB] * kLog2e;
     const float ziA = 1.f / P.z[row * kH + hA], ziB = 1.f / P.z[row * kH + hB];
     // accumulation layout operands of the row
@@ -568,13 +623,16 @@ k_attn_bwd_tile(const __grid_constant__ CUtensorMap tmA, const BwdArgs P) {
     for (int tb = b; tb < e; tb += 32) {
       const int n = min(32, e - tb);
       const bool two = n > 16;
-      const int mycol = (lane < n) ? P.col[tb + lane] : 0;
+      if (tb != b) mycol = (lane < n) ? P.col[tb + lane] : 0;
+      __syncwarp();
+      stage_v(v_s, vbar, P.v, ldv, mycol, n, lane);
       float2 kA[4], kB[4];
 #pragma unroll
       for (int idx = 0; idx < 4; ++idx) {
-        if (idx < 2 || two) {
-          const unsigned tc = (unsigned)__shfl_sync(kFull, mycol, 8 * idx + g);
-          const float* kp = kbase + (size_t)tc * (unsigned)P.ldk;
+        const unsigned tc = (unsigned)__shfl_sync(kFull, mycol, 8 * idx + g);
+        kA[idx] = make_float2(0.f, 0.f); kB[idx] = kA[idx];
+        if (8 * idx + g < n) {
+          const float* kp = kbase + (size_t)(tc * ldk);
           kA[idx] = ldg_stream2(kp);
           kB[idx] = ldg_stream2(kp + 8);
         }
@@ -587,51 +645,46 @@ k_attn_bwd_tile(const __grid_constant__ CUtensorMap tmA, const BwdArgs P) {
       float pA[4], pB[4];
 #pragma unroll
       for (int idx = 0; idx < 4; ++idx) {
-        pA[idx] = 0.f; pB[idx] = 0.f;
-        if (idx < 2 || two) {
-          const int m = idx >> 1, hf = (idx & 1) * 2;
-          acc[m][0][hf] += qA.x; acc[m][0][hf + 1] += qA.y;
-          acc[m][1][hf] += qB.x; acc[m][1][hf + 1] += qB.y;
-          acc[m][2][hf] += kA[idx].x; acc[m][2][hf + 1] += kA[idx].y;
-          acc[m][3][hf] += kB[idx].x; acc[m][3][hf + 1] += kB[idx].y;
-          float pa = acc[m][0][hf] * acc[m][2][hf];
-          pa = fmaf(acc[m][0][hf + 1], acc[m][2][hf + 1], pa);
-          float pb = acc[m][1][hf] * acc[m][3][hf];
-          pb = fmaf(acc[m][1][hf + 1], acc[m][3][hf + 1], pb);
-          pa += __shfl_xor_sync(kFull, pa, 1);
-          pb += __shfl_xor_sync(kFull, pb, 1);
-          if (8 * idx + g < n) {
-            pA[idx] = ex2(fmaf(pa, kLog2e, -m2A)) * ziA;
-            pB[idx] = ex2(fmaf(pb, kLog2e, -m2B)) * ziB;
-          }
-          if ((t & 1) == 0) {
-            p_s[(8 * idx + g) * kH + hA] = pA[idx];
-            p_s[(8 * idx + g) * kH + hB] = pB[idx];
-            if (8 * idx + g < n) {
-              P.Pbuf[(size_t)(tb + 8 * idx + g) * kH + hA] = pA[idx];
-              P.Pbuf[(size_t)(tb + 8 * idx + g) * kH + hB] = pB[idx];
-            }
-          }
+        const int m = idx >> 1, hf = (idx & 1) * 2;
+        acc[m][0][hf] += qA.x; acc[m][0][hf + 1] += qA.y;
+        acc[m][1][hf] += qB.x; acc[m][1][hf + 1] += qB.y;
+        acc[m][2][hf] += kA[idx].x; acc[m][2][hf + 1] += kA[idx].y;
+        acc[m][3][hf] += kB[idx].x; acc[m][3][hf + 1] += kB[idx].y;
+        float pa = acc[m][0][hf] * acc[m][2][hf];
+        pa = fmaf(acc[m][0][hf + 1], acc[m][2][hf + 1], pa);
+        float pb = acc[m][1][hf] * acc[m][3][hf];
+        pb = fmaf(acc[m][1][hf + 1], acc[m][3][hf + 1], pb);
+        pa += __shfl_xor_sync(kFull, pa, 1);
+        pb += __shfl_xor_sync(kFull, pb, 1);
+        const bool valid = 8 * idx + g < n;
+        pA[idx] = valid ? ex2(fmaf(pa, kLog2e, -m2A)) * ziA : 0.f;
+        pB[idx] = valid ? ex2(fmaf(pb, kLog2e, -m2B)) * ziB : 0.f;
+        if ((t & 1) == 0 && valid) {
+          P.Pbuf[(size_t)(tb + 8 * idx + g) * kH + hA] = pA[idx];
+          P.Pbuf[(size_t)(tb + 8 * idx + g) * kH + hB] = pB[idx];
         }
       }
-      __syncwarp();
 
       // dp - delta of every (edge, head): accumulation layout, 8 edges per butterfly
+      mbar_wait(vbar, vtile & 1u);
+      ++vtile;
+      const unsigned char* vrow = v_s + 16 * lane;
+      const uint32_t abase = smem_u32(ring.buf);
       for (int e0 = 0; e0 < n; e0 += 8) {
         float s[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           s[u] = 0.f;
           if (e0 + u < n) {
-            const unsigned tc = (unsigned)__shfl_sync(kFull, mycol, e0 + u);
-            const float4 x = ldg_stream4(vbase + (size_t)tc * (unsigned)P.ldv);
-            f32x2 d2 = mul2(dy01, pack2(x.x, x.y));
-            fma2(d2, dy23, pack2(x.z, x.w));
+            const ulonglong2 vv = *reinterpret_cast<const ulonglong2*>(vrow + (e0 + u) * (kC * 4));
+            f32x2 d2 = mul2(dy01, vv.x);
+            fma2(d2, dy23, vv.y);
             if (has_dab) {
               int r = prow + e0 + u;
               if (r >= kRingSlots) r -= kRingSlots;
-              const ulonglong2 a4 = *reinterpret_cast<const ulonglong2*>(
-                  ring.buf + r * 128 + (((j8 ^ r) & 7) << 4));
+              ulonglong2 a4;
+              const uint32_t ad = abase + r * 128 + (((lane ^ r) & 7) << 4);
+              asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(a4.x), "=l"(a4.y) : "r"(ad));
               fma2(d2, dab01, a4.x);
               fma2(d2, dab23, a4.y);
             }
@@ -663,32 +716,29 @@ k_attn_bwd_tile(const __grid_constant__ CUtensorMap tmA, const BwdArgs P) {
       float pk[4];   // p of k-slot t of the P . dAbar step, per edge
 #pragma unroll
       for (int idx = 0; idx < 4; ++idx) {
-        pk[idx] = 0.f;
-        if (idx < 2 || two) {
-          const int m = idx >> 1, hf = (idx & 1) * 2;
-          const bool valid = 8 * idx + g < n;
-          const float dA = valid ? pA[idx] * dp_s[(8 * idx + g) * kH + hA] : 0.f;
-          const float dB = valid ? pB[idx] * dp_s[(8 * idx + g) * kH + hB] : 0.f;
+        const int m = idx >> 1, hf = (idx & 1) * 2;
+        const bool valid = 8 * idx + g < n;
+        const float dA = valid ? pA[idx] * dp_s[(8 * idx + g) * kH + hA] : 0.f;
+        const float dB = valid ? pB[idx] * dp_s[(8 * idx + g) * kH + hB] : 0.f;
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const float qa = acc[m][0][hf + j], ka = acc[m][2][hf + j];
-            const float qb = acc[m][1][hf + j], kb = acc[m][3][hf + j];
-            acc[m][0][hf + j] = valid ? dA * ka : 0.f;
-            acc[m][2][hf + j] = valid ? dA * qa : 0.f;
-            acc[m][1][hf + j] = valid ? dB * kb : 0.f;
-            acc[m][3][hf + j] = valid ? dB * qb : 0.f;
-          }
-          pk[idx] = (t & 1) ? pB[idx] : pA[idx];
-          if (valid) {
-            float* gp = P.G + (size_t)(tb + 8 * idx + g) * kHD2 + 2 * t;
-#pragma unroll
-            for (int nn = 0; nn < 4; ++nn)
-              *reinterpret_cast<float2*>(gp + 8 * nn) =
-                  make_float2(acc[m][nn][hf], acc[m][nn][hf + 1]);
-          }
-          dqacc[0] += acc[m][0][hf]; dqacc[1] += acc[m][0][hf + 1];
-          dqacc[2] += acc[m][1][hf]; dqacc[3] += acc[m][1][hf + 1];
+        for (int j = 0; j < 2; ++j) {
+          const float qa = acc[m][0][hf + j], ka = acc[m][2][hf + j];
+          const float qb = acc[m][1][hf + j], kb = acc[m][3][hf + j];
+          acc[m][0][hf + j] = valid ? dA * ka : 0.f;
+          acc[m][2][hf + j] = valid ? dA * qa : 0.f;
+          acc[m][1][hf + j] = valid ? dB * kb : 0.f;
+          acc[m][3][hf + j] = valid ? dB * qb : 0.f;
         }
+        pk[idx] = (t & 1) ? pB[idx] : pA[idx];
+        if (valid) {
+          float* gp = P.G + (size_t)(tb + 8 * idx + g) * kHD2 + 2 * t;
+#pragma unroll
+          for (int nn = 0; nn < 4; ++nn)
+            *reinterpret_cast<float2*>(gp + 8 * nn) =
+                make_float2(acc[m][nn][hf], acc[m][nn][hf + 1]);
+        }
+        dqacc[0] += acc[m][0][hf]; dqacc[1] += acc[m][0][hf + 1];
+        dqacc[2] += acc[m][1][hf]; dqacc[3] += acc[m][1][hf + 1];
       }
 
       if (want_da) {
@@ -719,27 +769,26 @@ k_attn_bwd_tile(const __grid_constant__ CUtensorMap tmA, const BwdArgs P) {
         }
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          uint32_t ahi[2][4], alo[2][4];
+          uint4 bfr[4];
+#pragma unroll
+          for (int nf = 0; nf < 4; ++nf) bfr[nf] = frag2[(ks * 4 + nf) * 32 + lane];
 #pragma unroll
           for (int m = 0; m < 2; ++m) {
             if (m == 0 || two) {
               // k-slot s <-> output 8ks + 2s, slot 4 + s <-> 8ks + 2s + 1
-              split_tf32(__float_as_uint(acc[m][ks][0]), ahi[m][0], alo[m][0]);
-              split_tf32(__float_as_uint(acc[m][ks][2]), ahi[m][1], alo[m][1]);
-              split_tf32(__float_as_uint(acc[m][ks][1]), ahi[m][2], alo[m][2]);
-              split_tf32(__float_as_uint(acc[m][ks][3]), ahi[m][3], alo[m][3]);
-            }
-          }
+              uint32_t ahi[4], alo[4];
+              split_tf32(__float_as_uint(acc[m][ks][0]), ahi[0], alo[0]);
+              split_tf32(__float_as_uint(acc[m][ks][2]), ahi[1], alo[1]);
+              split_tf32(__float_as_uint(acc[m][ks][1]), ahi[2], alo[2]);
+              split_tf32(__float_as_uint(acc[m][ks][3]), ahi[3], alo[3]);
 #pragma unroll
-          for (int nf = 0; nf < 4; ++nf) {
-            const uint4 bfr = frag2[(ks * 4 + nf) * 32 + lane];
-            mma_3x(dacc[0][nf], ahi[0], alo[0], bfr);
-            if (two) mma_3x(dacc[1][nf], ahi[1], alo[1], bfr);
+              for (int nf = 0; nf < 4; ++nf) mma_3x(dacc[m][nf], ahi, alo, bfr[nf]);
+            }
           }
         }
 #pragma unroll
         for (int idx = 0; idx < 4; ++idx) {
-          if ((idx < 2 || two) && 8 * idx + g < n) {
+          if (8 * idx + g < n) {
             const int m = idx >> 1, hf = (idx & 1) * 2;
             float* dp_ = P.da + (size_t)(tb + 8 * idx + g) * kF + 2 * t;
 #pragma unroll

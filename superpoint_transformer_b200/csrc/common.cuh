@@ -40,6 +40,33 @@ inline int check_launch(const char* what) {
   } while (0)
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Per-device one-time setup.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the
+// CURRENT device only, and the SM count differs between parts: both are keyed by device id
+// (a process may drive several GPUs).
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
+inline int device_sm_count() {
+  static int cache[64] = {0};
+  const int dev = current_device() & 63;
+  if (cache[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev] = n > 0 ? n : 148;
+  }
+  return cache[dev];
+}
+template <typename Kernel>
+inline void ensure_dynamic_smem(Kernel kernel, int bytes, unsigned long long* done_mask) {
+  const unsigned long long bit = 1ull << (current_device() & 63);
+  if (!(*done_mask & bit)) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    *done_mask |= bit;
+  }
+}
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 __device__ __forceinline__ float warp_sum(float v) {

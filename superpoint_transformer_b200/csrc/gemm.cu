@@ -330,12 +330,8 @@ int spt_gemm_nt(const float* A, int64_t M, int64_t K, int64_t lda, const float* 
   SPT_REQUIRE(K < (1 << 24) && N < (1 << 24), SPT_E_TOO_LARGE, "gemm_nt: K/N too large");
   if (M >= 512 && use_umma() && umma::shape_ok(A, M, K, lda, B, N, ldb, C, ldc))
     return umma::launch(A, M, K, lda, B, N, ldb, bias, C, ldc, (cudaStream_t)stream_);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(gemm::k_gemm_nt, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)sizeof(gemm::NtSmem));
-    attr = true;
-  }
+  static unsigned long long attr_done = 0;
+  ensure_dynamic_smem(gemm::k_gemm_nt, (int)sizeof(gemm::NtSmem), &attr_done);
   dim3 grid((unsigned)ceil_div(N, gemm::BN), (unsigned)ceil_div(M, gemm::BM));
   SPT_REQUIRE(grid.y <= 65535u * 1024u, SPT_E_TOO_LARGE, "gemm_nt: M too large");
   if (grid.y > 65535) {
@@ -369,7 +365,7 @@ int spt_gemm_tn_acc(const float* A, int64_t M, int64_t N, int64_t lda, const flo
   int ntiles = (int)ceil_div(N, gemm::TM), ktiles = (int)ceil_div(K, gemm::TK);
   int64_t tiles = (int64_t)ntiles * ktiles;
   // enough row slabs to fill the machine (~4 CTAs per SM), slabs multiple of TR rows
-  int64_t slabs = ceil_div((int64_t)148 * 4, tiles);
+  int64_t slabs = ceil_div((int64_t)device_sm_count() * 4, tiles);
   int64_t rows_per = ceil_div(ceil_div(M, slabs), gemm::TR) * gemm::TR;
   if (rows_per < 256) rows_per = 256;
   slabs = ceil_div(M, rows_per);

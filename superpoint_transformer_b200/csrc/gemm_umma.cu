@@ -737,16 +737,9 @@ int launch(const float* A, int64_t M, int64_t K, int64_t lda, const float* B, in
                   make_map(&tmC, C, M, N, ldc, BM),
               SPT_E_UNSUPPORTED, "gemm_nt(umma): cuTensorMapEncodeTiled failed");
 
-  static int sm_count = 0;
-  static bool attr = false;
-  if (!attr) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(k_gemm_nt_umma, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)kSmemBudget);
-    attr = true;
-  }
+  static unsigned long long attr_done = 0;
+  ensure_dynamic_smem(k_gemm_nt_umma, (int)kSmemBudget, &attr_done);
+  const int sm_count = device_sm_count();
   const unsigned grid = (unsigned)(P.tiles < sm_count ? P.tiles : sm_count);
   static long long* trace_dev = nullptr;
   static const bool tracing = getenv("SPT_UMMA_TRACE") != nullptr;  // diagnostic only
@@ -1093,16 +1086,9 @@ int tn_launch(const float* A, int64_t M, int64_t N, int64_t lda, const float* B,
   SPT_REQUIRE(make_map(&tmA, A, M, N, lda, P.bkm, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) &&
                   make_map(&tmB, B, M, K, ldb, P.bkm, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B),
               SPT_E_UNSUPPORTED, "gemm_tn_acc(umma): cuTensorMapEncodeTiled failed");
-  static int sm_count = 0;
-  static bool attr = false;
-  if (!attr) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(k_gemm_tn_umma, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)kSmemBudget);
-    attr = true;
-  }
+  static unsigned long long attr_done = 0;
+  ensure_dynamic_smem(k_gemm_tn_umma, (int)kSmemBudget, &attr_done);
+  const int sm_count = device_sm_count();
   // >= 8 chunks per CTA so that the atomics of the [N, K] partials stay a small fraction
   int64_t grid = P.chunks / 8;
   if (grid < 1) grid = 1;

@@ -272,7 +272,7 @@ __global__ void k_segment_sum_i64(const int64_t* __restrict__ values,
   if (lane == 0) out[g] = s;
 }
 
-static inline int grid_for(int64_t n, int threads, int max_blocks = 148 * 16) {
+static inline int grid_for(int64_t n, int threads, int max_blocks = device_sm_count() * 16) {
   int64_t b = ceil_div(n, threads);
   if (b < 1) b = 1;
   if (b > max_blocks) b = max_blocks;

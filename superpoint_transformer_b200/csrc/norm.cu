@@ -506,9 +506,9 @@ int spt_graphnorm_fwd(const float* x, const int64_t* batch, int64_t N, int64_t C
   }
   int vec = (C % 4 == 0) ? 4 : 1;
   ColMap cm = col_map(C, vec);
-  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, kNormRows), 148 * 4);
+  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, kNormRows), device_sm_count() * 4);
   int64_t total = N * (C / vec);
-  int agrid = (int)imin(ceil_div(total > 0 ? total : 1, kNormThreads), 148 * 16);
+  int agrid = (int)imin(ceil_div(total > 0 ? total : 1, kNormThreads), device_sm_count() * 16);
   // single pass over x: shifted first and second moments around a per-channel pivot
   float* pivot = w.k2;  // [C] floats of the (forward-unused) k2 area
   if (N > 0) {
@@ -559,9 +559,9 @@ int spt_graphnorm_bwd(const float* x, const float* dy, const int64_t* batch, int
   }
   int vec = (C % 4 == 0) ? 4 : 1;
   ColMap cm = col_map(C, vec);
-  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, kNormRows), 148 * 4);
+  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, kNormRows), device_sm_count() * 4);
   int64_t total = N * (C / vec);
-  int agrid = (int)imin(ceil_div(total > 0 ? total : 1, kNormThreads), 148 * 16);
+  int agrid = (int)imin(ceil_div(total > 0 ? total : 1, kNormThreads), device_sm_count() * 16);
   if (N > 0) {
     if (vec == 4)
       k_graphnorm_stats<2, 4><<<slabs, kNormThreads, 0, st>>>(
@@ -608,9 +608,9 @@ int spt_groupnorm_fwd(const float* x, const int64_t* batch, int64_t N, int64_t C
   const int64_t G = num_groups;
   int vec = (C % 4 == 0) ? 4 : 1;
   ColMap cm = col_map(C, vec);
-  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, kNormRows), 148 * 4);
+  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, kNormRows), device_sm_count() * 4);
   int64_t total = N * (C / vec);
-  int agrid = (int)imin(ceil_div(total > 0 ? total : 1, kNormThreads), 148 * 16);
+  int agrid = (int)imin(ceil_div(total > 0 ? total : 1, kNormThreads), device_sm_count() * 16);
   const unsigned ggrid = (unsigned)ceil_div(B * G, 128);
   if (N > 0) {
     if (vec == 4)
@@ -667,9 +667,9 @@ int spt_groupnorm_bwd(const float* x, const float* dy, const int64_t* batch, int
   const int64_t G = num_groups;
   int vec = (C % 4 == 0) ? 4 : 1;
   ColMap cm = col_map(C, vec);
-  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, kNormRows), 148 * 4);
+  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, kNormRows), device_sm_count() * 4);
   int64_t total = N * (C / vec);
-  int agrid = (int)imin(ceil_div(total > 0 ? total : 1, kNormThreads), 148 * 16);
+  int agrid = (int)imin(ceil_div(total > 0 ? total : 1, kNormThreads), device_sm_count() * 16);
   if (N > 0) {
     if (vec == 4)
       k_graphnorm_stats<2, 4><<<slabs, kNormThreads, 0, st>>>(

@@ -228,6 +228,116 @@ __global__ void k_unitsphere_apply(const float* __restrict__ pos,
     pos_out[i * 3 + d] = (pos[i * 3 + d] - center[p * 3 + d]) * inv;
 }
 
+// ------------------------------------------------------------------ segment mean / std
+// torch_scatter semantics: mean = sum / max(count, 1);
+// std (unbiased) = sqrt(sum (x - mean)^2 / (max(count - 1, 1) + 1e-6)).  Warp per parent,
+// two passes over the parent's children (the second one hits L1/L2), lane = channel.
+__global__ void k_segment_mean_std(const float* __restrict__ x, const int32_t* __restrict__ ptr,
+                                   const int32_t* __restrict__ points, int64_t num_parents,
+                                   int64_t C, float* __restrict__ mean_out,
+                                   float* __restrict__ std_out) {
+  int lane = threadIdx.x & 31;
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t p = warp; p < num_parents; p += nwarps) {
+    const int b = ptr[p], e = ptr[p + 1];
+    const float inv = 1.f / (float)max(e - b, 1);
+    const float den = (float)max(e - b - 1, 1) + 1e-6f;
+    for (int64_t c = lane; c < C; c += 32) {
+      float s = 0.f;
+      for (int i = b; i < e; ++i) s += x[(int64_t)(points ? points[i] : i) * C + c];
+      const float mu = s * inv;
+      if (mean_out) mean_out[p * C + c] = mu;
+      if (std_out) {
+        float q = 0.f;
+        for (int i = b; i < e; ++i) {
+          const float d = x[(int64_t)(points ? points[i] : i) * C + c] - mu;
+          q = fmaf(d, d, q);
+        }
+        std_out[p * C + c] = sqrtf(q / den);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ superedge features
+// _minimalistic_horizontal_edge_features (reference src/transforms/graph.py:950-1060): one
+// warp per superedge over its sub-edges (CSR of se_id): mean offset, std of the offsets in an
+// orthonormal base built around the mean offset (src/utils/geometry.py:42-77, incl. its
+// (1,0,0) / (2,1,-1) fall-backs and the in-place overwrite of a zero mean offset), clipped to
+// [-2, 2], and sqrt of the mean sub-edge length.  out [num_se, 7].
+__global__ void k_superedge_features(const float* __restrict__ points,
+                                     const int64_t* __restrict__ sp_src,
+                                     const int64_t* __restrict__ sp_dst,
+                                     const int32_t* __restrict__ ptr,
+                                     const int32_t* __restrict__ perm, int64_t num_se,
+                                     float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t se = warp; se < num_se; se += nwarps) {
+    const int b = ptr[se], e = ptr[se + 1];
+    float sx = 0.f, sy = 0.f, sz = 0.f, sd = 0.f;
+    for (int i = b + lane; i < e; i += 32) {
+      const int64_t j = perm[i];
+      const int64_t ps = sp_src[j], pt = sp_dst[j];
+      const float ox = points[pt * 3] - points[ps * 3];
+      const float oy = points[pt * 3 + 1] - points[ps * 3 + 1];
+      const float oz = points[pt * 3 + 2] - points[ps * 3 + 2];
+      sx += ox; sy += oy; sz += oz;
+      sd += sqrtf(ox * ox + oy * oy + oz * oz);
+    }
+    sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz); sd = warp_sum(sd);
+    const float inv = 1.f / (float)max(e - b, 1);
+    float mx = sx * inv, my = sy * inv, mz = sz * inv;
+    const float md = sd * inv;
+    // base vectors (the reference overwrites a zero mean offset with (1,0,0) in place)
+    float na = sqrtf(mx * mx + my * my + mz * mz);
+    if (na == 0.f) { mx = 1.f; my = 0.f; mz = 0.f; na = 1.f; }
+    const float ax = mx / na, ay = my / na, az = mz / na;
+    float bx = ay - az, by = az - ax, bz = ax - ay;
+    float nb = sqrtf(bx * bx + by * by + bz * bz);
+    if (nb == 0.f) { bx = 2.f; by = 1.f; bz = -1.f; nb = sqrtf(6.f); }
+    bx /= nb; by /= nb; bz /= nb;
+    const float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+    // mean of the projections, then their unbiased std (two passes like scatter_std)
+    float pu = 0.f, pv = 0.f, pw = 0.f;
+    for (int i = b + lane; i < e; i += 32) {
+      const int64_t j = perm[i];
+      const int64_t ps = sp_src[j], pt = sp_dst[j];
+      const float ox = points[pt * 3] - points[ps * 3];
+      const float oy = points[pt * 3 + 1] - points[ps * 3 + 1];
+      const float oz = points[pt * 3 + 2] - points[ps * 3 + 2];
+      pu += ox * ax + oy * ay + oz * az;
+      pv += ox * bx + oy * by + oz * bz;
+      pw += ox * cx + oy * cy + oz * cz;
+    }
+    pu = warp_sum(pu) * inv; pv = warp_sum(pv) * inv; pw = warp_sum(pw) * inv;
+    float qu = 0.f, qv = 0.f, qw = 0.f;
+    for (int i = b + lane; i < e; i += 32) {
+      const int64_t j = perm[i];
+      const int64_t ps = sp_src[j], pt = sp_dst[j];
+      const float ox = points[pt * 3] - points[ps * 3];
+      const float oy = points[pt * 3 + 1] - points[ps * 3 + 1];
+      const float oz = points[pt * 3 + 2] - points[ps * 3 + 2];
+      const float du = ox * ax + oy * ay + oz * az - pu;
+      const float dv = ox * bx + oy * by + oz * bz - pv;
+      const float dw = ox * cx + oy * cy + oz * cz - pw;
+      qu = fmaf(du, du, qu); qv = fmaf(dv, dv, qv); qw = fmaf(dw, dw, qw);
+    }
+    qu = warp_sum(qu); qv = warp_sum(qv); qw = warp_sum(qw);
+    if (lane == 0) {
+      const float den = (float)max(e - b - 1, 1) + 1e-6f;
+      float* o = out + se * 7;
+      o[0] = mx; o[1] = my; o[2] = mz;
+      o[3] = fminf(fmaxf(sqrtf(qu / den), -2.f), 2.f);
+      o[4] = fminf(fmaxf(sqrtf(qv / den), -2.f), 2.f);
+      o[5] = fminf(fmaxf(sqrtf(qw / den), -2.f), 2.f);
+      o[6] = sqrtf(md);
+    }
+  }
+}
+
 static inline int warps_grid(int64_t rows, int threads, int64_t cap_blocks) {
   int64_t wpb = threads / 32;
   int64_t b = ceil_div(rows, wpb);
@@ -248,7 +358,7 @@ int spt_gather_rows_i64(const float* x, const int64_t* idx, int64_t n_out,
   if (n_out == 0 || C == 0) return SPT_OK;
   SPT_REQUIRE(x && idx && out, SPT_E_INVALID, "gather_rows: null pointer");
   cudaStream_t st = (cudaStream_t)stream_;
-  int grid = warps_grid(n_out, 256, 148 * 32);
+  int grid = warps_grid(n_out, 256, device_sm_count() * 32);
   if (C % 4 == 0)
     k_gather_rows<int64_t, 4><<<grid, 256, 0, st>>>(x, idx, n_out, C, out);
   else
@@ -262,7 +372,7 @@ int spt_gather_rows_i32(const float* x, const int32_t* idx, int64_t n_out,
   if (n_out == 0 || C == 0) return SPT_OK;
   SPT_REQUIRE(x && idx && out, SPT_E_INVALID, "gather_rows: null pointer");
   cudaStream_t st = (cudaStream_t)stream_;
-  int grid = warps_grid(n_out, 256, 148 * 32);
+  int grid = warps_grid(n_out, 256, device_sm_count() * 32);
   if (C % 4 == 0)
     k_gather_rows<int32_t, 4><<<grid, 256, 0, st>>>(x, idx, n_out, C, out);
   else
@@ -298,7 +408,7 @@ int spt_segment_pool_fwd(const float* x, const int32_t* ptr, const int32_t* poin
   if (num_parents == 0 || C == 0) return SPT_OK;
   SPT_REQUIRE(ptr && out, SPT_E_INVALID, "segment_pool_fwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream_;
-  int grid = warps_grid(num_parents, 128, 148 * 64);
+  int grid = warps_grid(num_parents, 128, device_sm_count() * 64);
   SPT_DISPATCH_REDUCE(k_segment_pool_fwd,
                       <<<grid, 128, 0, st>>>(x, ptr, points, num_parents, C, out, arg));
   return check_launch("segment_pool_fwd");
@@ -317,10 +427,35 @@ int spt_segment_pool_bwd(const float* dout, const int64_t* parent, const int32_t
   SPT_REQUIRE((reduce != SPT_REDUCE_MAX && reduce != SPT_REDUCE_MIN) || arg,
               SPT_E_INVALID, "segment_pool_bwd: max/min need arg");
   cudaStream_t st = (cudaStream_t)stream_;
-  int grid = warps_grid(num_children, 256, 148 * 32);
+  int grid = warps_grid(num_children, 256, device_sm_count() * 32);
   SPT_DISPATCH_REDUCE(k_segment_pool_bwd,
                       <<<grid, 256, 0, st>>>(dout, parent, ptr, arg, num_children, C, dx));
   return check_launch("segment_pool_bwd");
+}
+
+int spt_segment_mean_std_fwd(const float* x, const int32_t* ptr, const int32_t* points,
+                             int64_t num_parents, int64_t C, float* mean_out, float* std_out,
+                             void* stream_) {
+  SPT_REQUIRE(num_parents >= 0 && C >= 0, SPT_E_INVALID, "segment_mean_std: negative size");
+  if (num_parents == 0 || C == 0) return SPT_OK;
+  SPT_REQUIRE(x && ptr && (mean_out || std_out), SPT_E_INVALID, "segment_mean_std: null pointer");
+  int grid = warps_grid(num_parents, 128, device_sm_count() * 64);
+  k_segment_mean_std<<<grid, 128, 0, (cudaStream_t)stream_>>>(x, ptr, points, num_parents, C,
+                                                               mean_out, std_out);
+  return check_launch("segment_mean_std_fwd");
+}
+
+int spt_superedge_features_fwd(const float* points, const int64_t* sp_src, const int64_t* sp_dst,
+                               const int32_t* ptr, const int32_t* perm, int64_t num_se,
+                               float* out, void* stream_) {
+  SPT_REQUIRE(num_se >= 0, SPT_E_INVALID, "superedge_features: negative size");
+  if (num_se == 0) return SPT_OK;
+  SPT_REQUIRE(points && sp_src && sp_dst && ptr && perm && out, SPT_E_INVALID,
+              "superedge_features: null pointer");
+  int grid = warps_grid(num_se, 128, device_sm_count() * 64);
+  k_superedge_features<<<grid, 128, 0, (cudaStream_t)stream_>>>(points, sp_src, sp_dst, ptr,
+                                                                 perm, num_se, out);
+  return check_launch("superedge_features_fwd");
 }
 
 size_t spt_unitsphere_workspace_bytes(int64_t num_parents) {
@@ -392,7 +527,7 @@ extern "C" int spt_split_tf32(const float* x, int64_t n, float* hi, float* lo, v
               SPT_E_INVALID, "split_tf32: pointers must be 16-byte aligned");
   int64_t n4 = n >> 2;
   int64_t blocks = spt::ceil_div(n4 > 0 ? n4 : 1, 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > device_sm_count() * 16) blocks = device_sm_count() * 16;
   spt::k_split_tf32<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(x, n4, n, hi, lo);
   return spt::check_launch("split_tf32");
 }

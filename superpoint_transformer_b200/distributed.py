@@ -56,10 +56,18 @@ class FlatGradients:
         parameter (233 for the cfg-2 model); `collect()` packs them afterwards."""
         for p in self.params:
             p.grad = None
+        if self.flat.is_cuda:
+            from . import ops
+            ops.zero_pool.begin_step(self.flat.device)
 
-    def collect(self):
+    def collect(self, accumulate=False):
         """Pack the freshly produced gradients into the flat buffer with one multi-tensor
-        copy and re-point `.grad` at the flat views (missing gradients count as zero)."""
+        copy and re-point `.grad` at the flat views (missing gradients count as zero).
+        `accumulate=True` adds them instead (gradient accumulation over the micro-batches of
+        one optimizer step)."""
+        if self.flat.is_cuda:
+            from . import ops
+            ops.zero_pool.end_step()
         if not hasattr(self, '_views'):
             self._views, off = [], 0
             for p in self.params:
@@ -67,10 +75,14 @@ class FlatGradients:
                 self._views.append(self.flat[off:off + n].view_as(p))
                 off += n
         have = [(v, p.grad) for v, p in zip(self._views, self.params) if p.grad is not None]
-        if len(have) != len(self.params):
-            self.flat.zero_()
-        if have:
-            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        if accumulate:
+            if have:
+                torch._foreach_add_([v for v, _ in have], [g for _, g in have])
+        else:
+            if len(have) != len(self.params):
+                self.flat.zero_()
+            if have:
+                torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
         for v, p in zip(self._views, self.params):
             p.grad = v
 

@@ -40,15 +40,24 @@ class MLP(nn.Module):
     def forward(self, x, batch=None):
         mods = list(self.mlp)
         i = 0
+        fused_out = False   # x is the saved output of a fused norm+activation
         while i < len(mods):
             m = mods[i]
             nxt = mods[i + 1] if i + 1 < len(mods) else None
             if isinstance(m, GraphNorm) and isinstance(nxt, nn.LeakyReLU) and x.is_cuda:
-                # norm + LeakyReLU in one CUDA pass (forward and backward)
+                # norm + LeakyReLU in one CUDA pass (forward and backward); the backward
+                # reads the sign of the saved OUTPUT, so nothing may modify it in place
                 x = m(x, batch=batch, act_slope=nxt.negative_slope)
+                fused_out = True
                 i += 2
                 continue
-            x = m(x, batch=batch) if isinstance(m, INDEX_BASED_NORMS) else m(x)
+            if isinstance(m, nn.Dropout) and m.inplace and fused_out:
+                # the reference's trailing Dropout(inplace=True) (src/nn/mlp.py:56-57) would
+                # overwrite the tensor the fused backward needs: same mask semantics, new tensor
+                x = nn.functional.dropout(x, m.p, self.training, inplace=False)
+            else:
+                x = m(x, batch=batch) if isinstance(m, INDEX_BASED_NORMS) else m(x)
+            fused_out = False
             i += 1
         return x
 

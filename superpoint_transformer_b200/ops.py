@@ -57,6 +57,46 @@ class _timed:
         return False
 
 
+class _ZeroPool:
+    """Per-step pool of pre-zeroed fp32 scratch for accumulate-style outputs (the dW / dbias
+    targets of `spt_gemm_tn_acc`, the packed RPE weight gradients): ONE memset per step
+    instead of one fill kernel per buffer (~280 per cfg-2 step).  Opt-in: a training loop
+    brackets its backward pass with begin_step() / end_step() (FlatGradients.release() /
+    .collect() do); buffers handed out are only valid until the next begin_step(), which is
+    fine for gradients that are packed into the flat buffer right after backward.  Outside
+    such a bracket `take` is torch.zeros."""
+
+    def __init__(self):
+        self.buf, self.off, self.need, self.cur, self.on = None, 0, 0, 0, False
+
+    def begin_step(self, device):
+        if self.buf is None or self.buf.device != device or self.buf.numel() < self.need:
+            self.buf = torch.empty(max(self.need, 1 << 18), dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.off = self.cur = 0
+        self.on = True
+
+    def end_step(self):
+        self.need = max(self.need, self.cur)
+        self.on = False
+
+    def take(self, shape, device):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        n_al = (n + 3) // 4 * 4          # keep every buffer 16-byte aligned
+        self.cur += n_al
+        if (not self.on or self.buf is None or self.buf.device != device
+                or self.off + n_al > self.buf.numel()):
+            return torch.zeros(shape, dtype=torch.float32, device=device)
+        v = self.buf[self.off:self.off + n].view(shape)
+        self.off += n_al
+        return v
+
+
+zero_pool = _ZeroPool()
+
+
 def _require_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
@@ -112,6 +152,16 @@ class SegmentIndex:
         return int(self._err[0].item())
 
 
+_DEBUG_INDEX = bool(int(__import__('os').environ.get('SPT_DEBUG_INDEX', '0')))
+
+
+def set_debug_index(on=True):
+    """validate every index build (host sync): out-of-range super_index / edge_index entries
+    raise IndexError instead of being skipped"""
+    global _DEBUG_INDEX
+    _DEBUG_INDEX = bool(on)
+
+
 def group_index(key, num_groups, other=None):
     lib = _lib.load()
     _require_cuda(key, other)
@@ -120,17 +170,26 @@ def group_index(key, num_groups, other=None):
     n = key.numel()
     dev = key.device
     ptr = torch.empty(num_groups + 1, dtype=torch.int32, device=dev)
-    perm = torch.empty(n, dtype=torch.int32, device=dev)
-    osort = torch.empty(n, dtype=torch.int32, device=dev) if other is not None else None
+    # out-of-range keys are skipped by the kernel: with SPT_DEBUG_INDEX=1 their slots are
+    # zero-initialised and the call syncs and raises like the reference's index error
+    # (default: no host sync on the hot path; valid keys fill every slot)
+    alloc = torch.zeros if _DEBUG_INDEX else torch.empty
+    perm = alloc(n, dtype=torch.int32, device=dev)
+    osort = alloc(n, dtype=torch.int32, device=dev) if other is not None else None
     nbytes = lib.spt_group_index_workspace_bytes(n, num_groups)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _timed('group_index', n=n, G=num_groups, other=other is not None):
         rc = lib.spt_group_index(_p(key), _p(other), n, num_groups, _p(ptr), _p(perm),
                                  _p(osort), _p(ws), nbytes, _stream())
     _lib.check(rc, "spt_group_index")
     _count(8 if other is not None else 7)
     err = ws[:4].view(torch.int32)
-    return SegmentIndex(ptr, perm, osort, n, num_groups, err)
+    seg = SegmentIndex(ptr, perm, osort, n, num_groups, err)
+    if _DEBUG_INDEX:
+        bad = seg.num_invalid_keys()
+        if bad:
+            raise IndexError(f"group_index: {bad} of {n} keys outside [0, {num_groups})")
+    return seg
 
 
 class GraphIndex:
@@ -276,7 +335,7 @@ def _gather_rows(x, idx):
     n_out, C = idx.numel(), x.shape[1]
     out = torch.empty((n_out, C), dtype=x.dtype, device=x.device)
     fn = lib.spt_gather_rows_i32 if idx.dtype == torch.int32 else lib.spt_gather_rows_i64
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed('gather_rows', n=n_out, C=C):
         _lib.check(fn(_p(x), _p(idx), n_out, C, _p(out), _stream()), "spt_gather_rows")
     _count()
     return out
@@ -314,7 +373,38 @@ def permute_rows_cached(x, perm):
     CSR-ordered copy is made once and its gradient accumulates in CSR order."""
     if perm is None:   # edges already in CSR order (mark_csr_ordered)
         return _f32c(x)
-    return _permuted_cache.get(x, ("p", id(perm)), lambda: permute_rows(x, perm))
+    if x.requires_grad and torch.is_grad_enabled():
+        # a cached autograd output would be backpropagated through twice by a second forward
+        # (and would keep the upstream graph alive): the blocks of ONE forward share the copy
+        # through the `edge_attr` object identity + version below, nothing survives a backward
+        hit = _permuted_grad.get('v')
+        if (hit is not None and hit[0]() is x and hit[1] == x._version and hit[2]() is perm
+                and hit[3].grad_fn is not None and not getattr(hit[3], '_spt_used', False)):
+            return hit[3]
+        out = permute_rows(x, perm)
+        if out.grad_fn is not None:
+            out.register_hook(_mark_used(out))
+        _permuted_grad['v'] = (weakref.ref(x), x._version, weakref.ref(perm), out)
+        return out
+    return _permuted_cache.get(x, ("p", id(perm), perm.data_ptr()),
+                               lambda: permute_rows(x, perm))
+
+
+_permuted_grad = {}
+
+
+def _mark_used(t):
+    """once a gradient reaches the shared CSR copy its graph is being consumed: do not hand
+    the same tensor to a later forward"""
+    ref = weakref.ref(t)
+
+    def hook(g):
+        tt = ref()
+        if tt is not None:
+            tt._spt_used = True
+            _permuted_grad.pop('v', None)
+        return g
+    return hook
 
 
 class _IndexUnpool(torch.autograd.Function):
@@ -390,8 +480,8 @@ class _LinearTC(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = _gemm_nt(g, W.t().contiguous())
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dW = torch.zeros((N, K), dtype=torch.float32, device=g.device)
-            db = torch.zeros(N, dtype=torch.float32, device=g.device) if ctx.has_bias else None
+            dW = zero_pool.take((N, K), g.device)
+            db = zero_pool.take((N,), g.device) if ctx.has_bias else None
             with torch.cuda.device(g.device), _timed('gemm_tn', M=M, N=N, K=K):
                 _lib.check(lib.spt_gemm_tn_acc(_p(g), M, N, g.stride(0), _p(x), K, x.stride(0),
                                                _p(dW), K, _p(db), _stream()),
@@ -434,7 +524,7 @@ def _segment_pool_fwd(x, seg, reduce):
     Np, C = seg.num_groups, x.shape[1]
     out = torch.empty((Np, C), dtype=torch.float32, device=x.device)
     arg = torch.empty((Np, C), dtype=torch.int32, device=x.device) if r >= 2 else None
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _timed('segment_pool_fwd', Nc=x.shape[0], Np=Np, C=C, r=r):
         _lib.check(lib.spt_segment_pool_fwd(_p(x), _p(seg.ptr), _p(seg.perm), Np, C, r,
                                             _p(out), _p(arg), _stream()),
                    "spt_segment_pool_fwd")
@@ -460,7 +550,8 @@ class _SegmentPool(torch.autograd.Function):
         g = _f32c(g)
         Nc, C = ctx.shape
         dx = torch.empty((Nc, C), dtype=torch.float32, device=g.device)
-        with torch.cuda.device(g.device):
+        with torch.cuda.device(g.device), _timed('segment_pool_bwd', Nc=Nc, Np=g.shape[0], C=C,
+                                                 r=REDUCE[ctx.reduce]):
             _lib.check(lib.spt_segment_pool_bwd(_p(g), _p(index), _p(ctx.seg.ptr),
                                                 _p(arg) if ctx.has_arg else None, Nc, C,
                                                 REDUCE[ctx.reduce], _p(dx), _stream()),
@@ -477,6 +568,50 @@ def segment_pool(x, index, num_pool, reduce="max", seg=None):
     if seg is None:
         seg = segment_index(index, num_pool)
     return _SegmentPool.apply(_f32c(x), index, seg, reduce)
+
+
+def segment_mean_std(x, index, num_segments_, want_mean=True, want_std=True, seg=None):
+    """(scatter_mean, scatter_std) of torch_scatter over `index` (reference call sites
+    src/transforms/graph.py:266-285, 1025-1044): mean = sum / max(count, 1), unbiased std with
+    the `+ 1e-6` of torch_scatter.  No gradient (preprocessing-time features)."""
+    lib = _lib.load()
+    _require_cuda(x, index)
+    x = _f32c(x.detach())
+    squeeze = x.dim() == 1
+    if squeeze:
+        x = x.view(-1, 1)
+    index = _i64c(index)
+    if seg is None:
+        seg = segment_index(index, num_segments_)
+    C = x.shape[1]
+    mean = torch.empty((num_segments_, C), dtype=torch.float32, device=x.device) if want_mean else None
+    std = torch.empty((num_segments_, C), dtype=torch.float32, device=x.device) if want_std else None
+    with torch.cuda.device(x.device):
+        _lib.check(lib.spt_segment_mean_std_fwd(_p(x), _p(seg.ptr), _p(seg.perm), num_segments_,
+                                                C, _p(mean), _p(std), _stream()),
+                   "spt_segment_mean_std_fwd")
+    _count()
+    if squeeze:
+        mean = None if mean is None else mean.view(-1)
+        std = None if std is None else std.view(-1)
+    return mean, std
+
+
+def superedge_features(points, se_point_index, se_id, num_superedges):
+    """edge_attr [num_superedges, 7] = [mean_off(3) | std_off(3) | mean_dist(1)] of
+    _minimalistic_horizontal_edge_features (reference src/transforms/graph.py:950-1060)."""
+    lib = _lib.load()
+    _require_cuda(points, se_point_index, se_id)
+    points = _f32c(points.detach())
+    spi = _i64c(se_point_index)
+    seg = group_index(_i64c(se_id), num_superedges)
+    out = torch.empty((num_superedges, 7), dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        _lib.check(lib.spt_superedge_features_fwd(_p(points), _p(spi[0]), _p(spi[1]), _p(seg.ptr),
+                                                  _p(seg.perm), num_superedges, _p(out),
+                                                  _stream()), "spt_superedge_features_fwd")
+    _count()
+    return out
 
 
 def node_size(super_index, num_parents, child_size=None):
@@ -520,7 +655,7 @@ def unit_sphere_norm(pos, idx=None, w=None, num_super=None):
     diam = torch.empty((Np, 1), dtype=torch.float32, device=dev)
     nbytes = lib.spt_unitsphere_workspace_bytes(Np)
     ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _timed('unitsphere', N=N, Np=Np):
         _lib.check(lib.spt_unitsphere_fwd(_p(pos), _p(parent), _p(ptr), _p(points), _p(wf),
                                           N, Np, _p(out), _p(diam), _p(ws), nbytes,
                                           _stream()), "spt_unitsphere_fwd")
@@ -542,7 +677,7 @@ class _GraphNorm(torch.autograd.Function):
         rstd = torch.empty((B, C), dtype=torch.float32, device=dev)
         nbytes = lib.spt_graphnorm_workspace_bytes(B, C)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), _timed('graphnorm_fwd', N=N, C=C, B=B):
             _lib.check(lib.spt_graphnorm_fwd(_p(x), _p(batch), N, C, B, _p(weight), _p(bias),
                                              _p(mean_scale), eps, act_slope, _p(y), _p(mean),
                                              _p(rstd), _p(ws), nbytes, _stream()),
@@ -573,7 +708,8 @@ class _GraphNorm(torch.autograd.Function):
         dms = torch.empty(C, dtype=torch.float32, device=dev)
         nbytes = lib.spt_graphnorm_workspace_bytes(ctx.B, C)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), _timed('graphnorm_bwd', N=N, C=C, B=ctx.B,
+                                            act=yact is not None):
             _lib.check(lib.spt_graphnorm_bwd(_p(x), _p(dy), _p(batch), N, C, ctx.B, _p(weight),
                                              _p(mean_scale), _p(mean), _p(rstd), _p(yact),
                                              ctx.act_slope, _p(dx), _p(dw), _p(db), _p(dms),
@@ -748,10 +884,10 @@ class _AttnCore(torch.autograd.Function):
                 and (bq is None) == (bk is None)):
             # one contiguous [2HD, F] / [2HD] pair: lets the library run d[Wq;Wk] = G^T a as a
             # single tensor-core gemm_tn
-            dW2 = torch.zeros((2 * Wq.shape[0], Wq.shape[1]), dtype=torch.float32, device=dev)
+            dW2 = zero_pool.take((2 * Wq.shape[0], Wq.shape[1]), dev)
             dWq, dWk = dW2[:Wq.shape[0]], dW2[Wq.shape[0]:]
             if bq is not None:
-                db2 = torch.zeros(2 * Wq.shape[0], dtype=torch.float32, device=dev)
+                db2 = zero_pool.take((2 * Wq.shape[0],), dev)
                 dbq, dbk = db2[:Wq.shape[0]], db2[Wq.shape[0]:]
             else:
                 dbq = dbk = None
@@ -818,7 +954,8 @@ def horizontal_edge_features(se, edge_attr7, pos, normal, log_length, log_surfac
     E_out = 2 * Eh + (num_nodes if add_self_loops else 0)
     ei = torch.empty((2, E_out), dtype=torch.int64, device=dev)
     out = torch.empty((E_out, 18), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _timed('edge_features', Eh=Eh, N=num_nodes,
+                                        loops=bool(add_self_loops)):
         _lib.check(lib.spt_edge_features_fwd(_p(se), _p(ea), _p(pos), _p(normal), _p(ll), _p(ls),
                                              _p(lv), _p(lz), Eh, num_nodes,
                                              1 if add_self_loops else 0, _p(ei), _p(out),

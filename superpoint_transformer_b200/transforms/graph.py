@@ -11,7 +11,15 @@ import torch
 from .. import ops
 
 __all__ = ['NodeSize', 'OnTheFlyHorizontalEdgeFeatures', 'OnTheFlyVerticalEdgeFeatures',
-           'NAGAddSelfLoops', 'ON_THE_FLY_HORIZONTAL_FEATURES', 'ON_THE_FLY_VERTICAL_FEATURES']
+           'NAGAddSelfLoops', 'ON_THE_FLY_HORIZONTAL_FEATURES', 'ON_THE_FLY_VERTICAL_FEATURES',
+           'minimalistic_horizontal_edge_features', 'cluster_point_features']
+
+# columns of each key in the 18-column output (reference f_list assembly,
+# src/transforms/graph.py:1188-1266: mean_off is PREPENDED, the others appended in this order)
+_H_COLUMNS = {'mean_off': (0, 1, 2), 'std_off': (3, 4, 5), 'mean_dist': (6,),
+              'angle_source': (7,), 'angle_target': (8,), 'normal_angle': (9,),
+              'log_length': (10,), 'log_surface': (11,), 'log_volume': (12,), 'log_size': (13,),
+              'centroid_dir': (14, 15, 16), 'centroid_dist': (17,)}
 
 # column order of the reference's f_list assembly
 ON_THE_FLY_HORIZONTAL_FEATURES = [
@@ -44,7 +52,8 @@ class OnTheFlyHorizontalEdgeFeatures:
     [Eh, 7] (mean_off 3, std_off 3, mean_dist 1; fp16 or fp32), `pos`, `normal`,
     `log_length/log_surface/log_volume/log_size` [N, 1].  Output: `edge_index`
     [2, 2Eh (+N)] ordered [i->j | j->i (| self-loops)], `edge_attr` fp32 18 columns.
-    Only the full default key set is built by the kernel.
+    A subset of `keys` keeps the columns of those keys (in the reference's assembly order);
+    no key at all leaves `edge_attr = None` like the reference.
 
     `csr_order=True` (an extension; the model is invariant to the order of the edges)
     additionally groups the output edges by source node, stably, so that the attention
@@ -55,9 +64,13 @@ class OnTheFlyHorizontalEdgeFeatures:
     def __init__(self, keys=None, use_mean_normal=False, add_self_loops=False,
                  csr_order=False):
         keys = ON_THE_FLY_HORIZONTAL_FEATURES if keys is None else list(keys)
-        if sorted(keys) != sorted(ON_THE_FLY_HORIZONTAL_FEATURES):
-            raise NotImplementedError(
-                "the CUDA edge-feature kernel builds the full 18-column default set")
+        unknown = [k for k in keys if k not in _H_COLUMNS]
+        if unknown:
+            raise ValueError(f"unknown horizontal edge feature keys {unknown}")
+        self.keys = [k for k in ['mean_off'] + [k for k in ON_THE_FLY_HORIZONTAL_FEATURES
+                                                if k != 'mean_off'] if k in keys]
+        cols = [c for k in self.keys for c in _H_COLUMNS[k]]
+        self.columns = None if cols == list(range(18)) else cols
         self.normal_key = 'mean_normal' if use_mean_normal else 'normal'
         self.add_self_loops = add_self_loops
         self.csr_order = csr_order
@@ -73,10 +86,14 @@ class OnTheFlyHorizontalEdgeFeatures:
                 d.edge_index, d.edge_attr, d.pos, d[self.normal_key], d['log_length'],
                 d['log_surface'], d['log_volume'], d['log_size'], d.num_nodes,
                 add_self_loops=self.add_self_loops)
+            if self.columns is not None:   # key subset: the columns of the requested keys
+                ea = ea[:, torch.tensor(self.columns, device=ea.device)].contiguous() \
+                    if self.columns else None
             if self.csr_order:
                 seg = ops.group_index(ei[0], d.num_nodes)
                 ei = ei.index_select(1, seg.perm.long())
-                ea = ops._gather_rows(ea, seg.perm)
+                if ea is not None:
+                    ea = ops._gather_rows(ea, seg.perm)
                 ops.mark_csr_ordered(ei)
             d.edge_index, d.edge_attr = ei, ea
         return nag
@@ -127,3 +144,47 @@ class NAGAddSelfLoops:
                                   device=dev)
                 d.edge_attr = torch.cat((d.edge_attr, pad), dim=0)
         return nag
+
+
+def minimalistic_horizontal_edge_features(data, points, se_point_index, se_id, keys=None):
+    """Superedge features from the level-0 sub-edges of every superedge (reference
+    `_minimalistic_horizontal_edge_features`, src/transforms/graph.py:950-1060): sets
+    `data.edge_attr = [mean_off | std_off | mean_dist]` ([E/2, 7]) for the trimmed
+    `data.edge_index`.  `points` [N0, 3] level-0 positions, `se_point_index` [2, Es] the
+    level-0 end points of each sub-edge, `se_id` [Es] the superedge each sub-edge belongs to.
+    One CUDA pass per superedge (csrc/segment.cu:k_superedge_features) instead of 3 scatters,
+    3 gathers and ~15 elementwise launches."""
+    if keys is not None and not all(k in keys for k in ('mean_off', 'std_off', 'mean_dist')):
+        raise NotImplementedError(
+            "'mean_off', 'std_off' and 'mean_dist' must all be computed (same restriction as "
+            "the reference, src/transforms/graph.py:996-1001)")
+    data.edge_attr = ops.superedge_features(points, se_point_index, se_id,
+                                            data.edge_index.shape[1])
+    return data
+
+
+def cluster_point_features(nag, i_level, mean_keys=(), std_keys=(), strict=True):
+    """The scatter parts of `_compute_cluster_features` (reference
+    src/transforms/graph.py:262-285): `mean_<key>` / `std_<key>` of level-0 point attributes
+    over the level-`i_level` clusters (torch_scatter mean / unbiased std).  The sampled
+    geometric features of :221-258 need `pgeof` and stay on the host (out of scope)."""
+    data = nag[i_level]
+    super_index = nag.get_super_index(i_level)
+    n = data.num_nodes
+    seg = ops.segment_index(super_index, n)
+    for key in dict.fromkeys(list(mean_keys) + list(std_keys)):
+        f = nag[0][key] if key in nag[0].keys else None
+        if f is None:
+            if strict:
+                raise ValueError(f"No point key `{key}` to build 'mean_{key}' / 'std_{key}'")
+            continue
+        if key == 'normal' and key in mean_keys:
+            raise NotImplementedError("mean_normal needs scatter_mean_orientation (PCA), "
+                                      "a preprocessing-only helper outside SURVEY §8")
+        mean, std = ops.segment_mean_std(f.float(), super_index, n, want_mean=key in mean_keys,
+                                         want_std=key in std_keys, seg=seg)
+        if key in mean_keys:
+            data[f'mean_{key}'] = mean
+        if key in std_keys:
+            data[f'std_{key}'] = std
+    return nag

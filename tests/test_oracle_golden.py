@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import path as P
-from helpers import nag_from_golden
+from helpers import nag_from_golden, assert_close, grad_close
 
 TOL = dict(atol=2e-6, rtol=2e-6)
 
@@ -217,3 +217,52 @@ def test_transformer_block_graphwise_norms(golden, name, kind):
     (out * c['probe']).sum().backward()
     torch.testing.assert_close(x.grad, c['dx'], atol=1e-4, rtol=1e-4)
     torch.testing.assert_close(ea.grad, c['dedge_attr'], atol=1e-4, rtol=1e-4)
+
+
+# --------------------------------------------------------------------------- #
+#  round-2 fixtures (tests/golden/round2.pt)
+# --------------------------------------------------------------------------- #
+ATTPOOL = ['attpool_kq', 'attpool_k_shared', 'attpool_plain_inproj', 'attpool_learnt_kq',
+           'attpool_learnt_plain']
+
+
+@pytest.mark.parametrize('name', ATTPOOL)
+def test_attentive_pools(golden, name):
+    """oracle.path.attentive_pool == the reference AttentivePool / AttentivePoolWithLearntQueries
+    (src/nn/pool.py:156-360) on the same inputs, outputs and every gradient."""
+    c = golden('round2.pt')[name]
+    kw = c['kw']
+    sd = {'p.' + k: v.clone().requires_grad_(True) for k, v in c['sd'].items()}
+    xc, xp = c['x_child'].clone().requires_grad_(True), c['x_parent'].clone().requires_grad_(True)
+    ea = None if c['edge_attr'] is None else c['edge_attr'].clone().requires_grad_(True)
+    out = P.attentive_pool(sd, 'p', xc, xp, c['index'], ea, c['num_pool'],
+                           num_heads=kw['num_heads'], qk_dim=kw['qk_dim'],
+                           qk_scale_mode=kw.get('qk_scale'),
+                           heads_share_rpe=kw.get('heads_share_rpe', False),
+                           learnt_queries=c['cls'] == 'AttentivePoolWithLearntQueries')
+    assert_close(out, c['out'], atol=1e-5, rtol=1e-5, what=name)
+    (out * c['probe']).sum().backward()
+    grad_close(xc.grad, c['dx_child'], what=name + ' dx_child')
+    if c['cls'] == 'AttentivePool':
+        grad_close(xp.grad, c['dx_parent'], what=name + ' dx_parent')
+    if ea is not None:
+        grad_close(ea.grad, c['dedge_attr'], what=name + ' dedge_attr')
+    for k, g in c['dparams'].items():
+        grad_close(sd['p.' + k].grad, g, what=f'{name} d{k}')
+
+
+def test_superedge_features(golden):
+    c = golden('round2.pt')['superedge']
+    out = P.minimalistic_horizontal_edge_features(c['points'], c['se_point_index'], c['se_id'],
+                                                  c['edge_index'].shape[1])
+    assert_close(out, c['edge_attr'], atol=1e-6, rtol=1e-6, what='superedge features')
+
+
+def test_horizontal_feature_key_subsets(golden):
+    c = golden('round2.pt')['h_subsets']
+    for name, sub in c['subsets'].items():
+        ei, ea = P.horizontal_edge_features(c['edge_index'], c['edge_attr'], c['pos'], c['normal'],
+                                            c['log_length'], c['log_surface'], c['log_volume'],
+                                            c['log_size'], keys=sub['keys'])
+        assert torch.equal(ei, sub['edge_index'])
+        assert_close(ea, sub['edge_attr'], atol=1e-6, rtol=1e-6, what=f'subset {name}')

@@ -55,9 +55,18 @@ def main():
     torch.cuda.synchronize()
     print(f"enqueue time of one step (host): {t_enq * 1e3:.2f} ms")
     from torch.profiler import profile, ProfilerActivity
-    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
         step()
         torch.cuda.synchronize()
+    # which aten ops launch the glue kernels (fills / copies / adds / reductions), by input shape
+    glue = []
+    for e in prof.key_averages(group_by_input_shape=True):
+        if e.self_device_time_total > 0 and e.key.startswith('aten::'):
+            glue.append((e.self_device_time_total, e.count, e.key, str(e.input_shapes)[:90]))
+    glue.sort(reverse=True)
+    print("aten ops with their own kernels (self device time):")
+    for t_us, n, k, shp in glue[:70]:
+        print(f"{t_us / 1e3:9.3f} ms  x{n:<4d} {k:28s} {shp}")
     rows = []
     for e in prof.key_averages():
         if e.device_time_total > 0:

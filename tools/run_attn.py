@@ -1,0 +1,45 @@
+"""Runs the attention core (fwd + bwd) at a cfg-2 level shape a few times: the command ncu
+captures (tools/README).  N=<rows> ITERS=<n> python tools/run_attn.py; prints CUDA-event times."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from superpoint_transformer_b200 import ops  # noqa: E402
+from superpoint_transformer_b200.synthetic import _trimmed_graph  # noqa: E402
+
+N = int(os.environ.get('N', 100_000))
+ITERS = int(os.environ.get('ITERS', 3))
+MORTON = os.environ.get('SORTED', '0') == '1'
+dev = 'cuda'
+rng = np.random.default_rng(1)
+se = torch.from_numpy(_trimmed_graph(rng, N, 16))
+if MORTON:   # neighbours close in id space (stands for Morton-sorted node ids)
+    off = torch.from_numpy(rng.integers(1, 64, size=se.shape[1]))
+    se = torch.stack((se[0], (se[0] + off) % N))
+ei = torch.cat([se, se.flip(0), torch.arange(N).repeat(2, 1)], dim=1).to(dev)
+order = torch.argsort(ei[0], stable=True)
+ei = ei[:, order].contiguous()
+ops.mark_csr_ordered(ei)
+gi = ops.build_graph_index(ei, N)
+E = ei.shape[1]
+H, D, C, F = 4, 4, 128, 32
+g = torch.Generator().manual_seed(0)
+qkv = torch.randn(N, 2 * H * D + C, generator=g).to(dev).requires_grad_(True)
+a = torch.randn(E, F, generator=g).to(dev).requires_grad_(True)
+mk = lambda *s: (torch.randn(*s, generator=g) * 0.2).to(dev).requires_grad_(True)  # noqa: E731
+Wq, bq, Wk, bk = mk(16, 32), mk(16), mk(16, 32), mk(16)
+ops.enable_event_timing(True)
+for it in range(ITERS):
+    agg, abar, sump = ops.attention_core(qkv, None, a, Wq, bq, Wk, bk, gi, H, D,
+                                         ops.SCALE_D_TIMES_G, 32 ** -0.5)
+    (agg.sum() + abar.sum()).backward()
+torch.cuda.synchronize()
+acc = {}
+for tag, meta, s, e in ops.timing_records():
+    acc.setdefault(tag, []).append(s.elapsed_time(e))
+print(f'N={N} E={E} sorted={MORTON}')
+for k, v in acc.items():
+    print(f'  {k}: min {min(v):.4f} ms  last {v[-1]:.4f} ms')
