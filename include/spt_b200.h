@@ -136,6 +136,40 @@ int spt_gemm_tn_acc(const float* A, int64_t M, int64_t N, int64_t lda, const flo
                     float* colsumA /*nullable*/, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ *  On-device batch construction (src/data/nag.py:878-898, data.py:1154-1242,  *
+ *  csr.py:676-757): offset-concatenation of int64 index tensors                *
+ * ------------------------------------------------------------------------- */
+
+/* out[prefix[s] + j] = srcs[s][j (+1 if skip_first and s > 0)] + offsets[s] for the
+ * `num_segments` device arrays srcs[s] (device table of device pointers); prefix [S+1] =
+ * exclusive scan of the emitted lengths (device), offsets [S] (device, nullable = 0).
+ * srcs == NULL writes the segment id (the `batch` vector of Batch.from_data_list).
+ * skip_first = 1 concatenates CSR pointer arrays (element 0 of later items dropped). */
+int spt_concat_offset_i64(const int64_t* const* srcs, const int64_t* prefix,
+                          const int64_t* offsets, int num_segments, int64_t total,
+                          int skip_first, int64_t* out, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ *  Value RPE of SelfAttentionBlock (src/nn/attention.py:294-301), applied        *
+ *  algebraically: y = agg + Wbd . abar + bv (x) sump  (csrc/vrpe.cu)              *
+ * ------------------------------------------------------------------------- */
+
+/* Wbd [C, H*F] = blockdiag(Wv[h*Dv:(h+1)*Dv, :]) (transpose = 0) or its transpose
+ * [H*F, C] (transpose = 1); heads_share: Wv is the single-head encoder [Dv, F]. */
+int spt_vrpe_blockdiag(const float* Wv, int H, int Dv, int F, int heads_share, int transpose,
+                       float* out, void* stream);
+
+/* y[n, c] = agg[n, c] + rv[n, c] + sump[n, c / Dv] * bv[c]   (rv, bv nullable) */
+int spt_vrpe_epilogue(const float* agg, const float* rv, const float* sump, const float* bv,
+                      int64_t N, int H, int Dv, int heads_share, float* y, void* stream);
+
+/* parameter gradients: dbv[c] += sum_n dy[n, c] sump[n, c / Dv];
+ * dWv += diagonal blocks of dWbd [C, H*F] (summed over heads when shared).  Accumulating. */
+int spt_vrpe_bwd_params(const float* dy, const float* sump, const float* dWbd, int64_t N, int H,
+                        int Dv, int F, int heads_share, float* dWv /*nullable*/,
+                        float* dbv /*nullable*/, void* stream);
+
+/* ------------------------------------------------------------------------- *
  *  Segment pooling  (src/nn/pool.py:44-82 -> PyG *Aggregation -> scatter)    *
  * ------------------------------------------------------------------------- */
 

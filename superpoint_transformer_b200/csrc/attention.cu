@@ -505,11 +505,18 @@ static int tile_rows_per_warp(int64_t num_rows, int warps_per_cta) {
     if (r >= 1 && r <= 64) return r;
   }
   const int sms = device_sm_count();
-  const int64_t target_warps = (int64_t)sms * warps_per_cta * 4;   // >= 4 waves of 1 CTA/SM
+  const int64_t target_warps = (int64_t)sms * 2 * warps_per_cta * 3;   // >= 3 waves, 2 CTAs/SM
   int64_t r = num_rows / target_warps;
   if (r < 1) r = 1;
-  if (r > 16) r = 16;
+  if (r > 8) r = 8;
   return (int)r;
+}
+
+// boxes of 8 / 16 / 24 / 32 rows x 32 columns over the CSR-ordered edge features [E, 32]
+static bool make_tile_maps(tile::TileMaps* tm, const float* a, int64_t E, int F) {
+  for (int i = 0; i < 4; ++i)
+    if (!umma::make_map_rows32(&tm->m[i], a, E, F, 8 * (i + 1))) return false;
+  return true;
 }
 
 static bool tile_layout_ok(const float* q, const float* k, const float* v, const float* a,
@@ -540,8 +547,8 @@ int spt_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const
               SPT_E_INVALID, "attn_fwd: bad scale mode %d", scale_mode);
   cudaStream_t st = (cudaStream_t)stream_;
   if (a && tile::shape_ok(H, D, Dv, F) && tile_layout_ok(q, k, v, a, ldq, ldk, ldv, num_rows, E)) {
-    CUtensorMap tmA;
-    if (umma::make_map_rows32(&tmA, a, E, F, 8)) {
+    tile::TileMaps tmA;
+    if (make_tile_maps(&tmA, a, E, F)) {
       tile::FwdArgs A;
       A.q = q; A.ldq = (int)ldq; A.k = k; A.ldk = (int)ldk; A.v = v; A.ldv = (int)ldv;
       A.rowptr = rowptr; A.col = col; A.num_rows = num_rows;
@@ -613,8 +620,8 @@ int spt_attn_bwd_rows(const float* q, int64_t ldq, const float* k, int64_t ldk,
       ((uintptr_t)G & 7) == 0 && (!da || ((uintptr_t)da & 7) == 0) &&
       ((uintptr_t)d_agg_v & 15) == 0 && ((uintptr_t)agg_v & 15) == 0 &&
       (!abar || ((uintptr_t)abar & 15) == 0) && (!d_abar || ((uintptr_t)d_abar & 15) == 0)) {
-    CUtensorMap tmA;
-    if (umma::make_map_rows32(&tmA, a, E, F, 8)) {
+    tile::TileMaps tmA;
+    if (make_tile_maps(&tmA, a, E, F)) {
       tile::BwdArgs A;
       A.q = q; A.ldq = (int)ldq; A.k = k; A.ldk = (int)ldk; A.v = v; A.ldv = (int)ldv;
       A.rowptr = rowptr; A.col = col; A.num_rows = num_rows;

@@ -52,30 +52,59 @@ constexpr int kH = 4, kD = 4, kDv = 32, kF = 32;
 constexpr int kHD = kH * kD;          // 16
 constexpr int kHD2 = 2 * kHD;         // 32
 constexpr int kC = kH * kDv;          // 128
-constexpr int kChunk = 32;            // CSR slots per ring chunk = 4 TMA boxes of 8 rows
-constexpr int kRing = 3;              // chunks per warp: <= 2 under the current tile + 1 in flight
+constexpr int kChunk = 32;            // CSR slots per tile stage = 4 TMA boxes of 8 rows
 constexpr int kChunkBytes = kChunk * kF * 4;     // 4096
-constexpr int kRingSlots = kRing * kChunk;       // 96
 constexpr int kFragBytes = 16 * 32 * 16;         // one pre-split weight fragment set (8 KB)
 
-constexpr int kVStageBytes = 32 * kC * 4;        // gathered v rows of one tile (16 KB)
-
-// one CTA per SM (the per-warp staging buffers take the shared memory), 7 warps: the register
-// file then allows up to 255 registers per thread, i.e. no spills in either kernel
-constexpr int kFwdWarps = 7;
-constexpr int kBwdWarps = 7;
+// 2 CTAs per SM: forward 8 warps x 128 registers, backward 6 warps x 168 registers.  The
+// kernels are bound by instruction latency (dependent ALU / shuffle / LDS chains per row), so
+// resident warps per scheduler (4 / 3) are what hides it; shared memory per warp is 9-10 KB.
+constexpr int kFwdWarps = 8;
+constexpr int kBwdWarps = 6;
 
 __host__ __device__ inline bool shape_ok(int H, int D, int Dv, int F) {
   return H == kH && D == kD && Dv == kDv && F == kF;
 }
 
-__device__ __forceinline__ void tma_box(void* dst, const CUtensorMap* tm, int row, uint64_t* bar) {
+// one 2-D TMA box of the edge-feature matrix (rows `row`.. of the map's box height), L2
+// evict-first: the features are streamed once per kernel and must not push the gathered node
+// rows (k / v, re-read ~17 times) out of the L2
+__device__ __forceinline__ void tma_box(void* dst, const CUtensorMap* tm, int row, uint64_t* bar,
+                                        uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
-      "l"(tm), "r"(smem_u32(bar)), "r"(0), "r"(row)
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(0), "r"(row), "l"(policy)
       : "memory");
 }
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+// gathered node rows: read-only path, no L1 allocation, L2 evict-last
+__device__ __forceinline__ ulonglong2 ldg_row16(const char* p, uint64_t policy) {
+  ulonglong2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u64 {%0,%1}, [%2], %3;"
+               : "=l"(v.x), "=l"(v.y) : "l"(p), "l"(policy));
+  return v;
+}
+__device__ __forceinline__ float2 ldg_row8(const char* p, uint64_t policy) {
+  float2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;"
+               : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(policy));
+  return v;
+}
+// the four tensor maps of the edge-feature matrix: boxes of 8 / 16 / 24 / 32 rows, so that a
+// tile of any size is ONE TMA instruction
+struct TileMaps {
+  CUtensorMap m[4];
+};
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
                                         uint32_t& r3) {
@@ -117,59 +146,61 @@ __device__ __forceinline__ float2 ldg_stream2(const float* p) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Warp-private ring of edge-feature chunks.  Chunk j covers the CSR slots
-// [base + 32 j, base + 32 j + 32) of the warp's slab and lives in stage j % 3; its 8-row boxes
-// arrive by 2-D TMA on the stage's mbarrier (phase parity (j / 3) & 1).  Slot s of the slab
-// sits at physical row (s - base) % 96 of the ring; inside a row the 16-byte chunk c is at
-// c ^ (row & 7) (SWIZZLE_128B; the ring and every stage start on 1024-byte boundaries).
+// Warp-private double buffer of edge-feature tiles.  A tile = the <= 32 CSR slots
+// [tb, tb + n) of one row; its rows arrive as ceil(n / 8) 2-D TMA boxes (8 rows x 128 B,
+// SWIZZLE_128B) at the START of a 4 KB stage (1024-byte aligned), so the 16-byte chunk c of
+// tile row r always sits at r * 128 + ((c ^ (r & 7)) << 4): every ldmatrix / LDS address of
+// the consumers is a per-lane constant plus the stage base.  While tile i is consumed the
+// TMA of tile i + 1 (normally the next row) is in flight in the other stage.  The boxes
+// over-fetch up to 7 slots past the tile's end (other rows' features, L2-resident; slots
+// past E are zero-filled by the TMA).
 // ---------------------------------------------------------------------------------------
-struct Ring {
-  unsigned char* buf;
-  uint64_t* bar;
-  const CUtensorMap* tm;
-  int64_t base;
-  int slab;      // slots in the slab
-  int nchunks, issued, ready;
+struct TilePipe {
+  unsigned char* buf;       // 2 stages x 4 KB
+  uint64_t* bar;            // 2 mbarriers
+  const TileMaps* tm;
+  uint64_t policy;
   int lane;
+  uint32_t uses0, uses1;    // completed uses of each stage (phase parity)
+  int staged_tb;            // first slot of the tile in flight in stage `next`, -1 if none
+  int cur;                  // stage holding the current tile
 
-  __device__ __forceinline__ void init(int64_t e0, int64_t e1) {
-    base = e0;
-    slab = (int)(e1 - e0);
-    nchunks = (slab + kChunk - 1) / kChunk;
-    issued = ready = 0;
+  __device__ __forceinline__ void init() {
     if (lane == 0) {
-#pragma unroll
-      for (int s = 0; s < kRing; ++s) mbar_init(&bar[s], 1);
+      mbar_init(&bar[0], 1);
+      mbar_init(&bar[1], 1);
       mbar_fence_init();
     }
+    uses0 = uses1 = 0;
+    staged_tb = -1;
+    cur = 1;
     __syncwarp();
-    while (issued < nchunks && issued < kRing) issue_one();
   }
-  __device__ __forceinline__ void issue_one() {
-    const int j = issued;
+  __device__ __forceinline__ void issue(int stage, int tb, int n) {
     if (lane == 0) {
-      const int s0 = j * kChunk;
-      const int rows = min(kChunk, slab - s0);
-      const int nb = (rows + 7) >> 3;
-      const int stage = j % kRing;
+      const int nb = (n + 7) >> 3;     // 1..4 boxes of 8 rows = one box of the nb-th map
       unsigned char* dst = buf + stage * kChunkBytes;
       mbar_expect_tx(&bar[stage], (uint32_t)nb * 1024u);
-      for (int b = 0; b < nb; ++b)
-        tma_box(dst + b * 1024, tm, (int)(base + s0 + 8 * b), &bar[stage]);
+      tma_box(dst, &tm->m[nb - 1], tb, &bar[stage], policy);
     }
-    ++issued;
   }
-  // make the slab-relative slots [o, o + n) readable; returns their first physical row
-  __device__ __forceinline__ int prepare(int o, int n) {
-    const int c_lo = o / kChunk, c_hi = (o + n - 1) / kChunk;
-    __syncwarp();   // every lane is done with the chunks below c_lo
-    while (issued < nchunks && issued < c_lo + kRing) issue_one();
-    while (ready <= c_hi) {
-      mbar_wait(&bar[ready % kRing], (uint32_t)((ready / kRing) & 1), ready, o);
-      ++ready;
-    }
+  // start fetching the tile that will be consumed after the current one
+  __device__ __forceinline__ void prefetch(int tb, int n) {
+    issue(cur ^ 1, tb, n);
+    staged_tb = tb;
+  }
+  // make tile [tb, tb + n) current; returns the shared-memory address of its first row.
+  // All lanes must have finished reading the stage that gets recycled (callers __syncwarp).
+  __device__ __forceinline__ uint32_t acquire(int tb, int n) {
+    const int st = cur ^ 1;
+    if (staged_tb != tb) issue(st, tb, n);     // not prefetched (first tile / after empty rows)
+    staged_tb = -1;
+    cur = st;
+    const uint32_t par = (st ? uses1 : uses0) & 1u;
+    mbar_wait(&bar[st], par, tb, n);
+    if (st) ++uses1; else ++uses0;
     __syncwarp();
-    return o % kRingSlots;
+    return smem_u32(buf + st * kChunkBytes);
   }
 };
 
@@ -217,12 +248,11 @@ __device__ __forceinline__ void build_bias(float* bias_s, const float* Wq, const
   }
 }
 
-// R = A_tile . W^T + bias for the tile whose first physical ring row is `prow`:
+// R = A_tile . W^T + bias for the tile at shared-memory address `tile`:
 // acc[m][nn][.] = accumulator fragments (m-tile m = edges 16m..16m+15, n-tile nn = outputs
 // 8nn..8nn+7): c0,c1 = (edge 16m+g, outputs 8nn+2t, +1), c2,c3 = (edge 16m+8+g, same outputs).
-__device__ __forceinline__ void rpe_tile(float (&acc)[2][4][4], const unsigned char* ring,
-                                         int prow, bool two, const uint4* frag1,
-                                         const float* bias_s, int lane) {
+__device__ __forceinline__ void rpe_tile(float (&acc)[2][4][4], uint32_t tile, bool two,
+                                         const uint4* frag1, const float* bias_s, int lane) {
   const int t = lane & 3;
 #pragma unroll
   for (int nn = 0; nn < 4; ++nn) {
@@ -232,24 +262,18 @@ __device__ __forceinline__ void rpe_tile(float (&acc)[2][4][4], const unsigned c
       acc[m][nn][0] = b.x; acc[m][nn][1] = b.y; acc[m][nn][2] = b.x; acc[m][nn][3] = b.y;
     }
   }
-  // ldmatrix row addresses: lane L feeds row 16m + (L&7) + 8*((L>>3)&1) of matrix L>>3
-  uint32_t rowaddr[2], rsw[2];
-#pragma unroll
-  for (int m = 0; m < 2; ++m) {
-    int r = prow + 16 * m + (lane & 7) + ((lane >> 3) & 1) * 8;
-    if (r >= kRingSlots) r -= kRingSlots;
-    rowaddr[m] = smem_u32(ring + r * 128);
-    rsw[m] = (uint32_t)(r & 7);
-  }
-  const uint32_t csel = (uint32_t)(lane >> 4);
+  // ldmatrix: lane L feeds tile row 16m + (L&7) + 8*((L>>3)&1) of matrix L>>3; (row & 7) = L & 7
+  const uint32_t row0 = tile + (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * 128);
+  const uint32_t rsw = (uint32_t)(lane & 7), csel = (uint32_t)(lane >> 4);
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
+    const uint32_t coff = ((2 * kk + csel) ^ rsw) << 4;
     uint4 b[4];
 #pragma unroll
     for (int nn = 0; nn < 4; ++nn) b[nn] = frag1[(kk * 4 + nn) * 32 + lane];
     {
       uint32_t a[4], ahi[4], alo[4];
-      ldsm_x4(rowaddr[0] + (((2 * kk + csel) ^ rsw[0]) << 4), a[0], a[1], a[2], a[3]);
+      ldsm_x4(row0 + coff, a[0], a[1], a[2], a[3]);
 #pragma unroll
       for (int i = 0; i < 4; ++i) split_tf32(a[i], ahi[i], alo[i]);
 #pragma unroll
@@ -257,7 +281,7 @@ __device__ __forceinline__ void rpe_tile(float (&acc)[2][4][4], const unsigned c
     }
     if (two) {   // warp-uniform: rows 16..31 of the tile hold edges
       uint32_t a[4], ahi[4], alo[4];
-      ldsm_x4(rowaddr[1] + (((2 * kk + csel) ^ rsw[1]) << 4), a[0], a[1], a[2], a[3]);
+      ldsm_x4(row0 + 16 * 128 + coff, a[0], a[1], a[2], a[3]);
 #pragma unroll
       for (int i = 0; i < 4; ++i) split_tf32(a[i], ahi[i], alo[i]);
 #pragma unroll
@@ -266,15 +290,78 @@ __device__ __forceinline__ void rpe_tile(float (&acc)[2][4][4], const unsigned c
   }
 }
 
-// gathered value rows of a tile: lane e copies v[col_e, 0:128] (512 B) into slot e of the
-// warp's staging buffer with ONE bulk async copy (cp.async.bulk, completion on `bar`); issued
-// at the start of the tile, consumed after the tensor-core phase and the softmax.
-__device__ __forceinline__ void stage_v(unsigned char* v_s, uint64_t* bar, const float* v,
-                                        unsigned ldv, int mycol, int n, int lane) {
-  if (lane == 0) mbar_expect_tx(bar, (uint32_t)n * (kC * 4));
-  __syncwarp();
-  if (lane < n)
-    fast::tma_load_1d(v_s + lane * (kC * 4), v + (size_t)((unsigned)mycol * ldv), kC * 4, bar);
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// my 16-byte chunk of tile row r (the row's features 4*(lane&7)..): r*128 + ((l7 ^ (r&7)) << 4)
+template <bool ALIGNED>
+__device__ __forceinline__ ulonglong2 lds_a_chunk(uint32_t tile, int e0, int u, uint32_t l7s) {
+  uint32_t ad;
+  if (ALIGNED) {   // e0 % 8 == 0: (e0 + u) & 7 == u, a compile-time constant
+    ad = tile + (uint32_t)(e0 * 128) + (uint32_t)(u * 128) + (l7s ^ (uint32_t)(u << 4));
+  } else {
+    const uint32_t r = (uint32_t)(e0 + u);
+    ad = tile + r * 128u + (l7s ^ ((r & 7u) << 4));
+  }
+  ulonglong2 a4;
+  asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(a4.x), "=l"(a4.y) : "r"(ad));
+  return a4;
+}
+
+// accumulation phase of the forward: CNT consecutive edges of the tile starting at e0, no
+// per-edge predicates (the caller decomposes n into 8 + 4 + 2 + 1): CNT gathered v rows in
+// flight, then per edge one LDS.64 (p, p), one LDS.128 of the staged feature row, 4 packed FMAs
+template <int CNT, bool ALIGNED>
+__device__ __forceinline__ void fwd_accumulate(int e0, int mycol, const char* vbase,
+                                               unsigned ldvb, uint64_t keep, const f32x2* pcol,
+                                               uint32_t tile, uint32_t l7s, bool want_abar,
+                                               f32x2& accv01, f32x2& accv23, f32x2& acca01,
+                                               f32x2& acca23) {
+  ulonglong2 vv[CNT];
+#pragma unroll
+  for (int u = 0; u < CNT; ++u) {
+    const unsigned tc = (unsigned)__shfl_sync(kFull, mycol, e0 + u);
+    vv[u] = ldg_row16(vbase + (uint64_t)tc * (uint64_t)ldvb, keep);
+  }
+#pragma unroll
+  for (int u = 0; u < CNT; ++u) {
+    const f32x2 pp = pcol[(e0 + u) * kH];
+    fma2(accv01, pp, vv[u].x);
+    fma2(accv23, pp, vv[u].y);
+    if (want_abar) {
+      const ulonglong2 a4 = lds_a_chunk<ALIGNED>(tile, e0, u, l7s);
+      fma2(acca01, pp, a4.x);
+      fma2(acca23, pp, a4.y);
+    }
+  }
+}
+
+// backward: dp = <dY, v> + <dAbar, a> partial sums of CNT (<= 8) edges -> s[0..CNT)
+template <int CNT, bool ALIGNED>
+__device__ __forceinline__ void bwd_partials(float (&s)[8], int e0, int mycol, const char* vbase,
+                                             unsigned ldvb, uint64_t keep, uint32_t tile,
+                                             uint32_t l7s, bool has_dab, f32x2 dy01, f32x2 dy23,
+                                             f32x2 dab01, f32x2 dab23) {
+  ulonglong2 vv[CNT];
+#pragma unroll
+  for (int u = 0; u < CNT; ++u) {
+    const unsigned tc = (unsigned)__shfl_sync(kFull, mycol, e0 + u);
+    vv[u] = ldg_row16(vbase + (uint64_t)tc * (uint64_t)ldvb, keep);
+  }
+#pragma unroll
+  for (int u = 0; u < CNT; ++u) {
+    f32x2 d2 = mul2(dy01, vv[u].x);
+    fma2(d2, dy23, vv[u].y);
+    if (has_dab) {
+      const ulonglong2 a4 = lds_a_chunk<ALIGNED>(tile, e0, u, l7s);
+      fma2(d2, dab01, a4.x);
+      fma2(d2, dab23, a4.y);
+    }
+    s[u] = fast::hsum2(d2);
+  }
 }
 
 struct FwdArgs {
@@ -290,86 +377,102 @@ struct FwdArgs {
 };
 
 // shared memory (after 1024-byte alignment):
-//   [kWarps x edge-feature ring 12 KB][kWarps x gathered-v stage 16 KB]
-//   [weight fragments NFRAG x 8 KB][bias 128 B][mbarriers 4 per warp][kWarps x NP x p tile 512 B]
-template <int kWarps, int NFRAG, int NP>
+//   [kWarps x 2 tile stages 8 KB][weight fragments NFRAG x 8 KB][bias 128 B]
+//   [mbarriers 2 per warp][kWarps x p tile 1 KB]
+template <int kWarps, int NFRAG>
 struct Smem {
-  static constexpr int ring_off = 0;
-  static constexpr int v_off = kWarps * kRing * kChunkBytes;
-  static constexpr int frag_off = v_off + kWarps * kVStageBytes;
+  static constexpr int tile_off = 0;
+  static constexpr int frag_off = kWarps * 2 * kChunkBytes;
   static constexpr int bias_off = frag_off + NFRAG * kFragBytes;
   static constexpr int bar_off = bias_off + 128;
-  static constexpr int p_off = bar_off + kWarps * 4 * 8;
-  static constexpr int total = p_off + kWarps * NP * 32 * kH * 4;
+  static constexpr int p_off = bar_off + kWarps * 2 * 8;
+  static constexpr int total = p_off + kWarps * 32 * kH * 8;
 };
-using FwdSmem = Smem<kFwdWarps, 1, 1>;
-using BwdSmem = Smem<kBwdWarps, 2, 1>;
+using FwdSmem = Smem<kFwdWarps, 1>;
+using BwdSmem = Smem<kBwdWarps, 2>;
 
-// per-row operands fetched one row ahead (rowptr -> col -> gathered rows is otherwise a chain
-// of dependent memory latencies at the start of every row)
-struct RowAhead {
-  int e_next;       // rowptr[row + 2]
-  int col_next;     // col[first tile of row + 1][lane]
-  float2 qA, qB;    // q[row + 1][2t..], q[row + 1][8 + 2t..]
+// the warp's position in its list of tiles + the operands fetched one tile / one row ahead
+// (rowptr -> col -> gathered rows is otherwise a chain of dependent latencies per row)
+struct Cursor {
+  int64_t row, row1;
+  int b, e;          // CSR range of `row`
+  int e_next;        // rowptr[row + 2] (end of the next row), valid while row + 1 < row1
+  int e_end;         // end of the warp's slab
+  const int32_t* rowptr;
+  const int32_t* col;
+  int lane;
+  int col_next;      // col[first tile of the next tile][lane]
+  int tb_next, n_next;   // the tile after the current one (n_next = 0: none / not known)
+
+  // called when starting tile [tb, tb + n) of the current row: what comes after it?
+  __device__ __forceinline__ void look_ahead(int tb, int n) {
+    if (tb + 32 < e) { tb_next = tb + 32; n_next = min(32, e - tb_next); }
+    else if (row + 1 < row1) { tb_next = e; n_next = min(32, e_next - e); }
+    else { tb_next = e; n_next = 0; }
+    col_next = (n_next > 0 && lane < n_next) ? col[tb_next + lane] : 0;
+  }
 };
 
-__global__ void __launch_bounds__(kFwdWarps * 32, 1)
-k_attn_fwd_tile(const __grid_constant__ CUtensorMap tmA, const FwdArgs P) {
+__global__ void __launch_bounds__(kFwdWarps * 32, 2)
+k_attn_fwd_tile(const __grid_constant__ TileMaps tmA, const FwdArgs P) {
   using L = FwdSmem;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem =
       smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);   // SWIZZLE_128B atoms
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  uint4* frag1 = reinterpret_cast<uint4*>(smem + L::frag_off);
-  float* bias_s = reinterpret_cast<float*>(smem + L::bias_off);
-  float* p_s = reinterpret_cast<float*>(smem + L::p_off) + w * 32 * kH;
-  unsigned char* v_s = smem + L::v_off + w * kVStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bar_off) + w * 4;
+  const uint4* frag1 = reinterpret_cast<const uint4*>(smem + L::frag_off);
+  const float* bias_s = reinterpret_cast<const float*>(smem + L::bias_off);
+  float2* p_s = reinterpret_cast<float2*>(smem + L::p_off) + w * 32 * kH;   // (p, p) pairs
 
-  build_frag1(frag1, P.Wq, P.Wk);
-  build_bias(bias_s, P.Wq, P.bq, P.Wk, P.bk);
+  build_frag1(reinterpret_cast<uint4*>(smem + L::frag_off), P.Wq, P.Wk);
+  build_bias(reinterpret_cast<float*>(smem + L::bias_off), P.Wq, P.bq, P.Wk, P.bk);
   __syncthreads();
 
   const int64_t gw = (int64_t)blockIdx.x * kFwdWarps + w;
   const int64_t row0 = gw * P.rows_per_warp;
   if (row0 >= P.num_rows) return;
-  const int64_t row1 = min(row0 + (int64_t)P.rows_per_warp, P.num_rows);
 
-  Ring ring;
-  ring.buf = smem + L::ring_off + w * (kRing * kChunkBytes);
-  ring.bar = bars;
-  ring.tm = &tmA;
-  ring.lane = lane;
-  uint64_t* vbar = bars + 3;
-  if (lane == 0) mbar_init(vbar, 1);
-  const int e_begin = P.rowptr[row0];
-  const int e_end = P.rowptr[row1];
-  ring.init(e_begin, e_end);   // (fences the mbarrier inits, syncs the warp)
+  TilePipe pipe;
+  pipe.buf = smem + L::tile_off + w * (2 * kChunkBytes);
+  pipe.bar = reinterpret_cast<uint64_t*>(smem + L::bar_off) + w * 2;
+  pipe.tm = &tmA;
+  pipe.policy = policy_evict_first();
+  pipe.lane = lane;
+  pipe.init();
+  const uint64_t keep = policy_evict_last();
+
+  Cursor cu;
+  cu.row = row0;
+  cu.row1 = min(row0 + (int64_t)P.rows_per_warp, P.num_rows);
+  cu.rowptr = P.rowptr; cu.col = P.col; cu.lane = lane;
+  cu.b = P.rowptr[row0];
+  cu.e = P.rowptr[row0 + 1];
+  cu.e_next = (row0 + 1 < cu.row1) ? P.rowptr[row0 + 2] : cu.e;
+  cu.e_end = P.rowptr[cu.row1];
 
   const bool want_abar = P.abar != nullptr;
   const int hb = lane >> 3;                     // head of my 4 value channels
   const int hsrc = 2 * (hb & 1);                // a lane holding head hb in the fragment layout
-  const float* kbase = P.k + 2 * t;
-  const unsigned ldk = (unsigned)P.ldk, ldv = (unsigned)P.ldv;
-  uint32_t vtile = 0;                           // tiles staged so far (phase parity of vbar)
+  const int pw = ((hb & 1) << 1) | (hb >> 1);   // word of head hb in a p-tile row [h0 h2 h1 h3]
+  const char* kbase = reinterpret_cast<const char*>(P.k + 2 * t);
+  const char* vbase = reinterpret_cast<const char*>(P.v + 4 * lane);
+  const unsigned ldkb = (unsigned)P.ldk * 4u, ldvb = (unsigned)P.ldv * 4u;   // row strides, bytes
+  // byte offset of my 16-byte chunk in tile row u of a group of 8: u * 128 + ((l7 ^ u) << 4)
+  const uint32_t l7s = (uint32_t)((lane & 7) << 4);
 
-  int b = e_begin;
-  RowAhead nx;
-  nx.e_next = P.rowptr[row0 + 1];
-  nx.col_next = (b + lane < e_end) ? P.col[b + lane] : 0;
-  nx.qA = *reinterpret_cast<const float2*>(P.q + row0 * P.ldq + 2 * t);
-  nx.qB = *reinterpret_cast<const float2*>(P.q + row0 * P.ldq + 8 + 2 * t);
+  int mycol = (lane < min(32, cu.e - cu.b)) ? P.col[cu.b + lane] : 0;
+  float2 qA = *reinterpret_cast<const float2*>(P.q + row0 * P.ldq + 2 * t);
+  float2 qB = *reinterpret_cast<const float2*>(P.q + row0 * P.ldq + 8 + 2 * t);
 
-  for (int64_t row = row0; row < row1; ++row) {
-    const int e = nx.e_next;
-    int mycol = nx.col_next;
-    float2 qA = nx.qA, qB = nx.qB;
-    if (row + 1 < row1) {   // operands of the next row
-      nx.e_next = P.rowptr[row + 2];
-      nx.col_next = (e + lane < e_end) ? P.col[e + lane] : 0;
-      nx.qA = *reinterpret_cast<const float2*>(P.q + (row + 1) * P.ldq + 2 * t);
-      nx.qB = *reinterpret_cast<const float2*>(P.q + (row + 1) * P.ldq + 8 + 2 * t);
+  for (; cu.row < cu.row1; ++cu.row) {
+    const int64_t row = cu.row;
+    const int b = cu.b, e = cu.e;
+    // q of the next row
+    float2 qA_n = qA, qB_n = qB;
+    if (row + 1 < cu.row1) {
+      qA_n = *reinterpret_cast<const float2*>(P.q + (row + 1) * P.ldq + 2 * t);
+      qB_n = *reinterpret_cast<const float2*>(P.q + (row + 1) * P.ldq + 8 + 2 * t);
     }
     const float scale = fast::qk_scale_fast(P.scale_mode, P.scale_value, e - b);
     qA.x *= scale; qA.y *= scale; qB.x *= scale; qB.y *= scale;
@@ -379,24 +482,26 @@ k_attn_fwd_tile(const __grid_constant__ CUtensorMap tmA, const FwdArgs P) {
     for (int tb = b; tb < e; tb += 32) {
       const int n = min(32, e - tb);
       const bool two = n > 16;
-      if (tb != b) mycol = (lane < n) ? P.col[tb + lane] : 0;
-      __syncwarp();                              // previous tile's v / p stages are free
-      stage_v(v_s, vbar, P.v, ldv, mycol, n, lane);
+      __syncwarp();                              // previous tile's stage / p tile are free
+      const uint32_t tile = pipe.acquire(tb, n);
+      cu.look_ahead(tb, n);
+      if (cu.n_next > 0) pipe.prefetch(cu.tb_next, cu.n_next);
       // gathered k rows of my 4 edges (in flight during the tensor-core phase)
+      // (slots past n read node 0: their logits are masked below)
       float2 kA[4], kB[4];
 #pragma unroll
       for (int idx = 0; idx < 4; ++idx) {
-        const unsigned tc = (unsigned)__shfl_sync(kFull, mycol, 8 * idx + g);
-        kA[idx] = make_float2(0.f, 0.f); kB[idx] = kA[idx];
-        if (8 * idx + g < n) {
-          const float* kp = kbase + (size_t)(tc * ldk);
-          kA[idx] = ldg_stream2(kp);
-          kB[idx] = ldg_stream2(kp + 8);
+        if (idx < 2 || two) {
+          const unsigned tc = (unsigned)__shfl_sync(kFull, mycol, 8 * idx + g);
+          const char* kp = kbase + (uint64_t)tc * (uint64_t)ldkb;
+          kA[idx] = ldg_row8(kp, keep);
+          kB[idx] = ldg_row8(kp + 32, keep);
+        } else {
+          kA[idx] = make_float2(0.f, 0.f); kB[idx] = kA[idx];
         }
       }
-      const int prow = ring.prepare(tb - e_begin, n);
       float acc[2][4][4];
-      rpe_tile(acc, ring.buf, prow, two, frag1, bias_s, lane);
+      rpe_tile(acc, tile, two, frag1, bias_s, lane);
 
       // logits (base 2) of my 4 edges x 2 heads
       float cA[4], cB[4];
@@ -425,11 +530,12 @@ k_attn_fwd_tile(const __grid_constant__ CUtensorMap tmA, const FwdArgs P) {
       float sA = 0.f, sB = 0.f;
 #pragma unroll
       for (int idx = 0; idx < 4; ++idx) {
-        const float pA = ex2(cA[idx] - mA_new), pB = ex2(cB[idx] - mB_new);
+        const float pA = ex2(cA[idx] - mA_new), pB = ex2(cB[idx] - mB_new);   // 0 if invalid
         sA += pA; sB += pB;
+        // p tile row of edge 8idx+g: 4 (p, p) pairs in the word order [h0 h2 h1 h3]; lanes
+        // t = 0 / 2 own heads (0, 2) / (1, 3): one 16-byte store each
         if ((t & 1) == 0)
-          *reinterpret_cast<float2*>(p_s + (8 * idx + g) * kH + t) =
-              make_float2(pA, pB);   // heads (t>>1, 2+(t>>1)) stored at words t, t+1: see below
+          *reinterpret_cast<float4*>(p_s + (8 * idx + g) * kH + t) = make_float4(pA, pA, pB, pB);
       }
 #pragma unroll
       for (int o = 4; o < 32; o <<= 1) {
@@ -441,8 +547,6 @@ k_attn_fwd_tile(const __grid_constant__ CUtensorMap tmA, const FwdArgs P) {
       __syncwarp();
 
       // accumulation layout: lane = value channels 4*lane.. (head hb) + abar[hb][4*(lane&7)..]
-      // p tile word order per edge: [h0, h2, h1, h3] (the float2 stores above): head hb is word
-      const int pw = ((hb & 1) << 1) | (hb >> 1);
       if (tb != b) {   // later tiles of a long row: rescale the running sums
         const float a0 = __shfl_sync(kFull, alA, hsrc), a1 = __shfl_sync(kFull, alB, hsrc);
         const float al = hb < 2 ? a0 : a1;
@@ -450,40 +554,35 @@ k_attn_fwd_tile(const __grid_constant__ CUtensorMap tmA, const FwdArgs P) {
         accv01 = mul2(accv01, aa); accv23 = mul2(accv23, aa);
         acca01 = mul2(acca01, aa); acca23 = mul2(acca23, aa);
       }
-      mbar_wait(vbar, vtile & 1u);               // the gathered v rows have landed
-      ++vtile;
-      const unsigned char* vrow = v_s + 16 * lane;
-      const float* prow_s = p_s + pw;
-      // physical ring row of edge u: prow + u (wraps at 96); my 16-byte chunk is (lane&7)^(row&7)
-      const uint32_t abase = smem_u32(ring.buf);
-      for (int e0 = 0; e0 < n; e0 += 8) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          if (e0 + u < n) {
-            const ulonglong2 vv = *reinterpret_cast<const ulonglong2*>(vrow + (e0 + u) * (kC * 4));
-            const float p = prow_s[(e0 + u) * kH];
-            const f32x2 pp = pack2(p, p);
-            fma2(accv01, pp, vv.x);
-            fma2(accv23, pp, vv.y);
-            if (want_abar) {
-              int r = prow + e0 + u;
-              if (r >= kRingSlots) r -= kRingSlots;
-              ulonglong2 a4;
-              const uint32_t ad = abase + r * 128 + (((lane ^ r) & 7) << 4);
-              asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(a4.x), "=l"(a4.y) : "r"(ad));
-              fma2(acca01, pp, a4.x);
-              fma2(acca23, pp, a4.y);
-            }
-          }
+      const f32x2* pcol = reinterpret_cast<const f32x2*>(p_s) + pw;
+      {
+        int e0 = 0;
+        for (; e0 + 8 <= n; e0 += 8)
+          fwd_accumulate<8, true>(e0, mycol, vbase, ldvb, keep, pcol, tile, l7s, want_abar,
+                                  accv01, accv23, acca01, acca23);
+        if (n & 4) {
+          fwd_accumulate<4, false>(e0, mycol, vbase, ldvb, keep, pcol, tile, l7s, want_abar,
+                                   accv01, accv23, acca01, acca23);
+          e0 += 4;
         }
+        if (n & 2) {
+          fwd_accumulate<2, false>(e0, mycol, vbase, ldvb, keep, pcol, tile, l7s, want_abar,
+                                   accv01, accv23, acca01, acca23);
+          e0 += 2;
+        }
+        if (n & 1)
+          fwd_accumulate<1, false>(e0, mycol, vbase, ldvb, keep, pcol, tile, l7s, want_abar,
+                                   accv01, accv23, acca01, acca23);
       }
+      mycol = cu.col_next;
     }
 
     // epilogue of the row
     const float zA = lA + 1e-16f, zB = lB + 1e-16f;     // PyG softmax: + 1e-16 after the sum
+    const float iA = fast_rcp(zA), iB = fast_rcp(zB);
     {
-      const float z0 = __shfl_sync(kFull, zA, hsrc), z1 = __shfl_sync(kFull, zB, hsrc);
-      const float inv = 1.f / (hb < 2 ? z0 : z1);
+      const float z0 = __shfl_sync(kFull, iA, hsrc), z1 = __shfl_sync(kFull, iB, hsrc);
+      const float inv = hb < 2 ? z0 : z1;
       const f32x2 ii = pack2(inv, inv);
       ulonglong2 o;
       o.x = mul2(accv01, ii); o.y = mul2(accv23, ii);
@@ -500,10 +599,18 @@ k_attn_fwd_tile(const __grid_constant__ CUtensorMap tmA, const FwdArgs P) {
       P.m[row * kH + h1] = any ? mB * kLn2 : 0.f;
       P.z[row * kH + h0] = zA;
       P.z[row * kH + h1] = zB;
-      P.sump[row * kH + h0] = lA / zA;
-      P.sump[row * kH + h1] = lB / zB;
+      P.sump[row * kH + h0] = lA * iA;
+      P.sump[row * kH + h1] = lB * iB;
     }
-    b = e;
+    // advance to the next row
+    if (e == b) {   // empty row: nothing was prefetched through the tile loop
+      cu.look_ahead(b, 0);
+      mycol = cu.col_next;
+    }
+    cu.b = e;
+    cu.e = cu.e_next;
+    if (row + 2 < cu.row1) cu.e_next = P.rowptr[row + 3];
+    qA = qA_n; qB = qB_n;
   }
 }
 
@@ -526,72 +633,72 @@ struct BwdArgs {
   int rows_per_warp;
 };
 
-__global__ void __launch_bounds__(kBwdWarps * 32, 1)
-k_attn_bwd_tile(const __grid_constant__ CUtensorMap tmA, const BwdArgs P) {
+__global__ void __launch_bounds__(kBwdWarps * 32, 2)
+k_attn_bwd_tile(const __grid_constant__ TileMaps tmA, const BwdArgs P) {
   using L = BwdSmem;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  uint4* frag1 = reinterpret_cast<uint4*>(smem + L::frag_off);
-  uint4* frag2 = reinterpret_cast<uint4*>(smem + L::frag_off + kFragBytes);
-  float* bias_s = reinterpret_cast<float*>(smem + L::bias_off);
-  float* dp_s = reinterpret_cast<float*>(smem + L::p_off) + w * 32 * kH;
-  unsigned char* v_s = smem + L::v_off + w * kVStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bar_off) + w * 4;
+  const uint4* frag1 = reinterpret_cast<const uint4*>(smem + L::frag_off);
+  const uint4* frag2 = reinterpret_cast<const uint4*>(smem + L::frag_off + kFragBytes);
+  const float* bias_s = reinterpret_cast<const float*>(smem + L::bias_off);
+  float* dp_s = reinterpret_cast<float*>(smem + L::p_off) + w * 32 * kH * 2;
 
-  build_frag1(frag1, P.Wq, P.Wk);
-  build_frag2(frag2, P.Wq, P.Wk);
-  build_bias(bias_s, P.Wq, P.bq, P.Wk, P.bk);
+  build_frag1(reinterpret_cast<uint4*>(smem + L::frag_off), P.Wq, P.Wk);
+  build_frag2(reinterpret_cast<uint4*>(smem + L::frag_off + kFragBytes), P.Wq, P.Wk);
+  build_bias(reinterpret_cast<float*>(smem + L::bias_off), P.Wq, P.bq, P.Wk, P.bk);
   __syncthreads();
 
   const int64_t gw = (int64_t)blockIdx.x * kBwdWarps + w;
   const int64_t row0 = gw * P.rows_per_warp;
   if (row0 >= P.num_rows) return;
-  const int64_t row1 = min(row0 + (int64_t)P.rows_per_warp, P.num_rows);
 
-  Ring ring;
-  ring.buf = smem + L::ring_off + w * (kRing * kChunkBytes);
-  ring.bar = bars;
-  ring.tm = &tmA;
-  ring.lane = lane;
-  uint64_t* vbar = bars + 3;
-  if (lane == 0) mbar_init(vbar, 1);
-  const int e_begin = P.rowptr[row0];
-  const int e_end = P.rowptr[row1];
-  ring.init(e_begin, e_end);
+  TilePipe pipe;
+  pipe.buf = smem + L::tile_off + w * (2 * kChunkBytes);
+  pipe.bar = reinterpret_cast<uint64_t*>(smem + L::bar_off) + w * 2;
+  pipe.tm = &tmA;
+  pipe.policy = policy_evict_first();
+  pipe.lane = lane;
+  pipe.init();
+  const uint64_t keep = policy_evict_last();
+
+  Cursor cu;
+  cu.row = row0;
+  cu.row1 = min(row0 + (int64_t)P.rows_per_warp, P.num_rows);
+  cu.rowptr = P.rowptr; cu.col = P.col; cu.lane = lane;
+  cu.b = P.rowptr[row0];
+  cu.e = P.rowptr[row0 + 1];
+  cu.e_next = (row0 + 1 < cu.row1) ? P.rowptr[row0 + 2] : cu.e;
+  cu.e_end = P.rowptr[cu.row1];
 
   const bool has_dab = P.d_abar != nullptr && P.abar != nullptr;
   const bool want_da = P.da != nullptr;
   const int hb = lane >> 3;
   const int j8 = lane & 7;
-  const float* kbase = P.k + 2 * t;
-  const unsigned ldk = (unsigned)P.ldk, ldv = (unsigned)P.ldv;
+  const char* kbase = reinterpret_cast<const char*>(P.k + 2 * t);
+  const char* vbase = reinterpret_cast<const char*>(P.v + 4 * lane);
+  const unsigned ldkb = (unsigned)P.ldk * 4u, ldvb = (unsigned)P.ldv * 4u;   // row strides, bytes
   const int hA = t >> 1, hB = 2 + (t >> 1);
   const int hsl = (t & 1) * 2 + (t >> 1);   // head fed through k-slot t of the P . dAbar step
-  uint32_t vtile = 0;
+  const uint32_t l7s = (uint32_t)((lane & 7) << 4);
 
-  int b = e_begin;
-  RowAhead nx;
-  nx.e_next = P.rowptr[row0 + 1];
-  nx.col_next = (b + lane < e_end) ? P.col[b + lane] : 0;
-  nx.qA = *reinterpret_cast<const float2*>(P.q + row0 * P.ldq + 2 * t);
-  nx.qB = *reinterpret_cast<const float2*>(P.q + row0 * P.ldq + 8 + 2 * t);
+  int mycol = (lane < min(32, cu.e - cu.b)) ? P.col[cu.b + lane] : 0;
+  float2 qA = *reinterpret_cast<const float2*>(P.q + row0 * P.ldq + 2 * t);
+  float2 qB = *reinterpret_cast<const float2*>(P.q + row0 * P.ldq + 8 + 2 * t);
 
-  for (int64_t row = row0; row < row1; ++row) {
-    const int e = nx.e_next;
-    int mycol = nx.col_next;
-    float2 qA = nx.qA, qB = nx.qB;
-    if (row + 1 < row1) {
-      nx.e_next = P.rowptr[row + 2];
-      nx.col_next = (e + lane < e_end) ? P.col[e + lane] : 0;
-      nx.qA = *reinterpret_cast<const float2*>(P.q + (row + 1) * P.ldq + 2 * t);
-      nx.qB = *reinterpret_cast<const float2*>(P.q + (row + 1) * P.ldq + 8 + 2 * t);
+  for (; cu.row < cu.row1; ++cu.row) {
+    const int64_t row = cu.row;
+    const int b = cu.b, e = cu.e;
+    float2 qA_n = qA, qB_n = qB;
+    if (row + 1 < cu.row1) {
+      qA_n = *reinterpret_cast<const float2*>(P.q + (row + 1) * P.ldq + 2 * t);
+      qB_n = *reinterpret_cast<const float2*>(P.q + (row + 1) * P.ldq + 8 + 2 * t);
     }
     const float scale = fast::qk_scale_fast(P.scale_mode, P.scale_value, e - b);
     qA.x *= scale; qA.y *= scale; qB.x *= scale; qB.y *= scale;
     const float m2A = P.m[row * kH + hA] * kLog2e, m2B = P.m[row * kH + hB] * kLog2e;
-    const float ziA = 1.f / P.z[row * kH + hA], ziB = 1.f / P.z[row * kH + hB];
+    const float ziA = fast_rcp(P.z[row * kH + hA]), ziB = fast_rcp(P.z[row * kH + hB]);
     // accumulation layout operands of the row
     const float4 dy = *reinterpret_cast<const float4*>(P.d_agg_v + row * kC + 4 * lane);
     float4 dab = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -623,23 +730,25 @@ k_attn_bwd_tile(const __grid_constant__ CUtensorMap tmA, const BwdArgs P) {
     for (int tb = b; tb < e; tb += 32) {
       const int n = min(32, e - tb);
       const bool two = n > 16;
-      if (tb != b) mycol = (lane < n) ? P.col[tb + lane] : 0;
       __syncwarp();
-      stage_v(v_s, vbar, P.v, ldv, mycol, n, lane);
+      const uint32_t tile = pipe.acquire(tb, n);
+      cu.look_ahead(tb, n);
+      if (cu.n_next > 0) pipe.prefetch(cu.tb_next, cu.n_next);
+      // (slots past n read node 0: their logits are masked below)
       float2 kA[4], kB[4];
 #pragma unroll
       for (int idx = 0; idx < 4; ++idx) {
-        const unsigned tc = (unsigned)__shfl_sync(kFull, mycol, 8 * idx + g);
-        kA[idx] = make_float2(0.f, 0.f); kB[idx] = kA[idx];
-        if (8 * idx + g < n) {
-          const float* kp = kbase + (size_t)(tc * ldk);
-          kA[idx] = ldg_stream2(kp);
-          kB[idx] = ldg_stream2(kp + 8);
+        if (idx < 2 || two) {
+          const unsigned tc = (unsigned)__shfl_sync(kFull, mycol, 8 * idx + g);
+          const char* kp = kbase + (uint64_t)tc * (uint64_t)ldkb;
+          kA[idx] = ldg_row8(kp, keep);
+          kB[idx] = ldg_row8(kp + 32, keep);
+        } else {
+          kA[idx] = make_float2(0.f, 0.f); kB[idx] = kA[idx];
         }
       }
-      const int prow = ring.prepare(tb - e_begin, n);
       float acc[2][4][4];
-      rpe_tile(acc, ring.buf, prow, two, frag1, bias_s, lane);
+      rpe_tile(acc, tile, two, frag1, bias_s, lane);
 
       // q_e, k_e in place (acc[m][0/1] = q_e heads A/B, acc[m][2/3] = k_e), p of my edges
       float pA[4], pB[4];
@@ -666,29 +775,35 @@ k_attn_bwd_tile(const __grid_constant__ CUtensorMap tmA, const BwdArgs P) {
       }
 
       // dp - delta of every (edge, head): accumulation layout, 8 edges per butterfly
-      mbar_wait(vbar, vtile & 1u);
-      ++vtile;
-      const unsigned char* vrow = v_s + 16 * lane;
-      const uint32_t abase = smem_u32(ring.buf);
       for (int e0 = 0; e0 < n; e0 += 8) {
         float s[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          s[u] = 0.f;
-          if (e0 + u < n) {
-            const ulonglong2 vv = *reinterpret_cast<const ulonglong2*>(vrow + (e0 + u) * (kC * 4));
-            f32x2 d2 = mul2(dy01, vv.x);
-            fma2(d2, dy23, vv.y);
-            if (has_dab) {
-              int r = prow + e0 + u;
-              if (r >= kRingSlots) r -= kRingSlots;
-              ulonglong2 a4;
-              const uint32_t ad = abase + r * 128 + (((lane ^ r) & 7) << 4);
-              asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(a4.x), "=l"(a4.y) : "r"(ad));
-              fma2(d2, dab01, a4.x);
-              fma2(d2, dab23, a4.y);
-            }
-            s[u] = fast::hsum2(d2);
+        for (int u = 0; u < 8; ++u) s[u] = 0.f;
+        const int cnt = n - e0;              // edges of this group (the last one may be short)
+        if (cnt >= 8) {
+          bwd_partials<8, true>(s, e0, mycol, vbase, ldvb, keep, tile, l7s, has_dab, dy01, dy23,
+                                dab01, dab23);
+        } else {
+          float s4[8], s2[8], s1[8];
+          int o = 0;
+          if (cnt & 4) {
+            bwd_partials<4, true>(s4, e0, mycol, vbase, ldvb, keep, tile, l7s, has_dab, dy01,
+                                  dy23, dab01, dab23);
+            s[0] = s4[0]; s[1] = s4[1]; s[2] = s4[2]; s[3] = s4[3];
+            o = 4;
+          }
+          if (cnt & 2) {
+            bwd_partials<2, false>(s2, e0 + o, mycol, vbase, ldvb, keep, tile, l7s, has_dab, dy01,
+                                   dy23, dab01, dab23);
+            if (o) { s[4] = s2[0]; s[5] = s2[1]; } else { s[0] = s2[0]; s[1] = s2[1]; }
+            o += 2;
+          }
+          if (cnt & 1) {
+            bwd_partials<1, false>(s1, e0 + o, mycol, vbase, ldvb, keep, tile, l7s, has_dab, dy01,
+                                   dy23, dab01, dab23);
+            // o in {0, 2, 4, 6}
+            if (o == 0) s[0] = s1[0]; else if (o == 2) s[2] = s1[0];
+            else if (o == 4) s[4] = s1[0]; else s[6] = s1[0];
           }
         }
         // transpose-reduce over the 8 lanes of a head: lane j8 ends with edge e0 + j8
@@ -798,6 +913,7 @@ k_attn_bwd_tile(const __grid_constant__ CUtensorMap tmA, const BwdArgs P) {
           }
         }
       }
+      mycol = cu.col_next;
     }
 
     // dq of the row: reduce my 4 partial sums over the 8 row lanes (g)
@@ -814,7 +930,14 @@ k_attn_bwd_tile(const __grid_constant__ CUtensorMap tmA, const BwdArgs P) {
       *reinterpret_cast<float2*>(P.dq + row * P.lddq + 8 + 2 * t) =
           make_float2(dqacc[2], dqacc[3]);
     }
-    b = e;
+    if (e == b) {
+      cu.look_ahead(b, 0);
+      mycol = cu.col_next;
+    }
+    cu.b = e;
+    cu.e = cu.e_next;
+    if (row + 2 < cu.row1) cu.e_next = P.rowptr[row + 3];
+    qA = qA_n; qB = qB_n;
   }
 }
 

@@ -27,6 +27,8 @@ SOURCES = [
     "gemm.cu",
     "gemm_umma.cu",
     "edge_features.cu",
+    "vrpe.cu",
+    "batch.cu",
 ]
 HEADERS = sorted(f for f in os.listdir(HERE) if f.endswith((".cuh", ".h"))) + \
     [os.path.join(ROOT, "include", "spt_b200.h")]

@@ -225,13 +225,31 @@ class Batch(Data):
         sup_off = [0]
         for n in (num_super_list or []):
             sup_off.append(sup_off[-1] + n)
+        on_dev = data_list[0].device.type == 'cuda'
+        if on_dev:
+            from .. import ops
         for k in keys:
             vals = [d[k] for d in data_list]
             if k == 'edge_index':
-                out[k] = torch.cat([v + node_off[i] for i, v in enumerate(vals)], dim=1)
+                if on_dev:   # one offset-concat launch per row of the [2, E] index
+                    out[k] = torch.stack((
+                        ops.concat_offset([v[0] for v in vals], node_off[:-1]),
+                        ops.concat_offset([v[1] for v in vals], node_off[:-1])))
+                else:
+                    out[k] = torch.cat([v + node_off[i] for i, v in enumerate(vals)], dim=1)
             elif k == 'super_index':
-                out[k] = torch.cat([v + sup_off[i] for i, v in enumerate(vals)])
+                out[k] = ops.concat_offset(vals, sup_off[:-1]) if on_dev else \
+                    torch.cat([v + sup_off[i] for i, v in enumerate(vals)])
             elif k == 'sub':
+                if on_dev:
+                    child_off = [0]
+                    for c in vals:
+                        child_off.append(child_off[-1] + c.num_points)
+                    out[k] = Cluster(
+                        ops.concat_offset([c.pointers for c in vals], child_off[:-1],
+                                          skip_first=True),
+                        ops.concat_offset([c.points for c in vals], child_off[:-1]))
+                    continue
                 child_off, ptrs, pts = 0, [], []
                 ptr_off = 0
                 for i, c in enumerate(vals):
@@ -246,9 +264,12 @@ class Batch(Data):
             else:
                 out[k] = vals[0]
         dev = out.device
-        out['batch'] = torch.repeat_interleave(
-            torch.arange(len(data_list), device=dev),
-            torch.tensor(n_nodes, device=dev))
+        if on_dev:
+            out['batch'] = ops.segment_ids(n_nodes, dev)
+        else:
+            out['batch'] = torch.repeat_interleave(
+                torch.arange(len(data_list), device=dev),
+                torch.tensor(n_nodes, device=dev))
         out['_num_graphs'] = len(data_list)
         if out['batch'].is_cuda:
             from .. import ops

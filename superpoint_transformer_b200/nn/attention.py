@@ -124,15 +124,20 @@ class SelfAttentionBlock(nn.Module):
             Dv = self.dim // H
             Wv, bv = self.v_rpe.weight, self.v_rpe.bias
             F = abar.shape[2]
-            # one dense [N, H*F] x [H*F, C] GEMM with a block-diagonal weight instead
-            # of H tiny batched GEMMs (4x the MACs, but a well-shaped library GEMM)
-            blocks = [Wv] * H if self.heads_share_rpe else list(Wv.view(H, Dv, F))
-            Wbd = torch.block_diag(*blocks)              # [C, H*F]
-            rv = ops.linear(abar.reshape(N, H * F), Wbd)   # [N, C]
-            if bv is not None:
-                b_full = bv.repeat(H) if self.heads_share_rpe else bv
-                rv = rv + sump.repeat_interleave(Dv, dim=1) * b_full.view(1, -1)
-            y = y + rv
+            HF = H * F
+            if (self.dim % 4 == 0 and self.dim <= 256 and HF % 4 == 0 and N > 0
+                    and Wv.dtype == torch.float32):
+                # agg + Wbd abar + bv (x) sump: one tensor-core GEMM + the glue kernels of
+                # csrc/vrpe.cu (block-diagonal weight built on the device every step)
+                y = ops.value_rpe(agg, abar, sump, Wv, bv, H, self.heads_share_rpe)
+            else:
+                blocks = [Wv] * H if self.heads_share_rpe else list(Wv.view(H, Dv, F))
+                Wbd = torch.block_diag(*blocks)              # [C, H*F]
+                rv = ops.linear(abar.reshape(N, HF), Wbd)    # [N, C]
+                if bv is not None:
+                    b_full = bv.repeat(H) if self.heads_share_rpe else bv
+                    rv = rv + sump.repeat_interleave(Dv, dim=1) * b_full.view(1, -1)
+                y = y + rv
         if self.out_proj is not None:
             y = self.out_proj(y)
         if self.out_drop is not None:

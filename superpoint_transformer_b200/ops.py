@@ -614,6 +614,54 @@ def superedge_features(points, se_point_index, se_id, num_superedges):
     return out
 
 
+def concat_offset(tensors, offsets=None, skip_first=False):
+    """torch.cat([t + off for t, off in zip(tensors, offsets)]) for 1-D int64 CUDA tensors in
+    ONE launch (csrc/batch.cu): the integer work of Batch.from_data_list / CSRBatch.from_list
+    (reference src/data/data.py:1154-1242, src/data/csr.py:676-757).
+    skip_first: drop element 0 of every tensor but the first (CSR pointer concatenation)."""
+    lib = _lib.load()
+    _require_cuda(*tensors)
+    ts = [_i64c(t).view(-1) for t in tensors]
+    dev = ts[0].device
+    lens = [t.numel() - (1 if (skip_first and i > 0) else 0) for i, t in enumerate(ts)]
+    prefix = [0]
+    for n in lens:
+        prefix.append(prefix[-1] + n)
+    total = prefix[-1]
+    out = torch.empty(total, dtype=torch.int64, device=dev)
+    if total == 0:
+        return out
+    # one small H2D copy of the segment table (pointers, prefix, offsets)
+    table = [t.data_ptr() for t in ts] + prefix + [int(o) for o in (offsets or [0] * len(ts))]
+    tab = torch.tensor(table, dtype=torch.int64).to(dev, non_blocking=True)
+    S = len(ts)
+    with torch.cuda.device(dev):
+        _lib.check(lib.spt_concat_offset_i64(tab.data_ptr(), tab.data_ptr() + 8 * S,
+                                             tab.data_ptr() + 8 * (2 * S + 1), S, total,
+                                             1 if skip_first else 0, _p(out), _stream()),
+                   "spt_concat_offset_i64")
+    _count()
+    return out
+
+
+def segment_ids(sizes, device):
+    """repeat_interleave(arange(len(sizes)), sizes) on the device (the `batch` vector)."""
+    lib = _lib.load()
+    prefix = [0]
+    for n in sizes:
+        prefix.append(prefix[-1] + int(n))
+    total = prefix[-1]
+    out = torch.empty(total, dtype=torch.int64, device=device)
+    if total == 0:
+        return out
+    tab = torch.tensor(prefix, dtype=torch.int64).to(device, non_blocking=True)
+    with torch.cuda.device(device):
+        _lib.check(lib.spt_concat_offset_i64(None, tab.data_ptr(), None, len(sizes), total, 0,
+                                             _p(out), _stream()), "spt_concat_offset_i64")
+    _count()
+    return out
+
+
 def node_size(super_index, num_parents, child_size=None):
     """NAG.get_sub_size step (src/data/nag.py:59-110): exact int64 sums."""
     lib = _lib.load()
@@ -934,6 +982,82 @@ def attention_core(qsrc, kv, a_csr, Wq, bq, Wk, bk, graph, num_heads, qk_dim,
     return _AttnCore.apply(_f32c(qsrc), _f32c(kv), _f32c(a_csr), _f32c(Wq), _f32c(bq),
                            _f32c(Wk), _f32c(bk), graph, int(num_heads), int(qk_dim),
                            int(scale_mode), float(scale_value), bool(want_abar))
+
+
+class _ValueRpe(torch.autograd.Function):
+    """y = agg + blockdiag(Wv) . abar + bv (x) sump  — the value RPE of SelfAttentionBlock
+    (reference src/nn/attention.py:294-301) applied to the per-row sums the attention kernel
+    emits; one tensor-core GEMM + 2 small kernels forward, GEMM dX + GEMM dW + 2 small kernels
+    backward (csrc/vrpe.cu)."""
+
+    @staticmethod
+    def forward(ctx, agg, abar, sump, Wv, bv, H, share):
+        lib = _lib.load()
+        N, C = agg.shape
+        F = abar.shape[2]
+        Dv = C // H
+        dev = agg.device
+        Wbd = torch.empty((C, H * F), dtype=torch.float32, device=dev)
+        y = torch.empty_like(agg)
+        with torch.cuda.device(dev):
+            _lib.check(lib.spt_vrpe_blockdiag(_p(Wv), H, Dv, F, share, 0, _p(Wbd), _stream()),
+                       "spt_vrpe_blockdiag")
+            # small levels: the plain library GEMM (same rule as ops.linear)
+            rv = _gemm_nt(abar.view(N, H * F), Wbd) if N >= LINEAR_TC_MIN_ROWS \
+                else abar.view(N, H * F) @ Wbd.t()
+            with _timed('vrpe_epilogue', N=N, C=C):
+                _lib.check(lib.spt_vrpe_epilogue(_p(agg), _p(rv), _p(sump), _p(bv), N, H, Dv, share,
+                                                 _p(y), _stream()), "spt_vrpe_epilogue")
+        _count(2)
+        ctx.save_for_backward(abar, sump, Wv, bv if bv is not None else sump)
+        ctx.cfg = (H, share, bv is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        abar, sump, Wv, bv = ctx.saved_tensors
+        H, share, has_b = ctx.cfg
+        lib = _lib.load()
+        dy = _f32c(dy)
+        N, C = dy.shape
+        F = abar.shape[2]
+        Dv = C // H
+        dev = dy.device
+        need = ctx.needs_input_grad
+        d_abar = dWv = dbv = None
+        with torch.cuda.device(dev):
+            if need[1]:
+                WbdT = torch.empty((H * F, C), dtype=torch.float32, device=dev)
+                _lib.check(lib.spt_vrpe_blockdiag(_p(Wv), H, Dv, F, share, 1, _p(WbdT),
+                                                  _stream()), "spt_vrpe_blockdiag")
+                d_abar = (_gemm_nt(dy, WbdT) if N >= LINEAR_TC_MIN_ROWS
+                          else dy @ WbdT.t()).view(N, H, F)
+                _count()
+            if need[3] or (has_b and need[4]):
+                a2 = abar.view(N, H * F)
+                if N >= LINEAR_TC_MIN_ROWS:
+                    dWbd = zero_pool.take((C, H * F), dev)
+                    with _timed('gemm_tn', M=N, N=C, K=H * F):
+                        _lib.check(lib.spt_gemm_tn_acc(_p(dy), N, C, dy.stride(0), _p(a2), H * F,
+                                                       a2.stride(0), _p(dWbd), H * F, None,
+                                                       _stream()), "spt_gemm_tn_acc")
+                else:
+                    dWbd = (dy.t() @ a2).contiguous()
+                dWv = zero_pool.take(tuple(Wv.shape), dev)
+                dbv = zero_pool.take(tuple(bv.shape), dev) if has_b else None
+                _lib.check(lib.spt_vrpe_bwd_params(_p(dy), _p(sump), _p(dWbd), N, H, Dv, F, share,
+                                                   _p(dWv), _p(dbv), _stream()),
+                           "spt_vrpe_bwd_params")
+                _count(3)
+        return dy, d_abar, None, dWv, dbv, None, None
+
+
+def value_rpe(agg, abar, sump, Wv, bv, num_heads, heads_share):
+    """agg + v-RPE contribution; see _ValueRpe.  Requires C % 4 == 0, C <= 256 and the fused
+    GEMM preconditions; callers fall back to the plain composition otherwise."""
+    _require_cuda(agg, abar, sump, Wv, bv)
+    return _ValueRpe.apply(_f32c(agg), _f32c(abar), _f32c(sump), _f32c(Wv), _f32c(bv),
+                           int(num_heads), int(bool(heads_share)))
 
 
 # ---------------------------------------------------------------------------
