@@ -303,6 +303,44 @@ int spt_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk,
                  float* abar /*[R,H,F] nullable*/, float* sump /*[R,H]*/,
                  float* m /*[R,H]*/, float* z /*[R,H]*/, void* stream);
 
+/* Optional terms of the attention core (all pointers nullable; a NULL struct = none):
+ *   q_e += q_row_add[s] + q_tgt_add[t] ; k_e += k_row_add[s]
+ *     -> the node-difference encodings k_delta_rpe / q_delta_rpe of src/nn/attention.py:259-291:
+ *        enc(x_t - x_s) = W x_t - W x_s + b, i.e. one dense product per node + these addends;
+ *   softmax weights multiplied by drop_mask[e, h] (CSR order) AFTER the normalisation
+ *     -> attention dropout (src/nn/attention.py:310-311), mask drawn by the caller.
+ * Backward outputs: d_q_row_add[s] = sum_e dq_e, d_k_row_add[s] = sum_e dk_e (rows kernel),
+ * d_q_tgt_add[t] = sum_{e -> t} dq_e (targets kernel).  With any of these the generic kernels run. */
+typedef struct spt_attn_extras {
+  const float* q_row_add; /* [R, H*D] */
+  const float* q_tgt_add; /* [T, H*D] */
+  const float* k_row_add; /* [R, H*D] */
+  const float* drop_mask; /* [E, H]   */
+  float* d_q_row_add;     /* [R, H*D] */
+  float* d_k_row_add;     /* [R, H*D] */
+} spt_attn_extras;
+
+int spt_attn_fwd_ex(const float* q, int64_t ldq, const float* k, int64_t ldk,
+                    const float* v, int64_t ldv, const float* a, const int32_t* rowptr,
+                    const int32_t* col, int64_t num_rows, int64_t E, int H, int D, int Dv, int F,
+                    const float* Wq, const float* bq, const float* Wk, const float* bk,
+                    int scale_mode, float scale_value, float* agg_v, float* abar, float* sump,
+                    float* m, float* z, const spt_attn_extras* extras, void* stream);
+int spt_attn_bwd_rows_ex(const float* q, int64_t ldq, const float* k, int64_t ldk,
+                         const float* v, int64_t ldv, const float* a, const int32_t* rowptr,
+                         const int32_t* col, int64_t num_rows, int64_t E, int H, int D, int Dv,
+                         int F, const float* Wq, const float* bq, const float* Wk, const float* bk,
+                         int scale_mode, float scale_value, const float* m, const float* z,
+                         const float* agg_v, const float* abar, const float* d_agg_v,
+                         const float* d_abar, float* dq, int64_t lddq, float* da, float* dWq,
+                         float* dbq, float* dWk, float* dbk, float* Pbuf, float* G,
+                         const spt_attn_extras* extras, void* stream);
+int spt_attn_bwd_targets_ex(const int32_t* csc_ptr, const int32_t* csc_src,
+                            const int32_t* csc2csr, int64_t num_targets, int64_t E, int H, int D,
+                            int Dv, const float* Pbuf, const float* G, const float* d_agg_v,
+                            float* dk, int64_t lddk, float* dv, int64_t lddv,
+                            float* d_q_tgt_add /*[T, H*D] nullable*/, void* stream);
+
 /* Backward of spt_attn_fwd, three launches so each can be timed on its own:
  *  (1) rows    : per CSR row, recompute p from (m, z); writes dq [R rows, lddq],
  *                da [E,F] (CSR order, nullable) and the per-edge scratch

@@ -469,6 +469,48 @@ def round2_cases(ref):
             edge_attr=None if out is None else out.edge_attr)
     del raw['subsets']['none']   # sanitize_keys(None) = default set; the empty set is a host-side branch
     cases['h_subsets'] = raw
+    # ---- node-difference RPE (src/nn/attention.py:259-291) and attention dropout (:310-311) --------
+    N, C, H, D, F = 70, 32, 4, 4, 12
+    specs = {
+        'delta_kq': dict(k_delta_rpe=True, q_delta_rpe=True),
+        'delta_kq_minus_edge': dict(k_delta_rpe=True, q_delta_rpe=True, q_on_minus_rpe=True,
+                                    k_rpe=True, q_rpe=True, v_rpe=True),
+        'delta_k_share_minus': dict(k_delta_rpe=True, qk_share_rpe=True, q_on_minus_rpe=True,
+                                    k_rpe=True),
+        'delta_heads_share': dict(k_delta_rpe=True, q_delta_rpe=True, heads_share_rpe=True,
+                                  qk_scale='d+g'),
+        'attn_drop': dict(k_rpe=True, q_rpe=True, v_rpe=True, attn_drop=0.3),
+    }
+    for name, kw in specs.items():
+        gen = torch.Generator().manual_seed(zlib.crc32(name.encode()) % 100000)
+        ei, _ = _graph(gen, N, N * 4)
+        E = ei.shape[1]
+        x = torch.randn(N, C, generator=gen)
+        ea = torch.randn(E, F, generator=gen)
+        torch.manual_seed(4321)
+        blk = ref.SelfAttentionBlock(C, num_heads=H, qk_dim=D, in_rpe_dim=F, out_dim=C, **kw)
+        blk.apply(ref.init_weights)
+        for p in blk.parameters():
+            if p.dim() == 1:
+                p.data.normal_(0, 0.1, generator=gen)
+        mask = None
+        if 'attn_drop' in kw:
+            # the dropout of the attention weights is the first consumer of the global RNG in
+            # forward(): re-seeding reproduces the multipliers it used
+            blk.train()
+            torch.manual_seed(999)
+            mask = torch.nn.functional.dropout(torch.ones(E, H), kw['attn_drop'], True)
+            torch.manual_seed(999)
+        else:
+            blk.eval()
+        xin, ein = x.clone(), ea.clone()
+        outs, probe, grads, pgrads = _run(blk, (xin, ei, ein), {}, [xin, ein],
+                                          torch.Generator().manual_seed(17))
+        cases[name] = dict(cfg=dict(dim=C, num_heads=H, qk_dim=D, in_rpe_dim=F, **kw), x=x,
+                           edge_index=ei, edge_attr=ea, mask=mask,
+                           sd={k: v.detach().clone() for k, v in blk.state_dict().items()},
+                           out=outs[0], probe=probe, dx=grads[0], dedge_attr=grads[1],
+                           dparams=pgrads)
     return cases
 
 

@@ -158,9 +158,10 @@ def qk_scale(dim, num_heads, qk_scale, s, dtype=torch.float32):
 
 def self_attention(sd, prefix, x, edge_index, edge_attr=None, *, num_heads, qk_dim,
                    qk_scale_mode=None, heads_share_rpe=False, qk_share_rpe=False,
-                   q_on_minus_rpe=False):
+                   q_on_minus_rpe=False, attn_drop_mask=None):
     """SelfAttentionBlock.forward.  Which RPE encoders exist is read from the
-    parameter names ({k,q,v}_rpe.weight)."""
+    parameter names ({k,q,v}_rpe.weight, {k,q}_delta_rpe.weight).  `attn_drop_mask` [E, H]:
+    the multipliers nn.Dropout applied to the attention weights (:310-311), None in eval."""
     N, E = x.shape[0], edge_index.shape[1]
     H, D = num_heads, qk_dim
     DH = D * H
@@ -190,10 +191,20 @@ def self_attention(sd, prefix, x, edge_index, edge_attr=None, *, num_heads, qk_d
         q = q + rpe('q_rpe', -edge_attr if q_on_minus_rpe else edge_attr)
     elif has_k and qk_share_rpe and edge_attr is not None:            # :246-256
         q = q + rpe('k_rpe', -edge_attr if q_on_minus_rpe else edge_attr)
+    has_kd = _has(sd, prefix + '.k_delta_rpe.weight')
+    has_qd = _has(sd, prefix + '.q_delta_rpe.weight')
+    if has_kd:                                                        # :258-265
+        k = k + rpe('k_delta_rpe', x[t] - x[s])
+    if has_qd:                                                        # :269-279
+        q = q + rpe('q_delta_rpe', x[s] - x[t] if q_on_minus_rpe else x[t] - x[s])
+    elif has_kd and qk_share_rpe and edge_attr is not None:           # :280-291
+        q = q + rpe('k_delta_rpe', x[s] - x[t] if q_on_minus_rpe else x[t] - x[s])
     if has_v and edge_attr is not None:                               # :294-301
         v = v + rpe('v_rpe', edge_attr)
     compat = torch.einsum('ehd,ehd->eh', q, k)                        # :304
     attn = L.segment_softmax(compat, s, num_nodes=N)                  # :307
+    if attn_drop_mask is not None:                                    # :310-311
+        attn = attn * attn_drop_mask.to(attn.dtype)
     out = (v * attn.unsqueeze(-1)).reshape(E, dim)                    # :314
     out = L.scatter_sum(out, s, 0, N)                                 # :315
     if _has(sd, prefix + '.out_proj.weight'):

@@ -68,6 +68,21 @@ SIGNATURES = {
                                   c_ptr, c_i64, c_ptr,                               # dq da
                                   c_ptr, c_ptr, c_ptr, c_ptr,                        # dWq dbq dWk dbk
                                   c_ptr, c_ptr, c_ptr]),                             # P G stream
+    "spt_attn_fwd_ex": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr,
+                                c_ptr, c_i64, c_i64, c_int, c_int, c_int, c_int, c_ptr,
+                                c_ptr, c_ptr, c_ptr, c_int, c_f32, c_ptr, c_ptr, c_ptr,
+                                c_ptr, c_ptr, c_ptr, c_ptr]),
+    "spt_attn_bwd_rows_ex": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr,
+                                     c_ptr, c_ptr, c_i64, c_i64,
+                                     c_int, c_int, c_int, c_int,
+                                     c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_f32,
+                                     c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                     c_ptr, c_i64, c_ptr,
+                                     c_ptr, c_ptr, c_ptr, c_ptr,
+                                     c_ptr, c_ptr, c_ptr, c_ptr]),
+    "spt_attn_bwd_targets_ex": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int, c_int, c_int,
+                                        c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_ptr,
+                                        c_ptr]),
     "spt_attn_bwd_targets": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int, c_int, c_int,
                                      c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_ptr]),
     "spt_attn_bwd_weights": (c_int, [c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_ptr,
@@ -86,6 +101,13 @@ SIGNATURES = {
     "spt_vertical_edge_features_fwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                                c_i64, c_i64, c_ptr, c_ptr]),
 }
+
+
+class AttnExtras(ctypes.Structure):
+    """spt_attn_extras (include/spt_b200.h): optional terms of the attention core"""
+    _fields_ = [("q_row_add", ctypes.c_void_p), ("q_tgt_add", ctypes.c_void_p),
+                ("k_row_add", ctypes.c_void_p), ("drop_mask", ctypes.c_void_p),
+                ("d_q_row_add", ctypes.c_void_p), ("d_k_row_add", ctypes.c_void_p)]
 
 
 def library_path():

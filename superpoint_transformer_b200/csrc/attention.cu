@@ -61,6 +61,9 @@ struct FwdParams {
   const float* Wq; const float* bq; const float* Wk; const float* bk;
   int scale_mode; float scale_value;
   float* agg_v; float* abar; float* sump; float* m; float* z;
+  // optional terms (spt_attn_extras): q_e += q_row_add[s] + q_tgt_add[t], k_e += k_row_add[s],
+  // softmax weights multiplied by drop_mask[e, h] after the normalisation
+  const float* q_row_add; const float* q_tgt_add; const float* k_row_add; const float* drop_mask;
 };
 
 __device__ __forceinline__ void load_weights_smem(float* Wt, float* bqk, const AttnShape& s,
@@ -97,12 +100,13 @@ k_attn_fwd_generic(FwdParams P) {
   float* Wt = smem;
   float* bqk = Wt + s.F * ldw;
   float* warp_base = bqk + s.HD2;
-  const int per_warp = F4 + s.HD2 + s.HD + 32 + 32 + 32;
+  const int per_warp = F4 + s.HD2 + 2 * s.HD + 32 + 32 + 32;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* a_s = warp_base + w * per_warp;
   float* r_s = a_s + F4;
   float* qs_s = r_s + s.HD2;
-  float* p_s = qs_s + s.HD;
+  float* kr_s = qs_s + s.HD;
+  float* p_s = kr_s + s.HD;
   float* sc_s = p_s + 32;
   float* inv_s = sc_s + 32;
 
@@ -115,8 +119,11 @@ k_attn_fwd_generic(FwdParams P) {
   const int b = P.rowptr[row], e = P.rowptr[row + 1];
   const float scale = qk_scale(P.scale_mode, P.scale_value, e - b);
 
-  for (int o = lane; o < s.HD; o += 32) qs_s[o] = P.q[row * P.ldq + o] * scale;
-  float m_run = -INFINITY, l_run = 0.f;  // lanes < H
+  for (int o = lane; o < s.HD; o += 32) {
+    qs_s[o] = P.q[row * P.ldq + o] * scale + (P.q_row_add ? P.q_row_add[row * s.HD + o] : 0.f);
+    kr_s[o] = P.k_row_add ? P.k_row_add[row * s.HD + o] : 0.f;
+  }
+  float m_run = -INFINITY, l_run = 0.f, le_run = 0.f;  // lanes < H (le: dropout-masked sum)
   float acc_v[kVPL], acc_a[kAPL];
 #pragma unroll
   for (int i = 0; i < kVPL; ++i) acc_v[i] = 0.f;
@@ -135,7 +142,9 @@ k_attn_fwd_generic(FwdParams P) {
       if (has_a) {
         for (int f = 0; f < s.F; ++f) acc = fmaf(Wt[f * ldw + o], a_s[f], acc);
       }
-      float base = (o < s.HD) ? qs_s[o] : P.k[t * P.ldk + (o - s.HD)];
+      float base = (o < s.HD)
+                       ? qs_s[o] + (P.q_tgt_add ? P.q_tgt_add[t * s.HD + o] : 0.f)
+                       : P.k[t * P.ldk + (o - s.HD)] + kr_s[o - s.HD];
       r_s[o] = base + acc;
     }
     __syncwarp();
@@ -147,6 +156,8 @@ k_attn_fwd_generic(FwdParams P) {
       float alpha = (m_run == -INFINITY) ? 0.f : expf(m_run - m_new);
       l_run = fmaf(l_run, alpha, p);
       m_run = m_new;
+      if (P.drop_mask) p *= P.drop_mask[(int64_t)j * s.H + lane];   // attention dropout
+      le_run = fmaf(le_run, alpha, p);
       p_s[lane] = p;
       sc_s[lane] = alpha;
     }
@@ -178,7 +189,7 @@ k_attn_fwd_generic(FwdParams P) {
     inv_s[lane] = inv;
     P.m[row * s.H + lane] = (e > b) ? m_run : 0.f;
     P.z[row * s.H + lane] = zden;
-    P.sump[row * s.H + lane] = l_run * inv;
+    P.sump[row * s.H + lane] = le_run * inv;
   }
   __syncwarp();
 #pragma unroll
@@ -212,6 +223,8 @@ struct BwdParams {
   float* dq; int64_t lddq;
   float* da;
   float* Pbuf; float* G;
+  const float* q_row_add; const float* q_tgt_add; const float* k_row_add; const float* drop_mask;
+  float* d_q_row_add; float* d_k_row_add;     // [R, HD] row sums of dq_e / dk_e (nullable)
 };
 
 __global__ void __launch_bounds__(kAttnWarps * kWarp)
@@ -223,19 +236,21 @@ k_attn_bwd_rows_generic(BwdParams P) {
   float* Wt = smem;
   float* bqk = Wt + s.F * ldw;
   float* warp_base = bqk + s.HD2;
-  // a_s[F4] r_s[HD2] g_s[HD2] qs_s[HD] p_s dc_s delta_s m_s zinv_s (5*32) dy_s[C] dab_s[HF]
-  const int per_warp = F4 + 2 * s.HD2 + s.HD + 5 * 32 + round4(s.C) + round4(max(s.HF, 1));
+  // a_s[F4] r_s[HD2] g_s[HD2] qs_s[HD] kr_s[HD] p_s dc_s delta_s m_s zinv_s mk_s (6*32) dy_s[C] dab_s[HF]
+  const int per_warp = F4 + 2 * s.HD2 + 2 * s.HD + 6 * 32 + round4(s.C) + round4(max(s.HF, 1));
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* a_s = warp_base + w * per_warp;
   float* r_s = a_s + F4;
   float* g_s = r_s + s.HD2;
   float* qs_s = g_s + s.HD2;
-  float* p_s = qs_s + s.HD;
+  float* kr_s = qs_s + s.HD;
+  float* p_s = kr_s + s.HD;
   float* dc_s = p_s + 32;
   float* delta_s = dc_s + 32;
   float* m_s = delta_s + 32;
   float* zinv_s = m_s + 32;
-  float* dy_s = zinv_s + 32;
+  float* mk_s = zinv_s + 32;      // dropout multipliers of the current edge
+  float* dy_s = mk_s + 32;
   float* dab_s = dy_s + round4(s.C);
 
   load_weights_smem(Wt, bqk, s, P.Wq, P.bq, P.Wk, P.bk);
@@ -248,7 +263,10 @@ k_attn_bwd_rows_generic(BwdParams P) {
   const int b = P.rowptr[row], e = P.rowptr[row + 1];
   const float scale = qk_scale(P.scale_mode, P.scale_value, e - b);
 
-  for (int o = lane; o < s.HD; o += 32) qs_s[o] = P.q[row * P.ldq + o] * scale;
+  for (int o = lane; o < s.HD; o += 32) {
+    qs_s[o] = P.q[row * P.ldq + o] * scale + (P.q_row_add ? P.q_row_add[row * s.HD + o] : 0.f);
+    kr_s[o] = P.k_row_add ? P.k_row_add[row * s.HD + o] : 0.f;
+  }
   for (int c = lane; c < s.C; c += 32) dy_s[c] = P.d_agg_v[row * s.C + c];
   if (has_dab)
     for (int i = lane; i < s.HF; i += 32) dab_s[i] = P.d_abar[row * s.HF + i];
@@ -268,9 +286,9 @@ k_attn_bwd_rows_generic(BwdParams P) {
     part = warp_sum(part);
     if (lane == 0) delta_s[h] = part;
   }
-  float dq_acc[kOPL];
+  float dq_acc[kOPL], dk_acc[kOPL];
 #pragma unroll
-  for (int i = 0; i < kOPL; ++i) dq_acc[i] = 0.f;
+  for (int i = 0; i < kOPL; ++i) dq_acc[i] = dk_acc[i] = 0.f;
   __syncwarp();
 
   for (int j = b; j < e; ++j) {
@@ -282,7 +300,9 @@ k_attn_bwd_rows_generic(BwdParams P) {
       float acc = bqk[o];
       if (has_a)
         for (int f = 0; f < s.F; ++f) acc = fmaf(Wt[f * ldw + o], a_s[f], acc);
-      float base = (o < s.HD) ? qs_s[o] : P.k[t * P.ldk + (o - s.HD)];
+      float base = (o < s.HD)
+                       ? qs_s[o] + (P.q_tgt_add ? P.q_tgt_add[t * s.HD + o] : 0.f)
+                       : P.k[t * P.ldk + (o - s.HD)] + kr_s[o - s.HD];
       r_s[o] = base + acc;
     }
     __syncwarp();
@@ -290,8 +310,11 @@ k_attn_bwd_rows_generic(BwdParams P) {
       float c = 0.f;
       for (int d = 0; d < s.D; ++d) c = fmaf(r_s[lane * s.D + d], r_s[s.HD + lane * s.D + d], c);
       float p = expf(c - m_s[lane]) * zinv_s[lane];
+      // attention dropout: the value path (dv, abar) sees p * mask, the softmax Jacobian p
+      const float mk = P.drop_mask ? P.drop_mask[(int64_t)j * s.H + lane] : 1.f;
       p_s[lane] = p;
-      P.Pbuf[(int64_t)j * s.H + lane] = p;
+      mk_s[lane] = mk;
+      P.Pbuf[(int64_t)j * s.H + lane] = p * mk;
     }
     __syncwarp();
     for (int h = 0; h < s.H; ++h) {
@@ -301,7 +324,7 @@ k_attn_bwd_rows_generic(BwdParams P) {
       if (has_dab)
         for (int f = lane; f < s.F; f += 32) part = fmaf(dab_s[h * s.F + f], a_s[f], part);
       part = warp_sum(part);
-      if (lane == 0) dc_s[h] = p_s[h] * (part - delta_s[h]);
+      if (lane == 0) dc_s[h] = p_s[h] * (mk_s[h] * part - delta_s[h]);
     }
     __syncwarp();
 #pragma unroll
@@ -315,6 +338,7 @@ k_attn_bwd_rows_generic(BwdParams P) {
         g_s[o] = g;
         P.G[(int64_t)j * s.HD2 + o] = g;
         if (o < s.HD) dq_acc[i % kOPL] += g;
+        else dk_acc[i % kOPL] += g;
       }
     }
     __syncwarp();
@@ -322,7 +346,8 @@ k_attn_bwd_rows_generic(BwdParams P) {
       for (int f = lane; f < s.F; f += 32) {
         float acc = 0.f;
         if (has_dab)
-          for (int h = 0; h < s.H; ++h) acc = fmaf(p_s[h], dab_s[h * s.F + f], acc);
+          for (int h = 0; h < s.H; ++h)
+            acc = fmaf(p_s[h] * mk_s[h], dab_s[h * s.F + f], acc);
         for (int o = 0; o < s.HD2; ++o) acc = fmaf(Wt[f * ldw + o], g_s[o], acc);
         P.da[(int64_t)j * s.F + f] = acc;
       }
@@ -332,7 +357,18 @@ k_attn_bwd_rows_generic(BwdParams P) {
 #pragma unroll
   for (int i = 0; i < kOPL; ++i) {
     int o = lane + 32 * i;
-    if (o < s.HD) P.dq[row * P.lddq + o] = dq_acc[i] * scale;
+    if (o < s.HD) {
+      P.dq[row * P.lddq + o] = dq_acc[i] * scale;
+      if (P.d_q_row_add) P.d_q_row_add[row * s.HD + o] = dq_acc[i];
+    }
+  }
+  if (P.d_k_row_add) {
+    // o = lane + 32 i runs over [0, 2HD): the k half (o >= HD) was accumulated in slot i % kOPL
+#pragma unroll
+    for (int i = 0; i < 2 * kOPL; ++i) {
+      int o = lane + 32 * i;
+      if (o >= s.HD && o < s.HD2) P.d_k_row_add[row * s.HD + (o - s.HD)] = dk_acc[i % kOPL];
+    }
   }
 }
 
@@ -345,15 +381,15 @@ k_attn_bwd_targets_generic(const int32_t* __restrict__ csc_ptr,
                            AttnShape s, const float* __restrict__ Pbuf,
                            const float* __restrict__ G, const float* __restrict__ d_agg_v,
                            float* __restrict__ dk, int64_t lddk, float* __restrict__ dv,
-                           int64_t lddv) {
+                           int64_t lddv, float* __restrict__ d_q_tgt_add) {
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int64_t t = (int64_t)blockIdx.x * kAttnWarps + w;
   if (t >= num_targets) return;
-  float dv_acc[kVPL], dk_acc[kOPL];
+  float dv_acc[kVPL], dk_acc[kOPL], dqt_acc[kOPL];
 #pragma unroll
   for (int i = 0; i < kVPL; ++i) dv_acc[i] = 0.f;
 #pragma unroll
-  for (int i = 0; i < kOPL; ++i) dk_acc[i] = 0.f;
+  for (int i = 0; i < kOPL; ++i) dk_acc[i] = dqt_acc[i] = 0.f;
   const int b = csc_ptr[t], e = csc_ptr[t + 1];
   for (int jt = b; jt < e; ++jt) {
     const int64_t j = csc2csr[jt];
@@ -367,7 +403,10 @@ k_attn_bwd_targets_generic(const int32_t* __restrict__ csc_ptr,
 #pragma unroll
     for (int i = 0; i < kOPL; ++i) {
       int o = lane + 32 * i;
-      if (o < s.HD) dk_acc[i] += G[j * s.HD2 + s.HD + o];
+      if (o < s.HD) {
+        dk_acc[i] += G[j * s.HD2 + s.HD + o];
+        if (d_q_tgt_add) dqt_acc[i] += G[j * s.HD2 + o];
+      }
     }
   }
 #pragma unroll
@@ -378,7 +417,10 @@ k_attn_bwd_targets_generic(const int32_t* __restrict__ csc_ptr,
 #pragma unroll
   for (int i = 0; i < kOPL; ++i) {
     int o = lane + 32 * i;
-    if (o < s.HD) dk[t * lddk + o] = dk_acc[i];
+    if (o < s.HD) {
+      dk[t * lddk + o] = dk_acc[i];
+      if (d_q_tgt_add) d_q_tgt_add[t * s.HD + o] = dqt_acc[i];
+    }
   }
 }
 
@@ -536,6 +578,22 @@ int spt_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const
                  const float* bq, const float* Wk, const float* bk, int scale_mode,
                  float scale_value, float* agg_v, float* abar, float* sump, float* m,
                  float* z, void* stream_) {
+  return spt_attn_fwd_ex(q, ldq, k, ldk, v, ldv, a, rowptr, col, num_rows, E, H, D, Dv, F, Wq, bq,
+                         Wk, bk, scale_mode, scale_value, agg_v, abar, sump, m, z, nullptr,
+                         stream_);
+}
+
+static bool has_extras(const spt_attn_extras* ex) {
+  return ex && (ex->q_row_add || ex->q_tgt_add || ex->k_row_add || ex->drop_mask);
+}
+
+int spt_attn_fwd_ex(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v,
+                    int64_t ldv, const float* a, const int32_t* rowptr, const int32_t* col,
+                    int64_t num_rows, int64_t E, int H, int D, int Dv, int F, const float* Wq,
+                    const float* bq, const float* Wk, const float* bk, int scale_mode,
+                    float scale_value, float* agg_v, float* abar, float* sump, float* m,
+                    float* z, const spt_attn_extras* ex, void* stream_) {
+  const bool extras = has_extras(ex);
   SPT_REQUIRE(num_rows >= 0 && E >= 0, SPT_E_INVALID, "attn_fwd: negative size");
   if (num_rows == 0) return SPT_OK;
   AttnShape s;
@@ -546,7 +604,8 @@ int spt_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const
   SPT_REQUIRE(scale_mode >= SPT_SCALE_D_TIMES_G && scale_mode <= SPT_SCALE_CONST,
               SPT_E_INVALID, "attn_fwd: bad scale mode %d", scale_mode);
   cudaStream_t st = (cudaStream_t)stream_;
-  if (a && tile::shape_ok(H, D, Dv, F) && tile_layout_ok(q, k, v, a, ldq, ldk, ldv, num_rows, E)) {
+  if (!extras && a && tile::shape_ok(H, D, Dv, F) &&
+      tile_layout_ok(q, k, v, a, ldq, ldk, ldv, num_rows, E)) {
     tile::TileMaps tmA;
     if (make_tile_maps(&tmA, a, E, F)) {
       tile::FwdArgs A;
@@ -565,7 +624,8 @@ int spt_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const
       return check_launch("attn_fwd(tile)");
     }
   }
-  if (a && fast::shape_ok(H, D, Dv, F) && fast_layout_ok(v, a, ldq, ldk, ldv, num_rows)) {
+  if (!extras && a && fast::shape_ok(H, D, Dv, F) &&
+      fast_layout_ok(v, a, ldq, ldk, ldv, num_rows)) {
     fast::FwdArgs A;
     A.q = q; A.ldq = (int)ldq; A.k = k; A.ldk = (int)ldk; A.v = v; A.ldv = (int)ldv; A.a = a;
     A.rowptr = rowptr; A.col = col; A.num_rows = num_rows;
@@ -586,8 +646,11 @@ int spt_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const
   P.Wq = a ? Wq : nullptr; P.bq = bq; P.Wk = a ? Wk : nullptr; P.bk = bk;
   P.scale_mode = scale_mode; P.scale_value = scale_value;
   P.agg_v = agg_v; P.abar = a ? abar : nullptr; P.sump = sump; P.m = m; P.z = z;
+  P.q_row_add = ex ? ex->q_row_add : nullptr; P.q_tgt_add = ex ? ex->q_tgt_add : nullptr;
+  P.k_row_add = ex ? ex->k_row_add : nullptr;
+  P.drop_mask = (ex && E > 0) ? ex->drop_mask : nullptr;
   int F4 = round4(s.F > 1 ? s.F : 1);
-  int per_warp = F4 + s.HD2 + s.HD + 96;
+  int per_warp = F4 + s.HD2 + 2 * s.HD + 96;
   size_t smem = (size_t)(s.F * (s.HD2 + 1) + s.HD2 + kAttnWarps * per_warp) * sizeof(float);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(k_attn_fwd_generic, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -605,6 +668,21 @@ int spt_attn_bwd_rows(const float* q, int64_t ldq, const float* k, int64_t ldk,
                       const float* d_agg_v, const float* d_abar, float* dq, int64_t lddq,
                       float* da, float* dWq, float* dbq, float* dWk, float* dbk, float* Pbuf,
                       float* G, void* stream_) {
+  return spt_attn_bwd_rows_ex(q, ldq, k, ldk, v, ldv, a, rowptr, col, num_rows, E, H, D, Dv, F, Wq,
+                              bq, Wk, bk, scale_mode, scale_value, m, z, agg_v, abar, d_agg_v,
+                              d_abar, dq, lddq, da, dWq, dbq, dWk, dbk, Pbuf, G, nullptr, stream_);
+}
+
+int spt_attn_bwd_rows_ex(const float* q, int64_t ldq, const float* k, int64_t ldk,
+                         const float* v, int64_t ldv, const float* a, const int32_t* rowptr,
+                         const int32_t* col, int64_t num_rows, int64_t E, int H, int D, int Dv,
+                         int F, const float* Wq, const float* bq, const float* Wk,
+                         const float* bk, int scale_mode, float scale_value, const float* m,
+                         const float* z, const float* agg_v, const float* abar,
+                         const float* d_agg_v, const float* d_abar, float* dq, int64_t lddq,
+                         float* da, float* dWq, float* dbq, float* dWk, float* dbk, float* Pbuf,
+                         float* G, const spt_attn_extras* ex, void* stream_) {
+  const bool extras = has_extras(ex);
   SPT_REQUIRE(num_rows >= 0 && E >= 0, SPT_E_INVALID, "attn_bwd_rows: negative size");
   if (num_rows == 0) return SPT_OK;
   AttnShape s;
@@ -615,7 +693,8 @@ int spt_attn_bwd_rows(const float* q, int64_t ldq, const float* k, int64_t ldk,
               SPT_E_INVALID, "attn_bwd_rows: null pointer");
   cudaStream_t st = (cudaStream_t)stream_;
   bool tile_done = false;
-  if (a && tile::shape_ok(H, D, Dv, F) && tile_layout_ok(q, k, v, a, ldq, ldk, ldv, num_rows, E) &&
+  if (!extras && a && tile::shape_ok(H, D, Dv, F) &&
+      tile_layout_ok(q, k, v, a, ldq, ldk, ldv, num_rows, E) &&
       lddq < (1 << 20) && lddq % 2 == 0 && ((uintptr_t)dq & 7) == 0 &&
       ((uintptr_t)G & 7) == 0 && (!da || ((uintptr_t)da & 7) == 0) &&
       ((uintptr_t)d_agg_v & 15) == 0 && ((uintptr_t)agg_v & 15) == 0 &&
@@ -641,7 +720,7 @@ int spt_attn_bwd_rows(const float* q, int64_t ldq, const float* k, int64_t ldk,
       tile_done = true;
     }
   }
-  if (tile_done || (a && fast::shape_ok(H, D, Dv, F) &&
+  if (tile_done || (!extras && a && fast::shape_ok(H, D, Dv, F) &&
                     fast_layout_ok(v, a, ldq, ldk, ldv, num_rows) && lddq < (1 << 20))) {
     if (!tile_done) {
     fast::BwdArgs A;
@@ -690,8 +769,13 @@ int spt_attn_bwd_rows(const float* q, int64_t ldq, const float* k, int64_t ldk,
   P.scale_mode = scale_mode; P.scale_value = scale_value;
   P.m = m; P.z = z; P.agg_v = agg_v; P.abar = abar; P.d_agg_v = d_agg_v; P.d_abar = d_abar;
   P.dq = dq; P.lddq = lddq; P.da = da; P.Pbuf = Pbuf; P.G = G;
+  P.q_row_add = ex ? ex->q_row_add : nullptr; P.q_tgt_add = ex ? ex->q_tgt_add : nullptr;
+  P.k_row_add = ex ? ex->k_row_add : nullptr;
+  P.drop_mask = (ex && E > 0) ? ex->drop_mask : nullptr;
+  P.d_q_row_add = ex ? ex->d_q_row_add : nullptr;
+  P.d_k_row_add = ex ? ex->d_k_row_add : nullptr;
   int F4 = round4(s.F > 1 ? s.F : 1);
-  int per_warp = F4 + 2 * s.HD2 + s.HD + 160 + round4(s.C) + round4(s.HF > 1 ? s.HF : 1);
+  int per_warp = F4 + 2 * s.HD2 + 2 * s.HD + 192 + round4(s.C) + round4(s.HF > 1 ? s.HF : 1);
   size_t smem = (size_t)(s.F * (s.HD2 + 1) + s.HD2 + kAttnWarps * per_warp) * sizeof(float);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(k_attn_bwd_rows_generic, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -711,6 +795,15 @@ int spt_attn_bwd_targets(const int32_t* csc_ptr, const int32_t* csc_src,
                          const int32_t* csc2csr, int64_t num_targets, int64_t E, int H, int D,
                          int Dv, const float* Pbuf, const float* G, const float* d_agg_v,
                          float* dk, int64_t lddk, float* dv, int64_t lddv, void* stream_) {
+  return spt_attn_bwd_targets_ex(csc_ptr, csc_src, csc2csr, num_targets, E, H, D, Dv, Pbuf, G,
+                                 d_agg_v, dk, lddk, dv, lddv, nullptr, stream_);
+}
+
+int spt_attn_bwd_targets_ex(const int32_t* csc_ptr, const int32_t* csc_src,
+                            const int32_t* csc2csr, int64_t num_targets, int64_t E, int H, int D,
+                            int Dv, const float* Pbuf, const float* G, const float* d_agg_v,
+                            float* dk, int64_t lddk, float* dv, int64_t lddv,
+                            float* d_q_tgt_add, void* stream_) {
   SPT_REQUIRE(num_targets >= 0 && E >= 0, SPT_E_INVALID, "attn_bwd_targets: negative size");
   if (num_targets == 0) return SPT_OK;
   AttnShape s;
@@ -718,7 +811,7 @@ int spt_attn_bwd_targets(const int32_t* csc_ptr, const int32_t* csc_src,
   if (rc != SPT_OK) return rc;
   SPT_REQUIRE(csc_ptr && dk && dv && (E == 0 || (csc_src && csc2csr && Pbuf && G && d_agg_v)),
               SPT_E_INVALID, "attn_bwd_targets: null pointer");
-  if (fast::shape_ok(H, D, Dv, fast::kF) && lddv % 4 == 0 && lddk < (1 << 20) &&
+  if (!d_q_tgt_add && fast::shape_ok(H, D, Dv, fast::kF) && lddv % 4 == 0 && lddk < (1 << 20) &&
       lddv < (1 << 20) && (reinterpret_cast<uintptr_t>(dv) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(d_agg_v) & 15) == 0) {
     fast::TgtArgs T;
@@ -731,7 +824,8 @@ int spt_attn_bwd_targets(const int32_t* csc_ptr, const int32_t* csc_src,
   }
   k_attn_bwd_targets_generic<<<(unsigned)ceil_div(num_targets, kAttnWarps), kAttnWarps * kWarp,
                                0, (cudaStream_t)stream_>>>(
-      csc_ptr, csc_src, csc2csr, num_targets, s, Pbuf, G, d_agg_v, dk, lddk, dv, lddv);
+      csc_ptr, csc_src, csc2csr, num_targets, s, Pbuf, G, d_agg_v, dk, lddk, dv, lddv,
+      d_q_tgt_add);
   return check_launch("attn_bwd_targets");
 }
 

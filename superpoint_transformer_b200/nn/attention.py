@@ -58,11 +58,10 @@ class SelfAttentionBlock(nn.Module):
         self.in_proj = Linear(in_dim, dim) if in_dim is not None else None
         self.out_proj = Linear(dim, out_dim) if out_dim is not None else None
 
-        if attn_drop is not None and attn_drop > 0:
-            raise NotImplementedError(
-                "attention-weight dropout is not built into the fused kernel "
-                "(reference default: attn_drop=None, configs/model/semantic/_down.yaml:16)")
-        self.attn_drop = None
+        # attention-weight dropout (reference :162-163, 310-311): the mask is drawn by torch and
+        # applied inside the kernels (spt_attn_extras.drop_mask), forward and backward
+        self.attn_drop = nn.Dropout(attn_drop) \
+            if attn_drop is not None and attn_drop > 0 else None
         self.out_drop = nn.Dropout(drop) if drop is not None and drop > 0 else None
 
     # -- helpers -----------------------------------------------------------
@@ -83,20 +82,59 @@ class SelfAttentionBlock(nn.Module):
             b = b.repeat(self.num_heads) if b is not None else None
         return W, b
 
-    def forward(self, x, edge_index, edge_attr=None):
+    def _delta_terms(self, x, qkv, has_edge_attr):
+        """Node-difference encodings (reference :259-291).  The encoders are Linear, so
+        enc(x_t - x_s) = W x_t - W x_s + b: one dense product per node, then per-row /
+        per-target addends of the fused kernel.  Returns (q_row_add, q_tgt_add, k_row_add,
+        kv) with kv = [k + W_k x | v] when the key encoder is on, else None."""
+        H, HD = self.num_heads, self.num_heads * self.qk_dim
+
+        def proj(lin):
+            if not isinstance(lin, nn.Linear):
+                raise NotImplementedError("delta RPE encoders must be nn.Linear")
+            u = ops.linear(x, lin.weight)                 # [N, D or HD], no bias
+            b = lin.bias
+            if self.heads_share_rpe:
+                u = u.repeat(1, H)
+                b = b.repeat(H) if b is not None else None
+            return u, b
+
+        q_row = q_tgt = k_row = kv = None
+        if self.k_delta_rpe is not None:
+            uk, bk = proj(self.k_delta_rpe)
+            k_row = -uk if bk is None else bk - uk        # the x_s part (+ bias)
+            kv = torch.cat((qkv[:, HD:2 * HD] + uk, qkv[:, 2 * HD:]), dim=1)   # x_t part folded in k
+        q_enc = self.q_delta_rpe
+        if q_enc is None and self.k_delta_rpe is not None and self.qk_share_rpe and has_edge_attr:
+            q_enc = self.k_delta_rpe                      # reference :281-291 (incl. its condition)
+        if q_enc is not None:
+            uq, bq = proj(q_enc)
+            sign = -1.0 if self.q_on_minus_rpe else 1.0   # enc(x_s - x_t) when on_minus
+            q_tgt = sign * uq
+            q_row = -sign * uq if bq is None else bq - sign * uq
+        return q_row, q_tgt, k_row, kv
+
+    def forward(self, x, edge_index, edge_attr=None, attn_drop_mask=None):
         """x [N, Cx]; edge_index [2, E] (row 0 = querying node, row 1 = key node;
-        any order); edge_attr [E, F] or None.  Returns [N, out_dim or dim]."""
+        any order); edge_attr [E, F] or None.  Returns [N, out_dim or dim].
+        `attn_drop_mask` [E, H] (extension, tests): the dropout multipliers to use instead of
+        drawing them (original edge order, already scaled by 1 / (1 - p))."""
         N = x.shape[0]
         H, D = self.num_heads, self.qk_dim
-        if self.k_delta_rpe is not None or self.q_delta_rpe is not None:
-            raise NotImplementedError(
-                "k_delta_rpe / q_delta_rpe (off in every shipped config) are not "
-                "built into the fused kernel yet")
         if self.in_proj is not None:
             x = self.in_proj(x)
         qkv = self.qkv(x)
 
         g = ops.graph_index(edge_index, N)
+        q_row = q_tgt = k_row = kv = None
+        if self.k_delta_rpe is not None or self.q_delta_rpe is not None:
+            q_row, q_tgt, k_row, kv = self._delta_terms(x, qkv, edge_attr is not None)
+        mask = attn_drop_mask
+        if mask is None and self.attn_drop is not None and self.training:
+            E = edge_index.shape[1]
+            mask = self.attn_drop(torch.ones((E, H), dtype=qkv.dtype, device=qkv.device))
+        if mask is not None and g.perm is not None:
+            mask = ops._gather_rows(mask.detach().float().contiguous(), g.perm)
 
         # which encoders act on edge_attr (reference attention.py:225-256, 294-301)
         Wq = bq = Wk = bk = None
@@ -114,8 +152,10 @@ class SelfAttentionBlock(nn.Module):
             a = ops.permute_rows_cached(edge_attr, g.perm)
 
         mode, value = self.qk_scale
-        agg, abar, sump = ops.attention_core(qkv, None, a, Wq, bq, Wk, bk, g, H, D, mode,
-                                             value, want_abar=use_v)
+        qsrc = qkv if kv is None else qkv[:, :H * D].contiguous()
+        agg, abar, sump = ops.attention_core(qsrc, kv, a, Wq, bq, Wk, bk, g, H, D, mode,
+                                             value, want_abar=use_v, q_row_add=q_row,
+                                             q_tgt_add=q_tgt, k_row_add=k_row, drop_mask=mask)
         y = agg
         if use_v:
             # sum_e p_e (Wv a_e + bv) = Wv abar + bv * sum_e p_e

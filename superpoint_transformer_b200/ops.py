@@ -4,6 +4,7 @@ PyTorch is plumbing here (device memory, streams, autograd bookkeeping); all
 the arithmetic of the hot path happens in libspt_b200.so.  Every function
 refuses non-CUDA tensors: there is no CPU fallback.
 """
+import ctypes
 import weakref
 
 import torch
@@ -846,7 +847,7 @@ class _AttnCore(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, qsrc, kv, a, Wq, bq, Wk, bk, g, H, D, scale_mode, scale_value,
-                want_abar):
+                want_abar, q_row_add=None, q_tgt_add=None, k_row_add=None, drop_mask=None):
         lib = _lib.load()
         dev = qsrc.device
         HD = H * D
@@ -869,19 +870,27 @@ class _AttnCore(torch.autograd.Function):
         sump = torch.empty((R, H), dtype=torch.float32, device=dev)
         m = torch.empty((R, H), dtype=torch.float32, device=dev)
         z = torch.empty((R, H), dtype=torch.float32, device=dev)
+        has_ex = any(t is not None for t in (q_row_add, q_tgt_add, k_row_add, drop_mask))
+        ex = None
+        if has_ex:
+            ex = _lib.AttnExtras(_p(q_row_add), _p(q_tgt_add), _p(k_row_add), _p(drop_mask),
+                                 None, None)
         with torch.cuda.device(dev), _timed('attn_fwd', R=R, E=g.E, H=H, D=D, Dv=Dv, F=F,
                                             abar=abar is not None):
-            _lib.check(lib.spt_attn_fwd(qp, ldq, kp, ldk, vp, ldv, _p(a), _p(g.rowptr),
-                                        _p(g.col), R, g.E, H, D, Dv, F, _p(Wq), _p(bq),
-                                        _p(Wk), _p(bk), scale_mode, scale_value, _p(agg),
-                                        _p(abar), _p(sump), _p(m), _p(z), _stream()),
-                       "spt_attn_fwd")
+            _lib.check(lib.spt_attn_fwd_ex(qp, ldq, kp, ldk, vp, ldv, _p(a), _p(g.rowptr),
+                                           _p(g.col), R, g.E, H, D, Dv, F, _p(Wq), _p(bq),
+                                           _p(Wk), _p(bk), scale_mode, scale_value, _p(agg),
+                                           _p(abar), _p(sump), _p(m), _p(z),
+                                           ctypes.byref(ex) if ex is not None else None,
+                                           _stream()), "spt_attn_fwd")
         _count()
         ctx.g, ctx.H, ctx.D, ctx.Dv, ctx.F = g, H, D, Dv, F
         ctx.scale_mode, ctx.scale_value = scale_mode, scale_value
         ctx.fused = fused
         ctx.opt = (kv is not None, a is not None, Wq is not None, bq is not None,
                    Wk is not None, bk is not None, abar is not None)
+        ctx.ex = (q_row_add is not None, q_tgt_add is not None, k_row_add is not None,
+                  drop_mask is not None)
         dummy = m
         ctx.save_for_backward(qsrc, kv if kv is not None else dummy,
                               a if a is not None else dummy,
@@ -889,7 +898,11 @@ class _AttnCore(torch.autograd.Function):
                               bq if bq is not None else dummy,
                               Wk if Wk is not None else dummy,
                               bk if bk is not None else dummy, m, z, agg,
-                              abar if abar is not None else dummy)
+                              abar if abar is not None else dummy,
+                              q_row_add if q_row_add is not None else dummy,
+                              q_tgt_add if q_tgt_add is not None else dummy,
+                              k_row_add if k_row_add is not None else dummy,
+                              drop_mask if drop_mask is not None else dummy)
         ctx.mark_non_differentiable(sump)
         if abar is None:
             return agg, None, sump
@@ -898,8 +911,14 @@ class _AttnCore(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_agg, d_abar, _d_sump):
         lib = _lib.load()
-        qsrc, kv, a, Wq, bq, Wk, bk, m, z, agg, abar = ctx.saved_tensors
+        (qsrc, kv, a, Wq, bq, Wk, bk, m, z, agg, abar, q_row_add, q_tgt_add, k_row_add,
+         drop_mask) = ctx.saved_tensors
         has_kv, has_a, has_Wq, has_bq, has_Wk, has_bk, has_abar = ctx.opt
+        has_qr, has_qt, has_kr, has_dm = ctx.ex
+        q_row_add = q_row_add if has_qr else None
+        q_tgt_add = q_tgt_add if has_qt else None
+        k_row_add = k_row_add if has_kr else None
+        drop_mask = drop_mask if has_dm else None
         kv = kv if has_kv else None
         a = a if has_a else None
         Wq = Wq if has_Wq else None
@@ -949,18 +968,27 @@ class _AttnCore(torch.autograd.Function):
         G = torch.empty((max(E, 1), 2 * HD), dtype=torch.float32, device=dev)
         meta = dict(R=g.num_rows, T=g.num_targets, E=E, H=H, D=D, Dv=Dv, F=F,
                     abar=abar is not None, da=da is not None)
+        has_ex = has_qr or has_qt or has_kr or has_dm
+        d_qr = torch.empty_like(q_row_add) if has_qr else None
+        d_kr = torch.empty_like(k_row_add) if has_kr else None
+        d_qt = torch.empty_like(q_tgt_add) if has_qt else None
+        ex = None
+        if has_ex:
+            ex = _lib.AttnExtras(_p(q_row_add), _p(q_tgt_add), _p(k_row_add), _p(drop_mask),
+                                 _p(d_qr), _p(d_kr))
         with torch.cuda.device(dev):
             with _timed('attn_bwd_rows', **meta):
-                _lib.check(lib.spt_attn_bwd_rows(
+                _lib.check(lib.spt_attn_bwd_rows_ex(
                     qp, ldq, kp, ldk, vp, ldv, _p(a), _p(g.rowptr), _p(g.col), g.num_rows, E,
                     H, D, Dv, F, _p(Wq), _p(bq), _p(Wk), _p(bk), ctx.scale_mode,
                     ctx.scale_value, _p(m), _p(z), _p(agg), _p(abar), _p(d_agg), _p(d_abar),
                     dqp, lddq, _p(da), _p(dWq), _p(dbq), _p(dWk), _p(dbk), _p(Pb), _p(G),
-                    _stream()), "spt_attn_bwd_rows")
+                    ctypes.byref(ex) if ex is not None else None, _stream()),
+                    "spt_attn_bwd_rows")
             with _timed('attn_bwd_targets', **meta):
-                _lib.check(lib.spt_attn_bwd_targets(
+                _lib.check(lib.spt_attn_bwd_targets_ex(
                     _p(g.csc_ptr), _p(g.csc_src), _p(g.csc2csr), g.num_targets, E, H, D, Dv,
-                    _p(Pb), _p(G), _p(d_agg), dkp, lddk, dvp, lddv, _stream()),
+                    _p(Pb), _p(G), _p(d_agg), dkp, lddk, dvp, lddv, _p(d_qt), _stream()),
                     "spt_attn_bwd_targets")
             _count(2)
         if bq is not None and dbq is None:
@@ -971,17 +999,22 @@ class _AttnCore(torch.autograd.Function):
             dWq = torch.zeros_like(Wq)
         if Wk is not None and dWk is None:
             dWk = torch.zeros_like(Wk)
-        return (dqkv, dkv, da, dWq, dbq, dWk, dbk, None, None, None, None, None, None)
+        return (dqkv, dkv, da, dWq, dbq, dWk, dbk, None, None, None, None, None, None,
+                d_qr, d_qt, d_kr, None)
 
 
 def attention_core(qsrc, kv, a_csr, Wq, bq, Wk, bk, graph, num_heads, qk_dim,
-                   scale_mode=SCALE_D_TIMES_G, scale_value=1.0, want_abar=True):
-    """See include/spt_b200.h:spt_attn_fwd.  `a_csr` must already be in CSR order
-    (permute_rows(edge_attr, graph.perm))."""
-    _require_cuda(qsrc, kv, a_csr, Wq, bq, Wk, bk)
+                   scale_mode=SCALE_D_TIMES_G, scale_value=1.0, want_abar=True,
+                   q_row_add=None, q_tgt_add=None, k_row_add=None, drop_mask=None):
+    """See include/spt_b200.h:spt_attn_fwd(_ex).  `a_csr` and `drop_mask` must already be in
+    CSR order (permute_rows(edge_attr, graph.perm)).  The optional addends / mask are the
+    `spt_attn_extras` (node-difference RPE, attention dropout)."""
+    _require_cuda(qsrc, kv, a_csr, Wq, bq, Wk, bk, q_row_add, q_tgt_add, k_row_add, drop_mask)
     return _AttnCore.apply(_f32c(qsrc), _f32c(kv), _f32c(a_csr), _f32c(Wq), _f32c(bq),
                            _f32c(Wk), _f32c(bk), graph, int(num_heads), int(qk_dim),
-                           int(scale_mode), float(scale_value), bool(want_abar))
+                           int(scale_mode), float(scale_value), bool(want_abar),
+                           _f32c(q_row_add), _f32c(q_tgt_add), _f32c(k_row_add),
+                           _f32c(drop_mask))
 
 
 class _ValueRpe(torch.autograd.Function):

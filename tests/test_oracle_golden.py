@@ -266,3 +266,25 @@ def test_horizontal_feature_key_subsets(golden):
                                             c['log_size'], keys=sub['keys'])
         assert torch.equal(ei, sub['edge_index'])
         assert_close(ea, sub['edge_attr'], atol=1e-6, rtol=1e-6, what=f'subset {name}')
+
+
+DELTA = ['delta_kq', 'delta_kq_minus_edge', 'delta_k_share_minus', 'delta_heads_share',
+         'attn_drop']
+
+
+@pytest.mark.parametrize('name', DELTA)
+def test_delta_rpe_and_attention_dropout(golden, name):
+    """node-difference RPE (src/nn/attention.py:259-291) and attention dropout (:310-311):
+    oracle == reference block, outputs and every gradient."""
+    c = golden('round2.pt')[name]
+    cfg = c['cfg']
+    sd = {'sa.' + k: v.clone().requires_grad_(True) for k, v in c['sd'].items()}
+    x, ea = _req(c['x'], c['edge_attr'])
+    out = P.self_attention(sd, 'sa', x, c['edge_index'], ea, attn_drop_mask=c['mask'],
+                           **_attn_kw(cfg))
+    assert_close(out, c['out'], atol=2e-5, rtol=2e-5, what=name)
+    (out * c['probe']).sum().backward()
+    grad_close(x.grad, c['dx'], what=name + ' dx')
+    grad_close(ea.grad, c['dedge_attr'], what=name + ' dedge_attr')
+    for k, g in c['dparams'].items():
+        grad_close(sd['sa.' + k].grad, g, what=f'{name} d{k}')
