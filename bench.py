@@ -160,6 +160,7 @@ class ClockSampler:
 def _pin(nag, labels):
     """fp16 raw edge attributes (configs/datamodule/semantic/default.yaml:40-42), pinned"""
     nbytes = 0
+    pin = torch.cuda.is_available()
     for d in nag:
         if d.edge_attr is not None and d.edge_attr.dtype != torch.float16:
             d.edge_attr = d.edge_attr.half()
@@ -167,9 +168,9 @@ def _pin(nag, labels):
         for k in d.keys:
             v = d[k]
             if torch.is_tensor(v):
-                d[k] = v.pin_memory()
+                d[k] = v.pin_memory() if pin else v
                 nbytes += v.numel() * v.element_size()
-    labels = labels.pin_memory()
+    labels = labels.pin_memory() if pin else labels
     nbytes += labels.numel() * 8
     return nag, labels, nbytes
 
@@ -342,6 +343,10 @@ def kernel_bytes(tag, m):
         return m['Eh'] * (16 + 28) + (2 * m['Eh'] + (m['N'] if m.get('loops') else 0)) * (16 + 72)
     if tag == 'unitsphere':
         return m['N'] * (12 + 12 + 4 + 8) + m['Np'] * 16
+    if tag == 'vrpe_epilogue':   # agg, rv in; y out (sump / bias negligible)
+        return 3 * m['N'] * m['C'] * 4
+    if 'R' not in m or 'E' not in m:
+        return 0
     return attn_bytes(tag, m)
 
 

@@ -318,6 +318,10 @@ typedef struct spt_attn_extras {
   const float* drop_mask; /* [E, H]   */
   float* d_q_row_add;     /* [R, H*D] */
   float* d_k_row_add;     /* [R, H*D] */
+  /* backward only: gradient flowing into sump [R, H] (non-zero only with a dropout mask, when
+   * the caller's v-RPE bias multiplies sump) and the forward's sump */
+  const float* d_sump;    /* [R, H] */
+  const float* sump;      /* [R, H] */
 } spt_attn_extras;
 
 int spt_attn_fwd_ex(const float* q, int64_t ldq, const float* k, int64_t ldk,

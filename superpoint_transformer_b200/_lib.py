@@ -107,7 +107,8 @@ class AttnExtras(ctypes.Structure):
     """spt_attn_extras (include/spt_b200.h): optional terms of the attention core"""
     _fields_ = [("q_row_add", ctypes.c_void_p), ("q_tgt_add", ctypes.c_void_p),
                 ("k_row_add", ctypes.c_void_p), ("drop_mask", ctypes.c_void_p),
-                ("d_q_row_add", ctypes.c_void_p), ("d_k_row_add", ctypes.c_void_p)]
+                ("d_q_row_add", ctypes.c_void_p), ("d_k_row_add", ctypes.c_void_p),
+                ("d_sump", ctypes.c_void_p), ("sump", ctypes.c_void_p)]
 
 
 def library_path():

@@ -225,6 +225,7 @@ struct BwdParams {
   float* Pbuf; float* G;
   const float* q_row_add; const float* q_tgt_add; const float* k_row_add; const float* drop_mask;
   float* d_q_row_add; float* d_k_row_add;     // [R, HD] row sums of dq_e / dk_e (nullable)
+  const float* d_sump; const float* sump;     // [R, H] gradient into / value of sum_e p_e mask_e
 };
 
 __global__ void __launch_bounds__(kAttnWarps * kWarp)
@@ -284,7 +285,9 @@ k_attn_bwd_rows_generic(BwdParams P) {
       for (int f = lane; f < s.F; f += 32)
         part = fmaf(dab_s[h * s.F + f], P.abar[row * s.HF + h * s.F + f], part);
     part = warp_sum(part);
-    if (lane == 0) delta_s[h] = part;
+    if (lane == 0)
+      delta_s[h] = part + ((P.d_sump && P.sump) ? P.d_sump[row * s.H + h] * P.sump[row * s.H + h]
+                                                 : 0.f);
   }
   float dq_acc[kOPL], dk_acc[kOPL];
 #pragma unroll
@@ -324,7 +327,10 @@ k_attn_bwd_rows_generic(BwdParams P) {
       if (has_dab)
         for (int f = lane; f < s.F; f += 32) part = fmaf(dab_s[h * s.F + f], a_s[f], part);
       part = warp_sum(part);
-      if (lane == 0) dc_s[h] = p_s[h] * (mk_s[h] * part - delta_s[h]);
+      if (lane == 0) {
+        if (P.d_sump) part += P.d_sump[row * s.H + h];     // d(sum_e p_e mask_e) / d p_e = mask_e
+        dc_s[h] = p_s[h] * (mk_s[h] * part - delta_s[h]);
+      }
     }
     __syncwarp();
 #pragma unroll
@@ -774,6 +780,8 @@ int spt_attn_bwd_rows_ex(const float* q, int64_t ldq, const float* k, int64_t ld
   P.drop_mask = (ex && E > 0) ? ex->drop_mask : nullptr;
   P.d_q_row_add = ex ? ex->d_q_row_add : nullptr;
   P.d_k_row_add = ex ? ex->d_k_row_add : nullptr;
+  P.d_sump = ex ? ex->d_sump : nullptr;
+  P.sump = ex ? ex->sump : nullptr;
   int F4 = round4(s.F > 1 ? s.F : 1);
   int per_warp = F4 + 2 * s.HD2 + 2 * s.HD + 192 + round4(s.C) + round4(s.HF > 1 ? s.HF : 1);
   size_t smem = (size_t)(s.F * (s.HD2 + 1) + s.HD2 + kAttnWarps * per_warp) * sizeof(float);

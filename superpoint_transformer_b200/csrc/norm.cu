@@ -17,7 +17,7 @@
 namespace spt {
 
 constexpr int kNormThreads = 256;
-constexpr int kNormRows = 128;  // rows per CTA slab
+constexpr int kNormRows = 128;  // minimum rows per CTA slab (the launch picks the slab size)
 
 struct ColMap {
   int tx;  // threads along columns (each VEC wide)
@@ -46,15 +46,15 @@ k_graphnorm_stats(const float* __restrict__ x, const float* __restrict__ dy,
                   const double* __restrict__ sum_x, const double* __restrict__ count,
                   const float* __restrict__ mean, const float* __restrict__ rstd,
                   double* __restrict__ acc0 /*[B,C]*/, double* __restrict__ acc1 /*[B,C]*/,
-                  double* __restrict__ cnt_out /*[B]*/, int tx, int ty) {
+                  double* __restrict__ cnt_out /*[B]*/, int tx, int ty, int slab_rows) {
   constexpr int NACC = (MODE >= 2) ? 2 : 1;
   __shared__ float red[NACC][kNormThreads * VEC];
   int cx = threadIdx.x % tx;
   int ry = threadIdx.x / tx;
   // persistent CTA: slabs blockIdx.x, blockIdx.x + gridDim.x, ... ; partial sums
   // stay in registers across slabs and leave the CTA once (few fp64 atomics)
-  const int64_t nslabs = (N + kNormRows - 1) / kNormRows;
-  const int64_t first_row = (int64_t)blockIdx.x * kNormRows;
+  const int64_t nslabs = (N + slab_rows - 1) / slab_rows;
+  const int64_t first_row = (int64_t)blockIdx.x * slab_rows;
   int64_t first_b = batch ? batch[first_row < N ? first_row : 0] : 0;
   for (int64_t ct = 0; ct < C; ct += (int64_t)tx * VEC) {
     int64_t c0 = ct + (int64_t)cx * VEC;
@@ -74,8 +74,8 @@ k_graphnorm_stats(const float* __restrict__ x, const float* __restrict__ dy,
     int64_t rows_seen = 0;
     if (active) {
      for (int64_t slab = blockIdx.x; slab < nslabs; slab += gridDim.x) {
-      const int64_t r0 = slab * kNormRows;
-      const int64_t r1 = min(r0 + (int64_t)kNormRows, N);
+      const int64_t r0 = slab * slab_rows;
+      const int64_t r1 = min(r0 + (int64_t)slab_rows, N);
       rows_seen += r1 - r0;
       constexpr int U = 4;   // rows in flight per thread (independent 16-byte loads)
       for (int64_t rb = r0 + ry; rb < r1; rb += (int64_t)ty * U) {
@@ -438,6 +438,18 @@ __global__ void k_groupnorm_bwd_coef(const double* __restrict__ s1, const double
   }
 }
 
+// Statistics passes: one slab of rows per CTA, sized so that ~8 CTAs per SM cover N in a single
+// balanced wave (a fixed 128-row slab left 592 CTAs with 1 or 2 slabs each: 66 % efficiency at
+// 100 k rows); slab rows are a multiple of the rows one CTA iteration touches (ty * 4).
+static inline int norm_slab_rows(int64_t N, int ty) {
+  const int64_t per_iter = (int64_t)ty * 4;
+  int64_t want = (N + (int64_t)device_sm_count() * 8 - 1) / ((int64_t)device_sm_count() * 8);
+  want = (want + per_iter - 1) / per_iter * per_iter;
+  if (want < per_iter) want = per_iter;
+  if (want > (1 << 20)) want = (1 << 20);
+  return (int)want;
+}
+
 static inline ColMap col_map(int64_t C, int vec) {
   int64_t cols = C / vec;
   int tx = 1;
@@ -506,7 +518,8 @@ int spt_graphnorm_fwd(const float* x, const int64_t* batch, int64_t N, int64_t C
   }
   int vec = (C % 4 == 0) ? 4 : 1;
   ColMap cm = col_map(C, vec);
-  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, kNormRows), device_sm_count() * 4);
+  const int slab_rows = norm_slab_rows(N, cm.ty);
+  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, slab_rows), device_sm_count() * 8);
   int64_t total = N * (C / vec);
   int agrid = (int)imin(ceil_div(total > 0 ? total : 1, kNormThreads), device_sm_count() * 16);
   // single pass over x: shifted first and second moments around a per-channel pivot
@@ -516,11 +529,11 @@ int spt_graphnorm_fwd(const float* x, const int64_t* batch, int64_t N, int64_t C
     if (vec == 4)
       k_graphnorm_stats<3, 4><<<slabs, kNormThreads, 0, st>>>(
           x, nullptr, nullptr, 1.f, batch, N, C, B, pivot, nullptr, nullptr, nullptr, nullptr,
-          w.acc0, w.acc1, w.count, cm.tx, cm.ty);
+          w.acc0, w.acc1, w.count, cm.tx, cm.ty, slab_rows);
     else
       k_graphnorm_stats<3, 1><<<slabs, kNormThreads, 0, st>>>(
           x, nullptr, nullptr, 1.f, batch, N, C, B, pivot, nullptr, nullptr, nullptr, nullptr,
-          w.acc0, w.acc1, w.count, cm.tx, cm.ty);
+          w.acc0, w.acc1, w.count, cm.tx, cm.ty, slab_rows);
   } else {
     cudaMemsetAsync(pivot, 0, (size_t)C * 4, st);
   }
@@ -559,18 +572,19 @@ int spt_graphnorm_bwd(const float* x, const float* dy, const int64_t* batch, int
   }
   int vec = (C % 4 == 0) ? 4 : 1;
   ColMap cm = col_map(C, vec);
-  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, kNormRows), device_sm_count() * 4);
+  const int slab_rows = norm_slab_rows(N, cm.ty);
+  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, slab_rows), device_sm_count() * 8);
   int64_t total = N * (C / vec);
   int agrid = (int)imin(ceil_div(total > 0 ? total : 1, kNormThreads), device_sm_count() * 16);
   if (N > 0) {
     if (vec == 4)
       k_graphnorm_stats<2, 4><<<slabs, kNormThreads, 0, st>>>(
           x, dy, yact, act_slope, batch, N, C, B, mean_scale, nullptr, nullptr, mean, rstd, w.acc0,
-          w.acc1, w.count, cm.tx, cm.ty);   // also counts the rows per graph
+          w.acc1, w.count, cm.tx, cm.ty, slab_rows);   // also counts the rows per graph
     else
       k_graphnorm_stats<2, 1><<<slabs, kNormThreads, 0, st>>>(
           x, dy, yact, act_slope, batch, N, C, B, mean_scale, nullptr, nullptr, mean, rstd, w.acc0,
-          w.acc1, w.count, cm.tx, cm.ty);
+          w.acc1, w.count, cm.tx, cm.ty, slab_rows);
   }
   k_graphnorm_bwd_coef<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(
       w.acc0, w.acc1, w.count, B, C, weight, mean_scale, mean, rstd, w.k2, w.k3, dweight,
@@ -608,7 +622,8 @@ int spt_groupnorm_fwd(const float* x, const int64_t* batch, int64_t N, int64_t C
   const int64_t G = num_groups;
   int vec = (C % 4 == 0) ? 4 : 1;
   ColMap cm = col_map(C, vec);
-  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, kNormRows), device_sm_count() * 4);
+  const int slab_rows = norm_slab_rows(N, cm.ty);
+  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, slab_rows), device_sm_count() * 8);
   int64_t total = N * (C / vec);
   int agrid = (int)imin(ceil_div(total > 0 ? total : 1, kNormThreads), device_sm_count() * 16);
   const unsigned ggrid = (unsigned)ceil_div(B * G, 128);
@@ -616,22 +631,22 @@ int spt_groupnorm_fwd(const float* x, const int64_t* batch, int64_t N, int64_t C
     if (vec == 4)
       k_graphnorm_stats<0, 4><<<slabs, kNormThreads, 0, st>>>(
           x, nullptr, nullptr, 1.f, batch, N, C, B, nullptr, nullptr, nullptr, nullptr, nullptr,
-          w.acc0, nullptr, w.count, cm.tx, cm.ty);
+          w.acc0, nullptr, w.count, cm.tx, cm.ty, slab_rows);
     else
       k_graphnorm_stats<0, 1><<<slabs, kNormThreads, 0, st>>>(
           x, nullptr, nullptr, 1.f, batch, N, C, B, nullptr, nullptr, nullptr, nullptr, nullptr,
-          w.acc0, nullptr, w.count, cm.tx, cm.ty);
+          w.acc0, nullptr, w.count, cm.tx, cm.ty, slab_rows);
   }
   k_groupnorm_mean<<<ggrid, 128, 0, st>>>(w.acc0, w.count, B, C, G);
   if (N > 0) {
     if (vec == 4)
       k_graphnorm_stats<1, 4><<<slabs, kNormThreads, 0, st>>>(
           x, nullptr, nullptr, 1.f, batch, N, C, B, nullptr, w.acc0, w.count, nullptr, nullptr,
-          w.acc1, nullptr, nullptr, cm.tx, cm.ty);
+          w.acc1, nullptr, nullptr, cm.tx, cm.ty, slab_rows);
     else
       k_graphnorm_stats<1, 1><<<slabs, kNormThreads, 0, st>>>(
           x, nullptr, nullptr, 1.f, batch, N, C, B, nullptr, w.acc0, w.count, nullptr, nullptr,
-          w.acc1, nullptr, nullptr, cm.tx, cm.ty);
+          w.acc1, nullptr, nullptr, cm.tx, cm.ty, slab_rows);
   }
   k_groupnorm_finalize<<<ggrid, 128, 0, st>>>(w.acc0, w.acc1, w.count, B, C, G, eps, eps_outside,
                                               mean, rstd);
@@ -667,18 +682,19 @@ int spt_groupnorm_bwd(const float* x, const float* dy, const int64_t* batch, int
   const int64_t G = num_groups;
   int vec = (C % 4 == 0) ? 4 : 1;
   ColMap cm = col_map(C, vec);
-  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, kNormRows), device_sm_count() * 4);
+  const int slab_rows = norm_slab_rows(N, cm.ty);
+  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, slab_rows), device_sm_count() * 8);
   int64_t total = N * (C / vec);
   int agrid = (int)imin(ceil_div(total > 0 ? total : 1, kNormThreads), device_sm_count() * 16);
   if (N > 0) {
     if (vec == 4)
       k_graphnorm_stats<2, 4><<<slabs, kNormThreads, 0, st>>>(
           x, dy, nullptr, 1.f, batch, N, C, B, nullptr, nullptr, nullptr, mean, rstd, w.acc0,
-          w.acc1, w.count, cm.tx, cm.ty);
+          w.acc1, w.count, cm.tx, cm.ty, slab_rows);
     else
       k_graphnorm_stats<2, 1><<<slabs, kNormThreads, 0, st>>>(
           x, dy, nullptr, 1.f, batch, N, C, B, nullptr, nullptr, nullptr, mean, rstd, w.acc0,
-          w.acc1, w.count, cm.tx, cm.ty);
+          w.acc1, w.count, cm.tx, cm.ty, slab_rows);
   }
   const int64_t work = B * G > C ? B * G : C;
   k_groupnorm_bwd_coef<<<(unsigned)ceil_div(work, 128), 128, 0, st>>>(

@@ -874,7 +874,7 @@ class _AttnCore(torch.autograd.Function):
         ex = None
         if has_ex:
             ex = _lib.AttnExtras(_p(q_row_add), _p(q_tgt_add), _p(k_row_add), _p(drop_mask),
-                                 None, None)
+                                 None, None, None, None)
         with torch.cuda.device(dev), _timed('attn_fwd', R=R, E=g.E, H=H, D=D, Dv=Dv, F=F,
                                             abar=abar is not None):
             _lib.check(lib.spt_attn_fwd_ex(qp, ldq, kp, ldk, vp, ldv, _p(a), _p(g.rowptr),
@@ -903,7 +903,11 @@ class _AttnCore(torch.autograd.Function):
                               q_tgt_add if q_tgt_add is not None else dummy,
                               k_row_add if k_row_add is not None else dummy,
                               drop_mask if drop_mask is not None else dummy)
-        ctx.mark_non_differentiable(sump)
+        if drop_mask is None:
+            # sum_e p_e is the constant 1 (0 for an empty row): no gradient.  Under attention
+            # dropout sum_e p_e mask_e is not, and the caller's v-RPE bias multiplies it.
+            ctx.mark_non_differentiable(sump)
+        ctx.sump = sump if drop_mask is not None else None
         if abar is None:
             return agg, None, sump
         return agg, abar, sump
@@ -974,8 +978,12 @@ class _AttnCore(torch.autograd.Function):
         d_qt = torch.empty_like(q_tgt_add) if has_qt else None
         ex = None
         if has_ex:
+            d_sump = None
+            if has_dm and _d_sump is not None and ctx.sump is not None:
+                d_sump = _f32c(_d_sump)
             ex = _lib.AttnExtras(_p(q_row_add), _p(q_tgt_add), _p(k_row_add), _p(drop_mask),
-                                 _p(d_qr), _p(d_kr))
+                                 _p(d_qr), _p(d_kr), _p(d_sump),
+                                 _p(ctx.sump) if d_sump is not None else None)
         with torch.cuda.device(dev):
             with _timed('attn_bwd_rows', **meta):
                 _lib.check(lib.spt_attn_bwd_rows_ex(
@@ -1057,7 +1065,10 @@ class _ValueRpe(torch.autograd.Function):
         Dv = C // H
         dev = dy.device
         need = ctx.needs_input_grad
-        d_abar = dWv = dbv = None
+        d_abar = dWv = dbv = d_sump = None
+        if need[2] and has_b:   # only under attention dropout (sump is non-differentiable else)
+            bfull = bv.repeat(H) if share else bv
+            d_sump = (dy.view(N, H, Dv) * bfull.view(1, H, Dv)).sum(-1)
         with torch.cuda.device(dev):
             if need[1]:
                 WbdT = torch.empty((H * F, C), dtype=torch.float32, device=dev)
@@ -1082,7 +1093,7 @@ class _ValueRpe(torch.autograd.Function):
                                                    _p(dWv), _p(dbv), _stream()),
                            "spt_vrpe_bwd_params")
                 _count(3)
-        return dy, d_abar, None, dWv, dbv, None, None
+        return dy, d_abar, d_sump, dWv, dbv, None, None
 
 
 def value_rpe(agg, abar, sump, Wv, bv, num_heads, heads_share):

@@ -68,3 +68,26 @@ def test_flat_gradients_accumulate_over_micro_batches():
     want = torch.cat([p.grad.reshape(-1) for p in lin.parameters()])
     assert torch.allclose(got, want, atol=1e-6)
     assert all(p.grad.data_ptr() != 0 for p in lin.parameters())
+
+
+def test_strong_scaling_shards_cover_the_step_exactly_once(monkeypatch):
+    """cfg4 / cfg5 sharding (scenes / tiles LPT-assigned by edge count): the ranks' shares are
+    disjoint, cover the whole step, and every rank derives the same assignment on its own."""
+    small4 = dict(bench.BENCH_CONFIGS['cfg4'], levels=[600, 120, 24], scenes=6, scenes_per_batch=2)
+    small5 = dict(bench.BENCH_CONFIGS['cfg5'], levels=[8000, 1600, 320], tiles=4)
+    monkeypatch.setitem(bench.BENCH_CONFIGS, 'cfg4', small4)
+    monkeypatch.setitem(bench.BENCH_CONFIGS, 'cfg5', small5)
+    for name, per_item in (('cfg4', 600), ('cfg5', None)):
+        world = 2
+        shares = [bench.rank_micro_batches(name, r, world) for r in range(world)]
+        total_sp = sum(m[3] for mbs, _ in shares for m in mbs)
+        infos = [info for _, info in shares]
+        assert infos[0]['edges_per_rank'] == infos[1]['edges_per_rank']
+        assert sum(i['mine'] for i in infos) == infos[0]['items']
+        if per_item:
+            assert total_sp == per_item * infos[0]['items']
+        else:
+            assert total_sp == 8000
+        assert infos[0]['imbalance_max_over_mean'] < 1.35
+        one = bench.rank_micro_batches(name, 0, 1)
+        assert sum(m[3] for m in one[0]) == total_sp
