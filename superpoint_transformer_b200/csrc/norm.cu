@@ -438,16 +438,12 @@ __global__ void k_groupnorm_bwd_coef(const double* __restrict__ s1, const double
   }
 }
 
-// Statistics passes: one slab of rows per CTA, sized so that ~8 CTAs per SM cover N in a single
-// balanced wave (a fixed 128-row slab left 592 CTAs with 1 or 2 slabs each: 66 % efficiency at
-// 100 k rows); slab rows are a multiple of the rows one CTA iteration touches (ty * 4).
+// Statistics passes: persistent CTAs (4 per SM) over 128-row slabs.  (Round 2 tried one
+// balanced wave of ~8 smaller CTAs per SM: the extra fp64 atomics on the [B, C] accumulators
+// cost more than the tail imbalance — cfg-2 step 15.45 -> 15.85 ms — reverted.)
 static inline int norm_slab_rows(int64_t N, int ty) {
-  const int64_t per_iter = (int64_t)ty * 4;
-  int64_t want = (N + (int64_t)device_sm_count() * 8 - 1) / ((int64_t)device_sm_count() * 8);
-  want = (want + per_iter - 1) / per_iter * per_iter;
-  if (want < per_iter) want = per_iter;
-  if (want > (1 << 20)) want = (1 << 20);
-  return (int)want;
+  (void)N; (void)ty;
+  return kNormRows;
 }
 
 static inline ColMap col_map(int64_t C, int vec) {
@@ -519,7 +515,7 @@ int spt_graphnorm_fwd(const float* x, const int64_t* batch, int64_t N, int64_t C
   int vec = (C % 4 == 0) ? 4 : 1;
   ColMap cm = col_map(C, vec);
   const int slab_rows = norm_slab_rows(N, cm.ty);
-  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, slab_rows), device_sm_count() * 8);
+  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, slab_rows), device_sm_count() * 4);
   int64_t total = N * (C / vec);
   int agrid = (int)imin(ceil_div(total > 0 ? total : 1, kNormThreads), device_sm_count() * 16);
   // single pass over x: shifted first and second moments around a per-channel pivot
@@ -573,7 +569,7 @@ int spt_graphnorm_bwd(const float* x, const float* dy, const int64_t* batch, int
   int vec = (C % 4 == 0) ? 4 : 1;
   ColMap cm = col_map(C, vec);
   const int slab_rows = norm_slab_rows(N, cm.ty);
-  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, slab_rows), device_sm_count() * 8);
+  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, slab_rows), device_sm_count() * 4);
   int64_t total = N * (C / vec);
   int agrid = (int)imin(ceil_div(total > 0 ? total : 1, kNormThreads), device_sm_count() * 16);
   if (N > 0) {
@@ -623,7 +619,7 @@ int spt_groupnorm_fwd(const float* x, const int64_t* batch, int64_t N, int64_t C
   int vec = (C % 4 == 0) ? 4 : 1;
   ColMap cm = col_map(C, vec);
   const int slab_rows = norm_slab_rows(N, cm.ty);
-  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, slab_rows), device_sm_count() * 8);
+  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, slab_rows), device_sm_count() * 4);
   int64_t total = N * (C / vec);
   int agrid = (int)imin(ceil_div(total > 0 ? total : 1, kNormThreads), device_sm_count() * 16);
   const unsigned ggrid = (unsigned)ceil_div(B * G, 128);
@@ -683,7 +679,7 @@ int spt_groupnorm_bwd(const float* x, const float* dy, const int64_t* batch, int
   int vec = (C % 4 == 0) ? 4 : 1;
   ColMap cm = col_map(C, vec);
   const int slab_rows = norm_slab_rows(N, cm.ty);
-  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, slab_rows), device_sm_count() * 8);
+  unsigned slabs = (unsigned)imin(ceil_div(N > 0 ? N : 1, slab_rows), device_sm_count() * 4);
   int64_t total = N * (C / vec);
   int agrid = (int)imin(ceil_div(total > 0 ? total : 1, kNormThreads), device_sm_count() * 16);
   if (N > 0) {
