@@ -59,8 +59,14 @@ constexpr int kFragBytes = 16 * 32 * 16;         // one pre-split weight fragmen
 // 2 CTAs per SM: forward 8 warps x 128 registers, backward 6 warps x 168 registers.  The
 // kernels are bound by instruction latency (dependent ALU / shuffle / LDS chains per row), so
 // resident warps per scheduler (4 / 3) are what hides it; shared memory per warp is 9-10 KB.
-constexpr int kFwdWarps = 8;
-constexpr int kBwdWarps = 6;
+#ifndef SPT_FWD_WARPS
+#define SPT_FWD_WARPS 8
+#endif
+#ifndef SPT_BWD_WARPS
+#define SPT_BWD_WARPS 6
+#endif
+constexpr int kFwdWarps = SPT_FWD_WARPS;
+constexpr int kBwdWarps = SPT_BWD_WARPS;
 
 __host__ __device__ inline bool shape_ok(int H, int D, int Dv, int F) {
   return H == kH && D == kD && Dv == kDv && F == kF;
@@ -314,18 +320,20 @@ __device__ __forceinline__ ulonglong2 lds_a_chunk(uint32_t tile, int e0, int u, 
 // accumulation phase of the forward: CNT consecutive edges of the tile starting at e0, no
 // per-edge predicates (the caller decomposes n into 8 + 4 + 2 + 1): CNT gathered v rows in
 // flight, then per edge one LDS.64 (p, p), one LDS.128 of the staged feature row, 4 packed FMAs
-template <int CNT, bool ALIGNED>
-__device__ __forceinline__ void fwd_accumulate(int e0, int mycol, const char* vbase,
-                                               unsigned ldvb, uint64_t keep, const f32x2* pcol,
-                                               uint32_t tile, uint32_t l7s, bool want_abar,
-                                               f32x2& accv01, f32x2& accv23, f32x2& acca01,
-                                               f32x2& acca23) {
-  ulonglong2 vv[CNT];
+template <int CNT>
+__device__ __forceinline__ void fwd_gather(ulonglong2 (&vv)[CNT], int e0, int mycol,
+                                           const char* vbase, unsigned ldvb, uint64_t keep) {
 #pragma unroll
   for (int u = 0; u < CNT; ++u) {
     const unsigned tc = (unsigned)__shfl_sync(kFull, mycol, e0 + u);
     vv[u] = ldg_row16(vbase + (uint64_t)tc * (uint64_t)ldvb, keep);
   }
+}
+template <int CNT, bool ALIGNED>
+__device__ __forceinline__ void fwd_consume(const ulonglong2 (&vv)[CNT], int e0,
+                                            const f32x2* pcol, uint32_t tile, uint32_t l7s,
+                                            bool want_abar, f32x2& accv01, f32x2& accv23,
+                                            f32x2& acca01, f32x2& acca23) {
 #pragma unroll
   for (int u = 0; u < CNT; ++u) {
     const f32x2 pp = pcol[(e0 + u) * kH];
@@ -337,6 +345,16 @@ __device__ __forceinline__ void fwd_accumulate(int e0, int mycol, const char* vb
       fma2(acca23, pp, a4.y);
     }
   }
+}
+template <int CNT, bool ALIGNED>
+__device__ __forceinline__ void fwd_accumulate(int e0, int mycol, const char* vbase,
+                                               unsigned ldvb, uint64_t keep, const f32x2* pcol,
+                                               uint32_t tile, uint32_t l7s, bool want_abar,
+                                               f32x2& accv01, f32x2& accv23, f32x2& acca01,
+                                               f32x2& acca23) {
+  ulonglong2 vv[CNT];
+  fwd_gather<CNT>(vv, e0, mycol, vbase, ldvb, keep);
+  fwd_consume<CNT, ALIGNED>(vv, e0, pcol, tile, l7s, want_abar, accv01, accv23, acca01, acca23);
 }
 
 // backward: dp = <dY, v> + <dAbar, a> partial sums of CNT (<= 8) edges -> s[0..CNT)
@@ -518,6 +536,15 @@ k_attn_fwd_tile(const __grid_constant__ TileMaps tmA, const FwdArgs P) {
         cA[idx] = valid ? pa * kLog2e : -INFINITY;
         cB[idx] = valid ? pb * kLog2e : -INFINITY;
       }
+      // the first 8 gathered v rows are requested now: their latency overlaps the softmax
+      // (the accumulator fragments are dead, the registers are free)
+      ulonglong2 vpre[8];
+#ifdef SPT_FWD_NO_PREFETCH
+      const bool pre = false;
+#else
+      const bool pre = n >= 8;
+#endif
+      if (pre) fwd_gather<8>(vpre, 0, mycol, vbase, ldvb, keep);
       float tA = fmaxf(fmaxf(cA[0], cA[1]), fmaxf(cA[2], cA[3]));
       float tB = fmaxf(fmaxf(cB[0], cB[1]), fmaxf(cB[2], cB[3]));
 #pragma unroll
@@ -557,6 +584,11 @@ k_attn_fwd_tile(const __grid_constant__ TileMaps tmA, const FwdArgs P) {
       const f32x2* pcol = reinterpret_cast<const f32x2*>(p_s) + pw;
       {
         int e0 = 0;
+        if (pre) {
+          fwd_consume<8, true>(vpre, 0, pcol, tile, l7s, want_abar, accv01, accv23, acca01,
+                               acca23);
+          e0 = 8;
+        }
         for (; e0 + 8 <= n; e0 += 8)
           fwd_accumulate<8, true>(e0, mycol, vbase, ldvb, keep, pcol, tile, l7s, want_abar,
                                   accv01, accv23, acca01, acca23);

@@ -39,7 +39,8 @@ NVCC_FLAGS = [
     "-Xptxas=-v",
     "-Xcompiler", "-fPIC",
     "-shared",
-] + (["-DSPT_WATCHDOG"] if os.environ.get("SPT_WATCHDOG") else [])
+] + (["-DSPT_WATCHDOG"] if os.environ.get("SPT_WATCHDOG") else []) \
+  + [f"-D{d}" for d in os.environ.get("SPT_NVCC_DEFINES", "").split() if d]   # tuning experiments
 
 
 def _nvcc():
