@@ -438,12 +438,20 @@ __global__ void k_groupnorm_bwd_coef(const double* __restrict__ s1, const double
   }
 }
 
-// Statistics passes: persistent CTAs (4 per SM) over 128-row slabs.  (Round 2 tried one
-// balanced wave of ~8 smaller CTAs per SM: the extra fp64 atomics on the [B, C] accumulators
-// cost more than the tail imbalance — cfg-2 step 15.45 -> 15.85 ms — reverted.)
+// Statistics passes: ONE contiguous slab of rows per CTA, ~4 CTAs per SM.  Contiguous matters
+// for batches: a CTA that strides over the whole array (the round-1 persistent loop over 128-row
+// slabs) touches every graph of the batch and falls off the "whole CTA in one segment" fast
+// path — GraphNorm on an 8-scene NAGBatch was 2.2x slower than with contiguous slabs (cfg 4).
+// The CTA count stays at ~4 per SM so that the fp64 atomics on the [B, C] accumulators do not
+// grow (8 smaller CTAs per SM measured 3 % slower on the single-scene cfg 2).
 static inline int norm_slab_rows(int64_t N, int ty) {
-  (void)N; (void)ty;
-  return kNormRows;
+  const int64_t per_iter = (int64_t)ty * 4;
+  const int64_t ctas = (int64_t)device_sm_count() * 4;
+  int64_t want = (N + ctas - 1) / ctas;
+  want = (want + per_iter - 1) / per_iter * per_iter;
+  if (want < kNormRows) want = kNormRows;
+  if (want > (1 << 22)) want = (1 << 22);
+  return (int)want;
 }
 
 static inline ColMap col_map(int64_t C, int vec) {
