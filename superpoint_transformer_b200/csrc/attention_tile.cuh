@@ -536,13 +536,14 @@ k_attn_fwd_tile(const __grid_constant__ TileMaps tmA, const FwdArgs P) {
         cA[idx] = valid ? pa * kLog2e : -INFINITY;
         cB[idx] = valid ? pb * kLog2e : -INFINITY;
       }
-      // the first 8 gathered v rows are requested now: their latency overlaps the softmax
-      // (the accumulator fragments are dead, the registers are free)
+      // Requesting the first 8 gathered v rows here, so that their latency overlaps the softmax,
+      // was measured SLOWER (0.418 vs 0.297 ms): at the 128-register budget of 16 warps/SM the 32
+      // extra live registers spill (272 B).  Kept behind SPT_FWD_PREFETCH for the record.
       ulonglong2 vpre[8];
-#ifdef SPT_FWD_NO_PREFETCH
-      const bool pre = false;
-#else
+#ifdef SPT_FWD_PREFETCH
       const bool pre = n >= 8;
+#else
+      const bool pre = false;
 #endif
       if (pre) fwd_gather<8>(vpre, 0, mycol, vbase, ldvb, keep);
       float tA = fmaxf(fmaxf(cA[0], cA[1]), fmaxf(cA[2], cA[3]));

@@ -434,7 +434,7 @@ def index_unpool(x, idx):
 # ---------------------------------------------------------------------------
 # dense projections: fp32-accurate "3xTF32" GEMMs on the tensor cores
 # ---------------------------------------------------------------------------
-LINEAR_TC_MIN_ROWS = 2048   # below this the plain library GEMM is as fast
+LINEAR_TC_MIN_ROWS = int(__import__('os').environ.get('SPT_LINEAR_TC_MIN_ROWS', 2048))   # below this the plain library GEMM is as fast
 LINEAR_TC = True            # fused single-pass 3xTF32 tensor-core GEMMs (csrc/gemm.cu)
 
 
