@@ -50,9 +50,12 @@ BENCH_CONFIGS = {
                  workload=f"cfg2: S3DIS-shaped 3-level NAG 100k/20k/4k superpoints, {_LAW}; "
                           f"{_MODEL}"),
     'cfg3': dict(levels=[500_000, 100_000, 20_000], no_ffn=True, scaling='weak', seed=2,
-                 metric="superpoints/sec (fwd+bwd) on 500k-SP 3-level NAG (DALES tile)",
+                 attn_storage='bf16',
+                 metric="superpoints/sec (fwd+bwd) on 500k-SP 3-level NAG (DALES tile), bf16 storage",
                  workload=f"cfg3: DALES-tile 3-level NAG 500k/100k/20k superpoints, {_LAW}; "
-                          f"{_MODEL}"),
+                          f"{_MODEL}; bf16 STORAGE of the attention operands (fused projections "
+                          f"qkv and edge features), fp32 accumulation / outputs / gradients / "
+                          f"everything else"),
     'cfg4': dict(levels=[50_000, 10_000, 2_000], no_ffn=False, scaling='strong', seed=100,
                  scenes=64, scenes_per_batch=8,
                  metric="superpoints/sec (fwd+bwd), 64 scenes x 50k-SP 3-level NAGs per step",
@@ -368,6 +371,7 @@ def run_own(args):
     torch.backends.cudnn.allow_tf32 = False
     torch.manual_seed(0)
 
+    ops.set_attention_storage(args.attn_storage or cfg.get('attn_storage', 'fp32'))
     net = S.SPT(mlp_norm=S.nn.GraphNorm, norm=S.nn.GraphNorm,
                 **model_kwargs(S, no_ffn=cfg['no_ffn']))
     net.apply(S.init_weights)
@@ -684,7 +688,9 @@ def run_own(args):
             "metric": cfg['metric'], "value": round(value, 1), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
             "higher_is_better": True, "scaling": cfg['scaling'], "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "f32" if ops.ATTN_STORAGE == 'fp32' else
+                     "bf16 storage (attention operands) / f32 accumulate",
+            "data": "synthetic",
             "config": config,
             "exec": {"superpoints_per_step": int(sp_total), "superpoints_this_rank": int(sp_rank),
                      "micro_batches_this_rank": n_mb, "edges_level1_this_rank": edges_l1,
@@ -899,6 +905,8 @@ def main():
     ap.add_argument('--impl', default='own', choices=['own', 'reference'])
     ap.add_argument('--config', default=os.environ.get('BENCH_CONFIG', 'cfg2'),
                     choices=sorted(BENCH_CONFIGS))
+    ap.add_argument('--attn-storage', default=None, choices=['fp32', 'bf16'],
+                    help="override the configuration's storage of the attention operands")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='eager launches, no CUDA graphs')
     ap.add_argument('--kernels-out', default=None, help='write the full per-kernel timing table (JSON)')

@@ -345,6 +345,29 @@ int spt_attn_bwd_targets_ex(const int32_t* csc_ptr, const int32_t* csc_src,
                             float* dk, int64_t lddk, float* dv, int64_t lddv,
                             float* d_q_tgt_add /*[T, H*D] nullable*/, void* stream);
 
+/* bf16 STORAGE of the attention operands (BASELINE cfg 3: "bf16, fp32 accumulate"): q / k / v
+ * (leading dimensions in elements) and the CSR-ordered edge features a [E, 32] are bf16 in HBM,
+ * weights / statistics / outputs / gradients stay fp32, every sum is fp32 (the RPE products run as
+ * bf16 tensor-core MMAs with fp32 accumulation).  Only the shape family of the row-tile kernels
+ * (H=4, D=4, Dv=32, F=32); anything else returns SPT_E_UNSUPPORTED (the caller uses the fp32
+ * entry points).  The backward writes fp32 dq / da / P / G; d[Wq;Wk] (spt_gemm_tn_acc on G and
+ * the fp32 features) and spt_attn_bwd_targets are the fp32 calls. */
+int spt_cast_bf16(const float* x, int64_t n, uint16_t* out, void* stream);
+int spt_attn_fwd_bf16(const uint16_t* q, int64_t ldq, const uint16_t* k, int64_t ldk,
+                      const uint16_t* v, int64_t ldv, const uint16_t* a /*[E,32]*/,
+                      const int32_t* rowptr, const int32_t* col, int64_t num_rows, int64_t E,
+                      int H, int D, int Dv, int F, const float* Wq, const float* bq,
+                      const float* Wk, const float* bk, int scale_mode, float scale_value,
+                      float* agg_v, float* abar, float* sump, float* m, float* z, void* stream);
+int spt_attn_bwd_rows_bf16(const uint16_t* q, int64_t ldq, const uint16_t* k, int64_t ldk,
+                           const uint16_t* v, int64_t ldv, const uint16_t* a,
+                           const int32_t* rowptr, const int32_t* col, int64_t num_rows, int64_t E,
+                           int H, int D, int Dv, int F, const float* Wq, const float* bq,
+                           const float* Wk, const float* bk, int scale_mode, float scale_value,
+                           const float* m, const float* z, const float* agg_v, const float* abar,
+                           const float* d_agg_v, const float* d_abar, float* dq, int64_t lddq,
+                           float* da, float* Pbuf, float* G, void* stream);
+
 /* Backward of spt_attn_fwd, three launches so each can be timed on its own:
  *  (1) rows    : per CSR row, recompute p from (m, z); writes dq [R rows, lddq],
  *                da [E,F] (CSR order, nullable) and the per-edge scratch

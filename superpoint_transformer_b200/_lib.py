@@ -80,6 +80,17 @@ SIGNATURES = {
                                      c_ptr, c_i64, c_ptr,
                                      c_ptr, c_ptr, c_ptr, c_ptr,
                                      c_ptr, c_ptr, c_ptr, c_ptr]),
+    "spt_cast_bf16": (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
+    "spt_attn_fwd_bf16": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr,
+                                  c_ptr, c_i64, c_i64, c_int, c_int, c_int, c_int, c_ptr,
+                                  c_ptr, c_ptr, c_ptr, c_int, c_f32, c_ptr, c_ptr, c_ptr,
+                                  c_ptr, c_ptr, c_ptr]),
+    "spt_attn_bwd_rows_bf16": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr,
+                                       c_ptr, c_ptr, c_i64, c_i64,
+                                       c_int, c_int, c_int, c_int,
+                                       c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_f32,
+                                       c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                       c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
     "spt_attn_bwd_targets_ex": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int, c_int, c_int,
                                         c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_ptr,
                                         c_ptr]),

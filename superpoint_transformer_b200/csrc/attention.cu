@@ -521,6 +521,7 @@ bool tn_shape_ok(const float* A, int64_t M, int64_t N, int64_t lda, const float*
 int tn_launch(const float* A, int64_t M, int64_t N, int64_t lda, const float* B, int64_t K,
               int64_t ldb, float* C, int64_t ldc, float* colsum, cudaStream_t stream);
 bool make_map_rows32(CUtensorMap* tm, const float* ptr, int64_t rows, int64_t ld, int box_rows);
+bool make_map_rows32_bf16(CUtensorMap* tm, const void* ptr, int64_t rows, int box_rows);
 }  // namespace umma
 }  // namespace spt
 
@@ -564,6 +565,12 @@ static int tile_rows_per_warp(int64_t num_rows, int warps_per_cta) {
 static bool make_tile_maps(tile::TileMaps* tm, const float* a, int64_t E, int F) {
   for (int i = 0; i < 4; ++i)
     if (!umma::make_map_rows32(&tm->m[i], a, E, F, 8 * (i + 1))) return false;
+  return true;
+}
+
+static bool make_tile_maps_bf16(tile::TileMaps* tm, const void* a, int64_t E) {
+  for (int i = 0; i < 4; ++i)
+    if (!umma::make_map_rows32_bf16(&tm->m[i], a, E, 8 * (i + 1))) return false;
   return true;
 }
 
@@ -623,9 +630,9 @@ int spt_attn_fwd_ex(const float* q, int64_t ldq, const float* k, int64_t ldk, co
       A.rows_per_warp = tile_rows_per_warp(num_rows, tile::kFwdWarps);
       const int smem = tile::FwdSmem::total + 1024;
       static unsigned long long done = 0;
-      ensure_dynamic_smem(tile::k_attn_fwd_tile, smem, &done);
+      ensure_dynamic_smem(tile::k_attn_fwd_tile<false>, smem, &done);
       const int64_t warps = ceil_div(num_rows, A.rows_per_warp);
-      tile::k_attn_fwd_tile<<<(unsigned)ceil_div(warps, tile::kFwdWarps), tile::kFwdWarps * kWarp,
+      tile::k_attn_fwd_tile<false><<<(unsigned)ceil_div(warps, tile::kFwdWarps), tile::kFwdWarps * kWarp,
                               smem, st>>>(tmA, A);
       return check_launch("attn_fwd(tile)");
     }
@@ -717,9 +724,9 @@ int spt_attn_bwd_rows_ex(const float* q, int64_t ldq, const float* k, int64_t ld
       A.rows_per_warp = tile_rows_per_warp(num_rows, tile::kBwdWarps);
       const int smem = tile::BwdSmem::total + 1024;
       static unsigned long long done = 0;
-      ensure_dynamic_smem(tile::k_attn_bwd_tile, smem, &done);
+      ensure_dynamic_smem(tile::k_attn_bwd_tile<false>, smem, &done);
       const int64_t warps = ceil_div(num_rows, A.rows_per_warp);
-      tile::k_attn_bwd_tile<<<(unsigned)ceil_div(warps, tile::kBwdWarps), tile::kBwdWarps * kWarp,
+      tile::k_attn_bwd_tile<false><<<(unsigned)ceil_div(warps, tile::kBwdWarps), tile::kBwdWarps * kWarp,
                               smem, st>>>(tmA, A);
       int rc2 = check_launch("attn_bwd_rows(tile)");
       if (rc2 != SPT_OK) return rc2;
@@ -857,6 +864,90 @@ int spt_attn_bwd_weights(const float* G, const float* a, int64_t E, int H, int D
   k_attn_bwd_dw_generic<<<(unsigned)ctas, kDwThreads, smem, (cudaStream_t)stream_>>>(
       G, a, E, s, per, dWq, dbq, dWk, dbk);
   return check_launch("attn_bwd_weights");
+}
+
+
+// --------------------------------------------------------------------------------------------
+// bf16 storage of the attention operands (BASELINE cfg 3): q / k / v and the edge features are
+// bf16 in HBM (halves the gather and stream traffic), every sum is fp32; shape family of the
+// row-tile kernels only.
+// --------------------------------------------------------------------------------------------
+static bool bf16_layout_ok(const void* q, const void* k, const void* v, const void* a,
+                           int64_t ldq, int64_t ldk, int64_t ldv, int64_t rows, int64_t E) {
+  return E > 0 && E < (1ll << 31) - 64 && ldq % 2 == 0 && ldk % 2 == 0 && ldv % 4 == 0 &&
+         (((uintptr_t)q | (uintptr_t)k) & 3) == 0 && ((uintptr_t)v & 7) == 0 &&
+         ((uintptr_t)a & 15) == 0 && ldq < (1 << 20) && ldk < (1 << 20) && ldv < (1 << 20) &&
+         rows * (ldk > ldv ? ldk : ldv) * 2 < (int64_t)4000000000LL;
+}
+
+int spt_attn_fwd_bf16(const uint16_t* q, int64_t ldq, const uint16_t* k, int64_t ldk,
+                      const uint16_t* v, int64_t ldv, const uint16_t* a, const int32_t* rowptr,
+                      const int32_t* col, int64_t num_rows, int64_t E, int H, int D, int Dv, int F,
+                      const float* Wq, const float* bq, const float* Wk, const float* bk,
+                      int scale_mode, float scale_value, float* agg_v, float* abar, float* sump,
+                      float* m, float* z, void* stream_) {
+  SPT_REQUIRE(num_rows >= 0 && E >= 0, SPT_E_INVALID, "attn_fwd_bf16: negative size");
+  if (num_rows == 0) return SPT_OK;
+  SPT_REQUIRE(q && k && v && a && rowptr && col && agg_v && sump && m && z, SPT_E_INVALID,
+              "attn_fwd_bf16: null pointer");
+  SPT_REQUIRE(tile::shape_ok(H, D, Dv, F) && bf16_layout_ok(q, k, v, a, ldq, ldk, ldv, num_rows, E),
+              SPT_E_UNSUPPORTED,
+              "attn_fwd_bf16: only H=4, D=4, Dv=32, F=32 with aligned operands and E > 0");
+  tile::TileMaps tmA;
+  SPT_REQUIRE(make_tile_maps_bf16(&tmA, a, E), SPT_E_UNSUPPORTED,
+              "attn_fwd_bf16: cuTensorMapEncodeTiled failed");
+  tile::FwdArgs A;
+  A.q = q; A.ldq = (int)ldq; A.k = k; A.ldk = (int)ldk; A.v = v; A.ldv = (int)ldv;
+  A.rowptr = rowptr; A.col = col; A.num_rows = num_rows;
+  A.Wq = Wq; A.bq = bq; A.Wk = Wk; A.bk = bk;
+  A.scale_mode = scale_mode; A.scale_value = scale_value;
+  A.agg_v = agg_v; A.abar = abar; A.sump = sump; A.m = m; A.z = z;
+  A.rows_per_warp = tile_rows_per_warp(num_rows, tile::kFwdWarps);
+  const int smem = tile::FwdSmem::total + 1024;
+  static unsigned long long done = 0;
+  ensure_dynamic_smem(tile::k_attn_fwd_tile<true>, smem, &done);
+  const int64_t warps = ceil_div(num_rows, A.rows_per_warp);
+  tile::k_attn_fwd_tile<true><<<(unsigned)ceil_div(warps, tile::kFwdWarps), tile::kFwdWarps * kWarp,
+                                smem, (cudaStream_t)stream_>>>(tmA, A);
+  return check_launch("attn_fwd_bf16");
+}
+
+int spt_attn_bwd_rows_bf16(const uint16_t* q, int64_t ldq, const uint16_t* k, int64_t ldk,
+                           const uint16_t* v, int64_t ldv, const uint16_t* a,
+                           const int32_t* rowptr, const int32_t* col, int64_t num_rows, int64_t E,
+                           int H, int D, int Dv, int F, const float* Wq, const float* bq,
+                           const float* Wk, const float* bk, int scale_mode, float scale_value,
+                           const float* m, const float* z, const float* agg_v, const float* abar,
+                           const float* d_agg_v, const float* d_abar, float* dq, int64_t lddq,
+                           float* da, float* Pbuf, float* G, void* stream_) {
+  SPT_REQUIRE(num_rows >= 0 && E >= 0, SPT_E_INVALID, "attn_bwd_rows_bf16: negative size");
+  if (num_rows == 0) return SPT_OK;
+  SPT_REQUIRE(q && k && v && a && rowptr && col && m && z && agg_v && d_agg_v && dq && Pbuf && G,
+              SPT_E_INVALID, "attn_bwd_rows_bf16: null pointer");
+  SPT_REQUIRE(tile::shape_ok(H, D, Dv, F) && bf16_layout_ok(q, k, v, a, ldq, ldk, ldv, num_rows, E) &&
+                  lddq < (1 << 20) && lddq % 2 == 0 && ((uintptr_t)dq & 7) == 0 &&
+                  ((uintptr_t)G & 7) == 0 && (!da || ((uintptr_t)da & 7) == 0) &&
+                  ((uintptr_t)d_agg_v & 15) == 0 && ((uintptr_t)agg_v & 15) == 0 &&
+                  (!abar || ((uintptr_t)abar & 15) == 0) && (!d_abar || ((uintptr_t)d_abar & 15) == 0),
+              SPT_E_UNSUPPORTED, "attn_bwd_rows_bf16: unsupported shape / alignment");
+  tile::TileMaps tmA;
+  SPT_REQUIRE(make_tile_maps_bf16(&tmA, a, E), SPT_E_UNSUPPORTED,
+              "attn_bwd_rows_bf16: cuTensorMapEncodeTiled failed");
+  tile::BwdArgs A;
+  A.q = q; A.ldq = (int)ldq; A.k = k; A.ldk = (int)ldk; A.v = v; A.ldv = (int)ldv;
+  A.rowptr = rowptr; A.col = col; A.num_rows = num_rows;
+  A.Wq = Wq; A.bq = bq; A.Wk = Wk; A.bk = bk;
+  A.scale_mode = scale_mode; A.scale_value = scale_value;
+  A.m = m; A.z = z; A.agg_v = agg_v; A.abar = abar; A.d_agg_v = d_agg_v; A.d_abar = d_abar;
+  A.dq = dq; A.lddq = (int)lddq; A.da = da; A.Pbuf = Pbuf; A.G = G;
+  A.rows_per_warp = tile_rows_per_warp(num_rows, tile::kBwdWarps);
+  const int smem = tile::BwdSmem::total + 1024;
+  static unsigned long long done = 0;
+  ensure_dynamic_smem(tile::k_attn_bwd_tile<true>, smem, &done);
+  const int64_t warps = ceil_div(num_rows, A.rows_per_warp);
+  tile::k_attn_bwd_tile<true><<<(unsigned)ceil_div(warps, tile::kBwdWarps), tile::kBwdWarps * kWarp,
+                                smem, (cudaStream_t)stream_>>>(tmA, A);
+  return check_launch("attn_bwd_rows_bf16");
 }
 
 }  // extern "C"

@@ -106,6 +106,40 @@ __device__ __forceinline__ float2 ldg_row8(const char* p, uint64_t policy) {
                : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(policy));
   return v;
 }
+__device__ __forceinline__ uint32_t ldg_row4(const char* p, uint64_t policy) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b32 %0, [%1], %2;"
+               : "=r"(v) : "l"(p), "l"(policy));
+  return v;
+}
+__device__ __forceinline__ uint2 ldg_row8u(const char* p, uint64_t policy) {
+  uint2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.b32 {%0,%1}, [%2], %3;"
+               : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(policy));
+  return v;
+}
+// bf16 pair (low half = first element) -> two fp32
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t x) {
+  return make_float2(__uint_as_float(x << 16), __uint_as_float(x & 0xffff0000u));
+}
+__device__ __forceinline__ f32x2 bf2_to_f32x2(uint32_t x) {
+  return pack2(__uint_as_float(x << 16), __uint_as_float(x & 0xffff0000u));
+}
+// two fp32 -> packed bf16 pair (round to nearest even), low half = first element
+__device__ __forceinline__ uint32_t f2_to_bf2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+      "{%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 // the four tensor maps of the edge-feature matrix: boxes of 8 / 16 / 24 / 32 rows, so that a
 // tile of any size is ONE TMA instruction
 struct TileMaps {
@@ -166,6 +200,7 @@ struct TilePipe {
   uint64_t* bar;            // 2 mbarriers
   const TileMaps* tm;
   uint64_t policy;
+  uint32_t box_bytes;       // bytes of one 8-row box: 1024 (fp32 features) / 512 (bf16)
   int lane;
   uint32_t uses0, uses1;    // completed uses of each stage (phase parity)
   int staged_tb;            // first slot of the tile in flight in stage `next`, -1 if none
@@ -186,7 +221,7 @@ struct TilePipe {
     if (lane == 0) {
       const int nb = (n + 7) >> 3;     // 1..4 boxes of 8 rows = one box of the nb-th map
       unsigned char* dst = buf + stage * kChunkBytes;
-      mbar_expect_tx(&bar[stage], (uint32_t)nb * 1024u);
+      mbar_expect_tx(&bar[stage], (uint32_t)nb * box_bytes);
       tma_box(dst, &tm->m[nb - 1], tb, &bar[stage], policy);
     }
   }
@@ -254,6 +289,66 @@ __device__ __forceinline__ void build_bias(float* bias_s, const float* Wq, const
   }
 }
 
+// bf16 storage variant (cfg 3): the features arrive as bf16 [E, 32] (64-byte rows, SWIZZLE_64B:
+// the 16-byte chunk c of tile row r sits at r*64 + ((c ^ ((r >> 1) & 3)) << 4)), the products run
+// as single mma.sync.m16n8k16 bf16 with fp32 accumulation (no split), weights rounded to bf16
+// once per CTA:
+//   frag1b[(ks*4 + nn)*32 + lane] = {b0, b1}: b0 = (W[8nn+g][16ks+2t], W[8nn+g][16ks+2t+1]),
+//                                            b1 = the same at k + 8            (r = a W^T)
+//   frag2b[(ks*4 + nf)*32 + lane]: b0 = (W[16ks+2t][8nf+g], W[16ks+2t+1][8nf+g]), b1 at o + 8
+//                                  (da = G W; the accumulator fragment IS the A fragment)
+__device__ __forceinline__ void build_frag1_bf16(uint2* frag, const float* Wq, const float* Wk) {
+  for (int i = threadIdx.x; i < 8 * 32; i += blockDim.x) {
+    const int ln = i & 31, fr = i >> 5, ks = fr >> 2, nn = fr & 3, g = ln >> 2, t = ln & 3;
+    const int o = 8 * nn + g, f = 16 * ks + 2 * t;
+    frag[i] = make_uint2(f2_to_bf2(w_at(Wq, Wk, o, f), w_at(Wq, Wk, o, f + 1)),
+                         f2_to_bf2(w_at(Wq, Wk, o, f + 8), w_at(Wq, Wk, o, f + 9)));
+  }
+}
+__device__ __forceinline__ void build_frag2_bf16(uint2* frag, const float* Wq, const float* Wk) {
+  for (int i = threadIdx.x; i < 8 * 32; i += blockDim.x) {
+    const int ln = i & 31, fr = i >> 5, ks = fr >> 2, nf = fr & 3, g = ln >> 2, t = ln & 3;
+    const int o = 16 * ks + 2 * t, f = 8 * nf + g;
+    frag[i] = make_uint2(f2_to_bf2(w_at(Wq, Wk, o, f), w_at(Wq, Wk, o + 1, f)),
+                         f2_to_bf2(w_at(Wq, Wk, o + 8, f), w_at(Wq, Wk, o + 9, f)));
+  }
+}
+__device__ __forceinline__ void rpe_tile_bf16(float (&acc)[2][4][4], uint32_t tile, bool two,
+                                              const uint2* frag1, const float* bias_s, int lane) {
+  const int t = lane & 3;
+#pragma unroll
+  for (int nn = 0; nn < 4; ++nn) {
+    const float2 b = *reinterpret_cast<const float2*>(bias_s + 8 * nn + 2 * t);
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      acc[m][nn][0] = b.x; acc[m][nn][1] = b.y; acc[m][nn][2] = b.x; acc[m][nn][3] = b.y;
+    }
+  }
+  // ldmatrix: lane L feeds tile row 16m + (L&7) + 8*((L>>3)&1), 16-byte chunk 2ks + (L>>4)
+  const int r0 = (lane & 7) + ((lane >> 3) & 1) * 8;
+  const uint32_t row0 = tile + (uint32_t)(r0 * 64);
+  const uint32_t rsw = (uint32_t)((r0 >> 1) & 3), csel = (uint32_t)(lane >> 4);
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    const uint32_t coff = ((2 * ks + csel) ^ rsw) << 4;   // (r0 + 16) >> 1 & 3 == rsw as well
+    uint2 b[4];
+#pragma unroll
+    for (int nn = 0; nn < 4; ++nn) b[nn] = frag1[(ks * 4 + nn) * 32 + lane];
+    {
+      uint32_t a[4];
+      ldsm_x4(row0 + coff, a[0], a[1], a[2], a[3]);
+#pragma unroll
+      for (int nn = 0; nn < 4; ++nn) mma_bf16(acc[0][nn], a, b[nn].x, b[nn].y);
+    }
+    if (two) {
+      uint32_t a[4];
+      ldsm_x4(row0 + 16 * 64 + coff, a[0], a[1], a[2], a[3]);
+#pragma unroll
+      for (int nn = 0; nn < 4; ++nn) mma_bf16(acc[1][nn], a, b[nn].x, b[nn].y);
+    }
+  }
+}
+
 // R = A_tile . W^T + bias for the tile at shared-memory address `tile`:
 // acc[m][nn][.] = accumulator fragments (m-tile m = edges 16m..16m+15, n-tile nn = outputs
 // 8nn..8nn+7): c0,c1 = (edge 16m+g, outputs 8nn+2t, +1), c2,c3 = (edge 16m+8+g, same outputs).
@@ -302,9 +397,23 @@ __device__ __forceinline__ float fast_rcp(float x) {
   return y;
 }
 
-// my 16-byte chunk of tile row r (the row's features 4*(lane&7)..): r*128 + ((l7 ^ (r&7)) << 4)
-template <bool ALIGNED>
+// my 4 features 4*(lane&7).. of tile row r as two packed fp32 pairs.
+//   fp32 tiles: 16-byte chunk (lane&7) of the 128-byte row, at ((l7 ^ (r&7)) << 4)
+//   bf16 tiles: 8 bytes in the 64-byte row: chunk l7>>1 at ((l7>>1) ^ ((r>>1)&3)) << 4, half l7&1
+template <bool BF, bool ALIGNED>
 __device__ __forceinline__ ulonglong2 lds_a_chunk(uint32_t tile, int e0, int u, uint32_t l7s) {
+  ulonglong2 a4;
+  if (BF) {
+    const uint32_t l7 = l7s >> 4;
+    const uint32_t r = (uint32_t)(e0 + u);
+    const uint32_t sw = ALIGNED ? (uint32_t)((u >> 1) & 3) : ((r >> 1) & 3u);
+    const uint32_t ad = tile + r * 64u + ((((l7 >> 1) ^ sw)) << 4) + ((l7 & 1u) << 3);
+    uint2 w;
+    asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(w.x), "=r"(w.y) : "r"(ad));
+    a4.x = bf2_to_f32x2(w.x);
+    a4.y = bf2_to_f32x2(w.y);
+    return a4;
+  }
   uint32_t ad;
   if (ALIGNED) {   // e0 % 8 == 0: (e0 + u) & 7 == u, a compile-time constant
     ad = tile + (uint32_t)(e0 * 128) + (uint32_t)(u * 128) + (l7s ^ (uint32_t)(u << 4));
@@ -312,24 +421,63 @@ __device__ __forceinline__ ulonglong2 lds_a_chunk(uint32_t tile, int e0, int u, 
     const uint32_t r = (uint32_t)(e0 + u);
     ad = tile + r * 128u + (l7s ^ ((r & 7u) << 4));
   }
-  ulonglong2 a4;
   asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(a4.x), "=l"(a4.y) : "r"(ad));
   return a4;
+}
+
+// my 4 value channels of the gathered row `tc` as two packed fp32 pairs
+template <bool BF>
+__device__ __forceinline__ ulonglong2 gather_v(const char* vbase, unsigned tc, unsigned ldvb,
+                                               uint64_t keep) {
+  if (BF) {
+    const uint2 w = ldg_row8u(vbase + (uint64_t)tc * (uint64_t)ldvb, keep);
+    ulonglong2 v;
+    v.x = bf2_to_f32x2(w.x);
+    v.y = bf2_to_f32x2(w.y);
+    return v;
+  }
+  return ldg_row16(vbase + (uint64_t)tc * (uint64_t)ldvb, keep);
+}
+// k[tc][2t, 2t+1] and k[tc][8+2t, 8+2t+1]
+template <bool BF>
+__device__ __forceinline__ void gather_k(const char* kbase, unsigned tc, unsigned ldkb,
+                                         uint64_t keep, float2& kA, float2& kB) {
+  const char* kp = kbase + (uint64_t)tc * (uint64_t)ldkb;
+  if (BF) {
+    kA = bf2_to_f2(ldg_row4(kp, keep));
+    kB = bf2_to_f2(ldg_row4(kp + 16, keep));
+  } else {
+    kA = ldg_row8(kp, keep);
+    kB = ldg_row8(kp + 32, keep);
+  }
+}
+template <bool BF>
+__device__ __forceinline__ void load_q(const void* q, int64_t row, int ldq, int t, float2& qA,
+                                       float2& qB) {
+  if (BF) {
+    const uint16_t* p = reinterpret_cast<const uint16_t*>(q) + row * ldq + 2 * t;
+    qA = bf2_to_f2(*reinterpret_cast<const uint32_t*>(p));
+    qB = bf2_to_f2(*reinterpret_cast<const uint32_t*>(p + 8));
+  } else {
+    const float* p = reinterpret_cast<const float*>(q) + row * ldq + 2 * t;
+    qA = *reinterpret_cast<const float2*>(p);
+    qB = *reinterpret_cast<const float2*>(p + 8);
+  }
 }
 
 // accumulation phase of the forward: CNT consecutive edges of the tile starting at e0, no
 // per-edge predicates (the caller decomposes n into 8 + 4 + 2 + 1): CNT gathered v rows in
 // flight, then per edge one LDS.64 (p, p), one LDS.128 of the staged feature row, 4 packed FMAs
-template <int CNT>
+template <bool BF, int CNT>
 __device__ __forceinline__ void fwd_gather(ulonglong2 (&vv)[CNT], int e0, int mycol,
                                            const char* vbase, unsigned ldvb, uint64_t keep) {
 #pragma unroll
   for (int u = 0; u < CNT; ++u) {
     const unsigned tc = (unsigned)__shfl_sync(kFull, mycol, e0 + u);
-    vv[u] = ldg_row16(vbase + (uint64_t)tc * (uint64_t)ldvb, keep);
+    vv[u] = gather_v<BF>(vbase, tc, ldvb, keep);
   }
 }
-template <int CNT, bool ALIGNED>
+template <bool BF, int CNT, bool ALIGNED>
 __device__ __forceinline__ void fwd_consume(const ulonglong2 (&vv)[CNT], int e0,
                                             const f32x2* pcol, uint32_t tile, uint32_t l7s,
                                             bool want_abar, f32x2& accv01, f32x2& accv23,
@@ -340,25 +488,26 @@ __device__ __forceinline__ void fwd_consume(const ulonglong2 (&vv)[CNT], int e0,
     fma2(accv01, pp, vv[u].x);
     fma2(accv23, pp, vv[u].y);
     if (want_abar) {
-      const ulonglong2 a4 = lds_a_chunk<ALIGNED>(tile, e0, u, l7s);
+      const ulonglong2 a4 = lds_a_chunk<BF, ALIGNED>(tile, e0, u, l7s);
       fma2(acca01, pp, a4.x);
       fma2(acca23, pp, a4.y);
     }
   }
 }
-template <int CNT, bool ALIGNED>
+template <bool BF, int CNT, bool ALIGNED>
 __device__ __forceinline__ void fwd_accumulate(int e0, int mycol, const char* vbase,
                                                unsigned ldvb, uint64_t keep, const f32x2* pcol,
                                                uint32_t tile, uint32_t l7s, bool want_abar,
                                                f32x2& accv01, f32x2& accv23, f32x2& acca01,
                                                f32x2& acca23) {
   ulonglong2 vv[CNT];
-  fwd_gather<CNT>(vv, e0, mycol, vbase, ldvb, keep);
-  fwd_consume<CNT, ALIGNED>(vv, e0, pcol, tile, l7s, want_abar, accv01, accv23, acca01, acca23);
+  fwd_gather<BF, CNT>(vv, e0, mycol, vbase, ldvb, keep);
+  fwd_consume<BF, CNT, ALIGNED>(vv, e0, pcol, tile, l7s, want_abar, accv01, accv23, acca01,
+                                acca23);
 }
 
 // backward: dp = <dY, v> + <dAbar, a> partial sums of CNT (<= 8) edges -> s[0..CNT)
-template <int CNT, bool ALIGNED>
+template <bool BF, int CNT, bool ALIGNED>
 __device__ __forceinline__ void bwd_partials(float (&s)[8], int e0, int mycol, const char* vbase,
                                              unsigned ldvb, uint64_t keep, uint32_t tile,
                                              uint32_t l7s, bool has_dab, f32x2 dy01, f32x2 dy23,
@@ -367,14 +516,14 @@ __device__ __forceinline__ void bwd_partials(float (&s)[8], int e0, int mycol, c
 #pragma unroll
   for (int u = 0; u < CNT; ++u) {
     const unsigned tc = (unsigned)__shfl_sync(kFull, mycol, e0 + u);
-    vv[u] = ldg_row16(vbase + (uint64_t)tc * (uint64_t)ldvb, keep);
+    vv[u] = gather_v<BF>(vbase, tc, ldvb, keep);
   }
 #pragma unroll
   for (int u = 0; u < CNT; ++u) {
     f32x2 d2 = mul2(dy01, vv[u].x);
     fma2(d2, dy23, vv[u].y);
     if (has_dab) {
-      const ulonglong2 a4 = lds_a_chunk<ALIGNED>(tile, e0, u, l7s);
+      const ulonglong2 a4 = lds_a_chunk<BF, ALIGNED>(tile, e0, u, l7s);
       fma2(d2, dab01, a4.x);
       fma2(d2, dab23, a4.y);
     }
@@ -383,9 +532,9 @@ __device__ __forceinline__ void bwd_partials(float (&s)[8], int e0, int mycol, c
 }
 
 struct FwdArgs {
-  const float* q; int ldq;
-  const float* k; int ldk;
-  const float* v; int ldv;
+  const void* q; int ldq;     // fp32 or bf16 (template parameter BF), leading dims in elements
+  const void* k; int ldk;
+  const void* v; int ldv;
   const int32_t* rowptr; const int32_t* col;
   int64_t num_rows;
   const float* Wq; const float* bq; const float* Wk; const float* bk;
@@ -431,8 +580,10 @@ struct Cursor {
   }
 };
 
+template <bool BF>
 __global__ void __launch_bounds__(kFwdWarps * 32, 2)
 k_attn_fwd_tile(const __grid_constant__ TileMaps tmA, const FwdArgs P) {
+  constexpr int kElt = BF ? 2 : 4;
   using L = FwdSmem;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem =
@@ -443,7 +594,8 @@ k_attn_fwd_tile(const __grid_constant__ TileMaps tmA, const FwdArgs P) {
   const float* bias_s = reinterpret_cast<const float*>(smem + L::bias_off);
   float2* p_s = reinterpret_cast<float2*>(smem + L::p_off) + w * 32 * kH;   // (p, p) pairs
 
-  build_frag1(reinterpret_cast<uint4*>(smem + L::frag_off), P.Wq, P.Wk);
+  if (BF) build_frag1_bf16(reinterpret_cast<uint2*>(smem + L::frag_off), P.Wq, P.Wk);
+  else build_frag1(reinterpret_cast<uint4*>(smem + L::frag_off), P.Wq, P.Wk);
   build_bias(reinterpret_cast<float*>(smem + L::bias_off), P.Wq, P.bq, P.Wk, P.bk);
   __syncthreads();
 
@@ -456,6 +608,7 @@ k_attn_fwd_tile(const __grid_constant__ TileMaps tmA, const FwdArgs P) {
   pipe.bar = reinterpret_cast<uint64_t*>(smem + L::bar_off) + w * 2;
   pipe.tm = &tmA;
   pipe.policy = policy_evict_first();
+  pipe.box_bytes = BF ? 512u : 1024u;
   pipe.lane = lane;
   pipe.init();
   const uint64_t keep = policy_evict_last();
@@ -473,15 +626,15 @@ k_attn_fwd_tile(const __grid_constant__ TileMaps tmA, const FwdArgs P) {
   const int hb = lane >> 3;                     // head of my 4 value channels
   const int hsrc = 2 * (hb & 1);                // a lane holding head hb in the fragment layout
   const int pw = ((hb & 1) << 1) | (hb >> 1);   // word of head hb in a p-tile row [h0 h2 h1 h3]
-  const char* kbase = reinterpret_cast<const char*>(P.k + 2 * t);
-  const char* vbase = reinterpret_cast<const char*>(P.v + 4 * lane);
-  const unsigned ldkb = (unsigned)P.ldk * 4u, ldvb = (unsigned)P.ldv * 4u;   // row strides, bytes
+  const char* kbase = reinterpret_cast<const char*>(P.k) + 2 * t * kElt;
+  const char* vbase = reinterpret_cast<const char*>(P.v) + 4 * lane * kElt;
+  const unsigned ldkb = (unsigned)P.ldk * kElt, ldvb = (unsigned)P.ldv * kElt;   // row strides, bytes
   // byte offset of my 16-byte chunk in tile row u of a group of 8: u * 128 + ((l7 ^ u) << 4)
   const uint32_t l7s = (uint32_t)((lane & 7) << 4);
 
   int mycol = (lane < min(32, cu.e - cu.b)) ? P.col[cu.b + lane] : 0;
-  float2 qA = *reinterpret_cast<const float2*>(P.q + row0 * P.ldq + 2 * t);
-  float2 qB = *reinterpret_cast<const float2*>(P.q + row0 * P.ldq + 8 + 2 * t);
+  float2 qA, qB;
+  load_q<BF>(P.q, row0, P.ldq, t, qA, qB);
 
   for (; cu.row < cu.row1; ++cu.row) {
     const int64_t row = cu.row;
@@ -489,8 +642,7 @@ k_attn_fwd_tile(const __grid_constant__ TileMaps tmA, const FwdArgs P) {
     // q of the next row
     float2 qA_n = qA, qB_n = qB;
     if (row + 1 < cu.row1) {
-      qA_n = *reinterpret_cast<const float2*>(P.q + (row + 1) * P.ldq + 2 * t);
-      qB_n = *reinterpret_cast<const float2*>(P.q + (row + 1) * P.ldq + 8 + 2 * t);
+      load_q<BF>(P.q, row + 1, P.ldq, t, qA_n, qB_n);
     }
     const float scale = fast::qk_scale_fast(P.scale_mode, P.scale_value, e - b);
     qA.x *= scale; qA.y *= scale; qB.x *= scale; qB.y *= scale;
@@ -511,15 +663,14 @@ k_attn_fwd_tile(const __grid_constant__ TileMaps tmA, const FwdArgs P) {
       for (int idx = 0; idx < 4; ++idx) {
         if (idx < 2 || two) {
           const unsigned tc = (unsigned)__shfl_sync(kFull, mycol, 8 * idx + g);
-          const char* kp = kbase + (uint64_t)tc * (uint64_t)ldkb;
-          kA[idx] = ldg_row8(kp, keep);
-          kB[idx] = ldg_row8(kp + 32, keep);
+          gather_k<BF>(kbase, tc, ldkb, keep, kA[idx], kB[idx]);
         } else {
           kA[idx] = make_float2(0.f, 0.f); kB[idx] = kA[idx];
         }
       }
       float acc[2][4][4];
-      rpe_tile(acc, tile, two, frag1, bias_s, lane);
+      if (BF) rpe_tile_bf16(acc, tile, two, reinterpret_cast<const uint2*>(frag1), bias_s, lane);
+      else rpe_tile(acc, tile, two, frag1, bias_s, lane);
 
       // logits (base 2) of my 4 edges x 2 heads
       float cA[4], cB[4];
@@ -545,7 +696,7 @@ k_attn_fwd_tile(const __grid_constant__ TileMaps tmA, const FwdArgs P) {
 #else
       const bool pre = false;
 #endif
-      if (pre) fwd_gather<8>(vpre, 0, mycol, vbase, ldvb, keep);
+      if (pre) fwd_gather<BF, 8>(vpre, 0, mycol, vbase, ldvb, keep);
       float tA = fmaxf(fmaxf(cA[0], cA[1]), fmaxf(cA[2], cA[3]));
       float tB = fmaxf(fmaxf(cB[0], cB[1]), fmaxf(cB[2], cB[3]));
 #pragma unroll
@@ -586,25 +737,25 @@ k_attn_fwd_tile(const __grid_constant__ TileMaps tmA, const FwdArgs P) {
       {
         int e0 = 0;
         if (pre) {
-          fwd_consume<8, true>(vpre, 0, pcol, tile, l7s, want_abar, accv01, accv23, acca01,
+          fwd_consume<BF, 8, true>(vpre, 0, pcol, tile, l7s, want_abar, accv01, accv23, acca01,
                                acca23);
           e0 = 8;
         }
         for (; e0 + 8 <= n; e0 += 8)
-          fwd_accumulate<8, true>(e0, mycol, vbase, ldvb, keep, pcol, tile, l7s, want_abar,
+          fwd_accumulate<BF, 8, true>(e0, mycol, vbase, ldvb, keep, pcol, tile, l7s, want_abar,
                                   accv01, accv23, acca01, acca23);
         if (n & 4) {
-          fwd_accumulate<4, false>(e0, mycol, vbase, ldvb, keep, pcol, tile, l7s, want_abar,
+          fwd_accumulate<BF, 4, false>(e0, mycol, vbase, ldvb, keep, pcol, tile, l7s, want_abar,
                                    accv01, accv23, acca01, acca23);
           e0 += 4;
         }
         if (n & 2) {
-          fwd_accumulate<2, false>(e0, mycol, vbase, ldvb, keep, pcol, tile, l7s, want_abar,
+          fwd_accumulate<BF, 2, false>(e0, mycol, vbase, ldvb, keep, pcol, tile, l7s, want_abar,
                                    accv01, accv23, acca01, acca23);
           e0 += 2;
         }
         if (n & 1)
-          fwd_accumulate<1, false>(e0, mycol, vbase, ldvb, keep, pcol, tile, l7s, want_abar,
+          fwd_accumulate<BF, 1, false>(e0, mycol, vbase, ldvb, keep, pcol, tile, l7s, want_abar,
                                    accv01, accv23, acca01, acca23);
       }
       mycol = cu.col_next;
@@ -649,9 +800,9 @@ k_attn_fwd_tile(const __grid_constant__ TileMaps tmA, const FwdArgs P) {
 
 // ------------------------------------------------------------------ backward rows
 struct BwdArgs {
-  const float* q; int ldq;
-  const float* k; int ldk;
-  const float* v; int ldv;
+  const void* q; int ldq;
+  const void* k; int ldk;
+  const void* v; int ldv;
   const int32_t* rowptr; const int32_t* col;
   int64_t num_rows;
   const float* Wq; const float* bq; const float* Wk; const float* bk;
@@ -666,8 +817,10 @@ struct BwdArgs {
   int rows_per_warp;
 };
 
+template <bool BF>
 __global__ void __launch_bounds__(kBwdWarps * 32, 2)
 k_attn_bwd_tile(const __grid_constant__ TileMaps tmA, const BwdArgs P) {
+  constexpr int kElt = BF ? 2 : 4;
   using L = BwdSmem;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -678,8 +831,13 @@ k_attn_bwd_tile(const __grid_constant__ TileMaps tmA, const BwdArgs P) {
   const float* bias_s = reinterpret_cast<const float*>(smem + L::bias_off);
   float* dp_s = reinterpret_cast<float*>(smem + L::p_off) + w * 32 * kH * 2;
 
-  build_frag1(reinterpret_cast<uint4*>(smem + L::frag_off), P.Wq, P.Wk);
-  build_frag2(reinterpret_cast<uint4*>(smem + L::frag_off + kFragBytes), P.Wq, P.Wk);
+  if (BF) {
+    build_frag1_bf16(reinterpret_cast<uint2*>(smem + L::frag_off), P.Wq, P.Wk);
+    build_frag2_bf16(reinterpret_cast<uint2*>(smem + L::frag_off + kFragBytes), P.Wq, P.Wk);
+  } else {
+    build_frag1(reinterpret_cast<uint4*>(smem + L::frag_off), P.Wq, P.Wk);
+    build_frag2(reinterpret_cast<uint4*>(smem + L::frag_off + kFragBytes), P.Wq, P.Wk);
+  }
   build_bias(reinterpret_cast<float*>(smem + L::bias_off), P.Wq, P.bq, P.Wk, P.bk);
   __syncthreads();
 
@@ -692,6 +850,7 @@ k_attn_bwd_tile(const __grid_constant__ TileMaps tmA, const BwdArgs P) {
   pipe.bar = reinterpret_cast<uint64_t*>(smem + L::bar_off) + w * 2;
   pipe.tm = &tmA;
   pipe.policy = policy_evict_first();
+  pipe.box_bytes = BF ? 512u : 1024u;
   pipe.lane = lane;
   pipe.init();
   const uint64_t keep = policy_evict_last();
@@ -709,24 +868,23 @@ k_attn_bwd_tile(const __grid_constant__ TileMaps tmA, const BwdArgs P) {
   const bool want_da = P.da != nullptr;
   const int hb = lane >> 3;
   const int j8 = lane & 7;
-  const char* kbase = reinterpret_cast<const char*>(P.k + 2 * t);
-  const char* vbase = reinterpret_cast<const char*>(P.v + 4 * lane);
-  const unsigned ldkb = (unsigned)P.ldk * 4u, ldvb = (unsigned)P.ldv * 4u;   // row strides, bytes
+  const char* kbase = reinterpret_cast<const char*>(P.k) + 2 * t * kElt;
+  const char* vbase = reinterpret_cast<const char*>(P.v) + 4 * lane * kElt;
+  const unsigned ldkb = (unsigned)P.ldk * kElt, ldvb = (unsigned)P.ldv * kElt;   // row strides, bytes
   const int hA = t >> 1, hB = 2 + (t >> 1);
   const int hsl = (t & 1) * 2 + (t >> 1);   // head fed through k-slot t of the P . dAbar step
   const uint32_t l7s = (uint32_t)((lane & 7) << 4);
 
   int mycol = (lane < min(32, cu.e - cu.b)) ? P.col[cu.b + lane] : 0;
-  float2 qA = *reinterpret_cast<const float2*>(P.q + row0 * P.ldq + 2 * t);
-  float2 qB = *reinterpret_cast<const float2*>(P.q + row0 * P.ldq + 8 + 2 * t);
+  float2 qA, qB;
+  load_q<BF>(P.q, row0, P.ldq, t, qA, qB);
 
   for (; cu.row < cu.row1; ++cu.row) {
     const int64_t row = cu.row;
     const int b = cu.b, e = cu.e;
     float2 qA_n = qA, qB_n = qB;
     if (row + 1 < cu.row1) {
-      qA_n = *reinterpret_cast<const float2*>(P.q + (row + 1) * P.ldq + 2 * t);
-      qB_n = *reinterpret_cast<const float2*>(P.q + (row + 1) * P.ldq + 8 + 2 * t);
+      load_q<BF>(P.q, row + 1, P.ldq, t, qA_n, qB_n);
     }
     const float scale = fast::qk_scale_fast(P.scale_mode, P.scale_value, e - b);
     qA.x *= scale; qA.y *= scale; qB.x *= scale; qB.y *= scale;
@@ -755,8 +913,17 @@ k_attn_bwd_tile(const __grid_constant__ TileMaps tmA, const BwdArgs P) {
     uint32_t dbhi[4], dblo[4];
 #pragma unroll
     for (int nf = 0; nf < 4; ++nf) {
-      const float x = has_dab ? P.d_abar[row * (kH * kF) + hsl * kF + 8 * nf + g] : 0.f;
-      split_tf32(__float_as_uint(x), dbhi[nf], dblo[nf]);
+      if (BF) {
+        // bf16 k-step of 16 slots: slots (2t, 2t+1) of the even lanes t = 0 / 2 carry heads
+        // (0, 2) / (1, 3) — the pair a lane already holds; odd lanes and slots 8..15 are zero
+        const float x0 = has_dab ? P.d_abar[row * (kH * kF) + hA * kF + 8 * nf + g] : 0.f;
+        const float x1 = has_dab ? P.d_abar[row * (kH * kF) + hB * kF + 8 * nf + g] : 0.f;
+        dbhi[nf] = (t & 1) ? 0u : f2_to_bf2(x0, x1);
+        dblo[nf] = 0u;
+      } else {
+        const float x = has_dab ? P.d_abar[row * (kH * kF) + hsl * kF + 8 * nf + g] : 0.f;
+        split_tf32(__float_as_uint(x), dbhi[nf], dblo[nf]);
+      }
     }
     float dqacc[4] = {0.f, 0.f, 0.f, 0.f};   // dq[8nn + 2t + j], nn = 0,1
 
@@ -773,15 +940,14 @@ k_attn_bwd_tile(const __grid_constant__ TileMaps tmA, const BwdArgs P) {
       for (int idx = 0; idx < 4; ++idx) {
         if (idx < 2 || two) {
           const unsigned tc = (unsigned)__shfl_sync(kFull, mycol, 8 * idx + g);
-          const char* kp = kbase + (uint64_t)tc * (uint64_t)ldkb;
-          kA[idx] = ldg_row8(kp, keep);
-          kB[idx] = ldg_row8(kp + 32, keep);
+          gather_k<BF>(kbase, tc, ldkb, keep, kA[idx], kB[idx]);
         } else {
           kA[idx] = make_float2(0.f, 0.f); kB[idx] = kA[idx];
         }
       }
       float acc[2][4][4];
-      rpe_tile(acc, tile, two, frag1, bias_s, lane);
+      if (BF) rpe_tile_bf16(acc, tile, two, reinterpret_cast<const uint2*>(frag1), bias_s, lane);
+      else rpe_tile(acc, tile, two, frag1, bias_s, lane);
 
       // q_e, k_e in place (acc[m][0/1] = q_e heads A/B, acc[m][2/3] = k_e), p of my edges
       float pA[4], pB[4];
@@ -814,25 +980,25 @@ k_attn_bwd_tile(const __grid_constant__ TileMaps tmA, const BwdArgs P) {
         for (int u = 0; u < 8; ++u) s[u] = 0.f;
         const int cnt = n - e0;              // edges of this group (the last one may be short)
         if (cnt >= 8) {
-          bwd_partials<8, true>(s, e0, mycol, vbase, ldvb, keep, tile, l7s, has_dab, dy01, dy23,
+          bwd_partials<BF, 8, true>(s, e0, mycol, vbase, ldvb, keep, tile, l7s, has_dab, dy01, dy23,
                                 dab01, dab23);
         } else {
           float s4[8], s2[8], s1[8];
           int o = 0;
           if (cnt & 4) {
-            bwd_partials<4, true>(s4, e0, mycol, vbase, ldvb, keep, tile, l7s, has_dab, dy01,
+            bwd_partials<BF, 4, true>(s4, e0, mycol, vbase, ldvb, keep, tile, l7s, has_dab, dy01,
                                   dy23, dab01, dab23);
             s[0] = s4[0]; s[1] = s4[1]; s[2] = s4[2]; s[3] = s4[3];
             o = 4;
           }
           if (cnt & 2) {
-            bwd_partials<2, false>(s2, e0 + o, mycol, vbase, ldvb, keep, tile, l7s, has_dab, dy01,
+            bwd_partials<BF, 2, false>(s2, e0 + o, mycol, vbase, ldvb, keep, tile, l7s, has_dab, dy01,
                                    dy23, dab01, dab23);
             if (o) { s[4] = s2[0]; s[5] = s2[1]; } else { s[0] = s2[0]; s[1] = s2[1]; }
             o += 2;
           }
           if (cnt & 1) {
-            bwd_partials<1, false>(s1, e0 + o, mycol, vbase, ldvb, keep, tile, l7s, has_dab, dy01,
+            bwd_partials<BF, 1, false>(s1, e0 + o, mycol, vbase, ldvb, keep, tile, l7s, has_dab, dy01,
                                    dy23, dab01, dab23);
             // o in {0, 2, 4, 6}
             if (o == 0) s[0] = s1[0]; else if (o == 2) s[2] = s1[0];
@@ -898,6 +1064,41 @@ k_attn_bwd_tile(const __grid_constant__ TileMaps tmA, const BwdArgs P) {
           for (int nf = 0; nf < 4; ++nf)
 #pragma unroll
             for (int i = 0; i < 4; ++i) dacc[m][nf][i] = 0.f;
+        if (BF) {
+          if (has_dab) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+              if (m == 0 || two) {
+                uint32_t a[4];
+                a[0] = (t & 1) ? 0u : f2_to_bf2(pA[2 * m], pB[2 * m]);
+                a[1] = (t & 1) ? 0u : f2_to_bf2(pA[2 * m + 1], pB[2 * m + 1]);
+                a[2] = a[3] = 0u;
+#pragma unroll
+                for (int nf = 0; nf < 4; ++nf) mma_bf16(dacc[m][nf], a, dbhi[nf], 0u);
+              }
+            }
+          }
+          const uint2* frag2b = reinterpret_cast<const uint2*>(frag2);
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            uint2 bfr[4];
+#pragma unroll
+            for (int nf = 0; nf < 4; ++nf) bfr[nf] = frag2b[(ks * 4 + nf) * 32 + lane];
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+              if (m == 0 || two) {
+                // the accumulator fragments of n-tiles 2ks, 2ks+1 ARE the A fragment (k = output)
+                uint32_t a[4];
+                a[0] = f2_to_bf2(acc[m][2 * ks][0], acc[m][2 * ks][1]);
+                a[1] = f2_to_bf2(acc[m][2 * ks][2], acc[m][2 * ks][3]);
+                a[2] = f2_to_bf2(acc[m][2 * ks + 1][0], acc[m][2 * ks + 1][1]);
+                a[3] = f2_to_bf2(acc[m][2 * ks + 1][2], acc[m][2 * ks + 1][3]);
+#pragma unroll
+                for (int nf = 0; nf < 4; ++nf) mma_bf16(dacc[m][nf], a, bfr[nf].x, bfr[nf].y);
+              }
+            }
+          }
+        } else {
         if (has_dab) {
 #pragma unroll
           for (int m = 0; m < 2; ++m) {
@@ -933,6 +1134,7 @@ k_attn_bwd_tile(const __grid_constant__ TileMaps tmA, const BwdArgs P) {
               for (int nf = 0; nf < 4; ++nf) mma_3x(dacc[m][nf], ahi, alo, bfr[nf]);
             }
           }
+        }
         }
 #pragma unroll
         for (int idx = 0; idx < 4; ++idx) {

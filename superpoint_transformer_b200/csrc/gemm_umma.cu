@@ -671,6 +671,19 @@ static bool make_map(CUtensorMap* tm, const float* ptr, int64_t rows, int64_t co
 bool make_map_rows32(CUtensorMap* tm, const float* ptr, int64_t rows, int64_t ld, int box_rows) {
   return make_map(tm, ptr, rows, 32, ld, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
 }
+// the same for a bf16 [rows, 32] matrix (64-byte rows, SWIZZLE_64B)
+bool make_map_rows32_bf16(CUtensorMap* tm, const void* ptr, int64_t rows, int box_rows) {
+  EncodeTiledFn enc = encoder();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {32u, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {64u};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
+         CUDA_SUCCESS;
+}
 
 // layout the tensor-core path needs; otherwise the caller uses the mma.sync kernel
 bool shape_ok(const float* A, int64_t M, int64_t K, int64_t lda, const float* B, int64_t N,

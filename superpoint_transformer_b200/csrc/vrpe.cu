@@ -78,6 +78,24 @@ __global__ void k_vrpe_dweight(const float* __restrict__ dWbd, int H, int Dv, in
   }
 }
 
+// fp32 -> bf16 (round to nearest even), 2 elements per thread
+__global__ void k_cast_bf16(const float* __restrict__ x, int64_t n2, int64_t n,
+                            uint32_t* __restrict__ out2, uint16_t* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n2; i += stride) {
+    const float2 v = reinterpret_cast<const float2*>(x)[i];
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(v.y), "f"(v.x));
+    out2[i] = r;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && (n & 1)) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(0.f), "f"(x[n - 1]));
+    out[n - 1] = (uint16_t)(r & 0xffffu);
+  }
+}
+
 }  // namespace spt
 
 using namespace spt;
@@ -128,6 +146,20 @@ int spt_vrpe_bwd_params(const float* dy, const float* sump, const float* dWbd, i
                                                                    dWv);
   }
   return check_launch("vrpe_bwd_params");
+}
+
+int spt_cast_bf16(const float* x, int64_t n, uint16_t* out, void* stream_) {
+  SPT_REQUIRE(n >= 0, SPT_E_INVALID, "cast_bf16: negative size");
+  if (n == 0) return SPT_OK;
+  SPT_REQUIRE(x && out, SPT_E_INVALID, "cast_bf16: null pointer");
+  SPT_REQUIRE(((uintptr_t)x & 7) == 0 && ((uintptr_t)out & 3) == 0, SPT_E_INVALID,
+              "cast_bf16: x must be 8-byte and out 4-byte aligned");
+  const int64_t n2 = n >> 1;
+  int64_t blocks = ceil_div(n2 > 0 ? n2 : 1, 256);
+  if (blocks > device_sm_count() * 16) blocks = device_sm_count() * 16;
+  k_cast_bf16<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(
+      x, n2, n, reinterpret_cast<uint32_t*>(out), out);
+  return check_launch("cast_bf16");
 }
 
 }  // extern "C"

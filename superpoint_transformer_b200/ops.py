@@ -296,7 +296,7 @@ _permuted_cache = _IdentityCache()
 
 
 def clear_caches():
-    for c in (_graph_cache, _segment_cache, _numseg_cache, _permuted_cache):
+    for c in (_graph_cache, _segment_cache, _numseg_cache, _permuted_cache, _bf16_cache):
         c.clear()
 
 
@@ -1011,6 +1011,128 @@ class _AttnCore(torch.autograd.Function):
                 d_qr, d_qt, d_kr, None)
 
 
+# ---------------------------------------------------------------------------
+# bf16 storage of the attention operands (BASELINE cfg 3)
+# ---------------------------------------------------------------------------
+ATTN_STORAGE = 'fp32'
+_bf16_cache = _IdentityCache()
+
+
+def set_attention_storage(mode):
+    """'fp32' (default) or 'bf16': in bf16 mode SelfAttentionBlock stores the fused projections
+    qkv and the CSR-ordered edge features as bf16 in HBM for the attention kernels (fp32
+    accumulation, fp32 outputs and gradients) whenever the shape is the row-tile family
+    (H=4, D=4, Dv=32, F=32, k and q RPE); other shapes keep the fp32 kernels."""
+    global ATTN_STORAGE
+    if mode not in ('fp32', 'bf16'):
+        raise ValueError(mode)
+    ATTN_STORAGE = mode
+
+
+def cast_bf16(x):
+    """fp32 -> bf16 copy (round to nearest even) as a torch.bfloat16 tensor; no gradient."""
+    lib = _lib.load()
+    x = _f32c(x.detach())
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.spt_cast_bf16(_p(x), x.numel(), _p(out), _stream()), "spt_cast_bf16")
+    _count()
+    return out
+
+
+class _AttnCoreBf16(torch.autograd.Function):
+    """_AttnCore with q / k / v / edge features stored as bf16 (see spt_attn_fwd_bf16)."""
+
+    @staticmethod
+    def forward(ctx, qkv, a, Wq, bq, Wk, bk, g, H, D, scale_mode, scale_value, want_abar):
+        lib = _lib.load()
+        dev = qkv.device
+        HD = H * D
+        ld = qkv.shape[1]
+        C = ld - 2 * HD
+        Dv, F, R = C // H, a.shape[1], g.num_rows
+        qb = cast_bf16(qkv)
+        # the blocks of a stage share the edge features: one bf16 copy per tensor
+        ab = _bf16_cache.get(a, "bf16", lambda: cast_bf16(a))
+        agg = torch.empty((R, C), dtype=torch.float32, device=dev)
+        abar = torch.empty((R, H, F), dtype=torch.float32, device=dev) if want_abar else None
+        sump = torch.empty((R, H), dtype=torch.float32, device=dev)
+        m = torch.empty((R, H), dtype=torch.float32, device=dev)
+        z = torch.empty((R, H), dtype=torch.float32, device=dev)
+        base = qb.data_ptr()
+        with torch.cuda.device(dev), _timed('attn_fwd', R=R, E=g.E, H=H, D=D, Dv=Dv, F=F,
+                                            abar=abar is not None, bf16=True):
+            _lib.check(lib.spt_attn_fwd_bf16(base, ld, base + 2 * HD, ld, base + 4 * HD, ld,
+                                             _p(ab), _p(g.rowptr), _p(g.col), R, g.E, H, D, Dv, F,
+                                             _p(Wq), _p(bq), _p(Wk), _p(bk), scale_mode,
+                                             scale_value, _p(agg), _p(abar), _p(sump), _p(m),
+                                             _p(z), _stream()), "spt_attn_fwd_bf16")
+        _count()
+        ctx.g, ctx.H, ctx.D, ctx.Dv, ctx.F = g, H, D, Dv, F
+        ctx.scale_mode, ctx.scale_value = scale_mode, scale_value
+        ctx.has_abar = abar is not None
+        ctx.save_for_backward(qb, ab, a, Wq, bq, Wk, bk, m, z, agg,
+                              abar if abar is not None else m)
+        ctx.mark_non_differentiable(sump)
+        return agg, abar, sump
+
+    @staticmethod
+    def backward(ctx, d_agg, d_abar, _d_sump):
+        lib = _lib.load()
+        qb, ab, a, Wq, bq, Wk, bk, m, z, agg, abar = ctx.saved_tensors
+        abar = abar if ctx.has_abar else None
+        g, H, D, Dv, F = ctx.g, ctx.H, ctx.D, ctx.Dv, ctx.F
+        HD = H * D
+        dev = qb.device
+        ld = qb.shape[1]
+        d_agg = _f32c(d_agg) if d_agg is not None else torch.zeros_like(agg)
+        d_abar = _f32c(d_abar) if (d_abar is not None and abar is not None) else None
+        dqkv = torch.empty(qb.shape, dtype=torch.float32, device=dev)
+        da = torch.empty(a.shape, dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] \
+            else None
+        E = g.E
+        Pb = torch.empty((max(E, 1), H), dtype=torch.float32, device=dev)
+        G = torch.empty((max(E, 1), 2 * HD), dtype=torch.float32, device=dev)
+        dW2 = zero_pool.take((2 * HD, F), dev)
+        db2 = zero_pool.take((2 * HD,), dev)
+        base = qb.data_ptr()
+        dq_p = dqkv.data_ptr()
+        meta = dict(R=g.num_rows, T=g.num_targets, E=E, H=H, D=D, Dv=Dv, F=F,
+                    abar=abar is not None, da=da is not None, bf16=True)
+        with torch.cuda.device(dev):
+            with _timed('attn_bwd_rows', **meta):
+                _lib.check(lib.spt_attn_bwd_rows_bf16(
+                    base, ld, base + 2 * HD, ld, base + 4 * HD, ld, _p(ab), _p(g.rowptr),
+                    _p(g.col), g.num_rows, E, H, D, Dv, F, _p(Wq), _p(bq), _p(Wk), _p(bk),
+                    ctx.scale_mode, ctx.scale_value, _p(m), _p(z), _p(agg), _p(abar), _p(d_agg),
+                    _p(d_abar), dq_p, ld, _p(da), _p(Pb), _p(G), _stream()),
+                    "spt_attn_bwd_rows_bf16")
+                # d[Wq;Wk] = G^T a, d[bq;bk] = colsum(G): tcgen05 gemm_tn on the fp32 features
+                if E > 0:
+                    _lib.check(lib.spt_gemm_tn_acc(_p(G), E, 2 * HD, 2 * HD, _p(a), F, F,
+                                                   _p(dW2), F, _p(db2), _stream()),
+                               "spt_gemm_tn_acc")
+            with _timed('attn_bwd_targets', **meta):
+                _lib.check(lib.spt_attn_bwd_targets(
+                    _p(g.csc_ptr), _p(g.csc_src), _p(g.csc2csr), g.num_targets, E, H, D, Dv,
+                    _p(Pb), _p(G), _p(d_agg), dq_p + 4 * HD, ld, dq_p + 8 * HD, ld, _stream()),
+                    "spt_attn_bwd_targets")
+            _count(3)
+        return (dqkv, da, dW2[:HD], db2[:HD], dW2[HD:], db2[HD:], None, None, None, None, None,
+                None)
+
+
+def _bf16_ok(qsrc, kv, a, Wq, bq, Wk, bk, H, D, extras):
+    if ATTN_STORAGE != 'bf16' or kv is not None or a is None or extras:
+        return False
+    if Wq is None or Wk is None or bq is None or bk is None:
+        return False
+    C = qsrc.shape[1] - 2 * H * D
+    return (H == 4 and D == 4 and C == 128 and a.shape[1] == 32 and qsrc.shape[1] % 4 == 0
+            and tuple(Wq.shape) == (16, 32) and tuple(Wk.shape) == (16, 32)
+            and a.shape[0] > 0)
+
+
 def attention_core(qsrc, kv, a_csr, Wq, bq, Wk, bk, graph, num_heads, qk_dim,
                    scale_mode=SCALE_D_TIMES_G, scale_value=1.0, want_abar=True,
                    q_row_add=None, q_tgt_add=None, k_row_add=None, drop_mask=None):
@@ -1018,6 +1140,11 @@ def attention_core(qsrc, kv, a_csr, Wq, bq, Wk, bk, graph, num_heads, qk_dim,
     CSR order (permute_rows(edge_attr, graph.perm)).  The optional addends / mask are the
     `spt_attn_extras` (node-difference RPE, attention dropout)."""
     _require_cuda(qsrc, kv, a_csr, Wq, bq, Wk, bk, q_row_add, q_tgt_add, k_row_add, drop_mask)
+    extras = any(t is not None for t in (q_row_add, q_tgt_add, k_row_add, drop_mask))
+    if _bf16_ok(qsrc, kv, a_csr, Wq, bq, Wk, bk, int(num_heads), int(qk_dim), extras):
+        return _AttnCoreBf16.apply(_f32c(qsrc), _f32c(a_csr), _f32c(Wq), _f32c(bq), _f32c(Wk),
+                                   _f32c(bk), graph, int(num_heads), int(qk_dim),
+                                   int(scale_mode), float(scale_value), bool(want_abar))
     return _AttnCore.apply(_f32c(qsrc), _f32c(kv), _f32c(a_csr), _f32c(Wq), _f32c(bq),
                            _f32c(Wk), _f32c(bk), graph, int(num_heads), int(qk_dim),
                            int(scale_mode), float(scale_value), bool(want_abar),

@@ -31,6 +31,7 @@ qkv = torch.randn(N, 2 * H * D + C, generator=g).to(dev).requires_grad_(True)
 a = torch.randn(E, F, generator=g).to(dev).requires_grad_(True)
 mk = lambda *s: (torch.randn(*s, generator=g) * 0.2).to(dev).requires_grad_(True)  # noqa: E731
 Wq, bq, Wk, bk = mk(16, 32), mk(16), mk(16, 32), mk(16)
+ops.set_attention_storage(os.environ.get('SPT_ATTN_STORAGE', 'fp32'))
 ops.enable_event_timing(True)
 for it in range(ITERS):
     agg, abar, sump = ops.attention_core(qkv, None, a, Wq, bq, Wk, bk, gi, H, D,
@@ -40,6 +41,6 @@ torch.cuda.synchronize()
 acc = {}
 for tag, meta, s, e in ops.timing_records():
     acc.setdefault(tag, []).append(s.elapsed_time(e))
-print(f'N={N} E={E} sorted={MORTON}')
+print(f'N={N} E={E} sorted={MORTON} storage={ops.ATTN_STORAGE}')
 for k, v in acc.items():
     print(f'  {k}: min {min(v):.4f} ms  last {v[-1]:.4f} ms')
