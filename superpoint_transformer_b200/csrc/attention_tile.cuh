@@ -7,9 +7,10 @@
 // consecutive CSR rows; one row = one tile of <= 32 CSR slots (longer rows take
 // several tiles, merged with an online softmax):
 //
-//   A  edge features a[slots, 0:32] of the warp's slab stream HBM -> shared memory
-//      through a warp-private ring of 2-D TMA boxes (8 rows x 128 B, SWIZZLE_128B,
-//      completion on mbarriers) — read exactly once, independent of the row structure;
+//   A  the tile's edge features a[tb : tb+n, 0:32] arrive as ONE 2-D TMA copy (four tensor
+//      maps with boxes of 8 / 16 / 24 / 32 rows, SWIZZLE_128B, L2 evict-first) at the start
+//      of a warp-private 4 KB stage; two stages per warp, the next row's tile is in flight
+//      while the current one is consumed (struct TilePipe);
 //   B  the RPE product of the whole tile, R[32 x 32] = A_tile [32 x 32] . [Wq;Wk]^T, runs on
 //      the tensor cores: mma.sync m16n8k8 TF32 with the 3xTF32 split (fp32-accurate),
 //      A fragments by ldmatrix from the swizzled tile (conflict-free), weight fragments
@@ -17,15 +18,20 @@
 //   C  in the accumulator fragment a thread holds r_q[h,d] and r_k[h,d] of the same
 //      (edge, head, d in {2t,2t+1}): head logit = 2 FMAs + one shfl.xor(1);
 //      two-pass softmax over the tile in registers (3 shfl.xor over the row lanes);
-//   D  p goes through a [32 x 4] shared-memory tile to the accumulation layout
-//      (lane = 4 value channels + 4 abar entries): per edge one LDG.128 of the gathered
-//      v row, one LDS.128 of the staged a row and 4 packed FMAs, 8 edges in flight.
+//   D  p goes through a [32 x 4] shared-memory tile of (p, p) pairs to the accumulation
+//      layout (lane = 4 value channels + 4 abar entries): per edge one LDG.128 of the gathered
+//      v row (L2 evict-last, 8 in flight, no predicates: n = 8 + ... + 4 + 2 + 1), one LDS.64
+//      of (p, p), one LDS.128 of the staged feature row and 4 packed FMAs.
 //
 // The backward rows kernel has the same front end, recomputes p from the saved (m, z),
 // evaluates dp = <dY, v> + <dAbar, a> with a butterfly transpose-reduce (7 shuffles per 8
 // edges), forms G = [dq_e | dk_e] directly in the accumulator fragment, and feeds that
 // fragment — with a permuted k order, no shuffles — as the A operand of the second
 // tensor-core product da = G . [Wq;Wk] + P . dAbar.
+//
+// template <bool BF>: BF = true reads q / k / v / the features as bf16 (cfg 3): 64-byte feature
+// rows (SWIZZLE_64B), single bf16 m16n8k16 MMAs with fp32 accumulation instead of the 3xTF32
+// triple; the accumulator layout — and with it everything after the products — is shared.
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
