@@ -70,6 +70,8 @@ def run(N, seed, hub, want_abar, use_q, use_k, env):
 def main():
     cases = [(403, 3, True, True, True, True), (3001, 4, False, True, True, True),
              (3001, 5, True, False, False, True), (20000, 6, False, True, True, True)]
+    if os.environ.get('SMALL'):      # compute-sanitizer runs
+        cases = cases[:2]
     worst = 0.0
     for N, seed, hub, want_abar, use_q, use_k in cases:
         ref = run(N, seed, hub, want_abar, use_q, use_k,
