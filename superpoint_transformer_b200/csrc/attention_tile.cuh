@@ -422,7 +422,7 @@ __device__ __forceinline__ ulonglong2 lds_a_chunk(uint32_t tile, int e0, int u, 
   }
   uint32_t ad;
   if (ALIGNED) {   // e0 % 8 == 0: (e0 + u) & 7 == u, a compile-time constant
-    ad = tile + (uint32_t)(e0 * 128) + (uint32_t)(u * 128) + (l7s ^ (uint32_t)(u << 4));
+    ad = tile + (uint32_t)(e0 * 128) + (uint32_t)(u * 128) + (l7s ^ (uint32_t)((u & 7) << 4));
   } else {
     const uint32_t r = (uint32_t)(e0 + u);
     ad = tile + r * 128u + (l7s ^ ((r & 7u) << 4));
@@ -513,8 +513,8 @@ __device__ __forceinline__ void fwd_accumulate(int e0, int mycol, const char* vb
 }
 
 // backward: dp = <dY, v> + <dAbar, a> partial sums of CNT (<= 8) edges -> s[0..CNT)
-template <bool BF, int CNT, bool ALIGNED>
-__device__ __forceinline__ void bwd_partials(float (&s)[8], int e0, int mycol, const char* vbase,
+template <bool BF, int CNT, bool ALIGNED, int SN = 8>
+__device__ __forceinline__ void bwd_partials(float (&s)[SN], int e0, int mycol, const char* vbase,
                                              unsigned ldvb, uint64_t keep, uint32_t tile,
                                              uint32_t l7s, bool has_dab, f32x2 dy01, f32x2 dy23,
                                              f32x2 dab01, f32x2 dab23) {
@@ -747,6 +747,13 @@ k_attn_fwd_tile(const __grid_constant__ TileMaps tmA, const FwdArgs P) {
                                acca23);
           e0 = 8;
         }
+#ifdef SPT_FWD_GATHER16
+        // 16 gathered rows in flight for the rows that have them (the accumulator fragments
+        // are dead here, so the registers exist)
+        for (; e0 + 16 <= n; e0 += 16)
+          fwd_accumulate<BF, 16, true>(e0, mycol, vbase, ldvb, keep, pcol, tile, l7s, want_abar,
+                                       accv01, accv23, acca01, acca23);
+#endif
         for (; e0 + 8 <= n; e0 += 8)
           fwd_accumulate<BF, 8, true>(e0, mycol, vbase, ldvb, keep, pcol, tile, l7s, want_abar,
                                   accv01, accv23, acca01, acca23);
@@ -802,6 +809,27 @@ k_attn_fwd_tile(const __grid_constant__ TileMaps tmA, const FwdArgs P) {
     if (row + 2 < cu.row1) cu.e_next = P.rowptr[row + 3];
     qA = qA_n; qB = qB_n;
   }
+}
+
+// transpose-reduce of 8 per-edge partial sums over the 8 lanes of a head (7 shuffles): lane j8
+// ends up with the full sum of edge j8
+__device__ __forceinline__ float butterfly8(const float* s, int j8) {
+  float r4[4], r2[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = (j8 & 4) ? s[i] : s[i + 4];
+    const float keep = (j8 & 4) ? s[i + 4] : s[i];
+    r4[i] = keep + __shfl_xor_sync(kFull, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = (j8 & 2) ? r4[i] : r4[i + 2];
+    const float keep = (j8 & 2) ? r4[i + 2] : r4[i];
+    r2[i] = keep + __shfl_xor_sync(kFull, send, 2);
+  }
+  const float send = (j8 & 1) ? r2[0] : r2[1];
+  const float keep = (j8 & 1) ? r2[1] : r2[0];
+  return keep + __shfl_xor_sync(kFull, send, 1);
 }
 
 // ------------------------------------------------------------------ backward rows
@@ -981,10 +1009,21 @@ k_attn_bwd_tile(const __grid_constant__ TileMaps tmA, const BwdArgs P) {
 
       // dp - delta of every (edge, head): accumulation layout, 8 edges per butterfly
       for (int e0 = 0; e0 < n; e0 += 8) {
+        const int cnt = n - e0;              // edges of this group (the last one may be short)
+#ifdef SPT_BWD_GATHER16
+        if (cnt >= 16) {   // 16 gathered rows in flight, two butterflies
+          float s16[16];
+          bwd_partials<BF, 16, true, 16>(s16, e0, mycol, vbase, ldvb, keep, tile, l7s, has_dab,
+                                         dy01, dy23, dab01, dab23);
+          dp_s[(e0 + j8) * kH + hb] = butterfly8(s16, j8) - delta;
+          dp_s[(e0 + 8 + j8) * kH + hb] = butterfly8(s16 + 8, j8) - delta;
+          e0 += 8;
+          continue;
+        }
+#endif
         float s[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) s[u] = 0.f;
-        const int cnt = n - e0;              // edges of this group (the last one may be short)
         if (cnt >= 8) {
           bwd_partials<BF, 8, true>(s, e0, mycol, vbase, ldvb, keep, tile, l7s, has_dab, dy01, dy23,
                                 dab01, dab23);
@@ -1012,22 +1051,7 @@ k_attn_bwd_tile(const __grid_constant__ TileMaps tmA, const BwdArgs P) {
           }
         }
         // transpose-reduce over the 8 lanes of a head: lane j8 ends with edge e0 + j8
-        float r4[4], r2[2];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float send = (j8 & 4) ? s[i] : s[i + 4];
-          const float keep = (j8 & 4) ? s[i + 4] : s[i];
-          r4[i] = keep + __shfl_xor_sync(kFull, send, 4);
-        }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const float send = (j8 & 2) ? r4[i] : r4[i + 2];
-          const float keep = (j8 & 2) ? r4[i + 2] : r4[i];
-          r2[i] = keep + __shfl_xor_sync(kFull, send, 2);
-        }
-        const float send = (j8 & 1) ? r2[0] : r2[1];
-        const float keep = (j8 & 1) ? r2[1] : r2[0];
-        const float dp = keep + __shfl_xor_sync(kFull, send, 1);
+        const float dp = butterfly8(s, j8);
         dp_s[(e0 + j8) * kH + hb] = dp - delta;
       }
       __syncwarp();
