@@ -38,9 +38,21 @@ for it in range(ITERS):
                                          ops.SCALE_D_TIMES_G, 32 ** -0.5)
     (agg.sum() + abar.sum()).backward()
 torch.cuda.synchronize()
+# bare gather ceiling: out[row] = sum_e v[col[e]] (the 512-byte rows the forward gathers, nothing
+# else) with the CSR segment-sum kernel — 64 resident warps/SM, 2 rows in flight per warp
+seg = ops.SegmentIndex(gi.rowptr, gi.col, None, E, N, None)
+vmat = qkv.detach()[:, 2 * H * D:].contiguous()
+for it in range(ITERS):
+    ops._segment_pool_fwd(vmat, seg, 'sum')
+torch.cuda.synchronize()
 acc = {}
 for tag, meta, s, e in ops.timing_records():
     acc.setdefault(tag, []).append(s.elapsed_time(e))
 print(f'N={N} E={E} sorted={MORTON} storage={ops.ATTN_STORAGE}')
 for k, v in acc.items():
     print(f'  {k}: min {min(v):.4f} ms  last {v[-1]:.4f} ms')
+if 'segment_pool_fwd' in acc:
+    t = min(acc['segment_pool_fwd'])
+    gb = (E * 512 + N * 512 + E * 4) / 1e9
+    print(f'  bare gather of the v rows (segment-sum by col): {t:.4f} ms = {gb / t * 1e3:.0f} GB/s '
+          f'of gathered + written bytes')
