@@ -90,6 +90,11 @@ int spt_invert_permutation(const int32_t* perm, int64_t n, int32_t* inv,
 int spt_gather_i32(const int32_t* src, const int32_t* idx, int64_t n,
                    int32_t* out, void* stream);
 
+/* out[j] = g for ptr[g] <= j < ptr[g+1]  (the row of every CSR slot; `out` has ptr[num_groups]
+ * entries).  Input of the edge-parallel attention kernels (spt_attn_extras.edge_row).       */
+int spt_expand_pointers_i32(const int32_t* ptr, int64_t num_groups, int32_t* out,
+                            void* stream);
+
 /* Segment sum of int64 values (values==NULL -> ones), segments given by
  * ptr/points (points==NULL -> identity).  `NAG.get_sub_size`
  * (src/data/nag.py:59-110), used by `NodeSize` (src/transforms/graph.py:1475-1498). */
@@ -322,6 +327,14 @@ typedef struct spt_attn_extras {
    * the caller's v-RPE bias multiplies sump) and the forward's sump */
   const float* d_sump;    /* [R, H] */
   const float* sump;      /* [R, H] */
+  /* Workspace of the split kernels (csrc/attention_split.cuh: one edge-parallel pass on the
+   * tensor cores + one row-parallel pass, 16 bytes per edge between them).  With ws_logits and
+   * edge_row set (and none of the optional terms above) the forward takes that path and leaves
+   * the base-2 logits in ws_logits; the backward reads them back and needs ws_ds as well.
+   * NULL = the fused row-tile kernels. */
+  float* ws_logits;        /* [E, H] */
+  const int32_t* edge_row; /* [E] CSR row of every slot (spt_expand_pointers_i32) */
+  float* ws_ds;            /* [E, H] backward only */
 } spt_attn_extras;
 
 int spt_attn_fwd_ex(const float* q, int64_t ldq, const float* k, int64_t ldk,

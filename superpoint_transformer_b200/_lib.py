@@ -29,6 +29,7 @@ SIGNATURES = {
                                 c_ptr, c_size, c_ptr]),
     "spt_invert_permutation": (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
     "spt_gather_i32": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
+    "spt_expand_pointers_i32": (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
     "spt_segment_sum_i64": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
     "spt_gather_rows_i64": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
     "spt_gather_rows_i32": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
@@ -119,7 +120,9 @@ class AttnExtras(ctypes.Structure):
     _fields_ = [("q_row_add", ctypes.c_void_p), ("q_tgt_add", ctypes.c_void_p),
                 ("k_row_add", ctypes.c_void_p), ("drop_mask", ctypes.c_void_p),
                 ("d_q_row_add", ctypes.c_void_p), ("d_k_row_add", ctypes.c_void_p),
-                ("d_sump", ctypes.c_void_p), ("sump", ctypes.c_void_p)]
+                ("d_sump", ctypes.c_void_p), ("sump", ctypes.c_void_p),
+                ("ws_logits", ctypes.c_void_p), ("edge_row", ctypes.c_void_p),
+                ("ws_ds", ctypes.c_void_p)]
 
 
 def library_path():

@@ -20,6 +20,8 @@
 #include "common.cuh"
 #include "attention_fast.cuh"
 #include "attention_tile.cuh"
+#include "attention_split.cuh"
+#include "attention_umma.cuh"
 #include <stdlib.h>
 
 namespace spt {
@@ -574,6 +576,18 @@ static bool make_tile_maps_bf16(tile::TileMaps* tm, const void* a, int64_t E) {
   return true;
 }
 
+// split kernels (csrc/attention_split.cuh): 16-byte aligned q / k / v rows, workspace given
+static bool split_layout_ok(const float* q, const float* k, const float* v, const float* a,
+                            int64_t ldq, int64_t ldk, int64_t ldv, int64_t rows, int64_t E,
+                            const spt_attn_extras* ex) {
+  const uintptr_t al = (uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)a |
+                       (uintptr_t)(ex ? ex->ws_logits : nullptr);
+  return ex && ex->ws_logits && ex->edge_row && E > 0 && E < (1ll << 31) - 256 &&
+         (al & 15) == 0 && ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldq < (1 << 20) &&
+         ldk < (1 << 20) && ldv < (1 << 20) &&
+         rows * (ldk > ldv ? ldk : ldv) < (int64_t)4000000000LL && !getenv("SPT_ATTN_NO_SPLIT");
+}
+
 static bool tile_layout_ok(const float* q, const float* k, const float* v, const float* a,
                            int64_t ldq, int64_t ldk, int64_t ldv, int64_t rows, int64_t E) {
   const uintptr_t al8 = (uintptr_t)q | (uintptr_t)k;
@@ -617,6 +631,33 @@ int spt_attn_fwd_ex(const float* q, int64_t ldq, const float* k, int64_t ldk, co
   SPT_REQUIRE(scale_mode >= SPT_SCALE_D_TIMES_G && scale_mode <= SPT_SCALE_CONST,
               SPT_E_INVALID, "attn_fwd: bad scale mode %d", scale_mode);
   cudaStream_t st = (cudaStream_t)stream_;
+  if (!extras && a && split::shape_ok(H, D, Dv, F) &&
+      split_layout_ok(q, k, v, a, ldq, ldk, ldv, num_rows, E, ex) &&
+      ((uintptr_t)agg_v & 15) == 0 && (!abar || ((uintptr_t)abar & 15) == 0)) {
+    // edge pass: base-2 logits [E, 4]; row pass: softmax + gathered sums
+    split::EdgeFwdArgs A;
+    A.q = q; A.ldq = (int)ldq; A.k = k; A.ldk = (int)ldk; A.a = a;
+    A.rowptr = rowptr; A.col = col; A.edge_row = ex->edge_row; A.E = E;
+    A.Wq = Wq; A.bq = bq; A.Wk = Wk; A.bk = bk;
+    A.scale_mode = scale_mode; A.scale_value = scale_value;
+    A.logits = ex->ws_logits;
+    // tcgen05 tiles of 128 edges; the CUDA-core pass when the tensor map cannot be encoded
+    // (or SPT_ATTN_EDGE_SIMPLE is set: the A/B of the tests)
+    if (getenv("SPT_ATTN_EDGE_SIMPLE") || !aumma::edge_logits_launch(A, st, &rc)) {
+      split::k_edge_logits_simple<<<(unsigned)ceil_div(E, split::kEdgeThreads),
+                                    split::kEdgeThreads, 0, st>>>(A);
+      rc = check_launch("attn_fwd(edge)");
+    }
+    if (rc != SPT_OK) return rc;
+    split::RowFwdArgs B;
+    B.logits = ex->ws_logits; B.v = v; B.ldv = (int)ldv; B.a = a;
+    B.rowptr = rowptr; B.col = col; B.num_rows = num_rows;
+    B.agg_v = agg_v; B.abar = abar; B.sump = sump; B.m = m; B.z = z;
+    const unsigned grid = (unsigned)ceil_div(num_rows, split::kRowWarps);
+    if (abar) split::k_row_fwd<true><<<grid, split::kRowWarps * kWarp, 0, st>>>(B);
+    else split::k_row_fwd<false><<<grid, split::kRowWarps * kWarp, 0, st>>>(B);
+    return check_launch("attn_fwd(row)");
+  }
   if (!extras && a && tile::shape_ok(H, D, Dv, F) &&
       tile_layout_ok(q, k, v, a, ldq, ldk, ldv, num_rows, E)) {
     tile::TileMaps tmA;
@@ -706,7 +747,54 @@ int spt_attn_bwd_rows_ex(const float* q, int64_t ldq, const float* k, int64_t ld
               SPT_E_INVALID, "attn_bwd_rows: null pointer");
   cudaStream_t st = (cudaStream_t)stream_;
   bool tile_done = false;
-  if (!extras && a && tile::shape_ok(H, D, Dv, F) &&
+  if (!extras && a && split::shape_ok(H, D, Dv, F) &&
+      split_layout_ok(q, k, v, a, ldq, ldk, ldv, num_rows, E, ex) && ex->ws_ds &&
+      lddq < (1 << 20) &&
+      (((uintptr_t)G | (uintptr_t)da | (uintptr_t)d_agg_v | (uintptr_t)agg_v |
+        (uintptr_t)abar | (uintptr_t)d_abar | (uintptr_t)Pbuf | (uintptr_t)ex->ws_ds) & 15) == 0) {
+    // row pass: P, dS [E, 4] and dq; edge pass: G [E, 32] and da
+    const bool has_dab = d_abar && abar;
+    split::RowBwdArgs B;
+    B.logits = ex->ws_logits; B.k = k; B.ldk = (int)ldk; B.v = v; B.ldv = (int)ldv; B.a = a;
+    B.rowptr = rowptr; B.col = col; B.num_rows = num_rows;
+    B.Wk = Wk; B.bk = bk; B.scale_mode = scale_mode; B.scale_value = scale_value;
+    B.m = m; B.z = z; B.agg_v = agg_v; B.abar = abar; B.d_agg_v = d_agg_v; B.d_abar = d_abar;
+    B.dq = dq; B.lddq = (int)lddq; B.Pbuf = Pbuf; B.dS = ex->ws_ds;
+    const unsigned grid = (unsigned)ceil_div(num_rows, split::kRowWarps);
+    const unsigned thr = split::kRowWarps * kWarp;
+    const int rsm = split::kRowBwdSmem;
+    static unsigned long long rdone[4] = {0, 0, 0, 0};
+    if (has_dab && Wk) {
+      ensure_dynamic_smem(split::k_row_bwd<true, true>, rsm, &rdone[0]);
+      split::k_row_bwd<true, true><<<grid, thr, rsm, st>>>(B);
+    } else if (has_dab) {
+      ensure_dynamic_smem(split::k_row_bwd<true, false>, rsm, &rdone[1]);
+      split::k_row_bwd<true, false><<<grid, thr, rsm, st>>>(B);
+    } else if (Wk) {
+      ensure_dynamic_smem(split::k_row_bwd<false, true>, rsm, &rdone[2]);
+      split::k_row_bwd<false, true><<<grid, thr, rsm, st>>>(B);
+    } else {
+      ensure_dynamic_smem(split::k_row_bwd<false, false>, rsm, &rdone[3]);
+      split::k_row_bwd<false, false><<<grid, thr, rsm, st>>>(B);
+    }
+    rc = check_launch("attn_bwd_rows(row)");
+    if (rc != SPT_OK) return rc;
+    split::EdgeBwdArgs A;
+    A.q = q; A.ldq = (int)ldq; A.k = k; A.ldk = (int)ldk; A.a = a;
+    A.rowptr = rowptr; A.col = col; A.edge_row = ex->edge_row; A.E = E;
+    A.Wq = Wq; A.bq = bq; A.Wk = Wk; A.bk = bk;
+    A.scale_mode = scale_mode; A.scale_value = scale_value;
+    A.dS = ex->ws_ds; A.Pbuf = Pbuf; A.d_abar = has_dab ? d_abar : nullptr;
+    A.G = G; A.da = da;
+    if (getenv("SPT_ATTN_EDGE_SIMPLE") || !aumma::edge_bwd_launch(A, st, &rc)) {
+      split::k_edge_bwd_simple<<<(unsigned)ceil_div(E, split::kEdgeThreads), split::kEdgeThreads,
+                                 0, st>>>(A);
+      rc = check_launch("attn_bwd_rows(edge)");
+    }
+    if (rc != SPT_OK) return rc;
+    tile_done = true;
+  }
+  if (!tile_done && !extras && a && tile::shape_ok(H, D, Dv, F) &&
       tile_layout_ok(q, k, v, a, ldq, ldk, ldv, num_rows, E) &&
       lddq < (1 << 20) && lddq % 2 == 0 && ((uintptr_t)dq & 7) == 0 &&
       ((uintptr_t)G & 7) == 0 && (!da || ((uintptr_t)da & 7) == 0) &&

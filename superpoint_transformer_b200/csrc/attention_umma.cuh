@@ -1,0 +1,575 @@
+// attention_umma.cuh — the EDGE passes of the split attention kernels on the tcgen05 tensor cores.
+//
+// The relative-position encodings R_e = [Wq;Wk] a_e (src/nn/attention.py:225-256 of the
+// reference: three per-edge Linear layers) are a dense [E, 32] x [32, 32] product.  One
+// persistent CTA per SM works on tiles of 128 consecutive CSR slots:
+//   warp 0       TMA producer: 128 x 32 fp32 feature rows (SWIZZLE_128B, L2 evict-first) into a
+//                ring of 8 landing slots (128 KB in flight per SM)
+//   warps 8-11   splitter: row -> registers -> TF32 hi / lo -> tcgen05.st (A operand in TMEM)
+//   warp 1       MMA issuer: 12 x tcgen05.mma.kind::tf32 (M=128, N=32, K=8; lo.hi + hi.lo + hi.hi)
+//                per tile, weights resident in shared memory (pre-split, K-major SWIZZLE_128B)
+//   warps 4-7, 12-15  two epilogue groups, one per TMEM accumulator, alternating tiles:
+//                THREAD = EDGE: tcgen05.ld of the edge's 32 outputs, q row / gathered k row,
+//                4 logits, one 16-byte store
+//   warp 2       TMEM allocation
+// 3xTF32 keeps the product at fp32 accuracy (~2^-21 relative), like csrc/gemm_umma.cu.
+#pragma once
+#include "umma_common.cuh"
+#include "attention_split.cuh"
+
+namespace spt {
+namespace umma {  // csrc/gemm_umma.cu
+bool make_map_rows32(CUtensorMap* tm, const float* ptr, int64_t rows, int64_t ld, int box_rows);
+}
+namespace aumma {
+
+using namespace umma;   // mbarrier / TMA / tcgen05 helpers of umma_common.cuh
+
+constexpr int kThreads = 512;
+constexpr int kRing = 8;                       // landing slots of 16 KB
+constexpr int kAStages = 4;                    // hi / lo operand stages in TMEM (64 columns each)
+constexpr int kTileRows = 128;
+constexpr uint32_t kTileBytes = kTileRows * 32 * 4;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kAccCols = 32;              // accumulator a: columns [32 a, 32 a + 32)
+constexpr uint32_t kAStage0 = 64;              // stage s: hi at 64 + 64 s, lo at + 32
+constexpr int kWBytes = 32 * 32 * 4;           // one pre-split weight matrix
+
+struct Smem {
+  static constexpr int ring_off = 0;
+  static constexpr int bhi_off = kRing * (int)kTileBytes;
+  static constexpr int blo_off = bhi_off + kWBytes;
+  static constexpr int bias_off = blo_off + kWBytes;
+  static constexpr int bar_off = bias_off + 128;
+  // a_full[8] a_free[8] a_ready[4] a_empty[4] tmem_full[2] tmem_empty[2] + tmem slot
+  static constexpr int total = bar_off + (2 * kRing + 2 * kAStages + 4) * 8 + 16;
+};
+
+__device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* tm, int c0, int c1,
+                                                 uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+
+// [Wq;Wk] ([32 outputs, 32 features], K-major) as TF32 hi / lo in the SWIZZLE_128B layout the
+// UMMA smem descriptor reads: output row o = 128 bytes, 16-byte chunk c at ((c ^ (o & 7)) << 4)
+__device__ __forceinline__ void stage_weights(unsigned char* bhi, unsigned char* blo, float* bias_s,
+                                              const float* Wq, const float* bq, const float* Wk,
+                                              const float* bk) {
+  for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
+    const int o = i >> 5, f = i & 31;
+    const float* W = o < 16 ? Wq : Wk;
+    const float w = W ? W[(o & 15) * 32 + f] : 0.f;
+    const float hi = tf32_rna(w), lo = tf32_rna(w - hi);
+    const int off = o * 128 + (((f >> 2) ^ (o & 7)) << 4) + (f & 3) * 4;
+    *reinterpret_cast<float*>(bhi + off) = hi;
+    *reinterpret_cast<float*>(blo + off) = lo;
+  }
+  for (int o = threadIdx.x; o < 32; o += blockDim.x) {
+    const float* W = o < 16 ? Wq : Wk;
+    const float* b = o < 16 ? bq : bk;
+    bias_s[o] = (W && b) ? b[o & 15] : 0.f;
+  }
+  fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async proxy
+}
+
+// splitter role: landing slot row -> hi / lo -> TMEM operand stage (as in k_gemm_nt_umma)
+__device__ __forceinline__ void split_row_to_tmem(uint32_t arow, int row, uint32_t ta) {
+  float4 x[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) x[j] = lds128(arow + (uint32_t)((j ^ (row & 7)) << 4));
+  uint32_t hi[32], lo[32];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float xs[4] = {x[j].x, x[j].y, x[j].z, x[j].w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float h = tf32_rna(xs[c]);
+      hi[4 * j + c] = __float_as_uint(h);
+      lo[4 * j + c] = __float_as_uint(tf32_rna(xs[c] - h));
+    }
+  }
+  tmem_st32(ta, hi);
+  tmem_st32(ta + 32, lo);
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// 12 MMAs of one 128 x 32 x 32 tile: D = Alo.Bhi + Ahi.Blo + Ahi.Bhi
+__device__ __forceinline__ void issue_tile_mma(uint32_t d, uint32_t a_hi, uint64_t b_hi,
+                                               uint64_t b_lo, uint32_t idesc) {
+  const uint32_t a_lo = a_hi + 32;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint64_t o = (uint64_t)(k * 8 * 4 >> 4);   // advance inside the 128-byte swizzle row
+    umma_tf32_ts(d, a_lo + k * 8, b_hi + o, idesc, k != 0);
+    umma_tf32_ts(d, a_hi + k * 8, b_lo + o, idesc, 1);
+    umma_tf32_ts(d, a_hi + k * 8, b_hi + o, idesc, 1);
+  }
+}
+
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(32 >> 3) << 17) |
+                            ((uint32_t)(128 >> 4) << 24);
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_edge_logits_umma(const __grid_constant__ CUtensorMap tmA, const split::EdgeFwdArgs P) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem =
+      (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // swizzle atoms
+  unsigned char* ringbuf = smem + Smem::ring_off;
+  unsigned char* bhi = smem + Smem::bhi_off;
+  unsigned char* blo = smem + Smem::blo_off;
+  float* bias_s = reinterpret_cast<float*>(smem + Smem::bias_off);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + Smem::bar_off);
+  uint64_t* a_free = a_full + kRing;
+  uint64_t* a_ready = a_free + kRing;
+  uint64_t* a_empty = a_ready + kAStages;
+  uint64_t* tmem_full = a_empty + kAStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t tiles = (P.E + kTileRows - 1) / kTileRows;
+
+  if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+  if (warp == 1 && lane == 0) {
+    for (int r = 0; r < kRing; ++r) { mbar_init(&a_full[r], 1); mbar_init(&a_free[r], 128); }
+    for (int s = 0; s < kAStages; ++s) { mbar_init(&a_ready[s], 128); mbar_init(&a_empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  stage_weights(bhi, blo, bias_s, P.Wq, P.bq, P.Wk, P.bk);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    const uint64_t policy = tile::policy_evict_first();
+    uint32_t ph = 0;
+    int r = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+      mbar_wait(&a_free[r], ph ^ 1, 0);
+      if (elect_one()) {
+        mbar_expect_tx(&a_full[r], kTileBytes);
+        tma_load_2d_hint(ringbuf + (size_t)r * kTileBytes, &tmA, 0, (int)(t * kTileRows),
+                         &a_full[r], policy);
+      }
+      __syncwarp();
+      if (++r == kRing) { r = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    const uint64_t b_hi = smem_desc_sw128(smem_u32(bhi)), b_lo = smem_desc_sw128(smem_u32(blo));
+    uint32_t tl = 0, pha = 0;
+    int sa = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++tl) {
+      const uint32_t acc = tl & 1, accph = (tl >> 1) & 1;
+      mbar_wait(&tmem_empty[acc], accph ^ 1, 2);
+      mbar_wait(&a_ready[sa], pha, 3);
+      tc_fence_after();
+      if (elect_one()) {
+        issue_tile_mma(tmem_base + acc * kAccCols, tmem_base + kAStage0 + 64 * sa, b_hi, b_lo,
+                       kIdesc);
+        umma_commit(&a_empty[sa]);
+        umma_commit(&tmem_full[acc]);
+      }
+      __syncwarp();
+      if (++sa == kAStages) { sa = 0; pha ^= 1; }
+    }
+  } else if (warp >= 8 && warp < 12) {
+    // ---------------- splitter ----------------
+    const int q = warp - 8, row = q * 32 + lane;
+    uint32_t it = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+      const int r = it % kRing, s = it % kAStages;
+      mbar_wait(&a_full[r], (it / kRing) & 1, 4);
+      mbar_wait(&a_empty[s], ((it / kAStages) & 1) ^ 1, 5);    // the MMAs that read it retired
+      tc_fence_after();
+      split_row_to_tmem(smem_u32(ringbuf) + (uint32_t)r * kTileBytes + (uint32_t)row * 128u, row,
+                        tmem_base + kAStage0 + 64 * s + ((uint32_t)(q * 32) << 16));
+      mbar_arrive(&a_free[r]);      // after the tcgen05.st consumed the loaded values
+      tc_fence_before();
+      mbar_arrive(&a_ready[s]);
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue: thread = edge ----------------
+    const int g = warp >= 12 ? 1 : 0;
+    const int q = warp & 3, row = q * 32 + lane;
+    uint32_t tl = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++tl) {
+      if ((int)(tl & 1) != g) continue;
+      const int64_t e = t * kTileRows + row;
+      const bool valid = e < P.E;
+      float4 qv[4], kv[4];
+      float scale = 0.f;
+#pragma unroll
+      for (int h = 0; h < 4; ++h) qv[h] = kv[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) {
+        const int rr = P.edge_row[e], c = P.col[e];
+        const float4* qp = reinterpret_cast<const float4*>(P.q + (int64_t)rr * P.ldq);
+        const float4* kp = reinterpret_cast<const float4*>(P.k + (int64_t)c * P.ldk);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) { qv[h] = __ldg(qp + h); kv[h] = __ldg(kp + h); }
+        scale = fast::qk_scale_fast(P.scale_mode, P.scale_value,
+                                    P.rowptr[rr + 1] - P.rowptr[rr]);
+      }
+      mbar_wait(&tmem_full[g], (tl >> 1) & 1, 7);
+      tc_fence_after();
+      uint32_t R[32];
+      tmem_ld32(tmem_base + g * kAccCols + ((uint32_t)(q * 32) << 16), R);
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[g]);
+      float lg[4];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const float qs[4] = {qv[h].x, qv[h].y, qv[h].z, qv[h].w};
+        const float ks[4] = {kv[h].x, kv[h].y, kv[h].z, kv[h].w};
+        float s = 0.f;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          const float qe = fmaf(qs[d], scale, __uint_as_float(R[4 * h + d]) + bias_s[4 * h + d]);
+          const float ke = ks[d] + __uint_as_float(R[16 + 4 * h + d]) + bias_s[16 + 4 * h + d];
+          s = fmaf(qe, ke, s);
+        }
+        lg[h] = s * fast::kLog2e;
+      }
+      if (valid)
+        *reinterpret_cast<float4*>(P.logits + e * 4) = make_float4(lg[0], lg[1], lg[2], lg[3]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(kTmemCols)
+                 : "memory");
+  }
+}
+
+// host: false = tensor map could not be encoded (the caller runs the CUDA-core pass)
+inline bool edge_logits_launch(const split::EdgeFwdArgs& A, cudaStream_t st, int* rc) {
+  CUtensorMap tm;
+  if (!umma::make_map_rows32(&tm, A.a, A.E, 32, kTileRows)) return false;
+  const int smem = Smem::total + 1024;
+  static unsigned long long done = 0;
+  ensure_dynamic_smem(k_edge_logits_umma, smem, &done);
+  const int64_t tiles = (A.E + kTileRows - 1) / kTileRows;
+  const int64_t sms = device_sm_count();
+  k_edge_logits_umma<<<(unsigned)(tiles < sms ? tiles : sms), kThreads, smem, st>>>(tm, A);
+  *rc = check_launch("attn_fwd(edge, umma)");
+  return true;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// backward edge pass: per tile of 128 edges
+//   MMA 1   R = a [Wq;Wk]^T                       (as in the forward)
+//   epilogue 1 (thread = edge)  q_e, k_e, dS  ->  G_e = [dS k_e | dS q_e]  -> global (targets
+//           kernel, d[Wq;Wk] product) and, split into TF32 hi / lo, into a TMEM operand stage
+//   MMA 2   da = G [Wq;Wk]                        (A operand = G from TMEM, into the same
+//                                                  accumulator columns, R is dead by then)
+//   epilogue 2  da += sum_h p_e,h dAbar_s,h ; store
+// TMEM: 2 accumulators (one per epilogue group) + 4 feature stages + 2 G stages = 448 columns.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kGStage0 = kAStage0 + 64 * kAStages;    // G stage g: hi at +64 g, lo at +32
+
+struct SmemBwd {
+  static constexpr int ring_off = 0;
+  static constexpr int bhi_off = kRing * (int)kTileBytes;    // [Wq;Wk]   rows = outputs  (MMA 1)
+  static constexpr int blo_off = bhi_off + kWBytes;
+  static constexpr int thi_off = blo_off + kWBytes;          // [Wq;Wk]^T rows = features (MMA 2)
+  static constexpr int tlo_off = thi_off + kWBytes;
+  static constexpr int bias_off = tlo_off + kWBytes;
+  static constexpr int bar_off = bias_off + 128;
+  // a_full[8] a_free[8] a_ready[4] a_empty[4] r_full[2] acc_free[2] g_ready[2] d_full[2] + slot
+  static constexpr int total = bar_off + (2 * kRing + 2 * kAStages + 8) * 8 + 16;
+};
+
+// [Wq;Wk]^T: row f (feature) = the 32 outputs, K-major for da[e, f] = sum_o G[e, o] W[o, f]
+__device__ __forceinline__ void stage_weights_t(unsigned char* thi, unsigned char* tlo,
+                                                const float* Wq, const float* Wk) {
+  for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
+    const int f = i >> 5, o = i & 31;
+    const float* W = o < 16 ? Wq : Wk;
+    const float w = W ? W[(o & 15) * 32 + f] : 0.f;
+    const float hi = tf32_rna(w), lo = tf32_rna(w - hi);
+    const int off = f * 128 + (((o >> 2) ^ (f & 7)) << 4) + (o & 3) * 4;
+    *reinterpret_cast<float*>(thi + off) = hi;
+    *reinterpret_cast<float*>(tlo + off) = lo;
+  }
+  fence_proxy_async();
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_edge_bwd_umma(const __grid_constant__ CUtensorMap tmA, const split::EdgeBwdArgs P) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem =
+      (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  using L = SmemBwd;
+  unsigned char* ringbuf = smem + L::ring_off;
+  float* bias_s = reinterpret_cast<float*>(smem + L::bias_off);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + L::bar_off);
+  uint64_t* a_free = a_full + kRing;
+  uint64_t* a_ready = a_free + kRing;
+  uint64_t* a_empty = a_ready + kAStages;
+  uint64_t* r_full = a_empty + kAStages;     // [2] MMA 1 of the group's tile has landed
+  uint64_t* acc_free = r_full + 2;           // [2] the group has read da (accumulator reusable)
+  uint64_t* g_ready = acc_free + 2;          // [2] G hi / lo of the group's tile is in TMEM
+  uint64_t* d_full = g_ready + 2;            // [2] MMA 2 has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t tiles = (P.E + kTileRows - 1) / kTileRows;
+
+  if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+  if (warp == 1 && lane == 0) {
+    for (int r = 0; r < kRing; ++r) { mbar_init(&a_full[r], 1); mbar_init(&a_free[r], 128); }
+    for (int s = 0; s < kAStages; ++s) { mbar_init(&a_ready[s], 128); mbar_init(&a_empty[s], 1); }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&r_full[a], 1);
+      mbar_init(&acc_free[a], 128);
+      mbar_init(&g_ready[a], 128);
+      mbar_init(&d_full[a], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  stage_weights(smem + L::bhi_off, smem + L::blo_off, bias_s, P.Wq, P.bq, P.Wk, P.bk);
+  stage_weights_t(smem + L::thi_off, smem + L::tlo_off, P.Wq, P.Wk);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    const uint64_t policy = tile::policy_evict_first();
+    uint32_t ph = 0;
+    int r = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+      mbar_wait(&a_free[r], ph ^ 1, 0);
+      if (elect_one()) {
+        mbar_expect_tx(&a_full[r], kTileBytes);
+        tma_load_2d_hint(ringbuf + (size_t)r * kTileBytes, &tmA, 0, (int)(t * kTileRows),
+                         &a_full[r], policy);
+      }
+      __syncwarp();
+      if (++r == kRing) { r = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer: MMA1(0), MMA1(1), MMA2(0), MMA1(2), MMA2(1), ... ----------
+    const uint64_t b_hi = smem_desc_sw128(smem_u32(smem + L::bhi_off));
+    const uint64_t b_lo = smem_desc_sw128(smem_u32(smem + L::blo_off));
+    const uint64_t t_hi = smem_desc_sw128(smem_u32(smem + L::thi_off));
+    const uint64_t t_lo = smem_desc_sw128(smem_u32(smem + L::tlo_off));
+    uint32_t tl = 0, pha = 0;
+    int sa = 0;
+    int64_t n_mine = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) ++n_mine;
+    for (int64_t i = 0; i <= n_mine; ++i, ++tl) {
+      if (i < n_mine) {                       // MMA 1 of tile tl
+        const uint32_t acc = tl & 1, accph = (tl >> 1) & 1;
+        mbar_wait(&acc_free[acc], accph ^ 1, 2);
+        mbar_wait(&a_ready[sa], pha, 3);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_tile_mma(tmem_base + acc * kAccCols, tmem_base + kAStage0 + 64 * sa, b_hi, b_lo,
+                         kIdesc);
+          umma_commit(&a_empty[sa]);
+          umma_commit(&r_full[acc]);
+        }
+        __syncwarp();
+        if (++sa == kAStages) { sa = 0; pha ^= 1; }
+      }
+      if (i >= 1) {                           // MMA 2 of tile tl - 1
+        const uint32_t pt = tl - 1, acc = pt & 1, accph = (pt >> 1) & 1;
+        mbar_wait(&g_ready[acc], accph, 6);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_tile_mma(tmem_base + acc * kAccCols, tmem_base + kGStage0 + 64 * acc, t_hi, t_lo,
+                         kIdesc);
+          umma_commit(&d_full[acc]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 8 && warp < 12) {
+    // ---------------- splitter ----------------
+    const int q = warp - 8, row = q * 32 + lane;
+    uint32_t it = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+      const int r = it % kRing, s = it % kAStages;
+      mbar_wait(&a_full[r], (it / kRing) & 1, 4);
+      mbar_wait(&a_empty[s], ((it / kAStages) & 1) ^ 1, 5);
+      tc_fence_after();
+      split_row_to_tmem(smem_u32(ringbuf) + (uint32_t)r * kTileBytes + (uint32_t)row * 128u, row,
+                        tmem_base + kAStage0 + 64 * s + ((uint32_t)(q * 32) << 16));
+      mbar_arrive(&a_free[r]);
+      tc_fence_before();
+      mbar_arrive(&a_ready[s]);
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue: thread = edge ----------------
+    const int g = warp >= 12 ? 1 : 0;
+    const int q = warp & 3, row = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    uint32_t tl = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++tl) {
+      if ((int)(tl & 1) != g) continue;
+      const uint32_t ph = (tl >> 1) & 1;
+      const int64_t e = t * kTileRows + row;
+      const bool valid = e < P.E;
+      float4 qv[4], kv[4];
+      float4 ds4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      float scale = 0.f;
+      int rr = 0;
+#pragma unroll
+      for (int h = 0; h < 4; ++h) qv[h] = kv[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) {
+        rr = P.edge_row[e];
+        const int c = P.col[e];
+        const float4* qp = reinterpret_cast<const float4*>(P.q + (int64_t)rr * P.ldq);
+        const float4* kp = reinterpret_cast<const float4*>(P.k + (int64_t)c * P.ldk);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) { qv[h] = __ldg(qp + h); kv[h] = __ldg(kp + h); }
+        ds4 = __ldg(reinterpret_cast<const float4*>(P.dS) + e);
+        scale = fast::qk_scale_fast(P.scale_mode, P.scale_value,
+                                    P.rowptr[rr + 1] - P.rowptr[rr]);
+      }
+      mbar_wait(&r_full[g], ph, 7);
+      tc_fence_after();
+      uint32_t R[32];
+      tmem_ld32(tmem_base + g * kAccCols + lane_off, R);
+      // G_e = [dS k_e | dS q_e] (zero rows past E: dS = 0)
+      float G[32];
+      const float dsv[4] = {ds4.x, ds4.y, ds4.z, ds4.w};
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const float qs[4] = {qv[h].x, qv[h].y, qv[h].z, qv[h].w};
+        const float ks[4] = {kv[h].x, kv[h].y, kv[h].z, kv[h].w};
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          const float qe = fmaf(qs[d], scale, __uint_as_float(R[4 * h + d]) + bias_s[4 * h + d]);
+          const float ke = ks[d] + __uint_as_float(R[16 + 4 * h + d]) + bias_s[16 + 4 * h + d];
+          G[4 * h + d] = dsv[h] * ke;
+          G[16 + 4 * h + d] = dsv[h] * qe;
+        }
+      }
+      if (valid) {
+        float4* gp = reinterpret_cast<float4*>(P.G + e * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          gp[j] = make_float4(G[4 * j], G[4 * j + 1], G[4 * j + 2], G[4 * j + 3]);
+      }
+      if (P.da) {
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float h = tf32_rna(G[j]);
+          hi[j] = __float_as_uint(h);
+          lo[j] = __float_as_uint(tf32_rna(G[j] - h));
+        }
+        const uint32_t tg = tmem_base + kGStage0 + 64 * g + lane_off;
+        tmem_st32(tg, hi);
+        tmem_st32(tg + 32, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(&g_ready[g]);
+        // the abar term while MMA 2 runs: sum_h p_e,h dAbar_s,h
+        float da[32];
+#pragma unroll
+        for (int f = 0; f < 32; ++f) da[f] = 0.f;
+        if (valid && P.d_abar) {
+          const float4 p4 = __ldg(reinterpret_cast<const float4*>(P.Pbuf) + e);
+          const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
+          const float4* dab = reinterpret_cast<const float4*>(P.d_abar + (int64_t)rr * 128);
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+#pragma unroll
+            for (int f4 = 0; f4 < 8; ++f4) {
+              const float4 x = __ldg(dab + h * 8 + f4);
+              da[4 * f4 + 0] = fmaf(pv[h], x.x, da[4 * f4 + 0]);
+              da[4 * f4 + 1] = fmaf(pv[h], x.y, da[4 * f4 + 1]);
+              da[4 * f4 + 2] = fmaf(pv[h], x.z, da[4 * f4 + 2]);
+              da[4 * f4 + 3] = fmaf(pv[h], x.w, da[4 * f4 + 3]);
+            }
+          }
+        }
+        mbar_wait(&d_full[g], ph, 8);
+        tc_fence_after();
+        tmem_ld32(tmem_base + g * kAccCols + lane_off, R);
+        tc_fence_before();
+        mbar_arrive(&acc_free[g]);
+        if (valid) {
+          float4* dp = reinterpret_cast<float4*>(P.da + e * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dp[j] = make_float4(da[4 * j] + __uint_as_float(R[4 * j]),
+                                da[4 * j + 1] + __uint_as_float(R[4 * j + 1]),
+                                da[4 * j + 2] + __uint_as_float(R[4 * j + 2]),
+                                da[4 * j + 3] + __uint_as_float(R[4 * j + 3]));
+        }
+      } else {
+        // no feature gradient wanted: the accumulator is free, MMA 2 still runs (on zeros) to
+        // keep the issue order of the MMA warp
+        uint32_t zero[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) zero[j] = 0u;
+        const uint32_t tg = tmem_base + kGStage0 + 64 * g + lane_off;
+        tmem_st32(tg, zero);
+        tmem_st32(tg + 32, zero);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(&g_ready[g]);
+        mbar_wait(&d_full[g], ph, 8);
+        tc_fence_after();
+        tc_fence_before();
+        mbar_arrive(&acc_free[g]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(kTmemCols)
+                 : "memory");
+  }
+}
+
+inline bool edge_bwd_launch(const split::EdgeBwdArgs& A, cudaStream_t st, int* rc) {
+  CUtensorMap tm;
+  if (!umma::make_map_rows32(&tm, A.a, A.E, 32, kTileRows)) return false;
+  const int smem = SmemBwd::total + 1024;
+  static unsigned long long done = 0;
+  ensure_dynamic_smem(k_edge_bwd_umma, smem, &done);
+  const int64_t tiles = (A.E + kTileRows - 1) / kTileRows;
+  const int64_t sms = device_sm_count();
+  k_edge_bwd_umma<<<(unsigned)(tiles < sms ? tiles : sms), kThreads, smem, st>>>(tm, A);
+  *rc = check_launch("attn_bwd_rows(edge, umma)");
+  return true;
+}
+
+}  // namespace aumma
+}  // namespace spt

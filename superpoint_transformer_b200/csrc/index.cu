@@ -249,6 +249,16 @@ __global__ void k_gather_i32(const int32_t* __restrict__ src,
   for (; i < n; i += stride) out[i] = src[idx[i]];
 }
 
+// out[j] = g for ptr[g] <= j < ptr[g + 1]: one warp per group (groups are short)
+__global__ void k_expand_pointers(const int32_t* __restrict__ ptr, int64_t num_groups,
+                                  int32_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= num_groups) return;
+  const int b = ptr[g], e = ptr[g + 1];
+  for (int j = b + lane; j < e; j += 32) out[j] = (int32_t)g;
+}
+
 // one warp per group; int64 exact sums
 __global__ void k_segment_sum_i64(const int64_t* __restrict__ values,
                                   const int32_t* __restrict__ ptr,
@@ -377,6 +387,16 @@ int spt_gather_i32(const int32_t* src, const int32_t* idx, int64_t n,
   SPT_REQUIRE(src && idx && out, SPT_E_INVALID, "gather_i32: null pointer");
   k_gather_i32<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream_>>>(src, idx, n, out);
   return check_launch("gather_i32");
+}
+
+int spt_expand_pointers_i32(const int32_t* ptr, int64_t num_groups, int32_t* out,
+                            void* stream_) {
+  SPT_REQUIRE(num_groups >= 0, SPT_E_INVALID, "expand_pointers: negative size");
+  if (num_groups == 0) return SPT_OK;
+  SPT_REQUIRE(ptr && out, SPT_E_INVALID, "expand_pointers: null pointer");
+  k_expand_pointers<<<(unsigned)ceil_div(num_groups * 32, 256), 256, 0,
+                      (cudaStream_t)stream_>>>(ptr, num_groups, out);
+  return check_launch("expand_pointers");
 }
 
 int spt_segment_sum_i64(const int64_t* values, const int32_t* ptr,

@@ -5,6 +5,7 @@ the arithmetic of the hot path happens in libspt_b200.so.  Every function
 refuses non-CUDA tensors: there is no CPU fallback.
 """
 import ctypes
+import os
 import weakref
 
 import torch
@@ -203,7 +204,22 @@ class GraphIndex:
     """
 
     __slots__ = ("rowptr", "col", "perm", "csc_ptr", "csc_src", "csc2csr",
-                 "num_rows", "num_targets", "E", "__weakref__")
+                 "num_rows", "num_targets", "E", "_edge_row", "__weakref__")
+
+    @property
+    def edge_row(self):
+        """int32 [E]: the row of every CSR slot (input of the edge-parallel attention kernels);
+        built on first use, once per graph."""
+        er = getattr(self, "_edge_row", None)
+        if er is None:
+            lib = _lib.load()
+            er = torch.empty(max(self.E, 1), dtype=torch.int32, device=self.rowptr.device)
+            with torch.cuda.device(self.rowptr.device):
+                _lib.check(lib.spt_expand_pointers_i32(_p(self.rowptr), self.num_rows, _p(er),
+                                                       _stream()), "spt_expand_pointers_i32")
+            _count()
+            self._edge_row = er
+        return er
 
 
 # edge_index tensors whose columns are already grouped by source row in CSR order (stable):
@@ -872,9 +888,15 @@ class _AttnCore(torch.autograd.Function):
         z = torch.empty((R, H), dtype=torch.float32, device=dev)
         has_ex = any(t is not None for t in (q_row_add, q_tgt_add, k_row_add, drop_mask))
         ex = None
+        logits = None
         if has_ex:
             ex = _lib.AttnExtras(_p(q_row_add), _p(q_tgt_add), _p(k_row_add), _p(drop_mask),
                                  None, None, None, None)
+        elif ATTN_SPLIT and a is not None and (H, D, Dv, F) == (4, 4, 32, 32) and g.E > 0:
+            # workspace of the split kernels: base-2 logits [E, H] (kept for the backward)
+            logits = torch.empty((g.E, H), dtype=torch.float32, device=dev)
+            ex = _lib.AttnExtras(None, None, None, None, None, None, None, None,
+                                 _p(logits), _p(g.edge_row), None)
         with torch.cuda.device(dev), _timed('attn_fwd', R=R, E=g.E, H=H, D=D, Dv=Dv, F=F,
                                             abar=abar is not None):
             _lib.check(lib.spt_attn_fwd_ex(qp, ldq, kp, ldk, vp, ldv, _p(a), _p(g.rowptr),
@@ -887,6 +909,7 @@ class _AttnCore(torch.autograd.Function):
         ctx.g, ctx.H, ctx.D, ctx.Dv, ctx.F = g, H, D, Dv, F
         ctx.scale_mode, ctx.scale_value = scale_mode, scale_value
         ctx.fused = fused
+        ctx.logits = logits          # split kernels: the backward row pass reads them back
         ctx.opt = (kv is not None, a is not None, Wq is not None, bq is not None,
                    Wk is not None, bk is not None, abar is not None)
         ctx.ex = (q_row_add is not None, q_tgt_add is not None, k_row_add is not None,
@@ -984,6 +1007,10 @@ class _AttnCore(torch.autograd.Function):
             ex = _lib.AttnExtras(_p(q_row_add), _p(q_tgt_add), _p(k_row_add), _p(drop_mask),
                                  _p(d_qr), _p(d_kr), _p(d_sump),
                                  _p(ctx.sump) if d_sump is not None else None)
+        elif ctx.logits is not None and ATTN_SPLIT:
+            ws_ds = torch.empty((E, H), dtype=torch.float32, device=dev)
+            ex = _lib.AttnExtras(None, None, None, None, None, None, None, None,
+                                 _p(ctx.logits), _p(g.edge_row), _p(ws_ds))
         with torch.cuda.device(dev):
             with _timed('attn_bwd_rows', **meta):
                 _lib.check(lib.spt_attn_bwd_rows_ex(
@@ -1016,6 +1043,15 @@ class _AttnCore(torch.autograd.Function):
 # ---------------------------------------------------------------------------
 ATTN_STORAGE = 'fp32'
 _bf16_cache = _IdentityCache()
+# split attention kernels (csrc/attention_split.cuh, csrc/attention_umma.cu): one edge-parallel
+# pass on the tensor cores + one row-parallel pass; SPT_ATTN_SPLIT=0 keeps the fused row-tile
+# kernels (the A/B of tools/run_attn.py and the parity tests use the switch)
+ATTN_SPLIT = os.environ.get('SPT_ATTN_SPLIT', '1') != '0'
+
+
+def set_attention_split(on):
+    global ATTN_SPLIT
+    ATTN_SPLIT = bool(on)
 
 
 def set_attention_storage(mode):

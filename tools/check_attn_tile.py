@@ -1,4 +1,5 @@
-"""Device-side A/B of the row-tile attention kernels (csrc/attention_tile.cuh) against the
+"""Device-side A/B of the row-tile attention kernels (csrc/attention_tile.cuh) and of the split
+kernels (csrc/attention_split.cuh, `rpw=split`) against the
 round-1 per-edge kernels (attention_fast.cuh, 1 row per warp — the configuration the golden
 vectors pin): prints the max abs difference of every output and gradient.  Diagnosis tool;
 the parity tests proper are tests/test_gpu_parity.py."""
@@ -31,10 +32,11 @@ def graph(n, seed, hub=False):
     return ei[:, torch.randperm(ei.shape[1], generator=g)]
 
 
-def run(N, seed, hub, want_abar, use_q, use_k, env):
+def run(N, seed, hub, want_abar, use_q, use_k, env, split=False):
     for k in ('SPT_ATTN_NO_TILE', 'SPT_ATTN_ROWS_PER_WARP'):
         os.environ.pop(k, None)
     os.environ.update(env)
+    ops.set_attention_split(split)
     H, D, C, F = 4, 4, 128, 32
     g = torch.Generator().manual_seed(seed)
     ei = graph(N, seed, hub).to(DEV)
@@ -76,8 +78,11 @@ def main():
     for N, seed, hub, want_abar, use_q, use_k in cases:
         ref = run(N, seed, hub, want_abar, use_q, use_k,
                   dict(SPT_ATTN_NO_TILE='1', SPT_ATTN_ROWS_PER_WARP='1'))
-        for rpw in ('1', '3', '8'):
-            got = run(N, seed, hub, want_abar, use_q, use_k, dict(SPT_ATTN_ROWS_PER_WARP=rpw))
+        for rpw in ('1', '3', '8', 'split'):
+            if rpw == 'split':     # edge pass + row pass (csrc/attention_split.cuh)
+                got = run(N, seed, hub, want_abar, use_q, use_k, {}, split=True)
+            else:
+                got = run(N, seed, hub, want_abar, use_q, use_k, dict(SPT_ATTN_ROWS_PER_WARP=rpw))
             line = []
             for k in ref:
                 sc = max(float(ref[k].abs().max()), 1e-6)

@@ -33,11 +33,27 @@ mk = lambda *s: (torch.randn(*s, generator=g) * 0.2).to(dev).requires_grad_(True
 Wq, bq, Wk, bk = mk(16, 32), mk(16), mk(16, 32), mk(16)
 ops.set_attention_storage(os.environ.get('SPT_ATTN_STORAGE', 'fp32'))
 ops.enable_event_timing(True)
-for it in range(ITERS):
+
+
+def step():
     agg, abar, sump = ops.attention_core(qkv, None, a, Wq, bq, Wk, bk, gi, H, D,
                                          ops.SCALE_D_TIMES_G, 32 ** -0.5)
     (agg.sum() + abar.sum()).backward()
+
+
+for it in range(ITERS):
+    step()
 torch.cuda.synchronize()
+if os.environ.get('PROFILE', '0') == '1':   # per-kernel device times (torch.profiler / CUPTI)
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for it in range(3):
+            step()
+        torch.cuda.synchronize()
+    for ev in sorted(prof.key_averages(), key=lambda x: -x.device_time_total):
+        if ev.device_time_total > 0 and ('spt' in ev.key or 'umma' in ev.key):
+            print(f'  [kernel] {ev.device_time_total / ev.count / 1e3:.4f} ms x{ev.count // 3}/step  '
+                  f'{ev.key[:90]}')
 # bare gather ceiling: out[row] = sum_e v[col[e]] (the 512-byte rows the forward gathers, nothing
 # else) with the CSR segment-sum kernel — 64 resident warps/SM, 2 rows in flight per warp
 seg = ops.SegmentIndex(gi.rowptr, gi.col, None, E, N, None)
@@ -48,7 +64,7 @@ torch.cuda.synchronize()
 acc = {}
 for tag, meta, s, e in ops.timing_records():
     acc.setdefault(tag, []).append(s.elapsed_time(e))
-print(f'N={N} E={E} sorted={MORTON} storage={ops.ATTN_STORAGE}')
+print(f'N={N} E={E} sorted={MORTON} storage={ops.ATTN_STORAGE} split={ops.ATTN_SPLIT}')
 for k, v in acc.items():
     print(f'  {k}: min {min(v):.4f} ms  last {v[-1]:.4f} ms')
 if 'segment_pool_fwd' in acc:
