@@ -576,6 +576,19 @@ static bool make_tile_maps_bf16(tile::TileMaps* tm, const void* a, int64_t E) {
   return true;
 }
 
+// consecutive rows per warp of the split row kernels: the next row's operands are prefetched
+// while the current one gathers, so longer runs help as long as the grid still covers the
+// machine ~4 times over
+static int split_rows_per_warp(int64_t num_rows) {
+  if (const char* ov = getenv("SPT_ATTN_ROWS_PER_WARP")) {
+    int r = atoi(ov);
+    if (r >= 1 && r <= 16) return r;
+  }
+  const int64_t warps = (int64_t)device_sm_count() * 32 * 4;
+  int64_t r = num_rows / warps;
+  return (int)(r < 1 ? 1 : r > 4 ? 4 : r);
+}
+
 // split kernels (csrc/attention_split.cuh): 16-byte aligned q / k / v rows, workspace given
 static bool split_layout_ok(const float* q, const float* k, const float* v, const float* a,
                             int64_t ldq, int64_t ldk, int64_t ldv, int64_t rows, int64_t E,
@@ -653,7 +666,9 @@ int spt_attn_fwd_ex(const float* q, int64_t ldq, const float* k, int64_t ldk, co
     B.logits = ex->ws_logits; B.v = v; B.ldv = (int)ldv; B.a = a;
     B.rowptr = rowptr; B.col = col; B.num_rows = num_rows;
     B.agg_v = agg_v; B.abar = abar; B.sump = sump; B.m = m; B.z = z;
-    const unsigned grid = (unsigned)ceil_div(num_rows, split::kRowWarps);
+    B.rows_per_warp = split_rows_per_warp(num_rows);
+    const unsigned grid =
+        (unsigned)ceil_div(num_rows, (int64_t)split::kRowWarps * B.rows_per_warp);
     if (abar) split::k_row_fwd<true><<<grid, split::kRowWarps * kWarp, 0, st>>>(B);
     else split::k_row_fwd<false><<<grid, split::kRowWarps * kWarp, 0, st>>>(B);
     return check_launch("attn_fwd(row)");

@@ -183,6 +183,7 @@ struct RowFwdArgs {
   const int32_t* rowptr; const int32_t* col;
   int64_t num_rows;
   float* agg_v; float* abar; float* sump; float* m; float* z;
+  int rows_per_warp;                    // consecutive rows per warp, 1..16
 };
 
 constexpr int kRowWarps = 8;
@@ -294,85 +295,139 @@ __device__ __forceinline__ void row_fwd_chunk(int n, float4 lg, float4 mx, int m
   }
 }
 
+// per-warp shared memory of the forward row pass
+template <bool ABAR>
+struct RowFwdTiles {
+  float p[32 * kH];              // softmax numerators of the chunk
+  float pre_lg[2][32 * kH];      // logits of the first chunk of this / the next row (cp.async)
+  int pre_col[2][32];            // its column ids
+  float m[kH];                   // row maxima (long rows)
+  float a[ABAR ? 32 * kF : 4];   // feature rows of the chunk (cp.async)
+};
+
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16_plain(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+// A warp walks `rows_per_warp` consecutive rows.  The row extents come in one load, and the
+// logits / column ids of the NEXT row's first chunk are copied to shared memory while the
+// current row gathers: per row only the batches of gathered v rows remain as dependent round
+// trips.
 template <bool ABAR>
 __global__ void __launch_bounds__(kRowWarps * 32, kRowFwdCtas)
 k_row_fwd(const RowFwdArgs P) {
-  __shared__ __align__(16) float p_sm[kRowWarps][32 * kH];
-  __shared__ __align__(16) float m_sm[kRowWarps][kH];
-  __shared__ __align__(16) float a_sm[ABAR ? kRowWarps : 1][32 * kF];
+  __shared__ __align__(16) RowFwdTiles<ABAR> tiles[kRowWarps];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * kRowWarps + w;
-  if (row >= P.num_rows) return;
+  const int R = P.rows_per_warp;                  // <= 16
+  const int64_t r0 = ((int64_t)blockIdx.x * kRowWarps + w) * R;
+  if (r0 >= P.num_rows) return;
+  const int nrows = (int)min((int64_t)R, P.num_rows - r0);
+  RowFwdTiles<ABAR>& S = tiles[w];
   const int hb = lane >> 3;
-  const int b = P.rowptr[row], e = P.rowptr[row + 1];
-  float* p_s = p_sm[w];
-  float* a_s = a_sm[ABAR ? w : 0];
   const uint64_t stream = policy_evict_first();
-  if (ABAR && e > b) stage_features(a_s, P.a, b, min(32, e - b), lane, stream);
   const char* vbase = reinterpret_cast<const char*>(P.v) + 16 * lane;
   const unsigned ldvb = (unsigned)P.ldv * 4u;
   const float4* lg4 = reinterpret_cast<const float4*>(P.logits);
-
-  // pass 1: row maxima (a row of <= 32 edges keeps its logits and columns in registers)
-  const bool single = e - b <= 32;
-  float4 lg = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-  float4 mx = lg;
-  int mycol = 0;
-  for (int tb = b; tb < e; tb += 32) {
-    const int i = tb + lane;
-    if (i < e) {
-      lg = __ldg(lg4 + i);
-      mx.x = fmaxf(mx.x, lg.x); mx.y = fmaxf(mx.y, lg.y);
-      mx.z = fmaxf(mx.z, lg.z); mx.w = fmaxf(mx.w, lg.w);
-      if (single) mycol = P.col[i];
+  const int rp = P.rowptr[r0 + min(lane, nrows)];             // extents of my rows
+  const uint32_t pre_lg = smem_addr(S.pre_lg[0]) + 16 * lane;
+  const uint32_t pre_col = smem_addr(S.pre_col[0]) + 4 * lane;
+  {
+    const int b0 = __shfl_sync(kFull, rp, 0), e0 = __shfl_sync(kFull, rp, 1);
+    if (lane < min(32, e0 - b0)) {
+      cp_async16_plain(pre_lg, lg4 + b0 + lane);
+      cp_async4(pre_col, P.col + b0 + lane);
     }
+    cp_async_commit();
   }
-  mx.x = warp_max(mx.x); mx.y = warp_max(mx.y); mx.z = warp_max(mx.z); mx.w = warp_max(mx.w);
-  if (lane < kH) P.m[row * kH + lane] = (e > b) ? pick4(mx, lane) * kLn2 : 0.f;   // natural log
 
-  // pass 2: p = 2^(logit - max), sums, weighted accumulation
-  f32x2 accv01 = 0ull, accv23 = 0ull, acca01 = 0ull, acca23 = 0ull;
-  float l = 0.f;                                  // sum of p of head hsel_of_lane(lane)
-  if (single) {
-    if (e > b)
-      row_fwd_chunk<ABAR>(e - b, lg, mx, mycol, lane, p_s, a_s, vbase, ldvb, l, accv01, accv23,
-                          acca01, acca23);
-  } else {
-    // long row: the maxima wait in shared memory while the chunks stream through
-    if (lane == 0) *reinterpret_cast<float4*>(m_sm[w]) = mx;
 #pragma unroll 1
-    for (int tb = b; tb < e; tb += 32) {
-      const int i = tb + lane;
-      lg = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-      mycol = 0;
-      if (i < e) {
-        lg = __ldg(lg4 + i);
-        mycol = P.col[i];
-      }
-      __syncwarp();                               // the previous chunk's tiles have been read
-      if (ABAR && tb != b) stage_features(a_s, P.a, tb, min(32, e - tb), lane, stream);
-      mx = *reinterpret_cast<const float4*>(m_sm[w]);
-      row_fwd_chunk<ABAR>(min(32, e - tb), lg, mx, mycol, lane, p_s, a_s, vbase, ldvb, l,
-                          accv01, accv23, acca01, acca23);
+  for (int i = 0; i < nrows; ++i) {
+    const int64_t row = r0 + i;
+    const int b = __shfl_sync(kFull, rp, i), e = __shfl_sync(kFull, rp, i + 1);
+    const int n0 = min(32, e - b);
+    cp_async_wait_all();                          // my slot of this row's first chunk has landed
+    __syncwarp();                                 // and the previous row's tiles have been read
+    float4 lg = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    int mycol = 0;
+    if (lane < n0) {
+      lg = *reinterpret_cast<const float4*>(&S.pre_lg[i & 1][lane * kH]);
+      mycol = S.pre_col[i & 1][lane];
     }
-  }
+    if (i + 1 < nrows) {                          // the next row's first chunk
+      const int e2 = __shfl_sync(kFull, rp, min(i + 2, 31));
+      if (lane < min(32, e2 - e)) {
+        const uint32_t o = ((i + 1) & 1);
+        cp_async16_plain(pre_lg + o * (32 * kH * 4), lg4 + e + lane);
+        cp_async4(pre_col + o * (32 * 4), P.col + e + lane);
+      }
+    }
+    if (ABAR && n0 > 0) stage_features(S.a, P.a, b, n0, lane, stream);   // commits
+    else cp_async_commit();
 
-  // epilogue: PyG softmax adds 1e-16 to the denominator
-  const float zz = l + 1e-16f;
-  const float iz = fast_rcp(zz);
-  const float inv = __shfl_sync(kFull, iz, src_of_head(hb));
-  const f32x2 ii = pack2(inv, inv);
-  ulonglong2 o;
-  o.x = mul2(accv01, ii); o.y = mul2(accv23, ii);
-  *reinterpret_cast<ulonglong2*>(P.agg_v + row * kC + 4 * lane) = o;
-  if (ABAR) {
-    o.x = mul2(acca01, ii); o.y = mul2(acca23, ii);
-    *reinterpret_cast<ulonglong2*>(P.abar + row * (kH * kF) + 4 * lane) = o;
-  }
-  if (lane < kH) {
-    const int h = hsel_of_lane(lane);
-    P.z[row * kH + h] = zz;
-    P.sump[row * kH + h] = l * iz;
+    // pass 1: row maxima (later chunks of a long row are read directly)
+    const bool single = e - b <= 32;
+    float4 mx = lg;
+    for (int tb = b + 32; tb < e; tb += 32) {
+      const int j = tb + lane;
+      if (j < e) {
+        const float4 x = __ldg(lg4 + j);
+        mx.x = fmaxf(mx.x, x.x); mx.y = fmaxf(mx.y, x.y);
+        mx.z = fmaxf(mx.z, x.z); mx.w = fmaxf(mx.w, x.w);
+      }
+    }
+    mx.x = warp_max(mx.x); mx.y = warp_max(mx.y); mx.z = warp_max(mx.z); mx.w = warp_max(mx.w);
+    if (lane < kH) P.m[row * kH + lane] = (e > b) ? pick4(mx, lane) * kLn2 : 0.f;   // natural log
+
+    // pass 2: p = 2^(logit - max), sums, weighted accumulation
+    f32x2 accv01 = 0ull, accv23 = 0ull, acca01 = 0ull, acca23 = 0ull;
+    float l = 0.f;                                // sum of p of head hsel_of_lane(lane)
+    if (single) {
+      if (e > b)
+        row_fwd_chunk<ABAR>(n0, lg, mx, mycol, lane, S.p, S.a, vbase, ldvb, l, accv01, accv23,
+                            acca01, acca23);
+    } else {
+      // long row: the maxima wait in shared memory while the chunks stream through
+      if (lane == 0) *reinterpret_cast<float4*>(S.m) = mx;
+#pragma unroll 1
+      for (int tb = b; tb < e; tb += 32) {
+        if (tb != b) {
+          const int j = tb + lane;
+          lg = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+          mycol = 0;
+          if (j < e) {
+            lg = __ldg(lg4 + j);
+            mycol = P.col[j];
+          }
+          __syncwarp();                           // the previous chunk's tiles have been read
+          if (ABAR) stage_features(S.a, P.a, tb, min(32, e - tb), lane, stream);
+        }
+        __syncwarp();
+        mx = *reinterpret_cast<const float4*>(S.m);
+        row_fwd_chunk<ABAR>(min(32, e - tb), lg, mx, mycol, lane, S.p, S.a, vbase, ldvb, l,
+                            accv01, accv23, acca01, acca23);
+      }
+    }
+
+    // epilogue: PyG softmax adds 1e-16 to the denominator
+    const float zz = l + 1e-16f;
+    const float iz = fast_rcp(zz);
+    const float inv = __shfl_sync(kFull, iz, src_of_head(hb));
+    const f32x2 ii = pack2(inv, inv);
+    ulonglong2 o;
+    o.x = mul2(accv01, ii); o.y = mul2(accv23, ii);
+    *reinterpret_cast<ulonglong2*>(P.agg_v + row * kC + 4 * lane) = o;
+    if (ABAR) {
+      o.x = mul2(acca01, ii); o.y = mul2(acca23, ii);
+      *reinterpret_cast<ulonglong2*>(P.abar + row * (kH * kF) + 4 * lane) = o;
+    }
+    if (lane < kH) {
+      const int h = hsel_of_lane(lane);
+      P.z[row * kH + h] = zz;
+      P.sump[row * kH + h] = l * iz;
+    }
   }
 }
 

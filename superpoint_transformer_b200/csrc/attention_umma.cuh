@@ -26,7 +26,7 @@ namespace aumma {
 using namespace umma;   // mbarrier / TMA / tcgen05 helpers of umma_common.cuh
 
 constexpr int kThreads = 512;
-constexpr int kRing = 8;                       // landing slots of 16 KB
+constexpr int kRing = 6;                       // landing slots of 16 KB
 constexpr int kAStages = 4;                    // hi / lo operand stages in TMEM (64 columns each)
 constexpr int kTileRows = 128;
 constexpr uint32_t kTileBytes = kTileRows * 32 * 4;
@@ -37,13 +37,66 @@ constexpr int kWBytes = 32 * 32 * 4;           // one pre-split weight matrix
 
 struct Smem {
   static constexpr int ring_off = 0;
-  static constexpr int bhi_off = kRing * (int)kTileBytes;
+  static constexpr int qk_off = kRing * (int)kTileBytes;     // [2 groups][2 stages][128][q 16 | k 16]
+  static constexpr int bhi_off = qk_off + 4 * (int)kTileBytes;
   static constexpr int blo_off = bhi_off + kWBytes;
   static constexpr int bias_off = blo_off + kWBytes;
   static constexpr int bar_off = bias_off + 128;
-  // a_full[8] a_free[8] a_ready[4] a_empty[4] tmem_full[2] tmem_empty[2] + tmem slot
+  // a_full[R] a_free[R] a_ready[4] a_empty[4] tmem_full[2] tmem_empty[2] + tmem slot
   static constexpr int total = bar_off + (2 * kRing + 2 * kAStages + 4) * 8 + 16;
 };
+
+// ---- the epilogue's operands, staged two tiles ahead ------------------------------------
+// Thread = edge needs the q row of its source and the gathered k row of its target: two
+// dependent global round trips (slot -> row / column id -> 64-byte rows).  Each epilogue thread
+// copies them with cp.async into its own 128-byte row of a 2-stage buffer for the tile it will
+// process two turns later; the ids of the tile after that wait in registers.
+__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16_cg(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+struct EdgeIds {
+  int rr, c;
+  bool valid;
+};
+__device__ __forceinline__ EdgeIds load_ids(const int32_t* edge_row, const int32_t* col,
+                                            int64_t t, int64_t tiles, int row, int64_t E) {
+  EdgeIds id;
+  const int64_t e = t * kTileRows + row;
+  id.valid = t < tiles && e < E;
+  id.rr = 0; id.c = 0;
+  if (id.valid) { id.rr = edge_row[e]; id.c = col[e]; }
+  return id;
+}
+// q chunks 0..3, k chunks 4..7 of a 128-byte stage row, chunk j at ((j ^ (row & 7)) << 4):
+// conflict-free 16-byte reads by the thread that owns the row, and the SWIZZLE_128B pattern of
+// the TMA stores that later leave from the same rows.
+// The copy is COOPERATIVE: a row-per-thread gather costs one L1 wavefront per lane and
+// instruction (32 per LDG/LDGSTS, the limiter of the first version); here 4 lanes fetch the 4
+// chunks of one 64-byte row, so an instruction touches 8 rows = 8 wavefronts.  `wbase` is the
+// stage address of the warp's first row; ids travel by shuffle from the lanes that own them.
+__device__ __forceinline__ void stage_qk(uint32_t wbase, int lane, const EdgeIds& id,
+                                         const float* q, int ldq, const float* k, int ldk) {
+  const int sub = lane & 3, r8 = lane >> 2;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int rl = 8 * m + r8;
+    const int rr = __shfl_sync(0xffffffffu, id.rr, rl);
+    const int c = __shfl_sync(0xffffffffu, id.c, rl);
+    const int v = __shfl_sync(0xffffffffu, (int)id.valid, rl);
+    if (v) {
+      const uint32_t dst = wbase + (uint32_t)rl * 128u;
+      const int sw = rl & 7;
+      cp_async16_ca(dst + (uint32_t)((sub ^ sw) << 4),
+                    reinterpret_cast<const char*>(q + (int64_t)rr * ldq) + 16 * sub);
+      cp_async16_cg(dst + (uint32_t)(((4 + sub) ^ sw) << 4),
+                    reinterpret_cast<const char*>(k + (int64_t)c * ldk) + 16 * sub);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
 
 __device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* tm, int c0, int c1,
                                                  uint64_t* bar, uint64_t policy) {
@@ -205,36 +258,45 @@ k_edge_logits_umma(const __grid_constant__ CUtensorMap tmA, const split::EdgeFwd
   } else if (warp >= 4) {
     // ---------------- epilogue: thread = edge ----------------
     const int g = warp >= 12 ? 1 : 0;
-    const int q = warp & 3, row = q * 32 + lane;
-    uint32_t tl = 0;
-    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++tl) {
-      if ((int)(tl & 1) != g) continue;
+    const int q = warp & 3, row = q * 32 + lane, sw = row & 7;
+    const uint32_t wbase = smem_u32(smem + Smem::qk_off) + (uint32_t)g * 2 * kTileBytes +
+                           (uint32_t)(q * 32) * 128u;      // my warp's rows in stage 0
+    const uint32_t my = wbase + (uint32_t)lane * 128u;
+    const int64_t stride = 2 * (int64_t)gridDim.x;
+    const int64_t t0 = blockIdx.x + (int64_t)g * gridDim.x;
+    // extent of the source row of the tiles staged in stages 0 / 1 (raw loads: nothing waits on
+    // them until the tile is processed)
+    int rb0 = 0, re0 = 1, rb1 = 0, re1 = 1;
+    EdgeIds id = load_ids(P.edge_row, P.col, t0, tiles, row, P.E);
+    stage_qk(wbase, lane, id, P.q, P.ldq, P.k, P.ldk);
+    if (id.valid) { rb0 = P.rowptr[id.rr]; re0 = P.rowptr[id.rr + 1]; }
+    id = load_ids(P.edge_row, P.col, t0 + stride, tiles, row, P.E);
+    stage_qk(wbase + kTileBytes, lane, id, P.q, P.ldq, P.k, P.ldk);
+    if (id.valid) { rb1 = P.rowptr[id.rr]; re1 = P.rowptr[id.rr + 1]; }
+    id = load_ids(P.edge_row, P.col, t0 + 2 * stride, tiles, row, P.E);
+    uint32_t n = 0;
+    for (int64_t t = t0; t < tiles; t += stride, ++n) {
+      const uint32_t st = n & 1;
       const int64_t e = t * kTileRows + row;
       const bool valid = e < P.E;
-      float4 qv[4], kv[4];
-      float scale = 0.f;
-#pragma unroll
-      for (int h = 0; h < 4; ++h) qv[h] = kv[h] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid) {
-        const int rr = P.edge_row[e], c = P.col[e];
-        const float4* qp = reinterpret_cast<const float4*>(P.q + (int64_t)rr * P.ldq);
-        const float4* kp = reinterpret_cast<const float4*>(P.k + (int64_t)c * P.ldk);
-#pragma unroll
-        for (int h = 0; h < 4; ++h) { qv[h] = __ldg(qp + h); kv[h] = __ldg(kp + h); }
-        scale = fast::qk_scale_fast(P.scale_mode, P.scale_value,
-                                    P.rowptr[rr + 1] - P.rowptr[rr]);
-      }
-      mbar_wait(&tmem_full[g], (tl >> 1) & 1, 7);
+      const float scale =
+          fast::qk_scale_fast(P.scale_mode, P.scale_value, st ? re1 - rb1 : re0 - rb0);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");   // this tile's rows have landed
+      __syncwarp();                                          // (copied by my warp's lanes)
+      mbar_wait(&tmem_full[g], n & 1, 7);
       tc_fence_after();
       uint32_t R[32];
       tmem_ld32(tmem_base + g * kAccCols + ((uint32_t)(q * 32) << 16), R);
       tc_fence_before();
       mbar_arrive(&tmem_empty[g]);
+      const uint32_t src = my + st * kTileBytes;
       float lg[4];
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
-        const float qs[4] = {qv[h].x, qv[h].y, qv[h].z, qv[h].w};
-        const float ks[4] = {kv[h].x, kv[h].y, kv[h].z, kv[h].w};
+        const float4 q4 = lds128(src + (uint32_t)((h ^ sw) << 4));
+        const float4 k4 = lds128(src + (uint32_t)(((4 + h) ^ sw) << 4));
+        const float qs[4] = {q4.x, q4.y, q4.z, q4.w};
+        const float ks[4] = {k4.x, k4.y, k4.z, k4.w};
         float s = 0.f;
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
@@ -246,7 +308,17 @@ k_edge_logits_umma(const __grid_constant__ CUtensorMap tmA, const split::EdgeFwd
       }
       if (valid)
         *reinterpret_cast<float4*>(P.logits + e * 4) = make_float4(lg[0], lg[1], lg[2], lg[3]);
+      // the warp's rows of this stage are free: stage the tile two turns ahead, fetch the ids
+      // after it
+      __syncwarp();
+      stage_qk(wbase + st * kTileBytes, lane, id, P.q, P.ldq, P.k, P.ldk);
+      if (id.valid) {
+        const int nb = P.rowptr[id.rr], ne = P.rowptr[id.rr + 1];
+        if (st) { rb1 = nb; re1 = ne; } else { rb0 = nb; re0 = ne; }
+      }
+      id = load_ids(P.edge_row, P.col, t + 3 * stride, tiles, row, P.E);
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -288,7 +360,9 @@ constexpr uint32_t kGStage0 = kAStage0 + 64 * kAStages;    // G stage g: hi at +
 
 struct SmemBwd {
   static constexpr int ring_off = 0;
-  static constexpr int bhi_off = kRing * (int)kTileBytes;    // [Wq;Wk]   rows = outputs  (MMA 1)
+  static constexpr int qk_off = kRing * (int)kTileBytes;     // [2 groups][2 stages][128][q | k]
+  static constexpr int sp_off = qk_off + 4 * (int)kTileBytes;   // [2][2][128][dS 4 | P 4]
+  static constexpr int bhi_off = sp_off + 4 * kTileRows * 32;   // [Wq;Wk]   rows = outputs  (MMA 1)
   static constexpr int blo_off = bhi_off + kWBytes;
   static constexpr int thi_off = blo_off + kWBytes;          // [Wq;Wk]^T rows = features (MMA 2)
   static constexpr int tlo_off = thi_off + kWBytes;
@@ -314,7 +388,8 @@ __device__ __forceinline__ void stage_weights_t(unsigned char* thi, unsigned cha
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-k_edge_bwd_umma(const __grid_constant__ CUtensorMap tmA, const split::EdgeBwdArgs P) {
+k_edge_bwd_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmG,
+                const __grid_constant__ CUtensorMap tmD, const split::EdgeBwdArgs P) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem =
       (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -430,42 +505,75 @@ k_edge_bwd_umma(const __grid_constant__ CUtensorMap tmA, const split::EdgeBwdArg
   } else if (warp >= 4) {
     // ---------------- epilogue: thread = edge ----------------
     const int g = warp >= 12 ? 1 : 0;
-    const int q = warp & 3, row = q * 32 + lane;
+    const int q = warp & 3, row = q * 32 + lane, sw = row & 7;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    uint32_t tl = 0;
-    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++tl) {
-      if ((int)(tl & 1) != g) continue;
-      const uint32_t ph = (tl >> 1) & 1;
+    const uint32_t wbase = smem_u32(smem + L::qk_off) + (uint32_t)g * 2 * kTileBytes +
+                           (uint32_t)(q * 32) * 128u;      // my warp's rows in stage 0
+    const uint32_t my = wbase + (uint32_t)lane * 128u;
+    const uint32_t mysp = smem_u32(smem + L::sp_off) + (uint32_t)g * 2 * (kTileRows * 32) +
+                          (uint32_t)row * 32u;
+    const int64_t stride = 2 * (int64_t)gridDim.x;
+    const int64_t t0 = blockIdx.x + (int64_t)g * gridDim.x;
+    // per stage: extent of the source row (scale) and its id (dAbar row)
+    int rb0 = 0, re0 = 1, rb1 = 0, re1 = 1, rr0 = 0, rr1 = 0;
+    // stage = q / k rows (cooperative copy) + dS / P of my edge
+    auto stage_all = [&](uint32_t st, const EdgeIds& id, int64_t t) {
+      if (id.valid) {
+        const int64_t e = t * kTileRows + row;
+        cp_async16_cg(mysp + st * (kTileRows * 32), P.dS + e * 4);
+        if (P.d_abar) cp_async16_cg(mysp + st * (kTileRows * 32) + 16, P.Pbuf + e * 4);
+      }
+      stage_qk(wbase + st * kTileBytes, lane, id, P.q, P.ldq, P.k, P.ldk);   // commits the group
+    };
+    // 32 x 128-byte rows of my warp leave through one TMA store (clipped at E by the map)
+    auto store_rows = [&](const CUtensorMap* tm, uint32_t src_wbase, int64_t t) {
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::
+                         "l"(tm), "r"(src_wbase), "r"(0), "r"((int)(t * kTileRows + q * 32))
+                     : "memory");
+        bulk_commit();
+      }
+    };
+    auto rows_read = [&]() {          // the last store has read its rows
+      if (lane == 0) bulk_wait_read<0>();
+      __syncwarp();
+    };
+    EdgeIds id = load_ids(P.edge_row, P.col, t0, tiles, row, P.E);
+    stage_all(0, id, t0);
+    if (id.valid) { rb0 = P.rowptr[id.rr]; re0 = P.rowptr[id.rr + 1]; rr0 = id.rr; }
+    id = load_ids(P.edge_row, P.col, t0 + stride, tiles, row, P.E);
+    stage_all(1, id, t0 + stride);
+    if (id.valid) { rb1 = P.rowptr[id.rr]; re1 = P.rowptr[id.rr + 1]; rr1 = id.rr; }
+    id = load_ids(P.edge_row, P.col, t0 + 2 * stride, tiles, row, P.E);
+    uint32_t n = 0;
+    for (int64_t t = t0; t < tiles; t += stride, ++n) {
+      const uint32_t st = n & 1, ph = n & 1;
       const int64_t e = t * kTileRows + row;
       const bool valid = e < P.E;
-      float4 qv[4], kv[4];
-      float4 ds4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      float scale = 0.f;
-      int rr = 0;
-#pragma unroll
-      for (int h = 0; h < 4; ++h) qv[h] = kv[h] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid) {
-        rr = P.edge_row[e];
-        const int c = P.col[e];
-        const float4* qp = reinterpret_cast<const float4*>(P.q + (int64_t)rr * P.ldq);
-        const float4* kp = reinterpret_cast<const float4*>(P.k + (int64_t)c * P.ldk);
-#pragma unroll
-        for (int h = 0; h < 4; ++h) { qv[h] = __ldg(qp + h); kv[h] = __ldg(kp + h); }
-        ds4 = __ldg(reinterpret_cast<const float4*>(P.dS) + e);
-        scale = fast::qk_scale_fast(P.scale_mode, P.scale_value,
-                                    P.rowptr[rr + 1] - P.rowptr[rr]);
-      }
+      const float scale =
+          fast::qk_scale_fast(P.scale_mode, P.scale_value, st ? re1 - rb1 : re0 - rb0);
+      const int rr = st ? rr1 : rr0;
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      __syncwarp();
+      const uint32_t src = my + st * kTileBytes, ssp = mysp + st * (kTileRows * 32);
+      const uint32_t wsrc = wbase + st * kTileBytes;
       mbar_wait(&r_full[g], ph, 7);
       tc_fence_after();
       uint32_t R[32];
       tmem_ld32(tmem_base + g * kAccCols + lane_off, R);
-      // G_e = [dS k_e | dS q_e] (zero rows past E: dS = 0)
+      // G_e = [dS k_e | dS q_e] (rows past E: zeros)
       float G[32];
+      float4 ds4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) ds4 = lds128(ssp);
       const float dsv[4] = {ds4.x, ds4.y, ds4.z, ds4.w};
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
-        const float qs[4] = {qv[h].x, qv[h].y, qv[h].z, qv[h].w};
-        const float ks[4] = {kv[h].x, kv[h].y, kv[h].z, kv[h].w};
+        const float4 q4 = lds128(src + (uint32_t)((h ^ sw) << 4));
+        const float4 k4 = lds128(src + (uint32_t)(((4 + h) ^ sw) << 4));
+        const float qs[4] = {q4.x, q4.y, q4.z, q4.w};
+        const float ks[4] = {k4.x, k4.y, k4.z, k4.w};
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
           const float qe = fmaf(qs[d], scale, __uint_as_float(R[4 * h + d]) + bias_s[4 * h + d]);
@@ -474,23 +582,26 @@ k_edge_bwd_umma(const __grid_constant__ CUtensorMap tmA, const split::EdgeBwdArg
           G[16 + 4 * h + d] = dsv[h] * qe;
         }
       }
-      if (valid) {
-        float4* gp = reinterpret_cast<float4*>(P.G + e * 32);
+      // G leaves through my (now dead) q / k stage row: swizzled staging row + TMA store
+      __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          gp[j] = make_float4(G[4 * j], G[4 * j + 1], G[4 * j + 2], G[4 * j + 3]);
-      }
+      for (int j = 0; j < 8; ++j)
+        sts128(src + (uint32_t)((j ^ sw) << 4),
+               make_float4(G[4 * j], G[4 * j + 1], G[4 * j + 2], G[4 * j + 3]));
+      store_rows(&tmG, wsrc, t);
       if (P.da) {
-        uint32_t hi[32], lo[32];
+        {
+          uint32_t hi[32], lo[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float h = tf32_rna(G[j]);
-          hi[j] = __float_as_uint(h);
-          lo[j] = __float_as_uint(tf32_rna(G[j] - h));
+          for (int j = 0; j < 32; ++j) {
+            const float h = tf32_rna(G[j]);
+            hi[j] = __float_as_uint(h);
+            lo[j] = __float_as_uint(tf32_rna(G[j] - h));
+          }
+          const uint32_t tg = tmem_base + kGStage0 + 64 * g + lane_off;
+          tmem_st32(tg, hi);
+          tmem_st32(tg + 32, lo);
         }
-        const uint32_t tg = tmem_base + kGStage0 + 64 * g + lane_off;
-        tmem_st32(tg, hi);
-        tmem_st32(tg + 32, lo);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         mbar_arrive(&g_ready[g]);
@@ -499,7 +610,7 @@ k_edge_bwd_umma(const __grid_constant__ CUtensorMap tmA, const split::EdgeBwdArg
 #pragma unroll
         for (int f = 0; f < 32; ++f) da[f] = 0.f;
         if (valid && P.d_abar) {
-          const float4 p4 = __ldg(reinterpret_cast<const float4*>(P.Pbuf) + e);
+          const float4 p4 = lds128(ssp + 16);
           const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
           const float4* dab = reinterpret_cast<const float4*>(P.d_abar + (int64_t)rr * 128);
 #pragma unroll
@@ -519,18 +630,18 @@ k_edge_bwd_umma(const __grid_constant__ CUtensorMap tmA, const split::EdgeBwdArg
         tmem_ld32(tmem_base + g * kAccCols + lane_off, R);
         tc_fence_before();
         mbar_arrive(&acc_free[g]);
-        if (valid) {
-          float4* dp = reinterpret_cast<float4*>(P.da + e * 32);
+        rows_read();                      // the G store has read the stage rows
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            dp[j] = make_float4(da[4 * j] + __uint_as_float(R[4 * j]),
-                                da[4 * j + 1] + __uint_as_float(R[4 * j + 1]),
-                                da[4 * j + 2] + __uint_as_float(R[4 * j + 2]),
-                                da[4 * j + 3] + __uint_as_float(R[4 * j + 3]));
-        }
+        for (int j = 0; j < 8; ++j)
+          sts128(src + (uint32_t)((j ^ sw) << 4),
+                 make_float4(da[4 * j] + __uint_as_float(R[4 * j]),
+                             da[4 * j + 1] + __uint_as_float(R[4 * j + 1]),
+                             da[4 * j + 2] + __uint_as_float(R[4 * j + 2]),
+                             da[4 * j + 3] + __uint_as_float(R[4 * j + 3])));
+        store_rows(&tmD, wsrc, t);
       } else {
-        // no feature gradient wanted: the accumulator is free, MMA 2 still runs (on zeros) to
-        // keep the issue order of the MMA warp
+        // no feature gradient wanted: MMA 2 still runs (on zeros) to keep the issue order of
+        // the MMA warp
         uint32_t zero[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) zero[j] = 0u;
@@ -545,7 +656,18 @@ k_edge_bwd_umma(const __grid_constant__ CUtensorMap tmA, const split::EdgeBwdArg
         tc_fence_before();
         mbar_arrive(&acc_free[g]);
       }
+      // the stage rows are free once the last store has read them: stage the tile two turns
+      // ahead, fetch the ids after it
+      rows_read();
+      stage_all(st, id, t + 2 * stride);
+      if (id.valid) {
+        const int nb = P.rowptr[id.rr], ne = P.rowptr[id.rr + 1];
+        if (st) { rb1 = nb; re1 = ne; rr1 = id.rr; } else { rb0 = nb; re0 = ne; rr0 = id.rr; }
+      }
+      id = load_ids(P.edge_row, P.col, t + 3 * stride, tiles, row, P.E);
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (lane == 0) bulk_wait_read<0>();
   }
 
   tc_fence_before();
@@ -559,14 +681,17 @@ k_edge_bwd_umma(const __grid_constant__ CUtensorMap tmA, const split::EdgeBwdArg
 }
 
 inline bool edge_bwd_launch(const split::EdgeBwdArgs& A, cudaStream_t st, int* rc) {
-  CUtensorMap tm;
+  CUtensorMap tm, tmG, tmD;
   if (!umma::make_map_rows32(&tm, A.a, A.E, 32, kTileRows)) return false;
+  // output maps: one 32-row x 128-byte box per epilogue warp
+  if (!umma::make_map_rows32(&tmG, A.G, A.E, 32, 32)) return false;
+  if (!umma::make_map_rows32(&tmD, A.da ? A.da : A.G, A.E, 32, 32)) return false;
   const int smem = SmemBwd::total + 1024;
   static unsigned long long done = 0;
   ensure_dynamic_smem(k_edge_bwd_umma, smem, &done);
   const int64_t tiles = (A.E + kTileRows - 1) / kTileRows;
   const int64_t sms = device_sm_count();
-  k_edge_bwd_umma<<<(unsigned)(tiles < sms ? tiles : sms), kThreads, smem, st>>>(tm, A);
+  k_edge_bwd_umma<<<(unsigned)(tiles < sms ? tiles : sms), kThreads, smem, st>>>(tm, tmG, tmD, A);
   *rc = check_launch("attn_bwd_rows(edge, umma)");
   return true;
 }

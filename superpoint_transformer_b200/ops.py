@@ -905,7 +905,7 @@ class _AttnCore(torch.autograd.Function):
                                            _p(abar), _p(sump), _p(m), _p(z),
                                            ctypes.byref(ex) if ex is not None else None,
                                            _stream()), "spt_attn_fwd")
-        _count()
+        _count(2 if logits is not None else 1)        # edge pass + row pass, or one fused kernel
         ctx.g, ctx.H, ctx.D, ctx.Dv, ctx.F = g, H, D, Dv, F
         ctx.scale_mode, ctx.scale_value = scale_mode, scale_value
         ctx.fused = fused
@@ -1025,7 +1025,8 @@ class _AttnCore(torch.autograd.Function):
                     _p(g.csc_ptr), _p(g.csc_src), _p(g.csc2csr), g.num_targets, E, H, D, Dv,
                     _p(Pb), _p(G), _p(d_agg), dkp, lddk, dvp, lddv, _p(d_qt), _stream()),
                     "spt_attn_bwd_targets")
-            _count(2)
+            # rows (row pass + edge pass, or the fused kernel) + d[Wq;Wk] product + targets
+            _count(4 if (ex is not None and not has_ex) else 3)
         if bq is not None and dbq is None:
             dbq = torch.zeros_like(bq)
         if bk is not None and dbk is None:
