@@ -775,7 +775,9 @@ int spt_attn_bwd_rows_ex(const float* q, int64_t ldq, const float* k, int64_t ld
     B.Wk = Wk; B.bk = bk; B.scale_mode = scale_mode; B.scale_value = scale_value;
     B.m = m; B.z = z; B.agg_v = agg_v; B.abar = abar; B.d_agg_v = d_agg_v; B.d_abar = d_abar;
     B.dq = dq; B.lddq = (int)lddq; B.Pbuf = Pbuf; B.dS = ex->ws_ds;
-    const unsigned grid = (unsigned)ceil_div(num_rows, split::kRowWarps);
+    B.rows_per_warp = split_rows_per_warp(num_rows);
+    const unsigned grid =
+        (unsigned)ceil_div(num_rows, (int64_t)split::kRowWarps * B.rows_per_warp);
     const unsigned thr = split::kRowWarps * kWarp;
     const int rsm = split::kRowBwdSmem;
     static unsigned long long rdone[4] = {0, 0, 0, 0};

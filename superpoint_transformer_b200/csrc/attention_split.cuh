@@ -452,6 +452,7 @@ struct RowBwdArgs {
   float* dq; int lddq;
   float* Pbuf;                          // [E, 4] softmax weights (targets kernel, edge pass)
   float* dS;                            // [E, 4] gradient of the logits (natural units)
+  int rows_per_warp;                    // consecutive rows per warp, 1..16
 };
 
 __device__ __forceinline__ float hsum2f(f32x2 v) {
@@ -470,6 +471,31 @@ struct RowBwdTiles {
   float ds[32 * kH];       // dS of the chunk's (edge, head) pairs
 };
 
+// partial dot products <dY, v_t> (+ <dAbar, a_e>) of CNT edges e0.. : CNT gathered rows in flight
+template <int CNT, bool HAS_DAB>
+__device__ __forceinline__ void row_bwd_partials(float* s, int e0, int mycol, const char* vbase,
+                                                 unsigned ldvb, uint64_t keep,
+                                                 const ulonglong2* a_lane, f32x2 dy01, f32x2 dy23,
+                                                 f32x2 dab01, f32x2 dab23) {
+  ulonglong2 vv[CNT];
+#pragma unroll
+  for (int u = 0; u < CNT; ++u) {
+    const unsigned tc = (unsigned)__shfl_sync(kFull, mycol, e0 + u);
+    vv[u] = ldg_row16(vbase + (uint64_t)tc * (uint64_t)ldvb, keep);
+  }
+#pragma unroll
+  for (int u = 0; u < CNT; ++u) {
+    f32x2 acc = mul2(dy01, vv[u].x);
+    fma2(acc, dy23, vv[u].y);
+    if (HAS_DAB) {
+      const ulonglong2 a4 = a_lane[(e0 + u) * (kF / 4)];
+      fma2(acc, dab01, a4.x);
+      fma2(acc, dab23, a4.y);
+    }
+    s[u] = hsum2f(acc);
+  }
+}
+
 template <bool HAS_DAB, bool HAS_WK>
 __global__ void __launch_bounds__(kRowWarps * 32, kRowBwdCtas)
 k_row_bwd(const RowBwdArgs P) {
@@ -484,15 +510,24 @@ k_row_bwd(const RowBwdArgs P) {
   }
   constexpr bool NEED_A = HAS_DAB || HAS_WK;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * kRowWarps + w;
-  if (row >= P.num_rows) return;
+  const int R = P.rows_per_warp;
+  const int64_t r0 = ((int64_t)blockIdx.x * kRowWarps + w) * R;
+  if (r0 >= P.num_rows) return;
+  const int nrows = (int)min((int64_t)R, P.num_rows - r0);
   RowBwdTiles& S = tiles[w];
   const int hb = lane >> 3, j8 = lane & 7;
-  const int b = P.rowptr[row], e = P.rowptr[row + 1];
   const uint64_t keep = policy_evict_last(), stream = policy_evict_first();
-  if (NEED_A && e > b) stage_features(S.a, P.a, b, min(32, e - b), lane, stream);
   const char* vbase = reinterpret_cast<const char*>(P.v) + 16 * lane;
   const unsigned ldvb = (unsigned)P.ldv * 4u, ldkb = (unsigned)P.ldk * 4u;
+  const ulonglong2* a_lane = reinterpret_cast<const ulonglong2*>(S.a) + j8;
+  const int rp = P.rowptr[r0 + min(lane, nrows)];             // extents of my rows
+
+#pragma unroll 1
+  for (int ri = 0; ri < nrows; ++ri) {
+  const int64_t row = r0 + ri;
+  const int b = __shfl_sync(kFull, rp, ri), e = __shfl_sync(kFull, rp, ri + 1);
+  __syncwarp();                                    // the previous row's tiles have been read
+  if (NEED_A && e > b) stage_features(S.a, P.a, b, min(32, e - b), lane, stream);
 
   const float scale = fast::qk_scale_fast(P.scale_mode, P.scale_value, e - b);
   const float m2 = P.m[row * kH + hb] * kLog2e;
@@ -515,7 +550,6 @@ k_row_bwd(const RowBwdArgs P) {
   }
   const f32x2 dy01 = pack2(dy.x, dy.y), dy23 = pack2(dy.z, dy.w);
   const f32x2 dab01 = pack2(dab.x, dab.y), dab23 = pack2(dab.z, dab.w);
-  const ulonglong2* a_lane = reinterpret_cast<const ulonglong2*>(S.a) + j8;
 
   f32x2 T01 = 0ull, T23 = 0ull;
   float U = 0.f, SdS = 0.f;
@@ -523,8 +557,10 @@ k_row_bwd(const RowBwdArgs P) {
   for (int tb = b; tb < e; tb += 32) {
     const int n = min(32, e - tb);
     const int mycol = (lane < n) ? P.col[tb + lane] : 0;
-    __syncwarp();                                  // the previous chunk's tiles have been read
-    if (NEED_A && tb != b) stage_features(S.a, P.a, tb, n, lane, stream);
+    if (tb != b) {
+      __syncwarp();                                // the previous chunk's tiles have been read
+      if (NEED_A) stage_features(S.a, P.a, tb, n, lane, stream);
+    }
     {
       // gathered k rows -> S.k[slot][16]: lane copies chunk lane & 3 of the slots (lane >> 2) + 8 i
       const uint32_t dst = smem_addr(S.k) + 16 * (lane & 3);
@@ -547,26 +583,36 @@ k_row_bwd(const RowBwdArgs P) {
       const bool valid = j8 < cnt;
       const int64_t slot = (int64_t)(tb + e0 + j8) * kH + hb;
       const float lg = valid ? __ldg(P.logits + slot) : -INFINITY;
-      ulonglong2 vv[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        vv[u] = make_ulonglong2(0ull, 0ull);
-        if (u < cnt) {
-          const unsigned tc = (unsigned)__shfl_sync(kFull, mycol, e0 + u);
-          vv[u] = ldg_row16(vbase + (uint64_t)tc * (uint64_t)ldvb, keep);
-        }
-      }
       float s[8];
+      if (cnt == 8) {
+        row_bwd_partials<8, HAS_DAB>(s, e0, mycol, vbase, ldvb, keep, a_lane, dy01, dy23, dab01,
+                                     dab23);
+      } else {
+        // short last group: 4 + 2 + 1 rows, no wasted gathers
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        f32x2 acc = mul2(dy01, vv[u].x);
-        fma2(acc, dy23, vv[u].y);
-        if (HAS_DAB && u < cnt) {
-          const ulonglong2 a4 = a_lane[(e0 + u) * (kF / 4)];
-          fma2(acc, dab01, a4.x);
-          fma2(acc, dab23, a4.y);
+        for (int u = 0; u < 8; ++u) s[u] = 0.f;
+        int o = 0;
+        if (cnt & 4) {
+          float s4[4];
+          row_bwd_partials<4, HAS_DAB>(s4, e0, mycol, vbase, ldvb, keep, a_lane, dy01, dy23,
+                                       dab01, dab23);
+          s[0] = s4[0]; s[1] = s4[1]; s[2] = s4[2]; s[3] = s4[3];
+          o = 4;
         }
-        s[u] = hsum2f(acc);
+        if (cnt & 2) {
+          float s2[2];
+          row_bwd_partials<2, HAS_DAB>(s2, e0 + o, mycol, vbase, ldvb, keep, a_lane, dy01, dy23,
+                                       dab01, dab23);
+          if (o) { s[4] = s2[0]; s[5] = s2[1]; } else { s[0] = s2[0]; s[1] = s2[1]; }
+          o += 2;
+        }
+        if (cnt & 1) {
+          float s1[1];
+          row_bwd_partials<1, HAS_DAB>(s1, e0 + o, mycol, vbase, ldvb, keep, a_lane, dy01, dy23,
+                                       dab01, dab23);
+          if (o == 0) s[0] = s1[0]; else if (o == 2) s[2] = s1[0];
+          else if (o == 4) s[4] = s1[0]; else s[6] = s1[0];
+        }
       }
       const float dp = butterfly8(s, j8);                 // edge e0 + j8, head hb
       const float p = ex2(lg - m2) * zi;                   // 0 past the end of the row
@@ -617,9 +663,9 @@ k_row_bwd(const RowBwdArgs P) {
     }
     // 4 partial sums over the 8 lanes of the head: lane ends with dim 2 * bit2 + bit1
     const bool b4 = j8 & 4, b2 = j8 & 2;
-    float r0 = (b4 ? pd[2] : pd[0]) + __shfl_xor_sync(kFull, b4 ? pd[0] : pd[2], 4);
-    float r1 = (b4 ? pd[3] : pd[1]) + __shfl_xor_sync(kFull, b4 ? pd[1] : pd[3], 4);
-    float r = (b2 ? r1 : r0) + __shfl_xor_sync(kFull, b2 ? r0 : r1, 2);
+    float r0s = (b4 ? pd[2] : pd[0]) + __shfl_xor_sync(kFull, b4 ? pd[0] : pd[2], 4);
+    float r1s = (b4 ? pd[3] : pd[1]) + __shfl_xor_sync(kFull, b4 ? pd[1] : pd[3], 4);
+    float r = (b2 ? r1s : r0s) + __shfl_xor_sync(kFull, b2 ? r0s : r1s, 2);
     r += __shfl_xor_sync(kFull, r, 1);
     const int d = (b4 ? 2 : 0) + (b2 ? 1 : 0);
     const float Ud = __shfl_sync(kFull, U, (lane & 24) | d);
@@ -628,6 +674,7 @@ k_row_bwd(const RowBwdArgs P) {
   } else {
     if (j8 < 4) P.dq[row * P.lddq + hb * kD + j8] = scale * U;
   }
+  }   // rows of the warp
 }
 
 constexpr int kRowBwdSmem = kRowWarps * (int)sizeof(RowBwdTiles) + (kHD * kF + kHD) * 4;

@@ -38,7 +38,8 @@ constexpr int kWBytes = 32 * 32 * 4;           // one pre-split weight matrix
 struct Smem {
   static constexpr int ring_off = 0;
   static constexpr int qk_off = kRing * (int)kTileBytes;     // [2 groups][2 stages][128][q 16 | k 16]
-  static constexpr int bhi_off = qk_off + 4 * (int)kTileBytes;
+  static constexpr int ext_off = qk_off + 4 * (int)kTileBytes;  // [2][2][128][rowptr[s], rowptr[s+1], s, -]
+  static constexpr int bhi_off = ext_off + 4 * kTileRows * 16;
   static constexpr int blo_off = bhi_off + kWBytes;
   static constexpr int bias_off = blo_off + kWBytes;
   static constexpr int bar_off = bias_off + 128;
@@ -96,6 +97,23 @@ __device__ __forceinline__ void stage_qk(uint32_t wbase, int lane, const EdgeIds
     }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// extent of my edge's source row (-> q scale) and its id, parked in shared memory: nothing in
+// registers waits on these loads until the tile is processed two turns later
+__device__ __forceinline__ void stage_extent(uint32_t dst, const EdgeIds& id, const int32_t* rowptr) {
+  if (id.valid) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(rowptr + id.rr) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4), "l"(rowptr + id.rr + 1)
+                 : "memory");
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + 8), "r"(id.rr) : "memory");
+  }
+}
+__device__ __forceinline__ int4 lds_extent(uint32_t src) {
+  int4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src) : "memory");
+  return v;
 }
 
 __device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* tm, int c0, int c1,
@@ -264,25 +282,25 @@ k_edge_logits_umma(const __grid_constant__ CUtensorMap tmA, const split::EdgeFwd
     const uint32_t my = wbase + (uint32_t)lane * 128u;
     const int64_t stride = 2 * (int64_t)gridDim.x;
     const int64_t t0 = blockIdx.x + (int64_t)g * gridDim.x;
-    // extent of the source row of the tiles staged in stages 0 / 1 (raw loads: nothing waits on
-    // them until the tile is processed)
-    int rb0 = 0, re0 = 1, rb1 = 0, re1 = 1;
+    const uint32_t myext = smem_u32(smem + Smem::ext_off) + (uint32_t)g * 2 * (kTileRows * 16) +
+                           (uint32_t)row * 16u;
     EdgeIds id = load_ids(P.edge_row, P.col, t0, tiles, row, P.E);
+    stage_extent(myext, id, P.rowptr);
     stage_qk(wbase, lane, id, P.q, P.ldq, P.k, P.ldk);
-    if (id.valid) { rb0 = P.rowptr[id.rr]; re0 = P.rowptr[id.rr + 1]; }
     id = load_ids(P.edge_row, P.col, t0 + stride, tiles, row, P.E);
+    stage_extent(myext + kTileRows * 16, id, P.rowptr);
     stage_qk(wbase + kTileBytes, lane, id, P.q, P.ldq, P.k, P.ldk);
-    if (id.valid) { rb1 = P.rowptr[id.rr]; re1 = P.rowptr[id.rr + 1]; }
     id = load_ids(P.edge_row, P.col, t0 + 2 * stride, tiles, row, P.E);
     uint32_t n = 0;
     for (int64_t t = t0; t < tiles; t += stride, ++n) {
       const uint32_t st = n & 1;
       const int64_t e = t * kTileRows + row;
       const bool valid = e < P.E;
-      const float scale =
-          fast::qk_scale_fast(P.scale_mode, P.scale_value, st ? re1 - rb1 : re0 - rb0);
       asm volatile("cp.async.wait_group 1;" ::: "memory");   // this tile's rows have landed
       __syncwarp();                                          // (copied by my warp's lanes)
+      const int4 ext = lds_extent(myext + st * (kTileRows * 16));
+      const float scale =
+          fast::qk_scale_fast(P.scale_mode, P.scale_value, valid ? ext.y - ext.x : 1);
       mbar_wait(&tmem_full[g], n & 1, 7);
       tc_fence_after();
       uint32_t R[32];
@@ -311,11 +329,8 @@ k_edge_logits_umma(const __grid_constant__ CUtensorMap tmA, const split::EdgeFwd
       // the warp's rows of this stage are free: stage the tile two turns ahead, fetch the ids
       // after it
       __syncwarp();
+      stage_extent(myext + st * (kTileRows * 16), id, P.rowptr);
       stage_qk(wbase + st * kTileBytes, lane, id, P.q, P.ldq, P.k, P.ldk);
-      if (id.valid) {
-        const int nb = P.rowptr[id.rr], ne = P.rowptr[id.rr + 1];
-        if (st) { rb1 = nb; re1 = ne; } else { rb0 = nb; re0 = ne; }
-      }
       id = load_ids(P.edge_row, P.col, t + 3 * stride, tiles, row, P.E);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -362,7 +377,8 @@ struct SmemBwd {
   static constexpr int ring_off = 0;
   static constexpr int qk_off = kRing * (int)kTileBytes;     // [2 groups][2 stages][128][q | k]
   static constexpr int sp_off = qk_off + 4 * (int)kTileBytes;   // [2][2][128][dS 4 | P 4]
-  static constexpr int bhi_off = sp_off + 4 * kTileRows * 32;   // [Wq;Wk]   rows = outputs  (MMA 1)
+  static constexpr int ext_off = sp_off + 4 * kTileRows * 32;   // [2][2][128][rowptr[s], rowptr[s+1], s, -]
+  static constexpr int bhi_off = ext_off + 4 * kTileRows * 16;  // [Wq;Wk]   rows = outputs  (MMA 1)
   static constexpr int blo_off = bhi_off + kWBytes;
   static constexpr int thi_off = blo_off + kWBytes;          // [Wq;Wk]^T rows = features (MMA 2)
   static constexpr int tlo_off = thi_off + kWBytes;
@@ -514,15 +530,23 @@ k_edge_bwd_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                           (uint32_t)row * 32u;
     const int64_t stride = 2 * (int64_t)gridDim.x;
     const int64_t t0 = blockIdx.x + (int64_t)g * gridDim.x;
-    // per stage: extent of the source row (scale) and its id (dAbar row)
-    int rb0 = 0, re0 = 1, rb1 = 0, re1 = 1, rr0 = 0, rr1 = 0;
-    // stage = q / k rows (cooperative copy) + dS / P of my edge
+    const uint32_t myext = smem_u32(smem + L::ext_off) + (uint32_t)g * 2 * (kTileRows * 16) +
+                           (uint32_t)row * 16u;
+    // stage = q / k rows (cooperative copy) + dS / P and the row extent / id of my edge; the
+    // dAbar row of the edge is pulled into the L2 on the way
     auto stage_all = [&](uint32_t st, const EdgeIds& id, int64_t t) {
       if (id.valid) {
         const int64_t e = t * kTileRows + row;
         cp_async16_cg(mysp + st * (kTileRows * 32), P.dS + e * 4);
-        if (P.d_abar) cp_async16_cg(mysp + st * (kTileRows * 32) + 16, P.Pbuf + e * 4);
+        if (P.d_abar) {
+          cp_async16_cg(mysp + st * (kTileRows * 32) + 16, P.Pbuf + e * 4);
+          const char* dab = reinterpret_cast<const char*>(P.d_abar + (int64_t)id.rr * 128);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(dab + 128 * j) : "memory");
+        }
       }
+      stage_extent(myext + st * (kTileRows * 16), id, P.rowptr);
       stage_qk(wbase + st * kTileBytes, lane, id, P.q, P.ldq, P.k, P.ldk);   // commits the group
     };
     // 32 x 128-byte rows of my warp leave through one TMA store (clipped at E by the map)
@@ -542,21 +566,20 @@ k_edge_bwd_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     };
     EdgeIds id = load_ids(P.edge_row, P.col, t0, tiles, row, P.E);
     stage_all(0, id, t0);
-    if (id.valid) { rb0 = P.rowptr[id.rr]; re0 = P.rowptr[id.rr + 1]; rr0 = id.rr; }
     id = load_ids(P.edge_row, P.col, t0 + stride, tiles, row, P.E);
     stage_all(1, id, t0 + stride);
-    if (id.valid) { rb1 = P.rowptr[id.rr]; re1 = P.rowptr[id.rr + 1]; rr1 = id.rr; }
     id = load_ids(P.edge_row, P.col, t0 + 2 * stride, tiles, row, P.E);
     uint32_t n = 0;
     for (int64_t t = t0; t < tiles; t += stride, ++n) {
       const uint32_t st = n & 1, ph = n & 1;
       const int64_t e = t * kTileRows + row;
       const bool valid = e < P.E;
-      const float scale =
-          fast::qk_scale_fast(P.scale_mode, P.scale_value, st ? re1 - rb1 : re0 - rb0);
-      const int rr = st ? rr1 : rr0;
       asm volatile("cp.async.wait_group 1;" ::: "memory");
       __syncwarp();
+      const int4 ext = lds_extent(myext + st * (kTileRows * 16));
+      const float scale =
+          fast::qk_scale_fast(P.scale_mode, P.scale_value, valid ? ext.y - ext.x : 1);
+      const int rr = valid ? ext.z : 0;
       const uint32_t src = my + st * kTileBytes, ssp = mysp + st * (kTileRows * 32);
       const uint32_t wsrc = wbase + st * kTileBytes;
       mbar_wait(&r_full[g], ph, 7);
@@ -660,10 +683,6 @@ k_edge_bwd_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // ahead, fetch the ids after it
       rows_read();
       stage_all(st, id, t + 2 * stride);
-      if (id.valid) {
-        const int nb = P.rowptr[id.rr], ne = P.rowptr[id.rr + 1];
-        if (st) { rb1 = nb; re1 = ne; rr1 = id.rr; } else { rb0 = nb; re0 = ne; rr0 = id.rr; }
-      }
       id = load_ids(P.edge_row, P.col, t + 3 * stride, tiles, row, P.E);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
