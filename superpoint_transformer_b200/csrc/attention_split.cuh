@@ -193,12 +193,12 @@ constexpr int kRowWarps = 8;
 // registers, overlaps the softmax and the v gathers), so all the registers of the 8-deep batches
 // go to the gathered v rows; 24-32 resident warps per SM.
 #ifndef SPT_ROW_FWD_CTAS
-#define SPT_ROW_FWD_CTAS 4
+#define SPT_ROW_FWD_CTAS 3
 #endif
 #ifndef SPT_ROW_BWD_CTAS
 #define SPT_ROW_BWD_CTAS 3
 #endif
-constexpr int kRowFwdCtas = SPT_ROW_FWD_CTAS;   // 32 warps per SM at <= 64 registers
+constexpr int kRowFwdCtas = SPT_ROW_FWD_CTAS;   // 24 warps per SM at <= 85 registers (4 CTAs: spills, 0.148 vs 0.137 ms)
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -250,6 +250,37 @@ __device__ __forceinline__ void row_accumulate_v(int e0, int mycol, const char* 
   }
 }
 
+// the same with the staged feature rows consumed in the same pass (SPT_ROW_FWD_FUSED)
+template <int CNT, bool ABAR>
+__device__ __forceinline__ void row_accumulate_va(int e0, int mycol, const char* vbase,
+                                                  unsigned ldvb, uint64_t keep,
+                                                  const float* p_lane, const ulonglong2* a_lane,
+                                                  bool wait_a, f32x2& accv01, f32x2& accv23,
+                                                  f32x2& acca01, f32x2& acca23) {
+  ulonglong2 vv[CNT];
+#pragma unroll
+  for (int u = 0; u < CNT; ++u) {
+    const unsigned tc = (unsigned)__shfl_sync(kFull, mycol, e0 + u);
+    vv[u] = ldg_row16(vbase + (uint64_t)tc * (uint64_t)ldvb, keep);
+  }
+  if (ABAR && wait_a) {
+    cp_async_wait_all();
+    __syncwarp();
+  }
+#pragma unroll
+  for (int u = 0; u < CNT; ++u) {
+    const float p = p_lane[(e0 + u) * kH];
+    const f32x2 pp = pack2(p, p);
+    if (ABAR) {
+      const ulonglong2 a4 = a_lane[(e0 + u) * (kF / 4)];
+      fma2(acca01, pp, a4.x);
+      fma2(acca23, pp, a4.y);
+    }
+    fma2(accv01, pp, vv[u].x);
+    fma2(accv23, pp, vv[u].y);
+  }
+}
+
 // one chunk of <= 32 edges of a row: p tile, sum of p, weighted accumulation
 template <bool ABAR>
 __device__ __forceinline__ void row_fwd_chunk(int n, float4 lg, float4 mx, int mycol, int lane,
@@ -267,6 +298,33 @@ __device__ __forceinline__ void row_fwd_chunk(int n, float4 lg, float4 mx, int m
   const uint64_t keep = policy_evict_last();
   const float* p_lane = p_s + (lane >> 3);
   int e0 = 0;
+#ifdef SPT_ROW_FWD_FUSED
+  // v rows and staged feature rows consumed together (one read of p per edge); the wait for the
+  // staged rows sits behind the first batch of gathers
+  const ulonglong2* a_lane = reinterpret_cast<const ulonglong2*>(a_s) + (lane & 7);
+  bool first = ABAR;
+#pragma unroll 1
+  for (; e0 + 8 <= n; e0 += 8) {
+    row_accumulate_va<8, ABAR>(e0, mycol, vbase, ldvb, keep, p_lane, a_lane, first, accv01, accv23,
+                               acca01, acca23);
+    first = false;
+  }
+  if (n & 4) {
+    row_accumulate_va<4, ABAR>(e0, mycol, vbase, ldvb, keep, p_lane, a_lane, first, accv01, accv23,
+                               acca01, acca23);
+    first = false;
+    e0 += 4;
+  }
+  if (n & 2) {
+    row_accumulate_va<2, ABAR>(e0, mycol, vbase, ldvb, keep, p_lane, a_lane, first, accv01, accv23,
+                               acca01, acca23);
+    first = false;
+    e0 += 2;
+  }
+  if (n & 1)
+    row_accumulate_va<1, ABAR>(e0, mycol, vbase, ldvb, keep, p_lane, a_lane, first, accv01, accv23,
+                               acca01, acca23);
+#else
 #pragma unroll 1
   for (; e0 + 8 <= n; e0 += 8)
     row_accumulate_v<8>(e0, mycol, vbase, ldvb, keep, p_lane, accv01, accv23);
@@ -293,6 +351,7 @@ __device__ __forceinline__ void row_fwd_chunk(int n, float4 lg, float4 mx, int m
       fma2(acca23, pp, a4.y);
     }
   }
+#endif
 }
 
 // per-warp shared memory of the forward row pass
