@@ -240,8 +240,10 @@ int spt_unitsphere_fwd(const float* pos, const int64_t* parent /*nullable*/,
  * ------------------------------------------------------------------------- */
 
 /* y = weight * (x - mean_scale*mean[b]) * rstd[b] + bias, per graph b=batch[i].
- * batch==NULL -> single graph.  batch need not be sorted.  Outputs mean/rstd
- * [B, C] are saved for backward.  */
+ * batch==NULL -> single graph; with B == 1 `batch` is not read (every row is graph 0).
+ * batch need not be sorted.  Outputs mean/rstd [B, C] are saved for backward.
+ * Launches: memset + statistics + (finalise fused into) apply; backward: memset + statistics
+ * + (coefficients and parameter gradients fused into) apply, when C % 4 == 0 and B*C <= 2048. */
 size_t spt_graphnorm_workspace_bytes(int64_t B, int64_t C);
 int spt_graphnorm_fwd(const float* x, const int64_t* batch /*nullable*/,
                       int64_t N, int64_t C, int64_t B, const float* weight,

@@ -13,6 +13,7 @@
 // unsorted (edge-level norms use norm_index[edge_index[0]], src/models/components/
 // spt.py:829-835): threads flush whenever the segment id of their row changes.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace spt {
 
@@ -46,7 +47,8 @@ k_graphnorm_stats(const float* __restrict__ x, const float* __restrict__ dy,
                   const double* __restrict__ sum_x, const double* __restrict__ count,
                   const float* __restrict__ mean, const float* __restrict__ rstd,
                   double* __restrict__ acc0 /*[B,C]*/, double* __restrict__ acc1 /*[B,C]*/,
-                  double* __restrict__ cnt_out /*[B]*/, int tx, int ty, int slab_rows) {
+                  double* __restrict__ cnt_out /*[B]*/, int tx, int ty, int slab_rows,
+                  float* __restrict__ pivot_out = nullptr, int pivot_rows = 0) {
   constexpr int NACC = (MODE >= 2) ? 2 : 1;
   __shared__ float red[NACC][kNormThreads * VEC];
   int cx = threadIdx.x % tx;
@@ -67,6 +69,38 @@ k_graphnorm_stats(const float* __restrict__ x, const float* __restrict__ dy,
       mu[v] = 0.f;
       rs[v] = 1.f;
       ms[v] = (MODE != 0 && active) ? (mean_scale ? mean_scale[c0 + v] : 1.f) : 0.f;
+    }
+    if (MODE == 3 && pivot_out) {
+      // the per-channel pivot (mean of the first rows) computed by every CTA for itself — the
+      // same loads in the same order everywhere, so all CTAs hold identical bits — instead of
+      // a single-CTA kernel in front of this one; CTA 0 publishes it for the finalisation
+      float part[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) part[v] = 0.f;
+      if (active) {
+        for (int r = ry; r < pivot_rows; r += ty) {
+          if (VEC == 4) {
+            const float4 t = *reinterpret_cast<const float4*>(x + (int64_t)r * C + c0);
+            part[0] += t.x; part[1 % VEC] += t.y; part[2 % VEC] += t.z; part[3 % VEC] += t.w;
+          } else {
+            part[0] += x[(int64_t)r * C + c0];
+          }
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) red[0][threadIdx.x * VEC + v] = part[v];
+      __syncthreads();
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        float t = 0.f;
+        for (int yy = 0; yy < ty; ++yy) t += red[0][(yy * tx + cx) * VEC + v];
+        ms[v] = active ? t / (float)pivot_rows : 0.f;
+      }
+      __syncthreads();
+      if (blockIdx.x == 0 && ry == 0 && active) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) pivot_out[c0 + v] = ms[v];
+      }
     }
     int64_t cur = -1;
     int nrows = 0;
@@ -363,6 +397,205 @@ k_graphnorm_bwd_apply(const float* __restrict__ x, const float* __restrict__ dy,
 
 
 // ---------------------------------------------------------------------------------------
+// Fused finalise + apply (round 2).  The element-wise passes above spend ~25 loads and a 64-bit
+// division per 16 bytes of data (per-element parameter lookups), and each norm paid two
+// single-CTA kernels (finalise / coefficients) of ~4 us.  Here every CTA first builds the
+// [B, C] coefficient table in shared memory from the fp64 sums (a few hundred values), then
+// threads with FIXED columns stream their slab of rows: one FMA chain per element, 4 rows in
+// flight per thread, no divisions.  Used when B*C <= kNormTableMax and C % 4 == 0.
+// ---------------------------------------------------------------------------------------
+constexpr int kNormTableMax = 2048;
+
+// y = (x - M) * A + Bb  (then the fused LeakyReLU);  M = mean_scale*mean, A = weight*rstd
+__global__ void __launch_bounds__(kNormThreads)
+k_graphnorm_apply_fused(const float* __restrict__ x, const int64_t* __restrict__ batch,
+                        int64_t N, int C, int B, const float* __restrict__ weight,
+                        const float* __restrict__ bias, const float* __restrict__ mean_scale,
+                        const double* __restrict__ s1, const double* __restrict__ s2,
+                        const double* __restrict__ count, const float* __restrict__ pivot,
+                        float eps, float slope, float* __restrict__ y,
+                        float* __restrict__ mean_out, float* __restrict__ rstd_out, int tx,
+                        int ty, int slab_rows) {
+  extern __shared__ __align__(16) float norm_tab[];
+  float* tM = norm_tab;
+  float* tA = norm_tab + B * C;
+  float* tB = norm_tab + 2 * B * C;
+  for (int i = threadIdx.x; i < B * C; i += kNormThreads) {
+    const int b = i / C, c = i - b * C;
+    const double n = fmax(count[b], 1.0);
+    const double p = pivot[c], m1 = s1[i] / n, m2 = s2[i] / n;
+    const double mu = p + m1;
+    const double ms = mean_scale[c];
+    const double q = p - ms * mu;
+    const double var = fmax(m2 + 2.0 * q * m1 + q * q, 0.0);
+    const float rs = (float)(1.0 / sqrt(var + (double)eps));
+    const float muf = (float)mu;
+    tM[i] = (float)ms * muf;
+    tA[i] = (weight ? weight[c] : 1.f) * rs;
+    tB[i] = bias ? bias[c] : 0.f;
+    if (blockIdx.x == 0) { mean_out[i] = muf; rstd_out[i] = rs; }
+  }
+  __syncthreads();
+  const int cx = threadIdx.x % tx, ry = threadIdx.x / tx;
+  const int64_t nslabs = (N + slab_rows - 1) / slab_rows;
+  constexpr int U = 4;
+  for (int ct = 0; ct < C; ct += tx * 4) {
+    const int c0 = ct + cx * 4;
+    if (c0 >= C) continue;
+    float4 M0, A0, B0;   // B == 1: the coefficients live in registers
+    if (B == 1) {
+      M0 = *reinterpret_cast<const float4*>(tM + c0);
+      A0 = *reinterpret_cast<const float4*>(tA + c0);
+      B0 = *reinterpret_cast<const float4*>(tB + c0);
+    }
+    for (int64_t slab = blockIdx.x; slab < nslabs; slab += gridDim.x) {
+      const int64_t r0 = slab * slab_rows, r1 = min(r0 + (int64_t)slab_rows, N);
+      for (int64_t rb = r0 + ry; rb < r1; rb += (int64_t)ty * U) {
+        float4 xq[U];
+        int bq[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t r = rb + (int64_t)u * ty;
+          bq[u] = -1;
+          if (r < r1) {
+            bq[u] = batch ? (int)batch[r] : 0;
+            xq[u] = *reinterpret_cast<const float4*>(x + r * C + c0);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int b = bq[u];
+          if (b < 0 || b >= B) continue;
+          float4 M = M0, A = A0, Bb = B0;
+          if (B != 1) {
+            M = *reinterpret_cast<const float4*>(tM + b * C + c0);
+            A = *reinterpret_cast<const float4*>(tA + b * C + c0);
+            Bb = *reinterpret_cast<const float4*>(tB + b * C + c0);
+          }
+          float4 o;
+          o.x = fmaf(xq[u].x - M.x, A.x, Bb.x); o.y = fmaf(xq[u].y - M.y, A.y, Bb.y);
+          o.z = fmaf(xq[u].z - M.z, A.z, Bb.z); o.w = fmaf(xq[u].w - M.w, A.w, Bb.w);
+          o.x = o.x > 0.f ? o.x : o.x * slope; o.y = o.y > 0.f ? o.y : o.y * slope;
+          o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
+          *reinterpret_cast<float4*>(y + (rb + (int64_t)u * ty) * C + c0) = o;
+        }
+      }
+    }
+  }
+}
+
+// dx = k1 * g - k2 * xhat - k3,  xhat = (x - M) * rs,  g = dy * act'(y)   (see k_graphnorm_bwd_coef)
+__global__ void __launch_bounds__(kNormThreads)
+k_graphnorm_bwd_apply_fused(const float* __restrict__ x, const float* __restrict__ dy,
+                            const int64_t* __restrict__ batch, int64_t N, int C, int B,
+                            const float* __restrict__ weight,
+                            const float* __restrict__ mean_scale, const float* __restrict__ mean,
+                            const float* __restrict__ rstd, const double* __restrict__ s1,
+                            const double* __restrict__ s2, const double* __restrict__ count,
+                            const float* __restrict__ yact, float slope, float* __restrict__ dx,
+                            float* __restrict__ dweight, float* __restrict__ dbias,
+                            float* __restrict__ dmean_scale, int tx, int ty, int slab_rows) {
+  extern __shared__ __align__(16) float norm_tab[];
+  float* tM = norm_tab;                 // mean_scale * mean
+  float* tR = norm_tab + B * C;         // rstd
+  float* t1 = norm_tab + 2 * B * C;     // k1
+  float* t2 = norm_tab + 3 * B * C;     // k2
+  float* t3 = norm_tab + 4 * B * C;     // k3
+  for (int i = threadIdx.x; i < B * C; i += kNormThreads) {
+    const int b = i / C, c = i - b * C;
+    const double w = weight ? (double)weight[c] : 1.0;
+    const double ms = mean_scale[c];
+    const double n = fmax(count[b], 1.0);
+    const double S1 = s1[i], S2 = s2[i], rs = rstd[i], mu = mean[i];
+    const double T = rs * w * (S2 - S1 * rs * (1.0 - ms) * mu);
+    tM[i] = mean_scale[c] * mean[i];
+    tR[i] = rstd[i];
+    t1[i] = (float)(w * rs);
+    t2[i] = (float)(w * rs * S1 / n);
+    t3[i] = (float)(ms * T / n);
+  }
+  if (blockIdx.x == 0 && (dweight || dbias || dmean_scale)) {
+    // parameter gradients: one thread per column, sums over the graphs of the batch
+    for (int c = threadIdx.x; c < C; c += kNormThreads) {
+      const double w = weight ? (double)weight[c] : 1.0;
+      const double ms = mean_scale[c];
+      double dw = 0, db = 0, dms = 0;
+      for (int b = 0; b < B; ++b) {
+        const double S1 = s1[b * C + c], S2 = s2[b * C + c];
+        const double rs = rstd[b * C + c], mu = mean[b * C + c];
+        const double T = rs * w * (S2 - S1 * rs * (1.0 - ms) * mu);
+        dw += S1;
+        db += S2;
+        dms -= mu * T;
+      }
+      if (dweight) dweight[c] = (float)dw;
+      if (dbias) dbias[c] = (float)db;
+      if (dmean_scale) dmean_scale[c] = (float)dms;
+    }
+  }
+  __syncthreads();
+  const int cx = threadIdx.x % tx, ry = threadIdx.x / tx;
+  const int64_t nslabs = (N + slab_rows - 1) / slab_rows;
+  constexpr int U = 4;
+  for (int ct = 0; ct < C; ct += tx * 4) {
+    const int c0 = ct + cx * 4;
+    if (c0 >= C) continue;
+    float4 M0, R0, K1, K2, K3;
+    if (B == 1) {
+      M0 = *reinterpret_cast<const float4*>(tM + c0);
+      R0 = *reinterpret_cast<const float4*>(tR + c0);
+      K1 = *reinterpret_cast<const float4*>(t1 + c0);
+      K2 = *reinterpret_cast<const float4*>(t2 + c0);
+      K3 = *reinterpret_cast<const float4*>(t3 + c0);
+    }
+    for (int64_t slab = blockIdx.x; slab < nslabs; slab += gridDim.x) {
+      const int64_t r0 = slab * slab_rows, r1 = min(r0 + (int64_t)slab_rows, N);
+      for (int64_t rb = r0 + ry; rb < r1; rb += (int64_t)ty * U) {
+        float4 xq[U], gq[U];
+        int bq[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t r = rb + (int64_t)u * ty;
+          bq[u] = -1;
+          if (r < r1) {
+            bq[u] = batch ? (int)batch[r] : 0;
+            xq[u] = *reinterpret_cast<const float4*>(x + r * C + c0);
+            gq[u] = *reinterpret_cast<const float4*>(dy + r * C + c0);
+            if (yact) {
+              const float4 yy = *reinterpret_cast<const float4*>(yact + r * C + c0);
+              gq[u].x *= (yy.x > 0.f) ? 1.f : slope; gq[u].y *= (yy.y > 0.f) ? 1.f : slope;
+              gq[u].z *= (yy.z > 0.f) ? 1.f : slope; gq[u].w *= (yy.w > 0.f) ? 1.f : slope;
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int b = bq[u];
+          if (rb + (int64_t)u * ty >= r1) continue;   // past the slab
+          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (b >= 0 && b < B) {
+            float4 M = M0, R = R0, k1 = K1, k2 = K2, k3 = K3;
+            if (B != 1) {
+              M = *reinterpret_cast<const float4*>(tM + b * C + c0);
+              R = *reinterpret_cast<const float4*>(tR + b * C + c0);
+              k1 = *reinterpret_cast<const float4*>(t1 + b * C + c0);
+              k2 = *reinterpret_cast<const float4*>(t2 + b * C + c0);
+              k3 = *reinterpret_cast<const float4*>(t3 + b * C + c0);
+            }
+            o.x = k1.x * gq[u].x - k2.x * ((xq[u].x - M.x) * R.x) - k3.x;
+            o.y = k1.y * gq[u].y - k2.y * ((xq[u].y - M.y) * R.y) - k3.y;
+            o.z = k1.z * gq[u].z - k2.z * ((xq[u].z - M.z) * R.z) - k3.z;
+            o.w = k1.w * gq[u].w - k2.w * ((xq[u].w - M.w) * R.w) - k3.w;
+          }
+          *reinterpret_cast<float4*>(dx + (rb + (int64_t)u * ty) * C + c0) = o;
+        }
+      }
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------
 // Graph-wise GroupNorm / LayerNorm(mode='graph'): statistics per (graph b, channel group g)
 // over nodes x group channels (reference src/nn/norm.py:181-218; PyG LayerNorm 'graph' is
 // the num_groups = 1 case).  The N x C passes are the GraphNorm kernels above run with
@@ -454,6 +687,17 @@ static inline int norm_slab_rows(int64_t N, int ty) {
   return (int)want;
 }
 
+// element-wise passes: contiguous slabs too (coalesced streams per CTA), ~8 CTAs per SM
+static inline int norm_slab_rows_apply(int64_t N, int ty) {
+  const int64_t per_iter = (int64_t)ty * 4;
+  const int64_t ctas = (int64_t)device_sm_count() * 8;
+  int64_t want = (N + ctas - 1) / ctas;
+  want = (want + per_iter - 1) / per_iter * per_iter;
+  if (want < per_iter) want = per_iter;
+  if (want > (1 << 22)) want = (1 << 22);
+  return (int)want;
+}
+
 static inline ColMap col_map(int64_t C, int vec) {
   int64_t cols = C / vec;
   int tx = 1;
@@ -514,6 +758,9 @@ int spt_graphnorm_fwd(const float* x, const int64_t* batch, int64_t N, int64_t C
   SPT_REQUIRE(ws_bytes >= spt_graphnorm_workspace_bytes(B, C), SPT_E_WORKSPACE,
               "graphnorm_fwd: workspace too small");
   cudaStream_t st = (cudaStream_t)stream_;
+  // one graph: every row is in segment 0, the per-row id loads (8 bytes per 16 bytes of data
+  // per thread) are skipped
+  if (B == 1) batch = nullptr;
   NormWs w = carve(ws, B, C);
   cudaError_t ce = cudaMemsetAsync(ws, 0, w.zero_bytes, st);
   if (ce != cudaSuccess) {
@@ -529,6 +776,12 @@ int spt_graphnorm_fwd(const float* x, const int64_t* batch, int64_t N, int64_t C
   // single pass over x: shifted first and second moments around a per-channel pivot
   float* pivot = w.k2;  // [C] floats of the (forward-unused) k2 area
   if (N > 0) {
+    if (vec == 4 && !getenv("SPT_NORM_NO_FUSED")) {
+      // pivot computed inside the statistics kernel (one launch less)
+      k_graphnorm_stats<3, 4><<<slabs, kNormThreads, 0, st>>>(
+          x, nullptr, nullptr, 1.f, batch, N, C, B, nullptr, nullptr, nullptr, nullptr, nullptr,
+          w.acc0, w.acc1, w.count, cm.tx, cm.ty, slab_rows, pivot, (int)imin(N, 64));
+    } else {
     k_graphnorm_pivot<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(x, imin(N, 64), C, pivot);
     if (vec == 4)
       k_graphnorm_stats<3, 4><<<slabs, kNormThreads, 0, st>>>(
@@ -538,8 +791,18 @@ int spt_graphnorm_fwd(const float* x, const int64_t* batch, int64_t N, int64_t C
       k_graphnorm_stats<3, 1><<<slabs, kNormThreads, 0, st>>>(
           x, nullptr, nullptr, 1.f, batch, N, C, B, pivot, nullptr, nullptr, nullptr, nullptr,
           w.acc0, w.acc1, w.count, cm.tx, cm.ty, slab_rows);
+    }
   } else {
     cudaMemsetAsync(pivot, 0, (size_t)C * 4, st);
+  }
+  if (N > 0 && vec == 4 && B * C <= kNormTableMax && !getenv("SPT_NORM_NO_FUSED")) {
+    // finalise + apply in one launch (coefficient table in shared memory)
+    const int slab_a = norm_slab_rows_apply(N, cm.ty);
+    const unsigned ga = (unsigned)imin(ceil_div(N, slab_a), device_sm_count() * 8);
+    k_graphnorm_apply_fused<<<ga, kNormThreads, (size_t)3 * B * C * 4, st>>>(
+        x, batch, N, (int)C, (int)B, weight, bias, mean_scale, w.acc0, w.acc1, w.count, pivot,
+        eps, act_slope, y, mean, rstd, cm.tx, cm.ty, slab_a);
+    return check_launch("graphnorm_fwd");
   }
   k_graphnorm_finalize_shifted<<<(unsigned)ceil_div(B * C, 256), 256, 0, st>>>(
       w.acc0, w.acc1, w.count, pivot, mean_scale, B, C, eps, mean, rstd);
@@ -568,6 +831,7 @@ int spt_graphnorm_bwd(const float* x, const float* dy, const int64_t* batch, int
   SPT_REQUIRE(ws_bytes >= spt_graphnorm_workspace_bytes(B, C), SPT_E_WORKSPACE,
               "graphnorm_bwd: workspace too small");
   cudaStream_t st = (cudaStream_t)stream_;
+  if (B == 1) batch = nullptr;
   NormWs w = carve(ws, B, C);
   cudaError_t ce = cudaMemsetAsync(ws, 0, w.zero_bytes, st);
   if (ce != cudaSuccess) {
@@ -589,6 +853,15 @@ int spt_graphnorm_bwd(const float* x, const float* dy, const int64_t* batch, int
       k_graphnorm_stats<2, 1><<<slabs, kNormThreads, 0, st>>>(
           x, dy, yact, act_slope, batch, N, C, B, mean_scale, nullptr, nullptr, mean, rstd, w.acc0,
           w.acc1, w.count, cm.tx, cm.ty, slab_rows);
+  }
+  if (N > 0 && vec == 4 && B * C <= kNormTableMax && !getenv("SPT_NORM_NO_FUSED")) {
+    // coefficients + parameter gradients + apply in one launch
+    const int slab_a = norm_slab_rows_apply(N, cm.ty);
+    const unsigned ga = (unsigned)imin(ceil_div(N, slab_a), device_sm_count() * 8);
+    k_graphnorm_bwd_apply_fused<<<ga, kNormThreads, (size_t)5 * B * C * 4, st>>>(
+        x, dy, batch, N, (int)C, (int)B, weight, mean_scale, mean, rstd, w.acc0, w.acc1, w.count,
+        yact, act_slope, dx, dweight, dbias, dmean_scale, cm.tx, cm.ty, slab_a);
+    return check_launch("graphnorm_bwd");
   }
   k_graphnorm_bwd_coef<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(
       w.acc0, w.acc1, w.count, B, C, weight, mean_scale, mean, rstd, w.k2, w.k3, dweight,
