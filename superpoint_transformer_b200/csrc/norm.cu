@@ -233,6 +233,118 @@ k_graphnorm_stats(const float* __restrict__ x, const float* __restrict__ dy,
   }
 }
 
+// The statistics passes for ONE graph (batch == nullptr, C % 4 == 0): no segment bookkeeping per
+// row, 8 (forward) / 4 (backward, three streams) independent 16-byte loads in flight per thread.
+//   MODE 3: acc0 += d, acc1 += d*d, d = x - pivot (pivot = mean of the first rows, computed here)
+//   MODE 2: acc0 += g*xhat, acc1 += g, g = dy * act'(y)
+template <int MODE>
+__global__ void __launch_bounds__(kNormThreads)
+k_graphnorm_stats_single(const float* __restrict__ x, const float* __restrict__ dy,
+                         const float* __restrict__ yact, float slope, int64_t N, int C,
+                         const float* __restrict__ mean_scale, const float* __restrict__ mean,
+                         const float* __restrict__ rstd, double* __restrict__ acc0,
+                         double* __restrict__ acc1, double* __restrict__ cnt_out, int tx, int ty,
+                         int slab_rows, float* __restrict__ pivot_out, int pivot_rows) {
+  __shared__ float red[2][kNormThreads * 4];
+  const int cx = threadIdx.x % tx, ry = threadIdx.x / tx;
+  const int64_t nslabs = (N + slab_rows - 1) / slab_rows;
+  constexpr int U = (MODE == 3) ? 8 : 4;
+  for (int ct = 0; ct < C; ct += tx * 4) {
+    const int c0 = ct + cx * 4;
+    const bool active = c0 < C;
+    float4 sh = make_float4(0.f, 0.f, 0.f, 0.f), rs = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (MODE == 3) {
+      float4 part = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (active)
+        for (int r = ry; r < pivot_rows; r += ty) {
+          const float4 t = *reinterpret_cast<const float4*>(x + (int64_t)r * C + c0);
+          part.x += t.x; part.y += t.y; part.z += t.z; part.w += t.w;
+        }
+      *reinterpret_cast<float4*>(&red[0][threadIdx.x * 4]) = part;
+      __syncthreads();
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int yy = 0; yy < ty; ++yy) {
+        const float4 q = *reinterpret_cast<const float4*>(&red[0][(yy * tx + cx) * 4]);
+        t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w;
+      }
+      const float inv = 1.f / (float)pivot_rows;
+      sh = make_float4(t.x * inv, t.y * inv, t.z * inv, t.w * inv);
+      __syncthreads();
+      if (blockIdx.x == 0 && ry == 0 && active)
+        *reinterpret_cast<float4*>(pivot_out + c0) = sh;
+    } else if (active) {
+      const float4 ms = *reinterpret_cast<const float4*>(mean_scale + c0);
+      const float4 mu = *reinterpret_cast<const float4*>(mean + c0);
+      rs = *reinterpret_cast<const float4*>(rstd + c0);
+      sh = make_float4(ms.x * mu.x, ms.y * mu.y, ms.z * mu.z, ms.w * mu.w);
+    }
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    int64_t rows_seen = 0;
+    if (active) {
+      for (int64_t slab = blockIdx.x; slab < nslabs; slab += gridDim.x) {
+        const int64_t r0 = slab * slab_rows, r1 = min(r0 + (int64_t)slab_rows, N);
+        rows_seen += r1 - r0;
+        for (int64_t rb = r0 + ry; rb < r1; rb += (int64_t)ty * U) {
+          float4 xq[U], gq[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int64_t r = rb + (int64_t)u * ty;
+            // rows past the slab contribute zeros: x = shift, g = 0
+            xq[u] = sh;
+            gq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < r1) {
+              xq[u] = *reinterpret_cast<const float4*>(x + r * C + c0);
+              if (MODE == 2) {
+                gq[u] = *reinterpret_cast<const float4*>(dy + r * C + c0);
+                if (yact) {
+                  const float4 yy = *reinterpret_cast<const float4*>(yact + r * C + c0);
+                  gq[u].x *= (yy.x > 0.f) ? 1.f : slope; gq[u].y *= (yy.y > 0.f) ? 1.f : slope;
+                  gq[u].z *= (yy.z > 0.f) ? 1.f : slope; gq[u].w *= (yy.w > 0.f) ? 1.f : slope;
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (MODE == 3) {
+              const float dx_ = xq[u].x - sh.x, dy_ = xq[u].y - sh.y, dz_ = xq[u].z - sh.z,
+                          dw_ = xq[u].w - sh.w;
+              a0.x += dx_; a0.y += dy_; a0.z += dz_; a0.w += dw_;
+              a1.x = fmaf(dx_, dx_, a1.x); a1.y = fmaf(dy_, dy_, a1.y);
+              a1.z = fmaf(dz_, dz_, a1.z); a1.w = fmaf(dw_, dw_, a1.w);
+            } else {
+              a0.x = fmaf(gq[u].x, (xq[u].x - sh.x) * rs.x, a0.x);
+              a0.y = fmaf(gq[u].y, (xq[u].y - sh.y) * rs.y, a0.y);
+              a0.z = fmaf(gq[u].z, (xq[u].z - sh.z) * rs.z, a0.z);
+              a0.w = fmaf(gq[u].w, (xq[u].w - sh.w) * rs.w, a0.w);
+              a1.x += gq[u].x; a1.y += gq[u].y; a1.z += gq[u].z; a1.w += gq[u].w;
+            }
+          }
+        }
+      }
+    }
+    *reinterpret_cast<float4*>(&red[0][threadIdx.x * 4]) = a0;
+    *reinterpret_cast<float4*>(&red[1][threadIdx.x * 4]) = a1;
+    __syncthreads();
+    if (ry == 0 && active) {
+      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int yy = 0; yy < ty; ++yy) {
+        const float4 p0 = *reinterpret_cast<const float4*>(&red[0][(yy * tx + cx) * 4]);
+        const float4 p1 = *reinterpret_cast<const float4*>(&red[1][(yy * tx + cx) * 4]);
+        s0[0] += p0.x; s0[1] += p0.y; s0[2] += p0.z; s0[3] += p0.w;
+        s1[0] += p1.x; s1[1] += p1.y; s1[2] += p1.z; s1[3] += p1.w;
+      }
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        atomicAdd(&acc0[c0 + v], (double)s0[v]);
+        atomicAdd(&acc1[c0 + v], (double)s1[v]);
+      }
+      if (cnt_out && c0 == 0) atomicAdd(&cnt_out[0], (double)rows_seen);
+    }
+    __syncthreads();
+  }
+}
+
 // per-channel pivot = mean of the first `rows` rows (any graph): one thread per channel
 __global__ void k_graphnorm_pivot(const float* __restrict__ x, int64_t rows, int64_t C,
                                   float* __restrict__ pivot) {
@@ -776,7 +888,11 @@ int spt_graphnorm_fwd(const float* x, const int64_t* batch, int64_t N, int64_t C
   // single pass over x: shifted first and second moments around a per-channel pivot
   float* pivot = w.k2;  // [C] floats of the (forward-unused) k2 area
   if (N > 0) {
-    if (vec == 4 && !getenv("SPT_NORM_NO_FUSED")) {
+    if (vec == 4 && !batch && !getenv("SPT_NORM_NO_FUSED")) {
+      k_graphnorm_stats_single<3><<<slabs, kNormThreads, 0, st>>>(
+          x, nullptr, nullptr, 1.f, N, (int)C, nullptr, nullptr, nullptr, w.acc0, w.acc1, w.count,
+          cm.tx, cm.ty, slab_rows, pivot, (int)imin(N, 64));
+    } else if (vec == 4 && !getenv("SPT_NORM_NO_FUSED")) {
       // pivot computed inside the statistics kernel (one launch less)
       k_graphnorm_stats<3, 4><<<slabs, kNormThreads, 0, st>>>(
           x, nullptr, nullptr, 1.f, batch, N, C, B, nullptr, nullptr, nullptr, nullptr, nullptr,
@@ -845,7 +961,11 @@ int spt_graphnorm_bwd(const float* x, const float* dy, const int64_t* batch, int
   int64_t total = N * (C / vec);
   int agrid = (int)imin(ceil_div(total > 0 ? total : 1, kNormThreads), device_sm_count() * 16);
   if (N > 0) {
-    if (vec == 4)
+    if (vec == 4 && !batch && !getenv("SPT_NORM_NO_FUSED"))
+      k_graphnorm_stats_single<2><<<slabs, kNormThreads, 0, st>>>(
+          x, dy, yact, act_slope, N, (int)C, mean_scale, mean, rstd, w.acc0, w.acc1, w.count, cm.tx,
+          cm.ty, slab_rows, nullptr, 0);
+    else if (vec == 4)
       k_graphnorm_stats<2, 4><<<slabs, kNormThreads, 0, st>>>(
           x, dy, yact, act_slope, batch, N, C, B, mean_scale, nullptr, nullptr, mean, rstd, w.acc0,
           w.acc1, w.count, cm.tx, cm.ty, slab_rows);   // also counts the rows per graph
