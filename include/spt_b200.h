@@ -337,6 +337,11 @@ typedef struct spt_attn_extras {
   float* ws_logits;        /* [E, H] */
   const int32_t* edge_row; /* [E] CSR row of every slot (spt_expand_pointers_i32) */
   float* ws_ds;            /* [E, H] backward only */
+  /* split kernels only: the gathered value rows stored as bf16 ([T, ldv_bf16] elements; fp32
+   * accumulation).  Halves the bytes of the dominant gather and keeps it L2-resident — the
+   * "bf16 storage" configuration (BASELINE cfg 3); q, k and the edge features stay fp32. */
+  const uint16_t* v_bf16;
+  int64_t ldv_bf16;
 } spt_attn_extras;
 
 int spt_attn_fwd_ex(const float* q, int64_t ldq, const float* k, int64_t ldk,

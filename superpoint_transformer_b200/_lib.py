@@ -122,7 +122,8 @@ class AttnExtras(ctypes.Structure):
                 ("d_q_row_add", ctypes.c_void_p), ("d_k_row_add", ctypes.c_void_p),
                 ("d_sump", ctypes.c_void_p), ("sump", ctypes.c_void_p),
                 ("ws_logits", ctypes.c_void_p), ("edge_row", ctypes.c_void_p),
-                ("ws_ds", ctypes.c_void_p)]
+                ("ws_ds", ctypes.c_void_p), ("v_bf16", ctypes.c_void_p),
+                ("ldv_bf16", ctypes.c_int64)]
 
 
 def library_path():

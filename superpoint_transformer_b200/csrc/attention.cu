@@ -601,6 +601,11 @@ static bool split_layout_ok(const float* q, const float* k, const float* v, cons
          rows * (ldk > ldv ? ldk : ldv) < (int64_t)4000000000LL && !getenv("SPT_ATTN_NO_SPLIT");
 }
 
+static bool split_v_bf16_ok(const spt_attn_extras* ex) {
+  return ex && ex->v_bf16 && ((uintptr_t)ex->v_bf16 & 7) == 0 && ex->ldv_bf16 % 4 == 0 &&
+         ex->ldv_bf16 > 0 && ex->ldv_bf16 < (1 << 20);
+}
+
 static bool tile_layout_ok(const float* q, const float* k, const float* v, const float* a,
                            int64_t ldq, int64_t ldk, int64_t ldv, int64_t rows, int64_t E) {
   const uintptr_t al8 = (uintptr_t)q | (uintptr_t)k;
@@ -663,14 +668,20 @@ int spt_attn_fwd_ex(const float* q, int64_t ldq, const float* k, int64_t ldk, co
     }
     if (rc != SPT_OK) return rc;
     split::RowFwdArgs B;
-    B.logits = ex->ws_logits; B.v = v; B.ldv = (int)ldv; B.a = a;
+    const bool vbf = split_v_bf16_ok(ex);
+    B.logits = ex->ws_logits; B.a = a;
+    B.v = vbf ? (const void*)ex->v_bf16 : (const void*)v;
+    B.ldv = vbf ? (int)ex->ldv_bf16 : (int)ldv;
     B.rowptr = rowptr; B.col = col; B.num_rows = num_rows;
     B.agg_v = agg_v; B.abar = abar; B.sump = sump; B.m = m; B.z = z;
     B.rows_per_warp = split_rows_per_warp(num_rows);
     const unsigned grid =
         (unsigned)ceil_div(num_rows, (int64_t)split::kRowWarps * B.rows_per_warp);
-    if (abar) split::k_row_fwd<true><<<grid, split::kRowWarps * kWarp, 0, st>>>(B);
-    else split::k_row_fwd<false><<<grid, split::kRowWarps * kWarp, 0, st>>>(B);
+    const unsigned thr = split::kRowWarps * kWarp;
+    if (abar && vbf) split::k_row_fwd<true, true><<<grid, thr, 0, st>>>(B);
+    else if (abar) split::k_row_fwd<true, false><<<grid, thr, 0, st>>>(B);
+    else if (vbf) split::k_row_fwd<false, true><<<grid, thr, 0, st>>>(B);
+    else split::k_row_fwd<false, false><<<grid, thr, 0, st>>>(B);
     return check_launch("attn_fwd(row)");
   }
   if (!extras && a && tile::shape_ok(H, D, Dv, F) &&
@@ -780,20 +791,19 @@ int spt_attn_bwd_rows_ex(const float* q, int64_t ldq, const float* k, int64_t ld
         (unsigned)ceil_div(num_rows, (int64_t)split::kRowWarps * B.rows_per_warp);
     const unsigned thr = split::kRowWarps * kWarp;
     const int rsm = split::kRowBwdSmem;
-    static unsigned long long rdone[4] = {0, 0, 0, 0};
-    if (has_dab && Wk) {
-      ensure_dynamic_smem(split::k_row_bwd<true, true>, rsm, &rdone[0]);
-      split::k_row_bwd<true, true><<<grid, thr, rsm, st>>>(B);
-    } else if (has_dab) {
-      ensure_dynamic_smem(split::k_row_bwd<true, false>, rsm, &rdone[1]);
-      split::k_row_bwd<true, false><<<grid, thr, rsm, st>>>(B);
-    } else if (Wk) {
-      ensure_dynamic_smem(split::k_row_bwd<false, true>, rsm, &rdone[2]);
-      split::k_row_bwd<false, true><<<grid, thr, rsm, st>>>(B);
-    } else {
-      ensure_dynamic_smem(split::k_row_bwd<false, false>, rsm, &rdone[3]);
-      split::k_row_bwd<false, false><<<grid, thr, rsm, st>>>(B);
-    }
+    const bool vbf = split_v_bf16_ok(ex);
+    if (vbf) { B.v = ex->v_bf16; B.ldv = (int)ex->ldv_bf16; }
+    static unsigned long long rdone[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define SPT_ROW_BWD(DAB, WK, VB, IDX)                                              \
+  do {                                                                             \
+    ensure_dynamic_smem(split::k_row_bwd<DAB, WK, VB>, rsm, &rdone[IDX]);          \
+    split::k_row_bwd<DAB, WK, VB><<<grid, thr, rsm, st>>>(B);                      \
+  } while (0)
+    if (has_dab && Wk) { if (vbf) SPT_ROW_BWD(true, true, true, 0); else SPT_ROW_BWD(true, true, false, 1); }
+    else if (has_dab) { if (vbf) SPT_ROW_BWD(true, false, true, 2); else SPT_ROW_BWD(true, false, false, 3); }
+    else if (Wk) { if (vbf) SPT_ROW_BWD(false, true, true, 4); else SPT_ROW_BWD(false, true, false, 5); }
+    else { if (vbf) SPT_ROW_BWD(false, false, true, 6); else SPT_ROW_BWD(false, false, false, 7); }
+#undef SPT_ROW_BWD
     rc = check_launch("attn_bwd_rows(row)");
     if (rc != SPT_OK) return rc;
     split::EdgeBwdArgs A;

@@ -178,7 +178,7 @@ k_edge_logits_simple(const EdgeFwdArgs P) {
 // ------------------------------------------------------------------------------------------
 struct RowFwdArgs {
   const float* logits;                  // [E, 4] base-2 logits of the edge pass
-  const float* v; int ldv;
+  const void* v; int ldv;               // gathered value rows: fp32, or bf16 (template VBF)
   const float* a;                       // [E, 32]; read only when abar != nullptr
   const int32_t* rowptr; const int32_t* col;
   int64_t num_rows;
@@ -252,7 +252,22 @@ __device__ __forceinline__ void row_accumulate_v(int e0, int mycol, const char* 
 
 // the same with the staged feature rows consumed in the same pass: one read of p per edge
 // (0.127 vs 0.135 ms against a separate abar loop)
-template <int CNT, bool ABAR>
+// my 4 channels of gathered row `tc`: 16 bytes of fp32, or 8 bytes of bf16 (VBF: the value rows
+// stored as bf16, spt_attn_extras.v_bf16 — half the gather bytes, L2-resident)
+template <bool VBF>
+__device__ __forceinline__ ulonglong2 gather_v4(const char* vbase, unsigned tc, unsigned ldvb,
+                                                uint64_t keep) {
+  if (VBF) {
+    const uint2 w = tile::ldg_row8u(vbase + (uint64_t)tc * (uint64_t)ldvb, keep);
+    ulonglong2 v;
+    v.x = tile::bf2_to_f32x2(w.x);
+    v.y = tile::bf2_to_f32x2(w.y);
+    return v;
+  }
+  return ldg_row16(vbase + (uint64_t)tc * (uint64_t)ldvb, keep);
+}
+
+template <int CNT, bool ABAR, bool VBF>
 __device__ __forceinline__ void row_accumulate_va(int e0, int mycol, const char* vbase,
                                                   unsigned ldvb, uint64_t keep,
                                                   const float* p_lane, const ulonglong2* a_lane,
@@ -262,7 +277,7 @@ __device__ __forceinline__ void row_accumulate_va(int e0, int mycol, const char*
 #pragma unroll
   for (int u = 0; u < CNT; ++u) {
     const unsigned tc = (unsigned)__shfl_sync(kFull, mycol, e0 + u);
-    vv[u] = ldg_row16(vbase + (uint64_t)tc * (uint64_t)ldvb, keep);
+    vv[u] = gather_v4<VBF>(vbase, tc, ldvb, keep);
   }
   if (ABAR && wait_a) {
     cp_async_wait_all();
@@ -283,7 +298,7 @@ __device__ __forceinline__ void row_accumulate_va(int e0, int mycol, const char*
 }
 
 // one chunk of <= 32 edges of a row: p tile, sum of p, weighted accumulation
-template <bool ABAR>
+template <bool ABAR, bool VBF>
 __device__ __forceinline__ void row_fwd_chunk(int n, float4 lg, float4 mx, int mycol, int lane,
                                               float* p_s, const float* a_s, const char* vbase,
                                               unsigned ldvb, float& l, f32x2& accv01,
@@ -305,24 +320,24 @@ __device__ __forceinline__ void row_fwd_chunk(int n, float4 lg, float4 mx, int m
   bool first = ABAR;
 #pragma unroll 1
   for (; e0 + 8 <= n; e0 += 8) {
-    row_accumulate_va<8, ABAR>(e0, mycol, vbase, ldvb, keep, p_lane, a_lane, first, accv01, accv23,
+    row_accumulate_va<8, ABAR, VBF>(e0, mycol, vbase, ldvb, keep, p_lane, a_lane, first, accv01, accv23,
                                acca01, acca23);
     first = false;
   }
   if (n & 4) {
-    row_accumulate_va<4, ABAR>(e0, mycol, vbase, ldvb, keep, p_lane, a_lane, first, accv01, accv23,
+    row_accumulate_va<4, ABAR, VBF>(e0, mycol, vbase, ldvb, keep, p_lane, a_lane, first, accv01, accv23,
                                acca01, acca23);
     first = false;
     e0 += 4;
   }
   if (n & 2) {
-    row_accumulate_va<2, ABAR>(e0, mycol, vbase, ldvb, keep, p_lane, a_lane, first, accv01, accv23,
+    row_accumulate_va<2, ABAR, VBF>(e0, mycol, vbase, ldvb, keep, p_lane, a_lane, first, accv01, accv23,
                                acca01, acca23);
     first = false;
     e0 += 2;
   }
   if (n & 1)
-    row_accumulate_va<1, ABAR>(e0, mycol, vbase, ldvb, keep, p_lane, a_lane, first, accv01, accv23,
+    row_accumulate_va<1, ABAR, VBF>(e0, mycol, vbase, ldvb, keep, p_lane, a_lane, first, accv01, accv23,
                                acca01, acca23);
 }
 
@@ -347,7 +362,7 @@ __device__ __forceinline__ void cp_async16_plain(uint32_t dst, const void* src) 
 // logits / column ids of the NEXT row's first chunk are copied to shared memory while the
 // current row gathers: per row only the batches of gathered v rows remain as dependent round
 // trips.
-template <bool ABAR>
+template <bool ABAR, bool VBF>
 __global__ void __launch_bounds__(kRowWarps * 32, kRowFwdCtas)
 k_row_fwd(const RowFwdArgs P) {
   __shared__ __align__(16) RowFwdTiles<ABAR> tiles[kRowWarps];
@@ -359,8 +374,9 @@ k_row_fwd(const RowFwdArgs P) {
   RowFwdTiles<ABAR>& S = tiles[w];
   const int hb = lane >> 3;
   const uint64_t stream = policy_evict_first();
-  const char* vbase = reinterpret_cast<const char*>(P.v) + 16 * lane;
-  const unsigned ldvb = (unsigned)P.ldv * 4u;
+  constexpr unsigned kElt = VBF ? 2u : 4u;
+  const char* vbase = reinterpret_cast<const char*>(P.v) + 4 * kElt * lane;
+  const unsigned ldvb = (unsigned)P.ldv * kElt;
   const float4* lg4 = reinterpret_cast<const float4*>(P.logits);
   const int rp = P.rowptr[r0 + min(lane, nrows)];             // extents of my rows
   const uint32_t pre_lg = smem_addr(S.pre_lg[0]) + 16 * lane;
@@ -417,7 +433,7 @@ k_row_fwd(const RowFwdArgs P) {
     float l = 0.f;                                // sum of p of head hsel_of_lane(lane)
     if (single) {
       if (e > b)
-        row_fwd_chunk<ABAR>(n0, lg, mx, mycol, lane, S.p, S.a, vbase, ldvb, l, accv01, accv23,
+        row_fwd_chunk<ABAR, VBF>(n0, lg, mx, mycol, lane, S.p, S.a, vbase, ldvb, l, accv01, accv23,
                             acca01, acca23);
     } else {
       // long row: the maxima wait in shared memory while the chunks stream through
@@ -437,7 +453,7 @@ k_row_fwd(const RowFwdArgs P) {
         }
         __syncwarp();
         mx = *reinterpret_cast<const float4*>(S.m);
-        row_fwd_chunk<ABAR>(min(32, e - tb), lg, mx, mycol, lane, S.p, S.a, vbase, ldvb, l,
+        row_fwd_chunk<ABAR, VBF>(min(32, e - tb), lg, mx, mycol, lane, S.p, S.a, vbase, ldvb, l,
                             accv01, accv23, acca01, acca23);
       }
     }
@@ -472,7 +488,7 @@ k_row_fwd(const RowFwdArgs P) {
 struct RowBwdArgs {
   const float* logits;                  // [E, 4] base-2 logits of the forward edge pass
   const float* k; int ldk;
-  const float* v; int ldv;
+  const void* v; int ldv;               // gathered value rows: fp32, or bf16 (template VBF)
   const float* a;                       // [E, 32]
   const int32_t* rowptr; const int32_t* col;
   int64_t num_rows;
@@ -503,7 +519,7 @@ struct RowBwdTiles {
 };
 
 // partial dot products <dY, v_t> (+ <dAbar, a_e>) of CNT edges e0.. : CNT gathered rows in flight
-template <int CNT, bool HAS_DAB>
+template <int CNT, bool HAS_DAB, bool VBF>
 __device__ __forceinline__ void row_bwd_partials(float* s, int e0, int mycol, const char* vbase,
                                                  unsigned ldvb, uint64_t keep,
                                                  const ulonglong2* a_lane, f32x2 dy01, f32x2 dy23,
@@ -512,7 +528,7 @@ __device__ __forceinline__ void row_bwd_partials(float* s, int e0, int mycol, co
 #pragma unroll
   for (int u = 0; u < CNT; ++u) {
     const unsigned tc = (unsigned)__shfl_sync(kFull, mycol, e0 + u);
-    vv[u] = ldg_row16(vbase + (uint64_t)tc * (uint64_t)ldvb, keep);
+    vv[u] = gather_v4<VBF>(vbase, tc, ldvb, keep);
   }
 #pragma unroll
   for (int u = 0; u < CNT; ++u) {
@@ -527,7 +543,7 @@ __device__ __forceinline__ void row_bwd_partials(float* s, int e0, int mycol, co
   }
 }
 
-template <bool HAS_DAB, bool HAS_WK>
+template <bool HAS_DAB, bool HAS_WK, bool VBF>
 __global__ void __launch_bounds__(kRowWarps * 32, kRowBwdCtas)
 k_row_bwd(const RowBwdArgs P) {
   extern __shared__ __align__(16) unsigned char row_bwd_smem[];
@@ -548,8 +564,9 @@ k_row_bwd(const RowBwdArgs P) {
   RowBwdTiles& S = tiles[w];
   const int hb = lane >> 3, j8 = lane & 7;
   const uint64_t keep = policy_evict_last(), stream = policy_evict_first();
-  const char* vbase = reinterpret_cast<const char*>(P.v) + 16 * lane;
-  const unsigned ldvb = (unsigned)P.ldv * 4u, ldkb = (unsigned)P.ldk * 4u;
+  constexpr unsigned kElt = VBF ? 2u : 4u;
+  const char* vbase = reinterpret_cast<const char*>(P.v) + 4 * kElt * lane;
+  const unsigned ldvb = (unsigned)P.ldv * kElt, ldkb = (unsigned)P.ldk * 4u;
   const ulonglong2* a_lane = reinterpret_cast<const ulonglong2*>(S.a) + j8;
   const int rp = P.rowptr[r0 + min(lane, nrows)];             // extents of my rows
 
@@ -616,7 +633,7 @@ k_row_bwd(const RowBwdArgs P) {
       const float lg = valid ? __ldg(P.logits + slot) : -INFINITY;
       float s[8];
       if (cnt == 8) {
-        row_bwd_partials<8, HAS_DAB>(s, e0, mycol, vbase, ldvb, keep, a_lane, dy01, dy23, dab01,
+        row_bwd_partials<8, HAS_DAB, VBF>(s, e0, mycol, vbase, ldvb, keep, a_lane, dy01, dy23, dab01,
                                      dab23);
       } else {
         // short last group: 4 + 2 + 1 rows, no wasted gathers
@@ -625,21 +642,21 @@ k_row_bwd(const RowBwdArgs P) {
         int o = 0;
         if (cnt & 4) {
           float s4[4];
-          row_bwd_partials<4, HAS_DAB>(s4, e0, mycol, vbase, ldvb, keep, a_lane, dy01, dy23,
+          row_bwd_partials<4, HAS_DAB, VBF>(s4, e0, mycol, vbase, ldvb, keep, a_lane, dy01, dy23,
                                        dab01, dab23);
           s[0] = s4[0]; s[1] = s4[1]; s[2] = s4[2]; s[3] = s4[3];
           o = 4;
         }
         if (cnt & 2) {
           float s2[2];
-          row_bwd_partials<2, HAS_DAB>(s2, e0 + o, mycol, vbase, ldvb, keep, a_lane, dy01, dy23,
+          row_bwd_partials<2, HAS_DAB, VBF>(s2, e0 + o, mycol, vbase, ldvb, keep, a_lane, dy01, dy23,
                                        dab01, dab23);
           if (o) { s[4] = s2[0]; s[5] = s2[1]; } else { s[0] = s2[0]; s[1] = s2[1]; }
           o += 2;
         }
         if (cnt & 1) {
           float s1[1];
-          row_bwd_partials<1, HAS_DAB>(s1, e0 + o, mycol, vbase, ldvb, keep, a_lane, dy01, dy23,
+          row_bwd_partials<1, HAS_DAB, VBF>(s1, e0 + o, mycol, vbase, ldvb, keep, a_lane, dy01, dy23,
                                        dab01, dab23);
           if (o == 0) s[0] = s1[0]; else if (o == 2) s[2] = s1[0];
           else if (o == 4) s[4] = s1[0]; else s[6] = s1[0];

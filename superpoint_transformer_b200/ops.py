@@ -863,7 +863,8 @@ class _AttnCore(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, qsrc, kv, a, Wq, bq, Wk, bk, g, H, D, scale_mode, scale_value,
-                want_abar, q_row_add=None, q_tgt_add=None, k_row_add=None, drop_mask=None):
+                want_abar, q_row_add=None, q_tgt_add=None, k_row_add=None, drop_mask=None,
+                v_bf16=None):
         lib = _lib.load()
         dev = qsrc.device
         HD = H * D
@@ -897,6 +898,10 @@ class _AttnCore(torch.autograd.Function):
             logits = torch.empty((g.E, H), dtype=torch.float32, device=dev)
             ex = _lib.AttnExtras(None, None, None, None, None, None, None, None,
                                  _p(logits), _p(g.edge_row), None)
+            if v_bf16 is not None and fused:
+                # bf16 storage: the row passes gather the value rows from the bf16 copy of qkv
+                ex.v_bf16 = v_bf16.data_ptr() + 2 * (2 * HD)
+                ex.ldv_bf16 = v_bf16.shape[1]
         with torch.cuda.device(dev), _timed('attn_fwd', R=R, E=g.E, H=H, D=D, Dv=Dv, F=F,
                                             abar=abar is not None):
             _lib.check(lib.spt_attn_fwd_ex(qp, ldq, kp, ldk, vp, ldv, _p(a), _p(g.rowptr),
@@ -910,6 +915,7 @@ class _AttnCore(torch.autograd.Function):
         ctx.scale_mode, ctx.scale_value = scale_mode, scale_value
         ctx.fused = fused
         ctx.logits = logits          # split kernels: the backward row pass reads them back
+        ctx.v_bf16 = v_bf16 if (logits is not None and fused) else None
         ctx.opt = (kv is not None, a is not None, Wq is not None, bq is not None,
                    Wk is not None, bk is not None, abar is not None)
         ctx.ex = (q_row_add is not None, q_tgt_add is not None, k_row_add is not None,
@@ -1011,6 +1017,9 @@ class _AttnCore(torch.autograd.Function):
             ws_ds = torch.empty((E, H), dtype=torch.float32, device=dev)
             ex = _lib.AttnExtras(None, None, None, None, None, None, None, None,
                                  _p(ctx.logits), _p(g.edge_row), _p(ws_ds))
+            if ctx.v_bf16 is not None:
+                ex.v_bf16 = ctx.v_bf16.data_ptr() + 2 * (2 * HD)
+                ex.ldv_bf16 = ctx.v_bf16.shape[1]
         with torch.cuda.device(dev):
             with _timed('attn_bwd_rows', **meta):
                 _lib.check(lib.spt_attn_bwd_rows_ex(
@@ -1036,7 +1045,7 @@ class _AttnCore(torch.autograd.Function):
         if Wk is not None and dWk is None:
             dWk = torch.zeros_like(Wk)
         return (dqkv, dkv, da, dWq, dbq, dWk, dbk, None, None, None, None, None, None,
-                d_qr, d_qt, d_kr, None)
+                d_qr, d_qt, d_kr, None, None)
 
 
 # ---------------------------------------------------------------------------
@@ -1179,6 +1188,14 @@ def attention_core(qsrc, kv, a_csr, Wq, bq, Wk, bk, graph, num_heads, qk_dim,
     _require_cuda(qsrc, kv, a_csr, Wq, bq, Wk, bk, q_row_add, q_tgt_add, k_row_add, drop_mask)
     extras = any(t is not None for t in (q_row_add, q_tgt_add, k_row_add, drop_mask))
     if _bf16_ok(qsrc, kv, a_csr, Wq, bq, Wk, bk, int(num_heads), int(qk_dim), extras):
+        if ATTN_SPLIT:
+            # split kernels: the gathered value rows (the dominant stream) come from a bf16 copy
+            # of the fused projections; q, k and the edge features stay fp32
+            qf = _f32c(qsrc)
+            return _AttnCore.apply(qf, None, _f32c(a_csr), _f32c(Wq), _f32c(bq), _f32c(Wk),
+                                   _f32c(bk), graph, int(num_heads), int(qk_dim),
+                                   int(scale_mode), float(scale_value), bool(want_abar),
+                                   None, None, None, None, cast_bf16(qf))
         return _AttnCoreBf16.apply(_f32c(qsrc), _f32c(a_csr), _f32c(Wq), _f32c(bq), _f32c(Wk),
                                    _f32c(bk), graph, int(num_heads), int(qk_dim),
                                    int(scale_mode), float(scale_value), bool(want_abar))
