@@ -115,6 +115,21 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# A second stream per device for launches that are independent of what follows them on the
+# main stream (the d[Wq;Wk] product of the attention backward runs beside the targets pass).
+# Fork / join with wait_stream, so the pattern is CUDA-graph capturable.
+_SIDE_STREAMS = {}
+ATTN_DW_SIDE_STREAM = os.environ.get('SPT_ATTN_DW_SIDE_STREAM', '1') != '0'
+
+
+def _side_stream(device):
+    key = torch.device(device).index
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return st
+
+
 def _f32c(t):
     if t is None:
         return None
@@ -980,8 +995,10 @@ class _AttnCore(torch.autograd.Function):
             lddq, lddk, lddv = ldq, ldk, ldv
         need = ctx.needs_input_grad
         da = torch.empty_like(a) if (a is not None and need[2]) else None
-        if (a is not None and Wq is not None and Wk is not None and Wq.shape == Wk.shape
-                and (bq is None) == (bk is None)):
+        packed_dw = (a is not None and Wq is not None and Wk is not None
+                     and Wq.shape == Wk.shape and (bq is None) == (bk is None))
+        dW2 = db2 = None
+        if packed_dw:
             # one contiguous [2HD, F] / [2HD] pair: lets the library run d[Wq;Wk] = G^T a as a
             # single tensor-core gemm_tn
             dW2 = zero_pool.take((2 * Wq.shape[0], Wq.shape[1]), dev)
@@ -1020,20 +1037,35 @@ class _AttnCore(torch.autograd.Function):
             if ctx.v_bf16 is not None:
                 ex.v_bf16 = ctx.v_bf16.data_ptr() + 2 * (2 * HD)
                 ex.ldv_bf16 = ctx.v_bf16.shape[1]
+        # d[Wq;Wk] = G^T a (and the bias sums) beside the targets pass: both only read G, so the
+        # product goes to a side stream (fork / join).  Not while per-launch events are being
+        # recorded (bench --kernels-out): the table wants serialised times.
+        side_dw = (ATTN_DW_SIDE_STREAM and _TIMING is None and packed_dw and not has_ex
+                   and E >= 2048 and F % 4 == 0)
         with torch.cuda.device(dev):
             with _timed('attn_bwd_rows', **meta):
                 _lib.check(lib.spt_attn_bwd_rows_ex(
                     qp, ldq, kp, ldk, vp, ldv, _p(a), _p(g.rowptr), _p(g.col), g.num_rows, E,
                     H, D, Dv, F, _p(Wq), _p(bq), _p(Wk), _p(bk), ctx.scale_mode,
                     ctx.scale_value, _p(m), _p(z), _p(agg), _p(abar), _p(d_agg), _p(d_abar),
-                    dqp, lddq, _p(da), _p(dWq), _p(dbq), _p(dWk), _p(dbk), _p(Pb), _p(G),
+                    dqp, lddq, _p(da), None if side_dw else _p(dWq), None if side_dw else _p(dbq),
+                    None if side_dw else _p(dWk), None if side_dw else _p(dbk), _p(Pb), _p(G),
                     ctypes.byref(ex) if ex is not None else None, _stream()),
                     "spt_attn_bwd_rows")
+            if side_dw:
+                cur, side = torch.cuda.current_stream(dev), _side_stream(dev)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    _lib.check(lib.spt_gemm_tn_acc(_p(G), E, 2 * HD, 2 * HD, _p(a), F, F,
+                                                   _p(dW2), F, _p(db2) if bq is not None else None,
+                                                   side.cuda_stream), "spt_gemm_tn_acc")
             with _timed('attn_bwd_targets', **meta):
                 _lib.check(lib.spt_attn_bwd_targets_ex(
                     _p(g.csc_ptr), _p(g.csc_src), _p(g.csc2csr), g.num_targets, E, H, D, Dv,
                     _p(Pb), _p(G), _p(d_agg), dkp, lddk, dvp, lddv, _p(d_qt), _stream()),
                     "spt_attn_bwd_targets")
+            if side_dw:
+                cur.wait_stream(side)
             # rows (row pass + edge pass, or the fused kernel) + d[Wq;Wk] product + targets
             _count(4 if (ex is not None and not has_ex) else 3)
         if bq is not None and dbq is None:
