@@ -317,6 +317,24 @@ static bool use_umma() {
   return v == 1;
 }
 
+// rows below which the mma.sync kernels of this file run instead of the tcgen05 ones (whose
+// prologue — TMEM allocation, barrier set-up, weight split, first TMA round trip — is a fixed
+// ~5-15 us); tunable for experiments
+static int64_t umma_min_rows(const char* env, int64_t dflt) {
+  const char* e = getenv(env);
+  if (!e) return dflt;
+  const long long v = atoll(e);
+  return v > 0 ? (int64_t)v : dflt;
+}
+static int64_t nt_umma_min_rows() {
+  static int64_t v = umma_min_rows("SPT_GEMM_NT_UMMA_MIN", 512);
+  return v;
+}
+static int64_t tn_umma_min_rows() {
+  static int64_t v = umma_min_rows("SPT_GEMM_TN_UMMA_MIN", 2048);
+  return v;
+}
+
 extern "C" {
 
 int spt_gemm_nt(const float* A, int64_t M, int64_t K, int64_t lda, const float* B, int64_t N,
@@ -328,7 +346,7 @@ int spt_gemm_nt(const float* A, int64_t M, int64_t K, int64_t lda, const float* 
                   ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0,
               SPT_E_UNSUPPORTED, "gemm_nt: K, lda, ldb must be multiples of 4 and A, B 16-byte aligned");
   SPT_REQUIRE(K < (1 << 24) && N < (1 << 24), SPT_E_TOO_LARGE, "gemm_nt: K/N too large");
-  if (M >= 512 && use_umma() && umma::shape_ok(A, M, K, lda, B, N, ldb, C, ldc))
+  if (M >= nt_umma_min_rows() && use_umma() && umma::shape_ok(A, M, K, lda, B, N, ldb, C, ldc))
     return umma::launch(A, M, K, lda, B, N, ldb, bias, C, ldc, (cudaStream_t)stream_);
   static unsigned long long attr_done = 0;
   ensure_dynamic_smem(gemm::k_gemm_nt, (int)sizeof(gemm::NtSmem), &attr_done);
@@ -360,7 +378,7 @@ int spt_gemm_tn_acc(const float* A, int64_t M, int64_t N, int64_t lda, const flo
                   ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0,
               SPT_E_UNSUPPORTED,
               "gemm_tn_acc: N, K, lda, ldb must be multiples of 4 and A, B 16-byte aligned");
-  if (M >= 2048 && use_umma() && umma::tn_shape_ok(A, M, N, lda, B, K, ldb))
+  if (M >= tn_umma_min_rows() && use_umma() && umma::tn_shape_ok(A, M, N, lda, B, K, ldb))
     return umma::tn_launch(A, M, N, lda, B, K, ldb, C, ldc, colsumA, (cudaStream_t)stream_);
   int ntiles = (int)ceil_div(N, gemm::TM), ktiles = (int)ceil_div(K, gemm::TK);
   int64_t tiles = (int64_t)ntiles * ktiles;

@@ -119,7 +119,7 @@ def _stream():
 # main stream (the d[Wq;Wk] product of the attention backward runs beside the targets pass).
 # Fork / join with wait_stream, so the pattern is CUDA-graph capturable.
 _SIDE_STREAMS = {}
-ATTN_DW_SIDE_STREAM = os.environ.get('SPT_ATTN_DW_SIDE_STREAM', '1') != '0'
+ATTN_DW_SIDE_STREAM = os.environ.get('SPT_ATTN_DW_SIDE_STREAM', '0') != '0'   # measured: 13.4-13.6 vs 13.6 ms, within noise -> off
 
 
 def _side_stream(device):
@@ -1097,10 +1097,11 @@ def set_attention_split(on):
 
 
 def set_attention_storage(mode):
-    """'fp32' (default) or 'bf16': in bf16 mode SelfAttentionBlock stores the fused projections
-    qkv and the CSR-ordered edge features as bf16 in HBM for the attention kernels (fp32
-    accumulation, fp32 outputs and gradients) whenever the shape is the row-tile family
-    (H=4, D=4, Dv=32, F=32, k and q RPE); other shapes keep the fp32 kernels."""
+    """'fp32' (default) or 'bf16' (BASELINE cfg 3), for the shape family H=4, D=4, Dv=32, F=32 with
+    k and q RPE; other shapes keep the fp32 kernels.  fp32 accumulation, outputs and gradients
+    in both modes.  With the split kernels (default) 'bf16' makes the row passes gather the
+    value rows from a bf16 copy of the fused projections; with the fused row-tile kernels
+    (set_attention_split(False)) qkv and the CSR-ordered edge features are both stored as bf16."""
     global ATTN_STORAGE
     if mode not in ('fp32', 'bf16'):
         raise ValueError(mode)
