@@ -160,7 +160,7 @@ __device__ __forceinline__ void split_row_to_tmem(uint32_t arow, int row, uint32
     for (int c = 0; c < 4; ++c) {
       const float h = tf32_rna(xs[c]);
       hi[4 * j + c] = __float_as_uint(h);
-      lo[4 * j + c] = __float_as_uint(tf32_rna(xs[c] - h));
+      lo[4 * j + c] = __float_as_uint(xs[c] - h);   // fed raw: the tensor core ignores the low 13 bits
     }
   }
   tmem_st32(ta, hi);
@@ -619,7 +619,7 @@ k_edge_bwd_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int j = 0; j < 32; ++j) {
             const float h = tf32_rna(G[j]);
             hi[j] = __float_as_uint(h);
-            lo[j] = __float_as_uint(tf32_rna(G[j] - h));
+            lo[j] = __float_as_uint(G[j] - h);   // raw (truncated by the tensor core)
           }
           const uint32_t tg = tmem_base + kGStage0 + 64 * g + lane_off;
           tmem_st32(tg, hi);

@@ -4,7 +4,8 @@
 //
 // Replaces the cuBLAS calls behind src/nn/attention.py:191,318 and src/nn/mlp.py:45 of the
 // reference.  fp32 accuracy on TF32 tensor cores comes from the 3xTF32 split
-//   x = hi + lo,  hi = tf32(x),  lo = tf32(x - hi),   A.B ~= Alo.Bhi + Ahi.Blo + Ahi.Bhi
+//   x = hi + lo,  hi = tf32_rna(x),  lo = x - hi (stored as is: the tensor core reads only the
+//   top 19 bits of a tf32 operand, i.e. truncates it),   A.B ~= Alo.Bhi + Ahi.Blo + Ahi.Bhi
 // (~2^-21 relative), accumulated in fp32 in TMEM.
 //
 // k_gemm_nt_umma: one persistent CTA per SM, warp-specialised, tile = 128 rows x BN (<=192):
@@ -386,7 +387,7 @@ k_gemm_nt_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int c = 0; c < 4; ++c) {
             const float h = tf32_rna(xs[c]);
             hi[4 * j + c] = __float_as_uint(h);
-            lo[4 * j + c] = __float_as_uint(tf32_rna(xs[c] - h));
+            lo[4 * j + c] = __float_as_uint(xs[c] - h);   // fed raw: the tensor core ignores the low 13 bits
           }
         }
         mbar_wait(&a_empty[s], ((it / P.a_stages) & 1) ^ 1, 5);  // previous MMAs retired
@@ -771,8 +772,8 @@ k_gemm_tn_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const float4 x = lds128(ahi + 16u * (uint32_t)i);
           float4 h, l;
           h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
-          l.x = tf32_rna(x.x - h.x); l.y = tf32_rna(x.y - h.y);
-          l.z = tf32_rna(x.z - h.z); l.w = tf32_rna(x.w - h.w);
+          l.x = x.x - h.x; l.y = x.y - h.y;      // raw: the tensor core ignores the low 13 bits
+          l.z = x.z - h.z; l.w = x.w - h.w;
           sts128(ahi + 16u * (uint32_t)i, h);
           sts128(alo + 16u * (uint32_t)i, l);
           cs[u].x += x.x; cs[u].y += x.y; cs[u].z += x.z; cs[u].w += x.w;

@@ -162,8 +162,8 @@ __device__ __forceinline__ void split_chunk(void* hi_, void* lo_, int n4, int t,
         float4 h, l;
         h.x = tf32_rna(x[u].x); h.y = tf32_rna(x[u].y);
         h.z = tf32_rna(x[u].z); h.w = tf32_rna(x[u].w);
-        l.x = tf32_rna(x[u].x - h.x); l.y = tf32_rna(x[u].y - h.y);
-        l.z = tf32_rna(x[u].z - h.z); l.w = tf32_rna(x[u].w - h.w);
+        l.x = x[u].x - h.x; l.y = x[u].y - h.y;      // raw: the tensor core ignores the low 13 bits
+        l.z = x[u].z - h.z; l.w = x[u].w - h.w;
         sts128(hi + 16u * (uint32_t)(i0 + u * nt), h);
         sts128(lo + 16u * (uint32_t)(i0 + u * nt), l);
       }
