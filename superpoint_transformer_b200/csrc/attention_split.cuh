@@ -576,17 +576,6 @@ k_row_bwd(const RowBwdArgs P) {
   const int b = __shfl_sync(kFull, rp, ri), e = __shfl_sync(kFull, rp, ri + 1);
   __syncwarp();                                    // the previous row's tiles have been read
   if (NEED_A && e > b) stage_features(S.a, P.a, b, min(32, e - b), lane, stream);
-  if (ri + 1 < nrows) {
-    // the next row's per-row operands (dY, agg, dAbar, abar: 512 bytes each) on their way to
-    // the L2 while this row gathers: their first use is 16 % of the stall samples otherwise
-    const int64_t nr = row + 1;
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.d_agg_v + nr * kC + 4 * lane) : "memory");
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.agg_v + nr * kC + 4 * lane) : "memory");
-    if (HAS_DAB) {
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(P.d_abar + nr * (kH * kF) + 4 * lane) : "memory");
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(P.abar + nr * (kH * kF) + 4 * lane) : "memory");
-    }
-  }
 
   const float scale = fast::qk_scale_fast(P.scale_mode, P.scale_value, e - b);
   const float m2 = P.m[row * kH + hb] * kLog2e;

@@ -25,19 +25,19 @@ ei = ei[:, order].contiguous()
 ops.mark_csr_ordered(ei)
 gi = ops.build_graph_index(ei, N)
 E = ei.shape[1]
-H, D, C, F = 4, 4, 128, 32
+H, D, C, F = (int(os.environ.get(k, v)) for k, v in (('H', 4), ('D', 4), ('C', 128), ('F', 32)))
 g = torch.Generator().manual_seed(0)
 qkv = torch.randn(N, 2 * H * D + C, generator=g).to(dev).requires_grad_(True)
 a = torch.randn(E, F, generator=g).to(dev).requires_grad_(True)
 mk = lambda *s: (torch.randn(*s, generator=g) * 0.2).to(dev).requires_grad_(True)  # noqa: E731
-Wq, bq, Wk, bk = mk(16, 32), mk(16), mk(16, 32), mk(16)
+Wq, bq, Wk, bk = mk(H * D, F), mk(H * D), mk(H * D, F), mk(H * D)
 ops.set_attention_storage(os.environ.get('SPT_ATTN_STORAGE', 'fp32'))
 ops.enable_event_timing(True)
 
 
 def step():
     agg, abar, sump = ops.attention_core(qkv, None, a, Wq, bq, Wk, bk, gi, H, D,
-                                         ops.SCALE_D_TIMES_G, 32 ** -0.5)
+                                         ops.SCALE_D_TIMES_G, (C // H) ** -0.5)
     (agg.sum() + abar.sum()).backward()
 
 
@@ -64,11 +64,11 @@ torch.cuda.synchronize()
 acc = {}
 for tag, meta, s, e in ops.timing_records():
     acc.setdefault(tag, []).append(s.elapsed_time(e))
-print(f'N={N} E={E} sorted={MORTON} storage={ops.ATTN_STORAGE} split={ops.ATTN_SPLIT}')
+print(f'N={N} E={E} C={C} H={H} D={D} F={F} sorted={MORTON} storage={ops.ATTN_STORAGE} split={ops.ATTN_SPLIT}')
 for k, v in acc.items():
     print(f'  {k}: min {min(v):.4f} ms  last {v[-1]:.4f} ms')
 if 'segment_pool_fwd' in acc:
     t = min(acc['segment_pool_fwd'])
-    gb = (E * 512 + N * 512 + E * 4) / 1e9
+    gb = (E * C * 4 + N * C * 4 + E * 4) / 1e9
     print(f'  bare gather of the v rows (segment-sum by col): {t:.4f} ms = {gb / t * 1e3:.0f} GB/s '
           f'of gathered + written bytes')
