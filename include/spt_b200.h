@@ -330,7 +330,8 @@ typedef struct spt_attn_extras {
   const float* d_sump;    /* [R, H] */
   const float* sump;      /* [R, H] */
   /* Workspace of the split kernels (csrc/attention_split.cuh: one edge-parallel pass on the
-   * tensor cores + one row-parallel pass, 16 bytes per edge between them).  With ws_logits and
+   * tensor cores + one row-parallel pass, 16 bytes per edge between them; shape families
+   * H=4, D=4, Dv=32, F=32 and — csrc/attention_split16.cuh — H=16, D=4, Dv in {4, 8}, F=32).  With ws_logits and
    * edge_row set (and none of the optional terms above) the forward takes that path and leaves
    * the base-2 logits in ws_logits; the backward reads them back and needs ws_ds as well.
    * NULL = the fused row-tile kernels. */

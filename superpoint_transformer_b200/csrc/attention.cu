@@ -22,6 +22,7 @@
 #include "attention_tile.cuh"
 #include "attention_split.cuh"
 #include "attention_umma.cuh"
+#include "attention_split16.cuh"
 #include <stdlib.h>
 
 namespace spt {
@@ -649,6 +650,37 @@ int spt_attn_fwd_ex(const float* q, int64_t ldq, const float* k, int64_t ldk, co
   SPT_REQUIRE(scale_mode >= SPT_SCALE_D_TIMES_G && scale_mode <= SPT_SCALE_CONST,
               SPT_E_INVALID, "attn_fwd: bad scale mode %d", scale_mode);
   cudaStream_t st = (cudaStream_t)stream_;
+  if (!extras && a && split16::shape_ok(H, D, Dv, F) &&
+      split_layout_ok(q, k, v, a, ldq, ldk, ldv, num_rows, E, ex) &&
+      ((uintptr_t)agg_v & 15) == 0) {
+    // the shipped head layout (H = 16): CUDA-core edge pass + row pass (attention_split16.cuh)
+    split16::EdgeFwdArgs A;
+    A.q = q; A.ldq = (int)ldq; A.k = k; A.ldk = (int)ldk; A.a = a;
+    A.rowptr = rowptr; A.col = col; A.edge_row = ex->edge_row; A.E = E;
+    A.Wq = Wq; A.bq = bq; A.Wk = Wk; A.bk = bk;
+    A.scale_mode = scale_mode; A.scale_value = scale_value; A.logits = ex->ws_logits;
+    split16::k_edge_logits16<<<(unsigned)ceil_div(E, split16::kEdgeThreads),
+                               split16::kEdgeThreads, 0, st>>>(A);
+    rc = check_launch("attn_fwd(edge16)");
+    if (rc != SPT_OK) return rc;
+    split16::RowFwdArgs B;
+    B.logits = ex->ws_logits; B.v = v; B.ldv = (int)ldv; B.a = a;
+    B.rowptr = rowptr; B.col = col; B.num_rows = num_rows;
+    B.agg_v = agg_v; B.abar = abar; B.sump = sump; B.m = m; B.z = z;
+    const unsigned grid = (unsigned)ceil_div(num_rows, split16::kRowWarps);
+    const unsigned thr = split16::kRowWarps * kWarp;
+    const int sm = split16::kRowFwdSmem16;
+    static unsigned long long fdone[4] = {0, 0, 0, 0};
+#define SPT_ROW_FWD16(CPL, AB, IDX)                                                    \
+  do {                                                                                 \
+    ensure_dynamic_smem(split16::k_row_fwd16<CPL, AB>, sm, &fdone[IDX]);               \
+    split16::k_row_fwd16<CPL, AB><<<grid, thr, sm, st>>>(B);                           \
+  } while (0)
+    if (Dv == 8) { if (abar) SPT_ROW_FWD16(4, true, 0); else SPT_ROW_FWD16(4, false, 1); }
+    else { if (abar) SPT_ROW_FWD16(2, true, 2); else SPT_ROW_FWD16(2, false, 3); }
+#undef SPT_ROW_FWD16
+    return check_launch("attn_fwd(row16)");
+  }
   if (!extras && a && split::shape_ok(H, D, Dv, F) &&
       split_layout_ok(q, k, v, a, ldq, ldk, ldv, num_rows, E, ex) &&
       ((uintptr_t)agg_v & 15) == 0 && (!abar || ((uintptr_t)abar & 15) == 0)) {
@@ -773,6 +805,56 @@ int spt_attn_bwd_rows_ex(const float* q, int64_t ldq, const float* k, int64_t ld
               SPT_E_INVALID, "attn_bwd_rows: null pointer");
   cudaStream_t st = (cudaStream_t)stream_;
   bool tile_done = false;
+  if (!extras && a && split16::shape_ok(H, D, Dv, F) &&
+      split_layout_ok(q, k, v, a, ldq, ldk, ldv, num_rows, E, ex) && ex->ws_ds &&
+      lddq < (1 << 20) && lddq % 2 == 0 &&
+      (((uintptr_t)G | (uintptr_t)da | (uintptr_t)d_agg_v | (uintptr_t)agg_v |
+        (uintptr_t)abar | (uintptr_t)d_abar | (uintptr_t)Pbuf | (uintptr_t)ex->ws_ds) & 15) == 0 &&
+      ((uintptr_t)dq & 7) == 0) {
+    const bool has_dab = d_abar && abar;
+    split16::RowBwdArgs B;
+    B.logits = ex->ws_logits; B.k = k; B.ldk = (int)ldk; B.v = v; B.ldv = (int)ldv; B.a = a;
+    B.rowptr = rowptr; B.col = col; B.num_rows = num_rows;
+    B.Wk = Wk; B.bk = bk; B.scale_mode = scale_mode; B.scale_value = scale_value;
+    B.m = m; B.z = z; B.agg_v = agg_v; B.abar = abar; B.d_agg_v = d_agg_v; B.d_abar = d_abar;
+    B.dq = dq; B.lddq = (int)lddq; B.Pbuf = Pbuf; B.dS = ex->ws_ds;
+    const unsigned grid = (unsigned)ceil_div(num_rows, split16::kRowWarps);
+    const unsigned thr = split16::kRowWarps * kWarp;
+    const int rsm = split16::kRowBwdSmem16;
+#define SPT_ROW_BWD16(CPL)                                                                     \
+  do {                                                                                         \
+    if (has_dab && Wk) split16::k_row_bwd16<CPL, true, true><<<grid, thr, rsm, st>>>(B);       \
+    else if (has_dab) split16::k_row_bwd16<CPL, true, false><<<grid, thr, rsm, st>>>(B);       \
+    else if (Wk) split16::k_row_bwd16<CPL, false, true><<<grid, thr, rsm, st>>>(B);            \
+    else split16::k_row_bwd16<CPL, false, false><<<grid, thr, rsm, st>>>(B);                   \
+  } while (0)
+    if (Dv == 8) SPT_ROW_BWD16(4); else SPT_ROW_BWD16(2);
+#undef SPT_ROW_BWD16
+    rc = check_launch("attn_bwd_rows(row16)");
+    if (rc != SPT_OK) return rc;
+    split16::EdgeBwdArgs A;
+    A.q = q; A.ldq = (int)ldq; A.k = k; A.ldk = (int)ldk; A.a = a;
+    A.rowptr = rowptr; A.col = col; A.edge_row = ex->edge_row; A.E = E;
+    A.Wq = Wq; A.bq = bq; A.Wk = Wk; A.bk = bk;
+    A.scale_mode = scale_mode; A.scale_value = scale_value;
+    A.dS = ex->ws_ds; A.Pbuf = Pbuf; A.d_abar = has_dab ? d_abar : nullptr;
+    A.G = G; A.da = da;
+    split16::k_edge_bwd16<<<(unsigned)ceil_div(E, split16::kEdgeThreads), split16::kEdgeThreads,
+                            split16::kEdgeBwdSmem, st>>>(A);
+    rc = check_launch("attn_bwd_rows(edge16)");
+    if (rc != SPT_OK) return rc;
+    // d[Wq;Wk] = G^T a: tcgen05 gemm_tn on the packed gradient pair, else the slab reduction
+    if (E > 0 && ((Wq && (dWq || dbq)) || (Wk && (dWk || dbk)))) {
+      const bool packed = Wq && Wk && dWq && dWk && dWk == dWq + s.HD * s.F &&
+                          ((!dbq && !dbk) || (bq && bk && dbq && dbk && dbk == dbq + s.HD));
+      if (packed && E >= 2048 && umma::tn_shape_ok(G, E, s.HD2, s.HD2, a, s.F, s.F))
+        return umma::tn_launch(G, E, s.HD2, s.HD2, a, s.F, s.F, dWq, s.F, dbq, st);
+      return spt_attn_bwd_weights(G, a, E, H, D, F, Wq ? dWq : nullptr,
+                                  (Wq && bq) ? dbq : nullptr, Wk ? dWk : nullptr,
+                                  (Wk && bk) ? dbk : nullptr, stream_);
+    }
+    return SPT_OK;
+  }
   if (!extras && a && split::shape_ok(H, D, Dv, F) &&
       split_layout_ok(q, k, v, a, ldq, ldk, ldv, num_rows, E, ex) && ex->ws_ds &&
       lddq < (1 << 20) &&
@@ -941,6 +1023,20 @@ int spt_attn_bwd_targets_ex(const int32_t* csc_ptr, const int32_t* csc_src,
   if (rc != SPT_OK) return rc;
   SPT_REQUIRE(csc_ptr && dk && dv && (E == 0 || (csc_src && csc2csr && Pbuf && G && d_agg_v)),
               SPT_E_INVALID, "attn_bwd_targets: null pointer");
+  if (!d_q_tgt_add && split16::shape_ok(H, D, Dv, split16::kF) && lddv % 4 == 0 &&
+      lddk % 2 == 0 && lddk < (1 << 20) && lddv < (1 << 20) && E > 0 &&
+      (((uintptr_t)dv | (uintptr_t)d_agg_v) & 15) == 0 &&
+      (((uintptr_t)dk | (uintptr_t)G) & 7) == 0) {
+    // the shipped head layout (H = 16): csrc/attention_split16.cuh
+    split16::TgtArgs T;
+    T.csc_ptr = csc_ptr; T.csc_src = csc_src; T.csc2csr = csc2csr; T.num_targets = num_targets;
+    T.Pbuf = Pbuf; T.G = G; T.d_agg_v = d_agg_v;
+    T.dk = dk; T.lddk = (int)lddk; T.dv = dv; T.lddv = (int)lddv;
+    const unsigned grid = (unsigned)ceil_div(num_targets * 32, 256);
+    if (Dv == 8) split16::k_attn_bwd_targets16<4><<<grid, 256, 0, (cudaStream_t)stream_>>>(T);
+    else split16::k_attn_bwd_targets16<2><<<grid, 256, 0, (cudaStream_t)stream_>>>(T);
+    return check_launch("attn_bwd_targets(16)");
+  }
   if (!d_q_tgt_add && fast::shape_ok(H, D, Dv, fast::kF) && lddv % 4 == 0 && lddk < (1 << 20) &&
       lddv < (1 << 20) && (reinterpret_cast<uintptr_t>(dv) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(d_agg_v) & 15) == 0) {

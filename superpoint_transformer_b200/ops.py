@@ -872,6 +872,12 @@ def graph_norm(x, weight, bias, mean_scale, batch=None, batch_size=None, eps=1e-
 # ---------------------------------------------------------------------------
 # fused attention core
 # ---------------------------------------------------------------------------
+def _split_shape(H, D, Dv, F):
+    """shape families of the split attention kernels: the benchmark family (4 heads of 32
+    channels) and the shipped head layout (16 heads, C = 64 or 128)"""
+    return (H, D, Dv, F) == (4, 4, 32, 32) or (H == 16 and D == 4 and Dv in (4, 8) and F == 32)
+
+
 class _AttnCore(torch.autograd.Function):
     """q/k/v come either fused as qkv [N, 2HD+C] (kv=None) or as q [R,HD] and
     kv [T, HD+C].  Returns (agg_v [R,C], abar [R,H,F] or None, sump [R,H])."""
@@ -908,7 +914,7 @@ class _AttnCore(torch.autograd.Function):
         if has_ex:
             ex = _lib.AttnExtras(_p(q_row_add), _p(q_tgt_add), _p(k_row_add), _p(drop_mask),
                                  None, None, None, None)
-        elif ATTN_SPLIT and a is not None and (H, D, Dv, F) == (4, 4, 32, 32) and g.E > 0:
+        elif ATTN_SPLIT and a is not None and _split_shape(H, D, Dv, F) and g.E > 0:
             # workspace of the split kernels: base-2 logits [E, H] (kept for the backward)
             logits = torch.empty((g.E, H), dtype=torch.float32, device=dev)
             ex = _lib.AttnExtras(None, None, None, None, None, None, None, None,

@@ -32,12 +32,12 @@ def graph(n, seed, hub=False):
     return ei[:, torch.randperm(ei.shape[1], generator=g)]
 
 
-def run(N, seed, hub, want_abar, use_q, use_k, env, split=False):
+def run(N, seed, hub, want_abar, use_q, use_k, env, split=False, shape=(4, 4, 128, 32)):
     for k in ('SPT_ATTN_NO_TILE', 'SPT_ATTN_ROWS_PER_WARP'):
         os.environ.pop(k, None)
     os.environ.update(env)
     ops.set_attention_split(split)
-    H, D, C, F = 4, 4, 128, 32
+    H, D, C, F = shape
     g = torch.Generator().manual_seed(seed)
     ei = graph(N, seed, hub).to(DEV)
     E = ei.shape[1]
@@ -63,9 +63,9 @@ def run(N, seed, hub, want_abar, use_q, use_k, env, split=False):
     for nm, p in (('dWq', Wq), ('dbq', bq), ('dWk', Wk), ('dbk', bk)):
         if p is not None:
             out[nm] = p.grad
-    out['dq'] = qkv.grad[:, :16]
-    out['dk'] = qkv.grad[:, 16:32]
-    out['dv'] = qkv.grad[:, 32:]
+    out['dq'] = qkv.grad[:, :H * D]
+    out['dk'] = qkv.grad[:, H * D:2 * H * D]
+    out['dv'] = qkv.grad[:, 2 * H * D:]
     return {k: v.detach().clone() for k, v in out.items()}
 
 
@@ -92,7 +92,24 @@ def main():
                 line.append(f'{k}={err:.1e}' + ('(NaN)' if nan else ''))
             print(f'N={N} hub={hub} abar={want_abar} q={use_q} rpw={rpw}: ' + ' '.join(line),
                   flush=True)
+    # the shipped head layout (H = 16; C = 64 and 128): split16 kernels against the generic ones
+    for shape in ((16, 4, 64, 32), (16, 4, 128, 32)):
+        for N, seed, hub, want_abar, use_q, use_k in cases[:3]:
+            ref = run(N, seed, hub, want_abar, use_q, use_k, {}, split=False, shape=shape)
+            got = run(N, seed, hub, want_abar, use_q, use_k, {}, split=True, shape=shape)
+            line = []
+            for k in ref:
+                sc = max(float(ref[k].abs().max()), 1e-6)
+                err = float((got[k] - ref[k]).abs().max()) / sc
+                nan = bool(torch.isnan(got[k]).any())
+                if not (k == 'dbk' and not use_q):
+                    worst16 = max(globals().get('worst16', 0.0), err if not nan else 1e9)
+                    globals()['worst16'] = worst16
+                line.append(f'{k}={err:.1e}' + ('(NaN)' if nan else ''))
+            print(f'H16 C={shape[2]} N={N} hub={hub} abar={want_abar} q={use_q} rpw=split16: '
+                  + ' '.join(line), flush=True)
     print('WORST relative-to-scale difference:', worst)
+    print('WORST H=16 difference:', globals().get('worst16'))
 
 
 if __name__ == '__main__':
