@@ -659,8 +659,8 @@ int spt_attn_fwd_ex(const float* q, int64_t ldq, const float* k, int64_t ldk, co
     A.rowptr = rowptr; A.col = col; A.edge_row = ex->edge_row; A.E = E;
     A.Wq = Wq; A.bq = bq; A.Wk = Wk; A.bk = bk;
     A.scale_mode = scale_mode; A.scale_value = scale_value; A.logits = ex->ws_logits;
-    split16::k_edge_logits16<<<(unsigned)ceil_div(E, split16::kEdgeThreads),
-                               split16::kEdgeThreads, 0, st>>>(A);
+    split16::k_edge_logits16<<<(unsigned)ceil_div(ceil_div(E, 2), split16::kEdgeThreads),
+                               split16::kEdgeThreads, 0, st>>>(A);     // 2 edges per thread
     rc = check_launch("attn_fwd(edge16)");
     if (rc != SPT_OK) return rc;
     split16::RowFwdArgs B;
@@ -839,8 +839,8 @@ int spt_attn_bwd_rows_ex(const float* q, int64_t ldq, const float* k, int64_t ld
     A.scale_mode = scale_mode; A.scale_value = scale_value;
     A.dS = ex->ws_ds; A.Pbuf = Pbuf; A.d_abar = has_dab ? d_abar : nullptr;
     A.G = G; A.da = da;
-    split16::k_edge_bwd16<<<(unsigned)ceil_div(E, split16::kEdgeThreads), split16::kEdgeThreads,
-                            split16::kEdgeBwdSmem, st>>>(A);
+    split16::k_edge_bwd16<<<(unsigned)ceil_div(ceil_div(E, 2), split16::kEdgeThreads),
+                            split16::kEdgeThreads, split16::kEdgeBwdSmem, st>>>(A);   // 2 edges / thread
     rc = check_launch("attn_bwd_rows(edge16)");
     if (rc != SPT_OK) return rc;
     // d[Wq;Wk] = G^T a: tcgen05 gemm_tn on the packed gradient pair, else the slab reduction

@@ -89,43 +89,91 @@ __device__ __forceinline__ void rpe_group(float (&acc)[32], const float (&af)[kF
   for (int o = 0; o < 16; ++o) fast::unpack2(acc2[o], acc[2 * o], acc[2 * o + 1]);
 }
 
+// R of TWO edges per thread: every 16-byte weight read from shared memory feeds 8 packed FMAs
+// instead of 4 (the one-edge version is bound by the LDS pipe: 1 LDS.128 per 2 FFMA2)
+__device__ __forceinline__ void rpe_group2(float (&acc0)[32], float (&acc1)[32],
+                                           const float (&af0)[kF], const float (&af1)[kF],
+                                           const float (*Wg)[32], const float* bg) {
+  fast::f32x2 a0[16], a1[16];
+#pragma unroll
+  for (int o = 0; o < 16; ++o) a0[o] = a1[o] = fast::pack2(bg[2 * o], bg[2 * o + 1]);
+#pragma unroll
+  for (int f = 0; f < kF; ++f) {
+    const fast::f32x2 x0 = fast::pack2(af0[f], af0[f]), x1 = fast::pack2(af1[f], af1[f]);
+    const ulonglong2* wr = reinterpret_cast<const ulonglong2*>(Wg[f]);
+#pragma unroll
+    for (int o4 = 0; o4 < 8; ++o4) {
+      const ulonglong2 w = wr[o4];
+      fast::fma2(a0[2 * o4], x0, w.x);
+      fast::fma2(a0[2 * o4 + 1], x0, w.y);
+      fast::fma2(a1[2 * o4], x1, w.x);
+      fast::fma2(a1[2 * o4 + 1], x1, w.y);
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 16; ++o) {
+    fast::unpack2(a0[o], acc0[2 * o], acc0[2 * o + 1]);
+    fast::unpack2(a1[o], acc1[2 * o], acc1[2 * o + 1]);
+  }
+}
+
+__device__ __forceinline__ void load_row32(float (&af)[kF], const float* p) {
+  const float4* ap = reinterpret_cast<const float4*>(p);
+#pragma unroll
+  for (int j = 0; j < kF / 4; ++j) {
+    const float4 t = __ldg(ap + j);
+    af[4 * j] = t.x; af[4 * j + 1] = t.y; af[4 * j + 2] = t.z; af[4 * j + 3] = t.w;
+  }
+}
+
+// logits of 4 heads of one edge from its R (q part acc[0..15], k part acc[16..31])
+__device__ __forceinline__ float4 group_logits(const float (&acc)[32], const float4* qp,
+                                               const float4* kp, float scale) {
+  float lg[4];
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    const float4 q4 = __ldg(qp + h), k4 = __ldg(kp + h);
+    float s = fmaf(q4.x, scale, acc[4 * h + 0]) * (k4.x + acc[16 + 4 * h + 0]);
+    s = fmaf(fmaf(q4.y, scale, acc[4 * h + 1]), k4.y + acc[16 + 4 * h + 1], s);
+    s = fmaf(fmaf(q4.z, scale, acc[4 * h + 2]), k4.z + acc[16 + 4 * h + 2], s);
+    s = fmaf(fmaf(q4.w, scale, acc[4 * h + 3]), k4.w + acc[16 + 4 * h + 3], s);
+    lg[h] = s * kLog2e;
+  }
+  return make_float4(lg[0], lg[1], lg[2], lg[3]);
+}
+
+// thread = edges 2t and 2t + 1 (the second one clamped to the last edge; its store is skipped)
 __global__ void __launch_bounds__(kEdgeThreads)
 k_edge_logits16(const EdgeFwdArgs P) {
   __shared__ __align__(16) float W_s[kGroups][kF][32];
   __shared__ __align__(16) float b_s[kGroups][32];
   load_weights16(W_s, b_s, P.Wq, P.bq, P.Wk, P.bk);
   __syncthreads();
-  const int64_t e = (int64_t)blockIdx.x * kEdgeThreads + threadIdx.x;
-  if (e >= P.E) return;
-  const int row = P.edge_row[e], c = P.col[e];
-  float af[kF];
-  {
-    const float4* ap = reinterpret_cast<const float4*>(P.a + e * kF);
-#pragma unroll
-    for (int j = 0; j < kF / 4; ++j) {
-      const float4 t = __ldg(ap + j);
-      af[4 * j] = t.x; af[4 * j + 1] = t.y; af[4 * j + 2] = t.z; af[4 * j + 3] = t.w;
-    }
-  }
-  const float scale =
-      fast::qk_scale_fast(P.scale_mode, P.scale_value, P.rowptr[row + 1] - P.rowptr[row]);
-  const float4* qp = reinterpret_cast<const float4*>(P.q + (int64_t)row * P.ldq);
-  const float4* kp = reinterpret_cast<const float4*>(P.k + (int64_t)c * P.ldk);
+  const int64_t e0 = 2 * ((int64_t)blockIdx.x * kEdgeThreads + threadIdx.x);
+  if (e0 >= P.E) return;
+  const bool two = e0 + 1 < P.E;
+  const int64_t e1 = two ? e0 + 1 : e0;
+  const int row0 = P.edge_row[e0], c0 = P.col[e0], row1 = P.edge_row[e1], c1 = P.col[e1];
+  float af0[kF], af1[kF];
+  load_row32(af0, P.a + e0 * kF);
+  load_row32(af1, P.a + e1 * kF);
+  const float sc0 =
+      fast::qk_scale_fast(P.scale_mode, P.scale_value, P.rowptr[row0 + 1] - P.rowptr[row0]);
+  const float sc1 =
+      fast::qk_scale_fast(P.scale_mode, P.scale_value, P.rowptr[row1 + 1] - P.rowptr[row1]);
+  const float4* qp0 = reinterpret_cast<const float4*>(P.q + (int64_t)row0 * P.ldq);
+  const float4* kp0 = reinterpret_cast<const float4*>(P.k + (int64_t)c0 * P.ldk);
+  const float4* qp1 = reinterpret_cast<const float4*>(P.q + (int64_t)row1 * P.ldq);
+  const float4* kp1 = reinterpret_cast<const float4*>(P.k + (int64_t)c1 * P.ldk);
 #pragma unroll 1
   for (int g = 0; g < kGroups; ++g) {
-    float acc[32];
-    rpe_group(acc, af, W_s[g], b_s[g]);
-    float lg[4];
-#pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      const float4 q4 = __ldg(qp + 4 * g + h), k4 = __ldg(kp + 4 * g + h);
-      float s = fmaf(q4.x, scale, acc[4 * h + 0]) * (k4.x + acc[16 + 4 * h + 0]);
-      s = fmaf(fmaf(q4.y, scale, acc[4 * h + 1]), k4.y + acc[16 + 4 * h + 1], s);
-      s = fmaf(fmaf(q4.z, scale, acc[4 * h + 2]), k4.z + acc[16 + 4 * h + 2], s);
-      s = fmaf(fmaf(q4.w, scale, acc[4 * h + 3]), k4.w + acc[16 + 4 * h + 3], s);
-      lg[h] = s * kLog2e;
-    }
-    *reinterpret_cast<float4*>(P.logits + e * kH + 4 * g) = make_float4(lg[0], lg[1], lg[2], lg[3]);
+    float acc0[32], acc1[32];
+    rpe_group2(acc0, acc1, af0, af1, W_s[g], b_s[g]);
+    *reinterpret_cast<float4*>(P.logits + e0 * kH + 4 * g) =
+        group_logits(acc0, qp0 + 4 * g, kp0 + 4 * g, sc0);
+    if (two)
+      *reinterpret_cast<float4*>(P.logits + e1 * kH + 4 * g) =
+          group_logits(acc1, qp1 + 4 * g, kp1 + 4 * g, sc1);
   }
 }
 
@@ -142,86 +190,40 @@ struct EdgeBwdArgs {
   float* da;                            // [E, 32] nullable
 };
 
-__global__ void __launch_bounds__(kEdgeThreads)
-k_edge_bwd16(const EdgeBwdArgs P) {
-  extern __shared__ __align__(16) float edge16_smem[];
-  float (*W_s)[kF][32] = reinterpret_cast<float (*)[kF][32]>(edge16_smem);            // [g][f][o]
-  float (*Wn_s)[32][kF] = reinterpret_cast<float (*)[32][kF]>(edge16_smem + kGroups * kF * 32);  // [g][o][f]
-  float (*b_s)[32] = reinterpret_cast<float (*)[32]>(edge16_smem + 2 * kGroups * kF * 32);
-  load_weights16(W_s, b_s, P.Wq, P.bq, P.Wk, P.bk);
-  for (int i = threadIdx.x; i < kGroups * 32 * kF; i += blockDim.x) {
-    const int g = i / (32 * kF), o = (i / kF) % 32, f = i % kF;
-    const float* W = o < 16 ? P.Wq : P.Wk;
-    Wn_s[g][o][f] = W ? W[(16 * g + (o & 15)) * kF + f] : 0.f;
-  }
-  __syncthreads();
-  const int64_t e = (int64_t)blockIdx.x * kEdgeThreads + threadIdx.x;
-  if (e >= P.E) return;
-  const int row = P.edge_row[e], c = P.col[e];
-  float af[kF];
-  {
-    const float4* ap = reinterpret_cast<const float4*>(P.a + e * kF);
+// G of 4 heads of one edge from its R, dS, q, k; stored to G [E, 128] = [dq_e (64) | dk_e (64)]
+__device__ __forceinline__ void group_G(float (&G)[32], const float (&acc)[32], const float4* qp,
+                                        const float4* kp, float scale, const float4 ds4,
+                                        float* Gq, float* Gk, bool store) {
+  const float dsv[4] = {ds4.x, ds4.y, ds4.z, ds4.w};
 #pragma unroll
-    for (int j = 0; j < kF / 4; ++j) {
-      const float4 t = __ldg(ap + j);
-      af[4 * j] = t.x; af[4 * j + 1] = t.y; af[4 * j + 2] = t.z; af[4 * j + 3] = t.w;
+  for (int h = 0; h < 4; ++h) {
+    const float4 q4 = __ldg(qp + h), k4 = __ldg(kp + h);
+    const float qv[4] = {q4.x, q4.y, q4.z, q4.w}, kv[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+    for (int d = 0; d < kD; ++d) {
+      const float qe = fmaf(qv[d], scale, acc[4 * h + d]);
+      const float ke = kv[d] + acc[16 + 4 * h + d];
+      G[4 * h + d] = dsv[h] * ke;
+      G[16 + 4 * h + d] = dsv[h] * qe;
     }
   }
-  const float scale =
-      fast::qk_scale_fast(P.scale_mode, P.scale_value, P.rowptr[row + 1] - P.rowptr[row]);
-  const float4* qp = reinterpret_cast<const float4*>(P.q + (int64_t)row * P.ldq);
-  const float4* kp = reinterpret_cast<const float4*>(P.k + (int64_t)c * P.ldk);
-  const float4* dsp = reinterpret_cast<const float4*>(P.dS + e * kH);
-  fast::f32x2 da2[kF / 2];
-#pragma unroll
-  for (int f = 0; f < kF / 2; ++f) da2[f] = 0ull;
-#pragma unroll 1
-  for (int g = 0; g < kGroups; ++g) {
-    float acc[32];
-    rpe_group(acc, af, W_s[g], b_s[g]);
-    const float4 ds4 = __ldg(dsp + g);
-    const float dsv[4] = {ds4.x, ds4.y, ds4.z, ds4.w};
-    float G[32];
-#pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      const float4 q4 = __ldg(qp + 4 * g + h), k4 = __ldg(kp + 4 * g + h);
-      const float qv[4] = {q4.x, q4.y, q4.z, q4.w}, kv[4] = {k4.x, k4.y, k4.z, k4.w};
-#pragma unroll
-      for (int d = 0; d < kD; ++d) {
-        const float qe = fmaf(qv[d], scale, acc[4 * h + d]);
-        const float ke = kv[d] + acc[16 + 4 * h + d];
-        G[4 * h + d] = dsv[h] * ke;
-        G[16 + 4 * h + d] = dsv[h] * qe;
-      }
-    }
-    float4* gq = reinterpret_cast<float4*>(P.G + e * (2 * kHD) + 16 * g);
-    float4* gk = reinterpret_cast<float4*>(P.G + e * (2 * kHD) + kHD + 16 * g);
+  if (store) {
+    float4* gq = reinterpret_cast<float4*>(Gq);
+    float4* gk = reinterpret_cast<float4*>(Gk);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       gq[j] = make_float4(G[4 * j], G[4 * j + 1], G[4 * j + 2], G[4 * j + 3]);
       gk[j] = make_float4(G[16 + 4 * j], G[16 + 4 * j + 1], G[16 + 4 * j + 2], G[16 + 4 * j + 3]);
     }
-    if (P.da) {
-#pragma unroll
-      for (int o = 0; o < 32; ++o) {
-        const fast::f32x2 g2 = fast::pack2(G[o], G[o]);
-        const ulonglong2* wr = reinterpret_cast<const ulonglong2*>(Wn_s[g][o]);
-#pragma unroll
-        for (int f4 = 0; f4 < kF / 4; ++f4) {
-          const ulonglong2 w = wr[f4];
-          fast::fma2(da2[2 * f4], g2, w.x);
-          fast::fma2(da2[2 * f4 + 1], g2, w.y);
-        }
-      }
-    }
   }
-  if (!P.da) return;
-  float da[kF];
-#pragma unroll
-  for (int f = 0; f < kF / 2; ++f) fast::unpack2(da2[f], da[2 * f], da[2 * f + 1]);
-  if (P.d_abar) {
-    const float4* pp = reinterpret_cast<const float4*>(P.Pbuf + e * kH);
-    const float4* dab = reinterpret_cast<const float4*>(P.d_abar + (int64_t)row * (kH * kF));
+}
+
+// da += sum_h p_h dAbar[row][h][:] (16 heads), then store
+__device__ __forceinline__ void finish_da(float (&da)[kF], const float* Pbuf_e,
+                                          const float* dab_row, float* out) {
+  if (dab_row) {
+    const float4* pp = reinterpret_cast<const float4*>(Pbuf_e);
+    const float4* dab = reinterpret_cast<const float4*>(dab_row);
 #pragma unroll 1
     for (int g = 0; g < kGroups; ++g) {
       const float4 p4 = __ldg(pp + g);
@@ -239,10 +241,87 @@ k_edge_bwd16(const EdgeBwdArgs P) {
       }
     }
   }
-  float4* dp = reinterpret_cast<float4*>(P.da + e * kF);
+  float4* dp = reinterpret_cast<float4*>(out);
 #pragma unroll
   for (int j = 0; j < kF / 4; ++j)
     dp[j] = make_float4(da[4 * j], da[4 * j + 1], da[4 * j + 2], da[4 * j + 3]);
+}
+
+// thread = edges 2t and 2t + 1: every weight read feeds both (see rpe_group2)
+__global__ void __launch_bounds__(kEdgeThreads)
+k_edge_bwd16(const EdgeBwdArgs P) {
+  extern __shared__ __align__(16) float edge16_smem[];
+  float (*W_s)[kF][32] = reinterpret_cast<float (*)[kF][32]>(edge16_smem);            // [g][f][o]
+  float (*Wn_s)[32][kF] = reinterpret_cast<float (*)[32][kF]>(edge16_smem + kGroups * kF * 32);  // [g][o][f]
+  float (*b_s)[32] = reinterpret_cast<float (*)[32]>(edge16_smem + 2 * kGroups * kF * 32);
+  load_weights16(W_s, b_s, P.Wq, P.bq, P.Wk, P.bk);
+  for (int i = threadIdx.x; i < kGroups * 32 * kF; i += blockDim.x) {
+    const int g = i / (32 * kF), o = (i / kF) % 32, f = i % kF;
+    const float* W = o < 16 ? P.Wq : P.Wk;
+    Wn_s[g][o][f] = W ? W[(16 * g + (o & 15)) * kF + f] : 0.f;
+  }
+  __syncthreads();
+  const int64_t e0 = 2 * ((int64_t)blockIdx.x * kEdgeThreads + threadIdx.x);
+  if (e0 >= P.E) return;
+  const bool two = e0 + 1 < P.E;
+  const int64_t e1 = two ? e0 + 1 : e0;
+  const int row0 = P.edge_row[e0], c0 = P.col[e0], row1 = P.edge_row[e1], c1 = P.col[e1];
+  float af0[kF], af1[kF];
+  load_row32(af0, P.a + e0 * kF);
+  load_row32(af1, P.a + e1 * kF);
+  const float sc0 =
+      fast::qk_scale_fast(P.scale_mode, P.scale_value, P.rowptr[row0 + 1] - P.rowptr[row0]);
+  const float sc1 =
+      fast::qk_scale_fast(P.scale_mode, P.scale_value, P.rowptr[row1 + 1] - P.rowptr[row1]);
+  const float4* qp0 = reinterpret_cast<const float4*>(P.q + (int64_t)row0 * P.ldq);
+  const float4* kp0 = reinterpret_cast<const float4*>(P.k + (int64_t)c0 * P.ldk);
+  const float4* qp1 = reinterpret_cast<const float4*>(P.q + (int64_t)row1 * P.ldq);
+  const float4* kp1 = reinterpret_cast<const float4*>(P.k + (int64_t)c1 * P.ldk);
+  const float4* ds0 = reinterpret_cast<const float4*>(P.dS + e0 * kH);
+  const float4* ds1 = reinterpret_cast<const float4*>(P.dS + e1 * kH);
+  fast::f32x2 da0[kF / 2], da1[kF / 2];
+#pragma unroll
+  for (int f = 0; f < kF / 2; ++f) da0[f] = da1[f] = 0ull;
+#pragma unroll 1
+  for (int g = 0; g < kGroups; ++g) {
+    float acc0[32], acc1[32];
+    rpe_group2(acc0, acc1, af0, af1, W_s[g], b_s[g]);
+    float G0[32], G1[32];
+    group_G(G0, acc0, qp0 + 4 * g, kp0 + 4 * g, sc0, __ldg(ds0 + g),
+            P.G + e0 * (2 * kHD) + 16 * g, P.G + e0 * (2 * kHD) + kHD + 16 * g, true);
+    group_G(G1, acc1, qp1 + 4 * g, kp1 + 4 * g, sc1, __ldg(ds1 + g),
+            P.G + e1 * (2 * kHD) + 16 * g, P.G + e1 * (2 * kHD) + kHD + 16 * g, two);
+    if (P.da) {
+#pragma unroll
+      for (int o = 0; o < 32; ++o) {
+        const fast::f32x2 g0 = fast::pack2(G0[o], G0[o]), g1 = fast::pack2(G1[o], G1[o]);
+        const ulonglong2* wr = reinterpret_cast<const ulonglong2*>(Wn_s[g][o]);
+#pragma unroll
+        for (int f4 = 0; f4 < kF / 4; ++f4) {
+          const ulonglong2 w = wr[f4];
+          fast::fma2(da0[2 * f4], g0, w.x);
+          fast::fma2(da0[2 * f4 + 1], g0, w.y);
+          fast::fma2(da1[2 * f4], g1, w.x);
+          fast::fma2(da1[2 * f4 + 1], g1, w.y);
+        }
+      }
+    }
+  }
+  if (!P.da) return;
+  {
+    float da[kF];
+#pragma unroll
+    for (int f = 0; f < kF / 2; ++f) fast::unpack2(da0[f], da[2 * f], da[2 * f + 1]);
+    finish_da(da, P.Pbuf + e0 * kH, P.d_abar ? P.d_abar + (int64_t)row0 * (kH * kF) : nullptr,
+              P.da + e0 * kF);
+  }
+  if (two) {
+    float da[kF];
+#pragma unroll
+    for (int f = 0; f < kF / 2; ++f) fast::unpack2(da1[f], da[2 * f], da[2 * f + 1]);
+    finish_da(da, P.Pbuf + e1 * kH, P.d_abar ? P.d_abar + (int64_t)row1 * (kH * kF) : nullptr,
+              P.da + e1 * kF);
+  }
 }
 constexpr int kEdgeBwdSmem = (2 * kGroups * kF * 32 + kGroups * 32) * 4;
 
