@@ -100,9 +100,12 @@ def bench_config(cfg_name, world):
            if c['scaling'] == 'weak' else
            f"scene/tile-shard dp{world} (fixed work per step split over the ranks by edge "
            f"count, flat NCCL grad all-reduce)")
-    return {"workload": c['workload'], "name": cfg_name, "levels": c['levels'],
-            "parallelism": par,
-            "l2": "inputs_exceed_l2 (per-step working set > 126 MB; no flush needed)"}
+    out = {"workload": c['workload'], "name": cfg_name, "levels": c['levels'],
+           "parallelism": par,
+           "l2": "inputs_exceed_l2 (per-step working set > 126 MB; no flush needed)"}
+    if (DIM, HEADS) != (128, 4):   # --model shipped64 / shipped128: not a BASELINE configuration
+        out["model_variant"] = f"C={DIM}, {HEADS} heads (head layout of the shipped configs)"
+    return out
 
 
 # --------------------------------------------------------------------------- #
@@ -910,7 +913,15 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='eager launches, no CUDA graphs')
     ap.add_argument('--kernels-out', default=None, help='write the full per-kernel timing table (JSON)')
+    ap.add_argument('--model', default='baseline', choices=['baseline', 'shipped64', 'shipped128'],
+                    help="'baseline': the BASELINE.json model (C=128, 4 heads); 'shipped64' / "
+                         "'shipped128': the head layout of the shipped configs (16 heads, C = 64 "
+                         "as S3DIS / DALES, C = 128 as KITTI-360) on the same graphs — not a "
+                         "BASELINE configuration, reported with `config.model_variant`")
     args = ap.parse_args()
+    if args.model != 'baseline':
+        global DIM, HEADS
+        DIM, HEADS = (64, 16) if args.model == 'shipped64' else (128, 16)
     args.warmup = max(args.warmup, 3) if args.impl == 'own' else args.warmup
     if args.impl == 'reference':
         run_reference(args)
