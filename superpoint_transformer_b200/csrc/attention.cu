@@ -659,10 +659,30 @@ int spt_attn_fwd_ex(const float* q, int64_t ldq, const float* k, int64_t ldk, co
     A.rowptr = rowptr; A.col = col; A.edge_row = ex->edge_row; A.E = E;
     A.Wq = Wq; A.bq = bq; A.Wk = Wk; A.bk = bk;
     A.scale_mode = scale_mode; A.scale_value = scale_value; A.logits = ex->ws_logits;
-    split16::k_edge_logits16<<<(unsigned)ceil_div(ceil_div(E, 2), split16::kEdgeThreads),
-                               split16::kEdgeThreads, 0, st>>>(A);     // 2 edges per thread
-    rc = check_launch("attn_fwd(edge16)");
-    if (rc != SPT_OK) return rc;
+    // the logits of 16 heads = 4 independent 4-head problems: the tcgen05 edge pass of the
+    // 4-head family, once per head group (q / k / encoder rows offset by 16 g, logits strided);
+    // the CUDA-core pass (2 edges per thread) when the tensor map cannot be encoded
+    bool done16 = false;
+    if (!getenv("SPT_ATTN_EDGE_SIMPLE")) {
+      done16 = true;
+      for (int g = 0; g < 4 && done16; ++g) {
+        split::EdgeFwdArgs Ag;
+        Ag.q = q + 16 * g; Ag.ldq = (int)ldq; Ag.k = k + 16 * g; Ag.ldk = (int)ldk; Ag.a = a;
+        Ag.rowptr = rowptr; Ag.col = col; Ag.edge_row = ex->edge_row; Ag.E = E;
+        Ag.Wq = Wq ? Wq + 16 * g * F : nullptr; Ag.bq = bq ? bq + 16 * g : nullptr;
+        Ag.Wk = Wk ? Wk + 16 * g * F : nullptr; Ag.bk = bk ? bk + 16 * g : nullptr;
+        Ag.scale_mode = scale_mode; Ag.scale_value = scale_value;
+        Ag.logits = ex->ws_logits + 4 * g; Ag.ldl = 16;
+        if (!aumma::edge_logits_launch(Ag, st, &rc)) done16 = false;
+        else if (rc != SPT_OK) return rc;
+      }
+    }
+    if (!done16) {
+      split16::k_edge_logits16<<<(unsigned)ceil_div(ceil_div(E, 2), split16::kEdgeThreads),
+                                 split16::kEdgeThreads, 0, st>>>(A);     // 2 edges per thread
+      rc = check_launch("attn_fwd(edge16)");
+      if (rc != SPT_OK) return rc;
+    }
     split16::RowFwdArgs B;
     B.logits = ex->ws_logits; B.v = v; B.ldv = (int)ldv; B.a = a;
     B.rowptr = rowptr; B.col = col; B.num_rows = num_rows;
@@ -690,7 +710,7 @@ int spt_attn_fwd_ex(const float* q, int64_t ldq, const float* k, int64_t ldk, co
     A.rowptr = rowptr; A.col = col; A.edge_row = ex->edge_row; A.E = E;
     A.Wq = Wq; A.bq = bq; A.Wk = Wk; A.bk = bk;
     A.scale_mode = scale_mode; A.scale_value = scale_value;
-    A.logits = ex->ws_logits;
+    A.logits = ex->ws_logits; A.ldl = 4;
     // tcgen05 tiles of 128 edges; the CUDA-core pass when the tensor map cannot be encoded
     // (or SPT_ATTN_EDGE_SIMPLE is set: the A/B of the tests)
     if (getenv("SPT_ATTN_EDGE_SIMPLE") || !aumma::edge_logits_launch(A, st, &rc)) {

@@ -104,7 +104,8 @@ struct EdgeFwdArgs {
   int64_t E;
   const float* Wq; const float* bq; const float* Wk; const float* bk;   // each nullable
   int scale_mode; float scale_value;
-  float* logits;                        // [E, 4], base-2 units
+  float* logits;                        // [E, ldl]: 4 base-2 logits per edge at logits + e * ldl
+  int ldl;                              // 4; 16 when a 16-head problem runs as 4 head groups
 };
 
 constexpr int kEdgeThreads = 256;
@@ -169,7 +170,7 @@ k_edge_logits_simple(const EdgeFwdArgs P) {
     s = fmaf(fmaf(q4.w, scale, acc[4 * h + 3]), k4.w + acc[kHD + 4 * h + 3], s);
     lg[h] = s * kLog2e;
   }
-  *reinterpret_cast<float4*>(P.logits + e * kH) = make_float4(lg[0], lg[1], lg[2], lg[3]);
+  *reinterpret_cast<float4*>(P.logits + e * P.ldl) = make_float4(lg[0], lg[1], lg[2], lg[3]);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -325,7 +325,7 @@ k_edge_logits_umma(const __grid_constant__ CUtensorMap tmA, const split::EdgeFwd
         lg[h] = s * fast::kLog2e;
       }
       if (valid)
-        *reinterpret_cast<float4*>(P.logits + e * 4) = make_float4(lg[0], lg[1], lg[2], lg[3]);
+        *reinterpret_cast<float4*>(P.logits + e * P.ldl) = make_float4(lg[0], lg[1], lg[2], lg[3]);
       // the warp's rows of this stage are free: stage the tile two turns ahead, fetch the ids
       // after it
       __syncwarp();
