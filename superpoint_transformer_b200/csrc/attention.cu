@@ -859,10 +859,38 @@ int spt_attn_bwd_rows_ex(const float* q, int64_t ldq, const float* k, int64_t ld
     A.scale_mode = scale_mode; A.scale_value = scale_value;
     A.dS = ex->ws_ds; A.Pbuf = Pbuf; A.d_abar = has_dab ? d_abar : nullptr;
     A.G = G; A.da = da;
-    split16::k_edge_bwd16<<<(unsigned)ceil_div(ceil_div(E, 2), split16::kEdgeThreads),
-                            split16::kEdgeThreads, split16::kEdgeBwdSmem, st>>>(A);   // 2 edges / thread
-    rc = check_launch("attn_bwd_rows(edge16)");
-    if (rc != SPT_OK) return rc;
+    // G and da of 16 heads = the tcgen05 edge pass of the 4-head family once per head group:
+    // G halves stored at their columns of [E, 128], da summed by TMA reduce-add stores.  The
+    // CUDA-core pass (2 edges per thread) is the fallback.
+    bool done16 = false;
+    if (!getenv("SPT_ATTN_EDGE_SIMPLE")) {
+      done16 = true;
+      for (int g = 0; g < 4 && done16; ++g) {
+        split::EdgeBwdArgs Ag;
+        Ag.q = q + 16 * g; Ag.ldq = (int)ldq; Ag.k = k + 16 * g; Ag.ldk = (int)ldk; Ag.a = a;
+        Ag.rowptr = rowptr; Ag.col = col; Ag.edge_row = ex->edge_row; Ag.E = E;
+        Ag.Wq = Wq ? Wq + 16 * g * F : nullptr; Ag.bq = bq ? bq + 16 * g : nullptr;
+        Ag.Wk = Wk ? Wk + 16 * g * F : nullptr; Ag.bk = bk ? bk + 16 * g : nullptr;
+        Ag.scale_mode = scale_mode; Ag.scale_value = scale_value;
+        Ag.dS = ex->ws_ds + 4 * g; Ag.Pbuf = Pbuf + 4 * g;
+        Ag.d_abar = has_dab ? d_abar + 128 * g : nullptr;
+        Ag.G = G; Ag.da = da;
+        Ag.ld_ds = 16; Ag.ld_dab = 512; Ag.g_mode = 1;
+        Ag.g_col_q = 16 * g; Ag.g_col_k = 64 + 16 * g; Ag.da_reduce = g > 0;
+        if (!aumma::edge_bwd_launch(Ag, st, &rc)) done16 = false;
+        else if (rc != SPT_OK) return rc;
+        if (!done16 && g > 0) {
+          set_error("attn_bwd_rows: tensor map failed after the first head group");
+          return SPT_E_UNSUPPORTED;
+        }
+      }
+    }
+    if (!done16) {
+      split16::k_edge_bwd16<<<(unsigned)ceil_div(ceil_div(E, 2), split16::kEdgeThreads),
+                              split16::kEdgeThreads, split16::kEdgeBwdSmem, st>>>(A);   // 2 edges / thread
+      rc = check_launch("attn_bwd_rows(edge16)");
+      if (rc != SPT_OK) return rc;
+    }
     // d[Wq;Wk] = G^T a: tcgen05 gemm_tn on the packed gradient pair, else the slab reduction
     if (E > 0 && ((Wq && (dWq || dbq)) || (Wk && (dWk || dbk)))) {
       const bool packed = Wq && Wk && dWq && dWk && dWk == dWq + s.HD * s.F &&
@@ -915,6 +943,7 @@ int spt_attn_bwd_rows_ex(const float* q, int64_t ldq, const float* k, int64_t ld
     A.scale_mode = scale_mode; A.scale_value = scale_value;
     A.dS = ex->ws_ds; A.Pbuf = Pbuf; A.d_abar = has_dab ? d_abar : nullptr;
     A.G = G; A.da = da;
+    A.ld_ds = 4; A.ld_dab = 128; A.g_mode = 0; A.g_col_q = 0; A.g_col_k = 0; A.da_reduce = 0;
     if (getenv("SPT_ATTN_EDGE_SIMPLE") || !aumma::edge_bwd_launch(A, st, &rc)) {
       split::k_edge_bwd_simple<<<(unsigned)ceil_div(E, split::kEdgeThreads), split::kEdgeThreads,
                                  0, st>>>(A);

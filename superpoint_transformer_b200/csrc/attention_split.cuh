@@ -743,6 +743,13 @@ struct EdgeBwdArgs {
   const float* dS; const float* Pbuf; const float* d_abar;   // d_abar nullable
   float* G;                             // [E, 32]
   float* da;                            // [E, 32] nullable
+  // tcgen05 pass only — a 16-head problem run as 4 launches over head groups (the simple pass
+  // and the 4-head callers use the defaults 4 / 128 / 0):
+  int ld_ds;                            // floats between the dS / P rows of consecutive edges
+  int ld_dab;                           // floats between the dAbar rows of consecutive nodes
+  int g_mode;                           // 1: G is [E, 128]: dq_e half at column g_col_q, dk_e at g_col_k
+  int g_col_q, g_col_k;
+  int da_reduce;                        // 1: da += (TMA reduce-add store) instead of da =
 };
 
 __global__ void __launch_bounds__(kEdgeThreads)

@@ -20,6 +20,8 @@
 namespace spt {
 namespace umma {  // csrc/gemm_umma.cu
 bool make_map_rows32(CUtensorMap* tm, const float* ptr, int64_t rows, int64_t ld, int box_rows);
+bool make_map_box(CUtensorMap* tm, const float* ptr, int64_t rows, int64_t cols, int64_t ld,
+                  int box_cols, int box_rows);
 }
 namespace aumma {
 
@@ -537,10 +539,10 @@ k_edge_bwd_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     auto stage_all = [&](uint32_t st, const EdgeIds& id, int64_t t) {
       if (id.valid) {
         const int64_t e = t * kTileRows + row;
-        cp_async16_cg(mysp + st * (kTileRows * 32), P.dS + e * 4);
+        cp_async16_cg(mysp + st * (kTileRows * 32), P.dS + e * P.ld_ds);
         if (P.d_abar) {
-          cp_async16_cg(mysp + st * (kTileRows * 32) + 16, P.Pbuf + e * 4);
-          const char* dab = reinterpret_cast<const char*>(P.d_abar + (int64_t)id.rr * 128);
+          cp_async16_cg(mysp + st * (kTileRows * 32) + 16, P.Pbuf + e * P.ld_ds);
+          const char* dab = reinterpret_cast<const char*>(P.d_abar + (int64_t)id.rr * P.ld_dab);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(dab + 128 * j) : "memory");
@@ -556,6 +558,34 @@ k_edge_bwd_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (lane == 0) {
         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::
                          "l"(tm), "r"(src_wbase), "r"(0), "r"((int)(t * kTileRows + q * 32))
+                     : "memory");
+        bulk_commit();
+      }
+    };
+    // da of a later head group: added to what the earlier launches stored (TMA reduce-add)
+    auto reduce_rows = [&](const CUtensorMap* tm, uint32_t src_wbase, int64_t t) {
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile(
+            "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::
+                "l"(tm), "r"(src_wbase), "r"(0), "r"((int)(t * kTileRows + q * 32))
+            : "memory");
+        bulk_commit();
+      }
+    };
+    // G of one head group of a 16-head problem: two 16-column boxes of G [E, 128] (unswizzled
+    // 64-byte staging rows: dq_e half at wsrc, dk_e half at wsrc + 2 KB)
+    auto store_halves = [&](const CUtensorMap* tm, uint32_t src_wbase, int64_t t) {
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        const int r0 = (int)(t * kTileRows + q * 32);
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::
+                         "l"(tm), "r"(src_wbase), "r"(P.g_col_q), "r"(r0)
+                     : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::
+                         "l"(tm), "r"(src_wbase + 2048u), "r"(P.g_col_k), "r"(r0)
                      : "memory");
         bulk_commit();
       }
@@ -607,11 +637,22 @@ k_edge_bwd_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       // G leaves through my (now dead) q / k stage row: swizzled staging row + TMA store
       __syncwarp();
+      if (P.g_mode) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        sts128(src + (uint32_t)((j ^ sw) << 4),
-               make_float4(G[4 * j], G[4 * j + 1], G[4 * j + 2], G[4 * j + 3]));
-      store_rows(&tmG, wsrc, t);
+        for (int j = 0; j < 4; ++j) {
+          sts128(wsrc + (uint32_t)lane * 64u + 16u * j,
+                 make_float4(G[4 * j], G[4 * j + 1], G[4 * j + 2], G[4 * j + 3]));
+          sts128(wsrc + 2048u + (uint32_t)lane * 64u + 16u * j,
+                 make_float4(G[16 + 4 * j], G[16 + 4 * j + 1], G[16 + 4 * j + 2], G[16 + 4 * j + 3]));
+        }
+        store_halves(&tmG, wsrc, t);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          sts128(src + (uint32_t)((j ^ sw) << 4),
+                 make_float4(G[4 * j], G[4 * j + 1], G[4 * j + 2], G[4 * j + 3]));
+        store_rows(&tmG, wsrc, t);
+      }
       if (P.da) {
         {
           uint32_t hi[32], lo[32];
@@ -635,7 +676,7 @@ k_edge_bwd_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (valid && P.d_abar) {
           const float4 p4 = lds128(ssp + 16);
           const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
-          const float4* dab = reinterpret_cast<const float4*>(P.d_abar + (int64_t)rr * 128);
+          const float4* dab = reinterpret_cast<const float4*>(P.d_abar + (int64_t)rr * P.ld_dab);
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
 #pragma unroll
@@ -661,7 +702,8 @@ k_edge_bwd_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                              da[4 * j + 1] + __uint_as_float(R[4 * j + 1]),
                              da[4 * j + 2] + __uint_as_float(R[4 * j + 2]),
                              da[4 * j + 3] + __uint_as_float(R[4 * j + 3])));
-        store_rows(&tmD, wsrc, t);
+        if (P.da_reduce) reduce_rows(&tmD, wsrc, t);
+        else store_rows(&tmD, wsrc, t);
       } else {
         // no feature gradient wanted: MMA 2 still runs (on zeros) to keep the issue order of
         // the MMA warp
@@ -702,8 +744,13 @@ k_edge_bwd_umma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 inline bool edge_bwd_launch(const split::EdgeBwdArgs& A, cudaStream_t st, int* rc) {
   CUtensorMap tm, tmG, tmD;
   if (!umma::make_map_rows32(&tm, A.a, A.E, 32, kTileRows)) return false;
-  // output maps: one 32-row x 128-byte box per epilogue warp
-  if (!umma::make_map_rows32(&tmG, A.G, A.E, 32, 32)) return false;
+  // output maps: one 32-row x 128-byte box per epilogue warp (g_mode: 32 rows x 16 columns of
+  // the [E, 128] gradient buffer, unswizzled)
+  if (A.g_mode) {
+    if (!umma::make_map_box(&tmG, A.G, A.E, 128, 128, 16, 32)) return false;
+  } else if (!umma::make_map_rows32(&tmG, A.G, A.E, 32, 32)) {
+    return false;
+  }
   if (!umma::make_map_rows32(&tmD, A.da ? A.da : A.G, A.E, 32, 32)) return false;
   const int smem = SmemBwd::total + 1024;
   static unsigned long long done = 0;

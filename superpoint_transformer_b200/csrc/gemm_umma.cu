@@ -473,6 +473,21 @@ static bool make_map(CUtensorMap* tm, const float* ptr, int64_t rows, int64_t co
 bool make_map_rows32(CUtensorMap* tm, const float* ptr, int64_t rows, int64_t ld, int box_rows) {
   return make_map(tm, ptr, rows, 32, ld, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
 }
+// exported for csrc/attention_umma.cuh: unswizzled box of `box_cols` x `box_rows` over a row-major
+// fp32 matrix [rows, cols] (column-offset stores into a wider buffer)
+bool make_map_box(CUtensorMap* tm, const float* ptr, int64_t rows, int64_t cols, int64_t ld,
+                  int box_cols, int box_rows) {
+  EncodeTiledFn enc = encoder();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box,
+             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // the same for a bf16 [rows, 32] matrix (64-byte rows, SWIZZLE_64B)
 bool make_map_rows32_bf16(CUtensorMap* tm, const void* ptr, int64_t rows, int box_rows) {
   EncodeTiledFn enc = encoder();
