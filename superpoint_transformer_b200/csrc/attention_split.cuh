@@ -9,7 +9,7 @@
 //   forward
 //     edge pass  (thread = edge):  R_e = [Wq;Wk] a_e + b  (32 outputs, dense), q_s, k_t  ->
 //                logit2[e, h] = log2(e) * <q_s*scale + Rq_e, k_t + Rk_e>_h        [E, 4]
-//                - csrc/attention_umma.cu: 128 edges per tcgen05 tile (A operand split into
+//                - csrc/attention_umma.cuh: 128 edges per tcgen05 tile (A operand split into
 //                  TF32 hi/lo in TMEM), epilogue thread = edge;  k_edge_logits_simple below is
 //                  the CUDA-core version (exact fp32; validator and fallback)
 //     row pass   (warp = row, lane = 4 value channels): softmax over the row's logits, gather

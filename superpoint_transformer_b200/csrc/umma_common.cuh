@@ -1,5 +1,5 @@
 // umma_common.cuh — device-side building blocks of the tcgen05 kernels (csrc/gemm_umma.cu,
-// csrc/attention_umma.cu): mbarriers, 2-D TMA loads / stores, TMEM loads / stores, the
+// csrc/attention_umma.cuh): mbarriers, 2-D TMA loads / stores, TMEM loads / stores, the
 // kind::tf32 UMMA issue with its shared-memory / instruction descriptors, the TF32 hi/lo split.
 #pragma once
 #include <cuda.h>

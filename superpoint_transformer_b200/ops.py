@@ -1091,7 +1091,7 @@ class _AttnCore(torch.autograd.Function):
 # ---------------------------------------------------------------------------
 ATTN_STORAGE = 'fp32'
 _bf16_cache = _IdentityCache()
-# split attention kernels (csrc/attention_split.cuh, csrc/attention_umma.cu): one edge-parallel
+# split attention kernels (csrc/attention_split.cuh, csrc/attention_umma.cuh): one edge-parallel
 # pass on the tensor cores + one row-parallel pass; SPT_ATTN_SPLIT=0 keeps the fused row-tile
 # kernels (the A/B of tools/run_attn.py and the parity tests use the switch)
 ATTN_SPLIT = os.environ.get('SPT_ATTN_SPLIT', '1') != '0'
