@@ -155,6 +155,60 @@ int spt_concat_offset_i64(const int64_t* const* srcs, const int64_t* prefix,
                           int skip_first, int64_t* out, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ *  On-device node selection (NAG.select src/data/nag.py:306-399, Data.select    *
+ *  data.py:286-470, Cluster.select cluster.py:79-140, CSRData.__getitem__ /     *
+ *  index_select_pointers csr.py:328-393): csrc/select.cu.  Sizes that depend on *
+ *  the data come back in a 2-element device vector `counts` = {count, number of *
+ *  invalid input entries}; the caller reads it, allocates, and runs phase 2.     *
+ * ------------------------------------------------------------------------- */
+
+/* `consecutive_cluster` (torch_geometric.nn.pool.consecutive, called at cluster.py:131 and
+ * data.py:405) for ids in [0, num_ids): new_ids[i] = rank of ids[i] among the distinct values
+ * present (ascending), unique_ids[r] = the r-th distinct value (capacity min(n, num_ids)),
+ * counts = {number of distinct values, number of out-of-range ids (their new id is -1)}.
+ * A presence bitmap + exclusive scan instead of the reference's sort.  Optional
+ * payload_by_new[new_ids[i]] = payload[i] (only meaningful when the ids are distinct; this is
+ * `Cluster.to_super_index` of the selected clusters, cluster.py:67-77). */
+size_t spt_relabel_consecutive_workspace_bytes(int64_t num_ids);
+int spt_relabel_consecutive_i64(const int64_t* ids, int64_t n, int64_t num_ids,
+                                int64_t* new_ids, int64_t* unique_ids, int64_t* counts,
+                                const int64_t* payload /*nullable*/,
+                                int64_t* payload_by_new /*nullable*/, void* ws, size_t ws_bytes,
+                                void* stream);
+
+/* Data.select's edge update (data.py:356-371), phase 1: reindex[v] = j for v = idx[j], -1
+ * elsewhere (num_nodes entries); slot [E+1] = exclusive scan of "both end points survive";
+ * counts = {edges kept, entries of idx that are out of range or repeated}.  E = 0 only builds
+ * (and validates) the table.  edge_index is [2, E] contiguous. */
+size_t spt_select_edges_workspace_bytes(int64_t E);
+int spt_select_edges_mark(const int64_t* edge_index, int64_t E, const int64_t* idx, int64_t K,
+                          int64_t num_nodes, int64_t* reindex, int32_t* slot, int64_t* counts,
+                          void* ws, size_t ws_bytes, void* stream);
+/* phase 2: out_edge_index [2, num_kept] = reindex[edge_index[:, kept]] in the original edge
+ * order, idx_edge [num_kept] = the kept edge positions (to slice edge attributes). */
+int spt_select_edges_write(const int64_t* edge_index, int64_t E, const int64_t* reindex,
+                           const int32_t* slot, int64_t num_kept, int64_t* out_edge_index,
+                           int64_t* idx_edge, void* stream);
+
+/* CSRData.index_select_pointers (csr.py:328-356), phase 1: new_pointers [K+1] = exclusive scan
+ * of the sizes of groups idx[0..K); counts = {selected items, out-of-range group ids}. */
+size_t spt_csr_select_workspace_bytes(int64_t K);
+int spt_csr_select_pointers(const int64_t* pointers, int64_t num_groups, int64_t num_items,
+                            const int64_t* idx, int64_t K, int64_t* new_pointers,
+                            int64_t* counts, void* ws, size_t ws_bytes, void* stream);
+/* phase 2: out_values[j] = values[val_idx[j]] (the `v[val_idx]` of csr.py:384) for the M
+ * selected items; out_group[j] (nullable) = position in idx of the group item j belongs to. */
+int spt_csr_select_values_i64(const int64_t* pointers, const int64_t* idx, int64_t K,
+                              const int64_t* new_pointers, const int64_t* values, int64_t M,
+                              int64_t* out_values, int64_t* out_group /*nullable*/,
+                              void* stream);
+
+/* out[j, :] = src[idx[j], :] for rows of row_bytes bytes of any dtype (`item[idx]`,
+ * data.py:447-459); idx must be in range (validated by spt_select_edges_mark). */
+int spt_gather_rows_bytes(const void* src, int64_t row_bytes, const int64_t* idx, int64_t K,
+                          void* out, void* stream);
+
+/* ------------------------------------------------------------------------- *
  *  Value RPE of SelfAttentionBlock (src/nn/attention.py:294-301), applied        *
  *  algebraically: y = agg + Wbd . abar + bv (x) sump  (csrc/vrpe.cu)              *
  * ------------------------------------------------------------------------- */

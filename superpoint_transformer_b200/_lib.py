@@ -100,6 +100,19 @@ SIGNATURES = {
     "spt_attn_bwd_weights": (c_int, [c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_ptr,
                                      c_ptr, c_ptr, c_ptr]),
     "spt_concat_offset_i64": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_i64, c_int, c_ptr, c_ptr]),
+    "spt_relabel_consecutive_workspace_bytes": (c_size, [c_i64]),
+    "spt_relabel_consecutive_i64": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr,
+                                            c_ptr, c_ptr, c_size, c_ptr]),
+    "spt_select_edges_workspace_bytes": (c_size, [c_i64]),
+    "spt_select_edges_mark": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr,
+                                      c_ptr, c_size, c_ptr]),
+    "spt_select_edges_write": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
+    "spt_csr_select_workspace_bytes": (c_size, [c_i64]),
+    "spt_csr_select_pointers": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_ptr,
+                                        c_size, c_ptr]),
+    "spt_csr_select_values_i64": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_ptr,
+                                          c_ptr, c_ptr]),
+    "spt_gather_rows_bytes": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr]),
     "spt_vrpe_blockdiag": (c_int, [c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr]),
     "spt_vrpe_epilogue": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_ptr,
                                   c_ptr]),

@@ -29,6 +29,7 @@ SOURCES = [
     "edge_features.cu",
     "vrpe.cu",
     "batch.cu",
+    "select.cu",
 ]
 HEADERS = sorted(f for f in os.listdir(HERE) if f.endswith((".cuh", ".h"))) + \
     [os.path.join(ROOT, "include", "spt_b200.h")]

@@ -9,6 +9,7 @@
 // sort of the (short) id lists to restore the stable (original) order, so the
 // result is deterministic and equals torch.sort(stable=True).
 #include "common.cuh"
+#include "scan.cuh"
 
 namespace spt {
 
@@ -34,87 +35,6 @@ __global__ void k_count_keys(const int64_t* __restrict__ key, int64_t n,
       continue;
     }
     atomicAdd(&cnt[g], 1);
-  }
-}
-
-// ---------------------------------------------------------------- scan
-constexpr int kScanThreads = 1024;
-constexpr int kScanItems = 4;
-constexpr int kScanTile = kScanThreads * kScanItems;
-
-// inclusive block scan of one value per thread; returns inclusive prefix and
-// the block total through smem.
-__device__ __forceinline__ int block_inclusive_scan(int v, int* total) {
-  __shared__ int warp_tot[kScanThreads / kWarp];
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int t = __shfl_up_sync(kFull, v, o);
-    if (lane >= o) v += t;
-  }
-  if (lane == 31) warp_tot[w] = v;
-  __syncthreads();
-  if (w == 0) {
-    int t = (lane < (int)(blockDim.x >> 5)) ? warp_tot[lane] : 0;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int u = __shfl_up_sync(kFull, t, o);
-      if (lane >= o) t += u;
-    }
-    warp_tot[lane] = t;  // inclusive totals of warps
-  }
-  __syncthreads();
-  int add = (w > 0) ? warp_tot[w - 1] : 0;
-  *total = warp_tot[(blockDim.x >> 5) - 1];
-  __syncthreads();
-  return v + add;
-}
-
-__global__ void __launch_bounds__(kScanThreads)
-k_scan_tile_sums(const int32_t* __restrict__ in, int64_t n,
-                 int32_t* __restrict__ tile_sums) {
-  int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
-  int s = 0;
-#pragma unroll
-  for (int i = 0; i < kScanItems; ++i)
-    if (base + i < n) s += in[base + i];
-  int total;
-  block_inclusive_scan(s, &total);
-  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
-}
-
-// single block: exclusive scan of tile_sums (any length) in place
-__global__ void __launch_bounds__(kScanThreads)
-k_scan_tile_offsets(int32_t* __restrict__ tile_sums, int64_t num_tiles) {
-  int carry = 0;
-  for (int64_t base = 0; base < num_tiles; base += kScanThreads) {
-    int64_t i = base + threadIdx.x;
-    int v = (i < num_tiles) ? tile_sums[i] : 0;
-    int total;
-    int inc = block_inclusive_scan(v, &total);
-    if (i < num_tiles) tile_sums[i] = carry + inc - v;
-    carry += total;
-  }
-}
-
-__global__ void __launch_bounds__(kScanThreads)
-k_scan_apply(const int32_t* __restrict__ in, int64_t n,
-             const int32_t* __restrict__ tile_offsets, int32_t* __restrict__ out) {
-  int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
-  int v[kScanItems];
-  int s = 0;
-#pragma unroll
-  for (int i = 0; i < kScanItems; ++i) {
-    v[i] = (base + i < n) ? in[base + i] : 0;
-    s += v[i];
-  }
-  int total;
-  int inc = block_inclusive_scan(s, &total);
-  int run = tile_offsets[blockIdx.x] + inc - s;
-#pragma unroll
-  for (int i = 0; i < kScanItems; ++i) {
-    if (base + i < n) out[base + i] = run;
-    run += v[i];
   }
 }
 
@@ -353,9 +273,7 @@ int spt_group_index(const int64_t* key, const int64_t* other, int64_t n,
   if (n > 0) {
     k_count_keys<<<grid_for(n, 256), 256, 0, st>>>(key, n, num_groups, cnt, err);
   }
-  k_scan_tile_sums<<<(int)tiles, kScanThreads, 0, st>>>(cnt, ns, tile_sums);
-  k_scan_tile_offsets<<<1, kScanThreads, 0, st>>>(tile_sums, tiles);
-  k_scan_apply<<<(int)tiles, kScanThreads, 0, st>>>(cnt, ns, tile_sums, ptr);
+  exclusive_scan_i32(cnt, ns, ptr, tile_sums, st);
   if (n > 0) {
     k_fill_slots<<<grid_for(n, 256), 256, 0, st>>>(key, n, num_groups, ptr, cnt, perm);
     if (num_groups > 0) {

@@ -1,0 +1,358 @@
+// select.cu — on-device node selection of a nested partition: the integer
+// work of NAG.select -> Data.select -> Cluster.select -> CSRData.__getitem__ (reference
+// src/data/nag.py:306-399, src/data/data.py:286-470, src/data/cluster.py:79-140,
+// src/data/csr.py:328-393), which runs on every training batch right before the hot path.
+//
+// Design (B200): the reference relabels surviving ids with `consecutive_cluster`
+// (torch.unique(sorted=True, return_inverse=True): a device sort, flagged "bottleneck" at
+// cluster.py:128-130) and compacts edges with torch.where (a host round trip per call).  Ids
+// here are dense ([0, num_ids)), so a relabel is a presence bitmap + an exclusive scan — O(n)
+// streaming passes, no sort, bit-exact by construction (the rank of an id among the present ones
+// IS its position in the sorted unique list).  Edge and CSR selection are order-preserving
+// compactions on the same scan.  All kernels are HBM-bound integer streams: grid-stride,
+// coalesced int64 traffic; the random accesses (rank[id], reindex[node]) hit tables of the size
+// of one level, which the 126 MB L2 holds.
+//
+// Data-dependent output sizes are produced in two phases (count, then write) so that the caller
+// — who has to allocate — reads exactly one small `counts` vector per phase-1 call.
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace spt {
+
+constexpr int kSelThreads = 256;
+
+static inline int sel_grid(int64_t n) {
+  int64_t b = ceil_div(n > 0 ? n : 1, kSelThreads);
+  const int64_t cap = (int64_t)device_sm_count() * 16;
+  return (int)(b < cap ? b : cap);
+}
+
+#define SPT_GRID_STRIDE(i, n)                                            \
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x,       \
+               stride_ = (int64_t)gridDim.x * blockDim.x;                \
+       i < (n); i += stride_)
+
+// ---------------------------------------------------------------- consecutive relabel
+static __global__ void k_mark_ids(const int64_t* __restrict__ ids, int64_t n, int64_t num_ids,
+                                  int32_t* __restrict__ flags, int64_t* __restrict__ counts) {
+  SPT_GRID_STRIDE(i, n) {
+    const int64_t v = ids[i];
+    if (v < 0 || v >= num_ids) {
+      atomicAdd((unsigned long long*)&counts[1], 1ull);
+      continue;
+    }
+    flags[v] = 1;  // same value from every writer
+  }
+}
+
+static __global__ void k_apply_rank(const int64_t* __restrict__ ids, int64_t n, int64_t num_ids,
+                                    const int32_t* __restrict__ rank,
+                                    int64_t* __restrict__ new_ids,
+                                    const int64_t* __restrict__ payload,
+                                    int64_t* __restrict__ payload_by_new) {
+  SPT_GRID_STRIDE(i, n) {
+    const int64_t v = ids[i];
+    if (v < 0 || v >= num_ids) {
+      new_ids[i] = -1;
+      continue;
+    }
+    const int64_t r = rank[v];
+    new_ids[i] = r;
+    if (payload_by_new) payload_by_new[r] = payload[i];
+  }
+}
+
+static __global__ void k_emit_present(const int32_t* __restrict__ flags,
+                                      const int32_t* __restrict__ rank, int64_t num_ids,
+                                      int64_t* __restrict__ unique_ids,
+                                      int64_t* __restrict__ counts) {
+  SPT_GRID_STRIDE(v, num_ids) {
+    if (flags[v]) unique_ids[rank[v]] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) counts[0] = rank[num_ids];
+}
+
+// ---------------------------------------------------------------- node -> new position table
+static __global__ void k_fill_i64(int64_t* __restrict__ p, int64_t n, int64_t value) {
+  SPT_GRID_STRIDE(i, n) p[i] = value;
+}
+
+static __global__ void k_build_reindex(const int64_t* __restrict__ idx, int64_t K,
+                                       int64_t num_nodes, int64_t* __restrict__ reindex,
+                                       int64_t* __restrict__ counts) {
+  SPT_GRID_STRIDE(j, K) {
+    const int64_t v = idx[j];
+    bool bad = v < 0 || v >= num_nodes;
+    if (!bad) {
+      const unsigned long long old = atomicCAS((unsigned long long*)&reindex[v],
+                                               (unsigned long long)(int64_t)-1,
+                                               (unsigned long long)j);
+      bad = old != (unsigned long long)(int64_t)-1;  // duplicate entry
+    }
+    if (bad) atomicAdd((unsigned long long*)&counts[1], 1ull);
+  }
+}
+
+// ---------------------------------------------------------------- edge compaction
+static __global__ void k_edge_flags(const int64_t* __restrict__ edge_index, int64_t E,
+                                    int64_t num_nodes, const int64_t* __restrict__ reindex,
+                                    int32_t* __restrict__ flags) {
+  SPT_GRID_STRIDE(e, E + 1) {
+    int f = 0;
+    if (e < E) {
+      const int64_t s = edge_index[e], t = edge_index[E + e];
+      f = s >= 0 && s < num_nodes && t >= 0 && t < num_nodes && reindex[s] >= 0 &&
+          reindex[t] >= 0;
+    }
+    flags[e] = f;
+  }
+}
+
+static __global__ void k_edge_count(const int32_t* __restrict__ slot, int64_t E,
+                                    int64_t* __restrict__ counts) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) counts[0] = slot[E];
+}
+
+static __global__ void k_edge_write(const int64_t* __restrict__ edge_index, int64_t E,
+                                    const int64_t* __restrict__ reindex,
+                                    const int32_t* __restrict__ slot, int64_t num_kept,
+                                    int64_t* __restrict__ out_edge_index,
+                                    int64_t* __restrict__ idx_edge) {
+  SPT_GRID_STRIDE(e, E) {
+    const int32_t p = slot[e];
+    if (slot[e + 1] == p) continue;
+    out_edge_index[p] = reindex[edge_index[e]];
+    out_edge_index[num_kept + p] = reindex[edge_index[E + e]];
+    idx_edge[p] = e;
+  }
+}
+
+// ---------------------------------------------------------------- CSR group selection
+static __global__ void k_selected_sizes(const int64_t* __restrict__ pointers, int64_t num_groups,
+                                        const int64_t* __restrict__ idx, int64_t K,
+                                        int32_t* __restrict__ sizes,
+                                        int64_t* __restrict__ counts) {
+  SPT_GRID_STRIDE(j, K + 1) {
+    int32_t s = 0;
+    if (j < K) {
+      const int64_t g = idx[j];
+      if (g < 0 || g >= num_groups) atomicAdd((unsigned long long*)&counts[1], 1ull);
+      else s = (int32_t)(pointers[g + 1] - pointers[g]);
+    }
+    sizes[j] = s;
+  }
+}
+
+static __global__ void k_widen_pointers(const int32_t* __restrict__ in, int64_t n,
+                                        int64_t* __restrict__ out,
+                                        int64_t* __restrict__ counts) {
+  SPT_GRID_STRIDE(i, n) out[i] = in[i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) counts[0] = in[n - 1];
+}
+
+// one thread per selected item: group by binary search in the new pointers
+static __global__ void k_select_values(const int64_t* __restrict__ pointers,
+                                       const int64_t* __restrict__ idx, int64_t K,
+                                       const int64_t* __restrict__ new_pointers,
+                                       const int64_t* __restrict__ values, int64_t M,
+                                       int64_t* __restrict__ out_values,
+                                       int64_t* __restrict__ out_group) {
+  SPT_GRID_STRIDE(j, M) {
+    int64_t lo = 0, hi = K;  // largest g with new_pointers[g] <= j
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (new_pointers[mid] <= j) lo = mid; else hi = mid;
+    }
+    out_values[j] = values[pointers[idx[lo]] + (j - new_pointers[lo])];
+    if (out_group) out_group[j] = lo;
+  }
+}
+
+// ---------------------------------------------------------------- row gather (any dtype)
+template <typename Unit>
+static __global__ void k_gather_rows(const Unit* __restrict__ src, int64_t row_units,
+                                     const int64_t* __restrict__ idx, int64_t K,
+                                     Unit* __restrict__ out) {
+  const int64_t total = K * row_units;
+  SPT_GRID_STRIDE(t, total) {
+    const int64_t r = t / row_units, u = t - r * row_units;
+    out[t] = src[idx[r] * row_units + u];
+  }
+}
+
+}  // namespace spt
+
+using namespace spt;
+
+extern "C" {
+
+// ws: flags[num_ids+1] | rank[num_ids+1] | scan scratch
+size_t spt_relabel_consecutive_workspace_bytes(int64_t num_ids) {
+  if (num_ids < 0) return 0;
+  const size_t a = align_up((size_t)(num_ids + 1) * 4, 256);
+  return 2 * a + scan_workspace_bytes(num_ids + 1);
+}
+
+int spt_relabel_consecutive_i64(const int64_t* ids, int64_t n, int64_t num_ids,
+                                int64_t* new_ids, int64_t* unique_ids, int64_t* counts,
+                                const int64_t* payload, int64_t* payload_by_new, void* ws,
+                                size_t ws_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  SPT_REQUIRE(n >= 0 && num_ids >= 0, SPT_E_INVALID, "relabel_consecutive: negative size");
+  SPT_REQUIRE(n < 2147483647LL && num_ids < 2147483646LL, SPT_E_TOO_LARGE,
+              "relabel_consecutive: n=%lld / num_ids=%lld exceed int32 internals", (long long)n,
+              (long long)num_ids);
+  SPT_REQUIRE(counts && ws && (n == 0 || (ids && new_ids && unique_ids)), SPT_E_INVALID,
+              "relabel_consecutive: null pointer");
+  SPT_REQUIRE(!payload == !payload_by_new, SPT_E_INVALID,
+              "relabel_consecutive: payload and payload_by_new go together");
+  const size_t need = spt_relabel_consecutive_workspace_bytes(num_ids);
+  SPT_REQUIRE(ws_bytes >= need, SPT_E_WORKSPACE, "relabel_consecutive: workspace %zu < %zu",
+              ws_bytes, need);
+  const size_t a = align_up((size_t)(num_ids + 1) * 4, 256);
+  int32_t* flags = (int32_t*)ws;
+  int32_t* rank = (int32_t*)((char*)ws + a);
+  int32_t* tiles = (int32_t*)((char*)ws + 2 * a);
+  cudaError_t ce = cudaMemsetAsync(flags, 0, (size_t)(num_ids + 1) * 4, st);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(counts, 0, 16, st);
+  if (ce != cudaSuccess) {
+    set_error("relabel_consecutive memset: %s", cudaGetErrorString(ce));
+    return (int)ce;
+  }
+  if (n > 0) k_mark_ids<<<sel_grid(n), kSelThreads, 0, st>>>(ids, n, num_ids, flags, counts);
+  exclusive_scan_i32(flags, num_ids + 1, rank, tiles, st);
+  if (n > 0)
+    k_apply_rank<<<sel_grid(n), kSelThreads, 0, st>>>(ids, n, num_ids, rank, new_ids, payload,
+                                                      payload_by_new);
+  k_emit_present<<<sel_grid(num_ids), kSelThreads, 0, st>>>(flags, rank, num_ids, unique_ids,
+                                                            counts);
+  return check_launch("relabel_consecutive");
+}
+
+// ws: flags[E+1] | scan scratch
+size_t spt_select_edges_workspace_bytes(int64_t E) {
+  if (E < 0) return 0;
+  return align_up((size_t)(E + 1) * 4, 256) + scan_workspace_bytes(E + 1);
+}
+
+int spt_select_edges_mark(const int64_t* edge_index, int64_t E, const int64_t* idx, int64_t K,
+                          int64_t num_nodes, int64_t* reindex, int32_t* slot, int64_t* counts,
+                          void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  SPT_REQUIRE(E >= 0 && K >= 0 && num_nodes >= 0, SPT_E_INVALID,
+              "select_edges_mark: negative size");
+  SPT_REQUIRE(E < 2147483646LL, SPT_E_TOO_LARGE, "select_edges_mark: E=%lld exceeds int32 slots",
+              (long long)E);
+  SPT_REQUIRE(counts && (num_nodes == 0 || reindex) && (K == 0 || idx) &&
+                  (E == 0 || (edge_index && slot && ws)),
+              SPT_E_INVALID, "select_edges_mark: null pointer");
+  const size_t need = E > 0 ? spt_select_edges_workspace_bytes(E) : 0;
+  SPT_REQUIRE(ws_bytes >= need, SPT_E_WORKSPACE, "select_edges_mark: workspace %zu < %zu",
+              ws_bytes, need);
+  cudaError_t ce = cudaMemsetAsync(counts, 0, 16, st);
+  if (ce != cudaSuccess) {
+    set_error("select_edges_mark memset: %s", cudaGetErrorString(ce));
+    return (int)ce;
+  }
+  if (num_nodes > 0)
+    k_fill_i64<<<sel_grid(num_nodes), kSelThreads, 0, st>>>(reindex, num_nodes, -1);
+  if (K > 0)
+    k_build_reindex<<<sel_grid(K), kSelThreads, 0, st>>>(idx, K, num_nodes, reindex, counts);
+  if (E > 0) {
+    int32_t* flags = (int32_t*)ws;
+    int32_t* tiles = (int32_t*)((char*)ws + align_up((size_t)(E + 1) * 4, 256));
+    k_edge_flags<<<sel_grid(E + 1), kSelThreads, 0, st>>>(edge_index, E, num_nodes, reindex,
+                                                          flags);
+    exclusive_scan_i32(flags, E + 1, slot, tiles, st);
+    k_edge_count<<<1, 32, 0, st>>>(slot, E, counts);
+  }
+  return check_launch("select_edges_mark");
+}
+
+int spt_select_edges_write(const int64_t* edge_index, int64_t E, const int64_t* reindex,
+                           const int32_t* slot, int64_t num_kept, int64_t* out_edge_index,
+                           int64_t* idx_edge, void* stream_) {
+  SPT_REQUIRE(E >= 0 && num_kept >= 0 && num_kept <= E, SPT_E_INVALID,
+              "select_edges_write: bad sizes");
+  if (E == 0 || num_kept == 0) return SPT_OK;
+  SPT_REQUIRE(edge_index && reindex && slot && out_edge_index && idx_edge, SPT_E_INVALID,
+              "select_edges_write: null pointer");
+  k_edge_write<<<sel_grid(E), kSelThreads, 0, (cudaStream_t)stream_>>>(
+      edge_index, E, reindex, slot, num_kept, out_edge_index, idx_edge);
+  return check_launch("select_edges_write");
+}
+
+// ws: sizes[K+1] | scanned[K+1] | scan scratch
+size_t spt_csr_select_workspace_bytes(int64_t K) {
+  if (K < 0) return 0;
+  return 2 * align_up((size_t)(K + 1) * 4, 256) + scan_workspace_bytes(K + 1);
+}
+
+int spt_csr_select_pointers(const int64_t* pointers, int64_t num_groups, int64_t num_items,
+                            const int64_t* idx, int64_t K, int64_t* new_pointers,
+                            int64_t* counts, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  SPT_REQUIRE(num_groups >= 0 && K >= 0 && num_items >= 0, SPT_E_INVALID,
+              "csr_select_pointers: negative size");
+  SPT_REQUIRE(K < 2147483646LL && num_items < 2147483647LL, SPT_E_TOO_LARGE,
+              "csr_select_pointers: K=%lld / num_items=%lld exceed int32 internals",
+              (long long)K, (long long)num_items);
+  SPT_REQUIRE(pointers && new_pointers && counts && ws && (K == 0 || idx), SPT_E_INVALID,
+              "csr_select_pointers: null pointer");
+  const size_t need = spt_csr_select_workspace_bytes(K);
+  SPT_REQUIRE(ws_bytes >= need, SPT_E_WORKSPACE, "csr_select_pointers: workspace %zu < %zu",
+              ws_bytes, need);
+  const size_t a = align_up((size_t)(K + 1) * 4, 256);
+  int32_t* sizes = (int32_t*)ws;
+  int32_t* scanned = (int32_t*)((char*)ws + a);
+  int32_t* tiles = (int32_t*)((char*)ws + 2 * a);
+  cudaError_t ce = cudaMemsetAsync(counts, 0, 16, st);
+  if (ce != cudaSuccess) {
+    set_error("csr_select_pointers memset: %s", cudaGetErrorString(ce));
+    return (int)ce;
+  }
+  k_selected_sizes<<<sel_grid(K + 1), kSelThreads, 0, st>>>(pointers, num_groups, idx, K, sizes,
+                                                            counts);
+  exclusive_scan_i32(sizes, K + 1, scanned, tiles, st);
+  k_widen_pointers<<<sel_grid(K + 1), kSelThreads, 0, st>>>(scanned, K + 1, new_pointers, counts);
+  return check_launch("csr_select_pointers");
+}
+
+int spt_csr_select_values_i64(const int64_t* pointers, const int64_t* idx, int64_t K,
+                              const int64_t* new_pointers, const int64_t* values, int64_t M,
+                              int64_t* out_values, int64_t* out_group, void* stream_) {
+  SPT_REQUIRE(K >= 0 && M >= 0, SPT_E_INVALID, "csr_select_values: negative size");
+  if (M == 0 || K == 0) return SPT_OK;
+  SPT_REQUIRE(pointers && idx && new_pointers && values && out_values, SPT_E_INVALID,
+              "csr_select_values: null pointer");
+  k_select_values<<<sel_grid(M), kSelThreads, 0, (cudaStream_t)stream_>>>(
+      pointers, idx, K, new_pointers, values, M, out_values, out_group);
+  return check_launch("csr_select_values");
+}
+
+int spt_gather_rows_bytes(const void* src, int64_t row_bytes, const int64_t* idx, int64_t K, void* out,
+                    void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  SPT_REQUIRE(row_bytes >= 0 && K >= 0, SPT_E_INVALID, "gather_rows_bytes: negative size");
+  if (row_bytes == 0 || K == 0) return SPT_OK;
+  SPT_REQUIRE(src && idx && out, SPT_E_INVALID, "gather_rows_bytes: null pointer");
+  const uintptr_t align = (uintptr_t)src | (uintptr_t)out | (uintptr_t)row_bytes;
+  const int64_t units = K * row_bytes;
+  if ((align & 15) == 0) {
+    k_gather_rows<uint4><<<sel_grid(units / 16), kSelThreads, 0, st>>>(
+        (const uint4*)src, row_bytes / 16, idx, K, (uint4*)out);
+  } else if ((align & 7) == 0) {
+    k_gather_rows<uint2><<<sel_grid(units / 8), kSelThreads, 0, st>>>(
+        (const uint2*)src, row_bytes / 8, idx, K, (uint2*)out);
+  } else if ((align & 3) == 0) {
+    k_gather_rows<uint32_t><<<sel_grid(units / 4), kSelThreads, 0, st>>>(
+        (const uint32_t*)src, row_bytes / 4, idx, K, (uint32_t*)out);
+  } else {
+    k_gather_rows<uint8_t><<<sel_grid(units), kSelThreads, 0, st>>>(
+        (const uint8_t*)src, row_bytes, idx, K, (uint8_t*)out);
+  }
+  return check_launch("gather_rows_bytes");
+}
+
+}  // extern "C"

@@ -2,9 +2,12 @@
 reference src/data/data.py that the hot path touches: x, pos, edge_index,
 edge_attr, super_index, sub, node_size, v_edge_attr, batch, norm_index(),
 num_nodes, add_keys_to())."""
+import copy
+
 import torch
 
-from .cluster import Cluster
+from .cluster import Cluster, CSRData
+from ..utils.tensor import tensor_idx, is_arange
 
 __all__ = ['Data', 'Batch']
 
@@ -82,7 +85,14 @@ class Data:
 
     # derived ------------------------------------------------------------------
     @property
+    def v_edge_keys(self):
+        """reference src/data/data.py:178-180"""
+        return [k for k in self.keys if k.startswith('v_edge_')]
+
+    @property
     def num_nodes(self):
+        if '_num_nodes' in self._store:
+            return self._store['_num_nodes']
         for key in ('pos', 'x', 'super_index', 'node_size', 'batch'):
             t = self._get(key)
             if t is not None:
@@ -196,6 +206,80 @@ class Data:
         out = self.__class__()
         out._store.update(self._store)
         return out
+
+    def select(self, idx, update_sub=True, update_super=True, _num_super=None,
+               _skip_sub=False, _skip_super=False):
+        """Nodes `idx` (duplicate-free) of this level, with edges re-indexed and restricted to
+        the selection, `sub` restricted and — with `update_sub` / `update_super` — the ids of
+        the neighbouring levels made dense again (reference src/data/data.py:286-470).
+        Returns data, (idx_sub, sub_super), (idx_super, super_sub) exactly like the reference:
+        `idx_sub` / `idx_super` select the level below / above, `sub_super` replaces the lower
+        level's `super_index`, `super_sub` the upper level's `sub`.
+
+        CUDA tensors only: the integer work runs in csrc/select.cu (edge compaction and CSR
+        selection by scan, relabels by bitmap + scan instead of `consecutive_cluster`'s sort).
+        Inside a cluster of `super_sub` the points are in ascending order (the reference's
+        unstable torch.sort leaves that order unspecified, src/utils/sparse.py:31-33).
+        `_num_super`, `_skip_sub`, `_skip_super`: NAG.select's shortcuts (parent count known;
+        `sub` / `super_index` are about to be replaced by the neighbouring level's result)."""
+        device = self.device
+        idx = tensor_idx(idx, device=device)
+        num_nodes = self.num_nodes
+        if idx is None or is_arange(idx, num_nodes):
+            return self.clone(), (None, None), (None, None)
+        from .. import ops
+        num_sel = idx.shape[0]
+        data = Data()
+
+        # edges: re-index, drop those that lose an end point (data.py:356-371); the same call
+        # validates idx (range, duplicates)
+        idx_edge = None
+        if self.has_edges:
+            data.edge_index, idx_edge = ops.select_edges(self.edge_index, idx, num_nodes)
+        else:
+            ops.select_edges(None, idx, num_nodes)
+
+        out_sub = (None, None)
+        if self.is_super and not _skip_sub:
+            if not isinstance(self.sub, CSRData):
+                raise NotImplementedError("Data.select needs `sub` as a Cluster")
+            data.sub, out_sub = self.sub.select(idx, update_sub=update_sub)
+
+        out_super = (None, None)
+        if self.is_sub and not _skip_super:
+            data.super_index = ops.take_rows(self.super_index, idx)
+        if self.is_sub and update_super:
+            num_super = self.num_super if _num_super is None else int(_num_super)
+            data.super_index, idx_super = ops.relabel_consecutive(data.super_index, num_super)
+            super_sub = Cluster.from_super_index(data.super_index, idx_super.shape[0])
+            out_super = (idx_super, super_sub)
+
+        skip_keys = ('edge_index', 'sub', 'super_index', 'neighbor_index',
+                     'neighbor_distance')
+        edge_keys = ['edge_attr'] + self.edge_keys
+        v_edge_keys = self.v_edge_keys
+        num_edges = self.num_edges
+        for key, item in list(self._store.items()):
+            if key in skip_keys or key.startswith('_'):
+                continue
+            if isinstance(item, CSRData):
+                data[key] = item.select(idx)
+                continue
+            is_tensor = torch.is_tensor(item)
+            is_node_size = is_tensor and item.dim() > 0 and item.shape[0] == num_nodes
+            is_edge_size = is_tensor and item.dim() > 0 and item.shape[0] == num_edges
+            if is_node_size and key in v_edge_keys:
+                data[key] = ops.take_rows(item, idx)
+            elif self.has_edges and is_edge_size and key in edge_keys:
+                data[key] = ops.take_rows(item, idx_edge)
+            elif is_node_size:
+                data[key] = ops.take_rows(item, idx)
+            else:
+                data[key] = item.clone() if is_tensor else copy.deepcopy(item)
+
+        if data.num_nodes != num_sel:
+            data._store['_num_nodes'] = num_sel
+        return data, out_sub, out_super
 
     def __repr__(self):
         parts = []

@@ -4,6 +4,7 @@ get_sub_size / get_super_index)."""
 import torch
 
 from .data import Data, Batch
+from ..utils.tensor import tensor_idx, is_arange
 
 __all__ = ['NAG', 'NAGBatch']
 
@@ -107,6 +108,50 @@ class NAG:
                 continue
             self[i_level].add_keys_to(keys=ks, to=to, strict=strict,
                                       delete_after=delete_after)
+
+    def select(self, i_level, idx):
+        """New NAG holding the nodes `idx` (duplicate-free) of level `i_level`, everything below
+        them and every ancestor that keeps a child, with all cross-level indices consistent
+        (reference src/data/nag.py:306-399).  Runs on the device (csrc/select.cu)."""
+        assert isinstance(i_level, int)
+        assert i_level in self.level_range, \
+            f"Level {i_level} is out of range. NAG has levels {self.level_range}"
+        idx = tensor_idx(idx, device=self.device)
+        if idx is None or is_arange(idx, self[i_level].num_nodes):
+            return self.clone()
+        for i in self.level_range:
+            for k in ('obj', 'obj_pred'):
+                if k in self[i]:
+                    raise NotImplementedError(
+                        f"NAG.select: instance labels ('{k}') are outside this package's scope")
+
+        def num_parents(i):
+            return self[i + 1].num_nodes if i + 1 <= self.end_i_level else None
+
+        data_list = [None] * self.absolute_num_levels
+        data_list[i_level], out_sub, out_super = self[i_level].select(
+            idx, update_sub=True, update_super=True, _num_super=num_parents(i_level))
+
+        # lower levels: points selected by the level above, `super_index` handed down
+        for i in range(i_level - 1, self.start_i_level - 1, -1):
+            idx_sub, sub_super = out_sub
+            data_list[i], out_sub, _ = self[i].select(
+                idx_sub, update_sub=True, update_super=False, _skip_super=True)
+            # (no selection on this level -> nothing handed down: the level keeps its own
+            # `super_index`; the reference overwrites it with None there, nag.py:368-370)
+            if sub_super is not None:
+                data_list[i].super_index = sub_super
+
+        # higher levels: surviving parents, `sub` handed up
+        for i in range(i_level + 1, self.absolute_num_levels):
+            idx_super, super_sub = out_super
+            data_list[i], _, out_super = self[i].select(
+                idx_super, update_sub=False, update_super=True, _num_super=num_parents(i),
+                _skip_sub=True)
+            if super_sub is not None:
+                data_list[i].sub = super_sub
+
+        return NAG(data_list[self.start_i_level:], start_i_level=self.start_i_level)
 
     def get_sub_size(self, high, low=0):
         """Number of `low`-level elements under each `high`-level node, bottom-up

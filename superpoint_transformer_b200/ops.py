@@ -694,6 +694,137 @@ def segment_ids(sizes, device):
     return out
 
 
+# ---------------------------------------------------------------------------
+# node selection (csrc/select.cu): the integer primitives of NAG.select
+# ---------------------------------------------------------------------------
+def _ws_bytes(n, device):
+    return torch.empty(max(int(n), 1), dtype=torch.uint8, device=device)
+
+
+def _read_counts(counts, what):
+    """The one host read of a two-phase selection primitive: (count, invalid entries)."""
+    count, bad = counts.tolist()
+    if bad:
+        raise IndexError(f"{what}: {bad} index entries are out of range or repeated")
+    return count
+
+
+def relabel_consecutive(ids, num_ids, payload=None):
+    """`consecutive_cluster(ids)` of torch_geometric.nn.pool.consecutive for ids in
+    [0, num_ids) (reference call sites src/data/cluster.py:131, src/data/data.py:405) without
+    the sort: returns (new_ids, unique_ids) with new_ids[i] the rank of ids[i] among the distinct
+    values and unique_ids the distinct values in ascending order — the reference's
+    `ids[perm]`.  With `payload` also returns payload_by_new (payload_by_new[new_ids[i]] =
+    payload[i]; the ids must then be distinct)."""
+    lib = _lib.load()
+    _require_cuda(ids, payload)
+    ids = _i64c(ids).view(-1)
+    n, dev = ids.numel(), ids.device
+    cap = min(n, int(num_ids))
+    new_ids = torch.empty(n, dtype=torch.int64, device=dev)
+    uniq = torch.empty(cap, dtype=torch.int64, device=dev)
+    counts = torch.empty(2, dtype=torch.int64, device=dev)
+    by_new = None
+    if payload is not None:
+        payload = _i64c(payload).view(-1)
+        by_new = torch.empty(cap, dtype=torch.int64, device=dev)
+    nb = lib.spt_relabel_consecutive_workspace_bytes(int(num_ids))
+    ws = _ws_bytes(nb, dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.spt_relabel_consecutive_i64(
+            _p(ids), n, int(num_ids), _p(new_ids), _p(uniq), _p(counts), _p(payload),
+            _p(by_new), _p(ws), nb, _stream()), "spt_relabel_consecutive_i64")
+    _count(6)
+    num_unique = _read_counts(counts, "relabel_consecutive")
+    if payload is not None:
+        if num_unique != n:
+            raise IndexError("relabel_consecutive: payload given but the ids are not distinct")
+        return new_ids, uniq[:num_unique], by_new[:num_unique]
+    return new_ids, uniq[:num_unique]
+
+
+def select_edges(edge_index, idx, num_nodes):
+    """Edge update of Data.select (reference src/data/data.py:356-371): returns
+    (edge_index', idx_edge) with edge_index' = reindex[edge_index[:, idx_edge]], reindex the
+    old-id -> position-in-idx table, idx_edge the edges whose two end points are selected, in
+    their original order.  Also validates `idx` (range, duplicates).  edge_index None: only the
+    validation."""
+    lib = _lib.load()
+    _require_cuda(edge_index, idx)
+    idx = _i64c(idx).view(-1)
+    dev = idx.device
+    K = idx.numel()
+    E = 0 if edge_index is None else int(edge_index.shape[1])
+    ei = _i64c(edge_index) if E > 0 else None
+    reindex = torch.empty(int(num_nodes), dtype=torch.int64, device=dev)
+    slot = torch.empty(E + 1, dtype=torch.int32, device=dev) if E > 0 else None
+    counts = torch.empty(2, dtype=torch.int64, device=dev)
+    nb = lib.spt_select_edges_workspace_bytes(E) if E > 0 else 0
+    ws = _ws_bytes(nb, dev) if E > 0 else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.spt_select_edges_mark(
+            _p(ei), E, _p(idx), K, int(num_nodes), _p(reindex), _p(slot), _p(counts), _p(ws),
+            nb, _stream()), "spt_select_edges_mark")
+        _count(7 if E > 0 else 2)
+        kept = _read_counts(counts, "select: idx")
+        if edge_index is None:
+            return None, None
+        out = torch.empty((2, kept), dtype=torch.int64, device=dev)
+        idx_edge = torch.empty(kept, dtype=torch.int64, device=dev)
+        if kept > 0:
+            _lib.check(lib.spt_select_edges_write(
+                _p(ei), E, _p(reindex), _p(slot), kept, _p(out), _p(idx_edge), _stream()),
+                "spt_select_edges_write")
+            _count()
+    return out, idx_edge
+
+
+def csr_select(pointers, values, idx, want_group=False):
+    """CSRData.__getitem__ (reference src/data/csr.py:328-393) for one int64 value tensor:
+    (new_pointers, values[val_idx][, group of every selected item])."""
+    lib = _lib.load()
+    _require_cuda(pointers, values, idx)
+    pointers, values, idx = _i64c(pointers), _i64c(values).view(-1), _i64c(idx).view(-1)
+    dev = pointers.device
+    G, K = pointers.numel() - 1, idx.numel()
+    new_ptr = torch.empty(K + 1, dtype=torch.int64, device=dev)
+    counts = torch.empty(2, dtype=torch.int64, device=dev)
+    nb = lib.spt_csr_select_workspace_bytes(K)
+    ws = _ws_bytes(nb, dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.spt_csr_select_pointers(
+            _p(pointers), G, values.numel(), _p(idx), K, _p(new_ptr), _p(counts), _p(ws), nb,
+            _stream()), "spt_csr_select_pointers")
+        _count(5)
+        M = _read_counts(counts, "csr_select: idx")
+        out = torch.empty(M, dtype=torch.int64, device=dev)
+        group = torch.empty(M, dtype=torch.int64, device=dev) if want_group else None
+        if M > 0:
+            _lib.check(lib.spt_csr_select_values_i64(
+                _p(pointers), _p(idx), K, _p(new_ptr), _p(values), M, _p(out), _p(group),
+                _stream()), "spt_csr_select_values_i64")
+            _count()
+    return (new_ptr, out, group) if want_group else (new_ptr, out)
+
+
+def take_rows(t, idx):
+    """t[idx] along dim 0 for a CUDA tensor of any dtype (`item[idx]`, reference
+    src/data/data.py:447-459); idx int64, in range (Data.select validates it first)."""
+    lib = _lib.load()
+    _require_cuda(t, idx)
+    t = t.contiguous()
+    idx = _i64c(idx).view(-1)
+    K = idx.numel()
+    out = torch.empty((K,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    row_bytes = (t.numel() // t.shape[0] if t.shape[0] > 0 else 0) * t.element_size()
+    if K > 0 and row_bytes > 0:
+        with torch.cuda.device(t.device):
+            _lib.check(lib.spt_gather_rows_bytes(_p(t), row_bytes, _p(idx), K, _p(out),
+                                                 _stream()), "spt_gather_rows_bytes")
+        _count()
+    return out
+
+
 def node_size(super_index, num_parents, child_size=None):
     """NAG.get_sub_size step (src/data/nag.py:59-110): exact int64 sums."""
     lib = _lib.load()
