@@ -16,6 +16,12 @@ Parity status
   loads them verbatim with importlib) — `oracle/make_golden.py` writes the
   resulting input/output vectors to `tests/golden/*.pt`, and
   `tests/test_oracle_golden.py` replays them anywhere.
+* SELECTION pinned the same way: `oracle/select.py` (NAG.select / Data.select /
+  Cluster.select / CSRData.__getitem__, src/data/{nag,data,cluster,csr}.py) against
+  `tests/golden/select.pt`, which `oracle/make_golden_select.py` produces by running the
+  reference's own src/data/*.py and src/utils/{tensor,sparse}.py, loaded verbatim by
+  `oracle/reference_data.py` (restated there: the PyG `Data` attribute store and
+  `consecutive_cluster`, third-party and absent like the leaves below).
 * LEAVES unpinned: the arithmetic leaves the reference calls live in third-party
   wheels that are absent from /root/reference and from this image
   (`torch_scatter` unpinned for torch 2.2.0, `torch_geometric==2.3.0`;
