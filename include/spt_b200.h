@@ -207,6 +207,11 @@ int spt_csr_select_values_i64(const int64_t* pointers, const int64_t* idx, int64
  * data.py:447-459); idx must be in range (validated by spt_select_edges_mark). */
 int spt_gather_rows_bytes(const void* src, int64_t row_bytes, const int64_t* idx, int64_t K,
                           void* out, void* stream);
+/* The same for `num_tensors` tensors in one launch per 16 tensors (all node-level or all
+ * edge-level attributes of a Data object).  srcs / outs / row_bytes are HOST arrays of device
+ * pointers / byte counts: the table is passed in the kernel parameters. */
+int spt_gather_rows_multi(const void* const* srcs, void* const* outs, const int64_t* row_bytes,
+                          int num_tensors, const int64_t* idx, int64_t K, void* stream);
 
 /* ------------------------------------------------------------------------- *
  *  Value RPE of SelfAttentionBlock (src/nn/attention.py:294-301), applied        *

@@ -113,6 +113,7 @@ SIGNATURES = {
     "spt_csr_select_values_i64": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_ptr,
                                           c_ptr, c_ptr]),
     "spt_gather_rows_bytes": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr]),
+    "spt_gather_rows_multi": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_i64, c_ptr]),
     "spt_vrpe_blockdiag": (c_int, [c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr]),
     "spt_vrpe_epilogue": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_ptr,
                                   c_ptr]),

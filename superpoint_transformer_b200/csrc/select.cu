@@ -181,6 +181,36 @@ static __global__ void k_gather_rows(const Unit* __restrict__ src, int64_t row_u
   }
 }
 
+// several tensors, one launch: the table travels in the kernel parameters (no device copy)
+constexpr int kMultiMax = 16;
+struct GatherMulti {
+  const void* src[kMultiMax];
+  void* dst[kMultiMax];
+  int64_t row_units[kMultiMax];       // units per row
+  int64_t unit_prefix[kMultiMax + 1]; // exclusive scan of K * row_units
+  int32_t unit_log2[kMultiMax];       // log2 of the unit size in bytes: 0, 2, 3 or 4
+  int32_t n;
+};
+
+static __global__ void k_gather_rows_multi(const GatherMulti tab,
+                                           const int64_t* __restrict__ idx) {
+  const int64_t total = tab.unit_prefix[tab.n];
+  SPT_GRID_STRIDE(t, total) {
+    int s = 0;
+    while (s + 1 < tab.n && tab.unit_prefix[s + 1] <= t) ++s;
+    const int64_t local = t - tab.unit_prefix[s];
+    const int64_t ru = tab.row_units[s];
+    const int64_t r = local / ru, u = local - r * ru;
+    const int64_t from = idx[r] * ru + u;
+    switch (tab.unit_log2[s]) {
+      case 4: ((uint4*)tab.dst[s])[local] = ((const uint4*)tab.src[s])[from]; break;
+      case 3: ((uint2*)tab.dst[s])[local] = ((const uint2*)tab.src[s])[from]; break;
+      case 2: ((uint32_t*)tab.dst[s])[local] = ((const uint32_t*)tab.src[s])[from]; break;
+      default: ((uint8_t*)tab.dst[s])[local] = ((const uint8_t*)tab.src[s])[from]; break;
+    }
+  }
+}
+
 }  // namespace spt
 
 using namespace spt;
@@ -353,6 +383,36 @@ int spt_gather_rows_bytes(const void* src, int64_t row_bytes, const int64_t* idx
         (const uint8_t*)src, row_bytes, idx, K, (uint8_t*)out);
   }
   return check_launch("gather_rows_bytes");
+}
+
+int spt_gather_rows_multi(const void* const* srcs, void* const* outs, const int64_t* row_bytes,
+                          int num_tensors, const int64_t* idx, int64_t K, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  SPT_REQUIRE(num_tensors >= 0 && K >= 0, SPT_E_INVALID, "gather_rows_multi: negative size");
+  if (num_tensors == 0 || K == 0) return SPT_OK;
+  SPT_REQUIRE(srcs && outs && row_bytes && idx, SPT_E_INVALID, "gather_rows_multi: null pointer");
+  for (int base = 0; base < num_tensors; base += kMultiMax) {
+    GatherMulti tab;
+    tab.n = 0;
+    tab.unit_prefix[0] = 0;
+    for (int i = base; i < num_tensors && tab.n < kMultiMax; ++i) {
+      const int64_t rb = row_bytes[i];
+      SPT_REQUIRE(rb >= 0, SPT_E_INVALID, "gather_rows_multi: negative row size");
+      if (rb == 0) continue;
+      SPT_REQUIRE(srcs[i] && outs[i], SPT_E_INVALID, "gather_rows_multi: null tensor");
+      const uintptr_t align = (uintptr_t)srcs[i] | (uintptr_t)outs[i] | (uintptr_t)rb;
+      const int lg = (align & 15) == 0 ? 4 : (align & 7) == 0 ? 3 : (align & 3) == 0 ? 2 : 0;
+      const int j = tab.n++;
+      tab.src[j] = srcs[i];
+      tab.dst[j] = outs[i];
+      tab.unit_log2[j] = lg;
+      tab.row_units[j] = rb >> lg;
+      tab.unit_prefix[j + 1] = tab.unit_prefix[j] + K * (rb >> lg);
+    }
+    if (tab.n == 0) continue;
+    k_gather_rows_multi<<<sel_grid(tab.unit_prefix[tab.n]), kSelThreads, 0, st>>>(tab, idx);
+  }
+  return check_launch("gather_rows_multi");
 }
 
 }  // extern "C"

@@ -259,6 +259,7 @@ class Data:
         edge_keys = ['edge_attr'] + self.edge_keys
         v_edge_keys = self.v_edge_keys
         num_edges = self.num_edges
+        node_items, edge_items = [], []      # gathered in one launch each, below
         for key, item in list(self._store.items()):
             if key in skip_keys or key.startswith('_'):
                 continue
@@ -269,13 +270,18 @@ class Data:
             is_node_size = is_tensor and item.dim() > 0 and item.shape[0] == num_nodes
             is_edge_size = is_tensor and item.dim() > 0 and item.shape[0] == num_edges
             if is_node_size and key in v_edge_keys:
-                data[key] = ops.take_rows(item, idx)
+                node_items.append(key)
             elif self.has_edges and is_edge_size and key in edge_keys:
-                data[key] = ops.take_rows(item, idx_edge)
+                edge_items.append(key)
             elif is_node_size:
-                data[key] = ops.take_rows(item, idx)
+                node_items.append(key)
             else:
                 data[key] = item.clone() if is_tensor else copy.deepcopy(item)
+                continue
+            data[key] = item      # placeholder: keeps the reference's attribute order
+        for keys, index in ((node_items, idx), (edge_items, idx_edge)):
+            for key, out in zip(keys, ops.take_rows_multi([self._store[k] for k in keys], index)):
+                data[key] = out
 
         if data.num_nodes != num_sel:
             data._store['_num_nodes'] = num_sel

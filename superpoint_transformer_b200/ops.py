@@ -807,6 +807,34 @@ def csr_select(pointers, values, idx, want_group=False):
     return (new_ptr, out, group) if want_group else (new_ptr, out)
 
 
+def take_rows_multi(tensors, idx):
+    """[t[idx] for t in tensors] in one launch (per 16 tensors): all node-level or all
+    edge-level attributes of a Data object (reference src/data/data.py:420-463)."""
+    import ctypes
+    lib = _lib.load()
+    if len(tensors) == 0:
+        return []
+    _require_cuda(idx, *tensors)
+    tensors = [t.contiguous() for t in tensors]
+    idx = _i64c(idx).view(-1)
+    K, n = idx.numel(), len(tensors)
+    outs = [torch.empty((K,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            for t in tensors]
+    row_bytes = [(t.numel() // t.shape[0] if t.shape[0] > 0 else 0) * t.element_size()
+                 for t in tensors]
+    if K > 0:
+        srcs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in tensors])
+        dsts = (ctypes.c_void_p * n)(*[o.data_ptr() for o in outs])
+        rbs = (ctypes.c_int64 * n)(*row_bytes)
+        with torch.cuda.device(idx.device):
+            _lib.check(lib.spt_gather_rows_multi(
+                ctypes.cast(srcs, ctypes.c_void_p), ctypes.cast(dsts, ctypes.c_void_p),
+                ctypes.cast(rbs, ctypes.c_void_p), n, _p(idx), K, _stream()),
+                "spt_gather_rows_multi")
+        _count((n + 15) // 16)
+    return outs
+
+
 def take_rows(t, idx):
     """t[idx] along dim 0 for a CUDA tensor of any dtype (`item[idx]`, reference
     src/data/data.py:447-459); idx int64, in range (Data.select validates it first)."""

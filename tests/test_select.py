@@ -173,6 +173,7 @@ def oracle_primitives(monkeypatch):
     monkeypatch.setattr(ops, 'select_edges', select_edges)
     monkeypatch.setattr(ops, 'csr_select', csr_select)
     monkeypatch.setattr(ops, 'take_rows', lambda t, idx: t[idx])
+    monkeypatch.setattr(ops, 'take_rows_multi', lambda ts, idx: [t[idx] for t in ts])
     monkeypatch.setattr(Cluster, 'from_super_index', staticmethod(from_super_index))
 
 
@@ -328,6 +329,13 @@ def test_gpu_primitives_edge_cases():
                          ((1000, 2, 3), torch.float64), ((1000,), torch.bool)):
         t = (torch.rand(shape, generator=g) * 200).to(dtype)
         assert torch.equal(ops.take_rows(t.cuda(), idx.cuda()).cpu(), t[idx]), (shape, dtype)
+    # the same through the one-launch form, 19 tensors of mixed widths (two launches)
+    ts = [(torch.rand((1000,) + tuple(range(2, 2 + i % 3)), generator=g) * 200).to(dt)
+          for i, dt in enumerate([torch.float32, torch.int64, torch.uint8, torch.float16,
+                                  torch.float64, torch.bool, torch.int32] * 3)][:19]
+    ts.append(torch.empty(1000, 0))
+    for mine, t in zip(ops.take_rows_multi([t.cuda() for t in ts], idx.cuda()), ts):
+        assert mine.dtype == t.dtype and torch.equal(mine.cpu(), t[idx])
 
 
 @pytest.mark.gpu
