@@ -214,6 +214,26 @@ int spt_gather_rows_multi(const void* const* srcs, void* const* outs, const int6
                           int num_tensors, const int64_t* idx, int64_t K, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ *  Per-segment sampling without replacement: `sparse_sample`                     *
+ *  (src/utils/sparse.py:142-243), the core of NAG.get_sampling / SampleSubNodes   *
+ *  (src/data/nag.py:662-711, src/transforms/sampling.py:656-715): csrc/sample.cu  *
+ * ------------------------------------------------------------------------- */
+
+/* For every segment g of the stable CSR (seg_ptr [G+1], seg_perm [n]: spt_group_index of the
+ * candidates' segment ids) draw a uniformly random subset of min(n_samples[g], size_g)
+ * candidates and write their ids — elem_ids[c] for candidate c, or c itself when elem_ids is
+ * NULL — to out[out_ptr[g] ...) in candidate order (out_ptr [G+1] = exclusive scan of the
+ * clamped n_samples; the caller computes n_samples with the reference's fp32 heuristic,
+ * sparse.py:176-189).  Randomness: Philox-4x32-10 keyed by `seed` and the segment id, so the
+ * result depends on (seed, CSR) only.  The reference shuffles everything and sorts by segment;
+ * the SET sampled per segment has the same distribution, the order inside a segment differs. */
+size_t spt_sparse_sample_workspace_bytes(int64_t num_segments);
+int spt_sparse_sample(const int32_t* seg_ptr, const int32_t* seg_perm, int64_t num_segments,
+                      const int64_t* n_samples, const int64_t* out_ptr,
+                      const int64_t* elem_ids /*nullable*/, uint64_t seed, int64_t* out,
+                      void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------- *
  *  Value RPE of SelfAttentionBlock (src/nn/attention.py:294-301), applied        *
  *  algebraically: y = agg + Wbd . abar + bv (x) sump  (csrc/vrpe.cu)              *
  * ------------------------------------------------------------------------- */

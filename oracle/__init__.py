@@ -22,6 +22,9 @@ Parity status
   reference's own src/data/*.py and src/utils/{tensor,sparse}.py, loaded verbatim by
   `oracle/reference_data.py` (restated there: the PyG `Data` attribute store and
   `consecutive_cluster`, third-party and absent like the leaves below).
+* SAMPLING: `oracle/sampling.py` (sparse_sample, SampleSegments weights) against
+  `tests/golden/sampling.pt` from the same loader: counts per segment and the seeded
+  SampleSegments output bit-exact; the random draw itself is checked against the sampling law.
 * LEAVES unpinned: the arithmetic leaves the reference calls live in third-party
   wheels that are absent from /root/reference and from this image
   (`torch_scatter` unpinned for torch 2.2.0, `torch_geometric==2.3.0`;

@@ -164,6 +164,46 @@ def main():
                                          'unique': src[perm]})
     torch.save(out, OUT)
     print(OUT, {k: len(v) for k, v in out.items()})
+    make_sampling(ns, out['nags'])
+
+
+def make_sampling(ns, nags):
+    """tests/golden/sampling.pt: `sparse_sample` (deterministic part: samples per segment; the
+    drawn indices are kept for the record) and SampleSegments under a fixed torch seed."""
+    g = torch.Generator().manual_seed(4321)
+    out = {'sparse': [], 'segments': []}
+    for n, hi, n_max, n_min, masked in (
+            (1, 1, 4, 1, False), (500, 40, 8, 2, False), (500, 40, 8, 2, True),
+            (3000, 7, 32, 16, False), (3000, 7, 32, 1, True), (2000, 300, 4, 4, False),
+            (2000, 50, 0, 0, False), (5000, 3, 64, 1, False), (800, 100, 32, 16, 'bool')):
+        idx = torch.cat((torch.arange(hi), torch.randint(0, hi, (n - hi,), generator=g)))
+        idx = idx[torch.randperm(n, generator=g)]
+        mask = None
+        if masked:
+            mask = torch.randperm(n, generator=g)[:n // 2]
+            if masked == 'bool':
+                m = torch.zeros(n, dtype=torch.bool)
+                m[mask] = True
+                mask = m
+        samples, ptr = ns.sparse_sample(idx, n_max=n_max, n_min=n_min, mask=mask,
+                                        return_pointers=True)
+        out['sparse'].append({'idx': idx, 'n_max': n_max, 'n_min': n_min, 'mask': mask,
+                              'idx_samples': samples, 'ptr_samples': ptr})
+    for name, spec in nags.items():
+        if spec['start'] != 0:
+            continue
+        for ratio, by_size, by_class, seed in ((0.3, False, False, 1), (0.25, True, False, 2),
+                                               ([0.2, 0.5, 0.0][:len(spec['levels']) - 1],
+                                                True, True, 3)):
+            nag = to_reference(ns, spec['levels'], spec['start'])
+            torch.manual_seed(seed)
+            res = ns.SampleSegments(ratio=ratio, by_size=by_size, by_class=by_class)(nag)
+            out['segments'].append({
+                'nag': name, 'ratio': ratio, 'by_size': by_size, 'by_class': by_class,
+                'seed': seed, 'out': [level_dict(ns, res[i]) for i in range(res.num_levels)]})
+    path = OUT.replace('select.pt', 'sampling.pt')
+    torch.save(out, path)
+    print(path, {k: len(v) for k, v in out.items()})
 
 
 if __name__ == '__main__':

@@ -14,9 +14,10 @@ restated here:
     torch_geometric.data.storage.recursive_apply(_)
     torch_geometric.nn.pool.consecutive.consecutive_cluster
     torch_scatter.*                          oracle/leaves.py
-    h5py, numba, omegaconf                   import-only stubs (no I/O, no jit on this path)
+    h5py, numba, omegaconf, torch_cluster    import-only stubs (no I/O, no jit on this path)
 
-Everything under `src.data` and the helpers it calls (`src/utils/{tensor,sparse,dict,list,
+`src/transforms/sampling.py` is loaded too (SampleSubNodes, SampleSegments, through
+`sparse_sample` of src/utils/sparse.py).  Everything under `src.data` and the helpers it calls (`src/utils/{tensor,sparse,dict,list,
 memory}.py`) is the reference's code.  The synthetic modules are removed from sys.modules
 again after loading so that oracle/reference_shim.py (which registers its own `src`) can be
 used in the same process.
@@ -212,7 +213,8 @@ def _njit(*args, **kwargs):
 
 
 _LOADED = None
-_STUB_NAMES = ('h5py', 'numba', 'omegaconf', 'torch_scatter', 'torch_geometric', 'torch_geometric.data',
+_STUB_NAMES = ('h5py', 'numba', 'omegaconf', 'torch_cluster', 'torch_geometric.utils',
+               'torch_geometric.transforms', 'torch_scatter', 'torch_geometric', 'torch_geometric.data',
                'torch_geometric.data.storage', 'torch_geometric.nn', 'torch_geometric.nn.pool',
                'torch_geometric.nn.pool.consecutive')
 
@@ -292,6 +294,24 @@ def load_data():
             for k in getattr(mod, '__all__', []):
                 setattr(data, k, getattr(mod, k))
                 setattr(ns, k, getattr(mod, k))
+        # sampling transforms (src/transforms/sampling.py): SampleSubNodes / SampleSegments only
+        # touch sparse_sample, NAG.get_sampling, NAG.select and torch.multinomial; the voxel /
+        # k-hop / radius helpers the module imports at the top are placeholders
+        sys.modules['torch_geometric.nn.pool'].voxel_grid = None
+        module('torch_geometric.utils', k_hop_subgraph=None, to_undirected=None)
+        module('torch_cluster', grid_cluster=None)
+        module('torch_geometric.transforms', BaseTransform=type('BaseTransform', (), {}))
+        for k in ('scatter_pca', 'sanitize_keys', 'knn_brute_force', 'split_histogram'):
+            if not hasattr(utils, k):
+                setattr(utils, k, None)
+        module('src.utils.histogram', atomic_to_histogram=None)
+        transforms = package('src.transforms')
+        tr = load('src.transforms.transforms', 'src/transforms/transforms.py')
+        transforms.Transform = tr.Transform
+        sampling = load('src.transforms.sampling', 'src/transforms/sampling.py')
+        ns.SampleSubNodes = sampling.SampleSubNodes
+        ns.SampleSegments = sampling.SampleSegments
+        ns.sparse_sample = utils.sparse_sample
         ns.consecutive_cluster = consecutive_cluster
         ns.index_select_pointers = ns.CSRData.index_select_pointers
         ns.sizes_to_pointers = utils.sizes_to_pointers

@@ -113,6 +113,9 @@ SIGNATURES = {
     "spt_csr_select_values_i64": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_ptr,
                                           c_ptr, c_ptr]),
     "spt_gather_rows_bytes": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr]),
+    "spt_sparse_sample_workspace_bytes": (c_size, [c_i64]),
+    "spt_sparse_sample": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, ctypes.c_uint64,
+                                  c_ptr, c_ptr, c_size, c_ptr]),
     "spt_gather_rows_multi": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_i64, c_ptr]),
     "spt_vrpe_blockdiag": (c_int, [c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr]),
     "spt_vrpe_epilogue": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_ptr,

@@ -30,6 +30,7 @@ SOURCES = [
     "vrpe.cu",
     "batch.cu",
     "select.cu",
+    "sample.cu",
 ]
 HEADERS = sorted(f for f in os.listdir(HERE) if f.endswith((".cuh", ".h"))) + \
     [os.path.join(ROOT, "include", "spt_b200.h")]

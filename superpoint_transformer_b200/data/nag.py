@@ -196,6 +196,17 @@ class NAG:
             idx = self[i].super_index[idx]
         return idx
 
+    def get_sampling(self, high=1, low=0, n_max=32, n_min=1, mask=None,
+                     return_pointers=False, seed=None):
+        """Indices sampling `low`-level elements by the `high`-level segment they belong to:
+        at least `n_min`, at most `n_max` per segment, without replacement (reference
+        src/data/nag.py:662-711 -> `sparse_sample`).  On the device (csrc/sample.cu)."""
+        from .. import ops
+        super_index = self.get_super_index(high, low=low)
+        return ops.sparse_sample(super_index, n_max=n_max, n_min=n_min, mask=mask,
+                                 return_pointers=return_pointers,
+                                 num_segments=self[high].num_nodes, seed=seed)
+
     def __repr__(self):
         return (f"{self.__class__.__name__}(num_levels={self.num_levels}, "
                 f"start_i_level={self.start_i_level}, num_points={self.num_points})")

@@ -807,6 +807,63 @@ def csr_select(pointers, values, idx, want_group=False):
     return (new_ptr, out, group) if want_group else (new_ptr, out)
 
 
+def sampling_counts(size, n_max, n_min):
+    """Number of elements `sparse_sample` draws from segments of `size` elements: the
+    reference's fp32 heuristic, written with the same tensor ops (src/utils/sparse.py:176-189)
+    so that it rounds the same way."""
+    if n_max > 0:
+        n_samples = (n_max * torch.tanh(size / n_max)).floor().long()
+    else:
+        n_samples = size.sqrt().round().long()
+    return n_samples.clamp(min=n_min).clamp(max=size)
+
+
+def sparse_sample(idx, n_max=32, n_min=1, mask=None, return_pointers=False, num_segments=None,
+                  seed=None):
+    """Indices of elements sampled without replacement from every segment of `idx` — at least
+    `n_min`, at most `n_max` per segment, within its size (reference
+    src/utils/sparse.py:142-243).  Returns idx_samples (segments ascending) and, with
+    `return_pointers`, the [G+1] pointers of the segments in it.
+
+    Device path (csrc/sample.cu): the elements are grouped once (spt_group_index, cached for a
+    `super_index`) and every segment draws its own random subset — no global shuffle, no sort.
+    `seed`: 64-bit seed of the counter-based generator (default: drawn from torch's global CPU
+    generator, so torch.manual_seed makes the call reproducible).  `num_segments` saves the
+    idx.max() host read."""
+    from .utils.tensor import tensor_idx, sizes_to_pointers
+    assert 0 <= n_min <= n_max
+    lib = _lib.load()
+    _require_cuda(idx)
+    idx = _i64c(idx).view(-1)
+    dev = idx.device
+    G = int(idx.max()) + 1 if num_segments is None else int(num_segments)
+    seg = segment_index(idx, G)
+    size = (seg.ptr[1:] - seg.ptr[:-1]).long()
+    n_samples = sampling_counts(size, n_max, n_min)
+    elem_ids = None
+    mask = tensor_idx(mask, device=dev)
+    if mask is not None:                       # sparse.py:199-205
+        seg = group_index(idx[mask], G)
+        size = (seg.ptr[1:] - seg.ptr[:-1]).long()
+        n_samples = n_samples.clamp(max=size)
+        elem_ids = mask.contiguous()
+    ptr_samples = sizes_to_pointers(n_samples)
+    total = int(ptr_samples[-1])
+    out = torch.empty(total, dtype=torch.int64, device=dev)
+    if seed is None:
+        seed = int(torch.empty((), dtype=torch.int64).random_())
+    if total > 0:
+        nb = lib.spt_sparse_sample_workspace_bytes(G)
+        ws = _ws_bytes(nb, dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.spt_sparse_sample(
+                _p(seg.ptr), _p(seg.perm), G, _p(n_samples), _p(ptr_samples), _p(elem_ids),
+                int(seed) & 0xFFFFFFFFFFFFFFFF, _p(out), _p(ws), nb, _stream()),
+                "spt_sparse_sample")
+        _count(2)
+    return (out, ptr_samples.contiguous()) if return_pointers else out
+
+
 def take_rows_multi(tensors, idx):
     """[t[idx] for t in tensors] in one launch (per 16 tensors): all node-level or all
     edge-level attributes of a Data object (reference src/data/data.py:420-463)."""

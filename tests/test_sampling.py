@@ -1,0 +1,176 @@
+"""Per-segment sampling (sparse_sample / NAG.get_sampling / SampleSubNodes /
+SampleSegments).  Deterministic parts are held bit-exactly to vectors produced by the
+reference's own files (tests/golden/sampling.pt, oracle/make_golden_select.py); the random
+draw is held to the sampling law (the reference's random stream cannot be reproduced)."""
+import os
+
+import pytest
+import torch
+
+from oracle import sampling as OS
+from superpoint_transformer_b200 import ops
+from superpoint_transformer_b200.transforms import SampleSubNodes, SampleSegments
+
+from test_select import (assert_level_equal, levels_of, to_product, oracle_primitives,  # noqa
+                         GOLDEN as SELECT_GOLDEN)
+
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden', 'sampling.pt')
+
+
+@pytest.fixture(scope='module')
+def gold():
+    return torch.load(GOLDEN, weights_only=False)
+
+
+@pytest.fixture(scope='module')
+def nags():
+    return torch.load(SELECT_GOLDEN, weights_only=False)['nags']
+
+
+def check_draw(case, samples, ptr):
+    """what every valid draw satisfies: the reference's counts, distinct elements of the right
+    segment, inside the mask, segments ascending"""
+    idx, mask = case['idx'], case['mask']
+    assert torch.equal(ptr, case['ptr_samples'])
+    assert samples.shape == case['idx_samples'].shape
+    assert samples.unique().numel() == samples.numel()
+    sizes = ptr[1:] - ptr[:-1]
+    seg = torch.arange(sizes.shape[0]).repeat_interleave(sizes)
+    assert torch.equal(idx[samples], seg)
+    if mask is not None:
+        allowed = torch.zeros(idx.shape[0], dtype=torch.bool)
+        allowed[mask] = True
+        assert allowed[samples].all()
+
+
+# ----------------------------------------------------------------------------- CPU
+def test_oracle_sparse_sample_counts_match_reference(gold):
+    g = torch.Generator().manual_seed(0)
+    for case in gold['sparse']:
+        check_draw(case, case['idx_samples'], case['ptr_samples'])      # the reference itself
+        samples, ptr = OS.sparse_sample(case['idx'], case['n_max'], case['n_min'], case['mask'],
+                                        generator=g)
+        check_draw(case, samples, ptr)
+
+
+def test_host_logic_sample_segments_matches_reference(gold, nags, oracle_primitives):
+    """Same torch seed, CPU tensors, device primitives stood in by the oracle: the weights must
+    be the reference's to the bit for torch.multinomial to keep the same nodes."""
+    for case in gold['segments']:
+        spec = nags[case['nag']]
+        nag = to_product(spec['levels'], spec['start'])
+        torch.manual_seed(case['seed'])
+        res = SampleSegments(ratio=case['ratio'], by_size=case['by_size'],
+                             by_class=case['by_class'])(nag)
+        for j, (a, b) in enumerate(zip(levels_of(res), case['out'])):
+            # attributes the reference lost across levels are not compared
+            a = {k: v for k, v in a.items() if k in b}
+            assert_level_equal(a, b, f"{case['nag']} ratio={case['ratio']} level {j}",
+                               canonical_sub=True)
+
+
+def test_segment_weights_match_oracle(nags, oracle_primitives):
+    spec = nags['full4']
+    nag = to_product(spec['levels'], spec['start'])
+    for by_size in (False, True):
+        for by_class in (False, True):
+            t = SampleSegments(0.2, by_size=by_size, by_class=by_class)
+            for i_level in (1, 2, 3):
+                want = OS.segment_weights(nag[i_level].y, nag.get_sub_size(i_level, low=0),
+                                          by_size, by_class)
+                assert torch.equal(t.weights(nag, i_level), want)
+
+
+def test_sample_sub_nodes_identity_and_cpu_refusal(nags):
+    spec = nags['two']
+    nag = to_product(spec['levels'], spec['start'])
+    assert SampleSubNodes(high=1, low=1)(nag) is nag
+    with pytest.raises(RuntimeError, match='CUDA tensors only'):
+        SampleSubNodes(high=1, low=0)(nag)
+
+
+# ----------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+def test_gpu_sparse_sample_counts_and_validity(gold):
+    for case in gold['sparse']:
+        mask = None if case['mask'] is None else case['mask'].cuda()
+        samples, ptr = ops.sparse_sample(case['idx'].cuda(), case['n_max'], case['n_min'], mask,
+                                         return_pointers=True, seed=7)
+        check_draw(case, samples.cpu(), ptr.cpu())
+        again = ops.sparse_sample(case['idx'].cuda(), case['n_max'], case['n_min'], mask, seed=7)
+        assert torch.equal(again, samples)                       # (seed, input) -> output
+        if samples.numel() < case['idx'].numel() // 2 and samples.numel() > 8:
+            other = ops.sparse_sample(case['idx'].cuda(), case['n_max'], case['n_min'], mask,
+                                      seed=8)
+            assert not torch.equal(other, samples)
+        # candidate order inside a segment (the documented difference from the reference)
+        s, p = samples.cpu(), ptr.cpu()
+        for g in range(min(p.numel() - 1, 50)):
+            seg = s[p[g]:p[g + 1]]
+            assert torch.equal(seg, seg.sort().values) or case['mask'] is not None
+
+
+@pytest.mark.gpu
+def test_gpu_sparse_sample_is_uniform_short_segments():
+    """20 000 segments of 6 elements, 3 drawn from each: the 20 possible subsets must be
+    equally likely (chi-square, 19 degrees of freedom; fixed seed)."""
+    G, size = 20000, 6
+    idx = torch.arange(G).repeat_interleave(size).cuda()
+    samples, ptr = ops.sparse_sample(idx, n_max=4, n_min=1, return_pointers=True,
+                                     num_segments=G, seed=123)
+    assert int(ptr[-1]) == 3 * G                                 # floor(4 tanh(6/4)) = 3
+    local = (samples.view(G, 3) % size).cpu()
+    code = (2 ** local).sum(dim=1)
+    counts = torch.bincount(code, minlength=64)
+    counts = counts[counts > 0]
+    assert counts.numel() == 20
+    chi2 = float(((counts - G / 20.0) ** 2 / (G / 20.0)).sum())
+    assert chi2 < 50.0, chi2                                     # p ~ 1e-4 at 19 dof
+
+
+@pytest.mark.gpu
+def test_gpu_sparse_sample_is_uniform_long_segments():
+    """2 000 segments of 300 elements (the warp / radix-select path), 32 drawn from each: every
+    position is kept with probability 32/300, and pairs of neighbours are not correlated."""
+    G, size = 2000, 300
+    k = int(ops.sampling_counts(torch.tensor([size], device='cuda'), 32, 1))   # 32 (or 31)
+    idx = torch.arange(G).repeat_interleave(size).cuda()
+    samples, ptr = ops.sparse_sample(idx, n_max=32, n_min=1, return_pointers=True,
+                                     num_segments=G, seed=99)
+    assert int(ptr[-1]) == k * G
+    local = (samples.view(G, k) % size).cpu()
+    assert (local[:, 1:] > local[:, :-1]).all()                  # distinct, candidate order
+    counts = torch.bincount(local.flatten(), minlength=size).double()
+    expect = G * k / size
+    chi2 = float(((counts - expect) ** 2 / (expect * (1 - k / size))).sum())
+    assert 200.0 < chi2 < 420.0, chi2                            # 299 dof, mean 299, sd 24.5
+    kept = torch.zeros(G, size)
+    kept.scatter_(1, local, 1.0)
+    both = float((kept[:, 1:] * kept[:, :-1]).mean())
+    want = k * (k - 1) / (size * (size - 1))
+    assert abs(both - want) < 6 * (want / (G * (size - 1))) ** 0.5 + 1e-4
+
+
+@pytest.mark.gpu
+def test_gpu_sample_sub_nodes_and_segments_on_benchmark_partition():
+    from superpoint_transformer_b200.synthetic import make_nag, CONFIGS
+    nag = make_nag(**CONFIGS['cfg2']).cuda()
+    sizes = torch.bincount(nag[1].super_index, minlength=nag[2].num_nodes)
+    out = SampleSubNodes(high=2, low=1, n_max=4, n_min=2, seed=5)(nag)
+    want = OS.sampling_counts(sizes.cpu(), 4, 2)
+    got = torch.bincount(out[1].super_index, minlength=out[2].num_nodes).cpu()
+    assert torch.equal(got, want)                # every level-2 node keeps the reference's count
+    assert out[2].num_nodes == nag[2].num_nodes and out[3].num_nodes == nag[3].num_nodes
+    assert torch.equal(out[2].sub.to_super_index(), out[1].super_index)
+    assert int(out[1].edge_index.max()) < out[1].num_nodes
+    # the kept level-1 nodes carry their own attributes (pos is unique per node)
+    assert torch.isin(out[1].pos[:, 0], nag[1].pos[:, 0]).all()
+
+    torch.manual_seed(0)
+    res = SampleSegments(ratio=[0.2, 0.5, 0.1], by_size=True, by_class=False)(nag)
+    n3 = nag[3].num_nodes - int(nag[3].num_nodes * 0.1)
+    assert res[3].num_nodes <= n3      # (a node that loses every child later goes too)
+    for i in (1, 2):
+        assert int(res[i].super_index.max()) + 1 == res[i + 1].num_nodes
+        assert torch.equal(res[i + 1].sub.to_super_index(), res[i].super_index)
+    assert res[2].num_nodes <= nag[2].num_nodes - int(nag[2].num_nodes * 0.5)
