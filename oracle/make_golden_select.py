@@ -171,7 +171,7 @@ def make_sampling(ns, nags):
     """tests/golden/sampling.pt: `sparse_sample` (deterministic part: samples per segment; the
     drawn indices are kept for the record) and SampleSegments under a fixed torch seed."""
     g = torch.Generator().manual_seed(4321)
-    out = {'sparse': [], 'segments': []}
+    out = {'sparse': [], 'segments': [], 'restrict': [], 'edges': []}
     for n, hi, n_max, n_min, masked in (
             (1, 1, 4, 1, False), (500, 40, 8, 2, False), (500, 40, 8, 2, True),
             (3000, 7, 32, 16, False), (3000, 7, 32, 1, True), (2000, 300, 4, 4, False),
@@ -201,6 +201,22 @@ def make_sampling(ns, nags):
             out['segments'].append({
                 'nag': name, 'ratio': ratio, 'by_size': by_size, 'by_class': by_class,
                 'seed': seed, 'out': [level_dict(ns, res[i]) for i in range(res.num_levels)]})
+        for level, num_nodes, num_edges, seed in (('1+', 10, 40, 4), (1, 25, 0, 5),
+                                                  ('all', 30, 100, 6)):
+            nag = to_reference(ns, spec['levels'], spec['start'])
+            torch.manual_seed(seed)
+            res = ns.NAGRestrictSize(level=level, num_nodes=num_nodes, num_edges=num_edges)(nag)
+            out['restrict'].append({
+                'nag': name, 'level': level, 'num_nodes': num_nodes, 'num_edges': num_edges,
+                'seed': seed, 'out': [level_dict(ns, res[i]) for i in range(res.num_levels)]})
+        for n_min, n_max in ((1, 2), (2, 4), (0, 3)):
+            nag = to_reference(ns, spec['levels'], spec['start'])
+            res = ns.SampleEdges(level='1+', n_min=n_min, n_max=n_max)(nag)
+            out['edges'].append({
+                'nag': name, 'level': '1+', 'n_min': n_min, 'n_max': n_max,
+                'degree': [torch.bincount(res[i].edge_index[0], minlength=res[i].num_nodes)
+                           if res[i].edge_index is not None else None
+                           for i in range(res.num_levels)]})
     path = OUT.replace('select.pt', 'sampling.pt')
     torch.save(out, path)
     print(path, {k: len(v) for k, v in out.items()})

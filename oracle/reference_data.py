@@ -311,6 +311,8 @@ def load_data():
         sampling = load('src.transforms.sampling', 'src/transforms/sampling.py')
         ns.SampleSubNodes = sampling.SampleSubNodes
         ns.SampleSegments = sampling.SampleSegments
+        ns.SampleEdges = sampling.SampleEdges
+        ns.NAGRestrictSize = sampling.NAGRestrictSize
         ns.sparse_sample = utils.sparse_sample
         ns.consecutive_cluster = consecutive_cluster
         ns.index_select_pointers = ns.CSRData.index_select_pointers

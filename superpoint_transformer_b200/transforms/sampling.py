@@ -4,8 +4,9 @@ them to `NAG.select` (csrc/select.cu)."""
 import torch
 
 from ..data import NAG
+from ..data.nag import _fill_levels
 
-__all__ = ['SampleSubNodes', 'SampleSegments']
+__all__ = ['SampleSubNodes', 'SampleSegments', 'SampleEdges', 'RestrictSize', 'NAGRestrictSize']
 
 
 class SampleSubNodes:
@@ -76,4 +77,112 @@ class SampleSegments:
             num_keep = num_nodes - int(num_nodes * ratio[i_level - 1])
             idx = torch.multinomial(self.weights(nag, i_level), num_keep, replacement=False)
             nag = nag.select(i_level, idx)
+        return nag
+
+
+def _take_edges(data, idx):
+    """Keep the edges `idx` of `data` in place: edge_index, edge_attr and every `edge_*` key
+    (reference sampling.py:1303-1307), one gather launch for all of them."""
+    from .. import ops
+    keys = (['edge_attr'] if data.edge_attr is not None and data.edge_attr.shape[0] > 0
+            else []) + data.edge_keys
+    outs = ops.take_rows_multi(
+        [data.edge_index[0], data.edge_index[1]] + [data[k] for k in keys], idx)
+    data.edge_index = torch.stack(outs[:2])
+    for k, v in zip(keys, outs[2:]):
+        data[k] = v
+    return data
+
+
+class SampleEdges:
+    """Sample the edges of the chosen levels by source node: at least `n_min` and at most
+    `n_max` edges per node, within what the node has, without replacement (reference
+    src/transforms/sampling.py:1234-1312; `sparse_sample` on `edge_index[0]` = csrc/sample.cu).
+    Modifies the NAG in place and returns it, like the reference.
+
+    `level`: int, 'all', 'i+' or 'i-'.  The transform is applied at exactly those levels (the
+    reference's per-level closures all capture the values of the LAST level, sampling.py:1283,
+    so it only samples when the last level is selected; per-level lists of n_min / n_max fail
+    in the reference and are refused here)."""
+
+    def __init__(self, level='1+', n_min=16, n_max=32, seed=None):
+        assert isinstance(level, (int, str))
+        if not isinstance(n_min, int) or not isinstance(n_max, int):
+            raise NotImplementedError("per-level lists of n_min / n_max (they raise in the "
+                                      "reference as well)")
+        self.level, self.n_min, self.n_max, self.seed = level, n_min, n_max, seed
+
+    def __call__(self, nag):
+        assert isinstance(nag, NAG)
+        flags = _fill_levels(self.level, False, True, nag.absolute_num_levels,
+                             nag.start_i_level)
+        for i_level in nag.level_range:
+            if flags[i_level]:
+                self._process_single_level(nag[i_level], self.n_min, self.n_max, self.seed)
+        return nag
+
+    @staticmethod
+    def _process_single_level(data, n_min, n_max, seed=None):
+        if n_min < 0 or n_max < 0 or not data.has_edges:
+            return data
+        from .. import ops
+        idx = ops.sparse_sample(data.edge_index[0], n_max=n_max, n_min=n_min,
+                                return_pointers=False, num_segments=data.num_nodes, seed=seed)
+        return _take_edges(data, idx)
+
+
+class RestrictSize:
+    """At most `num_nodes` nodes and `num_edges` edges, drawn uniformly (torch.multinomial, as
+    the reference): `Data.select` then an edge gather (reference sampling.py:1315-1348, which
+    keeps the whole tuple `Data.select` returns and fails on the next line; the Data is used
+    here)."""
+
+    def __init__(self, num_nodes=0, num_edges=0):
+        self.num_nodes, self.num_edges = num_nodes, num_edges
+
+    def __call__(self, data):
+        if data.num_nodes > self.num_nodes and self.num_nodes > 0:
+            weights = torch.ones(data.num_nodes, device=data.device)
+            idx = torch.multinomial(weights, self.num_nodes, replacement=False)
+            data = data.select(idx)[0]
+        if data.num_edges > self.num_edges and self.num_edges > 0:
+            weights = torch.ones(data.num_edges, device=data.device)
+            idx = torch.multinomial(weights, self.num_edges, replacement=False)
+            _take_edges(data, idx)
+        return data
+
+
+class NAGRestrictSize:
+    """Per level: at most `num_nodes` nodes (through `NAG.select`, all levels stay consistent)
+    and `num_edges` edges (reference src/transforms/sampling.py:1351-1423).  `level`: int,
+    'all', 'i+' or 'i-'; values <= 0 disable the restriction."""
+
+    def __init__(self, level='1+', num_nodes=0, num_edges=0):
+        assert isinstance(level, (int, str))
+        assert isinstance(num_nodes, int) and isinstance(num_edges, int), \
+            "per-level lists raise in the reference too (a list is compared with an int)"
+        self.level, self.num_nodes, self.num_edges = level, num_nodes, num_edges
+
+    def __call__(self, nag):
+        assert isinstance(nag, NAG)
+        if isinstance(self.level, int):
+            return self._restrict_level(nag, self.level, self.num_nodes, self.num_edges)
+        n = nag.absolute_num_levels
+        level_num_nodes = _fill_levels(self.level, -1, self.num_nodes, n, nag.start_i_level)
+        level_num_edges = _fill_levels(self.level, -1, self.num_edges, n, nag.start_i_level)
+        for i_level in nag.level_range:
+            nag = self._restrict_level(nag, i_level, level_num_nodes[i_level],
+                                       level_num_edges[i_level])
+        return nag
+
+    @staticmethod
+    def _restrict_level(nag, i_level, num_nodes, num_edges):
+        if nag[i_level].num_nodes > num_nodes and num_nodes > 0:
+            weights = torch.ones(nag[i_level].num_nodes, device=nag.device)
+            idx = torch.multinomial(weights, num_nodes, replacement=False)
+            nag = nag.select(i_level, idx)
+        if nag[i_level].num_edges > num_edges and num_edges > 0:
+            weights = torch.ones(nag[i_level].num_edges, device=nag.device)
+            idx = torch.multinomial(weights, num_edges, replacement=False)
+            _take_edges(nag[i_level], idx)
         return nag

@@ -9,7 +9,8 @@ import torch
 
 from oracle import sampling as OS
 from superpoint_transformer_b200 import ops
-from superpoint_transformer_b200.transforms import SampleSubNodes, SampleSegments
+from superpoint_transformer_b200.transforms import (SampleSubNodes, SampleSegments, SampleEdges,
+                                                   NAGRestrictSize, RestrictSize)
 
 from test_select import (assert_level_equal, levels_of, to_product, oracle_primitives,  # noqa
                          GOLDEN as SELECT_GOLDEN)
@@ -69,6 +70,58 @@ def test_host_logic_sample_segments_matches_reference(gold, nags, oracle_primiti
                                canonical_sub=True)
 
 
+def test_host_logic_restrict_size_matches_reference(gold, nags, oracle_primitives):
+    for case in gold['restrict']:
+        spec = nags[case['nag']]
+        nag = to_product(spec['levels'], spec['start'])
+        torch.manual_seed(case['seed'])
+        res = NAGRestrictSize(level=case['level'], num_nodes=case['num_nodes'],
+                              num_edges=case['num_edges'])(nag)
+        for j, (a, b) in enumerate(zip(levels_of(res), case['out'])):
+            a = {k: v for k, v in a.items() if k in b}
+            assert_level_equal(a, b, f"{case['nag']} level={case['level']} level {j}",
+                               canonical_sub=True)
+    # Data-level variant: node and edge budgets are met, edges stay inside the selection
+    spec = nags['full4']
+    torch.manual_seed(0)
+    d = RestrictSize(num_nodes=20, num_edges=15)(to_product(spec['levels'], 0)[1])
+    assert d.num_nodes == 20 and d.num_edges <= 15 and int(d.edge_index.max()) < 20
+    assert d.edge_attr.shape[0] == d.num_edges
+
+
+def check_sample_edges(gold, nags, device):
+    for case in gold['edges']:
+        spec = nags[case['nag']]
+        nag = to_product(spec['levels'], spec['start'], device)
+        before = [None if nag[i].edge_index is None else
+                  (nag[i].edge_index.clone(), nag[i].edge_attr.clone()) for i in nag.level_range]
+        res = SampleEdges(level=case['level'], n_min=case['n_min'], n_max=case['n_max'],
+                          seed=3)(nag)
+        assert res is nag                                    # in place, like the reference
+        for j, want in enumerate(case['degree']):
+            d = res[j + spec['start']]
+            if want is None:
+                assert d.edge_index is None
+                continue
+            got = torch.bincount(d.edge_index[0], minlength=d.num_nodes).cpu()
+            assert torch.equal(got, want)                    # the reference's count per node
+            # every kept edge is an input edge and carries its own attributes
+            ei, ea = before[j]
+            n = d.num_nodes
+            key_in = (ei[0] * n + ei[1]).cpu()
+            key_out = (d.edge_index[0] * n + d.edge_index[1]).cpu()
+            assert torch.isin(key_out, key_in).all()
+            rows = {(int(k), tuple(r.tolist())) for k, r in zip(key_in, ea.cpu())}
+            assert all((int(k), tuple(r.tolist())) in rows
+                       for k, r in zip(key_out, d.edge_attr.cpu()))
+
+
+def test_host_logic_sample_edges_degrees_match_reference(gold, nags, oracle_primitives):
+    check_sample_edges(gold, nags, 'cpu')
+    with pytest.raises(NotImplementedError):
+        SampleEdges(n_min=[1, 2], n_max=4)
+
+
 def test_segment_weights_match_oracle(nags, oracle_primitives):
     spec = nags['full4']
     nag = to_product(spec['levels'], spec['start'])
@@ -108,6 +161,20 @@ def test_gpu_sparse_sample_counts_and_validity(gold):
         for g in range(min(p.numel() - 1, 50)):
             seg = s[p[g]:p[g + 1]]
             assert torch.equal(seg, seg.sort().values) or case['mask'] is not None
+
+
+@pytest.mark.gpu
+def test_gpu_sample_edges_and_restrict_size(gold, nags):
+    check_sample_edges(gold, nags, 'cuda')
+    spec = nags['full4']
+    res = NAGRestrictSize(level='1+', num_nodes=30, num_edges=50)(
+        to_product(spec['levels'], 0, 'cuda'))
+    for i in (1, 2, 3):
+        assert res[i].num_nodes <= 30 and res[i].num_edges <= 50
+        assert res[i].edge_attr.shape[0] == res[i].num_edges
+    for i in (0, 1, 2):
+        assert int(res[i].super_index.max()) + 1 == res[i + 1].num_nodes
+        assert torch.equal(res[i + 1].sub.to_super_index(), res[i].super_index)
 
 
 @pytest.mark.gpu

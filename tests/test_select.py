@@ -169,6 +169,13 @@ def oracle_primitives(monkeypatch):
         c = O.cluster_from_dense(super_index, torch.arange(super_index.shape[0]))
         return Cluster(c['pointers'], c['points'])
 
+    def sparse_sample(idx, n_max=32, n_min=1, mask=None, return_pointers=False,
+                      num_segments=None, seed=None):
+        from oracle import sampling as OS
+        samples, ptr = OS.sparse_sample(idx, n_max, n_min, mask)
+        return (samples, ptr) if return_pointers else samples
+
+    monkeypatch.setattr(ops, 'sparse_sample', sparse_sample)
     monkeypatch.setattr(ops, 'relabel_consecutive', relabel_consecutive)
     monkeypatch.setattr(ops, 'select_edges', select_edges)
     monkeypatch.setattr(ops, 'csr_select', csr_select)
