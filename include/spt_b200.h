@@ -213,6 +213,29 @@ int spt_gather_rows_bytes(const void* src, int64_t row_bytes, const int64_t* idx
 int spt_gather_rows_multi(const void* const* srcs, void* const* outs, const int64_t* row_bytes,
                           int num_tensors, const int64_t* idx, int64_t K, void* stream);
 
+/* Subgraph sampling (src/transforms/sampling.py:1003-1231).  Node sets are int32 flag vectors
+ * of N+1 entries (flags[N] = 0, the scan's sentinel).
+ * spt_radius_flags: flags[i] = 1 when node i is within r of one of the (<= 64) seeds that shares
+ * its `batch` id — a sphere, or with cylindrical != 0 a cylinder around z — and within[s] = the
+ * number of such nodes of seed s (for the caller's k_max check): the neighbour search of
+ * SampleRadiusSubgraphs (:1196-1231 -> knn_brute_force, src/utils/neighbors.py:245-295) in one
+ * pass instead of a full sort of the distances.  pos is [N, 3] fp32; z_offset (device scalar,
+ * required with batch) is the reference's per-batch-item z shift (neighbors.py:273-279).
+ * spt_khop_expand: flags_out = flags_in plus the neighbours of the flagged nodes over the edges
+ * taken in both directions — one hop of k_hop_subgraph(to_undirected(edge_index)) (:1080-1091).
+ * spt_where_count / spt_where_write: ascending positions of the non-zero flags (two phases:
+ * slot [n+1] = exclusive scan, counts[0] = how many). */
+int spt_radius_flags(const float* pos, int64_t N, const int64_t* batch /*nullable*/,
+                     const int64_t* seeds, int num_seeds, float r, int cylindrical,
+                     const float* z_offset /*nullable*/, int32_t* flags, int32_t* within,
+                     void* stream);
+int spt_khop_expand(const int64_t* edge_index, int64_t E, int64_t N, const int32_t* flags_in,
+                    int32_t* flags_out, void* stream);
+size_t spt_where_workspace_bytes(int64_t n);
+int spt_where_count(const int32_t* flags, int64_t n, int32_t* slot, int64_t* counts, void* ws,
+                    size_t ws_bytes, void* stream);
+int spt_where_write(const int32_t* slot, int64_t n, int64_t* out, void* stream);
+
 /* ------------------------------------------------------------------------- *
  *  Per-segment sampling without replacement: `sparse_sample`                     *
  *  (src/utils/sparse.py:142-243), the core of NAG.get_sampling / SampleSubNodes   *

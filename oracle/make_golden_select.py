@@ -171,7 +171,7 @@ def make_sampling(ns, nags):
     """tests/golden/sampling.pt: `sparse_sample` (deterministic part: samples per segment; the
     drawn indices are kept for the record) and SampleSegments under a fixed torch seed."""
     g = torch.Generator().manual_seed(4321)
-    out = {'sparse': [], 'segments': [], 'restrict': [], 'edges': []}
+    out = {'sparse': [], 'segments': [], 'restrict': [], 'edges': [], 'subgraphs': []}
     for n, hi, n_max, n_min, masked in (
             (1, 1, 4, 1, False), (500, 40, 8, 2, False), (500, 40, 8, 2, True),
             (3000, 7, 32, 16, False), (3000, 7, 32, 1, True), (2000, 300, 4, 4, False),
@@ -217,6 +217,36 @@ def make_sampling(ns, nags):
                 'degree': [torch.bincount(res[i].edge_index[0], minlength=res[i].num_nodes)
                            if res[i].edge_index is not None else None
                            for i in range(res.num_levels)]})
+        # subgraph sampling: seeds from torch's global CPU generator (fixed seed), then the
+        # reference's neighbour search + NAG.select.  `batch`: two halves of every level along x
+        for kind, kw in (('radius', dict(r=0.35, i_level=1, k=1)),
+                         ('radius', dict(r=0.3, i_level=1, k=3, by_size=True)),
+                         ('radius', dict(r=0.25, i_level=2, k=2, cylindrical=True,
+                                         by_class=True)),
+                         ('radius', dict(r=0.2, i_level=1, k=3, k_max=101)),
+                         ('radius_batch', dict(r=0.4, i_level=1, k=2, use_batch=True)),
+                         ('khop', dict(hops=1, i_level=1, k=2)),
+                         ('khop', dict(hops=2, i_level=2, k=1, by_size=True))):
+            if kw['i_level'] >= len(spec['levels']):
+                continue
+            nag = to_reference(ns, spec['levels'], spec['start'])
+            batches = None
+            if kind == 'radius_batch':
+                # consistent batch ids: the top level splits along x, children inherit
+                top = len(spec['levels']) - 1
+                b = (spec['levels'][top]['pos'][:, 0] > 0.5).long()
+                batches = [None] * (top + 1)
+                batches[top] = b
+                for i in range(top - 1, -1, -1):
+                    batches[i] = batches[i + 1][spec['levels'][i]['super_index']]
+                for i in range(top + 1):
+                    nag[i].batch = batches[i].clone()
+            cls = ns.SampleKHopSubgraphs if kind == 'khop' else ns.SampleRadiusSubgraphs
+            torch.manual_seed(17)
+            res = cls(disjoint=False, **kw)(nag)
+            out['subgraphs'].append({
+                'nag': name, 'kind': kind, 'kw': kw, 'seed': 17, 'batches': batches,
+                'out': [level_dict(ns, res[i]) for i in range(res.num_levels)]})
     path = OUT.replace('select.pt', 'sampling.pt')
     torch.save(out, path)
     print(path, {k: len(v) for k, v in out.items()})

@@ -206,6 +206,35 @@ class PyGBatch(PyGData):
                                   'in superpoint_transformer_b200/data/data.py')
 
 
+def to_undirected(edge_index, *args, **kwargs):
+    """torch_geometric.utils.to_undirected (PyG 2.3.0) without attributes: both directions,
+    sorted, duplicates removed."""
+    row = torch.cat((edge_index[0], edge_index[1]))
+    col = torch.cat((edge_index[1], edge_index[0]))
+    n = int(max(row.max(), col.max())) + 1 if row.numel() else 1
+    key = (row * n + col).unique()
+    return torch.stack((key // n, key % n))
+
+
+def k_hop_subgraph(node_idx, num_hops, edge_index, relabel_nodes=False, num_nodes=None,
+                   flow='source_to_target'):
+    """torch_geometric.utils.k_hop_subgraph (PyG 2.3.0): (subset, edge_index, inv, edge_mask);
+    the reference only reads `subset` (src/transforms/sampling.py:1086-1090)."""
+    col, row = edge_index if flow == 'source_to_target' else (edge_index[1], edge_index[0])
+    node_idx = node_idx.view(-1)
+    subsets = [node_idx]
+    for _ in range(num_hops):
+        node_mask = torch.zeros(num_nodes, dtype=torch.bool, device=row.device)
+        node_mask[subsets[-1]] = True
+        subsets.append(col[node_mask[row]])
+    subset, inv = torch.cat(subsets).unique(return_inverse=True)
+    inv = inv[:node_idx.numel()]
+    node_mask = torch.zeros(num_nodes, dtype=torch.bool, device=row.device)
+    node_mask[subset] = True
+    edge_mask = node_mask[row] & node_mask[col]
+    return subset, edge_index[:, edge_mask], inv, edge_mask
+
+
 def _njit(*args, **kwargs):
     if len(args) == 1 and callable(args[0]) and not kwargs:
         return args[0]
@@ -214,6 +243,7 @@ def _njit(*args, **kwargs):
 
 _LOADED = None
 _STUB_NAMES = ('h5py', 'numba', 'omegaconf', 'torch_cluster', 'torch_geometric.utils',
+               'torch_geometric.nn.pool',
                'torch_geometric.transforms', 'torch_scatter', 'torch_geometric', 'torch_geometric.data',
                'torch_geometric.data.storage', 'torch_geometric.nn', 'torch_geometric.nn.pool',
                'torch_geometric.nn.pool.consecutive')
@@ -298,7 +328,13 @@ def load_data():
         # touch sparse_sample, NAG.get_sampling, NAG.select and torch.multinomial; the voxel /
         # k-hop / radius helpers the module imports at the top are placeholders
         sys.modules['torch_geometric.nn.pool'].voxel_grid = None
-        module('torch_geometric.utils', k_hop_subgraph=None, to_undirected=None)
+        module('torch_geometric.utils', k_hop_subgraph=k_hop_subgraph,
+               to_undirected=to_undirected, coalesce=None)
+        module('src.dependencies')
+        module('src.dependencies.FRNN', frnn=None)
+        module('src.utils.scatter', scatter_nearest_neighbor=None)
+        nb = load('src.utils.neighbors', 'src/utils/neighbors.py')
+        utils.knn_brute_force, utils.knn_2 = nb.knn_brute_force, nb.knn_2
         module('torch_cluster', grid_cluster=None)
         module('torch_geometric.transforms', BaseTransform=type('BaseTransform', (), {}))
         for k in ('scatter_pca', 'sanitize_keys', 'knn_brute_force', 'split_histogram'):
@@ -312,6 +348,8 @@ def load_data():
         ns.SampleSubNodes = sampling.SampleSubNodes
         ns.SampleSegments = sampling.SampleSegments
         ns.SampleEdges = sampling.SampleEdges
+        ns.SampleRadiusSubgraphs = sampling.SampleRadiusSubgraphs
+        ns.SampleKHopSubgraphs = sampling.SampleKHopSubgraphs
         ns.NAGRestrictSize = sampling.NAGRestrictSize
         ns.sparse_sample = utils.sparse_sample
         ns.consecutive_cluster = consecutive_cluster

@@ -64,3 +64,37 @@ def segment_weights(y, node_size, by_size, by_class):
         weights += class_weights.squeeze()
     weights /= weights.sum()
     return weights
+
+
+def radius_nodes(pos, seeds, r, k_max=10000, batch=None, cylindrical=False):
+    """Neighbour search of SampleRadiusSubgraphs: src/transforms/sampling.py:1196-1231 with
+    knn_brute_force (src/utils/neighbors.py:245-295) -> sorted unique node ids."""
+    mask = torch.tensor([[1, 1, 0 if cylindrical else 1]])
+    x_search, x_query = pos * mask, pos[seeds] * mask
+    if batch is not None:
+        hi = max(x_search[:, 2].max(), x_query[:, 2].max())
+        lo = min(x_search[:, 2].min(), x_query[:, 2].min())
+        z_offset = hi - lo + r + 1
+        off_s, off_q = torch.zeros_like(x_search), torch.zeros_like(x_query)
+        off_s[:, 2] = batch * z_offset
+        off_q[:, 2] = batch[seeds] * z_offset
+        x_search, x_query = x_search + off_s, x_query + off_q
+    distances = (x_search.unsqueeze(0) - x_query.unsqueeze(1)).norm(dim=2)
+    distances, neighbors = distances.sort(dim=1)
+    distances, neighbors = distances[:, :k_max], neighbors[:, :k_max]
+    neighbors = neighbors.clone()
+    neighbors[distances > r] = -1
+    return neighbors[neighbors >= 0].unique()
+
+
+def khop_nodes(edge_index, seeds, hops, num_nodes):
+    """torch_geometric.utils.k_hop_subgraph(seeds, hops, to_undirected(edge_index))[0] (PyG
+    2.3.0, third-party): src/transforms/sampling.py:1080-1091."""
+    row = torch.cat((edge_index[0], edge_index[1]))
+    col = torch.cat((edge_index[1], edge_index[0]))
+    subsets = [seeds.view(-1)]
+    for _ in range(hops):
+        node_mask = torch.zeros(num_nodes, dtype=torch.bool)
+        node_mask[subsets[-1]] = True
+        subsets.append(col[node_mask[row]])
+    return torch.cat(subsets).unique()

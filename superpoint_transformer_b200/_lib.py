@@ -116,6 +116,12 @@ SIGNATURES = {
     "spt_sparse_sample_workspace_bytes": (c_size, [c_i64]),
     "spt_sparse_sample": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, ctypes.c_uint64,
                                   c_ptr, c_ptr, c_size, c_ptr]),
+    "spt_radius_flags": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_int, ctypes.c_float, c_int, c_ptr,
+                                 c_ptr, c_ptr, c_ptr]),
+    "spt_khop_expand": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr]),
+    "spt_where_workspace_bytes": (c_size, [c_i64]),
+    "spt_where_count": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
+    "spt_where_write": (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
     "spt_gather_rows_multi": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_i64, c_ptr]),
     "spt_vrpe_blockdiag": (c_int, [c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr]),
     "spt_vrpe_epilogue": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_ptr,

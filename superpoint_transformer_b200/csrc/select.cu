@@ -181,6 +181,86 @@ static __global__ void k_gather_rows(const Unit* __restrict__ src, int64_t row_u
   }
 }
 
+// ---------------------------------------------------------------- subgraph sampling helpers
+// flags[i] = 1 when node i lies within `r` of a seed of its own batch item (sphere, or
+// cylinder around z): the neighbour search of SampleRadiusSubgraphs (reference
+// src/transforms/sampling.py:1196-1231 -> knn_brute_force src/utils/neighbors.py:245-295, which
+// sorts ALL distances per seed).  The arithmetic follows the reference's tensor expression in
+// fp32 without contraction: z' = z * mask_z + batch * z_offset, d = sqrt(dx^2 + dy^2 + dz^2),
+// kept when d <= r.  within[s] counts the nodes of seed s (the caller needs it for k_max).
+constexpr int kMaxSeeds = 64;
+
+static __global__ void __launch_bounds__(kSelThreads)
+k_radius_flags(const float* __restrict__ pos, int64_t N, const int64_t* __restrict__ batch,
+               const int64_t* __restrict__ seeds, int num_seeds, float r, int cylindrical,
+               const float* __restrict__ z_offset, int32_t* __restrict__ flags,
+               int32_t* __restrict__ within) {
+  __shared__ float sx[kMaxSeeds], sy[kMaxSeeds], sz[kMaxSeeds];
+  __shared__ int32_t scount[kMaxSeeds];
+  const float zoff = (batch && z_offset) ? *z_offset : 0.f;
+  const float mz = cylindrical ? 0.f : 1.f;
+  if (threadIdx.x < num_seeds) {
+    const int64_t s = seeds[threadIdx.x];
+    sx[threadIdx.x] = pos[3 * s];
+    sy[threadIdx.x] = pos[3 * s + 1];
+    const float zb = batch ? __fmul_rn((float)batch[s], zoff) : 0.f;
+    sz[threadIdx.x] = __fadd_rn(__fmul_rn(pos[3 * s + 2], mz), zb);
+    scount[threadIdx.x] = 0;
+  }
+  __syncthreads();
+  SPT_GRID_STRIDE(i, N + 1) {
+    int f = 0;
+    if (i < N) {
+      const float x = pos[3 * i], y = pos[3 * i + 1];
+      const float zb = batch ? __fmul_rn((float)batch[i], zoff) : 0.f;
+      const float z = __fadd_rn(__fmul_rn(pos[3 * i + 2], mz), zb);
+      for (int s = 0; s < num_seeds; ++s) {
+        const float dx = __fsub_rn(x, sx[s]), dy = __fsub_rn(y, sy[s]), dz = __fsub_rn(z, sz[s]);
+        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)),
+                                   __fmul_rn(dz, dz));
+        if (__fsqrt_rn(d2) <= r) {
+          f = 1;
+          atomicAdd(&scount[s], 1);
+        }
+      }
+    }
+    flags[i] = f;
+  }
+  __syncthreads();
+  if (threadIdx.x < num_seeds && scount[threadIdx.x])
+    atomicAdd(&within[threadIdx.x], scount[threadIdx.x]);
+}
+
+// one hop over undirected edges: out (pre-filled with a copy of in) gains the neighbours of
+// every flagged node (torch_geometric.utils.k_hop_subgraph after to_undirected,
+// sampling.py:1080-1091)
+static __global__ void k_khop_expand(const int64_t* __restrict__ edge_index, int64_t E,
+                                     int64_t N, const int32_t* __restrict__ in,
+                                     int32_t* __restrict__ out) {
+  SPT_GRID_STRIDE(e, E) {
+    const int64_t u = edge_index[e], v = edge_index[E + e];
+    if (u < 0 || u >= N || v < 0 || v >= N) continue;
+    if (in[u]) out[v] = 1;
+    if (in[v]) out[u] = 1;
+  }
+}
+
+static __global__ void k_where_count(const int32_t* __restrict__ slot, int64_t n,
+                                     int64_t* __restrict__ counts) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    counts[0] = slot[n];
+    counts[1] = 0;
+  }
+}
+
+static __global__ void k_where_write(const int32_t* __restrict__ slot, int64_t n,
+                                     int64_t* __restrict__ out) {
+  SPT_GRID_STRIDE(i, n) {
+    const int32_t p = slot[i];
+    if (slot[i + 1] != p) out[p] = i;
+  }
+}
+
 // several tensors, one launch: the table travels in the kernel parameters (no device copy)
 constexpr int kMultiMax = 16;
 struct GatherMulti {
@@ -413,6 +493,65 @@ int spt_gather_rows_multi(const void* const* srcs, void* const* outs, const int6
     k_gather_rows_multi<<<sel_grid(tab.unit_prefix[tab.n]), kSelThreads, 0, st>>>(tab, idx);
   }
   return check_launch("gather_rows_multi");
+}
+
+int spt_radius_flags(const float* pos, int64_t N, const int64_t* batch, const int64_t* seeds,
+                     int num_seeds, float r, int cylindrical, const float* z_offset,
+                     int32_t* flags, int32_t* within, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  SPT_REQUIRE(N >= 0 && num_seeds >= 0, SPT_E_INVALID, "radius_flags: negative size");
+  SPT_REQUIRE(num_seeds <= kMaxSeeds, SPT_E_TOO_LARGE, "radius_flags: more than %d seeds",
+              kMaxSeeds);
+  SPT_REQUIRE(flags && within && (N == 0 || pos) && (num_seeds == 0 || seeds) &&
+                  (!batch || z_offset),
+              SPT_E_INVALID, "radius_flags: null pointer");
+  cudaError_t ce = cudaMemsetAsync(within, 0, sizeof(int32_t) * (num_seeds > 0 ? num_seeds : 1), st);
+  if (ce != cudaSuccess) {
+    set_error("radius_flags memset: %s", cudaGetErrorString(ce));
+    return (int)ce;
+  }
+  k_radius_flags<<<sel_grid(N + 1), kSelThreads, 0, st>>>(pos, N, batch, seeds, num_seeds, r,
+                                                           cylindrical, z_offset, flags, within);
+  return check_launch("radius_flags");
+}
+
+int spt_khop_expand(const int64_t* edge_index, int64_t E, int64_t N, const int32_t* flags_in,
+                    int32_t* flags_out, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  SPT_REQUIRE(E >= 0 && N >= 0, SPT_E_INVALID, "khop_expand: negative size");
+  SPT_REQUIRE(flags_in && flags_out && (E == 0 || edge_index), SPT_E_INVALID,
+              "khop_expand: null pointer");
+  cudaError_t ce = cudaMemcpyAsync(flags_out, flags_in, sizeof(int32_t) * (size_t)(N + 1),
+                                   cudaMemcpyDeviceToDevice, st);
+  if (ce != cudaSuccess) {
+    set_error("khop_expand copy: %s", cudaGetErrorString(ce));
+    return (int)ce;
+  }
+  if (E > 0)
+    k_khop_expand<<<sel_grid(E), kSelThreads, 0, st>>>(edge_index, E, N, flags_in, flags_out);
+  return check_launch("khop_expand");
+}
+
+size_t spt_where_workspace_bytes(int64_t n) { return n < 0 ? 0 : scan_workspace_bytes(n + 1); }
+
+int spt_where_count(const int32_t* flags, int64_t n, int32_t* slot, int64_t* counts, void* ws,
+                    size_t ws_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  SPT_REQUIRE(n >= 0 && n < 2147483646LL, SPT_E_INVALID, "where_count: bad size");
+  SPT_REQUIRE(flags && slot && counts && ws, SPT_E_INVALID, "where_count: null pointer");
+  SPT_REQUIRE(ws_bytes >= spt_where_workspace_bytes(n), SPT_E_WORKSPACE,
+              "where_count: workspace too small");
+  exclusive_scan_i32(flags, n + 1, slot, (int32_t*)ws, st);
+  k_where_count<<<1, 32, 0, st>>>(slot, n, counts);
+  return check_launch("where_count");
+}
+
+int spt_where_write(const int32_t* slot, int64_t n, int64_t* out, void* stream_) {
+  SPT_REQUIRE(n >= 0, SPT_E_INVALID, "where_write: negative size");
+  if (n == 0) return SPT_OK;
+  SPT_REQUIRE(slot && out, SPT_E_INVALID, "where_write: null pointer");
+  k_where_write<<<sel_grid(n), kSelThreads, 0, (cudaStream_t)stream_>>>(slot, n, out);
+  return check_launch("where_write");
 }
 
 }  // extern "C"

@@ -864,6 +864,95 @@ def sparse_sample(idx, n_max=32, n_min=1, mask=None, return_pointers=False, num_
     return (out, ptr_samples.contiguous()) if return_pointers else out
 
 
+def _flags_to_index(flags, n, extra=None):
+    """Ascending positions of the non-zero entries of an int32 flag vector [n+1] (two-phase
+    `where`, csrc/select.cu).  `extra`: a small int tensor read back in the same host read."""
+    lib = _lib.load()
+    dev = flags.device
+    slot = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    counts = torch.empty(2, dtype=torch.int64, device=dev)
+    nb = lib.spt_where_workspace_bytes(n)
+    ws = _ws_bytes(nb, dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.spt_where_count(_p(flags), n, _p(slot), _p(counts), _p(ws), nb,
+                                       _stream()), "spt_where_count")
+        _count(4)
+        if extra is None:
+            total, extra_host = _read_counts(counts, "where"), None
+        else:
+            host = torch.cat((counts, extra.long().view(-1))).tolist()
+            total, extra_host = host[0], host[2:]
+        out = torch.empty(total, dtype=torch.int64, device=dev)
+        if total > 0:
+            _lib.check(lib.spt_where_write(_p(slot), n, _p(out), _stream()), "spt_where_write")
+            _count()
+    return out, extra_host
+
+
+def radius_nodes(pos, seeds, r, k_max=10000, batch=None, cylindrical=False):
+    """Sorted ids of the nodes within `r` of one of `seeds` (same `batch` item; sphere, or
+    cylinder around z), at most the `k_max` closest per seed: the neighbour search of
+    SampleRadiusSubgraphs (reference src/transforms/sampling.py:1196-1231, which sorts every
+    seed's distances to all nodes with knn_brute_force, src/utils/neighbors.py:245-295).  One
+    pass over the nodes (csrc/select.cu) + an ordered compaction."""
+    lib = _lib.load()
+    _require_cuda(pos, seeds, batch)
+    pos = _f32c(pos)
+    seeds = _i64c(seeds).view(-1)
+    batch = _i64c(batch)
+    N, S, dev = pos.shape[0], seeds.numel(), pos.device
+    if pos.dim() != 2 or pos.shape[1] != 3:
+        raise ValueError("radius_nodes: pos must be [N, 3]")
+    z_offset = None
+    if batch is not None:                       # neighbors.py:272-275, same tensor ops
+        z = pos[:, 2] * (0 if cylindrical else 1)
+        z_offset = (z.max() - z.min() + r + 1).float().contiguous()
+    flags = torch.empty(N + 1, dtype=torch.int32, device=dev)
+    within = torch.empty(max(S, 1), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.spt_radius_flags(_p(pos), N, _p(batch), _p(seeds), S, float(r),
+                                        1 if cylindrical else 0, _p(z_offset), _p(flags),
+                                        _p(within), _stream()), "spt_radius_flags")
+    _count()
+    idx, per_seed = _flags_to_index(flags, N, extra=within)
+    if max(per_seed[:S], default=0) > k_max:
+        # more than k_max nodes inside the radius of a seed: the reference keeps the k_max
+        # closest.  Rare (k_max defaults to 10000): done with its own tensor expression.
+        mask = torch.tensor([[1, 1, 0 if cylindrical else 1]], device=dev)
+        xs, xq = pos * mask, pos[seeds] * mask
+        if batch is not None:
+            off_s, off_q = torch.zeros_like(xs), torch.zeros_like(xq)
+            off_s[:, 2] = batch * z_offset
+            off_q[:, 2] = batch[seeds] * z_offset
+            xs, xq = xs + off_s, xq + off_q
+        d = (xs.unsqueeze(0) - xq.unsqueeze(1)).norm(dim=2)
+        d, nb = d.sort(dim=1)
+        d, nb = d[:, :k_max], nb[:, :k_max]
+        idx = nb[d <= r].unique()
+    return idx
+
+
+def khop_nodes(edge_index, seeds, hops, num_nodes):
+    """Sorted ids of the nodes at most `hops` edges away from `seeds`, edges taken in both
+    directions: torch_geometric.utils.k_hop_subgraph(seeds, hops, to_undirected(edge_index))[0]
+    (reference src/transforms/sampling.py:1080-1091); one edge pass per hop."""
+    lib = _lib.load()
+    _require_cuda(edge_index, seeds)
+    ei = _i64c(edge_index)
+    seeds = _i64c(seeds).view(-1)
+    N, E, dev = int(num_nodes), int(ei.shape[1]), ei.device
+    flags = torch.zeros(N + 1, dtype=torch.int32, device=dev)
+    flags[seeds] = 1
+    other = torch.empty_like(flags)
+    with torch.cuda.device(dev):
+        for _ in range(int(hops)):
+            _lib.check(lib.spt_khop_expand(_p(ei), E, N, _p(flags), _p(other), _stream()),
+                       "spt_khop_expand")
+            flags, other = other, flags
+            _count(2)
+    return _flags_to_index(flags, N)[0]
+
+
 def take_rows_multi(tensors, idx):
     """[t[idx] for t in tensors] in one launch (per 16 tensors): all node-level or all
     edge-level attributes of a Data object (reference src/data/data.py:420-463)."""

@@ -3,10 +3,11 @@ keywords and behaviour of reference src/transforms/sampling.py).  They draw indi
 them to `NAG.select` (csrc/select.cu)."""
 import torch
 
-from ..data import NAG
+from ..data import NAG, NAGBatch
 from ..data.nag import _fill_levels
 
-__all__ = ['SampleSubNodes', 'SampleSegments', 'SampleEdges', 'RestrictSize', 'NAGRestrictSize']
+__all__ = ['SampleSubNodes', 'SampleSegments', 'SampleEdges', 'RestrictSize', 'NAGRestrictSize',
+           'SampleKHopSubgraphs', 'SampleRadiusSubgraphs']
 
 
 class SampleSubNodes:
@@ -46,23 +47,7 @@ class SampleSegments:
 
     def weights(self, nag, i_level):
         """Sampling weight of every node of `i_level` (sampling.py:771-798)."""
-        num_nodes = nag[i_level].num_nodes
-        weights = torch.ones(num_nodes, device=nag.device)
-        if self.by_size:
-            node_size = nag.get_sub_size(i_level, low=0)
-            size_weights = node_size ** 0.333
-            size_weights /= size_weights.sum()
-            weights += size_weights
-        if self.by_class and nag[i_level].y is not None:
-            counts = nag[i_level].y.sum(dim=0).sqrt()
-            scores = 1 / (counts + 1)
-            scores /= scores.sum()
-            mask = nag[i_level].y.gt(0)
-            class_weights = (mask * scores.view(1, -1)).max(dim=1).values
-            class_weights /= class_weights.sum()
-            weights += class_weights.squeeze()
-        weights /= weights.sum()
-        return weights
+        return _node_weights(nag, i_level, self.by_size, self.by_class)
 
     def __call__(self, nag):
         assert isinstance(nag, NAG)
@@ -78,6 +63,29 @@ class SampleSegments:
             idx = torch.multinomial(self.weights(nag, i_level), num_keep, replacement=False)
             nag = nag.select(i_level, idx)
         return nag
+
+
+def _node_weights(nag, i_level, by_size, by_class):
+    """Sampling weight of every node of `i_level`: uniform, plus a size term (level-0 size to
+    the power 0.333) and a rare-class term (reference sampling.py:771-798 and :893-918, the
+    same expression in both places)."""
+    num_nodes = nag[i_level].num_nodes
+    weights = torch.ones(num_nodes, device=nag.device)
+    if by_size:
+        node_size = nag.get_sub_size(i_level, low=0)
+        size_weights = node_size ** 0.333
+        size_weights /= size_weights.sum()
+        weights += size_weights
+    if by_class and nag[i_level].y is not None:
+        counts = nag[i_level].y.sum(dim=0).sqrt()
+        scores = 1 / (counts + 1)
+        scores /= scores.sum()
+        mask = nag[i_level].y.gt(0)
+        class_weights = (mask * scores.view(1, -1)).max(dim=1).values
+        class_weights /= class_weights.sum()
+        weights += class_weights.squeeze()
+    weights /= weights.sum()
+    return weights
 
 
 def _take_edges(data, idx):
@@ -186,3 +194,108 @@ class NAGRestrictSize:
             idx = torch.multinomial(weights, num_edges, replacement=False)
             _take_edges(nag[i_level], idx)
         return nag
+
+
+class _BaseSampleSubgraphs:
+    """Pick `k` seed nodes of `i_level` (uniformly, or favouring large segments / rare classes;
+    with `use_batch` spread over the items of a batch), grow a node set around them
+    (`_sample_subgraphs_from_seeds`) and `NAG.select` it — one NAG holding all the sets, or
+    with `disjoint` a NAGBatch of one NAG per seed (reference sampling.py:810-1000)."""
+
+    def __init__(self, i_level=1, k=1, by_size=False, by_class=False, use_batch=True,
+                 disjoint=True):
+        self.i_level, self.k, self.by_size, self.by_class = i_level, k, by_size, by_class
+        self.use_batch, self.disjoint = use_batch, disjoint
+
+    def seeds(self, nag, i_level):
+        """The seed draw (sampling.py:884-953), torch.multinomial like the reference."""
+        k = self.k if self.k < nag[i_level].num_nodes else 1
+        weights = _node_weights(nag, i_level, self.by_size, self.by_class)
+        batch = nag[i_level].batch
+        if batch is None or not self.use_batch:
+            return torch.multinomial(weights, k, replacement=False)
+        idx_list = []
+        batch_indices = batch.unique()
+        num_batch = batch_indices.numel()
+        batch_indices = batch_indices[torch.randperm(num_batch)]
+        num_sampled = 0
+        k_batch = max(k // num_batch, 1)
+        for i_step, i_batch in enumerate(batch_indices):
+            if i_step >= num_batch - 1:
+                k_batch = k - num_sampled
+            mask = torch.where(i_batch == batch)[0]
+            idx_ = torch.multinomial(weights[mask], k_batch, replacement=False)
+            idx_list.append(mask[idx_])
+            num_sampled += k_batch
+            if num_sampled >= k:
+                break
+        return torch.cat(idx_list)
+
+    def __call__(self, nag):
+        assert isinstance(nag, NAG)
+        if self.i_level is None or self.k <= 0:
+            return nag
+        if self.i_level == -1:
+            i_level = nag.end_i_level
+        elif nag.start_i_level <= self.i_level < nag.absolute_num_levels:
+            i_level = self.i_level
+        else:
+            raise ValueError(
+                f"Invalid i_level: {self.i_level}. Must be in range [{nag.start_i_level}, "
+                f"{nag.absolute_num_levels - 1}],\nor -1 for the highest level available.")
+        idx_seed = self.seeds(nag, i_level)
+        if self.disjoint:
+            idx_subgraphs = [self._sample_subgraphs_from_seeds(nag, i_level, i.view(1))
+                             for i in idx_seed]
+            if all(idx is None for idx in idx_subgraphs):
+                idx_subgraphs = None
+        else:
+            idx_subgraphs = self._sample_subgraphs_from_seeds(nag, i_level, idx_seed)
+        if isinstance(idx_subgraphs, list):
+            return NAGBatch.from_nag_list([nag.select(i_level, idx) for idx in idx_subgraphs])
+        return nag.select(i_level, idx_subgraphs)
+
+    def _sample_subgraphs_from_seeds(self, nag, i_level, idx_seed):
+        raise NotImplementedError
+
+
+class SampleKHopSubgraphs(_BaseSampleSubgraphs):
+    """Seeds plus everything within `hops` edges of them in the graph of `i_level`, edges taken
+    in both directions (reference sampling.py:1003-1091; the hop expansion is csrc/select.cu).
+    `hops` None or negative: the NAG is returned as it is."""
+
+    def __init__(self, hops=2, i_level=1, k=1, by_size=False, by_class=False, use_batch=True,
+                 disjoint=False):
+        super().__init__(i_level=i_level, k=k, by_size=by_size, by_class=by_class,
+                         use_batch=use_batch, disjoint=disjoint)
+        self.hops = hops
+
+    def _sample_subgraphs_from_seeds(self, nag, i_level, idx_seed):
+        if self.hops is None or self.hops < 0:
+            return None
+        assert nag[i_level].has_edges, \
+            "Expected Data object to have edges for k-hop subgraph sampling"
+        from .. import ops
+        return ops.khop_nodes(nag[i_level].edge_index, idx_seed, self.hops,
+                              nag[i_level].num_nodes)
+
+
+class SampleRadiusSubgraphs(_BaseSampleSubgraphs):
+    """Seeds plus every node of `i_level` within `r` of one of them (a sphere, or with
+    `cylindrical` a cylinder around z; never across batch items; at most the `k_max` closest
+    per seed) — reference sampling.py:1094-1231.  The neighbour search is one pass over the
+    nodes (csrc/select.cu) instead of the reference's full sort of the distances.  `r` None or
+    <= 0: the NAG is returned as it is."""
+
+    def __init__(self, r=2, k_max=10000, i_level=1, k=1, by_size=False, by_class=False,
+                 use_batch=True, disjoint=False, cylindrical=False):
+        super().__init__(i_level=i_level, k=k, by_size=by_size, by_class=by_class,
+                         use_batch=use_batch, disjoint=disjoint)
+        self.r, self.k_max, self.cylindrical = r, k_max, cylindrical
+
+    def _sample_subgraphs_from_seeds(self, nag, i_level, idx_seed):
+        if self.r is None or self.r <= 0:
+            return None
+        from .. import ops
+        return ops.radius_nodes(nag[i_level].pos, idx_seed, self.r, k_max=self.k_max,
+                                batch=nag[i_level].batch, cylindrical=self.cylindrical)

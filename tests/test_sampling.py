@@ -10,7 +10,8 @@ import torch
 from oracle import sampling as OS
 from superpoint_transformer_b200 import ops
 from superpoint_transformer_b200.transforms import (SampleSubNodes, SampleSegments, SampleEdges,
-                                                   NAGRestrictSize, RestrictSize)
+                                                   NAGRestrictSize, RestrictSize,
+                                                   SampleRadiusSubgraphs, SampleKHopSubgraphs)
 
 from test_select import (assert_level_equal, levels_of, to_product, oracle_primitives,  # noqa
                          GOLDEN as SELECT_GOLDEN)
@@ -122,6 +123,61 @@ def test_host_logic_sample_edges_degrees_match_reference(gold, nags, oracle_prim
         SampleEdges(n_min=[1, 2], n_max=4)
 
 
+def subgraph_case(case, nags, device, seeds=None):
+    """Run the product transform of a golden subgraph case; `seeds`: use these seed nodes
+    instead of drawing (GPU runs reuse the CPU draw: torch's CUDA generator is another stream)."""
+    spec = nags[case['nag']]
+    nag = to_product(spec['levels'], spec['start'], device)
+    if case['batches'] is not None:
+        for i, b in enumerate(case['batches']):
+            nag[i].batch = b.to(device)
+    cls = SampleKHopSubgraphs if case['kind'] == 'khop' else SampleRadiusSubgraphs
+    t = cls(disjoint=False, **case['kw'])
+    drawn = []
+    draw = t.seeds
+    t.seeds = (lambda n, i: (drawn.append(draw(n, i)) or drawn[-1])) if seeds is None \
+        else (lambda n, i: seeds.to(device))
+    torch.manual_seed(case['seed'])
+    res = t(nag)
+    return res, (drawn[0] if drawn else seeds)
+
+
+def check_subgraph(case, res):
+    want = case['out']
+    got = levels_of(res)
+    if case['batches'] is not None:
+        assert all('batch' in a for a in got)
+    for j, (a, b) in enumerate(zip(got, want)):
+        a = {k: v for k, v in a.items() if k in b}
+        assert_level_equal(a, b, f"{case['nag']} {case['kind']} {case['kw']} level {j}",
+                           canonical_sub=True)
+
+
+def test_host_logic_subgraph_sampling_matches_reference(gold, nags, oracle_primitives):
+    assert len(gold['subgraphs']) >= 10
+    for case in gold['subgraphs']:
+        res, _ = subgraph_case(case, nags, 'cpu')
+        check_subgraph(case, res)
+    # disjoint: a NAGBatch with one item per seed, each equal to the single-seed selection
+    case = gold['subgraphs'][1]
+    spec = nags[case['nag']]
+    nag = to_product(spec['levels'], spec['start'])
+    torch.manual_seed(3)
+    t = SampleRadiusSubgraphs(r=0.3, i_level=1, k=3, disjoint=True)
+    res = t(nag)
+    assert res[1].batch is not None and int(res[1].batch.max()) == 2
+    torch.manual_seed(3)
+    seeds = t.seeds(nag, 1)
+    sizes = [nag.select(1, OS.radius_nodes(nag[1].pos, s.view(1), 0.3))[1].num_nodes
+             for s in seeds]
+    assert torch.bincount(res[1].batch).tolist() == sizes
+    # r <= 0 / hops < 0: untouched
+    assert levels_of(SampleRadiusSubgraphs(r=0, disjoint=False)(nag))[1].keys() == \
+        levels_of(nag)[1].keys()
+    with pytest.raises(ValueError):
+        SampleKHopSubgraphs(i_level=7)(nag)
+
+
 def test_segment_weights_match_oracle(nags, oracle_primitives):
     spec = nags['full4']
     nag = to_product(spec['levels'], spec['start'])
@@ -175,6 +231,55 @@ def test_gpu_sample_edges_and_restrict_size(gold, nags):
     for i in (0, 1, 2):
         assert int(res[i].super_index.max()) + 1 == res[i + 1].num_nodes
         assert torch.equal(res[i + 1].sub.to_super_index(), res[i].super_index)
+
+
+@pytest.mark.gpu
+def test_gpu_subgraph_sampling_matches_reference_vectors(gold, nags, monkeypatch):
+    """Seeds drawn on the CPU (same torch seed as the reference run), neighbour search and
+    selection on the device: the reference's output, bit for bit."""
+    for case in gold['subgraphs']:
+        with monkeypatch.context() as m:          # CPU draw through the oracle stand-ins
+            for name, fn in (('radius_nodes', OS.radius_nodes), ('khop_nodes', OS.khop_nodes)):
+                m.setattr(ops, name, fn)
+            spec = nags[case['nag']]
+            nag = to_product(spec['levels'], spec['start'])
+            if case['batches'] is not None:
+                for i, b in enumerate(case['batches']):
+                    nag[i].batch = b
+            cls = SampleKHopSubgraphs if case['kind'] == 'khop' else SampleRadiusSubgraphs
+            torch.manual_seed(case['seed'])
+            i_level = case['kw']['i_level']
+            seeds = cls(disjoint=False, **case['kw']).seeds(nag, i_level)
+        res, _ = subgraph_case(case, nags, 'cuda', seeds=seeds)
+        check_subgraph(case, res)
+
+
+@pytest.mark.gpu
+def test_gpu_radius_and_khop_search_vs_oracle():
+    g = torch.Generator().manual_seed(21)
+    n = 50_000
+    pos = torch.rand(n, 3, generator=g) * torch.tensor([20.0, 20.0, 4.0])
+    batch = (pos[:, 0] > 10).long() + 2 * (pos[:, 1] > 10).long()
+    seeds = torch.randperm(n, generator=g)[:5]
+    for r, cyl, b, k_max in ((1.5, False, None, 10000), (2.0, True, None, 10000),
+                             (2.5, False, batch, 10000), (3.0, True, batch, 10000),
+                             (3.0, False, None, 150), (0.01, False, None, 10000)):
+        want = OS.radius_nodes(pos, seeds, r, k_max=k_max, batch=b, cylindrical=cyl)
+        got = ops.radius_nodes(pos.cuda(), seeds.cuda(), r, k_max=k_max,
+                               batch=None if b is None else b.cuda(), cylindrical=cyl)
+        if not torch.equal(got.cpu(), want):
+            # only nodes sitting on the sphere to within fp32 rounding may differ (the device
+            # evaluates sqrt(dx^2+dy^2+dz^2) unfused; torch's CPU norm may round differently)
+            a, w = set(got.cpu().tolist()), set(want.tolist())
+            m = torch.tensor([1.0, 1.0, 0.0 if cyl else 1.0])
+            for i in a ^ w:
+                d = ((pos[i] - pos[seeds]) * m).double().norm(dim=1)
+                assert ((d - r).abs() < 1e-5 * r).any(), (r, cyl, k_max, i)
+    ei = torch.randint(0, n, (2, 4 * n), generator=g)
+    for hops in (0, 1, 2, 3):
+        want = OS.khop_nodes(ei, seeds, hops, n)
+        got = ops.khop_nodes(ei.cuda(), seeds.cuda(), hops, n)
+        assert torch.equal(got.cpu(), want), hops
 
 
 @pytest.mark.gpu

@@ -176,6 +176,9 @@ def oracle_primitives(monkeypatch):
         return (samples, ptr) if return_pointers else samples
 
     monkeypatch.setattr(ops, 'sparse_sample', sparse_sample)
+    from oracle import sampling as OS
+    monkeypatch.setattr(ops, 'radius_nodes', OS.radius_nodes)
+    monkeypatch.setattr(ops, 'khop_nodes', OS.khop_nodes)
     monkeypatch.setattr(ops, 'relabel_consecutive', relabel_consecutive)
     monkeypatch.setattr(ops, 'select_edges', select_edges)
     monkeypatch.setattr(ops, 'csr_select', csr_select)
