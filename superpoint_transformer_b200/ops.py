@@ -907,13 +907,19 @@ def radius_nodes(pos, seeds, r, k_max=10000, batch=None, cylindrical=False):
     if batch is not None:                       # neighbors.py:272-275, same tensor ops
         z = pos[:, 2] * (0 if cylindrical else 1)
         z_offset = (z.max() - z.min() + r + 1).float().contiguous()
-    flags = torch.empty(N + 1, dtype=torch.int32, device=dev)
-    within = torch.empty(max(S, 1), dtype=torch.int32, device=dev)
+    flags, within = None, []
     with torch.cuda.device(dev):
-        _lib.check(lib.spt_radius_flags(_p(pos), N, _p(batch), _p(seeds), S, float(r),
-                                        1 if cylindrical else 0, _p(z_offset), _p(flags),
-                                        _p(within), _stream()), "spt_radius_flags")
-    _count()
+        for s0 in range(0, max(S, 1), 64):          # the kernel keeps <= 64 seeds in shared memory
+            chunk = seeds[s0:s0 + 64]
+            f = torch.empty(N + 1, dtype=torch.int32, device=dev)
+            w = torch.empty(max(chunk.numel(), 1), dtype=torch.int32, device=dev)
+            _lib.check(lib.spt_radius_flags(_p(pos), N, _p(batch), _p(chunk), chunk.numel(),
+                                            float(r), 1 if cylindrical else 0, _p(z_offset),
+                                            _p(f), _p(w), _stream()), "spt_radius_flags")
+            _count()
+            flags = f if flags is None else flags | f
+            within.append(w)
+    within = torch.cat(within)
     idx, per_seed = _flags_to_index(flags, N, extra=within)
     if max(per_seed[:S], default=0) > k_max:
         # more than k_max nodes inside the radius of a seed: the reference keeps the k_max
