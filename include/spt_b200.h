@@ -43,6 +43,7 @@ extern "C" {
 #define SPT_E_UNSUPPORTED -2  /* shape outside what the kernels implement     */
 #define SPT_E_WORKSPACE -3    /* workspace too small                          */
 #define SPT_E_TOO_LARGE -4    /* element count does not fit int32 internals   */
+#define SPT_E_INDEX -5        /* an index tensor holds out-of-range or repeated entries */
 
 /* reduce ops for segment pooling (src/nn/pool.py:24-82) */
 #define SPT_REDUCE_SUM 0
@@ -212,6 +213,45 @@ int spt_gather_rows_bytes(const void* src, int64_t row_bytes, const int64_t* idx
  * pointers / byte counts: the table is passed in the kernel parameters. */
 int spt_gather_rows_multi(const void* const* srcs, void* const* outs, const int64_t* row_bytes,
                           int num_tensors, const int64_t* idx, int64_t K, void* stream);
+
+/* One level of Data.select (src/data/data.py:286-470) in ONE call: every primitive above, with a
+ * single host read of the data-dependent sizes in the middle, outputs carved from a
+ * caller-provided device arena (256-byte aligned pieces).  The reference issues ~25 tensor ops
+ * with three host round trips per level; called piecewise from Python the primitives above cost
+ * ~40 allocations and ~4 reads per level, which is what this entry removes.
+ *   sub_pointers == NULL: the level has no `sub` (or the caller replaces it: NAG.select on the
+ *   levels above the selected one); super_index == NULL likewise.  update_sub / update_super as
+ *   in the reference.  node_src / edge_src (+ *_row_bytes): HOST arrays describing the node-level
+ *   and edge-level attribute tensors to gather (`item[idx]`, `item[idx_edge]`).
+ * layout (HOST, SPT_SEL_ROWS + num_node_rows + num_edge_rows int64): element counts and byte
+ * offsets into the arena of the outputs (-1 = absent); int64 outputs unless noted:
+ *   [NUM_EDGES] E'   [EDGE_INDEX] [2, E']   [IDX_EDGE] [E']
+ *   [NUM_ITEMS] M    [SUB_POINTERS] [K+1]   [SUB_POINTS] [M]   [IDX_SUB] [M]   [SUB_SUPER] [M]
+ *                    [SUB_COUNTS] 2 x int64 {distinct point ids, out-of-range ids} (device; for
+ *                    an optional check: a valid Cluster gives {M, 0})
+ *   [NUM_PARENTS] U  [SUPER_INDEX] [K]      [IDX_SUPER] [U]    [SUPER_SUB_POINTERS] [U+1]
+ *                    [SUPER_SUB_POINTS] [K]
+ *   [ROWS + i] the i-th node-level output (K rows), then the edge-level ones (E' rows).
+ * Returns SPT_E_INDEX when idx (or super_index) holds invalid or repeated entries. */
+typedef struct spt_select_level {
+  int64_t num_nodes;
+  const int64_t* idx;          int64_t num_selected;
+  const int64_t* edge_index;   int64_t num_edges;
+  const int64_t* sub_pointers; const int64_t* sub_points;
+  int64_t sub_items;           int64_t num_sub;
+  int update_sub;
+  const int64_t* super_index;  int64_t num_super;
+  int update_super;
+  int num_node_rows;  const void* const* node_src;  const int64_t* node_row_bytes;
+  int num_edge_rows;  const void* const* edge_src;  const int64_t* edge_row_bytes;
+} spt_select_level;
+enum { SPT_SEL_NUM_EDGES = 0, SPT_SEL_NUM_ITEMS, SPT_SEL_NUM_PARENTS, SPT_SEL_EDGE_INDEX,
+       SPT_SEL_IDX_EDGE, SPT_SEL_SUB_POINTERS, SPT_SEL_SUB_POINTS, SPT_SEL_IDX_SUB,
+       SPT_SEL_SUB_SUPER, SPT_SEL_SUB_COUNTS, SPT_SEL_SUPER_INDEX, SPT_SEL_IDX_SUPER,
+       SPT_SEL_SUPER_SUB_POINTERS, SPT_SEL_SUPER_SUB_POINTS, SPT_SEL_ROWS };
+size_t spt_data_select_arena_bytes(const spt_select_level* level);
+int spt_data_select(const spt_select_level* level, void* arena, size_t arena_bytes,
+                    int64_t* layout, void* stream);
 
 /* Subgraph sampling (src/transforms/sampling.py:1003-1231).  Node sets are int32 flag vectors
  * of N+1 entries (flags[N] = 0, the scan's sentinel).

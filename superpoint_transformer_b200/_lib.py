@@ -122,6 +122,8 @@ SIGNATURES = {
     "spt_where_workspace_bytes": (c_size, [c_i64]),
     "spt_where_count": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
     "spt_where_write": (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
+    "spt_data_select_arena_bytes": (c_size, [c_ptr]),
+    "spt_data_select": (c_int, [c_ptr, c_ptr, c_size, c_ptr, c_ptr]),
     "spt_gather_rows_multi": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_i64, c_ptr]),
     "spt_vrpe_blockdiag": (c_int, [c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr]),
     "spt_vrpe_epilogue": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_ptr,
@@ -190,7 +192,29 @@ def load():
     return _LIB
 
 
+E_INDEX = -5   # SPT_E_INDEX
+
+
+class SelectLevel(ctypes.Structure):
+    """spt_select_level (include/spt_b200.h)"""
+    _fields_ = [("num_nodes", c_i64), ("idx", c_ptr), ("num_selected", c_i64),
+                ("edge_index", c_ptr), ("num_edges", c_i64),
+                ("sub_pointers", c_ptr), ("sub_points", c_ptr),
+                ("sub_items", c_i64), ("num_sub", c_i64), ("update_sub", c_int),
+                ("super_index", c_ptr), ("num_super", c_i64), ("update_super", c_int),
+                ("num_node_rows", c_int), ("node_src", c_ptr), ("node_row_bytes", c_ptr),
+                ("num_edge_rows", c_int), ("edge_src", c_ptr), ("edge_row_bytes", c_ptr)]
+
+
+SEL_NUM_EDGES, SEL_NUM_ITEMS, SEL_NUM_PARENTS, SEL_EDGE_INDEX, SEL_IDX_EDGE, SEL_SUB_POINTERS, \
+    SEL_SUB_POINTS, SEL_IDX_SUB, SEL_SUB_SUPER, SEL_SUB_COUNTS, SEL_SUPER_INDEX, SEL_IDX_SUPER, \
+    SEL_SUPER_SUB_POINTERS, SEL_SUPER_SUB_POINTS, SEL_ROWS = range(15)
+
+
 def check(rc, what):
+    if rc == E_INDEX:
+        msg = load().spt_last_error()
+        raise IndexError(msg.decode() if msg else what)
     if rc != 0:
         msg = load().spt_last_error()
         msg = msg.decode() if msg else ""

@@ -17,6 +17,7 @@
 // — who has to allocate — reads exactly one small `counts` vector per phase-1 call.
 #include "common.cuh"
 #include "scan.cuh"
+#include <vector>
 
 namespace spt {
 
@@ -261,6 +262,11 @@ static __global__ void k_where_write(const int32_t* __restrict__ slot, int64_t n
   }
 }
 
+static __global__ void k_widen_i32(const int32_t* __restrict__ in, int64_t n,
+                                   int64_t* __restrict__ out) {
+  SPT_GRID_STRIDE(i, n) out[i] = in[i];
+}
+
 // several tensors, one launch: the table travels in the kernel parameters (no device copy)
 constexpr int kMultiMax = 16;
 struct GatherMulti {
@@ -270,6 +276,7 @@ struct GatherMulti {
   int64_t unit_prefix[kMultiMax + 1]; // exclusive scan of K * row_units
   int32_t unit_log2[kMultiMax];       // log2 of the unit size in bytes: 0, 2, 3 or 4
   int32_t n;
+  int64_t src_rows;                   // rows of idx outside [0, src_rows) are skipped
 };
 
 static __global__ void k_gather_rows_multi(const GatherMulti tab,
@@ -281,7 +288,9 @@ static __global__ void k_gather_rows_multi(const GatherMulti tab,
     const int64_t local = t - tab.unit_prefix[s];
     const int64_t ru = tab.row_units[s];
     const int64_t r = local / ru, u = local - r * ru;
-    const int64_t from = idx[r] * ru + u;
+    const int64_t row = idx[r];
+    if (row < 0 || row >= tab.src_rows) continue;
+    const int64_t from = row * ru + u;
     switch (tab.unit_log2[s]) {
       case 4: ((uint4*)tab.dst[s])[local] = ((const uint4*)tab.src[s])[from]; break;
       case 3: ((uint2*)tab.dst[s])[local] = ((const uint2*)tab.src[s])[from]; break;
@@ -465,17 +474,18 @@ int spt_gather_rows_bytes(const void* src, int64_t row_bytes, const int64_t* idx
   return check_launch("gather_rows_bytes");
 }
 
-int spt_gather_rows_multi(const void* const* srcs, void* const* outs, const int64_t* row_bytes,
-                          int num_tensors, const int64_t* idx, int64_t K, void* stream_) {
-  cudaStream_t st = (cudaStream_t)stream_;
+static int gather_rows_multi(const void* const* srcs, void* const* outs,
+                             const int64_t* row_bytes, int num_tensors, const int64_t* idx,
+                             int64_t K, int64_t src_rows, cudaStream_t st) {
   SPT_REQUIRE(num_tensors >= 0 && K >= 0, SPT_E_INVALID, "gather_rows_multi: negative size");
   if (num_tensors == 0 || K == 0) return SPT_OK;
   SPT_REQUIRE(srcs && outs && row_bytes && idx, SPT_E_INVALID, "gather_rows_multi: null pointer");
-  for (int base = 0; base < num_tensors; base += kMultiMax) {
+  for (int i = 0; i < num_tensors;) {
     GatherMulti tab;
     tab.n = 0;
+    tab.src_rows = src_rows;
     tab.unit_prefix[0] = 0;
-    for (int i = base; i < num_tensors && tab.n < kMultiMax; ++i) {
+    for (; i < num_tensors && tab.n < kMultiMax; ++i) {
       const int64_t rb = row_bytes[i];
       SPT_REQUIRE(rb >= 0, SPT_E_INVALID, "gather_rows_multi: negative row size");
       if (rb == 0) continue;
@@ -493,6 +503,12 @@ int spt_gather_rows_multi(const void* const* srcs, void* const* outs, const int6
     k_gather_rows_multi<<<sel_grid(tab.unit_prefix[tab.n]), kSelThreads, 0, st>>>(tab, idx);
   }
   return check_launch("gather_rows_multi");
+}
+
+int spt_gather_rows_multi(const void* const* srcs, void* const* outs, const int64_t* row_bytes,
+                          int num_tensors, const int64_t* idx, int64_t K, void* stream_) {
+  return gather_rows_multi(srcs, outs, row_bytes, num_tensors, idx, K, INT64_MAX,
+                           (cudaStream_t)stream_);
 }
 
 int spt_radius_flags(const float* pos, int64_t N, const int64_t* batch, const int64_t* seeds,
@@ -552,6 +568,253 @@ int spt_where_write(const int32_t* slot, int64_t n, int64_t* out, void* stream_)
   SPT_REQUIRE(slot && out, SPT_E_INVALID, "where_write: null pointer");
   k_where_write<<<sel_grid(n), kSelThreads, 0, (cudaStream_t)stream_>>>(slot, n, out);
   return check_launch("where_write");
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- one level in one call
+namespace {
+
+struct Arena {
+  char* base;      // nullptr: sizing pass
+  size_t off;
+  int64_t take(size_t bytes) {
+    off = align_up(off, 256);
+    const int64_t o = (int64_t)off;
+    off += bytes;
+    return o;
+  }
+  template <typename T>
+  T* at(int64_t o) const { return base ? (T*)(base + o) : nullptr; }
+};
+
+int64_t* pinned_counts() {
+  static thread_local int64_t* p = nullptr;
+  static thread_local int64_t fallback[8];
+  if (!p && cudaHostAlloc((void**)&p, 64, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    p = fallback;
+  }
+  return p;
+}
+
+#define SPT_TRY(call)            \
+  do {                           \
+    const int rc_ = (call);      \
+    if (rc_ != SPT_OK) return rc_; \
+  } while (0)
+
+// `dry`: no launches, worst-case counts -> A.off ends at the arena size the real pass can need
+int select_level(const spt_select_level* a, Arena& A, int64_t* layout, cudaStream_t st,
+                 bool dry) {
+  const int64_t N = a->num_nodes, K = a->num_selected, E = a->edge_index ? a->num_edges : 0;
+  const bool has_sub = a->sub_pointers != nullptr, has_super = a->super_index != nullptr;
+  const bool upd_sub = has_sub && a->update_sub, upd_super = has_super && a->update_super;
+  const int64_t cap_u = K < a->num_super ? K : a->num_super;
+  const int n_rows = a->num_node_rows + a->num_edge_rows;
+  if (layout)
+    for (int i = 0; i < SPT_SEL_ROWS + n_rows; ++i) layout[i] = -1;
+
+  // ---- phase 1: everything whose output size is known up front
+  const int64_t o_counts = A.take(64);
+  const int64_t o_reindex = A.take((size_t)N * 8);
+  int64_t o_slot = -1, o_ws_e = -1;
+  const size_t ws_e = E > 0 ? spt_select_edges_workspace_bytes(E) : 0;
+  if (E > 0) {
+    o_slot = A.take((size_t)(E + 1) * 4);
+    o_ws_e = A.take(ws_e);
+  }
+  int64_t o_newptr = -1, o_ws_c = -1;
+  const size_t ws_c = has_sub ? spt_csr_select_workspace_bytes(K) : 0;
+  if (has_sub) {
+    o_newptr = A.take((size_t)(K + 1) * 8);
+    o_ws_c = A.take(ws_c);
+  }
+  int64_t o_si = -1, o_newsi = -1, o_uniq = -1, o_ws_r = -1;
+  const size_t ws_r = upd_super ? spt_relabel_consecutive_workspace_bytes(a->num_super) : 0;
+  if (has_super) {
+    o_si = A.take((size_t)K * 8);
+    if (upd_super) {
+      o_newsi = A.take((size_t)K * 8);
+      o_uniq = A.take((size_t)cap_u * 8);
+      o_ws_r = A.take(ws_r);
+    }
+  }
+  std::vector<void*> outs((size_t)(n_rows > 0 ? n_rows : 1), nullptr);
+  for (int i = 0; i < a->num_node_rows; ++i) {
+    const int64_t o = A.take((size_t)K * (size_t)a->node_row_bytes[i]);
+    outs[i] = A.at<char>(o);
+    if (layout) layout[SPT_SEL_ROWS + i] = o;
+  }
+  int64_t kept = E, items = has_sub ? a->sub_items : 0, parents = cap_u;
+  if (!dry) {
+    int64_t* counts = A.at<int64_t>(o_counts);
+    SPT_TRY(spt_select_edges_mark(a->edge_index, E, a->idx, K, N, A.at<int64_t>(o_reindex),
+                                  E > 0 ? A.at<int32_t>(o_slot) : nullptr, counts,
+                                  E > 0 ? A.at<char>(o_ws_e) : nullptr, ws_e, st));
+    if (has_sub)
+      SPT_TRY(spt_csr_select_pointers(a->sub_pointers, N, a->sub_items, a->idx, K,
+                                      A.at<int64_t>(o_newptr), counts + 2, A.at<char>(o_ws_c),
+                                      ws_c, st));
+    else
+      cudaMemsetAsync(counts + 2, 0, 16, st);
+    // gathers skip rows an invalid idx entry points at (reported right after the read below)
+    if (has_super) {
+      const void* src1[1] = {a->super_index};
+      void* out1[1] = {A.at<int64_t>(o_si)};
+      const int64_t rb1[1] = {8};
+      SPT_TRY(gather_rows_multi(src1, out1, rb1, 1, a->idx, K, N, st));
+    }
+    if (upd_super)
+      SPT_TRY(spt_relabel_consecutive_i64(A.at<int64_t>(o_si), K, a->num_super,
+                                          A.at<int64_t>(o_newsi), A.at<int64_t>(o_uniq),
+                                          counts + 4, nullptr, nullptr, A.at<char>(o_ws_r), ws_r,
+                                          st));
+    else
+      cudaMemsetAsync(counts + 4, 0, 16, st);
+    if (a->num_node_rows > 0)
+      SPT_TRY(gather_rows_multi(a->node_src, outs.data(), a->node_row_bytes, a->num_node_rows,
+                                a->idx, K, N, st));
+    // the one host read of the level
+    int64_t* h = pinned_counts();
+    cudaError_t ce = cudaMemcpyAsync(h, counts, 48, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    if (ce != cudaSuccess) {
+      set_error("data_select: %s", cudaGetErrorString(ce));
+      return (int)ce;
+    }
+    SPT_REQUIRE(h[1] == 0, SPT_E_INDEX,
+                "select: %lld index entries are out of range or repeated", (long long)h[1]);
+    SPT_REQUIRE(h[3] == 0, SPT_E_INDEX, "select: %lld cluster ids out of range",
+                (long long)h[3]);
+    SPT_REQUIRE(h[5] == 0, SPT_E_INDEX, "select: %lld super_index entries out of range",
+                (long long)h[5]);
+    kept = E > 0 ? h[0] : 0;
+    items = has_sub ? h[2] : 0;
+    parents = upd_super ? h[4] : 0;
+    SPT_REQUIRE(items <= a->sub_items, SPT_E_INDEX, "select: selected clusters overlap");
+  }
+  if (layout) {
+    layout[SPT_SEL_NUM_EDGES] = E > 0 ? kept : 0;
+    layout[SPT_SEL_NUM_ITEMS] = items;
+    layout[SPT_SEL_NUM_PARENTS] = upd_super ? parents : 0;
+  }
+
+  // ---- phase 2: sized by the counts
+  if (E > 0) {
+    const int64_t o_ei = A.take((size_t)kept * 16), o_ie = A.take((size_t)kept * 8);
+    for (int i = 0; i < a->num_edge_rows; ++i) {
+      const int64_t o = A.take((size_t)kept * (size_t)a->edge_row_bytes[i]);
+      outs[a->num_node_rows + i] = A.at<char>(o);
+      if (layout) layout[SPT_SEL_ROWS + a->num_node_rows + i] = o;
+    }
+    if (layout) {
+      layout[SPT_SEL_EDGE_INDEX] = o_ei;
+      layout[SPT_SEL_IDX_EDGE] = o_ie;
+    }
+    if (!dry) {
+      SPT_TRY(spt_select_edges_write(a->edge_index, E, A.at<int64_t>(o_reindex),
+                                     A.at<int32_t>(o_slot), kept, A.at<int64_t>(o_ei),
+                                     A.at<int64_t>(o_ie), st));
+      if (a->num_edge_rows > 0 && kept > 0)
+        SPT_TRY(spt_gather_rows_multi(a->edge_src, outs.data() + a->num_node_rows,
+                                      a->edge_row_bytes, a->num_edge_rows, A.at<int64_t>(o_ie),
+                                      kept, st));
+    }
+  }
+  if (has_sub) {
+    const int64_t o_pts = A.take((size_t)items * 8);
+    if (layout) layout[SPT_SEL_SUB_POINTERS] = o_newptr;
+    if (!upd_sub) {
+      if (layout) layout[SPT_SEL_SUB_POINTS] = o_pts;
+      if (!dry)
+        SPT_TRY(spt_csr_select_values_i64(a->sub_pointers, a->idx, K, A.at<int64_t>(o_newptr),
+                                          a->sub_points, items, A.at<int64_t>(o_pts), nullptr,
+                                          st));
+    } else {
+      const size_t ws2 = spt_relabel_consecutive_workspace_bytes(a->num_sub);
+      const int64_t o_grp = A.take((size_t)items * 8), o_new = A.take((size_t)items * 8);
+      const int64_t o_isub = A.take((size_t)items * 8), o_ssup = A.take((size_t)items * 8);
+      const int64_t o_c2 = A.take(16), o_ws2 = A.take(ws2);
+      if (layout) {
+        layout[SPT_SEL_SUB_POINTS] = o_new;
+        layout[SPT_SEL_IDX_SUB] = o_isub;
+        layout[SPT_SEL_SUB_SUPER] = o_ssup;
+        layout[SPT_SEL_SUB_COUNTS] = o_c2;
+      }
+      if (!dry) {
+        SPT_TRY(spt_csr_select_values_i64(a->sub_pointers, a->idx, K, A.at<int64_t>(o_newptr),
+                                          a->sub_points, items, A.at<int64_t>(o_pts),
+                                          A.at<int64_t>(o_grp), st));
+        SPT_TRY(spt_relabel_consecutive_i64(A.at<int64_t>(o_pts), items, a->num_sub,
+                                            A.at<int64_t>(o_new), A.at<int64_t>(o_isub),
+                                            A.at<int64_t>(o_c2), A.at<int64_t>(o_grp),
+                                            A.at<int64_t>(o_ssup), A.at<char>(o_ws2), ws2, st));
+      }
+    }
+  }
+  if (has_super) {
+    if (layout) layout[SPT_SEL_SUPER_INDEX] = upd_super ? o_newsi : o_si;
+    if (upd_super) {
+      const size_t ws_g = spt_group_index_workspace_bytes(K, parents);
+      const int64_t o_p32 = A.take((size_t)(parents + 1) * 4), o_q32 = A.take((size_t)K * 4);
+      const int64_t o_ws_g = A.take(ws_g);
+      const int64_t o_sp = A.take((size_t)(parents + 1) * 8), o_sq = A.take((size_t)K * 8);
+      if (layout) {
+        layout[SPT_SEL_IDX_SUPER] = o_uniq;
+        layout[SPT_SEL_SUPER_SUB_POINTERS] = o_sp;
+        layout[SPT_SEL_SUPER_SUB_POINTS] = o_sq;
+      }
+      if (!dry) {
+        SPT_TRY(spt_group_index(A.at<int64_t>(o_newsi), nullptr, K, parents,
+                                A.at<int32_t>(o_p32), A.at<int32_t>(o_q32), nullptr,
+                                A.at<char>(o_ws_g), ws_g, st));
+        k_widen_i32<<<sel_grid(parents + 1), kSelThreads, 0, st>>>(
+            A.at<int32_t>(o_p32), parents + 1, A.at<int64_t>(o_sp));
+        if (K > 0)
+          k_widen_i32<<<sel_grid(K), kSelThreads, 0, st>>>(A.at<int32_t>(o_q32), K,
+                                                           A.at<int64_t>(o_sq));
+      }
+    }
+  }
+  return dry ? SPT_OK : check_launch("data_select");
+}
+
+int check_level(const spt_select_level* a) {
+  SPT_REQUIRE(a, SPT_E_INVALID, "data_select: null level");
+  SPT_REQUIRE(a->num_nodes >= 0 && a->num_selected >= 0 && a->num_edges >= 0 &&
+                  a->num_node_rows >= 0 && a->num_edge_rows >= 0,
+              SPT_E_INVALID, "data_select: negative size");
+  SPT_REQUIRE(a->num_selected == 0 || a->idx, SPT_E_INVALID, "data_select: null idx");
+  SPT_REQUIRE(!a->sub_pointers || (a->sub_points || a->sub_items == 0), SPT_E_INVALID,
+              "data_select: sub_points missing");
+  SPT_REQUIRE((a->num_node_rows == 0 || (a->node_src && a->node_row_bytes)) &&
+                  (a->num_edge_rows == 0 || (a->edge_src && a->edge_row_bytes)),
+              SPT_E_INVALID, "data_select: row tables missing");
+  return SPT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t spt_data_select_arena_bytes(const spt_select_level* level) {
+  if (check_level(level) != SPT_OK) return 0;
+  Arena A{nullptr, 0};
+  select_level(level, A, nullptr, nullptr, true);
+  return align_up(A.off, 256);
+}
+
+int spt_data_select(const spt_select_level* level, void* arena, size_t arena_bytes,
+                    int64_t* layout, void* stream_) {
+  SPT_TRY(check_level(level));
+  SPT_REQUIRE(arena && layout, SPT_E_INVALID, "data_select: null arena / layout");
+  SPT_REQUIRE(((uintptr_t)arena & 255) == 0, SPT_E_INVALID, "data_select: arena not 256-aligned");
+  const size_t need = spt_data_select_arena_bytes(level);
+  SPT_REQUIRE(arena_bytes >= need, SPT_E_WORKSPACE, "data_select: arena %zu < %zu", arena_bytes,
+              need);
+  Arena A{(char*)arena, 0};
+  return select_level(level, A, layout, (cudaStream_t)stream_, false);
 }
 
 }  // extern "C"

@@ -229,59 +229,94 @@ class Data:
             return self.clone(), (None, None), (None, None)
         from .. import ops
         num_sel = idx.shape[0]
-        data = Data()
-
-        # edges: re-index, drop those that lose an end point (data.py:356-371); the same call
-        # validates idx (range, duplicates)
-        idx_edge = None
-        if self.has_edges:
-            data.edge_index, idx_edge = ops.select_edges(self.edge_index, idx, num_nodes)
-        else:
-            ops.select_edges(None, idx, num_nodes)
-
-        out_sub = (None, None)
-        if self.is_super and not _skip_sub:
-            if not isinstance(self.sub, CSRData):
-                raise NotImplementedError("Data.select needs `sub` as a Cluster")
-            data.sub, out_sub = self.sub.select(idx, update_sub=update_sub)
-
-        out_super = (None, None)
-        if self.is_sub and not _skip_super:
-            data.super_index = ops.take_rows(self.super_index, idx)
-        if self.is_sub and update_super:
+        has_edges, num_edges = self.has_edges, self.num_edges
+        use_sub = self.is_super and not _skip_sub
+        if use_sub and not isinstance(self.sub, CSRData):
+            raise NotImplementedError("Data.select needs `sub` as a Cluster")
+        gather_super = self.is_sub and not _skip_super
+        relabel_super = self.is_sub and update_super
+        if relabel_super and not gather_super:
+            raise ValueError("update_super needs the level's own super_index")
+        num_super = None
+        if relabel_super:
             num_super = self.num_super if _num_super is None else int(_num_super)
-            data.super_index, idx_super = ops.relabel_consecutive(data.super_index, num_super)
-            super_sub = Cluster.from_super_index(data.super_index, idx_super.shape[0])
-            out_super = (idx_super, super_sub)
 
+        # which attribute follows the nodes, which the edges, which is copied (data.py:420-463)
         skip_keys = ('edge_index', 'sub', 'super_index', 'neighbor_index',
                      'neighbor_distance')
         edge_keys = ['edge_attr'] + self.edge_keys
         v_edge_keys = self.v_edge_keys
-        num_edges = self.num_edges
-        node_items, edge_items = [], []      # gathered in one launch each, below
+        order, node_items, edge_items, csr_items, copied = [], [], [], [], []
         for key, item in list(self._store.items()):
             if key in skip_keys or key.startswith('_'):
                 continue
-            if isinstance(item, CSRData):
-                data[key] = item.select(idx)
-                continue
+            order.append(key)
             is_tensor = torch.is_tensor(item)
             is_node_size = is_tensor and item.dim() > 0 and item.shape[0] == num_nodes
             is_edge_size = is_tensor and item.dim() > 0 and item.shape[0] == num_edges
-            if is_node_size and key in v_edge_keys:
+            if isinstance(item, CSRData):
+                csr_items.append(key)
+            elif is_node_size and key in v_edge_keys:
                 node_items.append(key)
-            elif self.has_edges and is_edge_size and key in edge_keys:
+            elif has_edges and is_edge_size and key in edge_keys:
                 edge_items.append(key)
             elif is_node_size:
                 node_items.append(key)
             else:
-                data[key] = item.clone() if is_tensor else copy.deepcopy(item)
-                continue
-            data[key] = item      # placeholder: keeps the reference's attribute order
-        for keys, index in ((node_items, idx), (edge_items, idx_edge)):
-            for key, out in zip(keys, ops.take_rows_multi([self._store[k] for k in keys], index)):
-                data[key] = out
+                copied.append(key)
+
+        data = Data()
+        out_sub, out_super = (None, None), (None, None)
+        values = {}
+        if idx.is_cuda and ops.SELECT_FUSED:
+            # one native call for the level (csrc/select.cu: spt_data_select)
+            res = ops.data_select(
+                num_nodes, idx, edge_index=self.edge_index if has_edges else None,
+                sub=(self.sub.pointers, self.sub.points) if use_sub else None,
+                update_sub=update_sub,
+                super_index=self.super_index if gather_super else None,
+                num_super=num_super if relabel_super else 0, update_super=relabel_super,
+                node_rows=[self._store[k] for k in node_items],
+                edge_rows=[self._store[k] for k in edge_items])
+            if has_edges:
+                data.edge_index = res['edge_index']
+            if use_sub:
+                data.sub = Cluster(*res['sub'])
+                if update_sub:
+                    out_sub = (res['idx_sub'], res['sub_super'])
+            if gather_super:
+                data.super_index = res['super_index']
+                if relabel_super:
+                    out_super = (res['idx_super'], Cluster(*res['super_sub']))
+            values.update(zip(node_items, res['node_rows']))
+            values.update(zip(edge_items, res['edge_rows']))
+        else:
+            # the same steps through the primitives, one by one
+            idx_edge = None
+            if has_edges:   # re-index, drop edges that lose an end point; validates idx too
+                data.edge_index, idx_edge = ops.select_edges(self.edge_index, idx, num_nodes)
+            else:
+                ops.select_edges(None, idx, num_nodes)
+            if use_sub:
+                data.sub, out_sub = self.sub.select(idx, update_sub=update_sub)
+            if gather_super:
+                data.super_index = ops.take_rows(self.super_index, idx)
+            if relabel_super:
+                data.super_index, idx_super = ops.relabel_consecutive(data.super_index,
+                                                                      num_super)
+                super_sub = Cluster.from_super_index(data.super_index, idx_super.shape[0])
+                out_super = (idx_super, super_sub)
+            for keys, index in ((node_items, idx), (edge_items, idx_edge)):
+                values.update(zip(keys, ops.take_rows_multi([self._store[k] for k in keys],
+                                                            index)))
+        for key in order:                      # the reference's attribute order
+            item = self._store[key]
+            if key in values:
+                data[key] = values[key]
+            elif key in csr_items:
+                data[key] = item.select(idx)
+            else:
+                data[key] = item.clone() if torch.is_tensor(item) else copy.deepcopy(item)
 
         if data.num_nodes != num_sel:
             data._store['_num_nodes'] = num_sel

@@ -959,6 +959,109 @@ def khop_nodes(edge_index, seeds, hops, num_nodes):
     return _flags_to_index(flags, N)[0]
 
 
+SELECT_FUSED = os.environ.get('SPT_SELECT_FUSED', '1') != '0'
+
+
+def set_select_fused(on=True):
+    """Data.select on CUDA tensors: one native call per level (default) or the primitives
+    above one by one (the form the CPU host-logic tests exercise)."""
+    global SELECT_FUSED
+    SELECT_FUSED = bool(on)
+
+
+def data_select(num_nodes, idx, edge_index=None, sub=None, num_sub=None, update_sub=True,
+                super_index=None, num_super=None, update_super=True, node_rows=(),
+                edge_rows=()):
+    """One level of Data.select (reference src/data/data.py:286-470) in one native call
+    (`spt_data_select`): all the primitives of this section with a single host read, outputs
+    carved from one arena allocation.  `sub` = (pointers, points) or None; `node_rows` /
+    `edge_rows`: the attribute tensors to gather with idx / with the kept edges.
+    Returns a dict: edge_index, idx_edge, sub (pointers, points), idx_sub, sub_super,
+    super_index, idx_super, super_sub (pointers, points), node_rows, edge_rows (lists)."""
+    import ctypes
+    lib = _lib.load()
+    idx = _i64c(idx).view(-1)
+    dev = idx.device
+    K = idx.numel()
+    E = 0 if edge_index is None else int(edge_index.shape[1])
+    ei = _i64c(edge_index) if E > 0 else None
+    node_rows = [t.contiguous() for t in node_rows]
+    edge_rows = [t.contiguous() for t in edge_rows] if E > 0 else []
+    _require_cuda(idx, ei, super_index, *node_rows, *edge_rows)
+
+    def table(ts):
+        n = len(ts)
+        ptrs = (ctypes.c_void_p * max(n, 1))(*[t.data_ptr() for t in ts])
+        rbs = (ctypes.c_int64 * max(n, 1))(
+            *[(t.numel() // t.shape[0] if t.shape[0] > 0 else 0) * t.element_size() for t in ts])
+        return ptrs, rbs
+
+    nptr, nrb = table(node_rows)
+    eptr, erb = table(edge_rows)
+    a = _lib.SelectLevel()
+    a.num_nodes, a.idx, a.num_selected = int(num_nodes), _p(idx), K
+    a.edge_index, a.num_edges = _p(ei), E
+    keep = [idx, ei, nptr, nrb, eptr, erb]
+    if sub is not None:
+        sp, spts = _i64c(sub[0]), _i64c(sub[1]).view(-1)
+        _require_cuda(sp, spts)
+        keep += [sp, spts]
+        a.sub_pointers, a.sub_points, a.sub_items = _p(sp), _p(spts), spts.numel()
+        a.num_sub = spts.numel() if num_sub is None else int(num_sub)
+        a.update_sub = 1 if update_sub else 0
+    if super_index is not None:
+        si = _i64c(super_index).view(-1)
+        keep.append(si)
+        a.super_index, a.num_super = _p(si), int(num_super)
+        a.update_super = 1 if update_super else 0
+    a.num_node_rows, a.node_src, a.node_row_bytes = len(node_rows), \
+        ctypes.cast(nptr, ctypes.c_void_p), ctypes.cast(nrb, ctypes.c_void_p)
+    a.num_edge_rows, a.edge_src, a.edge_row_bytes = len(edge_rows), \
+        ctypes.cast(eptr, ctypes.c_void_p), ctypes.cast(erb, ctypes.c_void_p)
+    nb = lib.spt_data_select_arena_bytes(ctypes.addressof(a))
+    arena = torch.empty(max(nb, 256), dtype=torch.uint8, device=dev)
+    n_rows = len(node_rows) + len(edge_rows)
+    layout = (ctypes.c_int64 * (_lib.SEL_ROWS + n_rows))()
+    with torch.cuda.device(dev):
+        _lib.check(lib.spt_data_select(ctypes.addressof(a), _p(arena), nb,
+                                       ctypes.cast(layout, ctypes.c_void_p), _stream()),
+                   "spt_data_select")
+    _count(20)
+    L = list(layout)
+
+    def i64(off, n):
+        return arena[off:off + 8 * n].view(torch.int64)
+
+    def rows(off, n, like):
+        nbytes = n * (like.numel() // like.shape[0] if like.shape[0] > 0 else 0) \
+            * like.element_size()
+        return arena[off:off + nbytes].view(like.dtype).view((n,) + tuple(like.shape[1:]))
+
+    kept, items, parents = L[_lib.SEL_NUM_EDGES], L[_lib.SEL_NUM_ITEMS], L[_lib.SEL_NUM_PARENTS]
+    out = {'node_rows': [rows(L[_lib.SEL_ROWS + i], K, t) for i, t in enumerate(node_rows)],
+           'edge_rows': [rows(L[_lib.SEL_ROWS + len(node_rows) + i], kept, t)
+                         for i, t in enumerate(edge_rows)]}
+    if E > 0:
+        out['edge_index'] = i64(L[_lib.SEL_EDGE_INDEX], 2 * kept).view(2, kept)
+        out['idx_edge'] = i64(L[_lib.SEL_IDX_EDGE], kept)
+    if sub is not None:
+        out['sub'] = (i64(L[_lib.SEL_SUB_POINTERS], K + 1), i64(L[_lib.SEL_SUB_POINTS], items))
+        if update_sub:
+            out['idx_sub'] = i64(L[_lib.SEL_IDX_SUB], items)
+            out['sub_super'] = i64(L[_lib.SEL_SUB_SUPER], items)
+            if _DEBUG_INDEX:
+                distinct, bad = i64(L[_lib.SEL_SUB_COUNTS], 2).tolist()
+                if bad or distinct != items:
+                    raise IndexError("select: `sub` points are not distinct ids below num_sub")
+    if super_index is not None:
+        out['super_index'] = i64(L[_lib.SEL_SUPER_INDEX], K)
+        if update_super:
+            out['idx_super'] = i64(L[_lib.SEL_IDX_SUPER], parents)
+            out['super_sub'] = (i64(L[_lib.SEL_SUPER_SUB_POINTERS], parents + 1),
+                                i64(L[_lib.SEL_SUPER_SUB_POINTS], K))
+    return out
+
+
 def take_rows_multi(tensors, idx):
     """[t[idx] for t in tensors] in one launch (per 16 tensors): all node-level or all
     edge-level attributes of a Data object (reference src/data/data.py:420-463)."""

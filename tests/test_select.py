@@ -267,14 +267,36 @@ def test_product_select_refuses_cpu_tensors(gold):
 
 
 # ----------------------------------------------------------------------------- GPU: C-ABI kernels
+@pytest.fixture(params=['fused', 'primitives'])
+def select_path(request):
+    """Data.select through one native call per level (default) or primitive by primitive."""
+    prev = ops.SELECT_FUSED
+    ops.set_select_fused(request.param == 'fused')
+    yield request.param
+    ops.set_select_fused(prev)
+
+
 @pytest.mark.gpu
-def test_gpu_nag_select_matches_reference_vectors(gold):
+def test_gpu_nag_select_matches_reference_vectors(gold, select_path):
     check_nag_cases(gold, 'cuda')
     check_kept_attributes(gold, 'cuda')
 
 
 @pytest.mark.gpu
-def test_gpu_data_and_cluster_select_match_reference_vectors(gold):
+def test_gpu_select_rejects_bad_indices(gold, select_path):
+    nag = gold['nags']['two']
+    prod = to_product(nag['levels'], nag['start'], 'cuda')
+    for bad in ([1, 1], [0, 60], [-1, 3]):          # repeated / beyond the 60 nodes / negative
+        with pytest.raises(IndexError):
+            prod.select(0, torch.tensor(bad, device='cuda'))
+    with pytest.raises(IndexError):
+        prod.select(1, torch.tensor([9, 2], device='cuda'))     # level 1 has 9 nodes
+    ok = prod.select(0, torch.tensor([5, 3], device='cuda'))    # the context is still healthy
+    assert ok[0].num_nodes == 2
+
+
+@pytest.mark.gpu
+def test_gpu_data_and_cluster_select_match_reference_vectors(gold, select_path):
     check_data_cases(gold, 'cuda')
     for case in gold['cluster_cases']:
         nag = gold['nags'][case['nag']]
@@ -349,7 +371,7 @@ def test_gpu_primitives_edge_cases():
 
 
 @pytest.mark.gpu
-def test_gpu_nag_select_benchmark_size_vs_oracle():
+def test_gpu_nag_select_benchmark_size_vs_oracle(select_path):
     """BASELINE cfg 2 partition (100 k / 20 k / 4 k nodes, 1.6 M edges on level 1): the device
     path against the oracle at every level, plus size-independent properties."""
     from superpoint_transformer_b200.synthetic import make_nag, CONFIGS

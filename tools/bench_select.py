@@ -41,7 +41,8 @@ def main():
     levels = [level_of(nag[i]) for i in nag.level_range]
     dev = nag.cuda()
     g = torch.Generator().manual_seed(0)
-    for i_level in nag.level_range:
+    for fused, i_level in [(f, l) for f in (True, False) for l in nag.level_range]:
+        ops.set_select_fused(fused)
         n = nag[i_level].num_nodes
         idx = torch.randperm(n, generator=g)[:int(frac * n)]
         idx_d = idx.cuda()
@@ -62,7 +63,7 @@ def main():
         out_bytes = sum(level_bytes(level_of(res[i])) for i in res.level_range)
         in_bytes = sum(level_bytes(l) for l in levels)
         print(json.dumps({
-            'config': cfg, 'i_level': i_level, 'selected': int(idx.numel()), 'of': n,
+            'config': cfg, 'path': 'fused' if fused else 'primitives', 'i_level': i_level, 'selected': int(idx.numel()), 'of': n,
             'gpu_ms': round(gpu_ms, 3), 'cpu_oracle_ms': round(cpu_ms, 1),
             'cpu_threads': torch.get_num_threads(), 'speedup': round(cpu_ms / gpu_ms, 1),
             'launches': launches, 'in_MB': round(in_bytes / 1e6, 1),
