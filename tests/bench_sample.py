@@ -1,6 +1,8 @@
-"""Time `sparse_sample` (csrc/sample.cu) beside the oracle's CPU restatement of the reference
+"""(Timing script, not a test: pytest does not collect it; it lives here because only
+tests/ may import oracle/.)
+Time `sparse_sample` (csrc/sample.cu) beside the oracle's CPU restatement of the reference
 (randperm + sort): N elements in G segments, the shape of SampleSubNodes on level 0.
-    python tools/bench_sample.py [N] [G] [n_max] [n_min]
+    python tests/bench_sample.py [N] [G] [n_max] [n_min]
 Device time: CUDA events around the call (it reads one scalar back); prints one JSON line."""
 import json
 import sys

@@ -1,6 +1,8 @@
-"""Time NAG.select (csrc/select.cu) on a BASELINE-config partition against the oracle's CPU
+"""(Timing script, not a test: pytest does not collect it; it lives here because only
+tests/ may import oracle/.)
+Time NAG.select (csrc/select.cu) on a BASELINE-config partition against the oracle's CPU
 restatement of the reference algorithm (sort-based relabel), level by level:
-    python tools/bench_select.py [cfg2|cfg3|cfg5] [fraction]
+    python tests/bench_select.py [cfg2|cfg3|cfg5] [fraction]
 Wall clock around the call with a device synchronize on both sides (the call reads a few
 8-byte counters back, so it is not a pure device region).  Prints one JSON line per level."""
 import json
