@@ -17,21 +17,19 @@ class SampleSubNodes:
     draw is csrc/sample.cu (`seed`: optional fixed seed, otherwise torch's global generator)."""
 
     def __init__(self, high=1, low=0, n_max=32, n_min=16, mask=None, seed=None):
-        assert isinstance(high, int)
-        assert isinstance(low, int)
-        assert isinstance(n_max, int)
-        assert isinstance(n_min, int)
+        for name, value in (('high', high), ('low', low), ('n_max', n_max), ('n_min', n_min)):
+            assert isinstance(value, int), f'{name} must be an int'
         self.high, self.low, self.n_max, self.n_min, self.mask = high, low, n_max, n_min, mask
         self.seed = seed
 
     def __call__(self, nag):
         assert isinstance(nag, NAG)
-        if self.low == self.high:
+        if self.high == self.low:          # identity, as in the reference
             return nag
-        idx = nag.get_sampling(high=self.high, low=self.low, n_max=self.n_max,
-                               n_min=self.n_min, mask=self.mask, return_pointers=False,
-                               seed=self.seed)
-        return nag.select(self.low, idx)
+        kept = nag.get_sampling(high=self.high, low=self.low, n_max=self.n_max,
+                                n_min=self.n_min, mask=self.mask, return_pointers=False,
+                                seed=self.seed)
+        return nag.select(self.low, kept)
 
 
 class SampleSegments:
@@ -41,8 +39,8 @@ class SampleSegments:
     `torch.multinomial` without replacement on the nodes' device, as in the reference."""
 
     def __init__(self, ratio=0.2, by_size=False, by_class=False):
-        assert isinstance(ratio, list) and all(0 <= r < 1 for r in ratio) \
-               or (0 <= ratio < 1)
+        ratios = ratio if isinstance(ratio, list) else [ratio]
+        assert all(0 <= r < 1 for r in ratios), "ratios must lie in [0, 1)"
         self.ratio, self.by_size, self.by_class = ratio, by_size, by_class
 
     def weights(self, nag, i_level):
@@ -51,41 +49,46 @@ class SampleSegments:
 
     def __call__(self, nag):
         assert isinstance(nag, NAG)
-        if not isinstance(self.ratio, list):
-            ratio = [self.ratio] * (nag.end_i_level - max(0, nag.start_i_level - 1))
-        else:
-            ratio = self.ratio
-        for i_level in range(nag.end_i_level, max(0, nag.start_i_level - 1), -1):
-            if ratio[i_level - 1] <= 0:
+        lowest = max(0, nag.start_i_level - 1)
+        per_level = self.ratio if isinstance(self.ratio, list) \
+            else [self.ratio] * (nag.end_i_level - lowest)
+        for level in range(nag.end_i_level, lowest, -1):      # top level first
+            drop = per_level[level - 1]
+            if drop <= 0:
                 continue
-            num_nodes = nag[i_level].num_nodes
-            num_keep = num_nodes - int(num_nodes * ratio[i_level - 1])
-            idx = torch.multinomial(self.weights(nag, i_level), num_keep, replacement=False)
-            nag = nag.select(i_level, idx)
+            total = nag[level].num_nodes
+            keep = total - int(total * drop)
+            chosen = torch.multinomial(self.weights(nag, level), keep, replacement=False)
+            nag = nag.select(level, chosen)
         return nag
+
+
+def _uniform_draw(total, count, device):
+    """`count` of `total` positions, uniformly, without replacement — drawn like the reference
+    (torch.multinomial over unit weights), so that a torch seed fixes it the same way."""
+    return torch.multinomial(torch.ones(total, device=device), count, replacement=False)
 
 
 def _node_weights(nag, i_level, by_size, by_class):
     """Sampling weight of every node of `i_level`: uniform, plus a size term (level-0 size to
     the power 0.333) and a rare-class term (reference sampling.py:771-798 and :893-918, the
-    same expression in both places)."""
-    num_nodes = nag[i_level].num_nodes
-    weights = torch.ones(num_nodes, device=nag.device)
+    same expression in both places; the tensor ops and their order are the reference's, so
+    that the weights — and with them the seeded draw — agree to the bit)."""
+    level = nag[i_level]
+    w = torch.ones(level.num_nodes, device=nag.device)
     if by_size:
-        node_size = nag.get_sub_size(i_level, low=0)
-        size_weights = node_size ** 0.333
-        size_weights /= size_weights.sum()
-        weights += size_weights
-    if by_class and nag[i_level].y is not None:
-        counts = nag[i_level].y.sum(dim=0).sqrt()
-        scores = 1 / (counts + 1)
-        scores /= scores.sum()
-        mask = nag[i_level].y.gt(0)
-        class_weights = (mask * scores.view(1, -1)).max(dim=1).values
-        class_weights /= class_weights.sum()
-        weights += class_weights.squeeze()
-    weights /= weights.sum()
-    return weights
+        size_term = nag.get_sub_size(i_level, low=0) ** 0.333
+        size_term /= size_term.sum()
+        w += size_term
+    y = level.y
+    if by_class and y is not None:
+        rarity = 1 / (y.sum(dim=0).sqrt() + 1)
+        rarity /= rarity.sum()
+        class_term = (y.gt(0) * rarity.view(1, -1)).max(dim=1).values
+        class_term /= class_term.sum()
+        w += class_term.squeeze()
+    w /= w.sum()
+    return w
 
 
 def _take_edges(data, idx):
@@ -149,14 +152,10 @@ class RestrictSize:
         self.num_nodes, self.num_edges = num_nodes, num_edges
 
     def __call__(self, data):
-        if data.num_nodes > self.num_nodes and self.num_nodes > 0:
-            weights = torch.ones(data.num_nodes, device=data.device)
-            idx = torch.multinomial(weights, self.num_nodes, replacement=False)
-            data = data.select(idx)[0]
-        if data.num_edges > self.num_edges and self.num_edges > 0:
-            weights = torch.ones(data.num_edges, device=data.device)
-            idx = torch.multinomial(weights, self.num_edges, replacement=False)
-            _take_edges(data, idx)
+        if 0 < self.num_nodes < data.num_nodes:
+            data = data.select(_uniform_draw(data.num_nodes, self.num_nodes, data.device))[0]
+        if 0 < self.num_edges < data.num_edges:
+            _take_edges(data, _uniform_draw(data.num_edges, self.num_edges, data.device))
         return data
 
 
@@ -185,14 +184,12 @@ class NAGRestrictSize:
 
     @staticmethod
     def _restrict_level(nag, i_level, num_nodes, num_edges):
-        if nag[i_level].num_nodes > num_nodes and num_nodes > 0:
-            weights = torch.ones(nag[i_level].num_nodes, device=nag.device)
-            idx = torch.multinomial(weights, num_nodes, replacement=False)
-            nag = nag.select(i_level, idx)
-        if nag[i_level].num_edges > num_edges and num_edges > 0:
-            weights = torch.ones(nag[i_level].num_edges, device=nag.device)
-            idx = torch.multinomial(weights, num_edges, replacement=False)
-            _take_edges(nag[i_level], idx)
+        if 0 < num_nodes < nag[i_level].num_nodes:
+            nag = nag.select(i_level, _uniform_draw(nag[i_level].num_nodes, num_nodes,
+                                                    nag.device))
+        level = nag[i_level]
+        if 0 < num_edges < level.num_edges:
+            _take_edges(level, _uniform_draw(level.num_edges, num_edges, nag.device))
         return nag
 
 
@@ -214,46 +211,38 @@ class _BaseSampleSubgraphs:
         batch = nag[i_level].batch
         if batch is None or not self.use_batch:
             return torch.multinomial(weights, k, replacement=False)
-        idx_list = []
-        batch_indices = batch.unique()
-        num_batch = batch_indices.numel()
-        batch_indices = batch_indices[torch.randperm(num_batch)]
-        num_sampled = 0
-        k_batch = max(k // num_batch, 1)
-        for i_step, i_batch in enumerate(batch_indices):
-            if i_step >= num_batch - 1:
-                k_batch = k - num_sampled
-            mask = torch.where(i_batch == batch)[0]
-            idx_ = torch.multinomial(weights[mask], k_batch, replacement=False)
-            idx_list.append(mask[idx_])
-            num_sampled += k_batch
-            if num_sampled >= k:
+        # spread the seeds over the batch items, visited in random order: an equal share each
+        # (at least one), the last item visited takes what is left
+        items = batch.unique()
+        items = items[torch.randperm(items.numel())]
+        share, taken, picked = max(k // items.numel(), 1), 0, []
+        for step, item in enumerate(items):
+            take = k - taken if step >= items.numel() - 1 else share
+            members = torch.where(item == batch)[0]
+            picked.append(members[torch.multinomial(weights[members], take,
+                                                    replacement=False)])
+            taken += take
+            if taken >= k:
                 break
-        return torch.cat(idx_list)
+        return torch.cat(picked)
 
     def __call__(self, nag):
         assert isinstance(nag, NAG)
-        if self.i_level is None or self.k <= 0:
+        if self.k <= 0 or self.i_level is None:
             return nag
-        if self.i_level == -1:
-            i_level = nag.end_i_level
-        elif nag.start_i_level <= self.i_level < nag.absolute_num_levels:
-            i_level = self.i_level
-        else:
+        i_level = nag.end_i_level if self.i_level == -1 else self.i_level
+        if not nag.start_i_level <= i_level < nag.absolute_num_levels:
             raise ValueError(
                 f"Invalid i_level: {self.i_level}. Must be in range [{nag.start_i_level}, "
                 f"{nag.absolute_num_levels - 1}],\nor -1 for the highest level available.")
-        idx_seed = self.seeds(nag, i_level)
-        if self.disjoint:
-            idx_subgraphs = [self._sample_subgraphs_from_seeds(nag, i_level, i.view(1))
-                             for i in idx_seed]
-            if all(idx is None for idx in idx_subgraphs):
-                idx_subgraphs = None
-        else:
-            idx_subgraphs = self._sample_subgraphs_from_seeds(nag, i_level, idx_seed)
-        if isinstance(idx_subgraphs, list):
-            return NAGBatch.from_nag_list([nag.select(i_level, idx) for idx in idx_subgraphs])
-        return nag.select(i_level, idx_subgraphs)
+        seeds = self.seeds(nag, i_level)
+        if not self.disjoint:
+            return nag.select(i_level, self._sample_subgraphs_from_seeds(nag, i_level, seeds))
+        # one node set, hence one NAG, per seed
+        node_sets = [self._sample_subgraphs_from_seeds(nag, i_level, s.view(1)) for s in seeds]
+        if all(ns is None for ns in node_sets):
+            return nag.select(i_level, None)
+        return NAGBatch.from_nag_list([nag.select(i_level, ns) for ns in node_sets])
 
     def _sample_subgraphs_from_seeds(self, nag, i_level, idx_seed):
         raise NotImplementedError
