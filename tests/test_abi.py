@@ -70,3 +70,26 @@ def test_product_never_imports_the_oracle():
             if f.endswith('.py'):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), f
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors of the header's structs have the C compiler's size and field offsets
+    (gcc on include/spt_b200.h: the header is plain C)."""
+    import ctypes
+    from superpoint_transformer_b200 import _lib
+    fields = [name for name, _ in _lib.SelectLevel._fields_]
+    src = tmp_path / 'layout.c'
+    src.write_text(
+        '#include <stdio.h>\n#include "spt_b200.h"\nint main(void) {\n'
+        '  printf("%zu\\n", sizeof(spt_select_level));\n' +
+        ''.join(f'  printf("%zu\\n", offsetof(spt_select_level, {f}));\n' for f in fields) +
+        '  printf("%d\\n", (int)SPT_SEL_ROWS);\n  return 0;\n}\n')
+    exe = tmp_path / 'layout'
+    cc = subprocess.run(['gcc', '-std=c99', '-I', os.path.join(ROOT, 'include'), str(src), '-o',
+                         str(exe)], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    out = [int(v) for v in subprocess.run([str(exe)], capture_output=True,
+                                          text=True).stdout.split()]
+    assert out[0] == ctypes.sizeof(_lib.SelectLevel)
+    assert out[1:-1] == [getattr(_lib.SelectLevel, f).offset for f in fields]
+    assert out[-1] == _lib.SEL_ROWS
