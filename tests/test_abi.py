@@ -77,19 +77,23 @@ def test_struct_layouts_match_the_header(tmp_path):
     (gcc on include/spt_b200.h: the header is plain C)."""
     import ctypes
     from superpoint_transformer_b200 import _lib
-    fields = [name for name, _ in _lib.SelectLevel._fields_]
+    structs = {'spt_select_level': _lib.SelectLevel, 'spt_attn_extras': _lib.AttnExtras}
+    lines = []
+    for cname, cls in structs.items():
+        lines.append(f'  printf("%zu\\n", sizeof({cname}));\n')
+        lines += [f'  printf("%zu\\n", offsetof({cname}, {f}));\n' for f, _ in cls._fields_]
     src = tmp_path / 'layout.c'
-    src.write_text(
-        '#include <stdio.h>\n#include "spt_b200.h"\nint main(void) {\n'
-        '  printf("%zu\\n", sizeof(spt_select_level));\n' +
-        ''.join(f'  printf("%zu\\n", offsetof(spt_select_level, {f}));\n' for f in fields) +
-        '  printf("%d\\n", (int)SPT_SEL_ROWS);\n  return 0;\n}\n')
+    src.write_text('#include <stdio.h>\n#include "spt_b200.h"\nint main(void) {\n' +
+                   ''.join(lines) + '  printf("%d\\n", (int)SPT_SEL_ROWS);\n  return 0;\n}\n')
     exe = tmp_path / 'layout'
     cc = subprocess.run(['gcc', '-std=c99', '-I', os.path.join(ROOT, 'include'), str(src), '-o',
                          str(exe)], capture_output=True, text=True)
     assert cc.returncode == 0, cc.stderr
     out = [int(v) for v in subprocess.run([str(exe)], capture_output=True,
                                           text=True).stdout.split()]
-    assert out[0] == ctypes.sizeof(_lib.SelectLevel)
-    assert out[1:-1] == [getattr(_lib.SelectLevel, f).offset for f in fields]
-    assert out[-1] == _lib.SEL_ROWS
+    for cname, cls in structs.items():
+        n = len(cls._fields_)
+        assert out[0] == ctypes.sizeof(cls), cname
+        assert out[1:n + 1] == [getattr(cls, f).offset for f, _ in cls._fields_], cname
+        out = out[n + 1:]
+    assert out == [_lib.SEL_ROWS]
