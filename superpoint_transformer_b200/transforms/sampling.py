@@ -80,8 +80,8 @@ def _node_weights(nag, i_level, by_size, by_class):
         size_term = nag.get_sub_size(i_level, low=0) ** 0.333
         size_term /= size_term.sum()
         w += size_term
-    y = level.y
-    if by_class and y is not None:
+    y = level['y'] if by_class else None          # (absent -> None, like the reference's Data.y)
+    if y is not None:
         rarity = 1 / (y.sum(dim=0).sqrt() + 1)
         rarity /= rarity.sum()
         class_term = (y.gt(0) * rarity.view(1, -1)).max(dim=1).values

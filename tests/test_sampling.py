@@ -218,6 +218,25 @@ def test_reference_loader_regenerates_sampling_vectors(gold, nags):
     assert torch.equal(ptr, case['ptr_samples'])
 
 
+def test_sampling_without_label_histograms(nags, oracle_primitives):
+    """Levels without `y` (the synthetic benchmark partitions): by_class has nothing to use and
+    the weights stay uniform (+ size term), as with the reference's `Data.y is None`."""
+    spec = nags['full4']
+    levels = [{k: v for k, v in lv.items() if k != 'y'} for lv in spec['levels']]
+    nag = to_product(levels, spec['start'])
+    for by_class in (False, True):
+        t = SampleSegments(0.25, by_size=True, by_class=by_class)
+        want = OS.segment_weights(None, nag.get_sub_size(2, low=0), True, by_class)
+        assert torch.equal(t.weights(nag, 2), want)
+        torch.manual_seed(0)
+        out = t(nag)
+        assert out[3].num_nodes == 3 and 'y' not in out[1]
+        torch.manual_seed(0)
+        sub = SampleRadiusSubgraphs(r=0.3, i_level=1, k=2, by_class=by_class,
+                                    disjoint=False)(nag)
+        assert 0 < sub[1].num_nodes <= nag[1].num_nodes
+
+
 def test_segment_weights_match_oracle(nags, oracle_primitives):
     spec = nags['full4']
     nag = to_product(spec['levels'], spec['start'])
@@ -363,10 +382,9 @@ def test_gpu_sparse_sample_is_uniform_long_segments():
     assert abs(both - want) < 6 * (want / (G * (size - 1))) ** 0.5 + 1e-4
 
 
-@pytest.mark.gpu
-def test_gpu_sample_sub_nodes_and_segments_on_benchmark_partition():
-    from superpoint_transformer_b200.synthetic import make_nag, CONFIGS
-    nag = make_nag(**CONFIGS['cfg2']).cuda()
+def check_synthetic_partition(nag):
+    """SampleSubNodes / SampleSegments on a partition of the synthetic generator (levels 1-3, no
+    label histograms, level-1 `node_size`)."""
     sizes = torch.bincount(nag[1].super_index, minlength=nag[2].num_nodes)
     out = SampleSubNodes(high=2, low=1, n_max=4, n_min=2, seed=5)(nag)
     want = OS.sampling_counts(sizes.cpu(), 4, 2)
@@ -386,3 +404,16 @@ def test_gpu_sample_sub_nodes_and_segments_on_benchmark_partition():
         assert int(res[i].super_index.max()) + 1 == res[i + 1].num_nodes
         assert torch.equal(res[i + 1].sub.to_super_index(), res[i].super_index)
     assert res[2].num_nodes <= nag[2].num_nodes - int(nag[2].num_nodes * 0.5)
+
+
+@pytest.mark.gpu
+def test_gpu_sample_sub_nodes_and_segments_on_benchmark_partition():
+    from superpoint_transformer_b200.synthetic import make_nag, CONFIGS
+    check_synthetic_partition(make_nag(**CONFIGS['cfg2']).cuda())
+
+
+def test_host_logic_sample_sub_nodes_and_segments_on_synthetic_partition(oracle_primitives):
+    """The same checks on CPU tensors (device primitives stood in by the oracle): what the GPU
+    test exercises above the kernels."""
+    from superpoint_transformer_b200.synthetic import make_nag
+    check_synthetic_partition(make_nag([6000, 1200, 240], mean_degree=8, seed=4))
