@@ -17,7 +17,9 @@
  *     Where scratch is needed the caller passes `ws` of at least
  *     `*_workspace_bytes(...)` bytes (256-byte aligned).
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
- *     no host synchronisation, no internal streams.
+ *     no host synchronisation, no internal streams.  One exception, stated at its
+ *     declaration: spt_data_select reads a 48-byte counter vector back in the middle
+ *     of the call (output sizes that depend on the data).
  *   - return value: 0 = ok; negative = invalid argument / unsupported shape
  *     (SPT_E_*); positive = cudaError_t of the failed launch.  Details via
  *     spt_last_error() (thread-local, host string).
