@@ -55,6 +55,17 @@ def test_oracle_sparse_sample_counts_match_reference(gold):
         check_draw(case, samples, ptr)
 
 
+def test_product_sampling_counts_match_reference(gold):
+    """ops.sampling_counts (the fp32 tanh heuristic, plain tensor ops) gives the reference's
+    number of samples per segment on the unmasked cases."""
+    for case in gold['sparse']:
+        if case['mask'] is not None:
+            continue
+        size = case['idx'].bincount()
+        n = ops.sampling_counts(size, case['n_max'], case['n_min'])
+        assert torch.equal(n, case['ptr_samples'][1:] - case['ptr_samples'][:-1])
+
+
 def test_host_logic_sample_segments_matches_reference(gold, nags, oracle_primitives):
     """Same torch seed, CPU tensors, device primitives stood in by the oracle: the weights must
     be the reference's to the bit for torch.multinomial to keep the same nodes."""

@@ -259,6 +259,34 @@ def test_select_identity_and_errors(gold, oracle_primitives):
         prod.select(5, torch.tensor([0]))
 
 
+def test_index_helpers_follow_the_reference():
+    """tensor_idx / is_arange / sizes_to_pointers / indices_to_pointers against the oracle's
+    restatement and, in the build container, the reference's own functions."""
+    from superpoint_transformer_b200.utils import (tensor_idx, is_arange, sizes_to_pointers,
+                                                   indices_to_pointers)
+    mask = torch.tensor([True, False, True, True])
+    cases = [3, slice(2, 6), np.array([4, 1]), mask, torch.tensor([5, 0, 2], dtype=torch.int32),
+             None]
+    refs = [O.tensor_idx]
+    from oracle import reference_data as R
+    if R.available():
+        import importlib.util
+        ns = R.load_data()
+        refs.append(ns.NAG.select.__globals__['tensor_idx'])
+    for ref in refs:
+        for c in cases:
+            a, b = tensor_idx(c), ref(c)
+            assert (a is None and b is None) or (a.dtype == torch.int64 and torch.equal(a, b))
+    with pytest.raises(ValueError):
+        tensor_idx([1, 2])
+    assert is_arange(torch.arange(5), 5) and not is_arange(torch.arange(5), 6)
+    assert not is_arange(torch.tensor([0, 2, 1]), 3) and is_arange(torch.arange(0), 0)
+    sizes = torch.tensor([2, 0, 3])
+    assert sizes_to_pointers(sizes).tolist() == [0, 2, 2, 5]
+    ptr, order = indices_to_pointers(torch.tensor([2, 0, 2, 1, 0]))
+    assert ptr.tolist() == [0, 2, 3, 5] and order.tolist() == [1, 4, 3, 0, 2]
+
+
 def test_product_select_refuses_cpu_tensors(gold):
     """No CPU path in the product: the device primitives insist on CUDA tensors."""
     nag = gold['nags']['two']
