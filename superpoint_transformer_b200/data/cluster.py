@@ -149,6 +149,14 @@ class Cluster(CSRData):
         return Cluster(pointers, new_points), (idx_sub, sub_super)
 
     @classmethod
+    def load(cls, f, non_fp_to_long=False, **kwargs):
+        """From a `_cluster_/<key>` group written by the reference's `Cluster.save` (reference
+        src/data/csr.py:495-575); returns cluster, (None, None) like the reference's
+        no-indexing branch (src/data/cluster.py:204-219)."""
+        from ..io import load_cluster
+        return load_cluster(f, non_fp_to_long=non_fp_to_long), (None, None)
+
+    @classmethod
     def from_super_index(cls, super_index, num_super):
         """CSR of `super_index` (int64 pointers/points like the reference).  CUDA
         tensors go through libspt_b200's stable grouping kernel; CPU tensors (data

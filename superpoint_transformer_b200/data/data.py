@@ -207,6 +207,15 @@ class Data:
         out._store.update(self._store)
         return out
 
+    @classmethod
+    def load(cls, f, keys=None, non_fp_to_long=False, rgb_to_float=False, **kwargs):
+        """One level from a file / group written by the reference's `Data.save` (reference
+        src/data/data.py:736-940); see io/nag_io.py."""
+        from ..io import load_data, H5File
+        if isinstance(f, str):
+            f = H5File(f)
+        return load_data(f, keys=keys, non_fp_to_long=non_fp_to_long, rgb_to_float=rgb_to_float)
+
     def select(self, idx, update_sub=True, update_super=True, _num_super=None,
                _skip_sub=False, _skip_super=False):
         """Nodes `idx` (duplicate-free) of this level, with edges re-indexed and restricted to

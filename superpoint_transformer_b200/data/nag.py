@@ -196,6 +196,16 @@ class NAG:
             idx = self[i].super_index[idx]
         return idx
 
+    @classmethod
+    def load(cls, path, low=0, high=-1, idx=None, keys_low=None, keys=None,
+             non_fp_to_long=False, rgb_to_float=False, **kwargs):
+        """Read levels `low`..`high` of a file written by the reference's `NAG.save` (reference
+        src/data/nag.py:436-570); see io/nag_io.py.  CPU tensors; integers stay in their
+        stored (smallest) dtype unless `non_fp_to_long`."""
+        from ..io import load_nag
+        return load_nag(path, low=low, high=high, idx=idx, keys_low=keys_low, keys=keys,
+                        non_fp_to_long=non_fp_to_long, rgb_to_float=rgb_to_float)
+
     def get_sampling(self, high=1, low=0, n_max=32, n_min=1, mask=None,
                      return_pointers=False, seed=None):
         """Indices sampling `low`-level elements by the `high`-level segment they belong to:

@@ -1,0 +1,2 @@
+from .h5lite import *  # noqa: F401,F403
+from .nag_io import *  # noqa: F401,F403
