@@ -216,6 +216,14 @@ class Data:
             f = H5File(f)
         return load_data(f, keys=keys, non_fp_to_long=non_fp_to_long, rgb_to_float=rgb_to_float)
 
+    def save(self, path, y_to_csr=True, pos_dtype=torch.float, fp_dtype=torch.float,
+             rgb_to_byte=True):
+        """This level alone as a file of the reference's format (reference
+        src/data/data.py:663-734: datasets at the root of the file)."""
+        from ..io import data_to_tree, write_h5
+        write_h5(path, data_to_tree(self, y_to_csr=y_to_csr, pos_dtype=pos_dtype,
+                                    fp_dtype=fp_dtype, rgb_to_byte=rgb_to_byte))
+
     def select(self, idx, update_sub=True, update_super=True, _num_super=None,
                _skip_sub=False, _skip_super=False):
         """Nodes `idx` (duplicate-free) of this level, with edges re-indexed and restricted to

@@ -206,6 +206,14 @@ class NAG:
         return load_nag(path, low=low, high=high, idx=idx, keys_low=keys_low, keys=keys,
                         non_fp_to_long=non_fp_to_long, rgb_to_float=rgb_to_float)
 
+    def save(self, path, y_to_csr=True, pos_dtype=torch.float, fp_dtype=torch.float,
+             rgb_to_byte=True):
+        """Write the file format of the reference's `NAG.save` (reference
+        src/data/nag.py:401-434; uncompressed HDF5, see io/h5write.py)."""
+        from ..io import save_nag
+        save_nag(self, path, y_to_csr=y_to_csr, pos_dtype=pos_dtype, fp_dtype=fp_dtype,
+                 rgb_to_byte=rgb_to_byte)
+
     def get_sampling(self, high=1, low=0, n_max=32, n_min=1, mask=None,
                      return_pointers=False, seed=None):
         """Indices sampling `low`-level elements by the `high`-level segment they belong to:

@@ -14,11 +14,13 @@ not offered: load, then `NAG.select` on the device."""
 import torch
 
 from .h5lite import H5File, H5Group
+from .h5write import write_h5
 from ..data.cluster import Cluster
 from ..data.data import Data
 from ..data.nag import NAG
 
-__all__ = ['load_tensor', 'load_csr_to_dense', 'load_cluster', 'load_data', 'load_nag']
+__all__ = ['load_tensor', 'load_csr_to_dense', 'load_cluster', 'load_data', 'load_nag',
+           'save_nag', 'data_to_tree', 'cluster_to_tree']
 
 LEVEL_PREFIX = 'level_'              # NAG._data_serialization_prefix
 START_KEY = 'start_i_level'          # NAG._start_i_level_serialization_key
@@ -119,3 +121,79 @@ def load_nag(path, low=0, high=-1, idx=None, keys_low=None, keys=None, non_fp_to
             levels.append(load_data(f[f'{LEVEL_PREFIX}{i}'], keys=keys_low if i == low else keys,
                                     non_fp_to_long=non_fp_to_long, rgb_to_float=rgb_to_float))
     return NAG(levels, start_i_level=low)
+
+
+# ------------------------------------------------------------------------------------- save
+def _smallest_int(a):
+    """reference src/utils/tensor.py:223-242: the smallest of uint8 / int16 / int32 / int64 that
+    holds the values."""
+    if a.numel() == 0:
+        return a.byte()
+    lo, hi = int(a.min()), int(a.max())
+    for dtype in (torch.uint8, torch.int16, torch.int32, torch.int64):
+        info = torch.iinfo(dtype)
+        if info.min <= lo and hi <= info.max:
+            return a.to(dtype)
+    raise ValueError(f"Could not cast dtype={a.dtype} to integer.")
+
+
+def _array(x, fp_dtype=torch.float):
+    """`cast_numpyfy` (reference src/utils/tensor.py:268-285): floats to `fp_dtype`, integers to
+    the smallest integer dtype."""
+    x = x.detach().cpu()
+    return (x.to(fp_dtype) if x.is_floating_point() else _smallest_int(x)).contiguous().numpy()
+
+
+def cluster_to_tree(cluster, fp_dtype=torch.float):
+    """`CSRData.save` (reference src/data/csr.py:456-493) of a Cluster."""
+    return {'pointers': _array(cluster.pointers, fp_dtype),
+            'is_index_value': _array(torch.tensor([True]), fp_dtype),
+            'value_0': _array(cluster.points, fp_dtype)}
+
+
+def data_to_tree(data, y_to_csr=True, pos_dtype=torch.float, fp_dtype=torch.float,
+                 rgb_to_byte=True):
+    """`Data.save` (reference src/data/data.py:663-734): the datasets and sub-groups of one
+    level as a nested dict."""
+    tree, num_nodes, not_indexable = {}, data.num_nodes, []
+    for k in data.keys:
+        if k.startswith('_'):
+            continue
+        val = data[k]
+        node_level = torch.is_tensor(val) and val.dim() > 0 and val.shape[0] == num_nodes
+        if not node_level or k in ('edge_index', 'edge_attr'):
+            not_indexable.append(k)
+        if k == 'pos_offset':
+            tree[k] = _array(val, torch.double)
+        elif k == 'pos':
+            tree[k] = _array(val, pos_dtype)
+        elif k == 'y' and val.dim() > 1 and y_to_csr:       # save_dense_to_csr, io.py:168-203
+            rows, columns = val.nonzero(as_tuple=True)
+            pointers = torch.zeros(val.shape[0] + 1, dtype=torch.long)
+            pointers[1:] = torch.bincount(rows, minlength=val.shape[0]).cumsum(0)
+            tree.setdefault('_csr_', {})[k] = {
+                'pointers': _array(pointers, fp_dtype), 'columns': _array(columns, fp_dtype),
+                'values': _array(val[rows, columns], fp_dtype),
+                'shape': torch.tensor(val.shape).numpy()}
+        elif k in ('rgb', 'mean_rgb') and rgb_to_byte:
+            tree[k] = _array((val * 255).byte() if val.is_floating_point() else val.byte(),
+                             fp_dtype)
+        elif isinstance(val, Cluster):
+            tree.setdefault('_cluster_', {})[k] = cluster_to_tree(val, fp_dtype)
+        elif torch.is_tensor(val):
+            tree[k] = _array(val, fp_dtype)
+        else:
+            raise NotImplementedError(
+                f"Cannot save attribute {k} with unsupported type {type(val)}")
+    tree['_not_indexable_'] = not_indexable
+    return tree
+
+
+def save_nag(nag, path, y_to_csr=True, pos_dtype=torch.float, fp_dtype=torch.float,
+             rgb_to_byte=True):
+    """`NAG.save` (reference src/data/nag.py:401-434): one `level_<i>` group per level, the
+    start level as a root attribute."""
+    tree = {f'{LEVEL_PREFIX}{i}': data_to_tree(nag[i], y_to_csr=y_to_csr, pos_dtype=pos_dtype,
+                                              fp_dtype=fp_dtype, rgb_to_byte=rgb_to_byte)
+            for i in nag.level_range}
+    write_h5(path, tree, {START_KEY: nag.start_i_level})

@@ -86,6 +86,83 @@ def test_reader_and_loaders_reproduce_the_fixture():
     assert level.num_nodes == 166 and isinstance(level.sub, Cluster)
 
 
+def test_save_load_round_trip(demo, tmp_path):
+    """NAG.save -> NAG.load on the real partition, a nano partition and a synthetic one: every
+    tensor comes back (integers through their smallest dtype, `y` through CSR, `sub` through
+    `_cluster_`), for the fp32 default and for fp16 features."""
+    from superpoint_transformer_b200.io import H5File
+    from superpoint_transformer_b200.synthetic import make_nag
+    nano = NAG(to_product(demo['levels'], 0)._list[1:], start_i_level=1)
+    cases = {'demo': to_product(demo['levels'], 0), 'nano': nano,
+             'synthetic': make_nag([500, 100, 20], mean_degree=6, seed=1)}
+    for name, nag in cases.items():
+        path = str(tmp_path / f'{name}.h5')
+        nag.save(path)
+        back = NAG.load(path, low=nag.start_i_level, non_fp_to_long=True)
+        assert back.start_i_level == nag.start_i_level and back.num_points == nag.num_points
+        for a, b in zip(levels_of(back), levels_of(nag)):
+            b = {k: (v if isinstance(v, dict) or v.is_floating_point() or k == 'rgb'
+                     else v.long()) for k, v in b.items()}
+            assert_level_equal(a, b, name)
+        with H5File(path) as f:
+            lvl = f[f'level_{nag.start_i_level + 1}']
+            assert sorted(lvl['_not_indexable_'].read()) == ['edge_attr', 'edge_index', 'sub']
+            assert int(f.attrs['start_i_level']) == nag.start_i_level
+            stored = lvl['super_index'].dtype
+            assert stored.itemsize < 8                       # smallest integer dtype on disk
+    half = str(tmp_path / 'half.h5')
+    cases['demo'].save(half, fp_dtype=torch.float16)
+    back = NAG.load(half)
+    assert back[1].edge_attr.dtype == torch.float16 and back[1].pos.dtype == torch.float32
+    assert torch.equal(back[1].edge_attr, cases['demo'][1].edge_attr.half())
+    one = str(tmp_path / 'level.h5')
+    cases['demo'][2].save(one)
+    level = Data.load(one, non_fp_to_long=True)
+    assert level.num_nodes == 501 and torch.equal(level.sub.points, cases['demo'][2].sub.points)
+
+
+def test_written_file_has_the_reference_files_structure(tmp_path):
+    """In the build container: saving the loaded demo partition gives the reference file's own
+    inventory (names, shapes, stored dtypes) and the same header messages byte for byte."""
+    if not os.path.isfile(DEMO_H5):
+        pytest.skip('reference demo file not mounted')
+    from superpoint_transformer_b200.io import H5File
+    out = str(tmp_path / 'again.h5')
+    NAG.load(DEMO_H5).save(out)
+
+    def inventory(g, path=''):
+        items = {}
+        for k in g.keys():
+            o = g[k]
+            if hasattr(o, 'keys'):
+                items.update(inventory(o, f'{path}/{k}'))
+            else:
+                items[f'{path}/{k}'] = (o.shape, str(o.dtype))
+        return items
+
+    ref, mine = H5File(DEMO_H5), H5File(out)
+    assert inventory(ref) == inventory(mine) and len(inventory(mine)) == 63
+    assert ref._r.buf[8:24] == mine._r.buf[8:24]                    # superblock parameters
+
+    def header_messages(f, key):
+        r = f._r
+        group, name = key.rsplit('/', 1)
+        addr = f[group]._links[name]
+        out = []
+        for mtype, size, body in r.messages(addr):
+            if mtype in (0x01, 0x03, 0x05):                        # dataspace, datatype, fill
+                out.append((mtype, bytes(r.buf[body:body + size])))
+            elif mtype == 0x08:                                    # layout: class + size
+                out.append((mtype, bytes(r.buf[body:body + 2]) + bytes(r.buf[body + 10:body + 18])))
+        return out
+
+    for key in ('level_1/pos', 'level_1/super_index', 'level_0/rgb', 'level_2/_not_indexable_',
+                'level_3/_cluster_/sub/pointers', 'level_0/_csr_/y/shape'):
+        assert header_messages(ref, key) == header_messages(mine, key), key
+    for key in ('level_1/edge_attr', 'level_2/_csr_/y/values', 'level_3/_cluster_/sub/value_0'):
+        assert (ref[key].read() == mine[key].read()).all()
+
+
 def test_reader_rejects_what_it_does_not_parse(tmp_path):
     from superpoint_transformer_b200.io import H5File
     bad = tmp_path / 'not.h5'
